@@ -1,0 +1,890 @@
+/*
+ * cmib_api.cu — implementation of the C ABI declared in include/cmib.h.
+ *
+ * Host side is thin: it owns device buffers, builds the tabulated spectra on the
+ * host (spectrum_tables.hpp), and launches the kernels of kernels.cuh on the
+ * context's stream.  There is no CPU compute path: every entry point that does
+ * work requires a CUDA device and fails loudly otherwise.
+ */
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/cmib.h"
+#include "kernels.cuh"
+#include "spectrum_tables.hpp"
+
+using namespace cmib;
+
+namespace {
+
+thread_local std::string g_last_error;
+int g_abort_on_error = -1; /* -1: read CMIB_ABORT_ON_ERROR lazily */
+uint64_t g_launches = 0;
+
+int fail(const char *file, const char *func, int line, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  char full[1200];
+  /* same shape as the reference's cmac_error (src/Error.hpp:101-106) */
+  snprintf(full, sizeof(full), "%s:%s():%d: Error: %s", file, func, line, buf);
+  g_last_error = full;
+  if (g_abort_on_error < 0) {
+    const char *e = getenv("CMIB_ABORT_ON_ERROR");
+    g_abort_on_error = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (g_abort_on_error) {
+    fprintf(stderr, "%s\n", full);
+    abort();
+  }
+  return 1;
+}
+#define CMIB_FAIL(...) return fail(__FILE__, __func__, __LINE__, __VA_ARGS__)
+#define CUDA_OK(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (expr);                                                            \
+    if (e_ != cudaSuccess) CMIB_FAIL("%s failed: %s", #expr, cudaGetErrorString(e_));   \
+  } while (0)
+#define CHECK_CTX(ctx)                                                                  \
+  do {                                                                                  \
+    if (!(ctx)) CMIB_FAIL("null context");                                              \
+    CUDA_OK(cudaSetDevice((ctx)->device));                                              \
+  } while (0)
+
+template <typename T> struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaError_t resize(size_t count) {
+    if (count == n) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const T *h, size_t count, cudaStream_t s) {
+    cudaError_t e = resize(count);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+} // namespace
+
+struct cmib_context {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  GridGeom geom;
+  /* grid state */
+  DevBuf<CellOpacity> cells;
+  DevBuf<double> xmetal, heat_norm, cr_factor, reemit_prob, acc;
+  bool have_cr_factor = false;
+  bool reemit_prob_valid = false;
+  /* staging for SoA <-> device layout conversion */
+  DevBuf<double> stage;
+  /* plugins */
+  double abund[NUM_ELEMENTS] = {0., 0., 0., 0., 0., 0.};
+  SourceModel src;
+  RecombinationModel rr;
+  TemperatureParams tp;
+  double luminosity = 0.;
+  DevBuf<double> d_src_pos, d_src_cum, d_planck, d_hlyc_freq, d_hlyc_temp, d_hlyc_cdf, d_helyc_freq,
+      d_helyc_temp, d_helyc_cdf, d_he2pc_freq, d_he2pc_cdf;
+  std::vector<double> h_planck, h_hlyc_freq, h_hlyc_temp, h_hlyc_cdf, h_helyc_freq, h_helyc_temp,
+      h_helyc_cdf, h_he2pc_freq, h_he2pc_cdf;
+  int acc_mode = ACC_FULL;
+  bool force_full = false;
+  double nu_H = 0., nu_He = 0.;
+
+  int pick_acc_mode() const {
+    if (force_full) return ACC_FULL;
+    if (src.xs_kind != XS_FIXED) return ACC_FULL;
+    for (int k = 1; k < NUM_IONS; ++k)
+      if (src.xs_fixed[k] != 0.) return ACC_FULL;
+    return ACC_HONLY;
+  }
+  size_t acc_doubles(int mode) const {
+    return ACC_COUNTERS + (size_t)geom.ncells * (mode == ACC_HONLY ? 2 : 16);
+  }
+};
+
+namespace {
+
+/* the accumulator layout follows the cross-section model; switching layouts
+ * discards the current sums (they are per-iteration scratch anyway) */
+int ensure_acc(cmib_context *ctx) {
+  const int mode = ctx->pick_acc_mode();
+  const size_t want = ctx->acc_doubles(mode);
+  if (mode != ctx->acc_mode || ctx->acc.n != want) {
+    ctx->acc_mode = mode;
+    CUDA_OK(ctx->acc.resize(want));
+    CUDA_OK(cudaMemsetAsync(ctx->acc.p, 0, want * sizeof(double), ctx->stream));
+  }
+  return 0;
+}
+
+/* UnitConverter::to_SI<QUANTITY_FREQUENCY>(x, "eV") (UnitConverter.hpp:259-275):
+ * value * eV, then times (1/h) */
+double ev_to_hz(double ev) { return (ev * ELECTRONVOLT) * (1. / PLANCK); }
+
+} // namespace
+
+/* scratch device buffers of the test hooks */
+namespace {
+struct Scratch {
+  std::vector<void *> ptrs;
+  ~Scratch() {
+    for (void *p : ptrs) cudaFree(p);
+  }
+  template <typename T> cudaError_t in(T **d, const T *h, size_t n, cudaStream_t s) {
+    *d = nullptr;
+    if (!h || n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)d, n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(*d);
+    return cudaMemcpyAsync(*d, h, n * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  template <typename T> cudaError_t out(T **d, size_t n) {
+    *d = nullptr;
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void **)d, n * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(*d);
+    return e;
+  }
+  template <typename T> cudaError_t back(T *h, const T *d, size_t n, cudaStream_t s) {
+    if (!h || !d || n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s);
+  }
+};
+} // namespace
+
+extern "C" {
+
+int cmib_abi_version(void) { return CMIB_ABI_VERSION; }
+const char *cmib_last_error(void) { return g_last_error.c_str(); }
+void cmib_set_abort_on_error(int on) { g_abort_on_error = on ? 1 : 0; }
+uint64_t cmib_kernel_launch_count(void) { return g_launches; }
+
+int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
+  if (!grid || !out) CMIB_FAIL("null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    CMIB_FAIL("no CUDA device available (%s); this library has no CPU path",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev) CMIB_FAIL("device %d out of range [0,%d)", device, ndev);
+  for (int d = 0; d < 3; ++d) {
+    if (grid->ncell[d] <= 0) CMIB_FAIL("number of cells must be positive");
+    if (!(grid->sides[d] > 0.)) CMIB_FAIL("box sides must be positive");
+  }
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) CMIB_FAIL("device %d is sm_%d%d; this library is built for sm_100a only", device,
+                                 prop.major, prop.minor);
+  cmib_context *ctx = new cmib_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  GridGeom &g = ctx->geom;
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = grid->anchor[d];
+    g.sides[d] = grid->sides[d];
+    g.ncell[d] = grid->ncell[d];
+    g.periodic[d] = grid->periodic[d] ? 1 : 0;
+    /* CartesianDensityGrid.cpp:80-86 */
+    g.cellside[d] = grid->sides[d] / grid->ncell[d];
+    g.inv_cellside[d] = 1. / g.cellside[d];
+  }
+  g.cell_volume = g.cellside[0] * g.cellside[1] * g.cellside[2];
+  g.ncells = (int64_t)g.ncell[0] * g.ncell[1] * g.ncell[2];
+  const size_t nc = (size_t)g.ncells;
+  CUDA_OK(ctx->cells.resize(nc));
+  CUDA_OK(ctx->xmetal.resize(nc * 12));
+  CUDA_OK(ctx->heat_norm.resize(nc * 2));
+  CUDA_OK(cudaMemsetAsync(ctx->cells.p, 0, nc * sizeof(CellOpacity), ctx->stream));
+  CUDA_OK(cudaMemsetAsync(ctx->xmetal.p, 0, nc * 12 * sizeof(double), ctx->stream));
+  CUDA_OK(cudaMemsetAsync(ctx->heat_norm.p, 0, nc * 2 * sizeof(double), ctx->stream));
+  memset(&ctx->src, 0, sizeof(ctx->src));
+  ctx->src.discrete_weight = 1.;
+  ctx->src.xs_kind = XS_VERNER;
+  ctx->src.spectrum_kind = SPECTRUM_MONOCHROMATIC;
+  ctx->src.mono_frequency = ev_to_hz(13.6);
+  ctx->src.reemission_kind = REEMISSION_NONE;
+  memset(&ctx->rr, 0, sizeof(ctx->rr));
+  ctx->rr.kind = RR_VERNER;
+  ctx->tp.do_temperature = 0;
+  ctx->tp.min_iterations = 3;
+  ctx->tp.epsilon = 1.e-3;
+  ctx->tp.max_iterations = 100;
+  ctx->tp.pahfac = 0.;
+  ctx->tp.crfac = 0.;
+  ctx->tp.crlim = 0.75;
+  ctx->tp.crscale = 1.33333 * 3.086e19;
+  ctx->tp.min_ionized_T = 4000.;
+  /* DensityGrid.hpp:219-222 */
+  ctx->nu_H = ev_to_hz(13.6);
+  ctx->nu_He = ev_to_hz(24.6);
+  ctx->acc_mode = -1;
+  if (ensure_acc(ctx)) {
+    delete ctx;
+    return 1;
+  }
+  *out = ctx;
+  return 0;
+}
+
+int cmib_destroy(cmib_context *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+int cmib_synchronize(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cmib_stream(cmib_context *ctx, void **stream) {
+  CHECK_CTX(ctx);
+  *stream = (void *)ctx->stream;
+  return 0;
+}
+
+/* ---- grid state ------------------------------------------------------------ */
+int cmib_upload_cells(cmib_context *ctx, const double *n, const double *T, const double *x,
+                      const double *cr_factor) {
+  CHECK_CTX(ctx);
+  if (!n || !T || !x) CMIB_FAIL("null cell array");
+  const size_t nc = (size_t)ctx->geom.ncells;
+  CUDA_OK(ctx->stage.resize(nc * 18));
+  double *s = ctx->stage.p;
+  CUDA_OK(cudaMemcpyAsync(s, n, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + nc, T, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + 2 * nc, x, nc * 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  pack_cells_kernel<<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, s, s + nc, s + 2 * nc,
+                                                                  ctx->cells.p, ctx->xmetal.p);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  if (cr_factor) {
+    CUDA_OK(ctx->cr_factor.upload(cr_factor, nc, ctx->stream));
+    ctx->have_cr_factor = true;
+  } else {
+    ctx->have_cr_factor = false;
+  }
+  ctx->reemit_prob_valid = false;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream)); /* host arrays may be reused on return */
+  return 0;
+}
+
+int cmib_download_cells(cmib_context *ctx, double *n, double *T, double *x, double *heat) {
+  CHECK_CTX(ctx);
+  const size_t nc = (size_t)ctx->geom.ncells;
+  CUDA_OK(ctx->stage.resize(nc * 18));
+  double *s = ctx->stage.p;
+  unpack_cells_kernel<<<blocks_for(nc, 256), 256, 0, ctx->stream>>>(
+      (int64_t)nc, ctx->cells.p, ctx->xmetal.p, ctx->heat_norm.p, s, s + nc, s + 2 * nc, s + 16 * nc);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  if (n) CUDA_OK(cudaMemcpyAsync(n, s, nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (T) CUDA_OK(cudaMemcpyAsync(T, s + nc, nc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (x) CUDA_OK(cudaMemcpyAsync(x, s + 2 * nc, nc * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (heat) CUDA_OK(cudaMemcpyAsync(heat, s + 16 * nc, nc * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cmib_download_accumulators(cmib_context *ctx, double *J, double *heat) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  const size_t nc = (size_t)ctx->geom.ncells;
+  CUDA_OK(ctx->stage.resize(nc * 18));
+  double *s = ctx->stage.p;
+  if (ctx->acc_mode == ACC_HONLY)
+    unpack_acc_kernel<ACC_HONLY><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, s, s + 14 * nc);
+  else
+    unpack_acc_kernel<ACC_FULL><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, s, s + 14 * nc);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  if (J) CUDA_OK(cudaMemcpyAsync(J, s, nc * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (heat) CUDA_OK(cudaMemcpyAsync(heat, s + 14 * nc, nc * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cmib_reset_accumulators(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  CUDA_OK(cudaMemsetAsync(ctx->acc.p, 0, ctx->acc.n * sizeof(double), ctx->stream));
+  return 0;
+}
+
+/* ---- plugins --------------------------------------------------------------- */
+int cmib_set_abundances(cmib_context *ctx, const double *abundances) {
+  CHECK_CTX(ctx);
+  if (!abundances) CMIB_FAIL("null abundances");
+  for (int k = 0; k < NUM_ELEMENTS; ++k) ctx->abund[k] = abundances[k];
+  ctx->src.A_He = abundances[EL_He];
+  return 0;
+}
+
+int cmib_set_cross_sections(cmib_context *ctx, int kind, const double *fixed) {
+  CHECK_CTX(ctx);
+  if (kind == CMIB_CROSS_SECTIONS_VERNER) {
+    ctx->src.xs_kind = XS_VERNER;
+  } else if (kind == CMIB_CROSS_SECTIONS_FIXED_VALUE) {
+    if (!fixed) CMIB_FAIL("FixedValue cross sections need 14 values");
+    ctx->src.xs_kind = XS_FIXED;
+    for (int k = 0; k < NUM_IONS; ++k) ctx->src.xs_fixed[k] = fixed[k];
+  } else {
+    CMIB_FAIL("Unknown CrossSections type: %d", kind);
+  }
+  return ensure_acc(ctx);
+}
+
+int cmib_set_recombination_rates(cmib_context *ctx, int kind, const double *fixed) {
+  CHECK_CTX(ctx);
+  if (kind == CMIB_RECOMBINATION_VERNER) {
+    ctx->rr.kind = RR_VERNER;
+  } else if (kind == CMIB_RECOMBINATION_FIXED_VALUE) {
+    if (!fixed) CMIB_FAIL("FixedValue recombination rates need 14 values");
+    ctx->rr.kind = RR_FIXED;
+    for (int k = 0; k < NUM_IONS; ++k) ctx->rr.fixed[k] = fixed[k];
+  } else {
+    CMIB_FAIL("Unknown RecombinationRates type: %d", kind);
+  }
+  return 0;
+}
+
+int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, const double *weights,
+                     double total_luminosity) {
+  CHECK_CTX(ctx);
+  if (n <= 0 || !positions || !weights) CMIB_FAIL("need at least one discrete source");
+  /* PhotonSource.cpp:74-100 */
+  std::vector<double> cum(n);
+  for (int i = 0; i < n; ++i) cum[i] = (i > 0 ? cum[i - 1] : 0.) + weights[i];
+  if (std::abs(cum[n - 1] - 1.) > 1.e-9) CMIB_FAIL("Discrete source weights do not sum to 1.0 (%g)!", cum[n - 1]);
+  cum[n - 1] = 1.;
+  CUDA_OK(ctx->d_src_pos.upload(positions, (size_t)n * 3, ctx->stream));
+  CUDA_OK(ctx->d_src_cum.upload(cum.data(), (size_t)n, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->src.n_sources = n;
+  ctx->src.src_pos = ctx->d_src_pos.p;
+  ctx->src.src_cum = ctx->d_src_cum.p;
+  ctx->src.continuous_probability = 0.;
+  ctx->src.discrete_weight = 1.;
+  ctx->luminosity = total_luminosity;
+  return 0;
+}
+
+int cmib_set_spectrum(cmib_context *ctx, int kind, double param) {
+  CHECK_CTX(ctx);
+  if (kind == CMIB_SPECTRUM_MONOCHROMATIC) {
+    ctx->src.spectrum_kind = SPECTRUM_MONOCHROMATIC;
+    ctx->src.mono_frequency = param;
+  } else if (kind == CMIB_SPECTRUM_PLANCK) {
+    if (!(param > 0.)) CMIB_FAIL("Planck temperature must be positive");
+    host::build_planck_table(param, ctx->h_planck);
+    CUDA_OK(ctx->d_planck.upload(ctx->h_planck.data(), ctx->h_planck.size(), ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->src.spectrum_kind = SPECTRUM_PLANCK;
+    ctx->src.planck = ctx->d_planck.p;
+  } else {
+    CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", kind);
+  }
+  return 0;
+}
+
+int cmib_set_reemission(cmib_context *ctx, int kind, double probability, double frequency) {
+  CHECK_CTX(ctx);
+  if (kind == CMIB_REEMISSION_NONE) {
+    ctx->src.reemission_kind = REEMISSION_NONE;
+  } else if (kind == CMIB_REEMISSION_FIXED_VALUE) {
+    ctx->src.reemission_kind = REEMISSION_FIXED;
+    ctx->src.fixed_reemission_probability = probability;
+    ctx->src.fixed_reemission_frequency = frequency;
+  } else if (kind == CMIB_REEMISSION_PHYSICAL) {
+    const SourceModel m = ctx->src;
+    auto sigma_of = [m](int ion) {
+      return [m, ion](double nu) {
+        return m.xs_kind == XS_VERNER ? verner_cross_section(ion, nu) : m.xs_fixed[ion];
+      };
+    };
+    host::build_lyc_table(0, sigma_of(ION_H_n), ctx->h_hlyc_freq, ctx->h_hlyc_temp, ctx->h_hlyc_cdf);
+    host::build_lyc_table(1, sigma_of(ION_He_n), ctx->h_helyc_freq, ctx->h_helyc_temp, ctx->h_helyc_cdf);
+    host::build_he2pc_table(ctx->h_he2pc_freq, ctx->h_he2pc_cdf);
+    CUDA_OK(ctx->d_hlyc_freq.upload(ctx->h_hlyc_freq.data(), ctx->h_hlyc_freq.size(), ctx->stream));
+    CUDA_OK(ctx->d_hlyc_temp.upload(ctx->h_hlyc_temp.data(), ctx->h_hlyc_temp.size(), ctx->stream));
+    CUDA_OK(ctx->d_hlyc_cdf.upload(ctx->h_hlyc_cdf.data(), ctx->h_hlyc_cdf.size(), ctx->stream));
+    CUDA_OK(ctx->d_helyc_freq.upload(ctx->h_helyc_freq.data(), ctx->h_helyc_freq.size(), ctx->stream));
+    CUDA_OK(ctx->d_helyc_temp.upload(ctx->h_helyc_temp.data(), ctx->h_helyc_temp.size(), ctx->stream));
+    CUDA_OK(ctx->d_helyc_cdf.upload(ctx->h_helyc_cdf.data(), ctx->h_helyc_cdf.size(), ctx->stream));
+    CUDA_OK(ctx->d_he2pc_freq.upload(ctx->h_he2pc_freq.data(), ctx->h_he2pc_freq.size(), ctx->stream));
+    CUDA_OK(ctx->d_he2pc_cdf.upload(ctx->h_he2pc_cdf.data(), ctx->h_he2pc_cdf.size(), ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->src.hlyc_freq = ctx->d_hlyc_freq.p;
+    ctx->src.hlyc_temp = ctx->d_hlyc_temp.p;
+    ctx->src.hlyc_cdf = ctx->d_hlyc_cdf.p;
+    ctx->src.helyc_freq = ctx->d_helyc_freq.p;
+    ctx->src.helyc_temp = ctx->d_helyc_temp.p;
+    ctx->src.helyc_cdf = ctx->d_helyc_cdf.p;
+    ctx->src.he2pc_freq = ctx->d_he2pc_freq.p;
+    ctx->src.he2pc_cdf = ctx->d_he2pc_cdf.p;
+    ctx->src.reemission_kind = REEMISSION_PHYSICAL;
+    CUDA_OK(ctx->reemit_prob.resize((size_t)ctx->geom.ncells * NUM_REEMIT));
+    ctx->reemit_prob_valid = false;
+  } else {
+    CMIB_FAIL("Unknown DiffuseReemissionHandler type: %d", kind);
+  }
+  return 0;
+}
+
+int cmib_set_temperature_params(cmib_context *ctx, const cmib_temperature_params *p) {
+  CHECK_CTX(ctx);
+  if (!p) CMIB_FAIL("null parameters");
+  ctx->tp.do_temperature = p->do_temperature_calculation;
+  ctx->tp.min_iterations = p->minimum_number_of_iterations;
+  ctx->tp.epsilon = p->epsilon_convergence;
+  ctx->tp.max_iterations = p->maximum_number_of_iterations;
+  ctx->tp.pahfac = p->pah_heating_factor;
+  ctx->tp.crfac = p->cosmic_ray_heating_factor;
+  ctx->tp.crlim = p->cosmic_ray_heating_limit;
+  ctx->tp.crscale = p->cosmic_ray_heating_scale_length;
+  ctx->tp.min_ionized_T = p->minimum_ionized_temperature;
+  return 0;
+}
+
+/* ---- iteration ------------------------------------------------------------- */
+int cmib_update_reemission_probabilities(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (ctx->src.reemission_kind != REEMISSION_PHYSICAL) return 0;
+  const int64_t nc = ctx->geom.ncells;
+  reemission_probabilities_kernel<<<blocks_for(nc, 256), 256, 0, ctx->stream>>>(nc, ctx->cells.p,
+                                                                                 ctx->reemit_prob.p);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  ctx->reemit_prob_valid = true;
+  return 0;
+}
+
+int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, uint64_t seed,
+               uint32_t iteration, double *totweight, double *typecount) {
+  CHECK_CTX(ctx);
+  if (ctx->src.n_sources <= 0) CMIB_FAIL("no photon sources set");
+  if (ensure_acc(ctx)) return 1;
+  if (ctx->src.reemission_kind == REEMISSION_PHYSICAL && !ctx->reemit_prob_valid)
+    if (cmib_update_reemission_probabilities(ctx)) return 1;
+  double before[5] = {0., 0., 0., 0., 0.};
+  if (totweight || typecount) {
+    CUDA_OK(cudaMemcpyAsync(before, ctx->acc.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_packets > 0) {
+    ShootParams P;
+    P.geom = ctx->geom;
+    P.src = ctx->src;
+    P.cells = ctx->cells.p;
+    P.reemit_prob = ctx->reemit_prob.p;
+    P.acc = ctx->acc.p;
+    P.nu_H = ctx->nu_H;
+    P.nu_He = ctx->nu_He;
+    P.seed = seed;
+    P.iteration = iteration;
+    P.packet_offset = packet_offset;
+    P.n_packets = n_packets;
+    const int bs = 256;
+    /* persistent-style grid: a multiple of the SM count, packets are strided over it */
+    uint64_t want = (n_packets + bs - 1) / bs;
+    uint64_t cap = (uint64_t)ctx->sm_count * 8;
+    unsigned grid = (unsigned)(want < cap ? want : cap);
+    if (ctx->acc_mode == ACC_HONLY)
+      shoot_kernel<ACC_HONLY><<<grid, bs, 0, ctx->stream>>>(P);
+    else
+      shoot_kernel<ACC_FULL><<<grid, bs, 0, ctx->stream>>>(P);
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+  }
+  if (totweight || typecount) {
+    double after[5];
+    CUDA_OK(cudaMemcpyAsync(after, ctx->acc.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    if (totweight) *totweight = after[0] - before[0];
+    if (typecount)
+      for (int t = 0; t < 4; ++t) typecount[t] = after[1 + t] - before[1 + t];
+  }
+  return 0;
+}
+
+int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  UpdateParams P;
+  P.geom = ctx->geom;
+  P.cells = ctx->cells.p;
+  P.xmetal = ctx->xmetal.p;
+  P.heat_norm = ctx->heat_norm.p;
+  P.cr_factor = ctx->have_cr_factor ? ctx->cr_factor.p : nullptr;
+  P.acc = ctx->acc.p;
+  P.luminosity = ctx->luminosity;
+  P.totweight = totweight;
+  for (int k = 0; k < NUM_ELEMENTS; ++k) P.abund[k] = ctx->abund[k];
+  P.rr = ctx->rr;
+  P.tp = ctx->tp;
+  /* TemperatureCalculator.cpp:948: strictly greater */
+  P.solve_temperature = (ctx->tp.do_temperature && loop > ctx->tp.min_iterations) ? 1 : 0;
+  const int64_t nc = ctx->geom.ncells;
+  if (ctx->acc_mode == ACC_HONLY)
+    update_state_kernel<ACC_HONLY><<<blocks_for(nc, 128), 128, 0, ctx->stream>>>(P);
+  else
+    update_state_kernel<ACC_FULL><<<blocks_for(nc, 128), 128, 0, ctx->stream>>>(P);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  ctx->reemit_prob_valid = false;
+  return 0;
+}
+
+int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_doubles) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  if (device_ptr) *device_ptr = ctx->acc.p;
+  if (n_doubles) *n_doubles = ctx->acc.n;
+  return 0;
+}
+
+/* ---- test hooks ------------------------------------------------------------ */
+
+int cmib_march_packets(cmib_context *ctx, int64_t np, const double *pos, const double *dir,
+                       const double *sigma, const double *sigma_He_corr, const double *nu,
+                       const double *weight, const double *tau, double *final_pos,
+                       int64_t *final_cell, int32_t *nsteps, int32_t max_trace, int64_t *trace) {
+  CHECK_CTX(ctx);
+  if (np <= 0) return 0;
+  if (!ctx->force_full) {
+    ctx->force_full = true; /* explicit packets carry all 14 cross sections */
+  }
+  if (ensure_acc(ctx)) return 1;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  MarchPacketsParams P;
+  P.geom = ctx->geom;
+  P.cells = ctx->cells.p;
+  P.acc = ctx->acc.p;
+  P.nu_H = ctx->nu_H;
+  P.nu_He = ctx->nu_He;
+  P.np = np;
+  double *d_pos, *d_dir, *d_sigma, *d_she, *d_nu, *d_w, *d_tau, *d_fp;
+  int64_t *d_fc, *d_trace = nullptr;
+  int32_t *d_ns;
+  CUDA_OK(sc.in(&d_pos, pos, (size_t)np * 3, s));
+  CUDA_OK(sc.in(&d_dir, dir, (size_t)np * 3, s));
+  CUDA_OK(sc.in(&d_sigma, sigma, (size_t)np * NUM_IONS, s));
+  CUDA_OK(sc.in(&d_she, sigma_He_corr, (size_t)np, s));
+  CUDA_OK(sc.in(&d_nu, nu, (size_t)np, s));
+  CUDA_OK(sc.in(&d_w, weight, (size_t)np, s));
+  CUDA_OK(sc.in(&d_tau, tau, (size_t)np, s));
+  CUDA_OK(sc.out(&d_fp, (size_t)np * 3));
+  CUDA_OK(sc.out(&d_fc, (size_t)np));
+  CUDA_OK(sc.out(&d_ns, (size_t)np));
+  if (trace && max_trace > 0) CUDA_OK(sc.out(&d_trace, (size_t)np * max_trace));
+  P.pos = d_pos; P.dir = d_dir; P.sigma = d_sigma; P.sigma_He_corr = d_she; P.nu = d_nu;
+  P.weight = d_w; P.tau = d_tau; P.final_pos = d_fp; P.final_cell = d_fc; P.nsteps = d_ns;
+  P.max_trace = d_trace ? max_trace : 0;
+  P.trace = d_trace;
+  march_packets_kernel<<<blocks_for(np, 128), 128, 0, s>>>(P);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(final_pos, d_fp, (size_t)np * 3, s));
+  CUDA_OK(sc.back(final_cell, d_fc, (size_t)np, s));
+  CUDA_OK(sc.back(nsteps, d_ns, (size_t)np, s));
+  if (d_trace) CUDA_OK(sc.back(trace, d_trace, (size_t)np * max_trace, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_sample_packets(cmib_context *ctx, int64_t n, uint64_t offset, uint64_t seed,
+                        uint32_t iteration, double *pos, double *dir, double *nu, double *sigma,
+                        double *sigma_He_corr, double *tau) {
+  CHECK_CTX(ctx);
+  if (ctx->src.n_sources <= 0) CMIB_FAIL("no photon sources set");
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  SamplePacketsParams P;
+  P.src = ctx->src;
+  P.n = n; P.offset = offset; P.seed = seed; P.iteration = iteration;
+  CUDA_OK(sc.out(&P.pos, (size_t)n * 3));
+  CUDA_OK(sc.out(&P.dir, (size_t)n * 3));
+  CUDA_OK(sc.out(&P.nu, (size_t)n));
+  CUDA_OK(sc.out(&P.sigma, (size_t)n * NUM_IONS));
+  CUDA_OK(sc.out(&P.sigma_He_corr, (size_t)n));
+  CUDA_OK(sc.out(&P.tau, (size_t)n));
+  sample_packets_kernel<<<blocks_for(n, 128), 128, 0, s>>>(P);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(pos, P.pos, (size_t)n * 3, s));
+  CUDA_OK(sc.back(dir, P.dir, (size_t)n * 3, s));
+  CUDA_OK(sc.back(nu, P.nu, (size_t)n, s));
+  CUDA_OK(sc.back(sigma, P.sigma, (size_t)n * NUM_IONS, s));
+  CUDA_OK(sc.back(sigma_He_corr, P.sigma_He_corr, (size_t)n, s));
+  CUDA_OK(sc.back(tau, P.tau, (size_t)n, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_cross_sections(cmib_context *ctx, int64_t n, const double *nu, double *sigma) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_nu, *d_sigma;
+  CUDA_OK(sc.in(&d_nu, nu, (size_t)n, s));
+  CUDA_OK(sc.out(&d_sigma, (size_t)n * NUM_IONS));
+  eval_cross_sections_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->src, d_nu, d_sigma);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(sigma, d_sigma, (size_t)n * NUM_IONS, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_recombination_rates(cmib_context *ctx, int64_t n, const double *T, double *alpha) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_T, *d_a;
+  CUDA_OK(sc.in(&d_T, T, (size_t)n, s));
+  CUDA_OK(sc.out(&d_a, (size_t)n * NUM_IONS));
+  eval_recombination_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, ctx->rr, d_T, d_a);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(alpha, d_a, (size_t)n * NUM_IONS, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_charge_transfer(cmib_context *ctx, int64_t n, const double *T4, double *out) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_T, *d_o;
+  CUDA_OK(sc.in(&d_T, T4, (size_t)n, s));
+  CUDA_OK(sc.out(&d_o, (size_t)n * 3 * NUM_IONS));
+  eval_charge_transfer_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, d_T, d_o);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(out, d_o, (size_t)n * 3 * NUM_IONS, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_line_cooling(cmib_context *ctx, int64_t n, const double *T, const double *ne,
+                           const double *abund, double *cooling) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_T, *d_ne, *d_ab, *d_c;
+  CUDA_OK(sc.in(&d_T, T, (size_t)n, s));
+  CUDA_OK(sc.in(&d_ne, ne, (size_t)n, s));
+  CUDA_OK(sc.in(&d_ab, abund, (size_t)n * LC_NUM, s));
+  CUDA_OK(sc.out(&d_c, (size_t)n));
+  eval_line_cooling_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, d_T, d_ne, d_ab, d_c);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(cooling, d_c, (size_t)n, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_solve5(cmib_context *ctx, int64_t n, double *A, double *B, int32_t *status) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_A, *d_B;
+  int32_t *d_s;
+  CUDA_OK(sc.in(&d_A, (const double *)A, (size_t)n * 25, s));
+  CUDA_OK(sc.in(&d_B, (const double *)B, (size_t)n * 5, s));
+  CUDA_OK(sc.out(&d_s, (size_t)n));
+  eval_solve5_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, d_A, d_B, d_s);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(A, d_A, (size_t)n * 25, s));
+  CUDA_OK(sc.back(B, d_B, (size_t)n * 5, s));
+  CUDA_OK(sc.back(status, d_s, (size_t)n, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_reemission_probabilities(cmib_context *ctx, int64_t n, const double *T, double *out) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_T, *d_o;
+  CUDA_OK(sc.in(&d_T, T, (size_t)n, s));
+  CUDA_OK(sc.out(&d_o, (size_t)n * NUM_REEMIT));
+  eval_reemission_probabilities_kernel<<<blocks_for(n, 128), 128, 0, s>>>(n, d_T, d_o);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(out, d_o, (size_t)n * NUM_REEMIT, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+static int eval_state_common(cmib_context *ctx, int solve_T, int64_t n, double jfac, double hfac,
+                             const double *J, const double *heat, const double *ndens,
+                             const double *T, const double *cr_factor, const double *midz,
+                             double *T_out, double *x, double *heat_out) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  EvalStateParams P;
+  P.n = n; P.jfac = jfac; P.hfac = hfac;
+  for (int k = 0; k < NUM_ELEMENTS; ++k) P.abund[k] = ctx->abund[k];
+  P.rr = ctx->rr;
+  P.tp = ctx->tp;
+  P.solve_temperature = solve_T;
+  double *dJ, *dh, *dn, *dT, *dcr, *dmz;
+  CUDA_OK(sc.in(&dJ, J, (size_t)n * NUM_IONS, s));
+  CUDA_OK(sc.in(&dh, heat, (size_t)n * 2, s));
+  CUDA_OK(sc.in(&dn, ndens, (size_t)n, s));
+  CUDA_OK(sc.in(&dT, T, (size_t)n, s));
+  CUDA_OK(sc.in(&dcr, cr_factor, (size_t)n, s));
+  CUDA_OK(sc.in(&dmz, midz, (size_t)n, s));
+  P.J = dJ; P.heat = dh; P.ndens = dn; P.T = dT; P.cr_factor = dcr; P.midz = dmz;
+  CUDA_OK(sc.out(&P.T_out, (size_t)n));
+  CUDA_OK(sc.out(&P.x, (size_t)n * NUM_IONS));
+  CUDA_OK(sc.out(&P.heat_out, (size_t)n * 2));
+  eval_state_kernel<<<blocks_for(n, 128), 128, 0, s>>>(P);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(T_out, P.T_out, (size_t)n, s));
+  CUDA_OK(sc.back(x, P.x, (size_t)n * NUM_IONS, s));
+  CUDA_OK(sc.back(heat_out, P.heat_out, (size_t)n * 2, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_eval_ionization_state(cmib_context *ctx, int64_t n, double jfac, double hfac,
+                               const double *J, const double *heat, const double *ndens,
+                               const double *T, double *x, double *heat_out) {
+  return eval_state_common(ctx, 0, n, jfac, hfac, J, heat, ndens, T, nullptr, nullptr, nullptr, x,
+                           heat_out);
+}
+
+int cmib_eval_temperature(cmib_context *ctx, int64_t n, double jfac, double hfac, const double *J,
+                          const double *heat, const double *ndens, const double *T,
+                          const double *cr_factor, const double *midz, double *T_out, double *x,
+                          double *heat_out) {
+  return eval_state_common(ctx, 1, n, jfac, hfac, J, heat, ndens, T, cr_factor, midz, T_out, x,
+                           heat_out);
+}
+
+int cmib_eval_cooling_heating_balance(cmib_context *ctx, int64_t n, const double *T,
+                                      const double *ndens, const double *j, const double *h,
+                                      const double *midz, double *h0, double *he0, double *gain,
+                                      double *loss, double *metals) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  EvalBalanceParams P;
+  P.n = n;
+  for (int k = 0; k < NUM_ELEMENTS; ++k) P.abund[k] = ctx->abund[k];
+  P.rr = ctx->rr;
+  P.pahfac = ctx->tp.pahfac;
+  P.crfac = ctx->tp.crfac;
+  P.crscale = ctx->tp.crscale;
+  double *dT, *dn, *dj, *dh, *dmz;
+  CUDA_OK(sc.in(&dT, T, (size_t)n, s));
+  CUDA_OK(sc.in(&dn, ndens, (size_t)n, s));
+  CUDA_OK(sc.in(&dj, j, (size_t)n * NUM_IONS, s));
+  CUDA_OK(sc.in(&dh, h, (size_t)n * 2, s));
+  CUDA_OK(sc.in(&dmz, midz, (size_t)n, s));
+  P.T = dT; P.ndens = dn; P.j = dj; P.h = dh; P.midz = dmz;
+  CUDA_OK(sc.out(&P.h0, (size_t)n));
+  CUDA_OK(sc.out(&P.he0, (size_t)n));
+  CUDA_OK(sc.out(&P.gain, (size_t)n));
+  CUDA_OK(sc.out(&P.loss, (size_t)n));
+  CUDA_OK(sc.out(&P.metals, (size_t)n * 12));
+  eval_balance_kernel<<<blocks_for(n, 128), 128, 0, s>>>(P);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(h0, P.h0, (size_t)n, s));
+  CUDA_OK(sc.back(he0, P.he0, (size_t)n, s));
+  CUDA_OK(sc.back(gain, P.gain, (size_t)n, s));
+  CUDA_OK(sc.back(loss, P.loss, (size_t)n, s));
+  CUDA_OK(sc.back(metals, P.metals, (size_t)n * 12, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int cmib_get_spectrum_tables(cmib_context *ctx, int which, double *a, double *b, double *c) {
+  if (!ctx) CMIB_FAIL("null context");
+  auto copy = [](double *dst, const std::vector<double> &v) {
+    if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * sizeof(double));
+  };
+  switch (which) {
+  case 0:
+    if (ctx->h_planck.empty()) CMIB_FAIL("no Planck spectrum set");
+    copy(a, ctx->h_planck);
+    break;
+  case 1:
+    if (ctx->h_hlyc_cdf.empty()) CMIB_FAIL("no Physical reemission handler set");
+    copy(a, ctx->h_hlyc_freq); copy(b, ctx->h_hlyc_temp); copy(c, ctx->h_hlyc_cdf);
+    break;
+  case 2:
+    if (ctx->h_helyc_cdf.empty()) CMIB_FAIL("no Physical reemission handler set");
+    copy(a, ctx->h_helyc_freq); copy(b, ctx->h_helyc_temp); copy(c, ctx->h_helyc_cdf);
+    break;
+  case 3:
+    if (ctx->h_he2pc_cdf.empty()) CMIB_FAIL("no Physical reemission handler set");
+    copy(a, ctx->h_he2pc_freq); copy(b, ctx->h_he2pc_cdf);
+    break;
+  default:
+    CMIB_FAIL("unknown table %d", which);
+  }
+  return 0;
+}
+
+int cmib_sample_spectrum(cmib_context *ctx, int which, double temperature, uint64_t seed, int64_t n,
+                         double *nu) {
+  CHECK_CTX(ctx);
+  if (n <= 0) return 0;
+  if (which != 0 && ctx->src.reemission_kind != REEMISSION_PHYSICAL)
+    CMIB_FAIL("diffuse spectra need the Physical reemission handler");
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_nu;
+  CUDA_OK(sc.out(&d_nu, (size_t)n));
+  sample_spectrum_kernel<<<blocks_for(n, 128), 128, 0, s>>>(ctx->src, which, temperature, seed, n, d_nu);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(nu, d_nu, (size_t)n, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+} /* extern "C" */

@@ -1,0 +1,530 @@
+/*
+ * kernels.cuh — the sm_100a kernels of the photoionization hot path.
+ *
+ *   shoot_kernel        emit -> tau -> voxel walk -> accumulate -> (re-emit)*   [hot]
+ *   march_packets_kernel test hook: the same walk on caller-supplied packets
+ *   reemission_probabilities_kernel, update_state_kernel   per-cell passes
+ *   eval_* kernels      element-wise probes of the physics for the parity tests
+ *
+ * Accumulator layouts: after 8 leading counter doubles,
+ *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
+ *   ACC_HONLY  acc[cell][2]  = J_H, heat_H              (16 B; used when only sigma_H != 0)
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+#include "cmib_common.cuh"
+#include "march.cuh"
+#include "rng.cuh"
+#include "source.cuh"
+#include "state.cuh"
+
+namespace cmib {
+
+enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
+constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], 3 pad: keeps cells 64-B aligned */
+
+template <int MODE> struct AccLayout;
+template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
+template <> struct AccLayout<ACC_HONLY> { static constexpr int NACC = 2; static constexpr int NSIG = 1; };
+
+struct ShootParams {
+  GridGeom geom;
+  SourceModel src;
+  const CellOpacity *cells;
+  const double *reemit_prob; /* [ncell][5] (REEMISSION_PHYSICAL) */
+  double *acc;               /* counters + per-cell accumulators */
+  double nu_H, nu_He;        /* 13.6 eV, 24.6 eV in Hz (DensityGrid.hpp:219-222) */
+  uint64_t seed;
+  uint32_t iteration;
+  uint64_t packet_offset;
+  uint64_t n_packets;
+};
+
+/* fire-and-forget FP64 add: compiles to RED.E.ADD.F64 (no return value) */
+CMIB_D void red_add(double *addr, double v) { atomicAdd(addr, v); }
+
+/* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which
+ * is exact (x + 0.0 == x) and removes most of the 16 RMWs for soft photons */
+template <int MODE>
+CMIB_D void accumulate(double *acc, int64_t cell, double ds, double weight, const double *sigma,
+                       double dnu_H, double dnu_He) {
+  const double dsw = ds * weight;
+  double *a = acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
+  if (MODE == ACC_HONLY) {
+    const double dJ = dsw * sigma[0];
+    red_add(a, dJ);
+    const double dh = dJ * dnu_H;
+    if (dh != 0.) red_add(a + 1, dh);
+  } else {
+    const double dJH = dsw * sigma[ION_H_n];
+    const double dJHe = dsw * sigma[ION_He_n];
+#pragma unroll
+    for (int ion = 0; ion < NUM_IONS; ++ion) {
+      const double dJ = dsw * sigma[ion];
+      if (dJ != 0.) red_add(a + ion, dJ);
+    }
+    const double dhH = dJH * dnu_H;
+    if (dhH != 0.) red_add(a + NUM_IONS + HEAT_H, dhH);
+    const double dhHe = dJHe * dnu_He;
+    if (dhHe != 0.) red_add(a + NUM_IONS + HEAT_He, dhHe);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* shoot: one thread follows one packet at a time (grid-stride over packet ids) */
+/* ------------------------------------------------------------------------- */
+template <int MODE>
+__global__ void __launch_bounds__(256)
+shoot_kernel(const __grid_constant__ ShootParams P) {
+  constexpr int NSIG = AccLayout<MODE>::NSIG;
+  const GridGeom &g = P.geom;
+  const SourceModel &m = P.src;
+  double w_tot = 0.;
+  double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
+
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_packets; i += stride) {
+    PacketRng rng;
+    rng_init(rng, P.seed, P.iteration, P.packet_offset + i);
+    MarchState s;
+    double sigma[NSIG];
+    double sigma_He_corr;
+    double nu;
+    int type = PACKET_PRIMARY;
+    /* --- PhotonSource::get_random_photon --- */
+    double x = rng_uniform(rng);
+    (void)x; /* discrete vs continuous: continuous sources are not on this path */
+    x = rng_uniform(rng);
+    int isrc = 0;
+    while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
+    s.px = m.src_pos[3 * isrc];
+    s.py = m.src_pos[3 * isrc + 1];
+    s.pz = m.src_pos[3 * isrc + 2];
+    random_direction(rng, s.dx, s.dy, s.dz);
+    nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+    const double weight = m.discrete_weight;
+    packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+
+    bool alive = true;
+    while (alive) {
+      s.ix_ = 1. / s.dx;
+      s.iy_ = 1. / s.dy;
+      s.iz_ = 1. / s.dz;
+      s.tau = -log(rng_uniform(rng));
+      march_locate(g, s);
+      const double dnu_H = nu - P.nu_H;
+      const double dnu_He = nu - P.nu_He;
+      CellOpacity c = {0., 0., 0., 0.};
+      bool inside;
+      while ((inside = march_inside(g, s)) && s.tau > 0.) {
+        const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
+        s.last_cell = cell;
+        const double2 *cp = reinterpret_cast<const double2 *>(P.cells + cell);
+        const double2 r0 = __ldg(cp), r1 = __ldg(cp + 1);
+        c.n = r0.x; c.xH = r0.y; c.xHe = r1.x; c.T = r1.y;
+        const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
+        if (c.n > 0.) accumulate<MODE>(P.acc, cell, ds, weight, sigma, dnu_H, dnu_He);
+      }
+      if (!inside) break; /* left the box: keeps its last type */
+      /* --- PhotonSource::reemit --- */
+      double new_nu = 0.;
+      if (m.reemission_kind == REEMISSION_PHYSICAL) {
+        double p[NUM_REEMIT];
+#pragma unroll
+        for (int k = 0; k < NUM_REEMIT; ++k) p[k] = P.reemit_prob[s.last_cell * NUM_REEMIT + k];
+        /* ACC_HONLY is only selected when sigma_He == 0 */
+        const double sHe = (NSIG > 1) ? sigma[(NSIG > 1) ? ION_He_n : 0] : 0.;
+        new_nu = physical_reemit(m, sigma[0], sHe, c.xH, c.xHe, c.T, p, rng, type);
+      } else if (m.reemission_kind == REEMISSION_FIXED) {
+        const double u = rng_uniform(rng);
+        if (u < m.fixed_reemission_probability) {
+          type = PACKET_DIFFUSE_HI;
+          new_nu = m.fixed_reemission_frequency;
+        } else {
+          type = PACKET_ABSORBED;
+        }
+      } else {
+        type = PACKET_ABSORBED;
+      }
+      if (new_nu == 0.) {
+        alive = false;
+      } else {
+        nu = new_nu;
+        random_direction(rng, s.dx, s.dy, s.dz);
+        packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+      }
+    }
+    w_tot += weight;
+#pragma unroll
+    for (int t = 0; t < NUM_PACKET_TYPES; ++t) w_type[t] += (t == type) ? weight : 0.;
+  }
+
+  /* IonizationPhotonShootJobMarket::update_counters: block reduce, one RED per block */
+  __shared__ double red[5][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[5] = {w_tot, w_type[0], w_type[1], w_type[2], w_type[3]};
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double sum = 0.;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[threadIdx.x][w];
+    if (sum != 0.) red_add(P.acc + threadIdx.x, sum);
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* test hook: CartesianDensityGrid::interact on explicit packets              */
+/* ------------------------------------------------------------------------- */
+struct MarchPacketsParams {
+  GridGeom geom;
+  const CellOpacity *cells;
+  double *acc;
+  double nu_H, nu_He;
+  int64_t np;
+  const double *pos, *dir, *sigma, *sigma_He_corr, *nu, *weight, *tau;
+  double *final_pos;
+  int64_t *final_cell;
+  int32_t *nsteps;
+  int32_t max_trace;
+  int64_t *trace;
+};
+
+__global__ void __launch_bounds__(128)
+march_packets_kernel(const __grid_constant__ MarchPacketsParams P) {
+  const GridGeom &g = P.geom;
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P.np) return;
+  MarchState s;
+  s.px = P.pos[3 * p]; s.py = P.pos[3 * p + 1]; s.pz = P.pos[3 * p + 2];
+  s.dx = P.dir[3 * p]; s.dy = P.dir[3 * p + 1]; s.dz = P.dir[3 * p + 2];
+  s.ix_ = 1. / s.dx; s.iy_ = 1. / s.dy; s.iz_ = 1. / s.dz;
+  s.tau = P.tau[p];
+  double sigma[NUM_IONS];
+#pragma unroll
+  for (int k = 0; k < NUM_IONS; ++k) sigma[k] = P.sigma[p * NUM_IONS + k];
+  const double sHe = P.sigma_He_corr[p];
+  const double nu = P.nu[p];
+  const double w = P.weight[p];
+  march_locate(g, s);
+  int32_t nsteps = 0;
+  bool inside;
+  while ((inside = march_inside(g, s)) && s.tau > 0.) {
+    const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
+    s.last_cell = cell;
+    const CellOpacity c = P.cells[cell];
+    const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sHe);
+    if (c.n > 0.) {
+      accumulate<ACC_FULL>(P.acc, cell, ds, w, sigma, nu - P.nu_H, nu - P.nu_He);
+      if (P.trace && nsteps < P.max_trace) P.trace[p * P.max_trace + nsteps] = cell;
+      ++nsteps;
+    }
+  }
+  /* interact() re-evaluates is_inside after the loop (:447): idempotent here */
+  P.final_pos[3 * p] = s.px; P.final_pos[3 * p + 1] = s.py; P.final_pos[3 * p + 2] = s.pz;
+  P.final_cell[p] = inside ? s.last_cell : -1;
+  P.nsteps[p] = nsteps;
+  if (P.trace)
+    for (int32_t k = nsteps; k < P.max_trace; ++k) P.trace[p * P.max_trace + k] = -1;
+}
+
+/* ------------------------------------------------------------------------- */
+/* per-cell passes                                                            */
+/* ------------------------------------------------------------------------- */
+__global__ void reemission_probabilities_kernel(int64_t ncell, const CellOpacity *cells,
+                                                double *prob) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  double p[NUM_REEMIT];
+  reemission_probabilities(cells[i].T, p);
+#pragma unroll
+  for (int k = 0; k < NUM_REEMIT; ++k) prob[i * NUM_REEMIT + k] = p[k];
+}
+
+struct UpdateParams {
+  GridGeom geom;
+  CellOpacity *cells;
+  double *xmetal;        /* [ncell][12] */
+  double *heat_norm;     /* [ncell][2] */
+  const double *cr_factor; /* [ncell] or NULL */
+  const double *acc;
+  double luminosity;
+  double totweight;      /* <= 0: read acc[0] */
+  double abund[NUM_ELEMENTS];
+  RecombinationModel rr;
+  TemperatureParams tp;
+  int solve_temperature;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128)
+update_state_kernel(const __grid_constant__ UpdateParams P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.geom.ncells) return;
+  const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
+  /* jfac = L / W, hfac = jfac * h, both divided by the cell volume per cell
+   * (IonizationStateCalculator.cpp:519-521, .hpp:135-139) */
+  const double jfac0 = P.luminosity / totweight;
+  const double hfac0 = jfac0 * PLANCK;
+  const double jfac = jfac0 / P.geom.cell_volume;
+  const double hfac = hfac0 / P.geom.cell_volume;
+  double J[NUM_IONS], heat[NUM_HEAT];
+  const double *a = P.acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
+  if (MODE == ACC_HONLY) {
+#pragma unroll
+    for (int k = 0; k < NUM_IONS; ++k) J[k] = 0.;
+    J[0] = a[0];
+    heat[0] = a[1];
+    heat[1] = 0.;
+  } else {
+#pragma unroll
+    for (int k = 0; k < NUM_IONS; ++k) J[k] = a[k];
+    heat[0] = a[NUM_IONS];
+    heat[1] = a[NUM_IONS + 1];
+  }
+  CellOpacity c = P.cells[i];
+  CellState out;
+  if (P.solve_temperature) {
+    double xprev[NUM_IONS];
+    xprev[0] = c.xH;
+    xprev[1] = c.xHe;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) xprev[2 + k] = P.xmetal[i * 12 + k];
+    /* cell midpoint z (CartesianDensityGrid.hpp:85-89): anchor + cellside*iz + 0.5*cellside */
+    const int32_t iz = (int32_t)(i % P.geom.ncell[2]);
+    const double midz = (P.geom.anchor[2] + P.geom.cellside[2] * iz) + 0.5 * P.geom.cellside[2];
+    const double crf = P.cr_factor ? P.cr_factor[i] : -1.;
+    cell_temperature(jfac, hfac, J, heat, c.n, c.T, crf, midz, P.abund, P.rr, P.tp, xprev, out);
+  } else {
+    cell_ionization_state(jfac, hfac, J, heat, c.n, c.T, P.abund, P.rr, out);
+  }
+  c.xH = out.x[ION_H_n];
+  c.xHe = out.x[ION_He_n];
+  c.T = out.T;
+  P.cells[i] = c;
+#pragma unroll
+  for (int k = 0; k < 12; ++k) P.xmetal[i * 12 + k] = out.x[2 + k];
+  P.heat_norm[i * 2] = out.heat[0];
+  P.heat_norm[i * 2 + 1] = out.heat[1];
+}
+
+/* host SoA <-> device layout */
+__global__ void pack_cells_kernel(int64_t ncell, const double *n, const double *T, const double *x,
+                                  CellOpacity *cells, double *xmetal) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  CellOpacity c;
+  c.n = n[i];
+  c.T = T[i];
+  c.xH = x[i];
+  c.xHe = x[ncell + i];
+  cells[i] = c;
+  for (int k = 0; k < 12; ++k) xmetal[i * 12 + k] = x[(2 + k) * ncell + i];
+}
+
+__global__ void unpack_cells_kernel(int64_t ncell, const CellOpacity *cells, const double *xmetal,
+                                    const double *heat_norm, double *n, double *T, double *x,
+                                    double *heat) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const CellOpacity c = cells[i];
+  n[i] = c.n;
+  T[i] = c.T;
+  x[i] = c.xH;
+  x[ncell + i] = c.xHe;
+  for (int k = 0; k < 12; ++k) x[(2 + k) * ncell + i] = xmetal[i * 12 + k];
+  heat[i] = heat_norm[2 * i];
+  heat[ncell + i] = heat_norm[2 * i + 1];
+}
+
+/* accumulators -> reference SoA view J[14][ncell], heat[2][ncell] */
+template <int MODE>
+__global__ void unpack_acc_kernel(int64_t ncell, const double *acc, double *J, double *heat) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ncell) return;
+  const double *a = acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
+  if (MODE == ACC_HONLY) {
+    for (int k = 1; k < NUM_IONS; ++k) J[k * ncell + i] = 0.;
+    J[i] = a[0];
+    heat[i] = a[1];
+    heat[ncell + i] = 0.;
+  } else {
+    for (int k = 0; k < NUM_IONS; ++k) J[k * ncell + i] = a[k];
+    heat[i] = a[NUM_IONS];
+    heat[ncell + i] = a[NUM_IONS + 1];
+  }
+}
+
+/* ------------------------------------------------------------------------- */
+/* element-wise probes                                                        */
+/* ------------------------------------------------------------------------- */
+__global__ void eval_cross_sections_kernel(int64_t n, SourceModel m, const double *nu, double *sigma) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s[NUM_IONS], sHe;
+  packet_cross_sections<NUM_IONS>(m, nu[i], s, sHe);
+  for (int k = 0; k < NUM_IONS; ++k) sigma[i * NUM_IONS + k] = s[k];
+}
+
+__global__ void eval_recombination_kernel(int64_t n, RecombinationModel rr, const double *T,
+                                          double *alpha) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < NUM_IONS; ++k) alpha[i * NUM_IONS + k] = recombination_rate(rr, k, T[i]);
+}
+
+__global__ void eval_charge_transfer_kernel(int64_t n, const double *T4, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double *o = out + i * 3 * NUM_IONS;
+  for (int k = 0; k < NUM_IONS; ++k) {
+    o[k] = (k == ION_H_n) ? 0. : ct_recombination_H(k, T4[i]);
+    o[NUM_IONS + k] = ct_ionization_H(k, T4[i]);
+    o[2 * NUM_IONS + k] = ct_recombination_He(k, T4[i]);
+  }
+}
+
+__global__ void eval_line_cooling_kernel(int64_t n, const double *T, const double *ne,
+                                         const double *abund, double *cooling) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double ab[LC_NUM];
+  for (int k = 0; k < LC_NUM; ++k) ab[k] = abund[i * LC_NUM + k];
+  cooling[i] = line_cooling(T[i], ne[i], ab);
+}
+
+__global__ void eval_solve5_kernel(int64_t n, double *A, double *B, int32_t *status) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a[5][5], b[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) a[r][c] = A[i * 25 + r * 5 + c];
+    b[r] = B[i * 5 + r];
+  }
+  status[i] = solve5(a, b);
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) A[i * 25 + r * 5 + c] = a[r][c];
+    B[i * 5 + r] = b[r];
+  }
+}
+
+__global__ void eval_reemission_probabilities_kernel(int64_t n, const double *T, double *out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double p[NUM_REEMIT];
+  reemission_probabilities(T[i], p);
+  for (int k = 0; k < NUM_REEMIT; ++k) out[i * NUM_REEMIT + k] = p[k];
+}
+
+struct EvalStateParams {
+  int64_t n;
+  double jfac, hfac;
+  double abund[NUM_ELEMENTS];
+  RecombinationModel rr;
+  TemperatureParams tp;
+  const double *J, *heat, *ndens, *T, *cr_factor, *midz;
+  double *T_out, *x, *heat_out;
+  int solve_temperature;
+};
+
+__global__ void __launch_bounds__(128) eval_state_kernel(const __grid_constant__ EvalStateParams P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double J[NUM_IONS], heat[NUM_HEAT];
+  for (int k = 0; k < NUM_IONS; ++k) J[k] = P.J[k * P.n + i];
+  heat[0] = P.heat[i];
+  heat[1] = P.heat[P.n + i];
+  CellState out;
+  if (P.solve_temperature) {
+    double xprev[NUM_IONS];
+    for (int k = 0; k < NUM_IONS; ++k) xprev[k] = 0.;
+    cell_temperature(P.jfac, P.hfac, J, heat, P.ndens[i], P.T[i], P.cr_factor ? P.cr_factor[i] : -1.,
+                     P.midz ? P.midz[i] : 0., P.abund, P.rr, P.tp, xprev, out);
+  } else {
+    cell_ionization_state(P.jfac, P.hfac, J, heat, P.ndens[i], P.T[i], P.abund, P.rr, out);
+  }
+  if (P.T_out) P.T_out[i] = out.T;
+  for (int k = 0; k < NUM_IONS; ++k) P.x[k * P.n + i] = out.x[k];
+  P.heat_out[i] = out.heat[0];
+  P.heat_out[P.n + i] = out.heat[1];
+}
+
+struct EvalBalanceParams {
+  int64_t n;
+  double abund[NUM_ELEMENTS];
+  RecombinationModel rr;
+  double pahfac, crfac, crscale;
+  const double *T, *ndens, *j, *h, *midz;
+  double *h0, *he0, *gain, *loss, *metals;
+};
+
+__global__ void __launch_bounds__(128) eval_balance_kernel(const __grid_constant__ EvalBalanceParams P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  double j[NUM_IONS], h[NUM_HEAT], x[NUM_IONS];
+  for (int k = 0; k < NUM_IONS; ++k) { j[k] = P.j[i * NUM_IONS + k]; x[k] = 0.; }
+  h[0] = P.h[2 * i];
+  h[1] = P.h[2 * i + 1];
+  double h0, he0, gain, loss;
+  cooling_heating_balance(h0, he0, gain, loss, P.T[i], P.ndens[i], P.midz ? P.midz[i] : 0., j,
+                          P.abund, h, P.pahfac, P.crfac, P.crscale, P.rr, x);
+  P.h0[i] = h0; P.he0[i] = he0; P.gain[i] = gain; P.loss[i] = loss;
+  for (int k = 0; k < 12; ++k) P.metals[i * 12 + k] = x[2 + k];
+}
+
+struct SamplePacketsParams {
+  SourceModel src;
+  int64_t n;
+  uint64_t offset, seed;
+  uint32_t iteration;
+  double *pos, *dir, *nu, *sigma, *sigma_He_corr, *tau;
+};
+
+__global__ void sample_packets_kernel(const __grid_constant__ SamplePacketsParams P) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n) return;
+  const SourceModel &m = P.src;
+  PacketRng rng;
+  rng_init(rng, P.seed, P.iteration, P.offset + i);
+  double x = rng_uniform(rng);
+  x = rng_uniform(rng);
+  int isrc = 0;
+  while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
+  double dx, dy, dz;
+  random_direction(rng, dx, dy, dz);
+  const double nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+  double s[NUM_IONS], sHe;
+  packet_cross_sections<NUM_IONS>(m, nu, s, sHe);
+  const double tau = -log(rng_uniform(rng));
+  for (int k = 0; k < 3; ++k) P.pos[3 * i + k] = m.src_pos[3 * isrc + k];
+  P.dir[3 * i] = dx; P.dir[3 * i + 1] = dy; P.dir[3 * i + 2] = dz;
+  P.nu[i] = nu;
+  for (int k = 0; k < NUM_IONS; ++k) P.sigma[i * NUM_IONS + k] = s[k];
+  P.sigma_He_corr[i] = sHe;
+  P.tau[i] = tau;
+}
+
+__global__ void sample_spectrum_kernel(SourceModel m, int which, double T, uint64_t seed, int64_t n,
+                                       double *nu) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PacketRng rng;
+  rng_init(rng, seed, 0u, (uint64_t)i);
+  double v;
+  if (which == 0) v = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+  else if (which == 1) v = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
+  else if (which == 2) v = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng);
+  else v = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+  nu[i] = v;
+}
+
+} // namespace cmib

@@ -1,0 +1,210 @@
+/*
+ * source.cuh — photon packet emission and diffuse re-emission.
+ *
+ * Behavioural contract:
+ *   PhotonSource::get_random_photon        /root/reference/src/PhotonSource.cpp:208-249
+ *   PhotonSource::get_random_direction     /root/reference/src/PhotonSource.hpp:141-148
+ *   PhotonSource::set_cross_sections       /root/reference/src/PhotonSource.cpp:189-199
+ *   PhotonSource::reemit                   ...:272-308
+ *   MonochromaticPhotonSourceSpectrum::get_random_frequency  MonochromaticPhotonSourceSpectrum.hpp:97-100
+ *   PlanckPhotonSourceSpectrum::get_random_frequency         PlanckPhotonSourceSpectrum.cpp:149-165
+ *   HydrogenLymanContinuumSpectrum::get_random_frequency     HydrogenLymanContinuumSpectrum.cpp:136-154
+ *   HeliumLymanContinuumSpectrum::get_random_frequency       HeliumLymanContinuumSpectrum.cpp:147-165
+ *   HeliumTwoPhotonContinuumSpectrum::get_random_frequency   HeliumTwoPhotonContinuumSpectrum.cpp:167-178
+ *   PhysicalDiffuseReemissionHandler::reemit(Photon...)      PhysicalDiffuseReemissionHandler.cpp:219-370
+ *   PhysicalDiffuseReemissionHandler::set_reemission_probabilities  .hpp:66-106
+ *   FixedValueDiffuseReemissionHandler::reemit               FixedValueDiffuseReemissionHandler.hpp:88-101
+ *   Utilities::locate                      /root/reference/src/Utilities.hpp:726-742
+ *
+ * The order in which uniforms are consumed follows the reference exactly (one
+ * draw for discrete-vs-continuous even when there is no continuous source, one
+ * for the source index, two for the direction, 0/1 for the frequency, one for
+ * tau), so that a packet's stream means the same thing in both codes.
+ */
+#pragma once
+#include "cmib_common.cuh"
+#include "cross_sections.cuh"
+#include "rng.cuh"
+
+namespace cmib {
+
+enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1 };
+enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
+
+constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
+constexpr int LYC_NUMTEMP = 100;
+
+/* everything the emission / re-emission code needs; pointers are device pointers */
+struct SourceModel {
+  /* discrete sources (PhotonSource.cpp:74-100) */
+  int n_sources;
+  const double *src_pos;   /* [n_sources][3] */
+  const double *src_cum;   /* cumulative probabilities, last == 1 */
+  double continuous_probability; /* 0: discrete sources only */
+  double discrete_weight;        /* 1 */
+  /* source spectrum */
+  int spectrum_kind;
+  double mono_frequency;
+  const double *planck; /* [3][1000]: cdf, log10 cdf, log10 nu/13.6eV */
+  /* cross sections */
+  int xs_kind;
+  double xs_fixed[NUM_IONS];
+  double A_He;
+  /* diffuse re-emission */
+  int reemission_kind;
+  double fixed_reemission_probability;
+  double fixed_reemission_frequency;
+  const double *hlyc_freq, *hlyc_temp, *hlyc_cdf;    /* [1000], [100], [100][1000] */
+  const double *helyc_freq, *helyc_temp, *helyc_cdf; /* same shapes */
+  const double *he2pc_freq, *he2pc_cdf;              /* [1000], [1000] */
+};
+
+/* Utilities::locate: bisection, result clamped to [0, length-2] */
+CMIB_HD uint32_t locate(double x, const double *xarr, uint32_t length) {
+  uint32_t jl = 0, ju = length;
+  while (ju - jl > 1) {
+    const uint32_t jm = (ju + jl) >> 1;
+    if (x > xarr[jm]) jl = jm; else ju = jm;
+  }
+  if (jl == length - 1) --jl;
+  return jl;
+}
+
+CMIB_HD void random_direction(PacketRng &rng, double &dx, double &dy, double &dz) {
+  const double cost = 2. * rng_uniform(rng) - 1.;
+  const double s2 = 1. - cost * cost;
+  const double sint = sqrt(s2 > 0. ? s2 : 0.);
+  const double phi = 2. * M_PI * rng_uniform(rng);
+  double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &sinp, &cosp);
+#else
+  sinp = sin(phi);
+  cosp = cos(phi);
+#endif
+  dx = sint * cosp;
+  dy = sint * sinp;
+  dz = cost;
+}
+
+CMIB_HD double planck_frequency(const double *tab, PacketRng &rng) {
+  const double x = rng_uniform(rng);
+  const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
+  const uint32_t ix = locate(x, cdf, SPECTRUM_NUMFREQ);
+  const double lf = (log10(x) - logcdf[ix]) / (logcdf[ix + 1] - logcdf[ix]) *
+                        (lognu[ix + 1] - lognu[ix]) + lognu[ix];
+  return pow(10., lf) * 3.288465385e15;
+}
+
+CMIB_HD double lyc_frequency(const double *freq, const double *temp, const double *cdf, double T,
+                             PacketRng &rng) {
+  const uint32_t iT = locate(T, temp, LYC_NUMTEMP);
+  const double x = rng_uniform(rng);
+  const uint32_t inu1 = locate(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ);
+  const uint32_t inu2 = locate(x, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ);
+  return freq[inu1] + (T - temp[iT]) * (freq[inu2] - freq[inu1]) / (temp[iT + 1] - temp[iT]);
+}
+
+CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng &rng) {
+  const double x = rng_uniform(rng);
+  const uint32_t inu = locate(x, cdf, SPECTRUM_NUMFREQ);
+  return freq[inu] + (freq[inu + 1] - freq[inu]) * (x - cdf[inu]) / (cdf[inu + 1] - cdf[inu]);
+}
+
+/* the five cumulative re-emission probabilities of a cell at temperature T */
+CMIB_HD void reemission_probabilities(double T, double *p) {
+  const double T4 = T * 1.e-4;
+  const double alpha_1_H = 1.58e-13 * pow(T4, -0.53);
+  const double alpha_A_agn = 4.18e-13 * pow(T4, -0.7);
+  p[REEMIT_H] = alpha_1_H / alpha_A_agn;
+  const double alpha_1_He = 1.54e-13 * pow(T4, -0.486);
+  const double alpha_e_2tS = 2.1e-13 * pow(T4, -0.381);
+  const double alpha_e_2sS = 2.06e-14 * pow(T4, -0.451);
+  const double alpha_e_2sP = 4.17e-14 * pow(T4, -0.695);
+  const double alphaHe = alpha_1_He + alpha_e_2tS + alpha_e_2sS + alpha_e_2sP;
+  const double He_LyC = alpha_1_He / alphaHe;
+  const double He_NpEEv = He_LyC + alpha_e_2tS / alphaHe;
+  const double He_TPC = He_NpEEv + alpha_e_2sS / alphaHe;
+  const double He_LyA = He_TPC + alpha_e_2sP / alphaHe;
+  p[REEMIT_HE_LYC] = He_LyC;
+  p[REEMIT_HE_NPEEV] = He_NpEEv;
+  p[REEMIT_HE_TPC] = He_TPC;
+  p[REEMIT_HE_LYA] = He_LyA;
+}
+
+/* cross sections of a packet at frequency nu.  NSIG = 14 (all ions) or 1 (H only) */
+template <int NSIG>
+CMIB_HD void packet_cross_sections(const SourceModel &m, double nu, double *sigma,
+                                   double &sigma_He_corr) {
+  if (m.xs_kind == XS_VERNER) {
+    double sHe = 0.;
+#pragma unroll 1
+    for (int ion = 0; ion < NUM_IONS; ++ion) {
+      const double s = verner_cross_section(ion, nu);
+      if (ion < NSIG) sigma[ion] = s;
+      if (ion == ION_He_n) sHe = s;
+    }
+    sigma_He_corr = m.A_He * sHe;
+  } else {
+#pragma unroll
+    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = m.xs_fixed[ion];
+    sigma_He_corr = m.A_He * m.xs_fixed[ION_He_n];
+  }
+}
+
+/*
+ * Physical diffuse re-emission decision.  xH, xHe, T = state of the absorbing
+ * cell, p = its 5 cumulative probabilities.  Returns the new frequency (0 =
+ * packet absorbed) and the new packet type.
+ */
+CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigma_He, double xH,
+                               double xHe, double T, const double *p, PacketRng &rng, int &type) {
+  double nu = 0.;
+  const double nH0anuH0 = xH * sigma_H;
+  const double nHe0anuHe0 = xHe * m.A_He * sigma_He;
+  const double pHabs = nH0anuH0 / (nH0anuH0 + nHe0anuHe0);
+  double x = rng_uniform(rng);
+  type = PACKET_ABSORBED;
+  if (x <= pHabs) {
+    x = rng_uniform(rng);
+    if (x <= p[REEMIT_H]) {
+      nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
+      type = PACKET_DIFFUSE_HI;
+    }
+  } else {
+    x = rng_uniform(rng);
+    if (x <= p[REEMIT_HE_LYC]) {
+      nu = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng);
+      type = PACKET_DIFFUSE_HeI;
+    } else if (x <= p[REEMIT_HE_NPEEV]) {
+      nu = 4.788e15;
+      type = PACKET_DIFFUSE_HeI;
+    } else if (x <= p[REEMIT_HE_TPC]) {
+      x = rng_uniform(rng);
+      if (x < 0.56) {
+        nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+        type = PACKET_DIFFUSE_HeI;
+      }
+    } else if (x <= p[REEMIT_HE_LYA]) {
+      const double sqrtTnH0 = sqrt(T) * xH;
+      const double pHots = sqrtTnH0 / (sqrtTnH0 + 77. * xHe);
+      x = rng_uniform(rng);
+      if (x < pHots) {
+        x = rng_uniform(rng);
+        if (x <= p[REEMIT_H]) {
+          nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
+          type = PACKET_DIFFUSE_HI;
+        }
+      } else {
+        x = rng_uniform(rng);
+        if (x < 0.56) {
+          nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+          type = PACKET_DIFFUSE_HeI;
+        }
+      }
+    }
+  }
+  return nu;
+}
+
+} // namespace cmib

@@ -1,0 +1,421 @@
+/*
+ * state.cuh — per-cell ionization-state and temperature solve.
+ *
+ * Behavioural contract:
+ *   IonizationStateCalculator::calculate_ionization_state(jfac,hfac,cell)
+ *                                   /root/reference/src/IonizationStateCalculator.cpp:70-272
+ *   ::compute_ionization_states_hydrogen_helium                     ...:649-753
+ *   ::compute_ionization_state_hydrogen                             ...:802-820
+ *   ::compute_ionization_states_metals                              ...:323-501
+ *   TemperatureCalculator::compute_cooling_and_heating_balance
+ *                                   /root/reference/src/TemperatureCalculator.cpp:207-501
+ *   TemperatureCalculator::calculate_temperature(cell,...)          ...:567-931
+ *   grid-level dispatch (do_T && loop > min_iter)                   ...:944-970
+ *
+ * One thread owns one cell; everything stays in registers.  All quirks of the
+ * reference that affect the result are kept: the
+ * neutral branch of the ionization-only path sets N0/O0/Ne0 fractions to 1 while
+ * the temperature path sets them to 0, the metals written by the LAST balance
+ * evaluation (at the pre-update T0) are the ones that survive, etc.
+ */
+#pragma once
+#include "cmib_common.cuh"
+#include "linecooling.cuh"
+#include "rates.cuh"
+
+namespace cmib {
+
+struct TemperatureParams {
+  int do_temperature;          /* TemperatureCalculator:do temperature calculation */
+  uint32_t min_iterations;     /* :minimum number of iterations (T solve when loop > this) */
+  double epsilon;              /* :epsilon convergence */
+  uint32_t max_iterations;     /* :maximum number of iterations */
+  double pahfac;               /* :PAH heating factor */
+  double crfac;                /* :cosmic ray heating factor */
+  double crlim;                /* :cosmic ray heating limit */
+  double crscale;              /* :cosmic ray heating scale length (m) */
+  double min_ionized_T;        /* :minimum ionized temperature (K) */
+};
+
+/* result of one cell update: T, 14 fractions, 2 normalised heating terms */
+struct CellState {
+  double T;
+  double x[NUM_IONS];
+  double heat[NUM_HEAT];
+};
+
+CMIB_HD double ionization_state_hydrogen(double alphaH, double jH, double nH) {
+  if (jH > 0. && nH > 0.) {
+    const double aa = 0.5 * jH / (nH * alphaH);
+    const double bb = 2. / aa;
+    if (bb < 1.e-10) {
+      const double v = 0.25 * bb;
+      return (1.e-14 < v) ? v : 1.e-14; /* std::max(1e-14, v) */
+    }
+    const double cc = sqrt(bb + 1.);
+    const double v = 1. + aa * (1. - cc);
+    return (1.e-14 < v) ? v : 1.e-14;
+  }
+  return 1.;
+}
+
+/* coupled H/He fixed point; returns number of iterations (>20 flags the
+ * reference's "Too many iterations" fatal error, here reported not aborted) */
+CMIB_HD int ionization_states_hydrogen_helium(double alphaH, double alphaHe, double jH, double jHe,
+                                              double nH, double AHe, double T, double &h0,
+                                              double &he0) {
+  if (jH < 1.e-20) {
+    h0 = 1.;
+    he0 = 1.;
+    return 0;
+  }
+  const double alpha_e_2sP = 4.17e-20 * pow(T * 1.e-4, -0.861);
+  const double ch1 = alphaH * nH / jH;
+  const double ch2 = AHe * alpha_e_2sP * nH / jH;
+  double che = 0.;
+  if (jHe > 0.) che = alphaHe * nH / jHe;
+  double h0old = 0.99 * (1. - exp(-0.5 / ch1));
+  h0 = 0.9 * h0old;
+  double he0old = 1.;
+  if (che > 0.) {
+    he0old = 0.5 / che;
+    he0old = (1. < he0old) ? 1. : he0old; /* std::min(he0old, 1.) */
+  }
+  he0 = 0.;
+  int niter = 0;
+  const double sqrtT = sqrt(T);
+  while (fabs(h0 - h0old) > 1.e-4 * h0old && fabs(he0 - he0old) > 1.e-4 * he0old) {
+    ++niter;
+    h0old = h0;
+    he0old = (he0 > 0.) ? he0 : 0.;
+    const double pHots = 1. / (1. + 77. * he0old / sqrtT / h0old);
+    const double ch = ch1 - ch2 * AHe * (1. - he0old) * pHots / (1. - h0old);
+    he0 = 1.;
+    if (che != 0.) {
+      const double bhe = (1. + 2. * AHe - h0) * che + 1.;
+      const double che_bhe = che / bhe;
+      const double opAHeh0 = 1. + AHe - h0;
+      const double t1he = 4. * AHe * opAHeh0 * che_bhe * che_bhe;
+      if (t1he < 1.e-3) {
+        he0 = opAHeh0 * che_bhe;
+      } else {
+        he0 = (bhe - sqrt(bhe * bhe - 4. * AHe * opAHeh0 * che * che)) / (2. * AHe * che);
+      }
+    }
+    const double b = ch * (2. + AHe - he0 * AHe) + 1.;
+    const double ch_b = ch / b;
+    const double opAHeh0AHe = 1. + AHe - he0 * AHe;
+    const double t1 = 4. * ch_b * ch_b * opAHeh0AHe;
+    if (t1 < 1.e-3) {
+      h0 = ch_b * opAHeh0AHe;
+    } else {
+      h0 = (b - sqrt(b * b - 4. * ch * ch * opAHeh0AHe)) / (2. * ch);
+    }
+    if (niter > 10) {
+      h0 = 0.5 * (h0 + h0old);
+      he0 = 0.5 * (he0 + he0old);
+    }
+    if (niter > 20) break;
+  }
+  return niter;
+}
+
+/* metals ladder balance; jm = 12 normalised mean intensities C+ .. S+++ ;
+ * writes x[ION_C_p1 .. ION_S_p3] */
+CMIB_HD void ionization_states_metals(const double *jm, double ne, double T, double T4,
+                                      double nh0, double nhe0, double nhp,
+                                      const RecombinationModel &rr, double *x) {
+  {
+    const double a0 = recombination_rate(rr, ION_C_p1, T);
+    const double a1 = recombination_rate(rr, ION_C_p2, T);
+    const double C21 = jm[0] / (ne * a0);
+    const double C32 = jm[1] / (ne * a1 + nh0 * ct_recombination_H(ION_C_p2, T4) +
+                                nhe0 * ct_recombination_He(ION_C_p2, T4));
+    const double C31 = C32 * C21;
+    const double s = 1. / (1. + C21 + C31);
+    x[ION_C_p1] = C21 * s;
+    x[ION_C_p2] = C31 * s;
+  }
+  {
+    const double a0 = recombination_rate(rr, ION_N_n, T);
+    const double a1 = recombination_rate(rr, ION_N_p1, T);
+    const double a2 = recombination_rate(rr, ION_N_p2, T);
+    const double N21 = (jm[2] + nhp * ct_ionization_H(ION_N_n, T4)) /
+                       (ne * a0 + nh0 * ct_recombination_H(ION_N_n, T4));
+    const double N32 = jm[3] / (ne * a1 + nh0 * ct_recombination_H(ION_N_p1, T4) +
+                                nhe0 * ct_recombination_He(ION_N_p1, T4));
+    const double N43 = jm[4] / (ne * a2 + nh0 * ct_recombination_H(ION_N_p2, T4) +
+                                nhe0 * ct_recombination_He(ION_N_p2, T4));
+    const double N31 = N32 * N21;
+    const double N41 = N43 * N31;
+    const double s = 1. / (1. + N21 + N31 + N41);
+    x[ION_N_n] = N21 * s;
+    x[ION_N_p1] = N31 * s;
+    x[ION_N_p2] = N41 * s;
+  }
+  {
+    const double a0 = recombination_rate(rr, ION_O_n, T);
+    const double a1 = recombination_rate(rr, ION_O_p1, T);
+    const double O21 = (jm[5] + nhp * ct_ionization_H(ION_O_n, T4)) /
+                       (ne * a0 + nh0 * ct_recombination_H(ION_O_n, T4));
+    const double O32 = jm[6] / (ne * a1 + nh0 * ct_recombination_H(ION_O_p1, T4) +
+                                nhe0 * ct_recombination_He(ION_O_p1, T4));
+    const double O31 = O32 * O21;
+    const double s = 1. / (1. + O21 + O31);
+    x[ION_O_n] = O21 * s;
+    x[ION_O_p1] = O31 * s;
+  }
+  {
+    const double a0 = recombination_rate(rr, ION_Ne_n, T);
+    const double a1 = recombination_rate(rr, ION_Ne_p1, T);
+    const double Ne21 = jm[7] / (ne * a0);
+    const double Ne32 = jm[8] / (ne * a1 + nh0 * ct_recombination_H(ION_Ne_p1, T4) +
+                                 nhe0 * ct_recombination_He(ION_Ne_p1, T4));
+    const double Ne31 = Ne32 * Ne21;
+    const double s = 1. / (1. + Ne21 + Ne31);
+    x[ION_Ne_n] = Ne21 * s;
+    x[ION_Ne_p1] = Ne31 * s;
+  }
+  {
+    const double a0 = recombination_rate(rr, ION_S_p1, T);
+    const double a1 = recombination_rate(rr, ION_S_p2, T);
+    const double a2 = recombination_rate(rr, ION_S_p3, T);
+    const double S21 = jm[9] / (ne * a0 + nh0 * ct_recombination_H(ION_S_p1, T4));
+    const double S32 = jm[10] / (ne * a1 + nh0 * ct_recombination_H(ION_S_p2, T4) +
+                                 nhe0 * ct_recombination_He(ION_S_p2, T4));
+    const double S43 = jm[11] / (ne * a2 + nh0 * ct_recombination_H(ION_S_p3, T4) +
+                                 nhe0 * ct_recombination_He(ION_S_p3, T4));
+    const double S31 = S32 * S21;
+    const double S41 = S43 * S31;
+    const double s = 1. / (1. + S21 + S31 + S41);
+    x[ION_S_p1] = S21 * s;
+    x[ION_S_p2] = S31 * s;
+    x[ION_S_p3] = S41 * s;
+  }
+}
+
+/* ionization-only update (temperature fixed).  J / heat are the raw
+ * accumulators; jfac/hfac already divided by the cell volume. */
+CMIB_HD void cell_ionization_state(double jfac, double hfac, const double *J, const double *heat,
+                                   double ntot, double T, const double *abund,
+                                   const RecombinationModel &rr, CellState &out) {
+  const double jH = jfac * J[ION_H_n];
+  const double jHe = jfac * J[ION_He_n];
+  out.heat[HEAT_H] = hfac * heat[HEAT_H];
+  out.heat[HEAT_He] = hfac * heat[HEAT_He];
+  out.T = T;
+  if (jH > 0. && ntot > 0.) {
+    const double alphaH = recombination_rate(rr, ION_H_n, T);
+    const double AHe = abund[EL_He];
+    double h0, he0 = 0.;
+    if (AHe != 0.) {
+      const double alphaHe = recombination_rate(rr, ION_He_n, T);
+      ionization_states_hydrogen_helium(alphaH, alphaHe, jH, jHe, ntot, AHe, T, h0, he0);
+    } else {
+      h0 = ionization_state_hydrogen(alphaH, jH, ntot);
+    }
+    out.x[ION_H_n] = h0;
+    out.x[ION_He_n] = he0;
+    const double nhp = ntot * (1. - h0);
+    const double ne = ntot * (1. - h0 + AHe * (1. - he0));
+    const double T4 = T * 1.e-4;
+    double jm[12];
+#pragma unroll
+    for (int m = 0; m < 12; ++m) jm[m] = jfac * J[2 + m];
+    const double nh0 = ntot * h0;
+    const double nhe0 = ntot * he0 * AHe;
+    ionization_states_metals(jm, ne, T, T4, nh0, nhe0, nhp, rr, out.x);
+  } else if (ntot > 0.) {
+    /* neutral cell: note N0, O0, Ne0 = 1 here (IonizationStateCalculator.cpp:190-224) */
+#pragma unroll
+    for (int i = 0; i < NUM_IONS; ++i) out.x[i] = 0.;
+    out.x[ION_H_n] = 1.;
+    out.x[ION_He_n] = 1.;
+    out.x[ION_N_n] = 1.;
+    out.x[ION_O_n] = 1.;
+    out.x[ION_Ne_n] = 1.;
+  } else {
+#pragma unroll
+    for (int i = 0; i < NUM_IONS; ++i) out.x[i] = 0.;
+  }
+}
+
+/* heating/cooling balance at temperature T.  j[14], h[2] normalised.  Writes the
+ * 12 metal fractions into xm (index by Ion). */
+CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, double &loss, double T,
+                                     double n, double midz, const double *j, const double *abund,
+                                     const double *h, double pahfac, double crfac, double crscale,
+                                     const RecombinationModel &rr, double *xm) {
+  const double alphaH = recombination_rate(rr, ION_H_n, T);
+  const double alphaHe = recombination_rate(rr, ION_He_n, T);
+  const double jH = j[ION_H_n];
+  const double jHe = j[ION_He_n];
+  const double hH = h[HEAT_H];
+  const double hHe = h[HEAT_He];
+  const double T4 = T * 1.e-4;
+  const double sqrtT = sqrt(T);
+  const double logT = log(T);
+  const double AHe = abund[EL_He];
+
+  ionization_states_hydrogen_helium(alphaH, alphaHe, jH, jHe, n, AHe, T, h0, he0);
+
+  const double ne = n * (1. - h0 + AHe * (1. - he0));
+  const double nhp = n * (1. - h0);
+  const double nhep = (1. - he0) * n * AHe;
+  const double nenhp = ne * nhp;
+  const double nenhep = ne * nhep;
+
+  gain = n * (hH * h0 + hHe * AHe * he0);
+  const double alpha_e_2sP = 4.17e-20 * pow(T4, -0.861);
+  const double pHots = 1. / (1. + 77. * he0 / (sqrtT * h0));
+  gain += pHots * 1.21765423e-18 * alpha_e_2sP * nenhep;
+  gain += 1.5e-37 * n * ne * pahfac;
+  double heatcr = 0.;
+  if (crfac > 0.) {
+    heatcr = crfac * 1.2e-25 / sqrt(ne);
+    if (crscale > 0.) heatcr *= exp(-fabs(midz) / crscale);
+  }
+  gain += heatcr;
+
+  const double nh0 = n * h0;
+  const double nhe0 = n * he0 * AHe;
+  ionization_states_metals(j + 2, ne, T, T4, nh0, nhe0, nhp, rr, xm);
+
+  double ab[LC_NUM];
+  ab[LC_CII] = abund[EL_C] * (1. - xm[ION_C_p1] - xm[ION_C_p2]);
+  ab[LC_CIII] = abund[EL_C] * xm[ION_C_p1];
+  ab[LC_NI] = abund[EL_N] * (1. - xm[ION_N_n] - xm[ION_N_p1] - xm[ION_N_p2]);
+  ab[LC_NII] = abund[EL_N] * xm[ION_N_n];
+  ab[LC_NIII] = abund[EL_N] * xm[ION_N_p1];
+  ab[LC_OI] = abund[EL_O] * (1. - xm[ION_O_n] - xm[ION_O_p1]);
+  ab[LC_OII] = abund[EL_O] * xm[ION_O_n];
+  ab[LC_OIII] = abund[EL_O] * xm[ION_O_p1];
+  ab[LC_NeII] = abund[EL_Ne] * xm[ION_Ne_n];
+  ab[LC_NeIII] = abund[EL_Ne] * xm[ION_Ne_p1];
+  ab[LC_SII] = abund[EL_S] * (1. - xm[ION_S_p1] - xm[ION_S_p2] - xm[ION_S_p3]);
+  ab[LC_SIII] = abund[EL_S] * xm[ION_S_p1];
+  ab[LC_SIV] = abund[EL_S] * xm[ION_S_p2];
+
+  loss = line_cooling(T, ne, ab) * n;
+
+  const double c = 5.5 - logT;
+  const double gff = 1.1 + 0.34 * exp(-c * c / 3.);
+  loss += 1.42e-40 * gff * sqrtT * (nenhp + nenhep);
+  const double Lhp = 2.85e-40 * nenhp * sqrtT * (5.914 - 0.5 * logT + 0.01184 * cbrt(T));
+  const double Lhep = 1.55e-39 * nenhep * pow(T, 0.3647);
+  loss += Lhp + Lhep;
+  loss = (loss < 0.) ? 0. : loss; /* std::max(loss, 0.) */
+  gain = (gain < 0.) ? 0. : gain;
+}
+
+CMIB_HD void set_neutral_T(CellState &out) {
+  out.T = 500.;
+#pragma unroll
+  for (int i = 0; i < NUM_IONS; ++i) out.x[i] = 0.;
+  out.x[ION_H_n] = 1.;
+  out.x[ION_He_n] = 1.;
+  out.heat[HEAT_H] = 0.;
+  out.heat[HEAT_He] = 0.;
+}
+
+/* full temperature + ionization update of one cell; `xprev` = current metal
+ * fractions of the cell (kept when no balance evaluation overwrites them). */
+CMIB_HD void cell_temperature(double jfac, double hfac, const double *J, const double *heat,
+                              double ntot, double Tcell, double cr_factor, double midz,
+                              const double *abund, const RecombinationModel &rr,
+                              const TemperatureParams &tp, const double *xprev, CellState &out) {
+  const double jH = jfac * J[ION_H_n];
+  const double jHe = jfac * J[ION_He_n];
+  if ((jH == 0. && jHe == 0.) || ntot == 0.) {
+    set_neutral_T(out);
+    return;
+  }
+  double crfac = tp.crfac * cr_factor;
+  if (crfac < 0.) crfac = tp.crfac;
+  double h0, he0;
+  if (crfac > 0.) {
+    const double alphaH = recombination_rate(rr, ION_H_n, 8000.);
+    const double alphaHe = recombination_rate(rr, ION_He_n, 8000.);
+    ionization_states_hydrogen_helium(alphaH, alphaHe, jH, jHe, ntot, abund[EL_He], 8000., h0, he0);
+    if (h0 > tp.crlim) {
+      set_neutral_T(out);
+      return;
+    }
+  }
+  double T0 = Tcell;
+  if (Tcell <= 4000.) T0 = 8000.;
+  double j[NUM_IONS];
+#pragma unroll
+  for (int i = 0; i < NUM_IONS; ++i) j[i] = jfac * J[i];
+  double h[NUM_HEAT];
+  h[HEAT_H] = hfac * heat[HEAT_H];
+  h[HEAT_He] = hfac * heat[HEAT_He];
+#pragma unroll
+  for (int i = 0; i < NUM_IONS; ++i) out.x[i] = xprev[i];
+
+  uint32_t niter = 0;
+  double gain0 = 1.;
+  double loss0 = 0.;
+  h0 = 0.;
+  he0 = 0.;
+  const double logtt = log(1.1 / 0.9);
+  while (fabs(gain0 - loss0) > tp.epsilon * gain0 && niter < tp.max_iterations) {
+    ++niter;
+    const double T1 = 1.1 * T0;
+    double h01, he01, gain1, loss1;
+    cooling_heating_balance(h01, he01, gain1, loss1, T1, ntot, midz, j, abund, h, tp.pahfac, crfac,
+                            tp.crscale, rr, out.x);
+    const double T2 = 0.9 * T0;
+    double h02, he02, gain2, loss2;
+    cooling_heating_balance(h02, he02, gain2, loss2, T2, ntot, midz, j, abund, h, tp.pahfac, crfac,
+                            tp.crscale, rr, out.x);
+    cooling_heating_balance(h0, he0, gain0, loss0, T0, ntot, midz, j, abund, h, tp.pahfac, crfac,
+                            tp.crscale, rr, out.x);
+    double expgain;
+    if (gain2 > 0.) {
+      expgain = (gain1 > 0.) ? log(gain1 / gain2) : -99.;
+    } else {
+      expgain = (gain1 > 0.) ? 99. : 0.;
+    }
+    double exploss;
+    if (loss2 > 0.) {
+      exploss = (loss1 > 0.) ? log(loss1 / loss2) : -99.;
+    } else {
+      exploss = (loss1 > 0.) ? 99. : 0.;
+    }
+    const double expdiff = expgain - exploss;
+    if (gain0 > 0. && expdiff != 0.) {
+      T0 *= pow(loss0 / gain0, logtt / expdiff);
+    } else {
+      T0 = T1;
+    }
+    if (T0 < tp.min_ionized_T) {
+      T0 = 500.;
+      h0 = 1.;
+      he0 = 1.;
+      gain0 = 1.;
+      loss0 = 1.;
+    }
+    if (T0 > 1.e10) {
+      T0 = 1.e10;
+      h0 = 1.e-10;
+      he0 = 1.e-10;
+      gain0 = 1.;
+      loss0 = 1.;
+    }
+  }
+  T0 = (T0 < 30000.) ? T0 : 30000.; /* std::min(30000., T0) */
+  out.T = T0;
+  if (J[ION_H_n] == 0.) h0 = 1.;
+  if (J[ION_He_n] == 0.) he0 = 1.;
+  out.x[ION_H_n] = h0;
+  out.x[ION_He_n] = he0;
+  if (h0 == 1. || h0 <= 1.e-10) {
+#pragma unroll
+    for (int i = 2; i < NUM_IONS; ++i) out.x[i] = 0.;
+  }
+  out.heat[HEAT_H] = h[HEAT_H];
+  out.heat[HEAT_He] = h[HEAT_He];
+}
+
+} // namespace cmib

@@ -1,0 +1,219 @@
+/*
+ * cmib.h — C ABI of the B200-native photoionization hot path ("CMacIonize
+ * B200 backend").  This is the drop-in boundary: plain pointers and sizes, no
+ * C++ or torch types.  Every entry point names the reference interface it
+ * replaces (paths relative to the reference tree, bwvdnbro/CMacIonize).
+ *
+ * The reference has no fine-grained FFI for this path; the path sits behind C++
+ * abstract classes chosen by parameter-file `type:` strings and is driven by
+ * IonizationSimulation::run (src/IonizationSimulation.cpp:334-679).  The entry
+ * points below are what a maintainer would call from the bodies of those
+ * classes (INTEGRATION.md shows the shim for each).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error; cmib_last_error()
+ *    returns the message.  The reference aborts on every error
+ *    (src/Error.hpp:101-106 `cmac_error`); set CMIB_ABORT_ON_ERROR=1 in the
+ *    environment or call cmib_set_abort_on_error(1) for the same behaviour.
+ *  - all physical quantities are SI, exactly as inside the reference.
+ *  - host arrays belong to the caller, device memory to the library.
+ *  - per-cell arrays use the reference's cell order: long index
+ *    ix*ny*nz + iy*nz + iz (src/CartesianDensityGrid.hpp:137-144); per-ion
+ *    arrays are [ion][cell] with the reference's IonName order
+ *    (src/ElementNames.hpp:107-160): H0 He0 C+ C++ N0 N+ N++ O0 O+ Ne0 Ne+ S+
+ *    S++ S+++.
+ *  - one host thread per context; a context owns one CUDA stream on one device.
+ *  - there is NO CPU fallback: every call fails if no sm_100 device is present.
+ */
+#ifndef CMIB_H
+#define CMIB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMIB_ABI_VERSION 1
+#define CMIB_NUM_IONS 14
+#define CMIB_NUM_HEATING_TERMS 2
+#define CMIB_NUM_ELEMENTS 6 /* He C N O Ne S (src/ElementNames.hpp:52-88) */
+#define CMIB_NUM_REEMISSION_PROBABILITIES 5
+#define CMIB_NUM_PACKET_TYPES 4 /* src/PhotonType.hpp:41-56 */
+
+typedef struct cmib_context cmib_context;
+
+/* SimulationBox + CartesianDensityGrid constructor arguments
+ * (src/SimulationBox.hpp:63-72, src/CartesianDensityGrid.cpp:44-92) */
+typedef struct cmib_grid_desc {
+  double anchor[3];    /* SimulationBox:anchor (m) */
+  double sides[3];     /* SimulationBox:sides (m) */
+  int32_t ncell[3];    /* DensityGrid:number of cells */
+  int32_t periodic[3]; /* SimulationBox:periodicity */
+} cmib_grid_desc;
+
+/* plugin selectors (the reference's `type:` strings) */
+enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
+enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
+enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1 };
+enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
+
+/* TemperatureCalculator parameters (src/TemperatureCalculator.cpp:133-160) */
+typedef struct cmib_temperature_params {
+  int32_t do_temperature_calculation;
+  uint32_t minimum_number_of_iterations;
+  double epsilon_convergence;
+  uint32_t maximum_number_of_iterations;
+  double pah_heating_factor;
+  double cosmic_ray_heating_factor;
+  double cosmic_ray_heating_limit;
+  double cosmic_ray_heating_scale_length; /* m */
+  double minimum_ionized_temperature;     /* K */
+} cmib_temperature_params;
+
+/* ---- library / context ------------------------------------------------- */
+int cmib_abi_version(void);
+const char *cmib_last_error(void);
+void cmib_set_abort_on_error(int on);
+/* number of kernels this library has launched in this process (bench evidence) */
+uint64_t cmib_kernel_launch_count(void);
+
+/* replaces: CartesianDensityGrid::CartesianDensityGrid + DensityGrid::allocate_memory
+ * (src/CartesianDensityGrid.cpp:44-92, src/DensityGrid.hpp:235-259) */
+int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out);
+int cmib_destroy(cmib_context *ctx);
+int cmib_synchronize(cmib_context *ctx);
+
+/* ---- grid state -------------------------------------------------------- */
+/* replaces: DensityGrid::set_densities (src/DensityGrid.cpp:40-62, per-cell functor
+ * src/DensityGrid.hpp:775-790).  x is [14][ncell]; cosmic_ray_factor may be NULL
+ * (reference default -1, src/IonizationVariables.hpp:125). */
+int cmib_upload_cells(cmib_context *ctx, const double *number_density, const double *temperature,
+                      const double *ionic_fractions, const double *cosmic_ray_factor);
+/* replaces: the IonizationVariables getters a DensityGridWriter walks
+ * (src/IonizationVariables.hpp:226-345).  Any pointer may be NULL.  heating is
+ * [2][ncell], the normalised heating terms the state update leaves in the cell. */
+int cmib_download_cells(cmib_context *ctx, double *number_density, double *temperature,
+                        double *ionic_fractions, double *heating);
+/* raw mean-intensity / heating sums of the current iteration, J [14][ncell],
+ * heat [2][ncell] (IonizationVariables::get_mean_intensity / get_heating before
+ * normalisation).  Either may be NULL. */
+int cmib_download_accumulators(cmib_context *ctx, double *mean_intensity, double *heating);
+/* replaces: DensityGrid::reset_grid (src/DensityGrid.hpp:803-807) */
+int cmib_reset_accumulators(cmib_context *ctx);
+
+/* ---- plugins ----------------------------------------------------------- */
+/* Abundances (src/Abundances.hpp:53-76): He C N O Ne S relative to H */
+int cmib_set_abundances(cmib_context *ctx, const double abundances[CMIB_NUM_ELEMENTS]);
+/* CrossSectionsFactory (src/CrossSectionsFactory.hpp:60-80); fixed[14] in m^2 is read
+ * for FIXED_VALUE (src/FixedValueCrossSections.hpp), ignored for VERNER */
+int cmib_set_cross_sections(cmib_context *ctx, int kind, const double fixed[CMIB_NUM_IONS]);
+/* RecombinationRatesFactory (src/RecombinationRatesFactory.hpp:59-72); fixed[14] m^3 s^-1 */
+int cmib_set_recombination_rates(cmib_context *ctx, int kind, const double fixed[CMIB_NUM_IONS]);
+/* PhotonSourceDistribution -> PhotonSource (src/PhotonSource.cpp:55-146): positions
+ * [n][3] (m), weights [n] summing to 1 (checked to 1e-9 like the reference),
+ * total luminosity (s^-1) */
+int cmib_set_sources(cmib_context *ctx, int32_t n_sources, const double *positions,
+                     const double *weights, double total_luminosity);
+/* PhotonSourceSpectrumFactory (src/PhotonSourceSpectrumFactory.hpp:84-152): param is the
+ * frequency (Hz) for MONOCHROMATIC, the black-body temperature (K) for PLANCK */
+int cmib_set_spectrum(cmib_context *ctx, int kind, double param);
+/* DiffuseReemissionHandlerFactory (src/DiffuseReemissionHandlerFactory.hpp:59-107);
+ * probability / frequency (Hz) are used by FIXED_VALUE only.  Builds the H-Lyc /
+ * He-Lyc / He-2-photon tables from the CURRENT cross sections, as the reference's
+ * PhysicalDiffuseReemissionHandler constructor does: set cross sections first. */
+int cmib_set_reemission(cmib_context *ctx, int kind, double probability, double frequency);
+int cmib_set_temperature_params(cmib_context *ctx, const cmib_temperature_params *params);
+
+/* ---- one photoionization iteration (src/IonizationSimulation.cpp:359-643) ---- */
+/* replaces: DiffuseReemissionHandler::set_reemission_probabilities(grid)
+ * (src/PhysicalDiffuseReemissionHandler.hpp:66-106; call site IonizationSimulation.cpp:380-383) */
+int cmib_update_reemission_probabilities(cmib_context *ctx);
+/* replaces: WorkDistributor::do_in_parallel(IonizationPhotonShootJobMarket)
+ * (src/IonizationSimulation.cpp:399-406; per packet src/IonizationPhotonShootJob.hpp:117-146).
+ * Shoots packets with global ids [packet_offset, packet_offset + n_packets); the
+ * RNG stream of a packet depends only on (seed, iteration, global id), so
+ * splitting a batch over GPUs does not change which packets are drawn.
+ * totweight / typecount[4] (may be NULL: no host synchronisation then) receive
+ * this call's sums (IonizationPhotonShootJobMarket::update_counters). */
+int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, uint64_t seed,
+               uint32_t iteration, double *totweight, double *typecount);
+/* replaces: TemperatureCalculator::calculate_temperature(loop, totweight, grid, block)
+ * (src/TemperatureCalculator.cpp:944-970), i.e. the temperature solve when enabled
+ * and loop > minimum number of iterations, else
+ * IonizationStateCalculator::calculate_ionization_state (src/IonizationStateCalculator.cpp:511-530).
+ * totweight <= 0 means "use the device-side sum" (after an all-reduce of the
+ * accumulator buffer, so no host round trip is needed). */
+int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight);
+
+/* ---- multi-GPU plumbing ------------------------------------------------ */
+/* Device pointer + length (in doubles) of the contiguous buffer that must be
+ * sum-all-reduced between cmib_shoot and cmib_update_state: 8 counters
+ * (totweight, typecount[4], padding) followed by the per-cell accumulators.
+ * Replaces the 16 chunked MPI_Allreduce calls + 2 counter reductions of
+ * src/IonizationSimulation.cpp:410-416,458-529 with ONE collective. */
+int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_doubles);
+/* raw cudaStream_t of the context (for ordering an external collective) */
+int cmib_stream(cmib_context *ctx, void **stream);
+
+/* ---- test hooks (parity against the oracle on identical inputs) -------- */
+/* CartesianDensityGrid::interact on explicit packets (src/CartesianDensityGrid.cpp:375-452).
+ * pos/dir [np][3], sigma [np][14], sigma_He_corr/nu/weight/tau [np].  Accumulates
+ * into the context's accumulators (full 16-term layout is forced).  Outputs:
+ * final_pos [np][3], final_cell [np] (-1 = left the box), nsteps [np] (cells with
+ * n > 0 that received a contribution), trace [np][max_trace] visit order of those
+ * cells (-1 padded); trace may be NULL. */
+int cmib_march_packets(cmib_context *ctx, int64_t np, const double *pos, const double *dir,
+                       const double *sigma, const double *sigma_He_corr, const double *nu,
+                       const double *weight, const double *tau, double *final_pos,
+                       int64_t *final_cell, int32_t *nsteps, int32_t max_trace, int64_t *trace);
+/* PhotonSource::get_random_photon for packets [offset, offset+n): pos, dir [n][3],
+ * nu [n], sigma [n][14], sigma_He_corr [n], tau [n] (the first optical depth). */
+int cmib_sample_packets(cmib_context *ctx, int64_t n, uint64_t offset, uint64_t seed,
+                        uint32_t iteration, double *pos, double *dir, double *nu, double *sigma,
+                        double *sigma_He_corr, double *tau);
+/* CrossSections::get_cross_section for the current model; sigma [n][14] */
+int cmib_eval_cross_sections(cmib_context *ctx, int64_t n, const double *nu, double *sigma);
+/* RecombinationRates::get_recombination_rate; alpha [n][14] */
+int cmib_eval_recombination_rates(cmib_context *ctx, int64_t n, const double *T, double *alpha);
+/* ChargeTransferRates; out [n][3][14] = recombination-with-H, ionization-with-H,
+ * recombination-with-He as function of T4 = T/1e4 K */
+int cmib_eval_charge_transfer(cmib_context *ctx, int64_t n, const double *T4, double *out);
+/* LineCoolingData::get_cooling; abund [n][13] */
+int cmib_eval_line_cooling(cmib_context *ctx, int64_t n, const double *T, const double *ne,
+                           const double *abund, double *cooling);
+/* LineCoolingData::solve_system_of_linear_equations; A [n][25], B [n][5] in/out */
+int cmib_eval_solve5(cmib_context *ctx, int64_t n, double *A, double *B, int32_t *status);
+/* set_reemission_probabilities; out [n][5] */
+int cmib_eval_reemission_probabilities(cmib_context *ctx, int64_t n, const double *T, double *out);
+/* IonizationStateCalculator::calculate_ionization_state(jfac, hfac, cell) on SoA cells:
+ * J [14][n], heat [2][n], ndens [n], T [n] -> x [14][n], heat_out [2][n] */
+int cmib_eval_ionization_state(cmib_context *ctx, int64_t n, double jfac, double hfac,
+                               const double *J, const double *heat, const double *ndens,
+                               const double *T, double *x, double *heat_out);
+/* TemperatureCalculator::compute_cooling_and_heating_balance: j [n][14], h [n][2]
+ * normalised; outputs h0, he0, gain, loss [n], metals [n][12] */
+int cmib_eval_cooling_heating_balance(cmib_context *ctx, int64_t n, const double *T,
+                                      const double *ndens, const double *j, const double *h,
+                                      const double *midz, double *h0, double *he0, double *gain,
+                                      double *loss, double *metals);
+/* TemperatureCalculator::calculate_temperature(cell, jfac, hfac, midpoint): J [14][n],
+ * heat [2][n], ndens, T, cr_factor (NULL = -1), midz (NULL = 0) -> T_out, x [14][n],
+ * heat_out [2][n] */
+int cmib_eval_temperature(cmib_context *ctx, int64_t n, double jfac, double hfac, const double *J,
+                          const double *heat, const double *ndens, const double *T,
+                          const double *cr_factor, const double *midz, double *T_out, double *x,
+                          double *heat_out);
+/* spectrum tables as built on the host for the device (compare with the reference's):
+ * which 0 Planck [3][1000]; 1 H-Lyc, 2 He-Lyc: freq[1000] temp[100] cdf[100][1000];
+ * 3 He-2-photon: freq[1000] cdf[1000].  Unused outputs may be NULL. */
+int cmib_get_spectrum_tables(cmib_context *ctx, int which, double *a, double *b, double *c);
+/* sample n frequencies on the device: which 0 source spectrum, 1 H-Lyc(T), 2 He-Lyc(T),
+ * 3 He-2-photon */
+int cmib_sample_spectrum(cmib_context *ctx, int which, double temperature, uint64_t seed,
+                         int64_t n, double *nu);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CMIB_H */

@@ -1,0 +1,222 @@
+"""ctypes binding of ``oracle/_ref/libcmi_ref.so`` — the UNMODIFIED reference
+(CMacIonize) compiled by ``oracle/build_ref.py`` plus the probes of
+``oracle/ref_harness.cpp``.
+
+TEST INFRASTRUCTURE ONLY.  Allowed importers: ``tests/``,
+``__graft_entry__.smoke()``, ``bench.py`` (cpu_baseline / --impl reference).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+NUM_IONS = 14
+LIB_PATH = Path(__file__).resolve().parent / "_ref" / "libcmi_ref.so"
+
+_lib = None
+
+
+def available() -> bool:
+    return LIB_PATH.exists()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} missing: run `python oracle/build_ref.py`")
+        _lib = C.CDLL(str(LIB_PATH))
+        _lib.cmi_ref_run_paramfile.restype = C.c_int64
+        _lib.cmi_ref_convert.restype = C.c_double
+    return _lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _f(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None:
+        assert a.shape == tuple(shape), (a.shape, shape)
+    return a
+
+
+def max_threads() -> int:
+    return int(lib().cmi_ref_max_threads())
+
+
+def verner_cross_sections(nu):
+    nu = _f(nu).reshape(-1)
+    out = np.empty((nu.size, NUM_IONS))
+    lib().cmi_ref_verner_cross_sections(C.c_int64(nu.size), _p(nu), _p(out))
+    return out
+
+
+def verner_recombination_rates(T):
+    T = _f(T).reshape(-1)
+    out = np.empty((T.size, NUM_IONS))
+    lib().cmi_ref_verner_recombination_rates(C.c_int64(T.size), _p(T), _p(out))
+    return out
+
+
+def charge_transfer(T4):
+    T4 = _f(T4).reshape(-1)
+    out = np.empty((T4.size, 3, NUM_IONS))
+    lib().cmi_ref_charge_transfer(C.c_int64(T4.size), _p(T4), _p(out))
+    return out
+
+
+def linecooling_get_cooling(T, ne, abund):
+    T = _f(T).reshape(-1)
+    ne = _f(ne, (T.size,))
+    abund = _f(abund, (T.size, 13))
+    out = np.empty(T.size)
+    lib().cmi_ref_linecooling_get_cooling(C.c_int64(T.size), _p(T), _p(ne), _p(abund), _p(out))
+    return out
+
+
+def solve5(A, B):
+    A = _f(A).reshape(-1, 25).copy()
+    B = _f(B).reshape(-1, 5).copy()
+    st = np.empty(A.shape[0], dtype=np.int32)
+    lib().cmi_ref_solve5(C.c_int64(A.shape[0]), _p(A), _p(B), _p(st))
+    return A, B, st
+
+
+def reemission_probabilities(T):
+    T = _f(T).reshape(-1)
+    out = np.empty((T.size, 5))
+    lib().cmi_ref_reemission_probabilities(C.c_int64(T.size), _p(T), _p(out))
+    return out
+
+
+def interact(anchor, sides, ncell, periodic, cell_n, cell_xH, cell_xHe, pos, direction, sigma,
+             sigma_He_corr, nu, weight, tau, max_trace=0, J=None, heat=None):
+    anchor = _f(anchor, (3,)); sides = _f(sides, (3,))
+    ncell = np.ascontiguousarray(ncell, dtype=np.int32)
+    periodic = np.ascontiguousarray([1 if p else 0 for p in periodic], dtype=np.int32)
+    nc = int(ncell[0]) * int(ncell[1]) * int(ncell[2])
+    cell_n = _f(cell_n).reshape(-1); cell_xH = _f(cell_xH).reshape(-1)
+    cell_xHe = _f(cell_xHe).reshape(-1)
+    assert cell_n.size == nc
+    pos = _f(pos).reshape(-1, 3)
+    n = pos.shape[0]
+    direction = _f(direction, (n, 3)); sigma = _f(sigma, (n, NUM_IONS))
+    she = _f(sigma_He_corr, (n,)); nu = _f(nu, (n,)); w = _f(weight, (n,)); tau = _f(tau, (n,))
+    accumulate = 0
+    if J is None:
+        J = np.zeros((NUM_IONS, nc)); heat = np.zeros((2, nc))
+    else:
+        accumulate = 1
+    fpos = np.empty((n, 3)); fcell = np.empty(n, dtype=np.int64)
+    nsteps = np.empty(n, dtype=np.int32)
+    trace = np.empty((n, max_trace), dtype=np.int64) if max_trace > 0 else None
+    lib().cmi_ref_interact(_p(anchor), _p(sides), _p(ncell), _p(periodic), _p(cell_n), _p(cell_xH),
+                           _p(cell_xHe), C.c_int64(n), _p(pos), _p(direction), _p(sigma), _p(she),
+                           _p(nu), _p(w), _p(tau), C.c_int(accumulate), _p(J), _p(heat), _p(fpos),
+                           _p(fcell), _p(nsteps), C.c_int32(max_trace), _p(trace))
+    return dict(J=J, heat=heat, final_pos=fpos, final_cell=fcell, nsteps=nsteps, trace=trace)
+
+
+def ionization_state(jfac, hfac, abundances, rr_kind, rr_fixed, J, heat, ndens, T):
+    J = _f(J).reshape(NUM_IONS, -1)
+    n = J.shape[1]
+    heat = _f(heat, (2, n)); ndens = _f(ndens, (n,)); T = _f(T, (n,))
+    ab = _f(abundances, (6,))
+    rf = _f(rr_fixed if rr_fixed is not None else np.zeros(NUM_IONS), (NUM_IONS,))
+    x = np.empty((NUM_IONS, n)); ho = np.empty((2, n))
+    lib().cmi_ref_ionization_state(C.c_int64(n), C.c_double(jfac), C.c_double(hfac), _p(ab),
+                                   C.c_int(rr_kind), _p(rf), _p(J), _p(heat), _p(ndens), _p(T),
+                                   _p(x), _p(ho))
+    return x, ho
+
+
+def h_he_state(alphaH, alphaHe, jH, jHe, nH, AHe, T):
+    arrs = [_f(a).reshape(-1) for a in (alphaH, alphaHe, jH, jHe, nH, AHe, T)]
+    n = arrs[0].size
+    h0 = np.empty(n); he0 = np.empty(n)
+    lib().cmi_ref_h_he_state(C.c_int64(n), *[_p(a) for a in arrs], _p(h0), _p(he0))
+    return h0, he0
+
+
+def cooling_heating_balance(T, ndens, j, h, abundances, pahfac=0., crfac=0., crscale=0., midz=None,
+                            rr_kind=1, rr_fixed=None):
+    T = _f(T).reshape(-1)
+    n = T.size
+    ndens = _f(ndens, (n,)); j = _f(j, (n, NUM_IONS)); h = _f(h, (n, 2))
+    ab = _f(abundances, (6,))
+    rf = _f(rr_fixed if rr_fixed is not None else np.zeros(NUM_IONS), (NUM_IONS,))
+    mz = _f(midz, (n,)) if midz is not None else None
+    h0 = np.empty(n); he0 = np.empty(n); gain = np.empty(n); loss = np.empty(n)
+    metals = np.empty((n, 12))
+    lib().cmi_ref_cooling_heating_balance(C.c_int64(n), _p(T), _p(ndens), _p(j), _p(h), _p(ab),
+                                          C.c_double(pahfac), C.c_double(crfac),
+                                          C.c_double(crscale), _p(mz), C.c_int(rr_kind), _p(rf),
+                                          _p(h0), _p(he0), _p(gain), _p(loss), _p(metals))
+    return h0, he0, gain, loss, metals
+
+
+def temperature(jfac, hfac, abundances, J, heat, ndens, T, rr_kind=1, rr_fixed=None, pahfac=0.,
+                crfac=0., crlim=0.75, crscale=1.33333 * 3.086e19, min_ionized_T=4000., epsilon=1.e-3,
+                max_iterations=100, cr_factor=None, midz=None):
+    J = _f(J).reshape(NUM_IONS, -1)
+    n = J.shape[1]
+    heat = _f(heat, (2, n)); ndens = _f(ndens, (n,)); T = _f(T, (n,))
+    ab = _f(abundances, (6,))
+    rf = _f(rr_fixed if rr_fixed is not None else np.zeros(NUM_IONS), (NUM_IONS,))
+    tp = _f([pahfac, crfac, crlim, crscale, min_ionized_T, epsilon, float(max_iterations)])
+    cr = _f(cr_factor, (n,)) if cr_factor is not None else None
+    mz = _f(midz, (n,)) if midz is not None else None
+    To = np.empty(n); x = np.empty((NUM_IONS, n)); ho = np.empty((2, n))
+    lib().cmi_ref_temperature(C.c_int64(n), C.c_double(jfac), C.c_double(hfac), _p(ab),
+                              C.c_int(rr_kind), _p(rf), _p(tp), _p(J), _p(heat), _p(ndens), _p(T),
+                              _p(cr), _p(mz), _p(To), _p(x), _p(ho))
+    return To, x, ho
+
+
+def planck_tables(temperature):
+    out = np.empty((3, 1000))
+    lib().cmi_ref_planck_tables(C.c_double(temperature), _p(out))
+    return out
+
+
+def lyc_tables(which, xs_kind=1, xs_fixed=None):
+    xf = _f(xs_fixed if xs_fixed is not None else np.zeros(NUM_IONS), (NUM_IONS,))
+    f = np.empty(1000); t = np.empty(100); c = np.empty((100, 1000))
+    lib().cmi_ref_lyc_tables(C.c_int(which), C.c_int(xs_kind), _p(xf), _p(f), _p(t), _p(c))
+    return f, t, c
+
+
+def he2pc_tables():
+    f = np.empty(1000); c = np.empty(1000)
+    lib().cmi_ref_he2pc_tables(_p(f), _p(c))
+    return f, c
+
+
+def sample_spectrum(which, temperature, n, seed=42):
+    nu = np.empty(n)
+    lib().cmi_ref_sample_spectrum(C.c_int(which), C.c_double(temperature), C.c_int(seed),
+                                  C.c_int64(n), _p(nu))
+    return nu
+
+
+def convert(value, unit_from, unit_to):
+    return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
+
+
+def run_paramfile(path, ncells, num_threads=-1, verbose=False):
+    """Run the reference IonizationSimulation; returns (fields[32][ncell], times): n, T, x[14], J[14], heat[2]."""
+    fields = np.zeros((32, ncells))
+    times = np.zeros(2)
+    n = lib().cmi_ref_run_paramfile(str(path).encode(), C.c_int(num_threads),
+                                    C.c_int(1 if verbose else 0), _p(fields), C.c_int64(ncells),
+                                    _p(times))
+    if n != ncells:
+        raise RuntimeError(f"reference run returned {n} cells, expected {ncells}")
+    return fields, times

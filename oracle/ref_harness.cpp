@@ -1,0 +1,584 @@
+/*
+ * oracle/ref_harness.cpp — C-ABI probes into the UNMODIFIED CMacIonize reference.
+ *
+ * TEST INFRASTRUCTURE ONLY: compiled by oracle/build_ref.py together with the
+ * reference's own sources (where they lie under /root/reference/src) into
+ * oracle/_ref/libcmi_ref.so.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load that library.
+ * Nothing here is a restatement: every function below instantiates the
+ * reference's own classes and calls the reference's own methods, so the numbers
+ * it returns ARE the reference's numbers (parity pinned by construction, and
+ * additionally checked against the reference's golden files in tests/).
+ *
+ * Each probe names the reference entry point it drives.
+ */
+#include <algorithm>
+#include <cfloat>
+#include <cinttypes>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+#include <dlfcn.h>
+#include <omp.h>
+
+/* The probes need to read a few private members of the reference classes
+ * (timers, the grid owned by IonizationSimulation, spectrum tables).  GCC does
+ * not reorder members on access specifiers, so the object layout is identical to
+ * the one the reference translation units were compiled with. */
+#define private public
+#define protected public
+#include "Abundances.hpp"
+#include "CartesianDensityGrid.hpp"
+#include "ChargeTransferRates.hpp"
+#include "DensityGridWriter.hpp"
+#include "FixedValueCrossSections.hpp"
+#include "FixedValueRecombinationRates.hpp"
+#include "HeliumLymanContinuumSpectrum.hpp"
+#include "HeliumTwoPhotonContinuumSpectrum.hpp"
+#include "HomogeneousDensityFunction.hpp"
+#include "HydrogenLymanContinuumSpectrum.hpp"
+#include "IonizationSimulation.hpp"
+#include "IonizationStateCalculator.hpp"
+#include "LineCoolingData.hpp"
+#include "Photon.hpp"
+#include "PhotonSource.hpp"
+#include "PhysicalDiffuseReemissionHandler.hpp"
+#include "PlanckPhotonSourceSpectrum.hpp"
+#include "RandomGenerator.hpp"
+#include "TemperatureCalculator.hpp"
+#include "TerminalLog.hpp"
+#include "Tracker.hpp"
+#include "UnitConverter.hpp"
+#include "VernerCrossSections.hpp"
+#include "VernerRecombinationRates.hpp"
+#undef private
+#undef protected
+
+/* ---- data-file resolver used by the generated *DataLocation.hpp headers ---- */
+std::string cmi_ref_data_file(const char *name) {
+  const char *env = getenv("CMI_REF_DATA_DIR");
+  std::string dir;
+  if (env) {
+    dir = env;
+  } else {
+    Dl_info info;
+    if (dladdr((void *)&cmi_ref_data_file, &info) && info.dli_fname) {
+      std::string so(info.dli_fname);
+      size_t p = so.find_last_of('/');
+      dir = (p == std::string::npos ? std::string(".") : so.substr(0, p)) + "/data";
+    } else {
+      dir = "data";
+    }
+  }
+  std::string full = dir + "/" + name;
+  std::ifstream probe(full);
+  if (!probe.good()) {
+    fprintf(stderr, "cmi_ref: data file %s not found\n", full.c_str());
+    abort();
+  }
+  return full;
+}
+
+namespace {
+
+/* lazily constructed reference singletons (read-only after construction) */
+const VernerCrossSections &verner_xs() {
+  static VernerCrossSections xs;
+  return xs;
+}
+const VernerRecombinationRates &verner_rr() {
+  static VernerRecombinationRates rr;
+  return rr;
+}
+const ChargeTransferRates &ctr() {
+  static ChargeTransferRates c;
+  return c;
+}
+const LineCoolingData &lcd() {
+  static LineCoolingData l;
+  return l;
+}
+
+/* Tracker that records the order in which cells receive update_integrals()
+ * calls (DensityGrid.hpp:188-191 calls count_photon under the cell lock). */
+struct CellTrace {
+  std::vector<int64_t> *sink;
+};
+class CellOrderTracker : public Tracker {
+public:
+  int64_t _cell;
+  std::vector<int64_t> *_sink;
+  CellOrderTracker(int64_t cell, std::vector<int64_t> *sink) : _cell(cell), _sink(sink) {}
+  virtual Tracker *duplicate() { return new CellOrderTracker(_cell, _sink); }
+  virtual void merge(Tracker *) {}
+  virtual void count_photon(const Photon &) { _sink->push_back(_cell); }
+  virtual void count_photon(const PhotonPacket &, const double *) {}
+  virtual void output_tracker(const std::string) const {}
+};
+
+} // namespace
+
+extern "C" {
+
+int cmi_ref_abi_version(void) { return 1; }
+
+int cmi_ref_num_ions(void) { return NUMBER_OF_IONNAMES; }
+
+int cmi_ref_max_threads(void) { return omp_get_max_threads(); }
+
+/* ---------------------------------------------------------------------------
+ * a6: VernerCrossSections::get_cross_section (VernerCrossSections.cpp:259-322)
+ * sigma is [n][14] row-major (m^2); nu in Hz.
+ * ------------------------------------------------------------------------- */
+void cmi_ref_verner_cross_sections(int64_t n, const double *nu, double *sigma) {
+  const VernerCrossSections &xs = verner_xs();
+  for (int64_t i = 0; i < n; ++i)
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion)
+      sigma[i * NUMBER_OF_IONNAMES + ion] = xs.get_cross_section(ion, nu[i]);
+}
+
+/* a14: VernerRecombinationRates::get_recombination_rate
+ * (VernerRecombinationRates.cpp:157-333); alpha is [n][14] (m^3 s^-1). */
+void cmi_ref_verner_recombination_rates(int64_t n, const double *T, double *alpha) {
+  const VernerRecombinationRates &rr = verner_rr();
+  for (int64_t i = 0; i < n; ++i)
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion)
+      alpha[i * NUMBER_OF_IONNAMES + ion] = rr.get_recombination_rate(ion, T[i]);
+}
+
+/* ---------------------------------------------------------------------------
+ * a7-a9: CartesianDensityGrid::interact (CartesianDensityGrid.cpp:375-452) with
+ * DensityGrid::get_optical_depth / update_integrals (DensityGrid.hpp:117-197).
+ *
+ * Cells are given as SoA arrays in the reference's long-index order
+ * (ix*ny*nz + iy*nz + iz).  Packets are given explicitly: position,
+ * direction, the 14 cross sections, the abundance-corrected He cross section,
+ * frequency, weight and the target optical depth.  Packets are processed
+ * serially in order so the accumulation order is deterministic.
+ *
+ * Outputs: J [14][ncell], heat [2][ncell] (accumulated on top of the given
+ * contents when accumulate != 0, else zeroed first); final position [np][3];
+ * final cell long index (-1 when the packet left the box); number of cells
+ * visited with n > 0 (nsteps); optional per-packet cell trace: trace_cells is
+ * [np][max_trace], filled with the visit order (only cells with n > 0 are
+ * reported because the hook sits inside update_integrals), -1 padded.
+ * Returns 0.
+ * ------------------------------------------------------------------------- */
+int cmi_ref_interact(const double *anchor, const double *sides, const int32_t *ncell,
+                     const int32_t *periodic, const double *cell_n, const double *cell_xH,
+                     const double *cell_xHe, int64_t np, const double *pos, const double *dir,
+                     const double *sigma, const double *sigma_He_corr, const double *nu,
+                     const double *weight, const double *tau, int accumulate, double *J,
+                     double *heat, double *final_pos, int64_t *final_cell, int32_t *nsteps,
+                     int32_t max_trace, int64_t *trace_cells) {
+  Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]),
+            CoordinateVector<>(sides[0], sides[1], sides[2]));
+  CartesianDensityGrid grid(box, CoordinateVector<int_fast32_t>(ncell[0], ncell[1], ncell[2]),
+                            CoordinateVector<bool>(periodic[0] != 0, periodic[1] != 0,
+                                                   periodic[2] != 0),
+                            false, nullptr);
+  const int64_t nc = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  std::vector<int64_t> sink;
+  std::vector<CellOrderTracker *> trackers;
+  const bool want_steps = (nsteps != nullptr) || (max_trace > 0 && trace_cells != nullptr);
+  for (int64_t i = 0; i < nc; ++i) {
+    IonizationVariables &iv = grid._ionization_variables[i];
+    iv.set_number_density(cell_n[i]);
+    iv.set_ionic_fraction(ION_H_n, cell_xH[i]);
+    iv.set_ionic_fraction(ION_He_n, cell_xHe ? cell_xHe[i] : 0.);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion)
+      iv.set_mean_intensity(ion, accumulate ? J[ion * nc + i] : 0.);
+    iv.set_heating(HEATINGTERM_H, accumulate ? heat[i] : 0.);
+    iv.set_heating(HEATINGTERM_He, accumulate ? heat[nc + i] : 0.);
+    if (want_steps) {
+      trackers.push_back(new CellOrderTracker(i, &sink));
+      iv.add_tracker(trackers.back());
+    }
+  }
+  for (int64_t p = 0; p < np; ++p) {
+    Photon photon(CoordinateVector<>(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]),
+                  CoordinateVector<>(dir[3 * p], dir[3 * p + 1], dir[3 * p + 2]), nu[p]);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion)
+      photon.set_cross_section(ion, sigma[p * NUMBER_OF_IONNAMES + ion]);
+    photon.set_cross_section_He_corr(sigma_He_corr[p]);
+    photon.set_weight(weight[p]);
+    sink.clear();
+    DensityGrid::iterator it = grid.interact(photon, tau[p]);
+    const CoordinateVector<> fp = photon.get_position();
+    final_pos[3 * p] = fp.x();
+    final_pos[3 * p + 1] = fp.y();
+    final_pos[3 * p + 2] = fp.z();
+    final_cell[p] = (it == grid.end()) ? -1 : (int64_t)it.get_index();
+    if (nsteps) nsteps[p] = (int32_t)sink.size();
+    if (max_trace > 0 && trace_cells) {
+      for (int32_t k = 0; k < max_trace; ++k)
+        trace_cells[p * max_trace + k] = (k < (int32_t)sink.size()) ? sink[k] : -1;
+    }
+  }
+  for (int64_t i = 0; i < nc; ++i) {
+    IonizationVariables &iv = grid._ionization_variables[i];
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) J[ion * nc + i] = iv.get_mean_intensity(ion);
+    heat[i] = iv.get_heating(HEATINGTERM_H);
+    heat[nc + i] = iv.get_heating(HEATINGTERM_He);
+    iv.add_tracker(nullptr); /* do not let ~IonizationVariables free ours twice */
+  }
+  for (size_t i = 0; i < trackers.size(); ++i) delete trackers[i];
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------
+ * a1: IonizationSimulation (IonizationSimulation.cpp:101-679) on a parameter
+ * file, with an in-process DensityGridWriter that captures every field.
+ *
+ * fields is [32][ncell]: n, T, x[14], raw J[14] of the last iteration, normalised
+ * heat[2]; the caller passes the ncell capacity.
+ * Returns number of cells, or <0 on error.  times[0] = "Total photon shooting
+ * time" (s), times[1] = "Total cell update time" (s) — the reference's own
+ * timers (IonizationSimulation.cpp:667-674).
+ * ------------------------------------------------------------------------- */
+namespace {
+class CaptureWriter : public DensityGridWriter {
+public:
+  double *_out;
+  int64_t _cap;
+  int64_t _n;
+  CaptureWriter(double *out, int64_t cap)
+      : DensityGridWriter(".", false, DensityGridWriterFields(false), nullptr), _out(out),
+        _cap(cap), _n(0) {}
+  virtual void write(DensityGrid &grid, uint_fast32_t, ParameterFile &, double,
+                     const InternalHydroUnits *) {
+    _n = grid.get_number_of_cells();
+    if (_n > _cap) return;
+    for (auto it = grid.begin(); it != grid.end(); ++it) {
+      const int64_t i = it.get_index();
+      const IonizationVariables &iv = it.get_ionization_variables();
+      _out[0 * _n + i] = iv.get_number_density();
+      _out[1 * _n + i] = iv.get_temperature();
+      for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) {
+        _out[(2 + ion) * _n + i] = iv.get_ionic_fraction(ion);
+        _out[(16 + ion) * _n + i] = iv.get_mean_intensity(ion);
+      }
+      _out[30 * _n + i] = iv.get_heating(HEATINGTERM_H);
+      _out[31 * _n + i] = iv.get_heating(HEATINGTERM_He);
+    }
+  }
+  virtual void write(DensitySubGridCreator<DensitySubGrid> &, const uint_fast32_t,
+                     ParameterFile &, double) {}
+  virtual void write(DensitySubGridCreator<HydroDensitySubGrid> &, const uint_fast32_t,
+                     ParameterFile &, double) {}
+};
+} // namespace
+
+int64_t cmi_ref_run_paramfile(const char *paramfile, int num_threads, int verbose,
+                              double *fields, int64_t ncell_capacity, double *times) {
+  TerminalLog *log = verbose ? new TerminalLog(LOGLEVEL_STATUS) : nullptr;
+  int64_t n = -1;
+  {
+    IonizationSimulation simulation(false, false, false, num_threads, paramfile, nullptr, log);
+    simulation.initialize();
+    CaptureWriter writer(fields, ncell_capacity);
+    simulation.run(&writer);
+    n = writer._n;
+    if (times) {
+      times[0] = simulation._photon_propagation_timer.value();
+      times[1] = simulation._cell_update_timer.value();
+    }
+  }
+  delete log;
+  return n;
+}
+
+
+/* ---------------------------------------------------------------------------
+ * Charge transfer (ChargeTransferRates.cpp:44-395).  out is [n][3][14]:
+ * [0] recombination with H, [1] ionization with H, [2] recombination with He;
+ * entries the reference refuses to evaluate (H with itself, He with itself)
+ * are returned as 0.
+ * ------------------------------------------------------------------------- */
+void cmi_ref_charge_transfer(int64_t n, const double *T4, double *out) {
+  const ChargeTransferRates &c = ctr();
+  for (int64_t i = 0; i < n; ++i) {
+    double *o = out + i * 3 * NUMBER_OF_IONNAMES;
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) {
+      o[ion] = (ion == ION_H_n) ? 0. : c.get_charge_transfer_recombination_rate_H(ion, T4[i]);
+      o[NUMBER_OF_IONNAMES + ion] =
+          (ion == ION_H_n) ? 0. : c.get_charge_transfer_ionization_rate_H(ion, T4[i]);
+      o[2 * NUMBER_OF_IONNAMES + ion] =
+          (ion == ION_He_n) ? 0. : c.get_charge_transfer_recombination_rate_He(ion, T4[i]);
+    }
+  }
+}
+
+/* ---------------------------------------------------------------------------
+ * LineCoolingData constants (LineCoolingData.cpp:42-1394), flattened:
+ *   cs5[10][10][7], A5[10][10], E5[10][10], invw5[10][5],
+ *   cs2[3][7], A2[3], E2[3], invw2[3][2], prefactor      (984 doubles)
+ * Used once by tools/gen_linecooling_data.py to carry the atomic data.
+ * ------------------------------------------------------------------------- */
+int cmi_ref_linecooling_tables(double *out, int capacity) {
+  const LineCoolingData &l = lcd();
+  int k = 0;
+  if (capacity < 984) return -1;
+  for (int e = 0; e < 10; ++e)
+    for (int t = 0; t < 10; ++t)
+      for (int c = 0; c < 7; ++c) out[k++] = l._five_level_collision_strength[e][t][c];
+  for (int e = 0; e < 10; ++e)
+    for (int t = 0; t < 10; ++t) out[k++] = l._five_level_transition_probability[e][t];
+  for (int e = 0; e < 10; ++e)
+    for (int t = 0; t < 10; ++t) out[k++] = l._five_level_energy_difference[e][t];
+  for (int e = 0; e < 10; ++e)
+    for (int t = 0; t < 5; ++t) out[k++] = l._five_level_inverse_statistical_weight[e][t];
+  for (int e = 0; e < 3; ++e)
+    for (int c = 0; c < 7; ++c) out[k++] = l._two_level_collision_strength[e][c];
+  for (int e = 0; e < 3; ++e) out[k++] = l._two_level_transition_probability[e];
+  for (int e = 0; e < 3; ++e) out[k++] = l._two_level_energy_difference[e];
+  for (int e = 0; e < 3; ++e)
+    for (int t = 0; t < 2; ++t) out[k++] = l._two_level_inverse_statistical_weight[e][t];
+  out[k++] = l._collision_strength_prefactor;
+  return k;
+}
+
+/* LineCoolingData::get_cooling (LineCoolingData.cpp:1767-1848); abund is [n][13]
+ * in LineCoolingData element order (NI NII OI OII OIII NeIII SII SIII CII CIII
+ * NIII NeII SIV). */
+void cmi_ref_linecooling_get_cooling(int64_t n, const double *T, const double *ne,
+                                     const double *abund, double *cooling) {
+  const LineCoolingData &l = lcd();
+  for (int64_t i = 0; i < n; ++i)
+    cooling[i] = l.get_cooling(T[i], ne[i], abund + i * LINECOOLINGDATA_NUMELEMENTS);
+}
+
+/* LineCoolingData::solve_system_of_linear_equations (:1492-1555); A is [n][25],
+ * B is [n][5], both overwritten; status [n]. */
+void cmi_ref_solve5(int64_t n, double *A, double *B, int32_t *status) {
+  for (int64_t i = 0; i < n; ++i) {
+    double a[5][5];
+    memcpy(a, A + 25 * i, sizeof(a));
+    status[i] = LineCoolingData::solve_system_of_linear_equations(a, B + 5 * i);
+    memcpy(A + 25 * i, a, sizeof(a));
+  }
+}
+
+/* PhysicalDiffuseReemissionHandler::set_reemission_probabilities
+ * (PhysicalDiffuseReemissionHandler.hpp:66-106); out is [n][5]. */
+void cmi_ref_reemission_probabilities(int64_t n, const double *T, double *out) {
+  static PhysicalDiffuseReemissionHandler *handler = nullptr;
+  if (!handler) handler = new PhysicalDiffuseReemissionHandler(verner_xs());
+  for (int64_t i = 0; i < n; ++i) {
+    IonizationVariables iv;
+    iv.set_temperature(T[i]);
+    handler->set_reemission_probabilities(iv);
+    for (int k = 0; k < NUMBER_OF_REEMISSIONPROBABILITIES; ++k)
+      out[i * NUMBER_OF_REEMISSIONPROBABILITIES + k] = iv.get_reemission_probability(k);
+  }
+}
+
+namespace {
+struct RatesHolder {
+  RecombinationRates *rates;
+  bool owned;
+  RatesHolder(int kind, const double *fixed) {
+    if (kind == 1) {
+      rates = const_cast<VernerRecombinationRates *>(&verner_rr());
+      owned = false;
+    } else {
+      rates = new FixedValueRecombinationRates(fixed[0], fixed[1], fixed[2], fixed[3], fixed[4],
+                                               fixed[5], fixed[6], fixed[7], fixed[8], fixed[9],
+                                               fixed[10], fixed[11], fixed[12], fixed[13]);
+      owned = true;
+    }
+  }
+  ~RatesHolder() {
+    if (owned) delete rates;
+  }
+};
+} // namespace
+
+/* ---------------------------------------------------------------------------
+ * a13/a14: IonizationStateCalculator::calculate_ionization_state(jfac, hfac,
+ * cell) (IonizationStateCalculator.cpp:70-272).  SoA inputs J[14][n],
+ * heat[2][n], ndens[n], T[n]; abundances[6] = He C N O Ne S; rr_kind 1 = Verner,
+ * 0 = FixedValue(rr_fixed[14]).  Outputs x[14][n], heat_out[2][n].
+ * ------------------------------------------------------------------------- */
+void cmi_ref_ionization_state(int64_t n, double jfac, double hfac, const double *abundances,
+                              int rr_kind, const double *rr_fixed, const double *J,
+                              const double *heat, const double *ndens, const double *T,
+                              double *x, double *heat_out) {
+  Abundances ab(abundances[0], abundances[1], abundances[2], abundances[3], abundances[4],
+                abundances[5]);
+  RatesHolder rh(rr_kind, rr_fixed);
+  IonizationStateCalculator calc(1., ab, *rh.rates, ctr());
+  for (int64_t i = 0; i < n; ++i) {
+    IonizationVariables iv;
+    iv.set_number_density(ndens[i]);
+    iv.set_temperature(T[i]);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) iv.set_mean_intensity(ion, J[ion * n + i]);
+    iv.set_heating(HEATINGTERM_H, heat[i]);
+    iv.set_heating(HEATINGTERM_He, heat[n + i]);
+    calc.calculate_ionization_state(jfac, hfac, iv);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) x[ion * n + i] = iv.get_ionic_fraction(ion);
+    heat_out[i] = iv.get_heating(HEATINGTERM_H);
+    heat_out[n + i] = iv.get_heating(HEATINGTERM_He);
+  }
+}
+
+/* IonizationStateCalculator::compute_ionization_states_hydrogen_helium (:649-753) */
+void cmi_ref_h_he_state(int64_t n, const double *alphaH, const double *alphaHe, const double *jH,
+                        const double *jHe, const double *nH, const double *AHe, const double *T,
+                        double *h0, double *he0) {
+  for (int64_t i = 0; i < n; ++i)
+    IonizationStateCalculator::compute_ionization_states_hydrogen_helium(
+        alphaH[i], alphaHe[i], jH[i], jHe[i], nH[i], AHe[i], T[i], h0[i], he0[i]);
+}
+
+/* ---------------------------------------------------------------------------
+ * a15: TemperatureCalculator::compute_cooling_and_heating_balance
+ * (TemperatureCalculator.cpp:207-501).  j is [n][14] ALREADY normalised, h is
+ * [n][2] already normalised.  Outputs h0, he0, gain, loss [n], metals [n][12].
+ * ------------------------------------------------------------------------- */
+void cmi_ref_cooling_heating_balance(int64_t n, const double *T, const double *ndens,
+                                     const double *j, const double *h, const double *abundances,
+                                     double pahfac, double crfac, double crscale,
+                                     const double *midz, int rr_kind, const double *rr_fixed,
+                                     double *h0, double *he0, double *gain, double *loss,
+                                     double *metals) {
+  Abundances ab(abundances[0], abundances[1], abundances[2], abundances[3], abundances[4],
+                abundances[5]);
+  RatesHolder rh(rr_kind, rr_fixed);
+  for (int64_t i = 0; i < n; ++i) {
+    IonizationVariables iv;
+    iv.set_number_density(ndens[i]);
+    TemperatureCalculator::compute_cooling_and_heating_balance(
+        h0[i], he0[i], gain[i], loss[i], T[i], iv,
+        CoordinateVector<>(0., 0., midz ? midz[i] : 0.), j + i * NUMBER_OF_IONNAMES, ab,
+        h + i * NUMBER_OF_HEATINGTERMS, pahfac, crfac, crscale, lcd(), *rh.rates, ctr());
+    for (int m = 0; m < 12; ++m) metals[i * 12 + m] = iv.get_ionic_fraction(2 + m);
+  }
+}
+
+/* ---------------------------------------------------------------------------
+ * a15: TemperatureCalculator::calculate_temperature(cell, jfac, hfac, midpoint)
+ * (TemperatureCalculator.cpp:567-931).  SoA inputs J[14][n], heat[2][n],
+ * ndens[n], T[n], cr_factor[n] (may be NULL = 1), midz[n] (may be NULL = 0).
+ * tparams = {pahfac, crfac, crlim, crscale, minimum_ionized_temperature,
+ *            epsilon_convergence, maximum_number_of_iterations}.
+ * Outputs T_out[n], x[14][n], heat_out[2][n].
+ * ------------------------------------------------------------------------- */
+void cmi_ref_temperature(int64_t n, double jfac, double hfac, const double *abundances,
+                         int rr_kind, const double *rr_fixed, const double *tparams,
+                         const double *J, const double *heat, const double *ndens,
+                         const double *T, const double *cr_factor, const double *midz,
+                         double *T_out, double *x, double *heat_out) {
+  Abundances ab(abundances[0], abundances[1], abundances[2], abundances[3], abundances[4],
+                abundances[5]);
+  RatesHolder rh(rr_kind, rr_fixed);
+  TemperatureCalculator calc(true, 0, 1., ab, tparams[5], (uint_fast32_t)tparams[6], tparams[0],
+                             tparams[1], tparams[2], tparams[3], tparams[4], lcd(), *rh.rates,
+                             ctr(), nullptr);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = 0; i < n; ++i) {
+    IonizationVariables iv;
+    iv.set_number_density(ndens[i]);
+    iv.set_temperature(T[i]);
+    if (cr_factor) iv.set_cosmic_ray_factor(cr_factor[i]);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) iv.set_mean_intensity(ion, J[ion * n + i]);
+    iv.set_heating(HEATINGTERM_H, heat[i]);
+    iv.set_heating(HEATINGTERM_He, heat[n + i]);
+    calc.calculate_temperature(iv, jfac, hfac, CoordinateVector<>(0., 0., midz ? midz[i] : 0.));
+    T_out[i] = iv.get_temperature();
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) x[ion * n + i] = iv.get_ionic_fraction(ion);
+    heat_out[i] = iv.get_heating(HEATINGTERM_H);
+    heat_out[n + i] = iv.get_heating(HEATINGTERM_He);
+  }
+}
+
+/* ---------------------------------------------------------------------------
+ * Spectrum tables as the reference builds them.
+ *  Planck (PlanckPhotonSourceSpectrum.cpp:53-115): out [3][1000] = cdf, logcdf, lognu
+ *  H-Lyc / He-Lyc (HydrogenLymanContinuumSpectrum.cpp:40-122,
+ *    HeliumLymanContinuumSpectrum.cpp): freq[1000], temp[100], cdf[100][1000];
+ *    xs_kind 1 = Verner cross sections, 0 = FixedValue(xs_fixed[14])
+ *  He two-photon (HeliumTwoPhotonContinuumSpectrum.cpp:44-101): freq[1000], cdf[1000]
+ * ------------------------------------------------------------------------- */
+void cmi_ref_planck_tables(double temperature, double *out) {
+  PlanckPhotonSourceSpectrum sp(temperature, -1., nullptr);
+  for (int i = 0; i < 1000; ++i) {
+    out[i] = sp._cumulative_distribution[i];
+    out[1000 + i] = sp._log_cumulative_distribution[i];
+    out[2000 + i] = sp._log_frequency[i];
+  }
+}
+
+namespace {
+CrossSections *make_xs(int xs_kind, const double *f) {
+  if (xs_kind == 1) return new VernerCrossSections();
+  return new FixedValueCrossSections(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], f[9],
+                                     f[10], f[11], f[12], f[13]);
+}
+} // namespace
+
+void cmi_ref_lyc_tables(int which /*0 = H, 1 = He*/, int xs_kind, const double *xs_fixed,
+                        double *freq, double *temp, double *cdf) {
+  CrossSections *xs = make_xs(xs_kind, xs_fixed);
+  if (which == 0) {
+    HydrogenLymanContinuumSpectrum sp(*xs);
+    for (int i = 0; i < 1000; ++i) freq[i] = sp._frequency[i];
+    for (int t = 0; t < 100; ++t) {
+      temp[t] = sp._temperature[t];
+      for (int i = 0; i < 1000; ++i) cdf[t * 1000 + i] = sp._cumulative_distribution[t][i];
+    }
+  } else {
+    HeliumLymanContinuumSpectrum sp(*xs);
+    for (int i = 0; i < 1000; ++i) freq[i] = sp._frequency[i];
+    for (int t = 0; t < 100; ++t) {
+      temp[t] = sp._temperature[t];
+      for (int i = 0; i < 1000; ++i) cdf[t * 1000 + i] = sp._cumulative_distribution[t][i];
+    }
+  }
+  delete xs;
+}
+
+void cmi_ref_he2pc_tables(double *freq, double *cdf) {
+  HeliumTwoPhotonContinuumSpectrum sp;
+  for (int i = 0; i < 1000; ++i) {
+    freq[i] = sp._frequency[i];
+    cdf[i] = sp._cumulative_distribution[i];
+  }
+}
+
+/* Sample n frequencies from a reference spectrum with the reference's own RNG
+ * (statistical parity of the samplers).  which: 0 Planck(T), 1 H-Lyc(T) Verner,
+ * 2 He-Lyc(T) Verner, 3 He two-photon. */
+void cmi_ref_sample_spectrum(int which, double temperature, int seed, int64_t n, double *nu) {
+  RandomGenerator rg(seed);
+  if (which == 0) {
+    PlanckPhotonSourceSpectrum sp(temperature, -1., nullptr);
+    for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, 0.);
+  } else if (which == 1) {
+    HydrogenLymanContinuumSpectrum sp(verner_xs());
+    for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, temperature);
+  } else if (which == 2) {
+    HeliumLymanContinuumSpectrum sp(verner_xs());
+    for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, temperature);
+  } else {
+    HeliumTwoPhotonContinuumSpectrum sp;
+    for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, temperature);
+  }
+}
+
+/* UnitConverter::to_SI for a quantity given by its SI unit name, e.g.
+ * ("13.6", "eV" -> "Hz").  Used to pin the host-side unit parser. */
+double cmi_ref_convert(double value, const char *unit_from, const char *unit_to) {
+  return UnitConverter::convert(value, unit_from, unit_to);
+}
+
+} /* extern "C" */

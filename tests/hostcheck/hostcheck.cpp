@@ -1,0 +1,221 @@
+/*
+ * tests/hostcheck/hostcheck.cpp — TEST INFRASTRUCTURE ONLY.
+ *
+ * Compiles the product's __host__ __device__ physics headers
+ * (cmacionize_b200/csrc/*.cuh) with plain g++ so that their logic can be
+ * checked against the oracle and the reference's golden vectors on machines
+ * without a GPU (the `-m "not gpu"` tier).  It is NOT a CPU fallback: nothing
+ * under cmacionize_b200/ loads this library, and the product's entry points
+ * fail when no B200 is present.  The GPU tier (`-m gpu`) repeats every one of
+ * these checks through the real C ABI on the device.
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../cmacionize_b200/csrc/march.cuh"
+#include "../../cmacionize_b200/csrc/source.cuh"
+#include "../../cmacionize_b200/csrc/spectrum_tables.hpp"
+#include "../../cmacionize_b200/csrc/state.cuh"
+
+using namespace cmib;
+
+extern "C" {
+
+void hc_verner_cross_sections(int64_t n, const double *nu, double *sigma) {
+  for (int64_t i = 0; i < n; ++i)
+    for (int k = 0; k < NUM_IONS; ++k) sigma[i * NUM_IONS + k] = verner_cross_section(k, nu[i]);
+}
+
+void hc_verner_recombination_rates(int64_t n, const double *T, double *alpha) {
+  for (int64_t i = 0; i < n; ++i)
+    for (int k = 0; k < NUM_IONS; ++k) alpha[i * NUM_IONS + k] = verner_recombination_rate(k, T[i]);
+}
+
+void hc_charge_transfer(int64_t n, const double *T4, double *out) {
+  for (int64_t i = 0; i < n; ++i) {
+    double *o = out + i * 3 * NUM_IONS;
+    for (int k = 0; k < NUM_IONS; ++k) {
+      o[k] = (k == ION_H_n) ? 0. : ct_recombination_H(k, T4[i]);
+      o[NUM_IONS + k] = ct_ionization_H(k, T4[i]);
+      o[2 * NUM_IONS + k] = ct_recombination_He(k, T4[i]);
+    }
+  }
+}
+
+void hc_line_cooling(int64_t n, const double *T, const double *ne, const double *abund, double *c) {
+  for (int64_t i = 0; i < n; ++i) c[i] = line_cooling(T[i], ne[i], abund + i * LC_NUM);
+}
+
+void hc_solve5(int64_t n, double *A, double *B, int32_t *status) {
+  for (int64_t i = 0; i < n; ++i) {
+    double a[5][5];
+    memcpy(a, A + 25 * i, sizeof(a));
+    status[i] = solve5(a, B + 5 * i);
+    memcpy(A + 25 * i, a, sizeof(a));
+  }
+}
+
+void hc_reemission_probabilities(int64_t n, const double *T, double *out) {
+  for (int64_t i = 0; i < n; ++i) reemission_probabilities(T[i], out + i * NUM_REEMIT);
+}
+
+static RecombinationModel make_rr(int kind, const double *fixed) {
+  RecombinationModel rr;
+  rr.kind = kind;
+  for (int k = 0; k < NUM_IONS; ++k) rr.fixed[k] = fixed ? fixed[k] : 0.;
+  return rr;
+}
+
+void hc_ionization_state(int64_t n, double jfac, double hfac, const double *abund, int rr_kind,
+                         const double *rr_fixed, const double *J, const double *heat,
+                         const double *ndens, const double *T, double *x, double *heat_out) {
+  const RecombinationModel rr = make_rr(rr_kind, rr_fixed);
+  for (int64_t i = 0; i < n; ++i) {
+    double j[NUM_IONS], h[2];
+    for (int k = 0; k < NUM_IONS; ++k) j[k] = J[k * n + i];
+    h[0] = heat[i];
+    h[1] = heat[n + i];
+    CellState out;
+    cell_ionization_state(jfac, hfac, j, h, ndens[i], T[i], abund, rr, out);
+    for (int k = 0; k < NUM_IONS; ++k) x[k * n + i] = out.x[k];
+    heat_out[i] = out.heat[0];
+    heat_out[n + i] = out.heat[1];
+  }
+}
+
+void hc_h_he_state(int64_t n, const double *alphaH, const double *alphaHe, const double *jH,
+                   const double *jHe, const double *nH, const double *AHe, const double *T,
+                   double *h0, double *he0) {
+  for (int64_t i = 0; i < n; ++i)
+    ionization_states_hydrogen_helium(alphaH[i], alphaHe[i], jH[i], jHe[i], nH[i], AHe[i], T[i],
+                                      h0[i], he0[i]);
+}
+
+void hc_cooling_heating_balance(int64_t n, const double *T, const double *ndens, const double *j,
+                                const double *h, const double *abund, double pahfac, double crfac,
+                                double crscale, const double *midz, int rr_kind,
+                                const double *rr_fixed, double *h0, double *he0, double *gain,
+                                double *loss, double *metals) {
+  const RecombinationModel rr = make_rr(rr_kind, rr_fixed);
+  for (int64_t i = 0; i < n; ++i) {
+    double x[NUM_IONS] = {0.};
+    cooling_heating_balance(h0[i], he0[i], gain[i], loss[i], T[i], ndens[i], midz ? midz[i] : 0.,
+                            j + i * NUM_IONS, abund, h + 2 * i, pahfac, crfac, crscale, rr, x);
+    for (int k = 0; k < 12; ++k) metals[i * 12 + k] = x[2 + k];
+  }
+}
+
+void hc_temperature(int64_t n, double jfac, double hfac, const double *abund, int rr_kind,
+                    const double *rr_fixed, const double *tparams, const double *J,
+                    const double *heat, const double *ndens, const double *T,
+                    const double *cr_factor, const double *midz, double *T_out, double *x,
+                    double *heat_out) {
+  const RecombinationModel rr = make_rr(rr_kind, rr_fixed);
+  TemperatureParams tp;
+  tp.do_temperature = 1;
+  tp.min_iterations = 0;
+  tp.pahfac = tparams[0];
+  tp.crfac = tparams[1];
+  tp.crlim = tparams[2];
+  tp.crscale = tparams[3];
+  tp.min_ionized_T = tparams[4];
+  tp.epsilon = tparams[5];
+  tp.max_iterations = (uint32_t)tparams[6];
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int64_t i = 0; i < n; ++i) {
+    double j[NUM_IONS], h[2], xprev[NUM_IONS] = {0.};
+    for (int k = 0; k < NUM_IONS; ++k) j[k] = J[k * n + i];
+    h[0] = heat[i];
+    h[1] = heat[n + i];
+    CellState out;
+    cell_temperature(jfac, hfac, j, h, ndens[i], T[i], cr_factor ? cr_factor[i] : -1.,
+                     midz ? midz[i] : 0., abund, rr, tp, xprev, out);
+    T_out[i] = out.T;
+    for (int k = 0; k < NUM_IONS; ++k) x[k * n + i] = out.x[k];
+    heat_out[i] = out.heat[0];
+    heat_out[n + i] = out.heat[1];
+  }
+}
+
+void hc_planck_tables(double temperature, double *out) {
+  std::vector<double> t;
+  host::build_planck_table(temperature, t);
+  memcpy(out, t.data(), t.size() * sizeof(double));
+}
+
+void hc_lyc_tables(int which, int xs_kind, const double *xs_fixed, double *freq, double *temp,
+                   double *cdf) {
+  std::vector<double> f, t, c;
+  const int ion = which == 0 ? ION_H_n : ION_He_n;
+  host::build_lyc_table(which,
+                        [=](double nu) {
+                          return xs_kind == XS_VERNER ? verner_cross_section(ion, nu) : xs_fixed[ion];
+                        },
+                        f, t, c);
+  memcpy(freq, f.data(), f.size() * sizeof(double));
+  memcpy(temp, t.data(), t.size() * sizeof(double));
+  memcpy(cdf, c.data(), c.size() * sizeof(double));
+}
+
+void hc_he2pc_tables(double *freq, double *cdf) {
+  std::vector<double> f, c;
+  host::build_he2pc_table(f, c);
+  memcpy(freq, f.data(), f.size() * sizeof(double));
+  memcpy(cdf, c.data(), c.size() * sizeof(double));
+}
+
+/* the voxel walk on explicit packets, serial, full 16-term accumulation */
+void hc_march_packets(const double *anchor, const double *sides, const int32_t *ncell,
+                      const int32_t *periodic, const double *cell_n, const double *cell_xH,
+                      const double *cell_xHe, int64_t np, const double *pos, const double *dir,
+                      const double *sigma, const double *sigma_He_corr, const double *nu,
+                      const double *weight, const double *tau, double *J, double *heat,
+                      double *final_pos, int64_t *final_cell, int32_t *nsteps, int32_t max_trace,
+                      int64_t *trace) {
+  GridGeom g;
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = anchor[d];
+    g.sides[d] = sides[d];
+    g.ncell[d] = ncell[d];
+    g.periodic[d] = periodic[d];
+    g.cellside[d] = sides[d] / ncell[d];
+    g.inv_cellside[d] = 1. / g.cellside[d];
+  }
+  g.ncells = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  const int64_t nc = g.ncells;
+  const double nu_H = (13.6 * ELECTRONVOLT) * (1. / PLANCK);
+  const double nu_He = (24.6 * ELECTRONVOLT) * (1. / PLANCK);
+  for (int64_t p = 0; p < np; ++p) {
+    MarchState s;
+    s.px = pos[3 * p]; s.py = pos[3 * p + 1]; s.pz = pos[3 * p + 2];
+    s.dx = dir[3 * p]; s.dy = dir[3 * p + 1]; s.dz = dir[3 * p + 2];
+    s.ix_ = 1. / s.dx; s.iy_ = 1. / s.dy; s.iz_ = 1. / s.dz;
+    s.tau = tau[p];
+    const double *sg = sigma + p * NUM_IONS;
+    march_locate(g, s);
+    int32_t ns = 0;
+    bool inside;
+    while ((inside = march_inside(g, s)) && s.tau > 0.) {
+      const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
+      s.last_cell = cell;
+      const double ds = march_step(g, s, cell_n[cell], cell_xH[cell], cell_xHe[cell], sg[0],
+                                   sigma_He_corr[p]);
+      if (cell_n[cell] > 0.) {
+        const double dsw = ds * weight[p];
+        for (int k = 0; k < NUM_IONS; ++k) J[k * nc + cell] += dsw * sg[k];
+        heat[cell] += dsw * sg[ION_H_n] * (nu[p] - nu_H);
+        heat[nc + cell] += dsw * sg[ION_He_n] * (nu[p] - nu_He);
+        if (trace && ns < max_trace) trace[p * max_trace + ns] = cell;
+        ++ns;
+      }
+    }
+    final_pos[3 * p] = s.px; final_pos[3 * p + 1] = s.py; final_pos[3 * p + 2] = s.pz;
+    final_cell[p] = inside ? s.last_cell : -1;
+    nsteps[p] = ns;
+    if (trace)
+      for (int32_t k = ns; k < max_trace; ++k) trace[p * max_trace + k] = -1;
+  }
+}
+
+} /* extern "C" */
