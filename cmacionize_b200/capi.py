@@ -218,6 +218,12 @@ class Context:
     def update_state(self, loop, totweight=0.):
         _check(lib.cmib_update_state(self._h, C.c_uint32(loop), C.c_double(totweight)))
 
+    def shoot_statistics(self):
+        a = C.c_double(0.)
+        b = C.c_double(0.)
+        _check(lib.cmib_shoot_statistics(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def accumulator_buffer(self):
         ptr = _vp()
         n = C.c_uint64()

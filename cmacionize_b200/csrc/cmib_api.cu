@@ -561,6 +561,17 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   return 0;
 }
 
+int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  double c[8];
+  CUDA_OK(cudaMemcpyAsync(c, ctx->acc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  if (cell_crossings) *cell_crossings = c[5];
+  if (emissions) *emissions = c[6];
+  return 0;
+}
+
 int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_doubles) {
   CHECK_CTX(ctx);
   if (ensure_acc(ctx)) return 1;

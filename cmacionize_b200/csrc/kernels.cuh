@@ -22,7 +22,7 @@
 namespace cmib {
 
 enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
-constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], 3 pad: keeps cells 64-B aligned */
+constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, pad */
 
 template <int MODE> struct AccLayout;
 template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
@@ -82,6 +82,7 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
   const SourceModel &m = P.src;
   double w_tot = 0.;
   double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
+  uint32_t n_steps = 0, n_emit = 0; /* diagnostics for the roofline: cell crossings, (re)emissions */
 
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_packets; i += stride) {
@@ -108,6 +109,7 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
 
     bool alive = true;
     while (alive) {
+      ++n_emit;
       s.ix_ = 1. / s.dx;
       s.iy_ = 1. / s.dy;
       s.iz_ = 1. / s.dz;
@@ -125,6 +127,7 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
         c.n = r0.x; c.xH = r0.y; c.xHe = r1.x; c.T = r1.y;
         const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
         if (c.n > 0.) accumulate<MODE>(P.acc, cell, ds, weight, sigma, dnu_H, dnu_He);
+        ++n_steps;
       }
       if (!inside) break; /* left the box: keeps its last type */
       /* --- PhotonSource::reemit --- */
@@ -161,17 +164,17 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
   }
 
   /* IonizationPhotonShootJobMarket::update_counters: block reduce, one RED per block */
-  __shared__ double red[5][8];
+  __shared__ double red[7][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[5] = {w_tot, w_type[0], w_type[1], w_type[2], w_type[3]};
+  double v[7] = {w_tot, w_type[0], w_type[1], w_type[2], w_type[3], (double)n_steps, (double)n_emit};
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
+  for (int k = 0; k < 7; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) red[k][warp] = v[k];
   }
   __syncthreads();
-  if (threadIdx.x < 5) {
+  if (threadIdx.x < 7) {
     double sum = 0.;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[threadIdx.x][w];
     if (sum != 0.) red_add(P.acc + threadIdx.x, sum);

@@ -146,10 +146,16 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
  * accumulator buffer, so no host round trip is needed). */
 int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight);
 
+/* diagnostics of the shoots since the last cmib_reset_accumulators: number of
+ * packet-cell crossings (the unit of work of the roofline) and of
+ * (re-)emissions.  No reference counterpart (gprof call counts were used there). */
+int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions);
+
 /* ---- multi-GPU plumbing ------------------------------------------------ */
 /* Device pointer + length (in doubles) of the contiguous buffer that must be
  * sum-all-reduced between cmib_shoot and cmib_update_state: 8 counters
- * (totweight, typecount[4], padding) followed by the per-cell accumulators.
+ * (totweight, typecount[4], cell crossings, emissions, padding) followed by the
+ * per-cell accumulators.
  * Replaces the 16 chunked MPI_Allreduce calls + 2 counter reductions of
  * src/IonizationSimulation.cpp:410-416,458-529 with ONE collective. */
 int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_doubles);

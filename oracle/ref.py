@@ -220,3 +220,45 @@ def run_paramfile(path, ncells, num_threads=-1, verbose=False):
     if n != ncells:
         raise RuntimeError(f"reference run returned {n} cells, expected {ncells}")
     return fields, times
+
+
+class Simulation:
+    """The reference IonizationSimulation driven one iteration at a time (probe
+    cmi_ref_sim_*: the loop body of IonizationSimulation::run on the reference's objects)."""
+
+    def __init__(self, paramfile, num_threads=-1):
+        L = lib()
+        L.cmi_ref_sim_create.restype = C.c_void_p
+        L.cmi_ref_sim_number_of_cells.restype = C.c_int64
+        self._h = C.c_void_p(L.cmi_ref_sim_create(str(paramfile).encode(), C.c_int(num_threads)))
+        self.ncells = int(L.cmi_ref_sim_number_of_cells(self._h))
+        self.threads = int(L.cmi_ref_sim_threads(self._h))
+
+    def iteration(self, loop, numphoton):
+        out = np.zeros(8)
+        lib().cmi_ref_sim_iteration(self._h, C.c_uint32(loop), C.c_uint64(int(numphoton)), _p(out))
+        return dict(shoot_s=out[0], update_s=out[1], totweight=out[2], typecount=out[3:7].copy(),
+                    prep_s=out[7])
+
+    def fields(self):
+        f = np.empty((32, self.ncells))
+        lib().cmi_ref_sim_get_fields(self._h, _p(f))
+        return f
+
+    def set_state(self, n, T, x):
+        f = np.empty((16, self.ncells))
+        f[0] = n
+        f[1] = T
+        f[2:16] = x
+        lib().cmi_ref_sim_set_state(self._h, _p(f))
+
+    def close(self):
+        if self._h:
+            lib().cmi_ref_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

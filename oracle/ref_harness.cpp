@@ -581,4 +581,103 @@ double cmi_ref_convert(double value, const char *unit_from, const char *unit_to)
   return UnitConverter::convert(value, unit_from, unit_to);
 }
 
+
+/* ---------------------------------------------------------------------------
+ * Step-by-step driving of the reference IonizationSimulation: the body of the
+ * `while (loop < _number_of_iterations)` loop of IonizationSimulation::run
+ * (IonizationSimulation.cpp:359-643, MPI branches excluded) executed one
+ * iteration per call ON THE REFERENCE'S OWN OBJECTS, so that each phase can be
+ * timed separately and the grid state can be read or replaced in between.
+ *   reset_grid                                   :379
+ *   set_reemission_probabilities(grid)           :380-383
+ *   set_numphoton + do_in_parallel(shoot market) :399-404
+ *   update_counters                              :406
+ *   calculate_temperature(loop, totweight, ...)  :532-533
+ * out[0] = shoot seconds, out[1] = state-update seconds, out[2] = totweight,
+ * out[3..6] = typecount, out[7] = reset + reemission-probability seconds.
+ * ------------------------------------------------------------------------- */
+struct cmi_ref_sim {
+  IonizationSimulation *sim;
+  std::pair<cellsize_t, cellsize_t> block;
+};
+
+void *cmi_ref_sim_create(const char *paramfile, int num_threads) {
+  cmi_ref_sim *h = new cmi_ref_sim();
+  h->sim = new IonizationSimulation(false, false, false, num_threads, paramfile, nullptr, nullptr);
+  h->sim->initialize();
+  h->block = std::make_pair((cellsize_t)0, h->sim->_density_grid->get_number_of_cells());
+  return h;
+}
+
+void cmi_ref_sim_destroy(void *handle) {
+  cmi_ref_sim *h = (cmi_ref_sim *)handle;
+  delete h->sim;
+  delete h;
+}
+
+int64_t cmi_ref_sim_number_of_cells(void *handle) {
+  return ((cmi_ref_sim *)handle)->sim->_density_grid->get_number_of_cells();
+}
+
+int cmi_ref_sim_threads(void *handle) { return ((cmi_ref_sim *)handle)->sim->_num_thread; }
+
+int cmi_ref_sim_iteration(void *handle, uint32_t loop, uint64_t numphoton, double *out) {
+  IonizationSimulation &s = *((cmi_ref_sim *)handle)->sim;
+  Timer t_prep, t_shoot, t_update;
+  t_prep.start();
+  s._density_grid->reset_grid(*s._density_function);
+  if (s._photon_source->get_reemission_handler())
+    s._photon_source->get_reemission_handler()->set_reemission_probabilities(*s._density_grid);
+  t_prep.stop();
+  double typecount[PHOTONTYPE_NUMBER] = {0};
+  double totweight = 0.;
+  s._ionization_photon_shoot_job_market->set_numphoton(numphoton);
+  t_shoot.start();
+  s._work_distributor.do_in_parallel(*s._ionization_photon_shoot_job_market);
+  t_shoot.stop();
+  s._ionization_photon_shoot_job_market->update_counters(totweight, typecount);
+  t_update.start();
+  s._temperature_calculator->calculate_temperature(loop, totweight, *s._density_grid,
+                                                   ((cmi_ref_sim *)handle)->block);
+  t_update.stop();
+  out[0] = t_shoot.value();
+  out[1] = t_update.value();
+  out[2] = totweight;
+  for (int k = 0; k < PHOTONTYPE_NUMBER; ++k) out[3 + k] = typecount[k];
+  out[7] = t_prep.value();
+  return 0;
+}
+
+/* fields [32][ncell]: n, T, x[14], raw J[14] (of the last shoot), heat[2] */
+void cmi_ref_sim_get_fields(void *handle, double *fields) {
+  DensityGrid &grid = *((cmi_ref_sim *)handle)->sim->_density_grid;
+  const int64_t n = grid.get_number_of_cells();
+  for (auto it = grid.begin(); it != grid.end(); ++it) {
+    const int64_t i = it.get_index();
+    const IonizationVariables &iv = it.get_ionization_variables();
+    fields[0 * n + i] = iv.get_number_density();
+    fields[1 * n + i] = iv.get_temperature();
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) {
+      fields[(2 + ion) * n + i] = iv.get_ionic_fraction(ion);
+      fields[(16 + ion) * n + i] = iv.get_mean_intensity(ion);
+    }
+    fields[30 * n + i] = iv.get_heating(HEATINGTERM_H);
+    fields[31 * n + i] = iv.get_heating(HEATINGTERM_He);
+  }
+}
+
+/* overwrite n, T, x[14] of every cell (fields [16][ncell]) */
+void cmi_ref_sim_set_state(void *handle, const double *fields) {
+  DensityGrid &grid = *((cmi_ref_sim *)handle)->sim->_density_grid;
+  const int64_t n = grid.get_number_of_cells();
+  for (auto it = grid.begin(); it != grid.end(); ++it) {
+    const int64_t i = it.get_index();
+    IonizationVariables &iv = it.get_ionization_variables();
+    iv.set_number_density(fields[0 * n + i]);
+    iv.set_temperature(fields[1 * n + i]);
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion)
+      iv.set_ionic_fraction(ion, fields[(2 + ion) * n + i]);
+  }
+}
+
 } /* extern "C" */

@@ -1,0 +1,168 @@
+"""GPU tier: the fused shoot kernel (emission + walk + accumulation + re-emission).
+
+Self-generated packets cannot be compared bitwise (different RNG by design, and
+CUDA's sin/cos/log differ from glibc's in the last ulp — SURVEY.md §7), so:
+  * the packets the shoot kernel would draw are exported with cmib_sample_packets
+    and pushed through the ORACLE's interact(): shoot's accumulators must equal the
+    oracle's on those same packets (this pins emission -> walk -> accumulate
+    end to end, at full 1e-6 parity);
+  * sampling distributions are checked statistically against the reference's own
+    samplers and analytic expectations (the reference's tests do the same,
+    test/testPhotonSource.cpp:92-131, test/testPhotonSourceSpectrum.cpp:153-305).
+"""
+import numpy as np
+import pytest
+
+from cases import ABUNDANCES
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+PC = 3.086e16
+
+
+def test_shoot_equals_oracle_on_the_same_packets(cmib, ref):
+    """No re-emission: shoot == sample_packets -> oracle interact, cell by cell."""
+    from cmacionize_b200 import problems
+    prob = problems.stromgren(ncell=32, n_packets=20000)
+    ctx = prob.ctx
+    rng = np.random.default_rng(3)
+    n = prob.number_density * np.exp(rng.normal(0, 0.5, ctx.ncells))
+    x = prob.ionic_fractions.copy()
+    x[0] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), ctx.ncells))
+    ctx.upload_cells(n, prob.temperature, x)
+    ctx.reset_accumulators()
+    tw, tc = ctx.shoot(20000, seed=7, iteration=3)
+    J, heat = ctx.download_accumulators()
+    pk = ctx.sample_packets(20000, seed=7, iteration=3)
+    r = ref.interact([-5 * PC] * 3, [10 * PC] * 3, [32] * 3, [0, 0, 0], n, x[0], x[1], pk["pos"],
+                     pk["dir"], pk["sigma"], pk["sigma_He_corr"], pk["nu"], np.ones(20000), pk["tau"])
+    scale = r["J"][0].max()
+    assert np.abs(J[0] - r["J"][0]).max() <= 1e-11 * scale
+    assert np.array_equal(J[1:], np.zeros_like(J[1:]))
+    assert tw == 20000.
+    absorbed = (r["final_cell"] >= 0).sum()
+    assert tc[3] == absorbed and tc[0] == 20000 - absorbed
+    ctx.close()
+
+
+def test_full_layout_shoot_equals_oracle(cmib, ref):
+    """Planck + Verner (16 accumulators), no re-emission."""
+    from cmacionize_b200 import capi
+    with cmib.Context([-3 * PC] * 3, [6 * PC] * 3, [24] * 3) as ctx:
+        nc = ctx.ncells
+        ctx.set_abundances(*ABUNDANCES)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_sources([[0., 0., 0.], [1e16, -2e16, 3e15]], [0.25, 0.75], 1e49)
+        ctx.set_spectrum(capi.SPECTRUM_PLANCK, 40000.)
+        rng = np.random.default_rng(5)
+        n = 1e8 * np.exp(rng.normal(0, 0.5, nc))
+        x = np.zeros((14, nc))
+        x[0] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), nc))
+        x[1] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), nc))
+        ctx.upload_cells(n, np.full(nc, 8000.), x)
+        ctx.reset_accumulators()
+        tw, tc = ctx.shoot(30000, seed=11, iteration=0)
+        J, heat = ctx.download_accumulators()
+        pk = ctx.sample_packets(30000, seed=11, iteration=0)
+        # cross sections of the emitted packets are the oracle's to 1e-13
+        assert rel_err(pk["sigma"], ref.verner_cross_sections(pk["nu"])) < 1e-13
+        assert np.allclose(pk["sigma_He_corr"], 0.1 * pk["sigma"][:, 1], rtol=1e-15)
+        r = ref.interact([-3 * PC] * 3, [6 * PC] * 3, [24] * 3, [0, 0, 0], n, x[0], x[1], pk["pos"],
+                         pk["dir"], pk["sigma"], pk["sigma_He_corr"], pk["nu"], np.ones(30000),
+                         pk["tau"])
+        for k in range(14):
+            s = r["J"][k].max()
+            assert np.abs(J[k] - r["J"][k]).max() <= 1e-11 * max(s, 1e-300), k
+        for k in range(2):
+            s = np.abs(r["heat"][k]).max()
+            assert np.abs(heat[k] - r["heat"][k]).max() <= 1e-11 * s
+        # two sources: 25 % / 75 %
+        frac = np.mean(np.all(pk["pos"] == 0., axis=1))
+        assert abs(frac - 0.25) < 0.01
+
+
+def test_emission_statistics(cmib, ref):
+    from cmacionize_b200 import capi
+    with cmib.Context([-1, -1, -1], [2, 2, 2], [4, 4, 4]) as ctx:
+        ctx.set_abundances(*ABUNDANCES)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_sources([[0., 0., 0.]], [1.], 1e49)
+        ctx.set_spectrum(capi.SPECTRUM_PLANCK, 40000.)
+        n = 1_000_000
+        pk = ctx.sample_packets(n, seed=42)
+        d = pk["dir"]
+        # test/testPhotonSource.cpp:92-131: isotropy
+        assert np.abs(d.mean(axis=0)).max() < 3e-3
+        assert np.abs(np.linalg.norm(d, axis=1) - 1.).max() < 1e-14
+        assert abs((d[:, 2] ** 2).mean() - 1. / 3.) < 2e-3
+        # tau ~ Exp(1)
+        assert abs(pk["tau"].mean() - 1.) < 5e-3 and abs(pk["tau"].var() - 1.) < 2e-2
+        # Planck sampler vs the reference's sampler (its own RNG): compare histograms
+        nu_ref = ref.sample_spectrum(0, 40000., n, seed=42)
+        edges = np.linspace(3.288465385e15, 4 * 3.288465385e15, 101)
+        h1, _ = np.histogram(pk["nu"], edges)
+        h2, _ = np.histogram(nu_ref, edges)
+        big = h2 > 2000
+        assert np.abs(h1[big] - h2[big]).max() / np.sqrt(2 * h2[big]).max() < 6.
+        assert np.abs((h1[big] - h2[big]) / np.sqrt(h1[big] + h2[big])).max() < 5.
+        # streams do not depend on how a batch is split (multi-GPU sharding)
+        a = ctx.sample_packets(1000, offset=0, seed=9)
+        b = ctx.sample_packets(500, offset=500, seed=9)
+        assert np.array_equal(a["dir"][500:], b["dir"]) and np.array_equal(a["nu"][500:], b["nu"])
+        c = ctx.sample_packets(1000, offset=0, seed=10)
+        assert not np.array_equal(a["dir"], c["dir"])
+
+
+def test_diffuse_spectra_statistics(cmib, ref):
+    from cmacionize_b200 import capi
+    with cmib.Context([-1, -1, -1], [2, 2, 2], [4, 4, 4]) as ctx:
+        ctx.set_abundances(*ABUNDANCES)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_reemission(capi.REEMISSION_PHYSICAL)
+        # tables built on the host must be the reference's tables bit for bit
+        f, t, c = ctx.get_spectrum_tables(1)
+        rf, rt, rc = ref.lyc_tables(0, 1)
+        assert np.array_equal(f, rf) and np.array_equal(t, rt) and np.array_equal(c, rc)
+        f, t, c = ctx.get_spectrum_tables(2)
+        rf, rt, rc = ref.lyc_tables(1, 1)
+        assert np.array_equal(c, rc)
+        f, c = ctx.get_spectrum_tables(3)
+        rf, rc = ref.he2pc_tables()
+        assert np.array_equal(f, rf) and np.array_equal(c, rc)
+        n = 400_000
+        for which, T in ((1, 8000.), (2, 8000.), (3, 0.), (1, 1000.), (2, 20000.)):
+            a = ctx.sample_spectrum(which, T, n, seed=3)
+            b = ref.sample_spectrum(which, T, n, seed=3)
+            lo, hi = min(a.min(), b.min()), max(a.max(), b.max())
+            h1, e = np.histogram(a, 60, (lo, hi))
+            h2, _ = np.histogram(b, 60, (lo, hi))
+            big = (h1 + h2) > 400
+            z = (h1[big] - h2[big]) / np.sqrt(h1[big] + h2[big])
+            assert np.abs(z).max() < 5., (which, T, np.abs(z).max())
+
+
+def test_shoot_is_deterministic_and_shardable(cmib):
+    """Same seed -> same accumulators (up to atomic summation order); [0,N) in one call ==
+    [0,N/2) + [N/2,N) in two calls: the property the 1/2/4/8-GPU split relies on."""
+    from cmacionize_b200 import problems
+    prob = problems.stromgren(ncell=32, n_packets=100000)
+    ctx = prob.ctx
+    outs = []
+    for split in (1, 1, 4):
+        ctx.reset_accumulators()
+        per = 100000 // split
+        tot = 0.
+        for k in range(split):
+            tw, tc = ctx.shoot(per, packet_offset=k * per, seed=5, iteration=2)
+            tot += tw
+        assert tot == 100000.
+        outs.append(ctx.download_accumulators()[0][0].copy())
+    s = outs[0].max()
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-12 * s
+    assert np.abs(outs[0] - outs[2]).max() <= 1e-12 * s
+    ctx.reset_accumulators()
+    ctx.shoot(100000, seed=6, iteration=2)
+    other = ctx.download_accumulators()[0][0]
+    assert np.abs(outs[0] - other).max() > 1e-6 * s  # a different seed is a different sample
+    ctx.close()

@@ -1,0 +1,215 @@
+"""GPU tier, tier 3 of the north star: converged fields against the reference's own
+CPU run of the same problem, within Monte Carlo noise.
+
+The noise tolerance is defined the way SURVEY.md §7 (hard part 4) prescribes: from
+two reference runs with different seeds.  The GPU run must be no further from a
+reference run than two reference runs are from each other (times a small factor)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PC = 3.086e16
+
+STROMGREN_PARAM = """
+SimulationBox:
+  anchor: [-5. pc, -5. pc, -5. pc]
+  sides: [10. pc, 10. pc, 10. pc]
+  periodicity: [false, false, false]
+DensityGrid:
+  type: Cartesian
+  number of cells: [{nc}, {nc}, {nc}]
+DensityFunction:
+  type: Homogeneous
+  density: 100. cm^-3
+  temperature: 8000. K
+TemperatureCalculator:
+  do temperature calculation: false
+PhotonSourceDistribution:
+  type: SingleStar
+  position: [0. pc, 0. pc, 0. pc]
+  luminosity: 4.26e49 s^-1
+PhotonSourceSpectrum:
+  type: Monochromatic
+  frequency: 13.6 eV
+IonizationSimulation:
+  number of photons: {npk}
+  number of iterations: {nit}
+  random seed: {seed}
+CrossSections:
+  type: FixedValue
+  hydrogen_0: 6.3e-18 cm^2
+  helium_0: 0. m^2
+  carbon_1: 0. m^2
+  carbon_2: 0. m^2
+  nitrogen_0: 0. m^2
+  nitrogen_1: 0. m^2
+  nitrogen_2: 0. m^2
+  oxygen_0: 0. m^2
+  oxygen_1: 0. m^2
+  neon_0: 0. m^2
+  neon_1: 0. m^2
+  sulphur_1: 0. m^2
+  sulphur_2: 0. m^2
+  sulphur_3: 0. m^2
+RecombinationRates:
+  type: FixedValue
+  hydrogen_1: 4.e-13 cm^3 s^-1
+  helium_1: 0. m^3 s^-1
+  carbon_2: 0. m^3 s^-1
+  carbon_3: 0. m^3 s^-1
+  nitrogen_1: 0. m^3 s^-1
+  nitrogen_2: 0. m^3 s^-1
+  nitrogen_3: 0. m^3 s^-1
+  oxygen_1: 0. m^3 s^-1
+  oxygen_2: 0. m^3 s^-1
+  neon_1: 0. m^3 s^-1
+  neon_2: 0. m^3 s^-1
+  sulphur_2: 0. m^3 s^-1
+  sulphur_3: 0. m^3 s^-1
+  sulphur_4: 0. m^3 s^-1
+{extra}
+"""
+
+
+def radial_profile(x, nc, half):
+    cs = 2 * half / nc
+    m = -half + cs * (np.arange(nc) + 0.5)
+    X, Y, Z = np.meshgrid(m, m, m, indexing="ij")
+    r = np.sqrt(X * X + Y * Y + Z * Z).reshape(-1)
+    return r
+
+
+def stromgren_radius(xH, r):
+    """radius where the spherically averaged neutral fraction crosses 0.5"""
+    bins = np.linspace(0, r.max(), 80)
+    idx = np.digitize(r, bins)
+    prof = np.array([xH[idx == i].mean() if (idx == i).any() else np.nan for i in range(1, len(bins))])
+    mid = 0.5 * (bins[1:] + bins[:-1])
+    k = np.where(prof > 0.5)[0][0]
+    return np.interp(0.5, [prof[k - 1], prof[k]], [mid[k - 1], mid[k]])
+
+
+@pytest.mark.parametrize("diffuse", [False, True])
+def test_stromgren_converges_to_the_reference(cmib, ref, tmp_path, diffuse):
+    from cmacionize_b200 import problems
+    nc, npk, nit = 32, 200000, 10
+    extra = "DiffuseReemissionHandler:\n  type: Physical\n" if diffuse else ""
+    runs = []
+    for seed in (42, 43):
+        pf = tmp_path / f"stromgren_{seed}.param"
+        pf.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=seed, extra=extra))
+        fields, _ = ref.run_paramfile(pf, nc ** 3)
+        runs.append(fields)
+    prob = problems.stromgren(ncell=nc, n_packets=npk, n_iterations=nit, diffuse=diffuse)
+    problems.run(prob)
+    n, T, x, heat = prob.ctx.download_cells()
+    prob.ctx.close()
+    assert np.array_equal(n, runs[0][0]) and np.array_equal(T, runs[0][1])  # same initial grid
+    xg, xa, xb = x[0], runs[0][2], runs[1][2]
+    r = radial_profile(xg, nc, 5 * PC)
+    ion = (xa < 0.1) & (xb < 0.1)
+    assert ion.sum() > 1000
+    noise = np.median(np.abs(xa[ion] - xb[ion]) / xa[ion])       # reference vs reference
+    dev = np.median(np.abs(xg[ion] - xa[ion]) / xa[ion])         # GPU vs reference
+    assert dev < 2.0 * noise + 1e-3, (dev, noise)
+    assert dev < 0.05
+    # Stroemgren radius: within one cell of the reference's and (no diffuse field) of the
+    # analytic value (0.75 Q / (pi n^2 alpha))^(1/3) (benchmarks/stromgren.py:47-64)
+    cell = 10 * PC / nc
+    Rg, Ra = stromgren_radius(xg, r), stromgren_radius(xa, r)
+    assert abs(Rg - Ra) < 0.5 * cell
+    if not diffuse:
+        Rs = (0.75 * 4.26e49 / (np.pi * (1e8) ** 2 * 4e-19)) ** (1. / 3.)
+        assert abs(Rg - Rs) < 1.0 * cell
+    # neutral outside, ionised inside, same cells
+    assert np.mean((xg > 0.5) != (xa > 0.5)) < 0.01
+
+
+def test_lexington_hii20_matches_the_reference(cmib, ref, tmp_path):
+    """Full physics: Planck + Verner + 14 ions + Physical diffuse field + temperature
+    solve with line cooling, reduced to 32^3 / 2e5 packets / 8 iterations so the CPU
+    reference finishes in seconds."""
+    from cmacionize_b200 import problems
+    nc, npk, nit = 32, 200000, 8
+    yml = tmp_path / "lex.yml"
+    yml.write_text("""number of blocks: 2
+block[0]:
+  origin: [0. pc, 0. pc, 0. pc]
+  sides: [6. pc, 6. pc, 6. pc]
+  type: cube
+  number density: 100. cm^-3
+  initial temperature: 8000. K
+block[1]:
+  origin: [0. pc, 0. pc, 0. pc]
+  sides: [6.e18 cm, 6.e18 cm, 6.e18 cm]
+  type: sphere
+  number density: 0. cm^-3
+  initial temperature: 0. K
+""")
+    runs = []
+    for seed in (42, 43):
+        pf = tmp_path / f"lex_{seed}.param"
+        pf.write_text(f"""AbundanceModel:
+  type: FixedValue
+  He: 0.1
+  C: 2.2e-4
+  N: 4.e-5
+  O: 3.3e-4
+  Ne: 5.e-5
+  S: 9.e-6
+DensityFunction:
+  type: BlockSyntax
+  filename: {yml}
+DiffuseReemissionHandler:
+  type: Physical
+SimulationBox:
+  anchor: [-3. pc, -3. pc, -3. pc]
+  sides: [6. pc, 6. pc, 6. pc]
+  periodicity: [false, false, false]
+DensityGrid:
+  type: Cartesian
+  number of cells: [{nc}, {nc}, {nc}]
+IonizationSimulation:
+  number of iterations: {nit}
+  number of photons: {npk}
+  random seed: {seed}
+TemperatureCalculator:
+  do temperature calculation: true
+  PAH heating factor: 0.
+PhotonSourceDistribution:
+  type: SingleStar
+  position: [0. pc, 0. pc, 0. pc]
+  luminosity: 1.e49 s^-1
+PhotonSourceSpectrum:
+  type: Planck
+  temperature: 20000. K
+""")
+        fields, _ = ref.run_paramfile(pf, nc ** 3)
+        runs.append(fields)
+    prob = problems.lexington(20, ncell=nc, n_packets=npk, n_iterations=nit)
+    assert np.array_equal(prob.number_density, runs[0][0])   # same vacuum sphere, cell for cell
+    problems.run(prob)
+    n, T, x, heat = prob.ctx.download_cells()
+    prob.ctx.close()
+    a, b = runs
+    gas = n > 0
+    ion = gas & (a[2] < 0.1) & (b[2] < 0.1)
+    assert ion.sum() > 500
+    # hydrogen
+    noise = np.median(np.abs(a[2][ion] - b[2][ion]) / a[2][ion])
+    dev = np.median(np.abs(x[0][ion] - a[2][ion]) / a[2][ion])
+    assert dev < 2.0 * noise + 1e-3, ("xH", dev, noise)
+    # temperature
+    noiseT = np.median(np.abs(a[1][ion] - b[1][ion]) / a[1][ion])
+    devT = np.median(np.abs(T[ion] - a[1][ion]) / a[1][ion])
+    assert devT < 2.0 * noiseT + 1e-3, ("T", devT, noiseT)
+    # every ion: volume-averaged fraction over the ionised region
+    for k in range(14):
+        ma, mb, mg = a[2 + k][ion].mean(), b[2 + k][ion].mean(), x[k][ion].mean()
+        tol = 3. * abs(ma - mb) + 0.02 * abs(ma) + 1e-6
+        assert abs(mg - ma) < tol, (k, mg, ma, mb)
+    # vacuum cells: T = 500 K, everything neutral/zero exactly as the reference leaves them
+    vac = ~gas
+    assert np.array_equal(T[vac], a[1][vac])
+    assert np.array_equal(x[:, vac], a[2:16][:, vac])

@@ -1,0 +1,155 @@
+"""CPU tier: the product's physics headers (cmacionize_b200/csrc/*.cuh), compiled
+for the host by tests/hostcheck, must agree BIT FOR BIT with the compiled
+reference on the same inputs — same libm, no FMA contraction on either side, so
+any difference is a logic error.  The GPU tier repeats these checks on the
+device through the C ABI (test_gpu_*.py)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cases import ABUNDANCES, MARCH_GRIDS, march_case, state_cells
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def test_verner_cross_sections_bitexact(hostcheck, ref):
+    rng = np.random.default_rng(1)
+    nu = 3.288e15 * np.exp(rng.uniform(-0.1, np.log(6.), 20000))
+    out = np.empty((nu.size, 14))
+    hostcheck.hc_verner_cross_sections(C.c_int64(nu.size), p(nu), p(out))
+    assert np.array_equal(out, ref.verner_cross_sections(nu))
+
+
+def test_recombination_charge_transfer_reemission_bitexact(hostcheck, ref):
+    rng = np.random.default_rng(2)
+    T = np.exp(rng.uniform(np.log(50.), np.log(1e7), 20000))
+    out = np.empty((T.size, 14))
+    hostcheck.hc_verner_recombination_rates(C.c_int64(T.size), p(T), p(out))
+    assert np.array_equal(out, ref.verner_recombination_rates(T))
+    T4 = T * 1e-4
+    out = np.empty((T.size, 3, 14))
+    hostcheck.hc_charge_transfer(C.c_int64(T.size), p(T4), p(out))
+    assert np.array_equal(out, ref.charge_transfer(T4))
+    out = np.empty((T.size, 5))
+    hostcheck.hc_reemission_probabilities(C.c_int64(T.size), p(T), p(out))
+    assert np.array_equal(out, ref.reemission_probabilities(T))
+
+
+def test_line_cooling_and_solver_bitexact(hostcheck, ref):
+    rng = np.random.default_rng(3)
+    n = 5000
+    T = np.exp(rng.uniform(np.log(3000.), np.log(40000.), n))
+    ne = np.exp(rng.uniform(np.log(1e3), np.log(1e12), n))
+    ne[:10] = 0.  # get_cooling returns 1e-99 (LineCoolingData.cpp:1771-1775)
+    ab = rng.uniform(0, 1e-4, (n, 13))
+    out = np.empty(n)
+    hostcheck.hc_line_cooling(C.c_int64(n), p(T), p(ne), p(ab), p(out))
+    assert np.array_equal(out, ref.linecooling_get_cooling(T, ne, ab))
+    A = rng.uniform(-1, 1, (10000, 25))
+    B = rng.uniform(-1, 1, (10000, 5))
+    A[:5] = 0.  # singular systems must be reported, not solved
+    A2, B2 = A.copy(), B.copy()
+    st = np.empty(10000, dtype=np.int32)
+    hostcheck.hc_solve5(C.c_int64(10000), p(A2), p(B2), p(st))
+    Ar, Br, sr = ref.solve5(A, B)
+    assert np.array_equal(st, sr) and (st[:5] == 1).all()
+    assert np.array_equal(B2[5:], Br[5:])
+
+
+def test_spectrum_tables_bitexact(hostcheck, ref):
+    for temp in (20000., 40000.):
+        o = np.empty((3, 1000))
+        hostcheck.hc_planck_tables(C.c_double(temp), p(o))
+        assert np.array_equal(o, ref.planck_tables(temp))
+    fixed = np.zeros(14)
+    fixed[0], fixed[1] = 6.3e-22, 1e-22
+    for which in (0, 1):
+        for kind, xf in ((1, np.zeros(14)), (0, fixed)):
+            f = np.empty(1000); t = np.empty(100); c = np.empty((100, 1000))
+            hostcheck.hc_lyc_tables(C.c_int(which), C.c_int(kind), p(xf), p(f), p(t), p(c))
+            rf, rt, rc = ref.lyc_tables(which, kind, xf)
+            assert np.array_equal(f, rf) and np.array_equal(t, rt) and np.array_equal(c, rc)
+    f = np.empty(1000); c = np.empty(1000)
+    hostcheck.hc_he2pc_tables(p(f), p(c))
+    rf, rc = ref.he2pc_tables()
+    assert np.array_equal(f, rf) and np.array_equal(c, rc)
+
+
+def test_ionization_state_bitexact(hostcheck, ref, golden):
+    J, heat, nd, T = state_cells(golden, reps=20)
+    n = nd.size
+    for ab, kind, fixed in ((ABUNDANCES, 1, np.zeros(14)),
+                            (np.zeros(6), 0, np.array([4e-19] + [0.] * 13))):
+        x = np.empty((14, n)); ho = np.empty((2, n))
+        hostcheck.hc_ionization_state(C.c_int64(n), C.c_double(1.3), C.c_double(1.3 * 6.626e-34), p(ab),
+                                      C.c_int(kind), p(fixed), p(J), p(heat), p(nd), p(T), p(x), p(ho))
+        xr, hr = ref.ionization_state(1.3, 1.3 * 6.626e-34, ab, kind, fixed, J, heat, nd, T)
+        assert np.array_equal(x, xr, equal_nan=True)
+        assert np.array_equal(ho, hr)
+
+
+def test_cooling_heating_balance_bitexact(hostcheck, ref, golden):
+    g = golden["ioneng"]
+    n = len(g)
+    T = np.ascontiguousarray(g[:, 16]); nd = np.ascontiguousarray(g[:, 19]) * 1e6
+    j = np.ascontiguousarray(g[:, :14]); h = np.ascontiguousarray(g[:, 14:16]) * 1e-7
+    mz = np.linspace(-1e19, 1e19, n)
+    for pah, cr, scale in ((1., 0., 0.75), (0.3, 0.4, 2e19)):
+        h0 = np.empty(n); he0 = np.empty(n); gain = np.empty(n); loss = np.empty(n)
+        met = np.empty((n, 12))
+        hostcheck.hc_cooling_heating_balance(C.c_int64(n), p(T), p(nd), p(j), p(h), p(ABUNDANCES),
+                                             C.c_double(pah), C.c_double(cr), C.c_double(scale), p(mz),
+                                             C.c_int(1), p(np.zeros(14)), p(h0), p(he0), p(gain),
+                                             p(loss), p(met))
+        r = ref.cooling_heating_balance(T, nd, j, h, ABUNDANCES, pah, cr, scale, midz=mz)
+        for a, b in zip((h0, he0, gain, loss, met), r):
+            assert np.array_equal(a, b)
+
+
+def test_temperature_bitexact(hostcheck, ref, golden):
+    J, heat, nd, T = state_cells(golden, reps=10)
+    n = nd.size
+    rng = np.random.default_rng(11)
+    crf = rng.uniform(-1, 2, n)
+    mz = rng.uniform(-1e19, 1e19, n)
+    for tp in ([0., 0., 0.75, 1.33333 * 3.086e19, 4000., 1e-3, 100.],
+               [0.5, 0.2, 0.75, 1e19, 4000., 1e-3, 100.]):
+        tpa = np.array(tp)
+        To = np.empty(n); x = np.empty((14, n)); ho = np.empty((2, n))
+        hostcheck.hc_temperature(C.c_int64(n), C.c_double(1.), C.c_double(1.), p(ABUNDANCES), C.c_int(1),
+                                 p(np.zeros(14)), p(tpa), p(J), p(heat), p(nd), p(T), p(crf), p(mz),
+                                 p(To), p(x), p(ho))
+        Tr, xr, hr = ref.temperature(1., 1., ABUNDANCES, J, heat, nd, T, pahfac=tp[0], crfac=tp[1],
+                                     crlim=tp[2], crscale=tp[3], cr_factor=crf, midz=mz)
+        assert np.array_equal(To, Tr)
+        assert np.array_equal(x, xr)
+        assert np.array_equal(ho, hr)
+        assert 500. in Tr and Tr.max() <= 30000.
+
+
+@pytest.mark.parametrize("name", list(MARCH_GRIDS))
+def test_march_bitexact(hostcheck, ref, name):
+    """Voxel traversal: visited-cell sequence, final position, final cell, and (serial
+    accumulation order being identical) even the J/heating sums are bit-identical."""
+    npk = 4000
+    c = march_case(name, npk)
+    nc = int(np.prod(c["ncell"]))
+    mt = 512
+    r = ref.interact(c["anchor"], c["sides"], c["ncell"], c["periodic"], c["n"], c["xH"], c["xHe"],
+                     c["pos"], c["dir"], c["sigma"], c["sigma_He_corr"], c["nu"], c["weight"],
+                     c["tau"], max_trace=mt)
+    J = np.zeros((14, nc)); heat = np.zeros((2, nc)); fp = np.empty((npk, 3))
+    fc = np.empty(npk, np.int64); ns = np.empty(npk, np.int32); tr = np.empty((npk, mt), np.int64)
+    hostcheck.hc_march_packets(p(c["anchor"]), p(c["sides"]), p(c["ncell"]), p(c["periodic"]), p(c["n"]),
+                               p(c["xH"]), p(c["xHe"]), C.c_int64(npk), p(c["pos"]), p(c["dir"]),
+                               p(c["sigma"]), p(c["sigma_He_corr"]), p(c["nu"]), p(c["weight"]),
+                               p(c["tau"]), p(J), p(heat), p(fp), p(fc), p(ns), C.c_int32(mt), p(tr))
+    assert np.array_equal(ns, r["nsteps"])
+    assert np.array_equal(tr, r["trace"])
+    assert np.array_equal(fc, r["final_cell"])
+    assert np.array_equal(fp, r["final_pos"])
+    assert np.array_equal(J, r["J"]) and np.array_equal(heat, r["heat"])
+    assert (ns > 0).any()
