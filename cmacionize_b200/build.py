@@ -18,6 +18,9 @@ LIB = HERE / "libcmib.so"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # the reference is built without FMA contraction; keep every FP64
+    # product/sum separately rounded so device results differ from it by libm ulps only
+    "-fmad=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
     "-Xptxas", "-v",
     "-shared",

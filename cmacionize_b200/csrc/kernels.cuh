@@ -16,60 +16,18 @@
 #include "cmib_common.cuh"
 #include "march.cuh"
 #include "rng.cuh"
+#include "shoot.cuh"
 #include "source.cuh"
 #include "state.cuh"
 
 namespace cmib {
 
-enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
-constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, pad */
-
-template <int MODE> struct AccLayout;
-template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
-template <> struct AccLayout<ACC_HONLY> { static constexpr int NACC = 2; static constexpr int NSIG = 1; };
-
-struct ShootParams {
-  GridGeom geom;
-  SourceModel src;
-  const CellOpacity *cells;
-  const double *reemit_prob; /* [ncell][5] (REEMISSION_PHYSICAL) */
-  double *acc;               /* counters + per-cell accumulators */
-  double nu_H, nu_He;        /* 13.6 eV, 24.6 eV in Hz (DensityGrid.hpp:219-222) */
-  uint64_t seed;
-  uint32_t iteration;
-  uint64_t packet_offset;
-  uint64_t n_packets;
-};
+/* AccMode / AccLayout / ShootParams / accumulate / shoot_packet: shoot.cuh */
 
 /* fire-and-forget FP64 add: compiles to RED.E.ADD.F64 (no return value) */
-CMIB_D void red_add(double *addr, double v) { atomicAdd(addr, v); }
-
-/* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which
- * is exact (x + 0.0 == x) and removes most of the 16 RMWs for soft photons */
-template <int MODE>
-CMIB_D void accumulate(double *acc, int64_t cell, double ds, double weight, const double *sigma,
-                       double dnu_H, double dnu_He) {
-  const double dsw = ds * weight;
-  double *a = acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
-  if (MODE == ACC_HONLY) {
-    const double dJ = dsw * sigma[0];
-    red_add(a, dJ);
-    const double dh = dJ * dnu_H;
-    if (dh != 0.) red_add(a + 1, dh);
-  } else {
-    const double dJH = dsw * sigma[ION_H_n];
-    const double dJHe = dsw * sigma[ION_He_n];
-#pragma unroll
-    for (int ion = 0; ion < NUM_IONS; ++ion) {
-      const double dJ = dsw * sigma[ion];
-      if (dJ != 0.) red_add(a + ion, dJ);
-    }
-    const double dhH = dJH * dnu_H;
-    if (dhH != 0.) red_add(a + NUM_IONS + HEAT_H, dhH);
-    const double dhHe = dJHe * dnu_He;
-    if (dhHe != 0.) red_add(a + NUM_IONS + HEAT_He, dhHe);
-  }
-}
+struct DeviceAdder {
+  __device__ __forceinline__ void operator()(double *addr, double v) const { atomicAdd(addr, v); }
+};
 
 /* ------------------------------------------------------------------------- */
 /* shoot: one thread follows one packet at a time (grid-stride over packet ids) */
@@ -77,91 +35,14 @@ CMIB_D void accumulate(double *acc, int64_t cell, double ds, double weight, cons
 template <int MODE>
 __global__ void __launch_bounds__(256)
 shoot_kernel(const __grid_constant__ ShootParams P) {
-  constexpr int NSIG = AccLayout<MODE>::NSIG;
-  const GridGeom &g = P.geom;
-  const SourceModel &m = P.src;
-  double w_tot = 0.;
-  double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
-  uint32_t n_steps = 0, n_emit = 0; /* diagnostics for the roofline: cell crossings, (re)emissions */
-
+  ShootCounters cnt;
+  const DeviceAdder add;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_packets; i += stride) {
-    PacketRng rng;
-    rng_init(rng, P.seed, P.iteration, P.packet_offset + i);
-    MarchState s;
-    double sigma[NSIG];
-    double sigma_He_corr;
-    double nu;
-    int type = PACKET_PRIMARY;
-    /* --- PhotonSource::get_random_photon --- */
-    double x = rng_uniform(rng);
-    (void)x; /* discrete vs continuous: continuous sources are not on this path */
-    x = rng_uniform(rng);
-    int isrc = 0;
-    while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
-    s.px = m.src_pos[3 * isrc];
-    s.py = m.src_pos[3 * isrc + 1];
-    s.pz = m.src_pos[3 * isrc + 2];
-    random_direction(rng, s.dx, s.dy, s.dz);
-    nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
-    const double weight = m.discrete_weight;
-    packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
-
-    bool alive = true;
-    while (alive) {
-      ++n_emit;
-      s.ix_ = 1. / s.dx;
-      s.iy_ = 1. / s.dy;
-      s.iz_ = 1. / s.dz;
-      s.tau = -log(rng_uniform(rng));
-      march_locate(g, s);
-      const double dnu_H = nu - P.nu_H;
-      const double dnu_He = nu - P.nu_He;
-      CellOpacity c = {0., 0., 0., 0.};
-      bool inside;
-      while ((inside = march_inside(g, s)) && s.tau > 0.) {
-        const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
-        s.last_cell = cell;
-        const double2 *cp = reinterpret_cast<const double2 *>(P.cells + cell);
-        const double2 r0 = __ldg(cp), r1 = __ldg(cp + 1);
-        c.n = r0.x; c.xH = r0.y; c.xHe = r1.x; c.T = r1.y;
-        const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
-        if (c.n > 0.) accumulate<MODE>(P.acc, cell, ds, weight, sigma, dnu_H, dnu_He);
-        ++n_steps;
-      }
-      if (!inside) break; /* left the box: keeps its last type */
-      /* --- PhotonSource::reemit --- */
-      double new_nu = 0.;
-      if (m.reemission_kind == REEMISSION_PHYSICAL) {
-        double p[NUM_REEMIT];
-#pragma unroll
-        for (int k = 0; k < NUM_REEMIT; ++k) p[k] = P.reemit_prob[s.last_cell * NUM_REEMIT + k];
-        /* ACC_HONLY is only selected when sigma_He == 0 */
-        const double sHe = (NSIG > 1) ? sigma[(NSIG > 1) ? ION_He_n : 0] : 0.;
-        new_nu = physical_reemit(m, sigma[0], sHe, c.xH, c.xHe, c.T, p, rng, type);
-      } else if (m.reemission_kind == REEMISSION_FIXED) {
-        const double u = rng_uniform(rng);
-        if (u < m.fixed_reemission_probability) {
-          type = PACKET_DIFFUSE_HI;
-          new_nu = m.fixed_reemission_frequency;
-        } else {
-          type = PACKET_ABSORBED;
-        }
-      } else {
-        type = PACKET_ABSORBED;
-      }
-      if (new_nu == 0.) {
-        alive = false;
-      } else {
-        nu = new_nu;
-        random_direction(rng, s.dx, s.dy, s.dz);
-        packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
-      }
-    }
-    w_tot += weight;
-#pragma unroll
-    for (int t = 0; t < NUM_PACKET_TYPES; ++t) w_type[t] += (t == type) ? weight : 0.;
-  }
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n_packets; i += stride)
+    shoot_packet<MODE>(P, i, add, cnt);
+  const double w_tot = cnt.w_tot;
+  const double *w_type = cnt.w_type;
+  const uint32_t n_steps = cnt.n_steps, n_emit = cnt.n_emit;
 
   /* IonizationPhotonShootJobMarket::update_counters: block reduce, one RED per block */
   __shared__ double red[7][8];
@@ -177,7 +58,7 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
   if (threadIdx.x < 7) {
     double sum = 0.;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[threadIdx.x][w];
-    if (sum != 0.) red_add(P.acc + threadIdx.x, sum);
+    if (sum != 0.) atomicAdd(P.acc + threadIdx.x, sum);
   }
 }
 
@@ -223,7 +104,7 @@ march_packets_kernel(const __grid_constant__ MarchPacketsParams P) {
     const CellOpacity c = P.cells[cell];
     const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sHe);
     if (c.n > 0.) {
-      accumulate<ACC_FULL>(P.acc, cell, ds, w, sigma, nu - P.nu_H, nu - P.nu_He);
+      accumulate<ACC_FULL>(DeviceAdder(), P.acc, cell, ds, w, sigma, nu - P.nu_H, nu - P.nu_He);
       if (P.trace && nsteps < P.max_trace) P.trace[p * P.max_trace + nsteps] = cell;
       ++nsteps;
     }

@@ -1,0 +1,175 @@
+/*
+ * shoot.cuh — life of one photon packet: emit -> tau -> voxel walk with
+ * accumulation -> (re-emit -> tau -> walk)* .
+ *
+ * Behavioural contract = IonizationPhotonShootJob::execute
+ * (/root/reference/src/IonizationPhotonShootJob.hpp:117-146) with
+ *   PhotonSource::get_random_photon   src/PhotonSource.cpp:208-249
+ *   CartesianDensityGrid::interact    src/CartesianDensityGrid.cpp:375-452
+ *   DensityGrid::update_integrals     src/DensityGrid.hpp:150-197
+ *   PhotonSource::reemit              src/PhotonSource.cpp:272-308
+ *
+ * Written once as a __host__ __device__ function over an `Adder` policy so that
+ * the kernels (atomic RED adds) and the CPU-tier logic check of the tests
+ * (tests/hostcheck, plain +=) execute the same statements.
+ *
+ * Accumulator layouts: after ACC_COUNTERS leading counter doubles,
+ *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
+ *   ACC_HONLY  acc[cell][2]  = J_H, heat_H              (16 B; used when only sigma_H != 0)
+ */
+#pragma once
+#include "cmib_common.cuh"
+#include "march.cuh"
+#include "rng.cuh"
+#include "source.cuh"
+
+namespace cmib {
+
+enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
+constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, pad */
+
+template <int MODE> struct AccLayout;
+template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
+template <> struct AccLayout<ACC_HONLY> { static constexpr int NACC = 2; static constexpr int NSIG = 1; };
+
+struct ShootParams {
+  GridGeom geom;
+  SourceModel src;
+  const CellOpacity *cells;
+  const double *reemit_prob; /* [ncell][5] (REEMISSION_PHYSICAL) */
+  double *acc;               /* counters + per-cell accumulators */
+  double nu_H, nu_He;        /* 13.6 eV, 24.6 eV in Hz (DensityGrid.hpp:219-222) */
+  uint64_t seed;
+  uint32_t iteration;
+  uint64_t packet_offset;
+  uint64_t n_packets;
+};
+
+/* per-thread partial sums of IonizationPhotonShootJob's counters + roofline diagnostics */
+struct ShootCounters {
+  double w_tot = 0.;
+  double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
+  uint32_t n_steps = 0, n_emit = 0; /* cell crossings, (re)emissions */
+};
+
+/* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which
+ * is exact (x + 0.0 == x) and removes most of the 16 RMWs for soft photons */
+template <int MODE, class Adder>
+CMIB_HD void accumulate(const Adder &add, double *acc, int64_t cell, double ds, double weight,
+                        const double *sigma, double dnu_H, double dnu_He) {
+  const double dsw = ds * weight;
+  double *a = acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
+  if (MODE == ACC_HONLY) {
+    const double dJ = dsw * sigma[0];
+    add(a, dJ);
+    const double dh = dJ * dnu_H;
+    if (dh != 0.) add(a + 1, dh);
+  } else {
+    const double dJH = dsw * sigma[ION_H_n];
+    const double dJHe = dsw * sigma[ION_He_n];
+#pragma unroll
+    for (int ion = 0; ion < NUM_IONS; ++ion) {
+      const double dJ = dsw * sigma[ion];
+      if (dJ != 0.) add(a + ion, dJ);
+    }
+    const double dhH = dJH * dnu_H;
+    if (dhH != 0.) add(a + NUM_IONS + HEAT_H, dhH);
+    const double dhHe = dJHe * dnu_He;
+    if (dhHe != 0.) add(a + NUM_IONS + HEAT_He, dhHe);
+  }
+}
+
+CMIB_HD CellOpacity load_cell(const CellOpacity *cells, int64_t cell) {
+#if defined(__CUDA_ARCH__)
+  const double2 *cp = reinterpret_cast<const double2 *>(cells + cell);
+  const double2 r0 = __ldg(cp), r1 = __ldg(cp + 1);
+  CellOpacity c;
+  c.n = r0.x; c.xH = r0.y; c.xHe = r1.x; c.T = r1.y;
+  return c;
+#else
+  return cells[cell];
+#endif
+}
+
+/* packet `i` of this call (global id P.packet_offset + i) */
+template <int MODE, class Adder>
+CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, ShootCounters &cnt) {
+  constexpr int NSIG = AccLayout<MODE>::NSIG;
+  const GridGeom &g = P.geom;
+  const SourceModel &m = P.src;
+  PacketRng rng;
+  rng_init(rng, P.seed, P.iteration, P.packet_offset + i);
+  MarchState s;
+  double sigma[NSIG];
+  double sigma_He_corr;
+  double nu;
+  int type = PACKET_PRIMARY;
+  /* --- PhotonSource::get_random_photon --- */
+  double x = rng_uniform(rng);
+  (void)x; /* discrete vs continuous: continuous sources are not on this path */
+  x = rng_uniform(rng);
+  int isrc = 0;
+  while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
+  s.px = m.src_pos[3 * isrc];
+  s.py = m.src_pos[3 * isrc + 1];
+  s.pz = m.src_pos[3 * isrc + 2];
+  random_direction(rng, s.dx, s.dy, s.dz);
+  nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+  const double weight = m.discrete_weight;
+  packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+
+  bool alive = true;
+  while (alive) {
+    ++cnt.n_emit;
+    s.ix_ = 1. / s.dx;
+    s.iy_ = 1. / s.dy;
+    s.iz_ = 1. / s.dz;
+    s.tau = -log(rng_uniform(rng));
+    march_locate(g, s);
+    const double dnu_H = nu - P.nu_H;
+    const double dnu_He = nu - P.nu_He;
+    CellOpacity c = {0., 0., 0., 0.};
+    bool inside;
+    while ((inside = march_inside(g, s)) && s.tau > 0.) {
+      const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
+      s.last_cell = cell;
+      c = load_cell(P.cells, cell);
+      const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
+      if (c.n > 0.) accumulate<MODE>(add, P.acc, cell, ds, weight, sigma, dnu_H, dnu_He);
+      ++cnt.n_steps;
+    }
+    if (!inside) break; /* left the box: keeps its last type */
+    /* --- PhotonSource::reemit --- */
+    double new_nu = 0.;
+    if (m.reemission_kind == REEMISSION_PHYSICAL) {
+      double p[NUM_REEMIT];
+#pragma unroll
+      for (int k = 0; k < NUM_REEMIT; ++k) p[k] = P.reemit_prob[s.last_cell * NUM_REEMIT + k];
+      /* ACC_HONLY is only selected when sigma_He == 0 */
+      const double sHe = (NSIG > 1) ? sigma[(NSIG > 1) ? ION_He_n : 0] : 0.;
+      new_nu = physical_reemit(m, sigma[0], sHe, c.xH, c.xHe, c.T, p, rng, type);
+    } else if (m.reemission_kind == REEMISSION_FIXED) {
+      const double u = rng_uniform(rng);
+      if (u < m.fixed_reemission_probability) {
+        type = PACKET_DIFFUSE_HI;
+        new_nu = m.fixed_reemission_frequency;
+      } else {
+        type = PACKET_ABSORBED;
+      }
+    } else {
+      type = PACKET_ABSORBED;
+    }
+    if (new_nu == 0.) {
+      alive = false;
+    } else {
+      nu = new_nu;
+      random_direction(rng, s.dx, s.dy, s.dz);
+      packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+    }
+  }
+  cnt.w_tot += weight;
+#pragma unroll
+  for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? weight : 0.;
+}
+
+} // namespace cmib

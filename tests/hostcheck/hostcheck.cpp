@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../cmacionize_b200/csrc/march.cuh"
+#include "../../cmacionize_b200/csrc/shoot.cuh"
 #include "../../cmacionize_b200/csrc/source.cuh"
 #include "../../cmacionize_b200/csrc/spectrum_tables.hpp"
 #include "../../cmacionize_b200/csrc/state.cuh"
@@ -216,6 +217,100 @@ void hc_march_packets(const double *anchor, const double *sides, const int32_t *
     if (trace)
       for (int32_t k = ns; k < max_trace; ++k) trace[p * max_trace + k] = -1;
   }
+}
+
+/* the product's shoot_packet (shoot.cuh) executed on the host with plain adds: logic check of
+ * emission / walk / re-emission for the CPU tier.  cells [nc][4] = n, xH, xHe, T.
+ * iparams: n_sources, spectrum_kind, xs_kind, reemission_kind, acc_mode(0 full,1 H-only)
+ * dparams: spectrum param, A_He, fixed reemission probability, fixed reemission frequency
+ * acc: ACC_COUNTERS + nc*NACC doubles, accumulated into */
+struct HostAdder {
+  void operator()(double *a, double v) const { *a += v; }
+};
+
+void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
+              const int32_t *periodic, const double *cells, const int32_t *iparams,
+              const double *dparams, const double *src_pos, const double *src_weights,
+              const double *xs_fixed, uint64_t n_packets, uint64_t packet_offset, uint64_t seed,
+              uint32_t iteration, double *acc) {
+  ShootParams P;
+  GridGeom &g = P.geom;
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = anchor[d];
+    g.sides[d] = sides[d];
+    g.ncell[d] = ncell[d];
+    g.periodic[d] = periodic[d];
+    g.cellside[d] = sides[d] / ncell[d];
+    g.inv_cellside[d] = 1. / g.cellside[d];
+  }
+  g.cell_volume = g.cellside[0] * g.cellside[1] * g.cellside[2];
+  g.ncells = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  const int64_t nc = g.ncells;
+  std::vector<CellOpacity> cell_rec(nc);
+  for (int64_t i = 0; i < nc; ++i) {
+    cell_rec[i].n = cells[4 * i];
+    cell_rec[i].xH = cells[4 * i + 1];
+    cell_rec[i].xHe = cells[4 * i + 2];
+    cell_rec[i].T = cells[4 * i + 3];
+  }
+  SourceModel &m = P.src;
+  memset(&m, 0, sizeof(m));
+  m.n_sources = iparams[0];
+  std::vector<double> cum(m.n_sources);
+  for (int i = 0; i < m.n_sources; ++i) cum[i] = (i ? cum[i - 1] : 0.) + src_weights[i];
+  cum[m.n_sources - 1] = 1.;
+  m.src_pos = src_pos;
+  m.src_cum = cum.data();
+  m.discrete_weight = 1.;
+  m.spectrum_kind = iparams[1];
+  std::vector<double> planck, hf, ht, hc, hef, het, hec, tf, tc;
+  if (m.spectrum_kind == SPECTRUM_PLANCK) {
+    host::build_planck_table(dparams[0], planck);
+    m.planck = planck.data();
+  } else {
+    m.mono_frequency = dparams[0];
+  }
+  m.xs_kind = iparams[2];
+  for (int k = 0; k < NUM_IONS; ++k) m.xs_fixed[k] = xs_fixed ? xs_fixed[k] : 0.;
+  m.A_He = dparams[1];
+  m.reemission_kind = iparams[3];
+  m.fixed_reemission_probability = dparams[2];
+  m.fixed_reemission_frequency = dparams[3];
+  std::vector<double> prob;
+  if (m.reemission_kind == REEMISSION_PHYSICAL) {
+    const SourceModel mm = m;
+    auto sig = [mm](int ion) {
+      return [mm, ion](double nu) { return mm.xs_kind == XS_VERNER ? verner_cross_section(ion, nu) : mm.xs_fixed[ion]; };
+    };
+    host::build_lyc_table(0, sig(ION_H_n), hf, ht, hc);
+    host::build_lyc_table(1, sig(ION_He_n), hef, het, hec);
+    host::build_he2pc_table(tf, tc);
+    m.hlyc_freq = hf.data(); m.hlyc_temp = ht.data(); m.hlyc_cdf = hc.data();
+    m.helyc_freq = hef.data(); m.helyc_temp = het.data(); m.helyc_cdf = hec.data();
+    m.he2pc_freq = tf.data(); m.he2pc_cdf = tc.data();
+    prob.resize(nc * NUM_REEMIT);
+    for (int64_t i = 0; i < nc; ++i) reemission_probabilities(cell_rec[i].T, &prob[i * NUM_REEMIT]);
+  }
+  P.cells = cell_rec.data();
+  P.reemit_prob = prob.data();
+  P.acc = acc;
+  P.nu_H = (13.6 * ELECTRONVOLT) * (1. / PLANCK);
+  P.nu_He = (24.6 * ELECTRONVOLT) * (1. / PLANCK);
+  P.seed = seed;
+  P.iteration = iteration;
+  P.packet_offset = packet_offset;
+  P.n_packets = n_packets;
+  ShootCounters cnt;
+  const HostAdder add;
+  if (iparams[4] == ACC_HONLY) {
+    for (uint64_t i = 0; i < n_packets; ++i) shoot_packet<ACC_HONLY>(P, i, add, cnt);
+  } else {
+    for (uint64_t i = 0; i < n_packets; ++i) shoot_packet<ACC_FULL>(P, i, add, cnt);
+  }
+  acc[0] += cnt.w_tot;
+  for (int t = 0; t < NUM_PACKET_TYPES; ++t) acc[1 + t] += cnt.w_type[t];
+  acc[5] += cnt.n_steps;
+  acc[6] += cnt.n_emit;
 }
 
 } /* extern "C" */

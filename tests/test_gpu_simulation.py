@@ -3,7 +3,10 @@ CPU run of the same problem, within Monte Carlo noise.
 
 The noise tolerance is defined the way SURVEY.md §7 (hard part 4) prescribes: from
 two reference runs with different seeds.  The GPU run must be no further from a
-reference run than two reference runs are from each other (times a small factor)."""
+reference run than two reference runs are from each other (times a small factor).
+The two reference seeds are far apart on purpose: the reference seeds OpenMP thread t with
+seed + t (IonizationPhotonShootJobMarket.hpp:80-87), so runs with seeds 42 and 43 share all
+but one of their random streams and under-estimate the noise."""
 import numpy as np
 import pytest
 
@@ -96,7 +99,7 @@ def test_stromgren_converges_to_the_reference(cmib, ref, tmp_path, diffuse):
     nc, npk, nit = 32, 200000, 10
     extra = "DiffuseReemissionHandler:\n  type: Physical\n" if diffuse else ""
     runs = []
-    for seed in (42, 43):
+    for seed in (42, 4242):
         pf = tmp_path / f"stromgren_{seed}.param"
         pf.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=seed, extra=extra))
         fields, _ = ref.run_paramfile(pf, nc ** 3)
@@ -148,7 +151,7 @@ block[1]:
   initial temperature: 0. K
 """)
     runs = []
-    for seed in (42, 43):
+    for seed in (42, 4242):
         pf = tmp_path / f"lex_{seed}.param"
         pf.write_text(f"""AbundanceModel:
   type: FixedValue
