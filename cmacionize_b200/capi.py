@@ -215,6 +215,10 @@ class Context:
                               C.c_uint64(seed), C.c_uint32(iteration), None, None))
         return None
 
+    def set_shoot_algorithm(self, algorithm: int):
+        """0 = wavefront pipeline (production), 1 = one-thread-per-packet kernel (A/B check)"""
+        _check(lib.cmib_set_shoot_algorithm(self._h, C.c_int(algorithm)))
+
     def update_state(self, loop, totweight=0.):
         _check(lib.cmib_update_state(self._h, C.c_uint32(loop), C.c_double(totweight)))
 

@@ -15,6 +15,7 @@
 
 #include "../../include/cmib.h"
 #include "kernels.cuh"
+#include "wavefront.cuh"
 #include "spectrum_tables.hpp"
 
 using namespace cmib;
@@ -108,6 +109,15 @@ struct cmib_context {
       h_helyc_cdf, h_he2pc_freq, h_he2pc_cdf;
   int acc_mode = ACC_FULL;
   bool force_full = false;
+  /* wavefront shoot (wavefront.cuh): queues + control block, allocated on first use */
+  int shoot_algorithm = 0; /* 0 wavefront (production), 1 one-thread-per-packet kernel (A/B check) */
+  uint64_t queue_capacity = 0;
+  int queue_mode = -1;
+  DevBuf<double> mq, rq;
+  DevBuf<unsigned long long> ctl;
+  unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
+  int march_blocks_per_sm[2] = {0, 0};
+  uint64_t shoot_rounds = 0;
   double nu_H = 0., nu_He = 0.;
 
   int pick_acc_mode() const {
@@ -170,6 +180,82 @@ struct Scratch {
     return cudaMemcpyAsync(h, d, n * sizeof(T), cudaMemcpyDeviceToHost, s);
   }
 };
+} // namespace
+
+
+namespace {
+
+uint64_t default_queue_capacity() {
+  const char *e = getenv("CMIB_QUEUE_CAPACITY");
+  if (e) {
+    const long long v = atoll(e);
+    if (v >= 1024) return (uint64_t)v;
+  }
+  return 1ull << 22;
+}
+
+/* one cmib_shoot call on the wavefront path: rounds of prepare -> march until the
+ * queues run dry.  The host only reads back the march-queue sizes every few rounds. */
+int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
+  const int mode = ctx->acc_mode;
+  uint64_t cap = default_queue_capacity();
+  if (P.n_packets < cap) cap = (P.n_packets + 1023) / 1024 * 1024;
+  const int nf = (mode == ACC_HONLY) ? MarchQueueLayout<ACC_HONLY>::NFIELDS : MarchQueueLayout<ACC_FULL>::NFIELDS;
+  if (ctx->queue_capacity < cap || ctx->queue_mode != mode) {
+    CUDA_OK(ctx->mq.resize((size_t)nf * cap));
+    CUDA_OK(ctx->rq.resize((size_t)RQ_NFIELDS * cap));
+    ctx->queue_capacity = cap;
+    ctx->queue_mode = mode;
+  }
+  cap = ctx->queue_capacity;
+  if (!ctx->ctl.p) {
+    CUDA_OK(ctx->ctl.resize(CTL_WORDS));
+    CUDA_OK(cudaMallocHost((void **)&ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long)));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks_per_sm[ACC_FULL],
+                                                          march_kernel<ACC_FULL>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks_per_sm[ACC_HONLY],
+                                                          march_kernel<ACC_HONLY>, MARCH_BLOCK, 0));
+  }
+  cudaStream_t s = ctx->stream;
+  memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
+  ctx->h_ctl[CTL_REMAINING] = P.n_packets;
+  CUDA_OK(cudaMemcpyAsync(ctx->ctl.p, ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+  WavefrontParams W;
+  W.sp = P;
+  W.ctl = ctx->ctl.p;
+  W.mq = ctx->mq.p;
+  W.rq = ctx->rq.p;
+  W.capacity = cap;
+  const unsigned prep_grid = (unsigned)ctx->sm_count * 4;
+  int bpm = ctx->march_blocks_per_sm[mode];
+  if (bpm < 1) bpm = 1;
+  const unsigned march_grid = (unsigned)(ctx->sm_count * bpm);
+  const int group = 4;
+  uint64_t round = 0;
+  /* upper bound: every round either emits min(remaining, room) primaries or shrinks the
+   * re-emission population; 1e6 rounds cannot be reached by a sane configuration */
+  while (round < 1000000) {
+    for (int k = 0; k < group; ++k, ++round) {
+      if (mode == ACC_HONLY) prepare_kernel<ACC_HONLY><<<prep_grid, 256, 0, s>>>(W);
+      else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
+      advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
+      if (mode == ACC_HONLY) march_kernel<ACC_HONLY><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      else march_kernel<ACC_FULL><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl);
+      g_launches += 4;
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl.p, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    bool done = false;
+    for (int k = 0; k < group; ++k)
+      if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;
+    if (done) break;
+  }
+  ctx->shoot_rounds = round;
+  return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -253,6 +339,7 @@ int cmib_destroy(cmib_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
+  if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   delete ctx;
   return 0;
 }
@@ -510,17 +597,21 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
     P.iteration = iteration;
     P.packet_offset = packet_offset;
     P.n_packets = n_packets;
-    const int bs = 256;
-    /* persistent-style grid: a multiple of the SM count, packets are strided over it */
-    uint64_t want = (n_packets + bs - 1) / bs;
-    uint64_t cap = (uint64_t)ctx->sm_count * 8;
-    unsigned grid = (unsigned)(want < cap ? want : cap);
-    if (ctx->acc_mode == ACC_HONLY)
-      shoot_kernel<ACC_HONLY><<<grid, bs, 0, ctx->stream>>>(P);
-    else
-      shoot_kernel<ACC_FULL><<<grid, bs, 0, ctx->stream>>>(P);
-    ++g_launches;
-    CUDA_OK(cudaGetLastError());
+    if (ctx->shoot_algorithm == 1) {
+      const int bs = 256;
+      /* persistent-style grid: a multiple of the SM count, packets are strided over it */
+      uint64_t want = (n_packets + bs - 1) / bs;
+      uint64_t cap = (uint64_t)ctx->sm_count * 8;
+      unsigned grid = (unsigned)(want < cap ? want : cap);
+      if (ctx->acc_mode == ACC_HONLY)
+        shoot_kernel<ACC_HONLY><<<grid, bs, 0, ctx->stream>>>(P);
+      else
+        shoot_kernel<ACC_FULL><<<grid, bs, 0, ctx->stream>>>(P);
+      ++g_launches;
+      CUDA_OK(cudaGetLastError());
+    } else {
+      if (shoot_wavefront(ctx, P)) return 1;
+    }
   }
   if (totweight || typecount) {
     double after[5];
@@ -558,6 +649,13 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   ++g_launches;
   CUDA_OK(cudaGetLastError());
   ctx->reemit_prob_valid = false;
+  return 0;
+}
+
+int cmib_set_shoot_algorithm(cmib_context *ctx, int algorithm) {
+  CHECK_CTX(ctx);
+  if (algorithm != 0 && algorithm != 1) CMIB_FAIL("unknown shoot algorithm %d", algorithm);
+  ctx->shoot_algorithm = algorithm;
   return 0;
 }
 

@@ -151,6 +151,11 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight);
  * (re-)emissions.  No reference counterpart (gprof call counts were used there). */
 int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions);
 
+/* test hook: 0 = wavefront pipeline (default, production: prepare/march kernels connected by
+ * device queues), 1 = one-thread-per-packet kernel.  Both draw the same packets from the same
+ * per-packet random streams; they differ only in the order of the atomic adds. */
+int cmib_set_shoot_algorithm(cmib_context *ctx, int algorithm);
+
 /* ---- multi-GPU plumbing ------------------------------------------------ */
 /* Device pointer + length (in doubles) of the contiguous buffer that must be
  * sum-all-reduced between cmib_shoot and cmib_update_state: 8 counters

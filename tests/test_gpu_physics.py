@@ -40,8 +40,15 @@ def ctx(cmib):
     c.close()
 
 
+def _flush():
+    out = Path(os.environ.get("GRAFT_REPO_ROOT", ".")) / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / "parity_physics.json").write_text(json.dumps(MEASURED, indent=1))
+
+
 def record(name, value):
     MEASURED[name] = float(value)
+    _flush()
     return value
 
 
@@ -202,10 +209,30 @@ def test_calculate_temperature(ctx, ref, golden):
     record("temperature_median_rel", np.median(dT))
     record("temperature_max_rel", dT.max())
     record("temperature_frac_gt_1e-9", np.mean(dT > 1e-9))
+    bad = np.where(dT > 2e-3)[0]
+    MEASURED["temperature_outliers"] = [dict(i=int(i), Tg=float(Tg[i]), Tr=float(Tr[i])) for i in bad[:10]]
+    _flush()
     assert np.mean(dT > 1e-6) < 0.05
-    assert dT.max() < 2e-3
+    # A cell may only be off by more than the solver's tolerance if it is ILL-CONDITIONED IN THE
+    # REFERENCE ITSELF: the reference's answer for it must jump when its input temperature is
+    # moved by 1e-13 .. 1e-10 relative (measured on B200: 1 such cell of 1160, a jittered fixture
+    # row whose heating is ~0 so that the sign of expgain - exploss is rounding noise and the
+    # secant step lands on 1e10 K -> 30000 K in one code and < 4000 K -> 500 K in the other).
+    assert bad.size <= 0.003 * n
+    for i in bad:
+        sl = slice(i, i + 1)
+        outs = []
+        for f in (1. - 1e-10, 1. - 1e-13, 1., 1. + 1e-13, 1. + 1e-10):
+            Tp, _, _ = ref.temperature(1., 1., ABUNDANCES, np.ascontiguousarray(J[:, sl]),
+                                       np.ascontiguousarray(heat[:, sl]), nd[sl].copy(), T0[sl] * f,
+                                       pahfac=0.5, crfac=0.2, crlim=0.75, crscale=1e19,
+                                       cr_factor=crf[sl].copy(), midz=mz[sl].copy())
+            outs.append(float(Tp[0]))
+        assert max(outs) / min(outs) - 1. > 2e-3, (int(i), outs, float(Tg[i]))
+        assert min(outs) * (1 - 2e-3) <= Tg[i] <= max(outs) * (1 + 2e-3)
+    ok = dT <= 2e-3
     same = dT <= 1e-9
     record("temperature_x_rel_where_T_same", rel_err(xg[:, same], xr[:, same]))
     assert rel_err(xg[:, same], xr[:, same]) < 1e-5
-    assert np.array_equal(Tg == 500., Tr == 500.)
-    assert rel_err(hg, hr) < 1e-14
+    assert np.array_equal(Tg[ok] == 500., Tr[ok] == 500.)
+    assert rel_err(hg[:, ok], hr[:, ok]) < 1e-14

@@ -166,3 +166,54 @@ def test_shoot_is_deterministic_and_shardable(cmib):
     other = ctx.download_accumulators()[0][0]
     assert np.abs(outs[0] - other).max() > 1e-6 * s  # a different seed is a different sample
     ctx.close()
+
+
+@pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission"])
+def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
+    """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
+    one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
+    streams: identical counters (packets by type, cell crossings, (re-)emissions) and
+    accumulators equal up to the order of the atomic adds.  Small queue capacities force many
+    rounds, chunk boundaries and partially filled warps."""
+    import os
+    from cmacionize_b200 import problems, capi
+    npk = 60000
+    if config == "stromgren":
+        prob = problems.stromgren(ncell=32, n_packets=npk)
+    elif config == "stromgren_diffuse":
+        prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
+    elif config == "lexington":
+        prob = problems.lexington(20, ncell=24, n_packets=npk)
+    else:
+        prob = problems.stromgren(ncell=16, n_packets=npk)
+        prob.ctx.set_reemission(capi.REEMISSION_FIXED_VALUE, 0.364, problems.ev_to_hz(19.8))
+    ctx = prob.ctx
+    rng = np.random.default_rng(17)
+    x = prob.ionic_fractions.copy()
+    x[0] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), ctx.ncells))
+    x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), ctx.ncells))
+    ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
+    results = []
+    for algorithm, capacity in ((1, None), (0, None), (0, 4096), (0, 1024)):
+        if capacity is None:
+            os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+        else:
+            os.environ["CMIB_QUEUE_CAPACITY"] = str(capacity)
+        ctx.set_shoot_algorithm(algorithm)
+        ctx.reset_accumulators()
+        ctx.update_reemission_probabilities()
+        tw, tc = ctx.shoot(npk, packet_offset=1000, seed=99, iteration=4)
+        J, heat = ctx.download_accumulators()
+        results.append((tw, tc, ctx.shoot_statistics(), J, heat))
+    os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+    ctx.close()
+    tw0, tc0, st0, J0, h0 = results[0]
+    assert tw0 == npk and tc0.sum() == npk
+    if config != "stromgren":
+        assert st0[1] > 1.05 * npk  # re-emission happened
+    for tw, tc, st, J, h in results[1:]:
+        assert tw == tw0 and np.array_equal(tc, tc0) and st == st0
+        for k in range(14):
+            assert np.abs(J[k] - J0[k]).max() <= 1e-12 * max(J0[k].max(), 1e-300), k
+        for k in range(2):
+            assert np.abs(h[k] - h0[k]).max() <= 1e-12 * max(np.abs(h0[k]).max(), 1e-300), k

@@ -93,10 +93,15 @@ def stromgren_radius(xH, r):
     return np.interp(0.5, [prof[k - 1], prof[k]], [mid[k - 1], mid[k]])
 
 
+def shell_means(f, r, edges):
+    idx = np.digitize(r, edges)
+    return np.array([f[idx == i].mean() for i in range(1, len(edges))])
+
+
 @pytest.mark.parametrize("diffuse", [False, True])
 def test_stromgren_converges_to_the_reference(cmib, ref, tmp_path, diffuse):
     from cmacionize_b200 import problems
-    nc, npk, nit = 32, 200000, 10
+    nc, npk, nit = 32, 1000000, 10
     extra = "DiffuseReemissionHandler:\n  type: Physical\n" if diffuse else ""
     runs = []
     for seed in (42, 4242):
@@ -111,17 +116,23 @@ def test_stromgren_converges_to_the_reference(cmib, ref, tmp_path, diffuse):
     assert np.array_equal(n, runs[0][0]) and np.array_equal(T, runs[0][1])  # same initial grid
     xg, xa, xb = x[0], runs[0][2], runs[1][2]
     r = radial_profile(xg, nc, 5 * PC)
-    ion = (xa < 0.1) & (xb < 0.1)
+    cell = 10 * PC / nc
+    Rg, Ra, Rb = stromgren_radius(xg, r), stromgren_radius(xa, r), stromgren_radius(xb, r)
+    # the region is chosen geometrically (well inside the front), NOT by the values being
+    # compared: selecting cells where both references are small biases them low
+    ion = r < 0.75 * Ra
     assert ion.sum() > 1000
     noise = np.median(np.abs(xa[ion] - xb[ion]) / xa[ion])       # reference vs reference
     dev = np.median(np.abs(xg[ion] - xa[ion]) / xa[ion])         # GPU vs reference
-    assert dev < 2.0 * noise + 1e-3, (dev, noise)
-    assert dev < 0.05
-    # Stroemgren radius: within one cell of the reference's and (no diffuse field) of the
-    # analytic value (0.75 Q / (pi n^2 alpha))^(1/3) (benchmarks/stromgren.py:47-64)
-    cell = 10 * PC / nc
-    Rg, Ra = stromgren_radius(xg, r), stromgren_radius(xa, r)
-    assert abs(Rg - Ra) < 0.5 * cell
+    assert dev < 1.5 * noise + 1e-3, (dev, noise)
+    # shell averages beat the per-cell noise down: 1 % agreement of the neutral-fraction profile
+    edges = np.linspace(0., 0.75 * Ra, 9)
+    sg, sa, sb = shell_means(xg, r, edges), shell_means(xa, r, edges), shell_means(xb, r, edges)
+    tol = np.maximum(3. * np.abs(sb / sa - 1.), 0.01)
+    assert (np.abs(sg / sa - 1.) < tol).all(), (sg / sa, sb / sa)
+    # Stroemgren radius: within a fraction of a cell of the reference's and (no diffuse field)
+    # of the analytic value (0.75 Q / (pi n^2 alpha))^(1/3) (benchmarks/stromgren.py:47-64)
+    assert abs(Rg - Ra) < max(0.25 * cell, 3. * abs(Ra - Rb))
     if not diffuse:
         Rs = (0.75 * 4.26e49 / (np.pi * (1e8) ** 2 * 4e-19)) ** (1. / 3.)
         assert abs(Rg - Rs) < 1.0 * cell
@@ -134,7 +145,7 @@ def test_lexington_hii20_matches_the_reference(cmib, ref, tmp_path):
     solve with line cooling, reduced to 32^3 / 2e5 packets / 8 iterations so the CPU
     reference finishes in seconds."""
     from cmacionize_b200 import problems
-    nc, npk, nit = 32, 200000, 8
+    nc, npk, nit = 32, 1000000, 8
     yml = tmp_path / "lex.yml"
     yml.write_text("""number of blocks: 2
 block[0]:
@@ -197,17 +208,21 @@ PhotonSourceSpectrum:
     prob.ctx.close()
     a, b = runs
     gas = n > 0
-    ion = gas & (a[2] < 0.1) & (b[2] < 0.1)
+    r = radial_profile(x[0], nc, 3 * PC)
+    # geometric region: gas inside 75 % of the reference's ionisation-front radius
+    Ra = stromgren_radius(np.where(gas, a[2], 0.), r)
+    ion = gas & (r < 0.75 * Ra)
     assert ion.sum() > 500
     # hydrogen
     noise = np.median(np.abs(a[2][ion] - b[2][ion]) / a[2][ion])
     dev = np.median(np.abs(x[0][ion] - a[2][ion]) / a[2][ion])
-    assert dev < 2.0 * noise + 1e-3, ("xH", dev, noise)
+    assert dev < 1.5 * noise + 1e-3, ("xH", dev, noise)
     # temperature
     noiseT = np.median(np.abs(a[1][ion] - b[1][ion]) / a[1][ion])
     devT = np.median(np.abs(T[ion] - a[1][ion]) / a[1][ion])
-    assert devT < 2.0 * noiseT + 1e-3, ("T", devT, noiseT)
-    # every ion: volume-averaged fraction over the ionised region
+    assert devT < 1.5 * noiseT + 1e-3, ("T", devT, noiseT)
+    assert abs(T[ion].mean() / a[1][ion].mean() - 1.) < max(3. * abs(b[1][ion].mean() / a[1][ion].mean() - 1.), 0.01)
+    # every ion: volume-averaged fraction over the region
     for k in range(14):
         ma, mb, mg = a[2 + k][ion].mean(), b[2 + k][ion].mean(), x[k][ion].mean()
         tol = 3. * abs(ma - mb) + 0.02 * abs(ma) + 1e-6
