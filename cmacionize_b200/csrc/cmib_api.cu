@@ -247,6 +247,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl.p, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
+    if (ctx->h_ctl[CTL_ERROR]) CMIB_FAIL("march kernel exceeded its pass limit (internal error)");
     bool done = false;
     for (int k = 0; k < group; ++k)
       if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;

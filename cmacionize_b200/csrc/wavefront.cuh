@@ -43,6 +43,7 @@ enum CtlWord : int {
   CTL_REMAINING,    /* primaries not yet emitted */
   CTL_NEXT_FRESH,   /* local index of the next primary */
   CTL_ROUND,
+  CTL_ERROR,        /* set by a kernel that hit its safety valve */
   CTL_STATUS = 8,   /* ring of CTL_STATUS_SLOTS words: march-queue size after each prepare */
   CTL_STATUS_SLOTS = 64,
   CTL_WORDS = CTL_STATUS + CTL_STATUS_SLOTS
@@ -231,99 +232,97 @@ __global__ void advance_after_march_kernel(unsigned long long *ctl) { ctl[CTL_QC
 /* ------------------------------------------------------------------------- */
 constexpr int MARCH_BLOCK = 256;
 constexpr int MARCH_CHUNK = 128;     /* queue entries a warp claims with one atomic */
-constexpr int MARCH_REFILL_MIN = 8;  /* idle lanes that trigger a refill while the queue has entries */
+constexpr int MARCH_REFILL_MIN = 8;  /* lanes waiting (walk ended or empty) that trigger finish + refill */
 
+enum LaneState : int { LANE_EMPTY = 0, LANE_LIVE = 1, LANE_ABSORBED = 2, LANE_ESCAPED = 3 };
+
+/*
+ * The hot loop executes ONE cell crossing per pass for every live lane and nothing else.
+ * Everything that happens once per packet — the partial-step correction with its four
+ * divisions (CartesianDensityGrid.cpp:413-417), the accumulation of that last partial
+ * step, the hand-over to the re-emission queue, loading the next packet — is deferred
+ * until at least MARCH_REFILL_MIN lanes wait for it, so that it runs on many lanes at
+ * once instead of on ~1 (ncu: profiles/r01_march_v1.md).
+ *
+ * Arithmetic of the crossing is that of march_step (march.cuh), operation for operation;
+ * the only re-arrangements are exact: (double)ix is carried as a double that is
+ * incremented by +-1 (integers are exact in FP64), and the upper wall lo + cellside of
+ * the reference is formed as lo + h with h = cellside (d > 0) or 0 (d < 0), x + 0 == x.
+ */
 template <int MODE>
-__global__ void __launch_bounds__(MARCH_BLOCK)
+__global__ void __launch_bounds__(MARCH_BLOCK, 3)
 march_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   constexpr int NMETAL = (MODE == ACC_FULL) ? 12 : 0;
-  __shared__ double s_sig[(NMETAL > 0 ? NMETAL : 1)][MARCH_BLOCK];
+  /* per-lane packet constants that are only touched once per packet or per accumulation */
+  __shared__ double s_sig[(NMETAL > 0 ? NMETAL + 1 : 1)][MARCH_BLOCK]; /* metals, then sigma_He */
+  __shared__ unsigned long long s_id[MARCH_BLOCK], s_meta[MARCH_BLOCK];
   const ShootParams &P = W.sp;
   const GridGeom &g = P.geom;
   const uint64_t cap = W.capacity;
   const uint64_t qcount = W.ctl[CTL_QCOUNT];
   const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
   const bool can_reemit = (P.src.reemission_kind != REEMISSION_NONE);
+  const bool any_periodic = (g.periodic[0] | g.periodic[1] | g.periodic[2]) != 0;
   const double weight = P.src.discrete_weight;
-  ShootCounters cnt;
+  const uint32_t ncx = (uint32_t)g.ncell[0], ncy = (uint32_t)g.ncell[1], ncz = (uint32_t)g.ncell[2];
+  uint32_t n_type[NUM_PACKET_TYPES] = {0u, 0u, 0u, 0u};
+  uint32_t n_steps = 0;
 
-  MarchState s;
-  double sigH = 0., sigHe = 0., sigHe_corr = 0., dnu_H = 0., dnu_He = 0.;
-  uint64_t id = 0, meta = 0;
-  uint32_t mask = 0;   /* metals (bits 2..13) with a non-zero cross section */
-  bool has = false, live = false;
-  s.last_cell = -1;
-  /* warp-uniform cursor into the claimed chunk */
-  uint64_t cur = 0, end = 0;
+  /* packet state */
+  double px = 0., py = 0., pz = 0., dx = 1., dy = 1., dz = 1., ivx = 1., ivy = 1., ivz = 1.;
+  double fx = 0., fy = 0., fz = 0.; /* cell indices as doubles */
+  double tau = 0., tau_cell = 0., ds = 0.;
+  double sigH = 0., sigHe_corr = 0., dnu_H = 0., dnu_He = 0.;
+  int32_t ix = 0, iy = 0, iz = 0;
+  uint32_t cell = 0;
+  uint32_t mask = 0; /* metals (bits 2..13) with a non-zero cross section */
+  int state = LANE_EMPTY;
+  bool warp_has_zero_dir = false; /* some lane's direction has a zero component (warp-uniform) */
+  uint64_t cur = 0, end = 0;      /* warp-uniform cursor into the claimed chunk */
   bool exhausted = (qcount == 0);
+  uint32_t n_pass = 0;
 
   while (true) {
-    /* ---- refill: hand queue entries to idle lanes ---- */
-    const unsigned idle = __ballot_sync(0xffffffffu, !has);
-    const int nidle = __popc(idle);
-    if (nidle > 0 && !exhausted && (nidle >= MARCH_REFILL_MIN || idle == 0xffffffffu)) {
-      if (cur == end) {
-        unsigned long long b = 0;
-        if (lane == 0) b = atomicAdd(&W.ctl[CTL_HEAD], (unsigned long long)MARCH_CHUNK);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= qcount) {
-          exhausted = true;
-        } else {
-          cur = b;
-          end = (b + MARCH_CHUNK < qcount) ? b + MARCH_CHUNK : qcount;
-        }
-      }
-      if (!exhausted) {
-        const int rank = __popc(idle & ((1u << lane) - 1u));
-        const uint64_t avail = end - cur;
-        if (!has && (uint64_t)rank < avail) {
-          const double *q = W.mq + (cur + rank);
-          s.px = q[MQ_PX * cap]; s.py = q[MQ_PY * cap]; s.pz = q[MQ_PZ * cap];
-          s.dx = q[MQ_DX * cap]; s.dy = q[MQ_DY * cap]; s.dz = q[MQ_DZ * cap];
-          const double nu = q[MQ_NU * cap];
-          s.tau = q[MQ_TAU * cap];
-          id = (uint64_t)__double_as_longlong(q[MQ_ID * cap]);
-          meta = (uint64_t)__double_as_longlong(q[MQ_META * cap]);
-          sigH = q[MQ_SIGMA * cap];
-          mask = 0;
-          if (MODE == ACC_FULL) {
-            sigHe = q[(MQ_SIGMA + 1) * cap];
-            sigHe_corr = q[(MQ_SIGMA + NSIG) * cap];
-#pragma unroll
-            for (int k = 0; k < NMETAL; ++k) {
-              const double v = q[(MQ_SIGMA + 2 + k) * cap];
-              s_sig[k][threadIdx.x] = v;
-              mask |= (v != 0.) ? (1u << (2 + k)) : 0u;
-            }
-          }
-          dnu_H = nu - P.nu_H;
-          dnu_He = nu - P.nu_He;
-          s.ix_ = 1. / s.dx;
-          s.iy_ = 1. / s.dy;
-          s.iz_ = 1. / s.dz;
-          march_locate(g, s);
-          has = true;
-          live = march_inside(g, s) && s.tau > 0.;
-        }
-        cur += ((uint64_t)nidle < avail) ? (uint64_t)nidle : avail;
-      }
+    /* safety valve: a warp needs ~(entries per warp) x (crossings per packet) passes, orders
+     * of magnitude below this bound; never spin forever on a shared GPU */
+    if (++n_pass > (1u << 26)) {
+      if (lane == 0) atomicExch(&W.ctl[CTL_ERROR], 1ull);
+      break;
     }
-    if (__ballot_sync(0xffffffffu, has) == 0u) {
-      if (exhausted) break;
-      continue;
-    }
-
-    /* ---- one cell crossing for every live lane ---- */
-    if (has && live) {
-      const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
-      s.last_cell = cell;
-      const CellOpacity c = load_cell(P.cells, cell);
-      const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigH, sigHe_corr);
-      if (c.n > 0.) {
-        /* update_integrals (DensityGrid.hpp:150-197); zero increments are skipped (exact) */
-        const double dsw = ds * weight;
-        double *a = P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
+    const unsigned live_m = __ballot_sync(0xffffffffu, state == LANE_LIVE);
+    const unsigned waiting = ~live_m;               /* empty lanes + lanes whose walk ended */
+    const unsigned empty_m = __ballot_sync(0xffffffffu, state == LANE_EMPTY);
+    const unsigned pend_m = waiting & ~empty_m;     /* walk ended, finish not yet done */
+    const int nwait = __popc(waiting);
+    if (live_m == 0u && pend_m == 0u && exhausted) break;
+    /* service (finish + refill) when enough lanes wait for it or when nothing can be stepped;
+     * once the queue is exhausted only lanes with a pending finish count */
+    const bool service = exhausted ? (pend_m != 0u && (__popc(pend_m) >= MARCH_REFILL_MIN || live_m == 0u))
+                                   : (nwait >= MARCH_REFILL_MIN || live_m == 0u);
+    if (service) {
+      /* ---- finish: absorbed ---- */
+      double fpx = 0., fpy = 0., fpz = 0.;
+      if (state == LANE_ABSORBED && !(tau < 0.)) {
+        /* tau == 0 exactly after a full crossing: the walk ends on the wall, in the cell the
+         * packet has just entered (interact() returns the cell of the current index, :445-451) */
+        fpx = px; fpy = py; fpz = pz;
+        cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
+        if (!can_reemit) ++n_type[PACKET_ABSORBED];
+      } else if (state == LANE_ABSORBED) {
+        /* tau < 0 after the crossing: shorten it (CartesianDensityGrid.cpp:413-417) */
+        const double nwx = xadd(px, xmul(ds, dx));
+        const double nwy = xadd(py, xmul(ds, dy));
+        const double nwz = xadd(pz, xmul(ds, dz));
+        const double Scorr = xdiv(xmul(ds, tau), tau_cell);
+        const double dss = xadd(ds, Scorr);
+        fpx = xadd(px, xdiv(xmul(xsub(nwx, px), dss), ds));
+        fpy = xadd(py, xdiv(xmul(xsub(nwy, py), dss), ds));
+        fpz = xadd(pz, xdiv(xmul(xsub(nwz, pz), dss), ds));
+        /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
+        const double dsw = dss * weight;
+        double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
         const double dJH = dsw * sigH;
         if (dJH != 0.) {
           atomicAdd(a + ION_H_n, dJH);
@@ -331,7 +330,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
         }
         if (MODE == ACC_FULL) {
-          const double dJHe = dsw * sigHe;
+          const double dJHe = dsw * s_sig[NMETAL][tid];
           if (dJHe != 0.) {
             atomicAdd(a + ION_He_n, dJHe);
             const double dh = dJHe * dnu_He;
@@ -341,46 +340,184 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1u;
-            const double dJ = dsw * s_sig[k - 2][threadIdx.x];
+            const double dJ = dsw * s_sig[k - 2][tid];
             if (dJ != 0.) atomicAdd(a + k, dJ);
           }
         }
+        if (!can_reemit) ++n_type[PACKET_ABSORBED]; /* PhotonSource::reemit without a handler (:304-306) */
+      } else if (state == LANE_ESCAPED) {
+        ++n_type[(int)(s_meta[tid] >> 32)]; /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
       }
-      ++cnt.n_steps;
-      live = march_inside(g, s) && s.tau > 0.;
-    }
-
-    /* ---- packets that ended: escaped (left the box) or absorbed (tau used up inside) ---- */
-    const bool fin = has && !live;
-    /* march_inside is idempotent once the periodic wrap has been applied */
-    const bool inside = fin && march_inside(g, s);
-    const bool absorbed = fin && inside;
-    if (fin && !(absorbed && can_reemit)) {
-      int type = (int)(meta >> 32);
-      if (absorbed) type = PACKET_ABSORBED; /* PhotonSource::reemit without a handler (:304-306) */
-      cnt.w_tot += weight;
-#pragma unroll
-      for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? weight : 0.;
-    }
-    if (can_reemit) {
-      const unsigned ab = __ballot_sync(0xffffffffu, absorbed);
-      if (ab) {
-        unsigned long long base = 0;
-        const int leader = __ffs(ab) - 1;
-        if (lane == leader) base = atomicAdd(&W.ctl[CTL_RQCOUNT], (unsigned long long)__popc(ab));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (absorbed) {
-          double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
-          q[RQ_PX * cap] = s.px; q[RQ_PY * cap] = s.py; q[RQ_PZ * cap] = s.pz;
-          q[RQ_SIGH * cap] = sigH;
-          q[RQ_SIGHE * cap] = sigHe;
-          q[RQ_CELL * cap] = __longlong_as_double((long long)s.last_cell);
-          q[RQ_ID * cap] = __longlong_as_double((long long)id);
-          q[RQ_META * cap] = __longlong_as_double((long long)meta);
+      if (can_reemit) {
+        const unsigned ab = __ballot_sync(0xffffffffu, state == LANE_ABSORBED);
+        if (ab) {
+          unsigned long long base = 0;
+          const int leader = __ffs(ab) - 1;
+          if (lane == leader) base = atomicAdd(&W.ctl[CTL_RQCOUNT], (unsigned long long)__popc(ab));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (state == LANE_ABSORBED) {
+            double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
+            q[RQ_PX * cap] = fpx; q[RQ_PY * cap] = fpy; q[RQ_PZ * cap] = fpz;
+            q[RQ_SIGH * cap] = sigH;
+            q[RQ_SIGHE * cap] = (MODE == ACC_FULL) ? s_sig[NMETAL][tid] : 0.;
+            q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
+            q[RQ_ID * cap] = __longlong_as_double((long long)s_id[tid]);
+            q[RQ_META * cap] = __longlong_as_double((long long)s_meta[tid]);
+          }
         }
       }
+      if (state != LANE_LIVE) state = LANE_EMPTY;
+
+      /* ---- refill: hand queue entries to the empty lanes ---- */
+      if (!exhausted) {
+        if (cur == end) {
+          unsigned long long b = 0;
+          if (lane == 0) b = atomicAdd(&W.ctl[CTL_HEAD], (unsigned long long)MARCH_CHUNK);
+          b = __shfl_sync(0xffffffffu, b, 0);
+          if (b >= qcount) {
+            exhausted = true;
+          } else {
+            cur = b;
+            end = (b + MARCH_CHUNK < qcount) ? b + MARCH_CHUNK : qcount;
+          }
+        }
+        if (!exhausted) {
+          const int rank = __popc(waiting & ((1u << lane) - 1u));
+          const uint64_t avail = end - cur;
+          if (state == LANE_EMPTY && (uint64_t)rank < avail) {
+            const double *q = W.mq + (cur + rank);
+            px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
+            dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
+            const double nu = q[MQ_NU * cap];
+            tau = q[MQ_TAU * cap];
+            s_id[tid] = (unsigned long long)__double_as_longlong(q[MQ_ID * cap]);
+            s_meta[tid] = (unsigned long long)__double_as_longlong(q[MQ_META * cap]);
+            sigH = q[MQ_SIGMA * cap];
+            mask = 0;
+            if (MODE == ACC_FULL) {
+              s_sig[NMETAL][tid] = q[(MQ_SIGMA + 1) * cap];
+              sigHe_corr = q[(MQ_SIGMA + NSIG) * cap];
+#pragma unroll
+              for (int k = 0; k < NMETAL; ++k) {
+                const double v = q[(MQ_SIGMA + 2 + k) * cap];
+                s_sig[k][tid] = v;
+                mask |= (v != 0.) ? (1u << (2 + k)) : 0u;
+              }
+            }
+            dnu_H = nu - P.nu_H;
+            dnu_He = nu - P.nu_He;
+            ivx = 1. / dx;
+            ivy = 1. / dy;
+            ivz = 1. / dz;
+            /* get_cell_indices (CartesianDensityGrid.cpp:152-161) */
+            ix = trunc_index(xmul(xsub(px, g.anchor[0]), g.inv_cellside[0]));
+            iy = trunc_index(xmul(xsub(py, g.anchor[1]), g.inv_cellside[1]));
+            iz = trunc_index(xmul(xsub(pz, g.anchor[2]), g.inv_cellside[2]));
+            state = LANE_LIVE;
+            if (any_periodic) {
+              MarchState ms;
+              ms.px = px; ms.py = py; ms.pz = pz; ms.ix = ix; ms.iy = iy; ms.iz = iz;
+              const bool in = march_inside(g, ms);
+              px = ms.px; py = ms.py; pz = ms.pz; ix = ms.ix; iy = ms.iy; iz = ms.iz;
+              if (!in) state = LANE_ESCAPED;
+            } else if ((uint32_t)ix >= ncx || (uint32_t)iy >= ncy || (uint32_t)iz >= ncz) {
+              state = LANE_ESCAPED; /* emitted outside the box: interact() returns end() */
+            }
+            fx = (double)ix; fy = (double)iy; fz = (double)iz;
+          }
+          cur += ((uint64_t)nwait < avail) ? (uint64_t)nwait : avail;
+        }
+      }
+      warp_has_zero_dir = __any_sync(0xffffffffu, state == LANE_LIVE && (dx == 0. || dy == 0. || dz == 0.));
+      continue;
     }
-    if (fin) has = false;
+
+    /* ---- one cell crossing for every live lane ---- */
+    if (state == LANE_LIVE) {
+      cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
+      const CellOpacity c = load_cell(P.cells, cell);
+      /* get_cell / get_wall_intersection (CartesianDensityGrid.cpp:170-176, 280-318) */
+      const double lox = xadd(g.anchor[0], xmul(g.cellside[0], fx));
+      const double loy = xadd(g.anchor[1], xmul(g.cellside[1], fy));
+      const double loz = xadd(g.anchor[2], xmul(g.cellside[2], fz));
+      const bool posx = dx > 0., posy = dy > 0., posz = dz > 0.;
+      double wx = xmul(xsub(xadd(lox, posx ? g.cellside[0] : 0.), px), ivx);
+      double wy = xmul(xsub(xadd(loy, posy ? g.cellside[1] : 0.), py), ivy);
+      double wz = xmul(xsub(xadd(loz, posz ? g.cellside[2] : 0.), pz), ivz);
+      if (warp_has_zero_dir) {
+        if (dx == 0.) wx = DBL_MAX;
+        if (dy == 0.) wy = DBL_MAX;
+        if (dz == 0.) wz = DBL_MAX;
+      }
+      const double myz = (wz < wy) ? wz : wy;
+      ds = (myz < wx) ? myz : wx;
+      /* ds * n * (sigma_H*x_H + sigma_Hecorr*x_He), left to right (DensityGrid.hpp:129-133) */
+      tau_cell = xmul(xmul(ds, c.n), xadd(xmul(sigH, c.xH), xmul(sigHe_corr, c.xHe)));
+      tau = xsub(tau, tau_cell);
+      ++n_steps;
+      if (tau < 0.) {
+        state = LANE_ABSORBED; /* position, ds, tau, tau_cell stay as they are for the deferred finish */
+      } else {
+        if (c.n > 0.) {
+          /* update_integrals (DensityGrid.hpp:150-197); zero increments are skipped (exact) */
+          const double dsw = ds * weight;
+          double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
+          const double dJH = dsw * sigH;
+          if (dJH != 0.) {
+            atomicAdd(a + ION_H_n, dJH);
+            const double dh = dJH * dnu_H;
+            if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
+          }
+          if (MODE == ACC_FULL) {
+            const double dJHe = dsw * s_sig[NMETAL][tid];
+            if (dJHe != 0.) {
+              atomicAdd(a + ION_He_n, dJHe);
+              const double dh = dJHe * dnu_He;
+              if (dh != 0.) atomicAdd(a + NUM_IONS + HEAT_He, dh);
+            }
+            uint32_t mm = mask;
+            while (mm) {
+              const int k = __ffs(mm) - 1;
+              mm &= mm - 1u;
+              const double dJ = dsw * s_sig[k - 2][tid];
+              if (dJ != 0.) atomicAdd(a + k, dJ);
+            }
+          }
+        }
+        /* move to the wall, step the indices of every axis whose wall was hit */
+        const bool hitx = (wx == ds), hity = (wy == ds), hitz = (wz == ds);
+        px = xadd(px, xmul(ds, dx));
+        py = xadd(py, xmul(ds, dy));
+        pz = xadd(pz, xmul(ds, dz));
+        ix += hitx ? (posx ? 1 : -1) : 0;
+        iy += hity ? (posy ? 1 : -1) : 0;
+        iz += hitz ? (posz ? 1 : -1) : 0;
+        fx += hitx ? (posx ? 1. : -1.) : 0.;
+        fy += hity ? (posy ? 1. : -1.) : 0.;
+        fz += hitz ? (posz ? 1. : -1.) : 0.;
+        if (any_periodic) {
+          MarchState ms;
+          ms.px = px; ms.py = py; ms.pz = pz; ms.ix = ix; ms.iy = iy; ms.iz = iz;
+          const bool in = march_inside(g, ms);
+          px = ms.px; py = ms.py; pz = ms.pz;
+          if (ms.ix != ix) { ix = ms.ix; fx = (double)ix; }
+          if (ms.iy != iy) { iy = ms.iy; fy = (double)iy; }
+          if (ms.iz != iz) { iz = ms.iz; fz = (double)iz; }
+          if (!in) state = LANE_ESCAPED;
+        } else if ((uint32_t)ix >= ncx || (uint32_t)iy >= ncy || (uint32_t)iz >= ncz) {
+          state = LANE_ESCAPED;
+        }
+        /* tau == 0 exactly: the walk ends inside (loop condition tau > 0, :391), on the wall */
+        if (state == LANE_LIVE && !(tau > 0.)) state = LANE_ABSORBED;
+      }
+    }
+  }
+  ShootCounters cnt;
+  cnt.n_steps = n_steps;
+#pragma unroll
+  for (int t = 0; t < NUM_PACKET_TYPES; ++t) {
+    cnt.w_type[t] = (double)n_type[t] * weight;
+    cnt.w_tot += cnt.w_type[t];
   }
   reduce_counters(P.acc, cnt);
 }

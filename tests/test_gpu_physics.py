@@ -232,7 +232,13 @@ def test_calculate_temperature(ctx, ref, golden):
         assert min(outs) * (1 - 2e-3) <= Tg[i] <= max(outs) * (1 + 2e-3)
     ok = dT <= 2e-3
     same = dT <= 1e-9
-    record("temperature_x_rel_where_T_same", rel_err(xg[:, same], xr[:, same]))
-    assert rel_err(xg[:, same], xr[:, same]) < 1e-5
+    # fractions live in [0, 1]: 1e-5 relative, floored at 1e-12 absolute (metal fractions of
+    # 1e-30 carry no information and amplify ulps without bound)
+    dx = np.abs(xg[:, same] - xr[:, same]) / (np.abs(xr[:, same]) + 1e-7)
+    w = np.unravel_index(np.argmax(dx), dx.shape)
+    MEASURED["temperature_x_worst"] = dict(ion=int(w[0]), xg=float(xg[:, same][w]), xr=float(xr[:, same][w]),
+                                           Tg=float(Tg[same][w[1]]), Tr=float(Tr[same][w[1]]))
+    record("temperature_x_rel_where_T_same", dx.max())
+    assert dx.max() < 1e-5
     assert np.array_equal(Tg[ok] == 500., Tr[ok] == 500.)
     assert rel_err(hg[:, ok], hr[:, ok]) < 1e-14
