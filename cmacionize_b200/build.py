@@ -51,5 +51,29 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST = HERE / "host"
+HOST_LIB = HERE / "libcmih.so"
+HOST_BIN = HERE / "bin" / "CMacIonizeB200"
+
+
+def build_host(force: bool = False) -> Path:
+    """C++ host layer (parameter file, plugin classes, IonizationSimulation driver) as a shared
+    library over libcmib.so + the command line program.  Plain g++: no CUDA in this layer."""
+    deps = list(HOST.glob("*")) + [HERE.parent / "include" / "cmib.h"]
+    stale = (not HOST_LIB.exists() or not HOST_BIN.exists()
+             or any(p.stat().st_mtime > min(HOST_LIB.stat().st_mtime, HOST_BIN.stat().st_mtime) for p in deps))
+    if not force and not stale:
+        return HOST_LIB
+    HOST_BIN.parent.mkdir(exist_ok=True)
+    common = ["g++", "-std=c++17", "-O2", "-Wall", "-ffp-contract=off", "-fPIC"]
+    link = [f"-L{HERE}", "-lcmib", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(common + ["-shared", str(HOST / "host_api.cpp"), "-o", str(HOST_LIB)] + link)
+    link_bin = [f"-L{HERE}", "-lcmib", "-Wl,-rpath,$ORIGIN/.."]
+    subprocess.check_call(common + [str(HOST / "CMacIonizeB200.cpp"), "-o", str(HOST_BIN)] + link_bin)
+    print(f"built {HOST_LIB} and {HOST_BIN}")
+    return HOST_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host(force="--force" in sys.argv)

@@ -1,0 +1,133 @@
+"""ctypes binding of the C++ host layer (``libcmih.so``: host/IonizationSimulation.hpp behind
+host/host_api.cpp) — the reference-facing surface: a parameter file in, an
+``IonizationSimulation`` that is initialised and run, fields out.
+
+Nothing here computes: the host layer configures a ``cmib_context`` and orders the C-ABI calls of
+one iteration; all physics runs in the CUDA library."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import capi
+
+LIB_PATH = Path(__file__).resolve().parent / "libcmih.so"
+if not LIB_PATH.exists():
+    raise ImportError(f"{LIB_PATH} is missing: build it with `python -m cmacionize_b200.build`")
+lib = C.CDLL(str(LIB_PATH))
+lib.cmih_last_error.restype = C.c_char_p
+
+QUANTITY = {"length": 6, "number_density": 8, "reaction_rate": 9, "surface_area": 10, "temperature": 11,
+            "frequency": 5}
+
+
+class HostError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise HostError(lib.cmih_last_error().decode())
+
+
+def convert(value, unit_from, unit_to):
+    out = C.c_double()
+    _check(lib.cmih_convert(C.c_double(value), unit_from.encode(), unit_to.encode(), C.byref(out)))
+    return out.value
+
+
+class ParameterFile:
+    def __init__(self, filename):
+        self._h = C.c_void_p()
+        _check(lib.cmih_paramfile_open(str(filename).encode(), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib.cmih_paramfile_close(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        self.close()
+
+    def get_string(self, key, default=""):
+        buf = C.create_string_buffer(4096)
+        _check(lib.cmih_paramfile_get_string(self._h, key.encode(), default.encode(), buf, 4096))
+        return buf.value.decode()
+
+    def get_double(self, key, default):
+        out = C.c_double()
+        _check(lib.cmih_paramfile_get_double(self._h, key.encode(), C.c_double(default), C.byref(out)))
+        return out.value
+
+    def get_physical(self, quantity, key, default):
+        out = C.c_double()
+        _check(lib.cmih_paramfile_get_physical(self._h, QUANTITY[quantity], key.encode(), default.encode(),
+                                               C.byref(out)))
+        return out.value
+
+    def used_values(self):
+        buf = C.create_string_buffer(1 << 16)
+        _check(lib.cmih_paramfile_used_values(self._h, buf, 1 << 16))
+        return buf.value.decode()
+
+    def density_function(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
+        n = x.shape[0]
+        dens, temp, xH = np.empty(n), np.empty(n), np.empty(n)
+        vp = C.c_void_p
+        _check(lib.cmih_density_function(self._h, C.c_int64(n), x.ctypes.data_as(vp), dens.ctypes.data_as(vp),
+                                         temp.ctypes.data_as(vp), xH.ctypes.data_as(vp)))
+        return dens, temp, xH
+
+
+class IonizationSimulation:
+    """cmi::IonizationSimulation (host/IonizationSimulation.hpp) on one GPU."""
+
+    def __init__(self, parameterfile, device=0, write_output=False, verbose=False):
+        self._h = C.c_void_p()
+        _check(lib.cmih_simulation_create(str(parameterfile).encode(), C.c_int(device),
+                                          C.c_int(1 if write_output else 0), C.c_int(1 if verbose else 0),
+                                          C.byref(self._h)))
+        info = (C.c_double * 4)()
+        _check(lib.cmih_simulation_info(self._h, info))
+        self.ncells = int(info[0])
+        self.number_of_iterations = int(info[1])
+        self.number_of_photons = int(info[2])
+        self.total_luminosity = float(info[3])
+
+    def close(self):
+        if self._h:
+            lib.cmih_simulation_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initialize(self):
+        _check(lib.cmih_simulation_initialize(self._h))
+
+    def run(self):
+        _check(lib.cmih_simulation_run(self._h))
+
+    def iteration(self, loop, numphoton):
+        out = (C.c_double * 8)()
+        _check(lib.cmih_simulation_iteration(self._h, C.c_uint32(loop), C.c_uint64(int(numphoton)), out))
+        return dict(totweight=out[0], typecount=np.array(out[1:5]), shoot_s=out[5], update_s=out[6])
+
+    def fields(self):
+        """(number density, temperature, ionic fractions [14][ncell], heating [2][ncell])"""
+        ctx = C.c_void_p()
+        _check(lib.cmih_simulation_context(self._h, C.byref(ctx)))
+        n = np.empty(self.ncells); T = np.empty(self.ncells)
+        x = np.empty((capi.NUM_IONS, self.ncells)); heat = np.empty((capi.NUM_HEAT, self.ncells))
+        vp = C.c_void_p
+        rc = capi.lib.cmib_download_cells(ctx, n.ctypes.data_as(vp), T.ctypes.data_as(vp), x.ctypes.data_as(vp),
+                                          heat.ctypes.data_as(vp))
+        if rc != 0:
+            raise HostError(capi.lib.cmib_last_error().decode())
+        return n, T, x, heat

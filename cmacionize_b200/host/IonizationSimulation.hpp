@@ -1,0 +1,733 @@
+/*
+ * IonizationSimulation.hpp — C++ host layer of the B200 backend: the reference's
+ * plugin classes for the photoionization path, re-implemented as thin owners of
+ * parameters that configure one `cmib_context` (include/cmib.h) per GPU.
+ *
+ * Same class names, parameter keys, defaults and error messages as the reference so
+ * that an existing parameter file and an existing caller keep working:
+ *
+ *   this file                       reference (under /root/reference/src)
+ *   ------------------------------  -------------------------------------------------
+ *   SimulationBox                   SimulationBox.hpp:63-72
+ *   DensityFunction (+Factory)      DensityFunctionFactory.hpp; HomogeneousDensityFunction.hpp:83-108;
+ *                                   BlockSyntaxDensityFunction.hpp:75-199, BlockSyntaxBlock.hpp:91-106
+ *   PhotonSourceDistribution        PhotonSourceDistributionFactory.hpp:99; SingleStarPhotonSourceDistribution.hpp:78-85;
+ *                                   AsciiFileTablePhotonSourceDistribution.cpp:40-118
+ *   PhotonSourceSpectrum            PhotonSourceSpectrumFactory.hpp:84-152; Monochromatic...hpp:78-86; Planck...cpp:128-139
+ *   CrossSections                   CrossSectionsFactory.hpp:60-80; FixedValueCrossSections.hpp:112-141
+ *   RecombinationRates              RecombinationRatesFactory.hpp:59-72; FixedValueRecombinationRates.hpp:118-147
+ *   AbundanceModel                  AbundanceModelFactory.hpp:54-89; FixedValueAbundanceModel.hpp:54-60
+ *   DiffuseReemissionHandler        DiffuseReemissionHandlerFactory.hpp:59-107; FixedValueDiffuseReemissionHandler.hpp:66-72
+ *   TemperatureCalculator params    TemperatureCalculator.cpp:133-160
+ *   CartesianDensityGrid            CartesianDensityGrid.cpp:44-134, .hpp:85-144; DensityGrid.hpp:235-259,775-790
+ *   AsciiFileDensityGridWriter      AsciiFileDensityGridWriter.cpp:58-95
+ *   IonizationSimulation            IonizationSimulation.cpp:101-231 (ctor), :239-326 (initialize), :334-679 (run)
+ *
+ * What is NOT here: every compute step.  Emission, the voxel walk, accumulation,
+ * re-emission and the per-cell ionization/temperature solve run on the GPU behind
+ * the C ABI; this layer only builds inputs, orders the calls of one iteration and
+ * moves results.  There is no CPU compute path.
+ */
+#pragma once
+#include <array>
+#include <chrono>
+#include <cinttypes>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/cmib.h"
+#include "Error.hpp"
+#include "ParameterFile.hpp"
+
+namespace cmi {
+
+using Vec3 = std::array<double, 3>;
+
+/* ---- logging: same levels as the reference's Log (Log.hpp:41-46), terminal only ---- */
+class Log {
+public:
+  enum Level { INFO = 0, STATUS, WARNING, ERROR_ };
+  explicit Log(Level level = STATUS, std::ostream &out = std::cerr) : level_(level), out_(out) {}
+  template <class... A> void write_info(const A &...a) { write(INFO, a...); }
+  template <class... A> void write_status(const A &...a) { write(STATUS, a...); }
+  template <class... A> void write_warning(const A &...a) { write(WARNING, a...); }
+
+private:
+  Level level_;
+  std::ostream &out_;
+  template <class... A> void write(Level l, const A &...a) {
+    if (l < level_) return;
+    std::ostringstream s;
+    (void)std::initializer_list<int>{(s << a, 0)...};
+    out_ << s.str() << "\n";
+  }
+};
+
+#define CMIB_CALL(expr)                                                                         \
+  do {                                                                                          \
+    if ((expr) != 0) cmi_error("%s failed: %s", #expr, cmib_last_error());                      \
+  } while (0)
+
+/* ---- ion / element names of the parameter files (ElementNames.hpp:107-160, 52-88) ---- */
+inline const char *ion_name(int ion) {
+  static const char *names[CMIB_NUM_IONS] = {"H_n", "He_n", "C_p1", "C_p2", "N_n", "N_p1", "N_p2",
+                                             "O_n", "O_p1", "Ne_n", "Ne_p1", "S_p1", "S_p2", "S_p3"};
+  return names[ion];
+}
+inline const char *element_name(int el) {
+  static const char *names[CMIB_NUM_ELEMENTS] = {"He", "C", "N", "O", "Ne", "S"};
+  return names[el];
+}
+
+struct SimulationBox {
+  Vec3 anchor, sides;
+  std::array<bool, 3> periodicity;
+  explicit SimulationBox(ParameterFile &params)
+      : anchor(params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:anchor", "[-5. pc, -5. pc, -5. pc]")),
+        sides(params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:sides", "[10. pc, 10. pc, 10. pc]")),
+        periodicity(params.get_value<std::array<bool, 3>>("SimulationBox:periodicity", {false, false, false})) {}
+};
+
+/* ---- DensityFunction ---- */
+struct DensityValues {
+  double number_density = 0.;
+  double temperature = 0.;
+  double ionic_fraction[CMIB_NUM_IONS] = {0.};
+  double cosmic_ray_factor = -1.; /* DensityValues.hpp:65-71 */
+};
+
+class DensityFunction {
+public:
+  virtual ~DensityFunction() {}
+  virtual void initialize() {}
+  virtual DensityValues operator()(const Vec3 &cell_midpoint) = 0;
+};
+
+class HomogeneousDensityFunction : public DensityFunction {
+public:
+  HomogeneousDensityFunction(double density, double temperature, double neutral_fraction_H)
+      : density_(density), temperature_(temperature), neutral_fraction_H_(neutral_fraction_H) {}
+  explicit HomogeneousDensityFunction(ParameterFile &params)
+      : HomogeneousDensityFunction(
+            params.get_physical_value<QUANTITY_NUMBER_DENSITY>("DensityFunction:density", "100. cm^-3"),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "8000. K"),
+            params.get_value<double>("DensityFunction:neutral fraction H", 1.e-6)) {}
+  DensityValues operator()(const Vec3 &) override {
+    DensityValues v;
+    v.number_density = density_;
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = neutral_fraction_H_;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  double density_, temperature_, neutral_fraction_H_;
+};
+
+class BlockSyntaxDensityFunction : public DensityFunction {
+  struct Block {
+    Vec3 origin, sides;
+    double exponent, number_density, temperature, neutral_fraction_H;
+    bool is_inside(const Vec3 &p) const {
+      double r = 0.;
+      for (int i = 0; i < 3; ++i) {
+        const double x = 2. * std::abs(p[i] - origin[i]) / sides[i];
+        if (exponent < 10.) r += std::pow(x, exponent);
+        else r = std::max(r, x);
+      }
+      if (exponent < 10.) r = std::pow(r, 1. / exponent);
+      return r <= 1.;
+    }
+  };
+
+public:
+  explicit BlockSyntaxDensityFunction(const std::string &filename) {
+    std::ifstream file(filename);
+    if (!file) cmi_error("Error while opening file \"%s\"!", filename.c_str());
+    YAMLDictionary blockfile(file);
+    const uint32_t numblock = blockfile.get_value<uint32_t>("number of blocks");
+    for (uint32_t i = 0; i < numblock; ++i) {
+      const std::string name = "block[" + std::to_string(i) + "]:";
+      Block b;
+      b.origin = blockfile.get_physical_vector<QUANTITY_LENGTH>(name + "origin");
+      b.sides = blockfile.get_physical_vector<QUANTITY_LENGTH>(name + "sides");
+      const std::string type = blockfile.get_value<std::string>(name + "type");
+      if (type == "rhombus") b.exponent = 1.;
+      else if (type == "sphere") b.exponent = 2.;
+      else if (type == "cube") b.exponent = 10.;
+      else cmi_error("Unknown block type: \"%s\"!", type.c_str());
+      if (blockfile.has_value(name + "number density")) {
+        b.number_density = blockfile.get_physical_value<QUANTITY_NUMBER_DENSITY>(name + "number density");
+      } else {
+        b.number_density = blockfile.get_physical_value<QUANTITY_DENSITY>(name + "density");
+        b.number_density /= constants::proton_mass;
+      }
+      b.temperature = blockfile.get_physical_value<QUANTITY_TEMPERATURE>(name + "initial temperature");
+      b.neutral_fraction_H = blockfile.get_value<double>(name + "neutral fraction H", 1.e-6);
+      (void)blockfile.get_physical_vector<QUANTITY_VELOCITY>(name + "initial velocity", "[0. m s^-1, 0. m s^-1, 0. m s^-1]");
+      if (b.number_density < 0.) cmi_error("Negative density (%g) given for block %u!", b.number_density, i);
+      if (b.temperature < 0.) cmi_error("Negative temperature (%g) given for block %u!", b.temperature, i);
+      blocks_.push_back(b);
+    }
+    std::ofstream ofile(filename + ".used-values");
+    blockfile.print_contents(ofile, true);
+  }
+  explicit BlockSyntaxDensityFunction(ParameterFile &params)
+      : BlockSyntaxDensityFunction(params.get_filename("DensityFunction:filename")) {}
+
+  DensityValues operator()(const Vec3 &position) override {
+    double density = -1., temperature = -1., xH = -1.;
+    for (const Block &b : blocks_) { /* later blocks win */
+      if (b.is_inside(position)) {
+        density = b.number_density;
+        temperature = b.temperature;
+        xH = b.neutral_fraction_H;
+      }
+    }
+    if (density < 0. || temperature < 0. || xH < 0.)
+      cmi_error("No block found containing position [%g m, %g m, %g m]!", position[0], position[1], position[2]);
+    DensityValues v;
+    v.number_density = density;
+    v.temperature = temperature;
+    v.ionic_fraction[0] = xH;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  std::vector<Block> blocks_;
+};
+
+struct DensityFunctionFactory {
+  static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
+    if (log) log->write_info("Requested DensityFunction type: ", type);
+    if (type == "Homogeneous") return new HomogeneousDensityFunction(params);
+    if (type == "BlockSyntax") return new BlockSyntaxDensityFunction(params);
+    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous and BlockSyntax)!",
+              type.c_str());
+  }
+};
+
+/* ---- PhotonSourceDistribution ---- */
+class PhotonSourceDistribution {
+public:
+  virtual ~PhotonSourceDistribution() {}
+  virtual size_t get_number_of_sources() const = 0;
+  virtual Vec3 get_position(size_t index) = 0;
+  virtual double get_weight(size_t index) const = 0;
+  virtual double get_total_luminosity() const = 0;
+};
+
+class SingleStarPhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  SingleStarPhotonSourceDistribution(const Vec3 &position, double luminosity)
+      : position_(position), luminosity_(luminosity) {}
+  explicit SingleStarPhotonSourceDistribution(ParameterFile &params)
+      : SingleStarPhotonSourceDistribution(
+            params.get_physical_vector<QUANTITY_LENGTH>("PhotonSourceDistribution:position", "[0. pc, 0. pc, 0. pc]"),
+            params.get_physical_value<QUANTITY_FREQUENCY>("PhotonSourceDistribution:luminosity", "4.26e49 s^-1")) {}
+  size_t get_number_of_sources() const override { return 1; }
+  Vec3 get_position(size_t) override { return position_; }
+  double get_weight(size_t) const override { return 1.; }
+  double get_total_luminosity() const override { return luminosity_; }
+
+private:
+  Vec3 position_;
+  double luminosity_;
+};
+
+/* number of sources, total luminosity, then "x y z weight" rows (SI); '#' comments */
+class AsciiFileTablePhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  explicit AsciiFileTablePhotonSourceDistribution(const std::string &filename) {
+    std::ifstream file(filename);
+    if (!file.is_open()) cmi_error("Could not open file \"%s\"!", filename.c_str());
+    std::string line;
+    size_t n = 0, got = 0;
+    int stage = 0;
+    while (std::getline(file, line)) {
+      if (line.empty() || line[0] == '#') continue;
+      std::stringstream ls(line);
+      if (stage == 0) {
+        ls >> n;
+        positions_.resize(n);
+        weights_.resize(n);
+        stage = 1;
+      } else if (stage == 1) {
+        ls >> luminosity_;
+        stage = 2;
+      } else {
+        if (got == n) break;
+        ls >> positions_[got][0] >> positions_[got][1] >> positions_[got][2] >> weights_[got];
+        ++got;
+      }
+    }
+    if (got < n) cmi_error("The file %s has fewer sources (%zu) than needed (%zu).\n", filename.c_str(), got, n);
+  }
+  explicit AsciiFileTablePhotonSourceDistribution(ParameterFile &params)
+      : AsciiFileTablePhotonSourceDistribution(
+            params.get_value<std::string>("PhotonSourceDistribution:filename", "sinks.txt")) {}
+  size_t get_number_of_sources() const override { return positions_.size(); }
+  Vec3 get_position(size_t i) override { return positions_[i]; }
+  double get_weight(size_t i) const override { return weights_[i]; }
+  double get_total_luminosity() const override { return luminosity_; }
+
+private:
+  std::vector<Vec3> positions_;
+  std::vector<double> weights_;
+  double luminosity_ = 0.;
+};
+
+struct PhotonSourceDistributionFactory {
+  static PhotonSourceDistribution *generate(ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>("PhotonSourceDistribution:type", "SingleStar");
+    if (log) log->write_info("Requested PhotonSourceDistribution type: ", type);
+    if (type == "SingleStar") return new SingleStarPhotonSourceDistribution(params);
+    if (type == "AsciiFileTable") return new AsciiFileTablePhotonSourceDistribution(params);
+    if (type == "None") return nullptr;
+    cmi_error("Unknown PhotonSourceDistribution type: \"%s\" (the B200 backend provides SingleStar and AsciiFileTable)!",
+              type.c_str());
+  }
+};
+
+/* ---- plugins that are pure parameters for the device ---- */
+struct PhotonSourceSpectrum {
+  int kind;     /* CMIB_SPECTRUM_* */
+  double param; /* frequency (Hz) or temperature (K) */
+  double total_flux = -1.;
+  static PhotonSourceSpectrum *generate(const std::string &role, ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>(role + ":type", "Monochromatic");
+    if (log) log->write_info("Requested PhotonSourceSpectrum for ", role, ": ", type);
+    if (type == "Monochromatic") {
+      auto *s = new PhotonSourceSpectrum{CMIB_SPECTRUM_MONOCHROMATIC,
+                                         params.get_physical_value<QUANTITY_FREQUENCY>(role + ":frequency", "13.6 eV")};
+      s->total_flux = params.get_physical_value<QUANTITY_FLUX>(role + ":total flux", "-1. m^-2 s^-1");
+      return s;
+    }
+    if (type == "Planck") {
+      auto *s = new PhotonSourceSpectrum{CMIB_SPECTRUM_PLANCK,
+                                         params.get_physical_value<QUANTITY_TEMPERATURE>(role + ":temperature", "4.e4 K")};
+      s->total_flux = params.get_physical_value<QUANTITY_FLUX>(role + ":ionizing flux", "-1. m^-2 s^-1");
+      return s;
+    }
+    if (type == "None") return nullptr;
+    cmi_error("Unknown PhotonSourceSpectrum type: \"%s\" (the B200 backend provides Monochromatic and Planck)!",
+              type.c_str());
+  }
+};
+
+struct CrossSections {
+  int kind;
+  double fixed[CMIB_NUM_IONS] = {0.};
+  static CrossSections *generate(ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>("CrossSections:type", "Verner");
+    if (log) log->write_info("Requested CrossSections type: ", type);
+    auto *c = new CrossSections();
+    if (type == "Verner") {
+      c->kind = CMIB_CROSS_SECTIONS_VERNER;
+    } else if (type == "FixedValue") {
+      c->kind = CMIB_CROSS_SECTIONS_FIXED_VALUE;
+      static const char *keys[CMIB_NUM_IONS] = {"hydrogen_0", "helium_0", "carbon_1", "carbon_2", "nitrogen_0",
+                                                "nitrogen_1", "nitrogen_2", "oxygen_0", "oxygen_1", "neon_0",
+                                                "neon_1", "sulphur_1", "sulphur_2", "sulphur_3"};
+      for (int i = 0; i < CMIB_NUM_IONS; ++i)
+        c->fixed[i] = params.get_physical_value<QUANTITY_SURFACE_AREA>(std::string("CrossSections:") + keys[i],
+                                                                      i == 0 ? "6.3e-18 cm^2" : "0. m^2");
+    } else {
+      delete c;
+      cmi_error("Unknown CrossSections type: \"%s\"!", type.c_str());
+    }
+    return c;
+  }
+};
+
+struct RecombinationRates {
+  int kind;
+  double fixed[CMIB_NUM_IONS] = {0.};
+  static RecombinationRates *generate(ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>("RecombinationRates:type", "Verner");
+    if (log) log->write_info("Requested RecombinationRates type: ", type);
+    auto *r = new RecombinationRates();
+    if (type == "Verner") {
+      r->kind = CMIB_RECOMBINATION_VERNER;
+    } else if (type == "FixedValue") {
+      r->kind = CMIB_RECOMBINATION_FIXED_VALUE;
+      static const char *keys[CMIB_NUM_IONS] = {"hydrogen_1", "helium_1", "carbon_2", "carbon_3", "nitrogen_1",
+                                                "nitrogen_2", "nitrogen_3", "oxygen_1", "oxygen_2", "neon_1",
+                                                "neon_2", "sulphur_2", "sulphur_3", "sulphur_4"};
+      for (int i = 0; i < CMIB_NUM_IONS; ++i)
+        r->fixed[i] = params.get_physical_value<QUANTITY_REACTION_RATE>(
+            std::string("RecombinationRates:") + keys[i], i == 0 ? "2.7e-13 cm^3 s^-1" : "0. m^3 s^-1");
+    } else {
+      delete r;
+      cmi_error("Unknown RecombinationRates type: \"%s\"!", type.c_str());
+    }
+    return r;
+  }
+};
+
+struct Abundances {
+  double abundance[CMIB_NUM_ELEMENTS] = {0.};
+  static Abundances generate(ParameterFile &params, Log *log = nullptr) {
+    /* deprecated "Abundances:helium" style block -> AbundanceModel (AbundanceModelFactory.hpp:54-86) */
+    static const char *old_names[CMIB_NUM_ELEMENTS] = {"helium", "carbon", "nitrogen", "oxygen", "neon", "sulphur"};
+    if (!params.has_value("AbundanceModel:type")) {
+      bool migrated = false;
+      for (int i = 0; i < CMIB_NUM_ELEMENTS; ++i) {
+        const std::string old_key = std::string("Abundances:") + old_names[i];
+        if (params.has_value(old_key)) {
+          params.add_value(std::string("AbundanceModel:") + element_name(i), params.get_value<std::string>(old_key));
+          migrated = true;
+        }
+      }
+      if (migrated) {
+        params.add_value("AbundanceModel:type", "FixedValue");
+        if (log) log->write_warning("Deprecated Abundances block converted to AbundanceModel:type FixedValue.");
+      }
+    }
+    const std::string type = params.get_value<std::string>("AbundanceModel:type", "FixedValue");
+    if (type != "FixedValue") cmi_error("Unknown AbundanceModel type: \"%s\"!", type.c_str());
+    Abundances a;
+    for (int i = 0; i < CMIB_NUM_ELEMENTS; ++i)
+      a.abundance[i] = params.get_value<double>(std::string("AbundanceModel:") + element_name(i), 0.);
+    return a;
+  }
+};
+
+struct DiffuseReemissionHandler {
+  int kind = CMIB_REEMISSION_NONE;
+  double probability = 0.364, frequency = 0.;
+  static DiffuseReemissionHandler generate(ParameterFile &params, Log *log = nullptr) {
+    if (!params.has_value("DiffuseReemissionHandler:type") && params.has_value("PhotonSource:diffuse field")) {
+      if (log) log->write_warning("\"PhotonSource:diffuse field\" was replaced by \"DiffuseReemissionHandler\"; converting.");
+      const bool on = params.get_value<bool>("PhotonSource:diffuse field", false);
+      params.add_value("DiffuseReemissionHandler:type", on ? "Physical" : "None");
+    }
+    const std::string type = params.get_value<std::string>("DiffuseReemissionHandler:type", "None");
+    if (log) log->write_info("Requested DiffuseReemissionHandler type: ", type);
+    DiffuseReemissionHandler h;
+    if (type == "FixedValue") {
+      h.kind = CMIB_REEMISSION_FIXED_VALUE;
+      h.probability = params.get_value<double>("DiffuseReemissionHandler:reemission probability", 0.364);
+      h.frequency = params.get_physical_value<QUANTITY_FREQUENCY>("DiffuseReemissionHandler:reemission frequency", "19.8 eV");
+    } else if (type == "Physical") {
+      h.kind = CMIB_REEMISSION_PHYSICAL;
+    } else if (type == "None") {
+      h.kind = CMIB_REEMISSION_NONE;
+    } else {
+      cmi_error("Unknown DiffuseReemissionHandler type: \"%s\"!", type.c_str());
+    }
+    return h;
+  }
+};
+
+inline cmib_temperature_params temperature_calculator_parameters(ParameterFile &params) {
+  cmib_temperature_params p;
+  p.do_temperature_calculation = params.get_value<bool>("TemperatureCalculator:do temperature calculation", false);
+  p.minimum_number_of_iterations = params.get_value<uint32_t>("TemperatureCalculator:minimum number of iterations", 3);
+  p.epsilon_convergence = params.get_value<double>("TemperatureCalculator:epsilon convergence", 1.e-3);
+  p.maximum_number_of_iterations = params.get_value<uint32_t>("TemperatureCalculator:maximum number of iterations", 100);
+  p.pah_heating_factor = params.get_value<double>("TemperatureCalculator:PAH heating factor", 0.);
+  p.cosmic_ray_heating_factor = params.get_value<double>("TemperatureCalculator:cosmic ray heating factor", 0.);
+  p.cosmic_ray_heating_limit = params.get_value<double>("TemperatureCalculator:cosmic ray heating limit", 0.75);
+  p.cosmic_ray_heating_scale_length =
+      params.get_physical_value<QUANTITY_LENGTH>("TemperatureCalculator:cosmic ray heating scale length", "1.33333 kpc");
+  p.minimum_ionized_temperature =
+      params.get_physical_value<QUANTITY_TEMPERATURE>("TemperatureCalculator:minimum ionized temperature", "4000. K");
+  return p;
+}
+
+/* ---- CartesianDensityGrid: host mirror of the cells + owner of the device context ---- */
+class CartesianDensityGrid {
+public:
+  CartesianDensityGrid(const SimulationBox &box, const std::array<int32_t, 3> &ncell, int device = 0)
+      : anchor_(box.anchor), sides_(box.sides), ncell_(ncell), periodicity_(box.periodicity) {
+    cmib_grid_desc d;
+    for (int k = 0; k < 3; ++k) {
+      d.anchor[k] = anchor_[k];
+      d.sides[k] = sides_[k];
+      d.ncell[k] = ncell_[k];
+      d.periodic[k] = periodicity_[k] ? 1 : 0;
+      cellside_[k] = sides_[k] / ncell_[k]; /* CartesianDensityGrid.cpp:80-86 */
+    }
+    CMIB_CALL(cmib_create(&d, device, &ctx_));
+    const size_t n = get_number_of_cells();
+    number_density.assign(n, 0.);
+    temperature.assign(n, 0.);
+    ionic_fraction.assign(n * CMIB_NUM_IONS, 0.);
+  }
+  CartesianDensityGrid(const SimulationBox &box, ParameterFile &params, int device = 0)
+      : CartesianDensityGrid(box, params.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}),
+                             device) {}
+  ~CartesianDensityGrid() {
+    if (ctx_) cmib_destroy(ctx_);
+  }
+  CartesianDensityGrid(const CartesianDensityGrid &) = delete;
+  CartesianDensityGrid &operator=(const CartesianDensityGrid &) = delete;
+
+  size_t get_number_of_cells() const { return (size_t)ncell_[0] * ncell_[1] * ncell_[2]; }
+  /* long index ix*ny*nz + iy*nz + iz (CartesianDensityGrid.hpp:137-144) */
+  Vec3 get_cell_midpoint(size_t index) const {
+    const size_t nyz = (size_t)ncell_[1] * ncell_[2];
+    const size_t ix = index / nyz, iy = (index % nyz) / ncell_[2], iz = index % ncell_[2];
+    const size_t i[3] = {ix, iy, iz};
+    Vec3 m;
+    for (int k = 0; k < 3; ++k) m[k] = anchor_[k] + cellside_[k] * (double)i[k] + 0.5 * cellside_[k];
+    return m;
+  }
+  double get_cell_volume() const { return cellside_[0] * cellside_[1] * cellside_[2]; }
+
+  /* DensityGrid::set_densities: evaluate the DensityFunction at every cell midpoint, upload */
+  void initialize(DensityFunction &function) {
+    const size_t n = get_number_of_cells();
+    for (size_t i = 0; i < n; ++i) {
+      const DensityValues v = function(get_cell_midpoint(i));
+      number_density[i] = v.number_density;
+      temperature[i] = v.temperature;
+      for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) ionic_fraction[(size_t)ion * n + i] = v.ionic_fraction[ion];
+    }
+    upload();
+  }
+  void upload() {
+    CMIB_CALL(cmib_upload_cells(ctx_, number_density.data(), temperature.data(), ionic_fraction.data(), nullptr));
+  }
+  /* refresh the host mirror (for writers) */
+  void download() {
+    CMIB_CALL(cmib_download_cells(ctx_, number_density.data(), temperature.data(), ionic_fraction.data(), nullptr));
+  }
+  void reset_grid() { CMIB_CALL(cmib_reset_accumulators(ctx_)); }
+  cmib_context *context() { return ctx_; }
+  const std::array<int32_t, 3> &get_number_of_cells_3d() const { return ncell_; }
+
+  /* host mirror, [ncell] and [14][ncell] in the reference's cell / ion order */
+  std::vector<double> number_density, temperature, ionic_fraction;
+
+private:
+  Vec3 anchor_, sides_, cellside_;
+  std::array<int32_t, 3> ncell_;
+  std::array<bool, 3> periodicity_;
+  cmib_context *ctx_ = nullptr;
+};
+
+/* ---- writer: the reference's ASCII snapshot layout, optionally with every field ---- */
+class AsciiFileDensityGridWriter {
+public:
+  AsciiFileDensityGridWriter(std::string prefix, std::string output_folder, bool all_fields = false)
+      : prefix_(std::move(prefix)), folder_(std::move(output_folder)), all_fields_(all_fields) {}
+  AsciiFileDensityGridWriter(const std::string &output_folder, ParameterFile &params)
+      : AsciiFileDensityGridWriter(params.get_value<std::string>("DensityGridWriter:prefix", "snapshot"), output_folder,
+                                   params.get_value<bool>("DensityGridWriter:all fields", false)) {}
+  std::string filename(uint32_t iteration) const {
+    char num[16];
+    snprintf(num, sizeof(num), "%03u", iteration);
+    return folder_ + "/" + prefix_ + num + ".txt";
+  }
+  void write(CartesianDensityGrid &grid, uint32_t iteration) {
+    grid.download();
+    std::ofstream file(filename(iteration));
+    if (!file) cmi_error("Unable to open snapshot file \"%s\"!", filename(iteration).c_str());
+    const size_t n = grid.get_number_of_cells();
+    const double volume = grid.get_cell_volume();
+    if (!all_fields_) {
+      /* AsciiFileDensityGridWriter.cpp:75-95 */
+      file << "#x (m)\ty (m)\tz (m)\tn (m^-3)\tvolume (m^3)\tneutral H fraction\n";
+      for (size_t i = 0; i < n; ++i) {
+        const Vec3 x = grid.get_cell_midpoint(i);
+        file << x[0] << "\t" << x[1] << "\t" << x[2] << "\t" << grid.number_density[i] << "\t" << volume << "\t"
+             << grid.ionic_fraction[i] << "\n";
+      }
+    } else {
+      file << "#x (m)\ty (m)\tz (m)\tn (m^-3)\tvolume (m^3)\tT (K)";
+      for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) file << "\tNeutralFraction" << ion_name(ion);
+      file << "\n" << std::setprecision(17);
+      for (size_t i = 0; i < n; ++i) {
+        const Vec3 x = grid.get_cell_midpoint(i);
+        file << x[0] << "\t" << x[1] << "\t" << x[2] << "\t" << grid.number_density[i] << "\t" << volume << "\t"
+             << grid.temperature[i];
+        for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) file << "\t" << grid.ionic_fraction[(size_t)ion * n + i];
+        file << "\n";
+      }
+    }
+  }
+
+private:
+  std::string prefix_, folder_;
+  bool all_fields_;
+};
+
+/* ---- the driver ---- */
+class IonizationSimulation {
+public:
+  /* same leading arguments as the reference; num_thread is accepted and ignored (the
+   * parallelism is the GPU's), `device` replaces the MPI communicator */
+  IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
+                       const std::string &parameterfile, int device = 0, Log *log = nullptr)
+      : every_iteration_output_(every_iteration_output), output_statistics_(output_statistics), log_(log),
+        parameter_file_(parameterfile),
+        number_of_iterations_(parameter_file_.get_value<uint32_t>("IonizationSimulation:number of iterations", 10)),
+        number_of_photons_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons", 100000)),
+        number_of_photons_init_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons first loop",
+                                                                    number_of_photons_)),
+        abundances_(Abundances::generate(parameter_file_, log)) {
+    (void)num_thread;
+    cross_sections_.reset(CrossSections::generate(parameter_file_, log_));
+    recombination_rates_.reset(RecombinationRates::generate(parameter_file_, log_));
+    density_function_.reset(DensityFunctionFactory::generate(parameter_file_, log_));
+    if (parameter_file_.get_value<std::string>("DensityMask:type", "None") != "None")
+      cmi_error("DensityMask is not provided by the B200 backend!");
+    const SimulationBox box(parameter_file_);
+    const std::string grid_type = parameter_file_.get_value<std::string>("DensityGrid:type", "Cartesian");
+    if (grid_type != "Cartesian")
+      cmi_error("Unknown DensityGrid type: \"%s\" (the B200 backend provides Cartesian)!", grid_type.c_str());
+    density_grid_.reset(new CartesianDensityGrid(box, parameter_file_, device));
+    photon_source_distribution_.reset(PhotonSourceDistributionFactory::generate(parameter_file_, log_));
+    photon_source_spectrum_.reset(PhotonSourceSpectrum::generate("PhotonSourceSpectrum", parameter_file_, log_));
+    if (photon_source_distribution_ && !photon_source_spectrum_)
+      cmi_error("No spectrum provided for the discrete photon sources!");
+    if (parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None") != "None")
+      cmi_error("Continuous photon sources are not provided by the B200 backend!");
+    if (!photon_source_distribution_) cmi_error("No photon sources!");
+    reemission_ = DiffuseReemissionHandler::generate(parameter_file_, log_);
+
+    /* configure the device context: PhotonSource ctor (PhotonSource.cpp:55-146) */
+    cmib_context *ctx = density_grid_->context();
+    CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
+    CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
+    CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
+    const size_t ns = photon_source_distribution_->get_number_of_sources();
+    std::vector<double> pos(3 * ns), w(ns);
+    for (size_t i = 0; i < ns; ++i) {
+      const Vec3 p = photon_source_distribution_->get_position(i);
+      pos[3 * i] = p[0]; pos[3 * i + 1] = p[1]; pos[3 * i + 2] = p[2];
+      w[i] = photon_source_distribution_->get_weight(i);
+    }
+    total_luminosity_ = photon_source_distribution_->get_total_luminosity();
+    CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), total_luminosity_));
+    CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
+    CMIB_CALL(cmib_set_reemission(ctx, reemission_.kind, reemission_.probability, reemission_.frequency));
+
+    output_folder_ = parameter_file_.get_value<std::string>("IonizationSimulation:output folder", ".");
+    if (write_output) {
+      const std::string wtype = parameter_file_.get_value<std::string>("DensityGridWriter:type", "AsciiFile");
+      if (wtype != "AsciiFile" && log_)
+        log_->write_warning("DensityGridWriter type ", wtype, " needs HDF5; writing the AsciiFile layout instead.");
+      density_grid_writer_.reset(new AsciiFileDensityGridWriter(output_folder_, parameter_file_));
+    }
+    const cmib_temperature_params tp = temperature_calculator_parameters(parameter_file_);
+    CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
+    random_seed_ = parameter_file_.get_value<int32_t>("IonizationSimulation:random seed", 42);
+    if (parameter_file_.get_value<bool>("IonizationSimulation:enable trackers", false))
+      cmi_error("Trackers are not provided by the B200 backend!");
+    if (write_output) {
+      std::ofstream pfile(parameterfile + ".used-values");
+      parameter_file_.print_contents(pfile);
+      if (log_) log_->write_status("Wrote used parameters to ", parameterfile + ".used-values", ".");
+    }
+  }
+
+  /* IonizationSimulation::initialize (IonizationSimulation.cpp:239-326) */
+  void initialize(DensityFunction *density_function = nullptr) {
+    if (!density_function) density_function = density_function_.get();
+    density_function->initialize();
+    density_grid_->initialize(*density_function);
+  }
+
+  struct IterationResult {
+    double totweight = 0.;
+    double typecount[CMIB_NUM_PACKET_TYPES] = {0., 0., 0., 0.};
+    double shoot_seconds = 0., update_seconds = 0.;
+  };
+
+  /* one pass of the loop body of IonizationSimulation::run (IonizationSimulation.cpp:359-643) */
+  IterationResult iteration(uint32_t loop, uint64_t numphoton) {
+    using clock = std::chrono::steady_clock;
+    cmib_context *ctx = density_grid_->context();
+    IterationResult r;
+    density_grid_->reset_grid();
+    CMIB_CALL(cmib_update_reemission_probabilities(ctx));
+    CMIB_CALL(cmib_synchronize(ctx));
+    const auto t0 = clock::now();
+    CMIB_CALL(cmib_shoot(ctx, numphoton, 0, (uint64_t)(int64_t)random_seed_, loop, &r.totweight, r.typecount));
+    const auto t1 = clock::now();
+    CMIB_CALL(cmib_update_state(ctx, loop, r.totweight));
+    CMIB_CALL(cmib_synchronize(ctx));
+    const auto t2 = clock::now();
+    r.shoot_seconds = std::chrono::duration<double>(t1 - t0).count();
+    r.update_seconds = std::chrono::duration<double>(t2 - t1).count();
+    return r;
+  }
+
+  /* IonizationSimulation::run */
+  void run() {
+    if (density_grid_writer_) density_grid_writer_->write(*density_grid_, 0);
+    double shoot = 0., update = 0.;
+    for (uint32_t loop = 0; loop < number_of_iterations_; ++loop) {
+      if (log_) log_->write_status("Starting loop ", loop, ".");
+      const uint64_t lnumphoton = (loop == 0) ? number_of_photons_init_ : number_of_photons_;
+      if (log_) log_->write_status("Start shooting ", lnumphoton, " photons...");
+      const IterationResult r = iteration(loop, lnumphoton);
+      shoot += r.shoot_seconds;
+      update += r.update_seconds;
+      if (log_) log_->write_status("Done shooting photons.");
+      if (output_statistics_ && log_) {
+        /* IonizationSimulation.cpp:421-446 */
+        const double W = r.totweight;
+        log_->write_info(100. * r.typecount[3] / W, "% of photons were reemitted as non-ionizing photons.");
+        log_->write_info(100. * (r.typecount[1] + r.typecount[2]) / W, "% of photons were scattered.");
+        const double escape = 100. * (W - r.typecount[3]) / W;
+        log_->write_info("Escape fraction: ", escape, "%.");
+        log_->write_info("Escape fraction from diffuse hydrogen: ", 100. * r.typecount[1] / W, "%.");
+        log_->write_info("Escape fraction from diffuse helium: ", 100. * r.typecount[2] / W, "%.");
+      }
+      if (every_iteration_output_ && density_grid_writer_ && loop + 1 < number_of_iterations_)
+        density_grid_writer_->write(*density_grid_, loop + 1);
+    }
+    if (density_grid_writer_) density_grid_writer_->write(*density_grid_, number_of_iterations_);
+    if (log_) {
+      log_->write_status("Total photon shooting time: ", shoot, " s.");
+      log_->write_status("Total cell update time: ", update, " s.");
+    }
+    total_shoot_seconds_ = shoot;
+    total_update_seconds_ = update;
+  }
+
+  CartesianDensityGrid &get_density_grid() { return *density_grid_; }
+  ParameterFile &get_parameter_file() { return parameter_file_; }
+  uint32_t get_number_of_iterations() const { return number_of_iterations_; }
+  uint64_t get_number_of_photons() const { return number_of_photons_; }
+  double get_total_luminosity() const { return total_luminosity_; }
+  double total_shoot_seconds() const { return total_shoot_seconds_; }
+  double total_update_seconds() const { return total_update_seconds_; }
+
+private:
+  bool every_iteration_output_, output_statistics_;
+  Log *log_;
+  ParameterFile parameter_file_;
+  uint32_t number_of_iterations_;
+  uint64_t number_of_photons_, number_of_photons_init_;
+  Abundances abundances_;
+  std::unique_ptr<CrossSections> cross_sections_;
+  std::unique_ptr<RecombinationRates> recombination_rates_;
+  std::unique_ptr<DensityFunction> density_function_;
+  std::unique_ptr<CartesianDensityGrid> density_grid_;
+  std::unique_ptr<PhotonSourceDistribution> photon_source_distribution_;
+  std::unique_ptr<PhotonSourceSpectrum> photon_source_spectrum_;
+  DiffuseReemissionHandler reemission_;
+  std::unique_ptr<AsciiFileDensityGridWriter> density_grid_writer_;
+  std::string output_folder_;
+  double total_luminosity_ = 0.;
+  int32_t random_seed_ = 42;
+  double total_shoot_seconds_ = 0., total_update_seconds_ = 0.;
+};
+
+} // namespace cmi

@@ -1,0 +1,148 @@
+/*
+ * host_api.cpp — C entry points over the C++ host layer (IonizationSimulation.hpp), so that
+ * the tests and bench.py drive the SAME host code a C++ caller links against.
+ *
+ * Mirrors the shape of the reference's coarse library interface (cmi_init / cmi_destroy,
+ * /root/reference/src/CMILibrary.cpp:48-58) but per-object instead of global singletons.
+ * Errors: return code + cmih_last_error(); with CMIB_ABORT_ON_ERROR=1 the message is printed
+ * and the process aborts like the reference's cmac_error.
+ */
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "IonizationSimulation.hpp"
+
+using namespace cmi;
+
+namespace {
+thread_local std::string g_error;
+int fail(const std::exception &e) {
+  g_error = e.what();
+  const char *a = getenv("CMIB_ABORT_ON_ERROR");
+  if (a && a[0] == '1') {
+    fprintf(stderr, "%s\n", g_error.c_str());
+    abort();
+  }
+  return 1;
+}
+struct Sim {
+  Log log;
+  IonizationSimulation sim;
+  Sim(const char *paramfile, int device, int write_output, int verbose)
+      : log(verbose ? Log::INFO : Log::WARNING),
+        sim(write_output != 0, false, verbose != 0, -1, paramfile, device, &log) {}
+};
+} // namespace
+
+#define CMIH_TRY(body)                      \
+  try {                                     \
+    body;                                   \
+    return 0;                               \
+  } catch (const std::exception &e) {       \
+    return fail(e);                         \
+  }
+
+extern "C" {
+
+const char *cmih_last_error(void) { return g_error.c_str(); }
+
+/* IonizationSimulation(write_output, false, output_statistics, -1, parameterfile, device, log) */
+int cmih_simulation_create(const char *paramfile, int device, int write_output, int verbose, void **out) {
+  CMIH_TRY(*out = new Sim(paramfile, device, write_output, verbose));
+}
+int cmih_simulation_destroy(void *h) {
+  delete static_cast<Sim *>(h);
+  return 0;
+}
+int cmih_simulation_initialize(void *h) { CMIH_TRY(static_cast<Sim *>(h)->sim.initialize()); }
+int cmih_simulation_run(void *h) { CMIH_TRY(static_cast<Sim *>(h)->sim.run()); }
+/* out[8]: totweight, typecount[4], shoot seconds, update seconds, 0 */
+int cmih_simulation_iteration(void *h, uint32_t loop, uint64_t numphoton, double *out) {
+  CMIH_TRY({
+    const IonizationSimulation::IterationResult r = static_cast<Sim *>(h)->sim.iteration(loop, numphoton);
+    out[0] = r.totweight;
+    for (int t = 0; t < 4; ++t) out[1 + t] = r.typecount[t];
+    out[5] = r.shoot_seconds;
+    out[6] = r.update_seconds;
+    out[7] = 0.;
+  });
+}
+/* info[4]: number of cells, iterations, photons per iteration, total luminosity */
+int cmih_simulation_info(void *h, double *info) {
+  CMIH_TRY({
+    IonizationSimulation &s = static_cast<Sim *>(h)->sim;
+    info[0] = (double)s.get_density_grid().get_number_of_cells();
+    info[1] = (double)s.get_number_of_iterations();
+    info[2] = (double)s.get_number_of_photons();
+    info[3] = s.get_total_luminosity();
+  });
+}
+/* the cmib_context of the simulation's grid (for cmib_download_cells etc.) */
+int cmih_simulation_context(void *h, cmib_context **ctx) {
+  CMIH_TRY(*ctx = static_cast<Sim *>(h)->sim.get_density_grid().context());
+}
+
+/* ---- parameter-file probes (parity tests against the reference's ParameterFile) ---- */
+int cmih_paramfile_open(const char *filename, void **out) { CMIH_TRY(*out = new ParameterFile(filename)); }
+int cmih_paramfile_close(void *h) {
+  delete static_cast<ParameterFile *>(h);
+  return 0;
+}
+/* quantity: the Quantity enum of ParameterFile.hpp; unit conversion to SI */
+int cmih_convert_to_SI(int quantity, double value, const char *unit, double *out) {
+  CMIH_TRY(*out = UnitConverter::to_SI((Quantity)quantity, value, unit));
+}
+int cmih_convert(double value, const char *unit_from, const char *unit_to, double *out) {
+  CMIH_TRY(*out = UnitConverter::convert(value, unit_from, unit_to));
+}
+int cmih_paramfile_get_string(void *h, const char *key, const char *default_value, char *out, int n) {
+  CMIH_TRY({
+    const std::string v = static_cast<ParameterFile *>(h)->get_value(std::string(key), default_value);
+    strncpy(out, v.c_str(), n - 1);
+    out[n - 1] = 0;
+  });
+}
+int cmih_paramfile_get_double(void *h, const char *key, double default_value, double *out) {
+  CMIH_TRY(*out = static_cast<ParameterFile *>(h)->get_value<double>(key, default_value));
+}
+int cmih_paramfile_get_physical(void *h, int quantity, const char *key, const char *default_value, double *out) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    switch ((Quantity)quantity) {
+    case QUANTITY_LENGTH: *out = p.get_physical_value<QUANTITY_LENGTH>(key, default_value); break;
+    case QUANTITY_NUMBER_DENSITY: *out = p.get_physical_value<QUANTITY_NUMBER_DENSITY>(key, default_value); break;
+    case QUANTITY_TEMPERATURE: *out = p.get_physical_value<QUANTITY_TEMPERATURE>(key, default_value); break;
+    case QUANTITY_FREQUENCY: *out = p.get_physical_value<QUANTITY_FREQUENCY>(key, default_value); break;
+    case QUANTITY_SURFACE_AREA: *out = p.get_physical_value<QUANTITY_SURFACE_AREA>(key, default_value); break;
+    case QUANTITY_REACTION_RATE: *out = p.get_physical_value<QUANTITY_REACTION_RATE>(key, default_value); break;
+    default: cmi_error("quantity %d not exposed by this probe", quantity);
+    }
+  });
+}
+/* the used-values dump (YAMLDictionary::print_contents(stream, true)) into a caller buffer */
+int cmih_paramfile_used_values(void *h, char *out, int n) {
+  CMIH_TRY({
+    std::ostringstream s;
+    static_cast<YAMLDictionary *>(static_cast<ParameterFile *>(h))->print_contents(s, true);
+    strncpy(out, s.str().c_str(), n - 1);
+    out[n - 1] = 0;
+  });
+}
+/* evaluate the parameter file's DensityFunction at n points (x[n][3]) -> number density,
+ * temperature, neutral fraction of H */
+int cmih_density_function(void *h, int64_t n, const double *x, double *dens, double *temp, double *xH) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<DensityFunction> f(DensityFunctionFactory::generate(p));
+    f->initialize();
+    for (int64_t i = 0; i < n; ++i) {
+      const DensityValues v = (*f)({x[3 * i], x[3 * i + 1], x[3 * i + 2]});
+      dens[i] = v.number_density;
+      temp[i] = v.temperature;
+      xH[i] = v.ionic_fraction[0];
+    }
+  });
+}
+
+} /* extern "C" */

@@ -210,6 +210,16 @@ def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 
 
+def paramfile_query(path, queries):
+    """queries: list of (kind, key, default) -> (list of value strings, used-values dump)"""
+    q = "\n".join(f"{k}|{key}|{d}" for k, key, d in queries) + "\n"
+    buf = C.create_string_buffer(1 << 17)
+    lib().cmi_ref_paramfile_query(str(path).encode(), q.encode(), buf, C.c_int(1 << 17))
+    text = buf.value.decode()
+    head, dump = text.split("---\n", 1)
+    return head.strip("\n").split("\n"), dump
+
+
 def run_paramfile(path, ncells, num_threads=-1, verbose=False):
     """Run the reference IonizationSimulation; returns (fields[32][ncell], times): n, T, x[14], J[14], heat[2]."""
     fields = np.zeros((32, ncells))

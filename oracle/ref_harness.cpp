@@ -582,6 +582,51 @@ double cmi_ref_convert(double value, const char *unit_from, const char *unit_to)
 }
 
 
+/* The reference's ParameterFile on a file: query `nkeys` keys (newline separated list
+ * "kind|key|default", kind in s(tring) d(ouble) b(ool) i(nteger) and the physical quantities
+ * L(ength) N(umber density) T(emperature) F(requency) A(rea) R(eaction rate)), write the values
+ * as text lines into `out`, followed by the used-values dump (print_contents).  Pins the
+ * host-side parameter-file parser of the product. */
+int cmi_ref_paramfile_query(const char *filename, const char *queries, char *out, int nout) {
+  ParameterFile params(filename);
+  std::stringstream in(queries), res;
+  res.precision(17);
+  std::string line;
+  while (std::getline(in, line)) {
+    if (line.empty()) continue;
+    const char kind = line[0];
+    const size_t bar = line.find('|', 2);
+    const std::string key = line.substr(2, bar - 2);
+    const std::string def = line.substr(bar + 1);
+    switch (kind) {
+    case 's': res << params.get_value< std::string >(key, def); break;
+    case 'd': res << params.get_value< double >(key, atof(def.c_str())); break;
+    case 'b': res << params.get_value< bool >(key, def == "true"); break;
+    case 'i': res << params.get_value< uint_fast64_t >(key, (uint_fast64_t)atof(def.c_str())); break;
+    case 'L': res << params.get_physical_value< QUANTITY_LENGTH >(key, def); break;
+    case 'N': res << params.get_physical_value< QUANTITY_NUMBER_DENSITY >(key, def); break;
+    case 'T': res << params.get_physical_value< QUANTITY_TEMPERATURE >(key, def); break;
+    case 'F': res << params.get_physical_value< QUANTITY_FREQUENCY >(key, def); break;
+    case 'A': res << params.get_physical_value< QUANTITY_SURFACE_AREA >(key, def); break;
+    case 'R': res << params.get_physical_value< QUANTITY_REACTION_RATE >(key, def); break;
+    default: res << "?";
+    }
+    res << "\n";
+  }
+  res << "---\n";
+  std::stringstream dump;
+  params.print_contents(dump);
+  /* drop the time-stamp line */
+  std::string d = dump.str();
+  d = d.substr(d.find('\n') + 1);
+  res << d;
+  const std::string r = res.str();
+  strncpy(out, r.c_str(), nout - 1);
+  out[nout - 1] = 0;
+  return (int)r.size();
+}
+
+
 /* ---------------------------------------------------------------------------
  * Step-by-step driving of the reference IonizationSimulation: the body of the
  * `while (loop < _number_of_iterations)` loop of IonizationSimulation::run

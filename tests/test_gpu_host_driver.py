@@ -1,0 +1,77 @@
+"""GPU tier: the C++ host layer end to end — a reference parameter file in, the reference's
+loop (IonizationSimulation::initialize + run) on the GPU, the reference's snapshot layout out."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from test_gpu_simulation import STROMGREN_PARAM, radial_profile, shell_means, stromgren_radius
+
+pytestmark = pytest.mark.gpu
+
+PC = 3.086e16
+
+
+@pytest.fixture(scope="module")
+def host(cmib):
+    import sys
+    from conftest import ROOT
+    subprocess.check_call([sys.executable, "-c", "from cmacionize_b200 import build as b; b.build_host()"],
+                          cwd=str(ROOT))
+    from cmacionize_b200 import host as h
+    return h
+
+
+def test_parameter_file_run_matches_the_reference(host, ref, tmp_path):
+    nc, npk, nit = 32, 500000, 8
+    pf = tmp_path / "stromgren.param"
+    pf.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=42, extra=""))
+    fields, _ = ref.run_paramfile(pf, nc ** 3)
+    sim = host.IonizationSimulation(pf)
+    assert sim.ncells == nc ** 3 and sim.number_of_iterations == nit and sim.number_of_photons == npk
+    assert sim.total_luminosity == 4.26e49
+    sim.initialize()
+    n0, T0, x0, _ = sim.fields()
+    assert (n0 == 1e8).all() and (T0 == 8000.).all() and (x0[0] == 1e-6).all() and (x0[1] == 1e-6).all()
+    sim.run()
+    n, T, x, heat = sim.fields()
+    sim.close()
+    assert np.array_equal(n, fields[0])
+    r = radial_profile(x[0], nc, 5 * PC)
+    Ra, Rg = stromgren_radius(fields[2], r), stromgren_radius(x[0], r)
+    assert abs(Rg - Ra) < 0.25 * 10 * PC / nc
+    edges = np.linspace(0., 0.75 * Ra, 7)
+    sg, sa = shell_means(x[0], r, edges), shell_means(fields[2], r, edges)
+    assert (np.abs(sg / sa - 1.) < 0.01).all(), sg / sa
+
+
+def test_command_line_program_writes_the_reference_snapshot_layout(host, tmp_path):
+    from conftest import ROOT
+    nc, npk, nit = 16, 100000, 5
+    pf = tmp_path / "run.param"
+    # a group header may appear twice: the keys merge (YAMLDictionary.hpp:177-260)
+    pf.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=1, extra=f"""DensityGridWriter:
+  type: AsciiFile
+  prefix: snap
+IonizationSimulation:
+  output folder: {tmp_path}
+"""))
+    exe = ROOT / "cmacionize_b200" / "bin" / "CMacIonizeB200"
+    out = subprocess.run([str(exe), "--params", str(pf), "--threads", "4", "--output-statistics"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "Total photon shooting time" in out.stderr
+    assert (tmp_path / "run.param.used-values").exists()
+    first = (tmp_path / "snap000.txt").read_text().splitlines()
+    assert first[0] == "#x (m)\ty (m)\tz (m)\tn (m^-3)\tvolume (m^3)\tneutral H fraction"
+    assert len(first) == 1 + nc ** 3
+    last = np.loadtxt(tmp_path / f"snap{nit:03d}.txt")
+    assert last.shape == (nc ** 3, 6)
+    cs = 10 * PC / nc
+    assert np.allclose(last[0, :3], -5 * PC + 0.5 * cs, rtol=1e-5) and np.allclose(last[:, 4], cs ** 3, rtol=1e-5)
+    r = np.sqrt((last[:, :3] ** 2).sum(1))
+    Rs = (0.75 * 4.26e49 / (np.pi * (1e8) ** 2 * 4e-19)) ** (1. / 3.)
+    assert last[r < 0.6 * Rs, 5].max() < 0.05 and last[r > 1.3 * Rs, 5].min() > 0.9
+    # unknown mode of the reference executable -> rejected, not silently ignored
+    bad = subprocess.run([str(exe), "--params", str(pf), "--rhd"], capture_output=True, text=True)
+    assert bad.returncode != 0

@@ -1,0 +1,165 @@
+"""CPU tier: the C++ host layer (cmacionize_b200/host) reads the reference's parameter files
+exactly like the reference does — same keys, defaults, unit conversions (bit for bit), same
+used-values dump, same initial grids from the DensityFunction plugins.  No GPU needed: only the
+parts of the host layer that do not create a device context are exercised here; the full
+IonizationSimulation driver is covered by the GPU tier (tests/test_gpu_host_driver.py)."""
+import numpy as np
+import pytest
+
+PC = 3.086e16
+
+LEX_YML = """number of blocks: 2
+block[0]:
+  origin: [0. pc, 0. pc, 0. pc]
+  sides: [6. pc, 6. pc, 6. pc]
+  type: cube
+  number density: 100. cm^-3
+  initial temperature: 8000. K
+block[1]:
+  origin: [0. pc, 0. pc, 0. pc]
+  sides: [6.e18 cm, 6.e18 cm, 6.e18 cm]
+  type: sphere
+  number density: 0. cm^-3
+  initial temperature: 0. K
+"""
+
+PARAM = """# a comment line
+AbundanceModel:
+  type: FixedValue
+  He: 0.1
+  C: 2.2e-4   # trailing comment
+DensityFunction:
+  type: BlockSyntax
+  filename: {yml}
+SimulationBox:
+  anchor: [-3. pc, -3. pc, -3. pc]
+  sides: [6. pc, 6. pc, 6. pc]
+  periodicity: [false, false, false]
+DensityGrid:
+  type: Cartesian
+  number of cells: [12, 12, 12]
+IonizationSimulation:
+  number of iterations: 3
+  number of photons: 1e5
+  random seed: 42
+TemperatureCalculator:
+  do temperature calculation: true
+  cosmic ray heating scale length: 2. kpc
+PhotonSourceDistribution:
+  type: SingleStar
+  position: [0. pc, 0. pc, 0. pc]
+  luminosity: 1.e49 s^-1
+PhotonSourceSpectrum:
+  type: Planck
+  temperature: 20000. K
+CrossSections:
+  type: FixedValue
+  hydrogen_0: 6.3e-18 cm^2
+RecombinationRates:
+  type: FixedValue
+  hydrogen_1: 4.e-13 cm^3 s^-1
+Nested:
+  Deeper:
+    key: 13.6 eV
+    wavelength: 912. angstrom
+"""
+
+QUERIES = [
+    ("s", "AbundanceModel:type", "FixedValue"), ("d", "AbundanceModel:He", "0."), ("d", "AbundanceModel:C", "0."),
+    ("d", "AbundanceModel:N", "0."), ("s", "DensityGrid:type", "Cartesian"),
+    ("L", "TemperatureCalculator:cosmic ray heating scale length", "1.33333 kpc"),
+    ("T", "TemperatureCalculator:minimum ionized temperature", "4000. K"),
+    ("F", "PhotonSourceDistribution:luminosity", "4.26e49 s^-1"), ("T", "PhotonSourceSpectrum:temperature", "4.e4 K"),
+    ("A", "CrossSections:hydrogen_0", "6.3e-18 cm^2"), ("A", "CrossSections:helium_0", "0. m^2"),
+    ("R", "RecombinationRates:hydrogen_1", "2.7e-13 cm^3 s^-1"), ("R", "RecombinationRates:helium_1", "0. m^3 s^-1"),
+    ("F", "Nested:Deeper:key", "1. Hz"), ("F", "Nested:Deeper:wavelength", "1. Hz"),
+    ("F", "PhotonSourceSpectrum:frequency", "13.6 eV"), ("N", "DensityFunction:density", "100. cm^-3"),
+    ("d", "IonizationSimulation:number of photons", "1e5"),
+    ("d", "TemperatureCalculator:epsilon convergence", "1e-3"),
+]
+KIND = {"L": "length", "T": "temperature", "F": "frequency", "A": "surface_area", "R": "reaction_rate",
+        "N": "number_density"}
+
+
+@pytest.fixture(scope="module")
+def host(cmib):
+    import subprocess, sys
+    from conftest import ROOT
+    subprocess.check_call([sys.executable, "-c", "from cmacionize_b200 import build as b; b.build_host()"],
+                          cwd=str(ROOT))
+    from cmacionize_b200 import host as h
+    return h
+
+
+def test_unit_conversions_bitexact(host, ref):
+    cases = [(13.6, "eV", "Hz"), (24.6, "eV", "Hz"), (19.8, "eV", "Hz"), (912., "angstrom", "Hz"),
+             (3.288465385e15, "Hz", "eV"), (1., "pc", "m"), (10., "pc", "cm"), (1.33333, "kpc", "m"),
+             (100., "cm^-3", "m^-3"), (6.3e-18, "cm^2", "m^2"), (4.e-13, "cm^3 s^-1", "m^3 s^-1"),
+             (2.7e-13, "cm^3 s^-1", "m^3 s^-1"), (1., "Myr", "s"), (1., "g cm^-3", "kg m^-3"),
+             (5., "km s^-1", "m s^-1"), (1., "Msol", "g"), (3., "K kg^3 s^-1m ", "K kg^3 s^-1 m"),
+             (1.e49, "s^-1", "Hz"), (1., "erg", "J"), (2., "au", "km")]
+    for v, a, b in cases:
+        assert host.convert(v, a, b) == ref.convert(v, a, b), (v, a, b)
+    with pytest.raises(host.HostError, match="Unknown unit"):
+        host.convert(1., "parsec", "m")
+
+
+def test_parameter_file_same_values_and_used_values_dump(host, ref, tmp_path):
+    yml = tmp_path / "blocks.yml"
+    yml.write_text(LEX_YML)
+    pf = tmp_path / "test.param"
+    pf.write_text(PARAM.format(yml=yml))
+    want, dump = ref.paramfile_query(pf, QUERIES)
+    p = host.ParameterFile(pf)
+    got = []
+    for kind, key, default in QUERIES:
+        if kind == "s":
+            got.append(p.get_string(key, default))
+        elif kind == "d":
+            got.append(repr(p.get_double(key, float(default))))
+        else:
+            got.append(repr(p.get_physical(KIND[kind], key, default)))
+    for (kind, key, _), g, w in zip(QUERIES, got, want):
+        if kind == "s":
+            assert g == w, key
+        else:
+            assert float(g) == float(w), (key, g, w)   # bit-identical doubles
+    assert p.used_values() == dump
+    # a mandatory key that is absent -> the reference's "Parameter ... not found!" error
+    bad = tmp_path / "bad.param"
+    bad.write_text("DensityFunction:\n  type: BlockSyntax\n")
+    with pytest.raises(host.HostError, match="not found"):
+        host.ParameterFile(bad).density_function(np.zeros((1, 3)))
+    # unknown plugin type -> the factory's error
+    bad.write_text("DensityFunction:\n  type: Fractal\n")
+    with pytest.raises(host.HostError, match="Unknown DensityFunction type"):
+        host.ParameterFile(bad).density_function(np.zeros((1, 3)))
+
+
+@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks"])
+def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
+    nc = 12
+    if kind == "homogeneous_defaults":
+        text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+                "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+                f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n  type: Homogeneous\n"
+                "  neutral fraction H: 1.e-4\nPhotonSourceSpectrum:\n  type: Monochromatic\n")
+        half = 5 * PC
+    else:
+        yml = tmp_path / "blocks.yml"
+        yml.write_text(LEX_YML)
+        text = PARAM.format(yml=yml)
+        half = 3 * PC
+    pf = tmp_path / "grid.param"
+    pf.write_text(text)
+    sim = ref.Simulation(pf)
+    f = sim.fields()
+    sim.close()
+    cs = 2 * half / nc
+    m = -half + cs * np.arange(nc) + 0.5 * cs      # CartesianDensityGrid::get_cell_midpoint
+    X, Y, Z = np.meshgrid(m, m, m, indexing="ij")
+    x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], 1)
+    dens, temp, xH = host.ParameterFile(pf).density_function(x)
+    assert np.array_equal(dens, f[0]) and np.array_equal(temp, f[1]) and np.array_equal(xH, f[2])
+    if kind == "lexington_blocks":
+        assert (dens == 0).sum() > 0 and (dens > 0).sum() > 0
