@@ -252,31 +252,23 @@ def main():
     ctx = prob.ctx
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
+    from cmacionize_b200.distributed import accumulator_tensor, allreduce_sum, shard_packets
     # accumulator buffer as a torch tensor (zero copy) for the NCCL all-reduce
-    ptr, nd = ctx.accumulator_buffer()
-
-    class _Buf:
-        __cuda_array_interface__ = {"shape": (nd,), "typestr": "<f8", "data": (ptr, False), "version": 3}
-    acc = torch.as_tensor(_Buf(), device=torch.device("cuda", local_rank))
-
-    # shard packets by global id
-    per = n_packets // world
-    lo = rank * per
-    cnt = per if rank < world - 1 else n_packets - lo
+    acc = accumulator_tensor(ctx, torch.device("cuda", local_rank))
+    lo, cnt = shard_packets(n_packets, rank, world)   # shard packets by global id
 
     def allreduce(_ctx):
-        if world > 1:
-            dist.all_reduce(acc)
+        allreduce_sum(acc)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     shoot_ms = []
+    kernel_ms = []   # (prepare ms, march ms, rounds) per timed step, from the library's CUDA events
 
     def step(loop, npk_total=None, timed=False):
         if npk_total is None:
             my_lo, my_cnt = lo, cnt
         else:
-            p = npk_total // world
-            my_lo, my_cnt = rank * p, p
+            my_lo, my_cnt = shard_packets(npk_total, rank, world)
         with torch.cuda.stream(stream):
             ctx.reset_accumulators()
             ctx.update_reemission_probabilities()
@@ -287,6 +279,7 @@ def main():
             if timed:
                 e1.record(stream)
                 shoot_ms.append((e0, e1))
+                kernel_ms.append(ctx.shoot_timing(want_adds=False)[:3])
             allreduce(ctx)
             ctx.update_state(loop, 0.)
 
@@ -304,6 +297,7 @@ def main():
         loop += 1
     barrier()
     launches0 = capi.kernel_launch_count()
+    ctx.set_shoot_timing(True)
     with ClockSampler(local_rank) as clocks:
         t0e, t1e = ev(), ev()
         with torch.cuda.stream(stream):
@@ -325,19 +319,39 @@ def main():
     value = n_packets * args.steps / elapsed
     shoot_s = float(np.mean([a.elapsed_time(b) for a, b in shoot_ms])) * 1e-3
 
-    # ---- roofline of the dominant kernel (shoot) ----
+    # ---- roofline of the dominant kernel (march_kernel: voxel walk + accumulation) ----
+    # unit of work = one packet-cell crossing; algorithmic bytes per crossing from SURVEY.md §8(d)
+    # (152 B: 24 B gather + 16 x 8 B accumulate).  One step launches the kernel once per round of the
+    # wavefront pipeline; bytes and time are summed over the rounds of a step, which gives the same
+    # ratio as per-launch averages.  Times are CUDA events recorded by the library on its own stream.
     peak, peak_src = measured_peaks()
+    _, _, _, red_ops = ctx.shoot_timing()            # accumulator adds of the last step (all ranks after all-reduce)
+    prep_ms = float(np.mean([k[0] for k in kernel_ms]))
+    march_ms = float(np.mean([k[1] for k in kernel_ms]))
+    rounds = float(np.mean([k[2] for k in kernel_ms]))
     steps_per_packet = crossings / n_packets
-    bytes_per_step = prob.bytes_per_step  # 152 B: 24 B gather + 16 x 8 B accumulate
-    alg_bytes = (crossings / world) * bytes_per_step  # per launch = per rank per iteration
-    achieved = alg_bytes / shoot_s / 1e9
-    roofline = {"bound": "hbm", "kernel": "shoot_kernel<ACC_FULL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    bytes_per_step = prob.bytes_per_step
+    alg_bytes = (crossings / world) * bytes_per_step  # per rank per iteration
+    achieved = alg_bytes / (march_ms * 1e-3) / 1e9
+    red_rate = (red_ops / world) / (march_ms * 1e-3)
+    RED_PEAK = 1.878e11  # scattered FP64 RED/s measured on B200 (profiles/r01_microbench_red_gather.txt)
+    roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak,
+                "traffic": 1.142e9, "traffic_note": "dram__bytes_read+write of the first (4 Mi packet) march launch of a "
+                "shoot, ncu --set full, profiles/r01_wavefront_lexington.md; algorithmic bytes of that launch are ~19 GB: "
+                "the 42 MB grid is L2 resident, DRAM only sees the packet queues",
+                "peak_source": peak_src,
                 "cell_crossings_per_packet": steps_per_packet, "emissions_per_packet": emissions / n_packets,
-                "algorithmic_bytes_per_crossing": bytes_per_step, "kernel_ms": 1e3 * shoot_s,
-                "kernel_share_of_step": 1e3 * shoot_s / ms_per_step,
-                "note": "64^3 working set (8 MB cells + 34 MB accumulators) is L2 resident: the binding limit is "
-                        "L2 atomic/gather throughput, the HBM figure is the contract's common denominator"}
+                "algorithmic_bytes_per_crossing": bytes_per_step, "kernel_ms": march_ms,
+                "kernel_launches_per_step": rounds,
+                "kernel_share_of_step": march_ms / ms_per_step,
+                "prepare_kernel_ms": prep_ms, "prepare_share_of_step": prep_ms / ms_per_step,
+                "shoot_ms": 1e3 * shoot_s,
+                "atomic": {"achieved": red_rate, "peak": RED_PEAK, "unit": "FP64 RED/s", "frac": red_rate / RED_PEAK,
+                           "red_per_crossing": red_ops / max(crossings, 1.),
+                           "note": "64^3 working set (8 MB cells + 34 MB accumulators) is L2 resident; ncu shows the "
+                                   "binding unit is L1TEX (scattered gather + RED lanes, 88 % busy), so the meaningful "
+                                   "denominator is the measured scattered-RED ceiling, not HBM"}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -219,6 +219,17 @@ class Context:
         """0 = wavefront pipeline (production), 1 = one-thread-per-packet kernel (A/B check)"""
         _check(lib.cmib_set_shoot_algorithm(self._h, C.c_int(algorithm)))
 
+    def set_shoot_timing(self, on=True):
+        _check(lib.cmib_set_shoot_timing(self._h, C.c_int(1 if on else 0)))
+
+    def shoot_timing(self, want_adds=True):
+        """(prepare ms, march ms, rounds, accumulator adds) of the last shoot / since the last reset"""
+        a, b, d = C.c_double(), C.c_double(), C.c_double()
+        r = C.c_uint64()
+        _check(lib.cmib_shoot_timing(self._h, C.byref(a), C.byref(b), C.byref(r),
+                                     C.byref(d) if want_adds else None))
+        return a.value, b.value, int(r.value), d.value
+
     def update_state(self, loop, totweight=0.):
         _check(lib.cmib_update_state(self._h, C.c_uint32(loop), C.c_double(totweight)))
 

@@ -118,6 +118,10 @@ struct cmib_context {
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2] = {0, 0};
   uint64_t shoot_rounds = 0;
+  /* optional per-kernel timing of the shoot (CUDA events on the context's stream) */
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;
+  double prepare_ms = 0., march_ms = 0.;
   double nu_H = 0., nu_He = 0.;
 
   int pick_acc_mode() const {
@@ -232,15 +236,30 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   const unsigned march_grid = (unsigned)(ctx->sm_count * bpm);
   const int group = 4;
   uint64_t round = 0;
+  size_t ev_used = 0;
+  auto stamp = [&]() {
+    if (!ctx->timing) return;
+    if (ev_used == ctx->ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      ctx->ev_pool.push_back(e);
+    }
+    cudaEventRecord(ctx->ev_pool[ev_used++], s);
+  };
+  ctx->prepare_ms = ctx->march_ms = 0.;
   /* upper bound: every round either emits min(remaining, room) primaries or shrinks the
    * re-emission population; 1e6 rounds cannot be reached by a sane configuration */
   while (round < 1000000) {
     for (int k = 0; k < group; ++k, ++round) {
+      stamp();
       if (mode == ACC_HONLY) prepare_kernel<ACC_HONLY><<<prep_grid, 256, 0, s>>>(W);
       else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
+      stamp();
       advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
+      stamp();
       if (mode == ACC_HONLY) march_kernel<ACC_HONLY><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
       else march_kernel<ACC_FULL><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      stamp();
       advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl);
       g_launches += 4;
     }
@@ -254,6 +273,13 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     if (done) break;
   }
   ctx->shoot_rounds = round;
+  for (size_t k = 0; k + 3 < ev_used; k += 4) {
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
+    cudaEventElapsedTime(&b, ctx->ev_pool[k + 2], ctx->ev_pool[k + 3]);
+    ctx->prepare_ms += a;
+    ctx->march_ms += b;
+  }
   return 0;
 }
 
@@ -341,6 +367,7 @@ int cmib_destroy(cmib_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
+  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -657,6 +684,27 @@ int cmib_set_shoot_algorithm(cmib_context *ctx, int algorithm) {
   CHECK_CTX(ctx);
   if (algorithm != 0 && algorithm != 1) CMIB_FAIL("unknown shoot algorithm %d", algorithm);
   ctx->shoot_algorithm = algorithm;
+  return 0;
+}
+
+int cmib_set_shoot_timing(cmib_context *ctx, int on) {
+  CHECK_CTX(ctx);
+  ctx->timing = on != 0;
+  return 0;
+}
+
+int cmib_shoot_timing(cmib_context *ctx, double *prepare_ms, double *march_ms, uint64_t *rounds,
+                      double *accumulator_adds) {
+  CHECK_CTX(ctx);
+  if (prepare_ms) *prepare_ms = ctx->prepare_ms;
+  if (march_ms) *march_ms = ctx->march_ms;
+  if (rounds) *rounds = ctx->shoot_rounds;
+  if (accumulator_adds) {
+    double v = 0.;
+    CUDA_OK(cudaMemcpyAsync(&v, ctx->acc.p + 7, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *accumulator_adds = v;
+  }
   return 0;
 }
 

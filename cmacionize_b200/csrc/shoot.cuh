@@ -26,7 +26,7 @@
 namespace cmib {
 
 enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
-constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, pad */
+constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, accumulator adds */
 
 template <int MODE> struct AccLayout;
 template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
@@ -50,6 +50,7 @@ struct ShootCounters {
   double w_tot = 0.;
   double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
   uint32_t n_steps = 0, n_emit = 0; /* cell crossings, (re)emissions */
+  uint32_t n_red = 0;               /* accumulator terms added (wavefront path only) */
 };
 
 /* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which

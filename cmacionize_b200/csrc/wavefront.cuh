@@ -81,20 +81,20 @@ CMIB_D void rng_restore(PacketRng &r, uint64_t seed, uint32_t iteration, uint64_
   }
 }
 
-/* block-wide sum of per-thread counters into the 7 leading doubles of acc */
+/* block-wide sum of per-thread counters into the 8 leading doubles of acc */
 CMIB_D void reduce_counters(double *acc, const ShootCounters &cnt) {
-  __shared__ double red[7][32];
+  __shared__ double red[8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[7] = {cnt.w_tot, cnt.w_type[0], cnt.w_type[1], cnt.w_type[2], cnt.w_type[3],
-                 (double)cnt.n_steps, (double)cnt.n_emit};
+  double v[8] = {cnt.w_tot, cnt.w_type[0], cnt.w_type[1], cnt.w_type[2], cnt.w_type[3],
+                 (double)cnt.n_steps, (double)cnt.n_emit, (double)cnt.n_red};
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < 8; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) red[k][warp] = v[k];
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 8) {
     double sum = 0.;
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) sum += red[threadIdx.x][w];
     if (sum != 0.) atomicAdd(acc + threadIdx.x, sum);
@@ -278,6 +278,8 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   int32_t ix = 0, iy = 0, iz = 0;
   uint32_t cell = 0;
   uint32_t mask = 0; /* metals (bits 2..13) with a non-zero cross section */
+  uint32_t nacc = 0; /* accumulator terms this packet adds per crossing (diagnostic for the roofline) */
+  uint32_t n_red = 0;
   int state = LANE_EMPTY;
   bool warp_has_zero_dir = false; /* some lane's direction has a zero component (warp-uniform) */
   uint64_t cur = 0, end = 0;      /* warp-uniform cursor into the claimed chunk */
@@ -322,6 +324,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         fpy = xadd(py, xdiv(xmul(xsub(nwy, py), dss), ds));
         fpz = xadd(pz, xdiv(xmul(xsub(nwz, pz), dss), ds));
         /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
+        n_red += nacc;
         const double dsw = dss * weight;
         double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
         const double dJH = dsw * sigH;
@@ -407,6 +410,8 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             }
             dnu_H = nu - P.nu_H;
             dnu_He = nu - P.nu_He;
+            nacc = (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask);
+            if (MODE == ACC_FULL) nacc += (s_sig[NMETAL][tid] != 0.) * (1u + (dnu_He != 0.));
             ivx = 1. / dx;
             ivy = 1. / dy;
             ivz = 1. / dz;
@@ -471,6 +476,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
       } else {
         if (c.n > 0.) {
           /* update_integrals (DensityGrid.hpp:150-197); zero increments are skipped (exact) */
+          n_red += nacc;
           const double dsw = ds * weight;
           double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
           const double dJH = dsw * sigH;
@@ -525,6 +531,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   }
   ShootCounters cnt;
   cnt.n_steps = n_steps;
+  cnt.n_red = n_red;
 #pragma unroll
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) {
     cnt.w_type[t] = (double)n_type[t] * weight;

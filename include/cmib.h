@@ -151,6 +151,14 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight);
  * (re-)emissions.  No reference counterpart (gprof call counts were used there). */
 int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions);
 
+/* per-kernel device times of the LAST cmib_shoot (CUDA events on the context's stream; enable with
+ * cmib_set_shoot_timing before the shoot): summed prepare / march kernel milliseconds, number of
+ * rounds, and the number of accumulator terms added since the last reset (RED operations, the
+ * unit of the atomic roofline).  Any pointer may be NULL.  No reference counterpart. */
+int cmib_set_shoot_timing(cmib_context *ctx, int on);
+int cmib_shoot_timing(cmib_context *ctx, double *prepare_ms, double *march_ms, uint64_t *rounds,
+                      double *accumulator_adds);
+
 /* test hook: 0 = wavefront pipeline (default, production: prepare/march kernels connected by
  * device queues), 1 = one-thread-per-packet kernel.  Both draw the same packets from the same
  * per-packet random streams; they differ only in the order of the atomic adds. */

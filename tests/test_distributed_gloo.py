@@ -1,0 +1,77 @@
+"""CPU tier: the N>1 path on 2 ranks over gloo.  Each rank shoots its shard of the global packet
+ids (host logic check `hc_shoot` of tests/hostcheck standing in for the kernel: same shoot_packet
+code, same Philox streams), the accumulator buffers are combined with the ONE all-reduce the
+multi-GPU path uses, and the result must equal the single-rank run: identical counters, sums equal
+up to summation order."""
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+
+PC = 3.086e16
+NC = 16
+NPK = 20001  # odd on purpose: the last rank takes the remainder
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shoot(lib_path, lo, cnt):
+    hc = C.CDLL(lib_path)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    ncells = NC ** 3
+    rng = np.random.default_rng(3)
+    cells = np.ascontiguousarray(np.stack([np.full(ncells, 1e8), np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), ncells)),
+                                           np.full(ncells, 1e-6), np.full(ncells, 8000.)], 1))
+    acc = np.zeros(8 + ncells * 2)
+    anchor = np.array([-5 * PC] * 3); sides = np.array([10 * PC] * 3)
+    ncell = np.array([NC] * 3, np.int32); per = np.zeros(3, np.int32)
+    ip = np.array([2, 0, 0, 2, 1], np.int32)          # 2 sources, mono, FixedValue, FixedValue re-emission, H-only
+    dp = np.array([(13.6 * 1.6021766208e-19) * (1 / 6.626070040e-34), 0., 0.364, 3.4e15])
+    sp = np.array([0., 0., 0., PC, -PC, 0.5 * PC]); sw = np.array([0.3, 0.7])
+    xs = np.zeros(14); xs[0] = 6.3e-22
+    hc.hc_shoot(p(anchor), p(sides), p(ncell), p(per), p(cells), p(ip), p(dp), p(sp), p(sw), p(xs), C.c_uint64(cnt),
+                C.c_uint64(lo), C.c_uint64(42), C.c_uint32(3), p(acc))
+    return acc
+
+
+def _worker(rank, world, port, lib_path, out):
+    import torch
+    import torch.distributed as dist
+    from cmacionize_b200.distributed import allreduce_sum, shard_packets
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, cnt = shard_packets(NPK, rank, world)
+    acc = torch.from_numpy(_shoot(lib_path, lo, cnt))
+    allreduce_sum(acc)
+    if rank == 0:
+        np.save(out, acc.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_shoot_equals_single_rank(hostcheck, cmib, tmp_path):
+    import torch.multiprocessing as mp
+    from cmacionize_b200.distributed import shard_packets
+    # shards tile the id range exactly
+    for n, w in ((NPK, 2), (10, 3), (7, 8), (1000, 4)):
+        sh = [shard_packets(n, r, w) for r in range(w)]
+        assert sh[0][0] == 0 and sum(c for _, c in sh) == n
+        assert all(sh[r][0] + sh[r][1] == sh[r + 1][0] for r in range(w - 1))
+    lib_path = hostcheck._name
+    single = _shoot(lib_path, 0, NPK)
+    out = str(tmp_path / "acc.npy")
+    mp.spawn(_worker, args=(2, _free_port(), lib_path, out), nprocs=2, join=True)
+    both = np.load(out)
+    assert np.array_equal(both[:7], single[:7])          # weights by type, crossings, emissions: exact
+    assert both[0] == NPK and both[6] > 1.05 * NPK       # re-emission happened
+    scale = np.abs(single[8:]).max()
+    assert np.abs(both[8:] - single[8:]).max() <= 1e-12 * scale
