@@ -197,7 +197,18 @@ def cpu_reference_measure(full_packets: int, sample_packets: int, steps: int, wa
 
 
 # --------------------------------------------------------------------------- our arm
+def _claim_stdout():
+    """Libraries (NCCL's version banner, torchrun's OMP notice) write to fd 1; the contract is ONE JSON
+    line on stdout.  Point fd 1 at stderr for the duration of the run and keep the real stdout for the
+    result line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
 def main():
+    result_out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -235,7 +246,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
         return
 
     import torch
@@ -388,7 +399,7 @@ def main():
             line["cpu_baseline"] = {"error": repr(exc)}
 
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), file=result_out, flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

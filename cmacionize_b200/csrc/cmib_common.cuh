@@ -63,6 +63,31 @@ CMIB_HD double xsub(double a, double b) { return a - b; }
 CMIB_HD double xdiv(double a, double b) { return a / b; }
 #endif
 
+/*
+ * x^a for the smooth temperature / frequency fits (recombination, charge transfer, collision
+ * strengths, re-emission probabilities).  Host build: pow(), the reference's call, so the CPU tier
+ * pins every fit bit for bit.  Device: exp(a ln x) — FP64 pow costs about 4 exp on sm_100a and a
+ * temperature solve evaluates ~270 of these per heating/cooling balance.  |a ln x| < ~30 for every
+ * fit on the path, so the value moves by a few 1e-15 relative; the GPU-tier tests state and measure
+ * the resulting bound for every function.  powl(lnx, a) is the same with the logarithm supplied.
+ */
+CMIB_HD double fpow(double x, double a) {
+#if defined(__CUDA_ARCH__)
+  return exp(a * log(x));
+#else
+  return pow(x, a);
+#endif
+}
+CMIB_HD double powl(double x, double lnx, double a) {
+#if defined(__CUDA_ARCH__)
+  (void)x;
+  return exp(a * lnx);
+#else
+  (void)lnx;
+  return pow(x, a);
+#endif
+}
+
 /* geometry of the Cartesian grid; constants derived exactly as in
  * CartesianDensityGrid.cpp:80-86 (cellside = sides / ncell; inv = 1. / cellside) */
 struct GridGeom {

@@ -95,8 +95,8 @@ CMIB_HD int solve5(double A[5][5], double B[5]) {
 
 CMIB_HD double collision_strength(const double *c, double prefactor, double T, double Tinv,
                                   double logT) {
-  return prefactor * pow(T, 1. + c[0]) *
-         (c[1] + c[2] * Tinv + c[3] * logT + c[4] * T * (1. + (c[5] - 1.) * pow(T, c[6])));
+  return prefactor * powl(T, logT, 1. + c[0]) *
+         (c[1] + c[2] * Tinv + c[3] * logT + c[4] * T * (1. + (c[5] - 1.) * powl(T, logT, c[6])));
 }
 
 /* level populations of five-level element e; returns solver status */

@@ -28,9 +28,9 @@ CMIB_HD double rrfit_metal(int m, double T) {
   const double *p = CMIB_TBL(RRFIT)[m];
   if (p[0] != 0.) {
     const double tt = sqrt(T * p[3]);
-    return p[1] / (tt * pow(tt + 1., 1. - p[2]) * pow(1. + sqrt(T * p[4]), 1. + p[2]));
+    return p[1] / (tt * fpow(tt + 1., 1. - p[2]) * fpow(1. + sqrt(T * p[4]), 1. + p[2]));
   }
-  return p[1] * pow(T * 1.e-4, -p[2]);
+  return p[1] * fpow(T * 1.e-4, -p[2]);
 }
 
 /* Nussbaumer & Storey dielectronic fit coefficients (a, b, c, d, f):
@@ -40,7 +40,7 @@ struct DielectronicNS { double a, b, c, d, f; };
 
 CMIB_HD double dielectronic_ns(double a, double b, double c, double d, double f, double T4) {
   const double T4_inv = 1. / T4;
-  return 1.e-12 * (a * T4_inv + b + c * T4 + d * T4 * T4) * pow(T4, -1.5) * exp(-f * T4_inv);
+  return 1.e-12 * (a * T4_inv + b + c * T4 + d * T4 * T4) * fpow(T4, -1.5) * exp(-f * T4_inv);
 }
 
 CMIB_HD double verner_recombination_rate(int ion, double T) {
@@ -50,13 +50,13 @@ CMIB_HD double verner_recombination_rate(int ion, double T) {
   case ION_H_n: {
     const double T1 = T / 3.148;
     const double T2 = T / 7.036e5;
-    rate = 7.982e-11 / (sqrt(T1) * pow(1. + sqrt(T1), 0.252) * pow(1. + sqrt(T2), 1.748));
+    rate = 7.982e-11 / (sqrt(T1) * fpow(1. + sqrt(T1), 0.252) * fpow(1. + sqrt(T2), 1.748));
     break;
   }
   case ION_He_n: {
     const double T1 = T / 15.54;
     const double T2 = T / 3.676e7;
-    rate = 3.294e-11 / (sqrt(T1) * pow(1. + sqrt(T1), 0.309) * pow(1. + sqrt(T2), 1.691));
+    rate = 3.294e-11 / (sqrt(T1) * fpow(1. + sqrt(T1), 0.309) * fpow(1. + sqrt(T2), 1.691));
     break;
   }
   case ION_C_p1:
@@ -68,7 +68,7 @@ CMIB_HD double verner_recombination_rate(int ion, double T) {
   case ION_N_n:
     /* no 1/T4 term, and the exponent is written -0.4398 / T4 in the reference */
     rate = rrfit_metal(2, T) + 1.e-12 * (0.6310 + 0.1990 * T4 - 0.0197 * T4 * T4) *
-                                   pow(T4, -1.5) * exp(-0.4398 / T4);
+                                   fpow(T4, -1.5) * exp(-0.4398 / T4);
     break;
   case ION_N_p1:
     rate = rrfit_metal(3, T) + dielectronic_ns(0.0320, -0.6624, 4.3191, 0.0003, 0.5946, T4);
@@ -90,14 +90,14 @@ CMIB_HD double verner_recombination_rate(int ion, double T) {
     break;
   case ION_S_p1: {
     const double TeV = T / 1.16045221e4;
-    rate = rrfit_metal(9, T) + 1.37e-9 * exp(-14.95 / TeV) * pow(TeV, -1.5);
+    rate = rrfit_metal(9, T) + 1.37e-9 * exp(-14.95 / TeV) * fpow(TeV, -1.5);
     break;
   }
   case ION_S_p2: {
     const double TeV = T / 1.16045221e4;
     const double TeV_inv = 1. / TeV;
     rate = rrfit_metal(10, T) +
-           (8.0729e-9 * exp(-17.56 * TeV_inv) + 1.1012e-10 * exp(-7.07 * TeV_inv)) * pow(TeV, -1.5);
+           (8.0729e-9 * exp(-17.56 * TeV_inv) + 1.1012e-10 * exp(-7.07 * TeV_inv)) * fpow(TeV, -1.5);
     break;
   }
   case ION_S_p3: {
@@ -106,7 +106,7 @@ CMIB_HD double verner_recombination_rate(int ion, double T) {
            (5.817e-7 * exp(-362.8 * T_inv) + 1.391e-6 * exp(-1058. * T_inv) +
             1.123e-5 * exp(-7160. * T_inv) + 1.521e-4 * exp(-3.26e4 * T_inv) +
             1.875e-3 * exp(-1.235e5 * T_inv) + 2.097e-2 * exp(-2.07e5 * T_inv)) *
-               pow(T, -1.5);
+               fpow(T, -1.5);
     break;
   }
   default:
@@ -133,7 +133,7 @@ CMIB_HD double ct_clamp(double t, double lo, double hi) {
   return s;
 }
 CMIB_HD double ct_fit(double a, double b, double c, double d, double t) {
-  return a * pow(t, b) * (1. + c * exp(d * t));
+  return a * fpow(t, b) * (1. + c * exp(d * t));
 }
 
 /* recombination X^(i+1) + H0 -> X^i + H+ ; T4 = T / 1e4 K */
@@ -161,11 +161,11 @@ CMIB_HD double ct_ionization_H(int ion, double T4) {
   switch (ion) {
   case ION_N_n: {
     const double t = ct_clamp(T4, 0.01, 5.);
-    return 4.55e-18 * pow(t, -0.29) * (1. - 0.92 * exp(-8.38 * t)) * exp(-1.086 / t);
+    return 4.55e-18 * fpow(t, -0.29) * (1. - 0.92 * exp(-8.38 * t)) * exp(-1.086 / t);
   }
   case ION_O_n: {
     const double t = ct_clamp(T4, 0.001, 1.);
-    return 7.4e-17 * pow(t, 0.47) * (1. + 24.37 * exp(-0.74 * t)) * exp(-0.023 / t);
+    return 7.4e-17 * fpow(t, 0.47) * (1. + 24.37 * exp(-0.74 * t)) * exp(-0.023 / t);
   }
   default: return 0.;
   }
@@ -180,9 +180,9 @@ CMIB_HD double ct_recombination_He(int ion, double T4) {
   }
   case ION_N_p1: return ct_fit(3.3e-16, 0.29, 1.3, -4.5, ct_clamp(T4, 0.1, 3.));
   case ION_N_p2: return 1.5e-16;
-  case ION_O_p1: return 2.e-16 * pow(ct_clamp(T4, 0.5, 5.), 0.95);
+  case ION_O_p1: return 2.e-16 * fpow(ct_clamp(T4, 0.5, 5.), 0.95);
   case ION_Ne_p1: return 1.e-20;
-  case ION_S_p2: return 1.1e-15 * pow(ct_clamp(T4, 0.1, 3.), 0.56);
+  case ION_S_p2: return 1.1e-15 * fpow(ct_clamp(T4, 0.1, 3.), 0.56);
   case ION_S_p3: return ct_fit(7.6e-19, 0.32, 3.4, -5.25, ct_clamp(T4, 0.1, 3.));
   default: return 0.;
   }

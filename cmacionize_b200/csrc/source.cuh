@@ -114,13 +114,13 @@ CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng 
 /* the five cumulative re-emission probabilities of a cell at temperature T */
 CMIB_HD void reemission_probabilities(double T, double *p) {
   const double T4 = T * 1.e-4;
-  const double alpha_1_H = 1.58e-13 * pow(T4, -0.53);
-  const double alpha_A_agn = 4.18e-13 * pow(T4, -0.7);
+  const double alpha_1_H = 1.58e-13 * fpow(T4, -0.53);
+  const double alpha_A_agn = 4.18e-13 * fpow(T4, -0.7);
   p[REEMIT_H] = alpha_1_H / alpha_A_agn;
-  const double alpha_1_He = 1.54e-13 * pow(T4, -0.486);
-  const double alpha_e_2tS = 2.1e-13 * pow(T4, -0.381);
-  const double alpha_e_2sS = 2.06e-14 * pow(T4, -0.451);
-  const double alpha_e_2sP = 4.17e-14 * pow(T4, -0.695);
+  const double alpha_1_He = 1.54e-13 * fpow(T4, -0.486);
+  const double alpha_e_2tS = 2.1e-13 * fpow(T4, -0.381);
+  const double alpha_e_2sS = 2.06e-14 * fpow(T4, -0.451);
+  const double alpha_e_2sP = 4.17e-14 * fpow(T4, -0.695);
   const double alphaHe = alpha_1_He + alpha_e_2tS + alpha_e_2sS + alpha_e_2sP;
   const double He_LyC = alpha_1_He / alphaHe;
   const double He_NpEEv = He_LyC + alpha_e_2tS / alphaHe;

@@ -69,7 +69,7 @@ CMIB_HD int ionization_states_hydrogen_helium(double alphaH, double alphaHe, dou
     he0 = 1.;
     return 0;
   }
-  const double alpha_e_2sP = 4.17e-20 * pow(T * 1.e-4, -0.861);
+  const double alpha_e_2sP = 4.17e-20 * fpow(T * 1.e-4, -0.861);
   const double ch1 = alphaH * nH / jH;
   const double ch2 = AHe * alpha_e_2sP * nH / jH;
   double che = 0.;
@@ -266,7 +266,7 @@ CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, doub
   const double nenhep = ne * nhep;
 
   gain = n * (hH * h0 + hHe * AHe * he0);
-  const double alpha_e_2sP = 4.17e-20 * pow(T4, -0.861);
+  const double alpha_e_2sP = 4.17e-20 * fpow(T4, -0.861);
   const double pHots = 1. / (1. + 77. * he0 / (sqrtT * h0));
   gain += pHots * 1.21765423e-18 * alpha_e_2sP * nenhep;
   gain += 1.5e-37 * n * ne * pahfac;
@@ -302,7 +302,7 @@ CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, doub
   const double gff = 1.1 + 0.34 * exp(-c * c / 3.);
   loss += 1.42e-40 * gff * sqrtT * (nenhp + nenhep);
   const double Lhp = 2.85e-40 * nenhp * sqrtT * (5.914 - 0.5 * logT + 0.01184 * cbrt(T));
-  const double Lhep = 1.55e-39 * nenhep * pow(T, 0.3647);
+  const double Lhep = 1.55e-39 * nenhep * powl(T, logT, 0.3647);
   loss += Lhp + Lhep;
   loss = (loss < 0.) ? 0. : loss; /* std::max(loss, 0.) */
   gain = (gain < 0.) ? 0. : gain;

@@ -19,6 +19,7 @@ ap.add_argument("--packets", type=float, default=4194304)
 ap.add_argument("--problem", default="lexington", choices=["lexington", "stromgren", "stromgren256", "clumpy256"])
 ap.add_argument("--algorithm", type=int, default=0)
 ap.add_argument("--repeat", type=int, default=1)
+ap.add_argument("--spinup-packets", type=float, default=2e6)
 args = ap.parse_args()
 
 import torch
@@ -39,7 +40,7 @@ else:
     spin = 6
 ctx = prob.ctx
 for loop in range(spin):
-    problems.run_iteration(prob, loop, n_packets=2_000_000)
+    problems.run_iteration(prob, loop, n_packets=int(args.spinup_packets))
 ctx.synchronize()
 ctx.set_shoot_algorithm(args.algorithm)
 cudart = ctypes.CDLL("libcudart.so")
