@@ -92,6 +92,7 @@ struct cmib_context {
   GridGeom geom;
   /* grid state */
   DevBuf<CellOpacity> cells;
+  DevBuf<double2> cells_h;
   DevBuf<double> xmetal, heat_norm, cr_factor, reemit_prob, acc;
   bool have_cr_factor = false;
   bool reemit_prob_valid = false;
@@ -115,6 +116,9 @@ struct cmib_context {
   int queue_mode = -1;
   DevBuf<double> mq, rq;
   DevBuf<unsigned long long> ctl;
+  DevBuf<uint32_t> sort_key, sort_order, sort_hist;
+  int sort_mode = 0; /* 0 off (default: measured slower), 1 on, -1 auto by working set */
+  size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2] = {0, 0};
   uint64_t shoot_rounds = 0;
@@ -131,6 +135,10 @@ struct cmib_context {
       if (src.xs_fixed[k] != 0.) return ACC_FULL;
     return ACC_HONLY;
   }
+  /* H-only accumulator layout: planes when cells_h + accumulators do not fit in L2 */
+  bool honly_planar() const { return (size_t)geom.ncells * 32 > l2_bytes; }
+  int64_t honly_cell_stride() const { return honly_planar() ? 1 : 2; }
+  int64_t honly_term_stride() const { return honly_planar() ? geom.ncells : 1; }
   size_t acc_doubles(int mode) const {
     return ACC_COUNTERS + (size_t)geom.ncells * (mode == ACC_HONLY ? 2 : 16);
   }
@@ -230,6 +238,31 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   W.mq = ctx->mq.p;
   W.rq = ctx->rq.p;
   W.capacity = cap;
+  /* coherence sort: on when the gathered + accumulated working set does not fit in L2 */
+  int sort = ctx->sort_mode;
+  if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
+  if (sort < 0) {
+    const size_t working_set = (size_t)ctx->geom.ncells * (sizeof(CellOpacity) + (mode == ACC_HONLY ? 16 : 128));
+    sort = working_set > ctx->l2_bytes ? 1 : 0;
+  }
+  W.sort = sort;
+  W.key = nullptr; W.order = nullptr; W.hist = nullptr; W.nbins = 0; W.isrc_bits_shift = SORT_DIR_BITS;
+  if (sort) {
+    /* keep the number of bins <= 2^20: fewer direction bits when there are many sources */
+    int shift = 6; /* 8 x 8 direction bins per source: see wavefront.cuh */
+    if (const char *e = getenv("CMIB_SORT_DIR_BITS")) shift = atoi(e);
+    if (shift < 0) shift = 0;
+    if (shift > SORT_DIR_BITS) shift = SORT_DIR_BITS;
+    while (shift > 0 && ((uint64_t)P.src.n_sources << shift) > (1ull << 20)) --shift;
+    W.isrc_bits_shift = shift;
+    W.nbins = (uint32_t)(((uint64_t)P.src.n_sources << shift) + SORT_POS_BINS);
+    if (ctx->sort_key.n < cap) {
+      CUDA_OK(ctx->sort_key.resize(cap));
+      CUDA_OK(ctx->sort_order.resize(cap));
+    }
+    if (ctx->sort_hist.n < W.nbins + 1) CUDA_OK(ctx->sort_hist.resize(W.nbins + 1));
+    W.key = ctx->sort_key.p; W.order = ctx->sort_order.p; W.hist = ctx->sort_hist.p;
+  }
   const unsigned prep_grid = (unsigned)ctx->sm_count * 4;
   int bpm = ctx->march_blocks_per_sm[mode];
   if (bpm < 1) bpm = 1;
@@ -256,6 +289,13 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
       else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
       stamp();
       advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
+      if (sort) {
+        CUDA_OK(cudaMemsetAsync(W.hist, 0, (W.nbins + 1) * sizeof(uint32_t), s));
+        sort_histogram_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist);
+        sort_scan_kernel<<<1, 1024, 0, s>>>(W.hist, W.nbins);
+        sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist, W.order);
+        g_launches += 3;
+      }
       stamp();
       if (mode == ACC_HONLY) march_kernel<ACC_HONLY><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
       else march_kernel<ACC_FULL><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
@@ -312,6 +352,7 @@ int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
   cmib_context *ctx = new cmib_context();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
   CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   GridGeom &g = ctx->geom;
   for (int d = 0; d < 3; ++d) {
@@ -327,6 +368,8 @@ int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
   g.ncells = (int64_t)g.ncell[0] * g.ncell[1] * g.ncell[2];
   const size_t nc = (size_t)g.ncells;
   CUDA_OK(ctx->cells.resize(nc));
+  CUDA_OK(ctx->cells_h.resize(nc));
+  CUDA_OK(cudaMemsetAsync(ctx->cells_h.p, 0, nc * sizeof(double2), ctx->stream));
   CUDA_OK(ctx->xmetal.resize(nc * 12));
   CUDA_OK(ctx->heat_norm.resize(nc * 2));
   CUDA_OK(cudaMemsetAsync(ctx->cells.p, 0, nc * sizeof(CellOpacity), ctx->stream));
@@ -396,7 +439,7 @@ int cmib_upload_cells(cmib_context *ctx, const double *n, const double *T, const
   CUDA_OK(cudaMemcpyAsync(s + nc, T, nc * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(cudaMemcpyAsync(s + 2 * nc, x, nc * 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   pack_cells_kernel<<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, s, s + nc, s + 2 * nc,
-                                                                  ctx->cells.p, ctx->xmetal.p);
+                                                                  ctx->cells.p, ctx->cells_h.p, ctx->xmetal.p);
   ++g_launches;
   CUDA_OK(cudaGetLastError());
   if (cr_factor) {
@@ -434,9 +477,10 @@ int cmib_download_accumulators(cmib_context *ctx, double *J, double *heat) {
   CUDA_OK(ctx->stage.resize(nc * 18));
   double *s = ctx->stage.p;
   if (ctx->acc_mode == ACC_HONLY)
-    unpack_acc_kernel<ACC_HONLY><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, s, s + 14 * nc);
+    unpack_acc_kernel<ACC_HONLY><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>(
+        (int64_t)nc, ctx->acc.p, ctx->honly_cell_stride(), ctx->honly_term_stride(), s, s + 14 * nc);
   else
-    unpack_acc_kernel<ACC_FULL><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, s, s + 14 * nc);
+    unpack_acc_kernel<ACC_FULL><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, 0, 0, s, s + 14 * nc);
   ++g_launches;
   CUDA_OK(cudaGetLastError());
   if (J) CUDA_OK(cudaMemcpyAsync(J, s, nc * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -617,8 +661,11 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
     P.geom = ctx->geom;
     P.src = ctx->src;
     P.cells = ctx->cells.p;
+    P.cells_h = ctx->cells_h.p;
     P.reemit_prob = ctx->reemit_prob.p;
     P.acc = ctx->acc.p;
+    P.honly_cell_stride = ctx->honly_cell_stride();
+    P.honly_term_stride = ctx->honly_term_stride();
     P.nu_H = ctx->nu_H;
     P.nu_He = ctx->nu_He;
     P.seed = seed;
@@ -658,10 +705,13 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   UpdateParams P;
   P.geom = ctx->geom;
   P.cells = ctx->cells.p;
+  P.cells_h = ctx->cells_h.p;
   P.xmetal = ctx->xmetal.p;
   P.heat_norm = ctx->heat_norm.p;
   P.cr_factor = ctx->have_cr_factor ? ctx->cr_factor.p : nullptr;
   P.acc = ctx->acc.p;
+  P.honly_cell_stride = ctx->honly_cell_stride();
+  P.honly_term_stride = ctx->honly_term_stride();
   P.luminosity = ctx->luminosity;
   P.totweight = totweight;
   for (int k = 0; k < NUM_ELEMENTS; ++k) P.abund[k] = ctx->abund[k];

@@ -21,6 +21,11 @@
 #define CMIB_D inline
 #endif
 
+#if !defined(__CUDACC__)
+/* host build of the shared headers (tests/hostcheck): CUDA's vector type */
+struct double2 { double x, y; };
+#endif
+
 namespace cmib {
 
 enum Ion : int {

@@ -8,7 +8,7 @@
  *
  * Accumulator layouts: after 8 leading counter doubles,
  *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
- *   ACC_HONLY  acc[cell][2]  = J_H, heat_H              (16 B; used when only sigma_H != 0)
+ *   ACC_HONLY  J_H[ncell], heat_H[ncell] planes         (used when only sigma_H != 0)
  */
 #pragma once
 #include <cuda_runtime.h>
@@ -104,7 +104,9 @@ march_packets_kernel(const __grid_constant__ MarchPacketsParams P) {
     const CellOpacity c = P.cells[cell];
     const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sHe);
     if (c.n > 0.) {
-      accumulate<ACC_FULL>(DeviceAdder(), P.acc, cell, ds, w, sigma, nu - P.nu_H, nu - P.nu_He);
+      ShootParams sp;
+      sp.acc = P.acc;
+      accumulate<ACC_FULL>(DeviceAdder(), sp, cell, ds, w, sigma, nu - P.nu_H, nu - P.nu_He);
       if (P.trace && nsteps < P.max_trace) P.trace[p * P.max_trace + nsteps] = cell;
       ++nsteps;
     }
@@ -133,10 +135,12 @@ __global__ void reemission_probabilities_kernel(int64_t ncell, const CellOpacity
 struct UpdateParams {
   GridGeom geom;
   CellOpacity *cells;
+  double2 *cells_h;      /* compact (n, x_H) copy, kept in step with cells */
   double *xmetal;        /* [ncell][12] */
   double *heat_norm;     /* [ncell][2] */
   const double *cr_factor; /* [ncell] or NULL */
   const double *acc;
+  int64_t honly_cell_stride, honly_term_stride; /* H-only accumulator layout (shoot.cuh) */
   double luminosity;
   double totweight;      /* <= 0: read acc[0] */
   double abund[NUM_ELEMENTS];
@@ -162,8 +166,8 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
   if (MODE == ACC_HONLY) {
 #pragma unroll
     for (int k = 0; k < NUM_IONS; ++k) J[k] = 0.;
-    J[0] = a[0];
-    heat[0] = a[1];
+    J[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride];
+    heat[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride + P.honly_term_stride];
     heat[1] = 0.;
   } else {
 #pragma unroll
@@ -191,6 +195,7 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
   c.xHe = out.x[ION_He_n];
   c.T = out.T;
   P.cells[i] = c;
+  P.cells_h[i] = make_double2(c.n, c.xH);
 #pragma unroll
   for (int k = 0; k < 12; ++k) P.xmetal[i * 12 + k] = out.x[2 + k];
   P.heat_norm[i * 2] = out.heat[0];
@@ -199,7 +204,7 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
 
 /* host SoA <-> device layout */
 __global__ void pack_cells_kernel(int64_t ncell, const double *n, const double *T, const double *x,
-                                  CellOpacity *cells, double *xmetal) {
+                                  CellOpacity *cells, double2 *cells_h, double *xmetal) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell) return;
   CellOpacity c;
@@ -208,6 +213,7 @@ __global__ void pack_cells_kernel(int64_t ncell, const double *n, const double *
   c.xH = x[i];
   c.xHe = x[ncell + i];
   cells[i] = c;
+  cells_h[i] = make_double2(c.n, c.xH);
   for (int k = 0; k < 12; ++k) xmetal[i * 12 + k] = x[(2 + k) * ncell + i];
 }
 
@@ -228,14 +234,15 @@ __global__ void unpack_cells_kernel(int64_t ncell, const CellOpacity *cells, con
 
 /* accumulators -> reference SoA view J[14][ncell], heat[2][ncell] */
 template <int MODE>
-__global__ void unpack_acc_kernel(int64_t ncell, const double *acc, double *J, double *heat) {
+__global__ void unpack_acc_kernel(int64_t ncell, const double *acc, int64_t honly_cell_stride,
+                                  int64_t honly_term_stride, double *J, double *heat) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell) return;
   const double *a = acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
   if (MODE == ACC_HONLY) {
     for (int k = 1; k < NUM_IONS; ++k) J[k * ncell + i] = 0.;
-    J[i] = a[0];
-    heat[i] = a[1];
+    J[i] = acc[ACC_COUNTERS + i * honly_cell_stride];
+    heat[i] = acc[ACC_COUNTERS + i * honly_cell_stride + honly_term_stride];
     heat[ncell + i] = 0.;
   } else {
     for (int k = 0; k < NUM_IONS; ++k) J[k * ncell + i] = a[k];

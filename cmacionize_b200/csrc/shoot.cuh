@@ -15,7 +15,10 @@
  *
  * Accumulator layouts: after ACC_COUNTERS leading counter doubles,
  *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
- *   ACC_HONLY  acc[cell][2]  = J_H, heat_H              (16 B; used when only sigma_H != 0)
+ *   ACC_HONLY  J_H, heat_H per cell (used when only sigma_H != 0), interleaved or as two planes
+ *              (ShootParams::honly_*_stride): a monochromatic source at the threshold adds no
+ *              heat, so with planes only the 8 B/cell J plane is ever touched — half the
+ *              footprint competing for L2 on HBM-resident grids
  */
 #pragma once
 #include "cmib_common.cuh"
@@ -36,8 +39,13 @@ struct ShootParams {
   GridGeom geom;
   SourceModel src;
   const CellOpacity *cells;
+  const double2 *cells_h;    /* compact (n, x_H) copy for the H-only walk: 16 B instead of 32 B per gather */
   const double *reemit_prob; /* [ncell][5] (REEMISSION_PHYSICAL) */
   double *acc;               /* counters + per-cell accumulators */
+  /* H-only layout: term k of cell c lives at acc[8 + c*honly_cell_stride + k*honly_term_stride]:
+   * interleaved (2, 1) while the grid is L2 resident (spreads hot cells over more sectors),
+   * planar (1, ncells) when it is not (halves the footprint a threshold source touches) */
+  int64_t honly_cell_stride, honly_term_stride;
   double nu_H, nu_He;        /* 13.6 eV, 24.6 eV in Hz (DensityGrid.hpp:219-222) */
   uint64_t seed;
   uint32_t iteration;
@@ -55,16 +63,23 @@ struct ShootCounters {
 
 /* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which
  * is exact (x + 0.0 == x) and removes most of the 16 RMWs for soft photons */
+/* address of accumulator term k (FULL: 0..13 J, 14 heat_H, 15 heat_He; HONLY: 0 J_H, 1 heat_H) */
+template <int MODE>
+CMIB_HD double *acc_term(const ShootParams &P, int64_t cell, int k) {
+  if (MODE == ACC_HONLY) return P.acc + ACC_COUNTERS + cell * P.honly_cell_stride + (int64_t)k * P.honly_term_stride;
+  return P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + k;
+}
+
 template <int MODE, class Adder>
-CMIB_HD void accumulate(const Adder &add, double *acc, int64_t cell, double ds, double weight,
+CMIB_HD void accumulate(const Adder &add, const ShootParams &P, int64_t cell, double ds, double weight,
                         const double *sigma, double dnu_H, double dnu_He) {
   const double dsw = ds * weight;
-  double *a = acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
+  double *a = P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC;
   if (MODE == ACC_HONLY) {
     const double dJ = dsw * sigma[0];
-    add(a, dJ);
+    add(acc_term<MODE>(P, cell, 0), dJ);
     const double dh = dJ * dnu_H;
-    if (dh != 0.) add(a + 1, dh);
+    if (dh != 0.) add(acc_term<MODE>(P, cell, 1), dh);
   } else {
     const double dJH = dsw * sigma[ION_H_n];
     const double dJHe = dsw * sigma[ION_He_n];
@@ -136,7 +151,7 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
       s.last_cell = cell;
       c = load_cell(P.cells, cell);
       const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
-      if (c.n > 0.) accumulate<MODE>(add, P.acc, cell, ds, weight, sigma, dnu_H, dnu_He);
+      if (c.n > 0.) accumulate<MODE>(add, P, cell, ds, weight, sigma, dnu_H, dnu_He);
       ++cnt.n_steps;
     }
     if (!inside) break; /* left the box: keeps its last type */

@@ -64,7 +64,93 @@ struct WavefrontParams {
   double *mq;              /* march queue: [NFIELDS][capacity] */
   double *rq;              /* re-emission queue: [RQ_NFIELDS][capacity] */
   uint64_t capacity;
+  /* optional coherence sort of the march queue (grids that do not fit in L2) */
+  int sort;                /* 0: march reads the queue in emission order */
+  uint32_t *key;           /* [capacity] sort key of each queue entry */
+  uint32_t *order;         /* [capacity] queue entries in key order */
+  uint32_t *hist;          /* [nbins + 1] */
+  uint32_t nbins;
+  int isrc_bits_shift;     /* key = isrc << shift | direction bin (primaries) */
 };
+
+/*
+ * Coherence key.  Packets that start at the same source and leave in nearly the same direction
+ * walk through the same cells: queue entries are ordered by (source, direction bin on a
+ * 64 x 64 octahedral map in Morton order) so that the packets in flight at any time — the
+ * warps claim consecutive chunks of the ordered queue — cover a narrow cone of the grid that
+ * fits in L2, instead of the whole HBM-resident grid.  Re-emitted packets start anywhere; they are
+ * ordered by a 16^3 Morton bin of their start position.  Ordering changes which packets run
+ * together, not what any packet does: results are identical up to the order of the atomic adds.
+ */
+constexpr int SORT_DIR_BITS = 12;  /* 64 x 64 direction bins */
+constexpr int SORT_POS_BINS = 4096; /* 16^3 position bins */
+
+CMIB_D uint32_t morton2_6(uint32_t x, uint32_t y) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) r |= ((x >> b) & 1u) << (2 * b) | ((y >> b) & 1u) << (2 * b + 1);
+  return r;
+}
+CMIB_D uint32_t morton3_4(uint32_t x, uint32_t y, uint32_t z) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+    r |= ((x >> b) & 1u) << (3 * b) | ((y >> b) & 1u) << (3 * b + 1) | ((z >> b) & 1u) << (3 * b + 2);
+  return r;
+}
+CMIB_D uint32_t direction_bin(double dx, double dy, double dz) {
+  const float ax = fabsf((float)dx), ay = fabsf((float)dy), az = fabsf((float)dz);
+  const float inv = 1.f / fmaxf(ax + ay + az, 1e-30f);
+  float u = (float)dx * inv, v = (float)dy * inv;
+  if (dz < 0.) {
+    const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f);
+    const float vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
+    u = uu; v = vv;
+  }
+  const int iu = min(63, max(0, (int)((u * 0.5f + 0.5f) * 64.f)));
+  const int iv = min(63, max(0, (int)((v * 0.5f + 0.5f) * 64.f)));
+  return morton2_6((uint32_t)iu, (uint32_t)iv);
+}
+CMIB_D uint32_t position_bin(const GridGeom &g, double px, double py, double pz) {
+  const int ix = min(15, max(0, (int)((px - g.anchor[0]) / g.sides[0] * 16.)));
+  const int iy = min(15, max(0, (int)((py - g.anchor[1]) / g.sides[1] * 16.)));
+  const int iz = min(15, max(0, (int)((pz - g.anchor[2]) / g.sides[2] * 16.)));
+  return morton3_4((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+}
+
+/* counting sort of the march queue by key: histogram -> exclusive scan -> scatter */
+__global__ void sort_histogram_kernel(const unsigned long long *ctl, const uint32_t *key, uint32_t *hist) {
+  const uint64_t n = ctl[CTL_QCOUNT];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    atomicAdd(&hist[key[i]], 1u);
+}
+/* one block: hist[b] <- number of entries with a smaller key */
+__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *hist, uint32_t nbins) {
+  __shared__ uint32_t part[1024];
+  const uint32_t per = (nbins + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per, hi = min(nbins, lo + per);
+  uint32_t sum = 0;
+  for (uint32_t b = lo; b < hi; ++b) sum += hist[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const uint32_t v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - sum; /* exclusive */
+  for (uint32_t b = lo; b < hi; ++b) {
+    const uint32_t c = hist[b];
+    hist[b] = run;
+    run += c;
+  }
+}
+__global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_t *key, uint32_t *hist, uint32_t *order) {
+  const uint64_t n = ctl[CTL_QCOUNT];
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    order[atomicAdd(&hist[key[i]], 1u)] = (uint32_t)i;
+}
 
 CMIB_D uint64_t pack_meta(uint32_t ndraw, int type) { return ((uint64_t)(uint32_t)type << 32) | ndraw; }
 
@@ -129,6 +215,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     double px = 0., py = 0., pz = 0., nu = 0.;
     uint64_t id = 0;
     int type = PACKET_PRIMARY;
+    int isrc_key = -1; /* source index of a primary, -1 for a re-emitted packet */
     if (w < n_re) {
       /* --- PhotonSource::reemit --- */
       px = W.rq[RQ_PX * cap + w];
@@ -176,6 +263,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       px = m.src_pos[3 * isrc];
       py = m.src_pos[3 * isrc + 1];
       pz = m.src_pos[3 * isrc + 2];
+      isrc_key = isrc;
       emit = true;
     }
     double dx = 0., dy = 0., dz = 0., tau = 0., sigma_He_corr = 0.;
@@ -204,6 +292,13 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
 #pragma unroll
         for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
         if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
+        if (W.sort) {
+          const uint32_t nprim = (uint32_t)m.n_sources << W.isrc_bits_shift;
+          uint32_t k;
+          if (isrc_key >= 0) k = ((uint32_t)isrc_key << W.isrc_bits_shift) | (direction_bin(dx, dy, dz) >> (SORT_DIR_BITS - W.isrc_bits_shift));
+          else k = nprim + position_bin(P.geom, px, py, pz);
+          W.key[slot] = k;
+        }
       }
     }
   }
@@ -329,9 +424,9 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
         const double dJH = dsw * sigH;
         if (dJH != 0.) {
-          atomicAdd(a + ION_H_n, dJH);
+          atomicAdd(acc_term<MODE>(P, cell, ION_H_n), dJH);
           const double dh = dJH * dnu_H;
-          if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
+          if (dh != 0.) atomicAdd(acc_term<MODE>(P, cell, MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
         }
         if (MODE == ACC_FULL) {
           const double dJHe = dsw * s_sig[NMETAL][tid];
@@ -389,7 +484,8 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           const int rank = __popc(waiting & ((1u << lane) - 1u));
           const uint64_t avail = end - cur;
           if (state == LANE_EMPTY && (uint64_t)rank < avail) {
-            const double *q = W.mq + (cur + rank);
+            const uint64_t slot = W.sort ? (uint64_t)W.order[cur + rank] : (cur + rank);
+            const double *q = W.mq + slot;
             px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
             dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
             const double nu = q[MQ_NU * cap];
@@ -445,7 +541,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
        * (n, x_H) only = one 16-byte load, the full walk takes the sector as one 256-bit load */
       CellOpacity c;
       if (MODE == ACC_HONLY) {
-        const double2 r0 = __ldg(reinterpret_cast<const double2 *>(P.cells + cell));
+        const double2 r0 = __ldg(P.cells_h + cell);
         c.n = r0.x; c.xH = r0.y; c.xHe = 0.; c.T = 0.;
       } else {
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -481,9 +577,9 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
           const double dJH = dsw * sigH;
           if (dJH != 0.) {
-            atomicAdd(a + ION_H_n, dJH);
+            atomicAdd(acc_term<MODE>(P, cell, ION_H_n), dJH);
             const double dh = dJH * dnu_H;
-            if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
+            if (dh != 0.) atomicAdd(acc_term<MODE>(P, cell, MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
           }
           if (MODE == ACC_FULL) {
             const double dJHe = dsw * s_sig[NMETAL][tid];

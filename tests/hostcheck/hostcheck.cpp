@@ -292,8 +292,11 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
     for (int64_t i = 0; i < nc; ++i) reemission_probabilities(cell_rec[i].T, &prob[i * NUM_REEMIT]);
   }
   P.cells = cell_rec.data();
+  P.cells_h = nullptr;
   P.reemit_prob = prob.data();
   P.acc = acc;
+  P.honly_cell_stride = 2;
+  P.honly_term_stride = 1;
   P.nu_H = (13.6 * ELECTRONVOLT) * (1. / PLANCK);
   P.nu_He = (24.6 * ELECTRONVOLT) * (1. / PLANCK);
   P.seed = seed;

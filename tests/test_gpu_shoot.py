@@ -174,7 +174,8 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
     streams: identical counters (packets by type, cell crossings, (re-)emissions) and
     accumulators equal up to the order of the atomic adds.  Small queue capacities force many
-    rounds, chunk boundaries and partially filled warps."""
+    rounds, chunk boundaries and partially filled warps; the coherence sort only changes which
+    packets run together."""
     import os
     from cmacionize_b200 import problems, capi
     npk = 60000
@@ -194,11 +195,12 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), ctx.ncells))
     ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
     results = []
-    for algorithm, capacity in ((1, None), (0, None), (0, 4096), (0, 1024)):
+    for algorithm, capacity, sort in ((1, None, 0), (0, None, 0), (0, 4096, 0), (0, 1024, 0), (0, None, 1), (0, 2048, 1)):
         if capacity is None:
             os.environ.pop("CMIB_QUEUE_CAPACITY", None)
         else:
             os.environ["CMIB_QUEUE_CAPACITY"] = str(capacity)
+        os.environ["CMIB_SORT"] = str(sort)   # coherence sort of the march queue (wavefront.cuh)
         ctx.set_shoot_algorithm(algorithm)
         ctx.reset_accumulators()
         ctx.update_reemission_probabilities()
@@ -206,6 +208,7 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         J, heat = ctx.download_accumulators()
         results.append((tw, tc, ctx.shoot_statistics(), J, heat))
     os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+    os.environ.pop("CMIB_SORT", None)
     ctx.close()
     tw0, tc0, st0, J0, h0 = results[0]
     assert tw0 == npk and tc0.sum() == npk
