@@ -44,6 +44,7 @@ enum CtlWord : int {
   CTL_NEXT_FRESH,   /* local index of the next primary */
   CTL_ROUND,
   CTL_ERROR,        /* set by a kernel that hit its safety valve */
+  CTL_EQCOUNT,      /* entries in the emission queue (re-emissions that survived the decision) */
   CTL_STATUS = 8,   /* ring of CTL_STATUS_SLOTS words: march-queue size after each prepare */
   CTL_STATUS_SLOTS = 64,
   CTL_WORDS = CTL_STATUS + CTL_STATUS_SLOTS
@@ -63,6 +64,7 @@ struct WavefrontParams {
   unsigned long long *ctl;
   double *mq;              /* march queue: [NFIELDS][capacity] */
   double *rq;              /* re-emission queue: [RQ_NFIELDS][capacity] */
+  double *eq;              /* emission queue: [EQ_NFIELDS][capacity] */
   uint64_t capacity;
   /* optional coherence sort of the march queue (grids that do not fit in L2) */
   int sort;                /* 0: march reads the queue in emission order */
@@ -188,36 +190,33 @@ CMIB_D void reduce_counters(double *acc, const ShootCounters &cnt) {
 }
 
 /* ------------------------------------------------------------------------- */
-/* prepare: re-emission decisions + fresh primaries -> march queue            */
+/* re-emission decision: re-emission queue -> emission queue                   */
 /* ------------------------------------------------------------------------- */
-template <int MODE>
+/* PhotonSource::reemit up to the choice of the new frequency (PhotonSource.cpp:272-295,
+ * PhysicalDiffuseReemissionHandler.cpp:219-370).  Cheap and branchy; its survivors are compacted
+ * into the emission queue so that the expensive, uniform part of an emission (direction, 14 cross
+ * sections, optical depth) runs on full warps in prepare_kernel.  (With both in one kernel the
+ * mixed rounds ran at 10 active threads per instruction, profiles/r01_prepare.md.) */
+enum EmitField : int { EQ_PX = 0, EQ_PY, EQ_PZ, EQ_NU, EQ_ID, EQ_META, EQ_NFIELDS };
+
 __global__ void __launch_bounds__(256)
-prepare_kernel(const __grid_constant__ WavefrontParams W) {
-  constexpr int NSIG = AccLayout<MODE>::NSIG;
+reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
   const ShootParams &P = W.sp;
   const SourceModel &m = P.src;
   const uint64_t cap = W.capacity;
   const uint64_t n_re = W.ctl[CTL_RQCOUNT];
-  const uint64_t remaining = W.ctl[CTL_REMAINING];
-  const uint64_t next_fresh = W.ctl[CTL_NEXT_FRESH];
-  const uint64_t room = cap - n_re;
-  const uint64_t n_fresh = remaining < room ? remaining : room;
-  const uint64_t n_items = n_re + n_fresh;
   ShootCounters cnt;
   const int lane = threadIdx.x & 31;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  /* warp-uniform trip count so that the ballot below is executed by whole warps */
   const uint64_t first = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
-  for (uint64_t w0 = first; w0 < n_items; w0 += stride) {
+  for (uint64_t w0 = first; w0 < n_re; w0 += stride) {
     const uint64_t w = w0 + lane;
     bool emit = false;
     PacketRng rng;
     double px = 0., py = 0., pz = 0., nu = 0.;
     uint64_t id = 0;
-    int type = PACKET_PRIMARY;
-    int isrc_key = -1; /* source index of a primary, -1 for a re-emitted packet */
+    int type = PACKET_ABSORBED;
     if (w < n_re) {
-      /* --- PhotonSource::reemit --- */
       px = W.rq[RQ_PX * cap + w];
       py = W.rq[RQ_PY * cap + w];
       pz = W.rq[RQ_PZ * cap + w];
@@ -251,9 +250,65 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       } else {
         emit = true;
       }
-    } else if (w < n_items) {
-      /* --- PhotonSource::get_random_photon --- */
-      id = P.packet_offset + next_fresh + (w - n_re);
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, emit);
+    if (ballot) {
+      unsigned long long base = 0;
+      const int leader = __ffs(ballot) - 1;
+      if (lane == leader) base = atomicAdd(&W.ctl[CTL_EQCOUNT], (unsigned long long)__popc(ballot));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (emit) {
+        double *q = W.eq + (base + __popc(ballot & ((1u << lane) - 1u)));
+        q[EQ_PX * cap] = px; q[EQ_PY * cap] = py; q[EQ_PZ * cap] = pz;
+        q[EQ_NU * cap] = nu;
+        q[EQ_ID * cap] = __longlong_as_double((long long)id);
+        q[EQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type));
+      }
+    }
+  }
+  reduce_counters(P.acc, cnt);
+}
+
+/* ------------------------------------------------------------------------- */
+/* prepare: emission queue + fresh primaries -> march queue                    */
+/* ------------------------------------------------------------------------- */
+/* Every item becomes a packet: item w goes to march-queue slot w (no atomics).  Items
+ * [0, n_eq) are re-emissions (frequency already drawn), [n_eq, n_eq + n_fresh) are primaries
+ * (PhotonSource::get_random_photon, PhotonSource.cpp:208-249); both then draw the direction
+ * (PhotonSource.hpp:141-148), evaluate the 14 cross sections (set_cross_sections, :189-199) and the
+ * optical depth tau = -ln u (IonizationPhotonShootJob.hpp:135). */
+template <int MODE>
+__global__ void __launch_bounds__(256)
+prepare_kernel(const __grid_constant__ WavefrontParams W) {
+  constexpr int NSIG = AccLayout<MODE>::NSIG;
+  const ShootParams &P = W.sp;
+  const SourceModel &m = P.src;
+  const uint64_t cap = W.capacity;
+  const uint64_t n_eq = W.ctl[CTL_EQCOUNT];
+  const uint64_t remaining = W.ctl[CTL_REMAINING];
+  const uint64_t next_fresh = W.ctl[CTL_NEXT_FRESH];
+  const uint64_t room = cap - n_eq;
+  const uint64_t n_fresh = remaining < room ? remaining : room;
+  const uint64_t n_items = n_eq + n_fresh;
+  ShootCounters cnt;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_items; w += stride) {
+    PacketRng rng;
+    double px, py, pz, nu;
+    uint64_t id;
+    int type = PACKET_PRIMARY;
+    int isrc_key = -1; /* source index of a primary, -1 for a re-emitted packet */
+    if (w < n_eq) {
+      px = W.eq[EQ_PX * cap + w];
+      py = W.eq[EQ_PY * cap + w];
+      pz = W.eq[EQ_PZ * cap + w];
+      nu = W.eq[EQ_NU * cap + w];
+      id = (uint64_t)__double_as_longlong(W.eq[EQ_ID * cap + w]);
+      const uint64_t meta = (uint64_t)__double_as_longlong(W.eq[EQ_META * cap + w]);
+      rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
+      type = (int)(meta >> 32);
+    } else {
+      id = P.packet_offset + next_fresh + (w - n_eq);
       rng_init(rng, P.seed, P.iteration, id);
       double x = rng_uniform(rng);
       (void)x; /* discrete vs continuous draw: consumed as in the reference */
@@ -264,42 +319,30 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       py = m.src_pos[3 * isrc + 1];
       pz = m.src_pos[3 * isrc + 2];
       isrc_key = isrc;
-      emit = true;
+      nu = 0.;
     }
-    double dx = 0., dy = 0., dz = 0., tau = 0., sigma_He_corr = 0.;
+    double dx, dy, dz, sigma_He_corr;
     double sigma[NSIG];
-    if (emit) {
-      ++cnt.n_emit;
-      random_direction(rng, dx, dy, dz);
-      if (w >= n_re) nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
-      packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
-      tau = -log(rng_uniform(rng));
-    }
-    /* warp-aggregated append */
-    const unsigned ballot = __ballot_sync(0xffffffffu, emit);
-    if (ballot) {
-      unsigned long long base = 0;
-      if (lane == (__ffs(ballot) - 1)) base = atomicAdd(&W.ctl[CTL_QCOUNT], (unsigned long long)__popc(ballot));
-      base = __shfl_sync(0xffffffffu, base, __ffs(ballot) - 1);
-      if (emit) {
-        const uint64_t slot = base + __popc(ballot & ((1u << lane) - 1u));
-        double *q = W.mq + slot;
-        q[MQ_PX * cap] = px; q[MQ_PY * cap] = py; q[MQ_PZ * cap] = pz;
-        q[MQ_DX * cap] = dx; q[MQ_DY * cap] = dy; q[MQ_DZ * cap] = dz;
-        q[MQ_NU * cap] = nu; q[MQ_TAU * cap] = tau;
-        q[MQ_ID * cap] = __longlong_as_double((long long)id);
-        q[MQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type));
+    ++cnt.n_emit;
+    random_direction(rng, dx, dy, dz);
+    if (w >= n_eq) nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+    packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+    const double tau = -log(rng_uniform(rng));
+    double *q = W.mq + w;
+    q[MQ_PX * cap] = px; q[MQ_PY * cap] = py; q[MQ_PZ * cap] = pz;
+    q[MQ_DX * cap] = dx; q[MQ_DY * cap] = dy; q[MQ_DZ * cap] = dz;
+    q[MQ_NU * cap] = nu; q[MQ_TAU * cap] = tau;
+    q[MQ_ID * cap] = __longlong_as_double((long long)id);
+    q[MQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type));
 #pragma unroll
-        for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
-        if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
-        if (W.sort) {
-          const uint32_t nprim = (uint32_t)m.n_sources << W.isrc_bits_shift;
-          uint32_t k;
-          if (isrc_key >= 0) k = ((uint32_t)isrc_key << W.isrc_bits_shift) | (direction_bin(dx, dy, dz) >> (SORT_DIR_BITS - W.isrc_bits_shift));
-          else k = nprim + position_bin(P.geom, px, py, pz);
-          W.key[slot] = k;
-        }
-      }
+    for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
+    if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
+    if (W.sort) {
+      const uint32_t nprim = (uint32_t)m.n_sources << W.isrc_bits_shift;
+      uint32_t k;
+      if (isrc_key >= 0) k = ((uint32_t)isrc_key << W.isrc_bits_shift) | (direction_bin(dx, dy, dz) >> (SORT_DIR_BITS - W.isrc_bits_shift));
+      else k = nprim + position_bin(P.geom, px, py, pz);
+      W.key[w] = k;
     }
   }
   reduce_counters(P.acc, cnt);
@@ -307,13 +350,15 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
 
 /* bookkeeping after prepare: consume the primaries, empty the re-emission queue */
 __global__ void advance_after_prepare_kernel(unsigned long long *ctl, uint64_t capacity) {
-  const uint64_t n_re = ctl[CTL_RQCOUNT];
+  const uint64_t n_eq = ctl[CTL_EQCOUNT];
   const uint64_t remaining = ctl[CTL_REMAINING];
-  const uint64_t room = capacity - n_re;
+  const uint64_t room = capacity - n_eq;
   const uint64_t n_fresh = remaining < room ? remaining : room;
   ctl[CTL_REMAINING] = remaining - n_fresh;
   ctl[CTL_NEXT_FRESH] += n_fresh;
+  ctl[CTL_QCOUNT] = n_eq + n_fresh; /* every item of prepare became a packet */
   ctl[CTL_RQCOUNT] = 0;
+  ctl[CTL_EQCOUNT] = 0;
   ctl[CTL_HEAD] = 0;
   const uint64_t round = ctl[CTL_ROUND];
   ctl[CTL_STATUS + (round % CTL_STATUS_SLOTS)] = ctl[CTL_QCOUNT];
