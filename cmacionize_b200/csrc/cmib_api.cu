@@ -274,6 +274,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   }
   const unsigned prep_grid = (unsigned)ctx->sm_count * 4;
   int bpm = ctx->march_blocks_per_sm[mode];
+  if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e);
   if (bpm < 1) bpm = 1;
   const unsigned march_grid = (unsigned)(ctx->sm_count * bpm);
   const int group = 4;

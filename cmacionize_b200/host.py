@@ -85,11 +85,12 @@ class ParameterFile:
 class IonizationSimulation:
     """cmi::IonizationSimulation (host/IonizationSimulation.hpp) on one GPU."""
 
-    def __init__(self, parameterfile, device=0, write_output=False, verbose=False):
+    def __init__(self, parameterfile, device=0, write_output=False, verbose=False, ngpus=1):
         self._h = C.c_void_p()
-        _check(lib.cmih_simulation_create(str(parameterfile).encode(), C.c_int(device),
-                                          C.c_int(1 if write_output else 0), C.c_int(1 if verbose else 0),
-                                          C.byref(self._h)))
+        self.ngpus = ngpus
+        _check(lib.cmih_simulation_create_multi(str(parameterfile).encode(), C.c_int(device), C.c_int(ngpus),
+                                                C.c_int(1 if write_output else 0), C.c_int(1 if verbose else 0),
+                                                C.byref(self._h)))
         info = (C.c_double * 4)()
         _check(lib.cmih_simulation_info(self._h, info))
         self.ncells = int(info[0])
@@ -119,10 +120,10 @@ class IonizationSimulation:
         _check(lib.cmih_simulation_iteration(self._h, C.c_uint32(loop), C.c_uint64(int(numphoton)), out))
         return dict(totweight=out[0], typecount=np.array(out[1:5]), shoot_s=out[5], update_s=out[6])
 
-    def fields(self):
+    def fields(self, device_index=0):
         """(number density, temperature, ionic fractions [14][ncell], heating [2][ncell])"""
         ctx = C.c_void_p()
-        _check(lib.cmih_simulation_context(self._h, C.byref(ctx)))
+        _check(lib.cmih_simulation_context_of(self._h, C.c_int(device_index), C.byref(ctx)))
         n = np.empty(self.ncells); T = np.empty(self.ncells)
         x = np.empty((capi.NUM_IONS, self.ncells)); heat = np.empty((capi.NUM_HEAT, self.ncells))
         vp = C.c_void_p

@@ -3,10 +3,11 @@
  * (photoionization) mode of the reference's executable
  * (/root/reference/src/CMacIonize.cpp:100-377, default branch :348-362):
  *
- *     CMacIonizeB200 --params <file> [--threads N] [--device D] [--every-iteration-output]
+ *     CMacIonizeB200 --params <file> [--threads N] [--device D] [--gpus G] [--every-iteration-output]
  *                    [--output-statistics] [--dry-run] [--verbose]
  *
- * --threads is accepted for command-line compatibility and ignored.  Other modes of the
+ * --threads is accepted for command-line compatibility and ignored.  --gpus G uses devices
+ * D .. D+G-1 of this node (packets split by global id, one ncclAllReduce per iteration).  Other modes of the
  * reference (--rhd, --dusty-radiative-transfer, --emission, --task-based) are outside the
  * accelerated path and are rejected with an error.
  */
@@ -17,13 +18,14 @@
 
 int main(int argc, char **argv) {
   std::string params;
-  int device = 0;
+  int device = 0, gpus = 1;
   bool every = false, stats = false, dry = false, verbose = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--params" && i + 1 < argc) params = argv[++i];
     else if (a == "--threads" && i + 1 < argc) ++i;
     else if (a == "--device" && i + 1 < argc) device = atoi(argv[++i]);
+    else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
     else if (a == "--every-iteration-output") every = true;
     else if (a == "--output-statistics") stats = true;
     else if (a == "--dry-run") dry = true;
@@ -37,13 +39,15 @@ int main(int argc, char **argv) {
     }
   }
   if (params.empty()) {
-    std::cerr << "usage: CMacIonizeB200 --params <parameter file> [--device D] [--every-iteration-output] "
+    std::cerr << "usage: CMacIonizeB200 --params <parameter file> [--device D] [--gpus G] [--every-iteration-output] "
                  "[--output-statistics] [--dry-run] [--verbose]\n";
     return 1;
   }
   try {
     cmi::Log log(verbose ? cmi::Log::INFO : cmi::Log::STATUS);
-    cmi::IonizationSimulation sim(true, every, stats, -1, params, device, &log);
+    std::vector<int> devices;
+    for (int g = 0; g < (gpus > 0 ? gpus : 1); ++g) devices.push_back(device + g);
+    cmi::IonizationSimulation sim(true, every, stats, -1, params, devices, &log);
     if (dry) {
       log.write_warning("Dry run requested. Program will now halt.");
       return 0;

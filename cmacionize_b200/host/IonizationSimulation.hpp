@@ -41,7 +41,11 @@
 #include <memory>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <dlfcn.h>
+#include <nccl.h> /* types only: the library is bound at run time, see NcclApi */
 
 #include "../../include/cmib.h"
 #include "Error.hpp"
@@ -565,21 +569,53 @@ private:
   bool all_fields_;
 };
 
+/* ---- NCCL, bound at run time ----
+ * Only multi-GPU runs need NCCL, and a process may already carry one (PyTorch bundles its own
+ * libnccl.so.2): dlopen picks up whatever is loaded, else the system library; nothing is linked. */
+struct NcclApi {
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  static NcclApi &get() {
+    static NcclApi api = load();
+    return api;
+  }
+
+private:
+  static NcclApi load() {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) cmi_error("Multi-GPU runs need NCCL: %s", dlerror());
+    NcclApi a;
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    if (!a.CommInitAll || !a.AllReduce || !a.CommDestroy) cmi_error("libnccl lacks the expected entry points!");
+    return a;
+  }
+};
+
 /* ---- the driver ---- */
 class IonizationSimulation {
 public:
-  /* same leading arguments as the reference; num_thread is accepted and ignored (the
-   * parallelism is the GPU's), `device` replaces the MPI communicator */
+  /* same leading arguments as the reference (IonizationSimulation.hpp:196-202); num_thread is
+   * accepted and ignored (the parallelism is the GPU's); the MPICommunicator* is replaced by the
+   * list of devices of this node.  With more than one device the packets of an iteration are
+   * split by global packet id, every device holds the whole grid, and ONE ncclAllReduce over the
+   * accumulator buffers replaces the reference's 16 chunked MPI_Allreduce + counter reductions
+   * (IonizationSimulation.cpp:410-416, 458-529); the state update is then run on every device
+   * (replicated), so no gather is needed (:540-618). */
   IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
-                       const std::string &parameterfile, int device = 0, Log *log = nullptr)
+                       const std::string &parameterfile, const std::vector<int> &devices, Log *log = nullptr)
       : every_iteration_output_(every_iteration_output), output_statistics_(output_statistics), log_(log),
         parameter_file_(parameterfile),
         number_of_iterations_(parameter_file_.get_value<uint32_t>("IonizationSimulation:number of iterations", 10)),
         number_of_photons_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons", 100000)),
         number_of_photons_init_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons first loop",
                                                                     number_of_photons_)),
-        abundances_(Abundances::generate(parameter_file_, log)) {
+        abundances_(Abundances::generate(parameter_file_, log)), devices_(devices) {
     (void)num_thread;
+    if (devices_.empty()) cmi_error("No device given!");
     cross_sections_.reset(CrossSections::generate(parameter_file_, log_));
     recombination_rates_.reset(RecombinationRates::generate(parameter_file_, log_));
     density_function_.reset(DensityFunctionFactory::generate(parameter_file_, log_));
@@ -589,7 +625,8 @@ public:
     const std::string grid_type = parameter_file_.get_value<std::string>("DensityGrid:type", "Cartesian");
     if (grid_type != "Cartesian")
       cmi_error("Unknown DensityGrid type: \"%s\" (the B200 backend provides Cartesian)!", grid_type.c_str());
-    density_grid_.reset(new CartesianDensityGrid(box, parameter_file_, device));
+    const auto ncell = parameter_file_.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64});
+    for (int device : devices_) density_grids_.emplace_back(new CartesianDensityGrid(box, ncell, device));
     photon_source_distribution_.reset(PhotonSourceDistributionFactory::generate(parameter_file_, log_));
     photon_source_spectrum_.reset(PhotonSourceSpectrum::generate("PhotonSourceSpectrum", parameter_file_, log_));
     if (photon_source_distribution_ && !photon_source_spectrum_)
@@ -598,12 +635,9 @@ public:
       cmi_error("Continuous photon sources are not provided by the B200 backend!");
     if (!photon_source_distribution_) cmi_error("No photon sources!");
     reemission_ = DiffuseReemissionHandler::generate(parameter_file_, log_);
+    const cmib_temperature_params tp = temperature_calculator_parameters(parameter_file_);
 
-    /* configure the device context: PhotonSource ctor (PhotonSource.cpp:55-146) */
-    cmib_context *ctx = density_grid_->context();
-    CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
-    CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
-    CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
+    /* configure every device context alike: PhotonSource ctor (PhotonSource.cpp:55-146) */
     const size_t ns = photon_source_distribution_->get_number_of_sources();
     std::vector<double> pos(3 * ns), w(ns);
     for (size_t i = 0; i < ns; ++i) {
@@ -612,9 +646,21 @@ public:
       w[i] = photon_source_distribution_->get_weight(i);
     }
     total_luminosity_ = photon_source_distribution_->get_total_luminosity();
-    CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), total_luminosity_));
-    CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
-    CMIB_CALL(cmib_set_reemission(ctx, reemission_.kind, reemission_.probability, reemission_.frequency));
+    for (auto &grid : density_grids_) {
+      cmib_context *ctx = grid->context();
+      CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
+      CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
+      CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
+      CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), total_luminosity_));
+      CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
+      CMIB_CALL(cmib_set_reemission(ctx, reemission_.kind, reemission_.probability, reemission_.frequency));
+      CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
+    }
+    if (devices_.size() > 1) {
+      comms_.resize(devices_.size());
+      if (NcclApi::get().CommInitAll(comms_.data(), (int)devices_.size(), devices_.data()) != ncclSuccess)
+        cmi_error("ncclCommInitAll failed for %zu devices!", devices_.size());
+    }
 
     output_folder_ = parameter_file_.get_value<std::string>("IonizationSimulation:output folder", ".");
     if (write_output) {
@@ -623,8 +669,6 @@ public:
         log_->write_warning("DensityGridWriter type ", wtype, " needs HDF5; writing the AsciiFile layout instead.");
       density_grid_writer_.reset(new AsciiFileDensityGridWriter(output_folder_, parameter_file_));
     }
-    const cmib_temperature_params tp = temperature_calculator_parameters(parameter_file_);
-    CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
     random_seed_ = parameter_file_.get_value<int32_t>("IonizationSimulation:random seed", 42);
     if (parameter_file_.get_value<bool>("IonizationSimulation:enable trackers", false))
       cmi_error("Trackers are not provided by the B200 backend!");
@@ -635,11 +679,26 @@ public:
     }
   }
 
+  IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
+                       const std::string &parameterfile, int device = 0, Log *log = nullptr)
+      : IonizationSimulation(write_output, every_iteration_output, output_statistics, num_thread, parameterfile,
+                             std::vector<int>{device}, log) {}
+
+  ~IonizationSimulation() {
+    for (ncclComm_t c : comms_) NcclApi::get().CommDestroy(c);
+  }
+
   /* IonizationSimulation::initialize (IonizationSimulation.cpp:239-326) */
   void initialize(DensityFunction *density_function = nullptr) {
     if (!density_function) density_function = density_function_.get();
     density_function->initialize();
-    density_grid_->initialize(*density_function);
+    density_grids_[0]->initialize(*density_function);
+    for (size_t d = 1; d < density_grids_.size(); ++d) {
+      density_grids_[d]->number_density = density_grids_[0]->number_density;
+      density_grids_[d]->temperature = density_grids_[0]->temperature;
+      density_grids_[d]->ionic_fraction = density_grids_[0]->ionic_fraction;
+      density_grids_[d]->upload();
+    }
   }
 
   struct IterationResult {
@@ -651,25 +710,65 @@ public:
   /* one pass of the loop body of IonizationSimulation::run (IonizationSimulation.cpp:359-643) */
   IterationResult iteration(uint32_t loop, uint64_t numphoton) {
     using clock = std::chrono::steady_clock;
-    cmib_context *ctx = density_grid_->context();
+    const size_t ndev = density_grids_.size();
+    std::vector<IterationResult> part(ndev);
+    std::vector<std::string> errors(ndev);
+    auto work = [&](size_t d) {
+      try {
+        cmib_context *ctx = density_grids_[d]->context();
+        /* MPICommunicator::distribute (MPICommunicator.hpp:207-222): contiguous id blocks */
+        const uint64_t per = numphoton / ndev;
+        const uint64_t lo = d * per;
+        const uint64_t cnt = (d + 1 < ndev) ? per : numphoton - lo;
+        IterationResult &r = part[d];
+        density_grids_[d]->reset_grid();
+        CMIB_CALL(cmib_update_reemission_probabilities(ctx));
+        CMIB_CALL(cmib_synchronize(ctx));
+        const auto t0 = clock::now();
+        CMIB_CALL(cmib_shoot(ctx, cnt, lo, (uint64_t)(int64_t)random_seed_, loop, &r.totweight, r.typecount));
+        const auto t1 = clock::now();
+        double totweight = r.totweight;
+        if (ndev > 1) {
+          void *buf = nullptr, *stream = nullptr;
+          uint64_t n = 0;
+          CMIB_CALL(cmib_accumulator_buffer(ctx, &buf, &n));
+          CMIB_CALL(cmib_stream(ctx, &stream));
+          if (NcclApi::get().AllReduce(buf, buf, n, ncclDouble, ncclSum, comms_[d], (cudaStream_t)stream) != ncclSuccess)
+            cmi_error("ncclAllReduce failed on device %d!", devices_[d]);
+          totweight = 0.; /* use the reduced device-side sum */
+        }
+        CMIB_CALL(cmib_update_state(ctx, loop, totweight));
+        CMIB_CALL(cmib_synchronize(ctx));
+        const auto t2 = clock::now();
+        r.shoot_seconds = std::chrono::duration<double>(t1 - t0).count();
+        r.update_seconds = std::chrono::duration<double>(t2 - t1).count();
+      } catch (const std::exception &e) {
+        errors[d] = e.what();
+      }
+    };
+    if (ndev == 1) {
+      work(0);
+    } else {
+      std::vector<std::thread> threads;
+      for (size_t d = 0; d < ndev; ++d) threads.emplace_back(work, d);
+      for (auto &t : threads) t.join();
+    }
+    for (const std::string &e : errors)
+      if (!e.empty()) throw Error(e);
     IterationResult r;
-    density_grid_->reset_grid();
-    CMIB_CALL(cmib_update_reemission_probabilities(ctx));
-    CMIB_CALL(cmib_synchronize(ctx));
-    const auto t0 = clock::now();
-    CMIB_CALL(cmib_shoot(ctx, numphoton, 0, (uint64_t)(int64_t)random_seed_, loop, &r.totweight, r.typecount));
-    const auto t1 = clock::now();
-    CMIB_CALL(cmib_update_state(ctx, loop, r.totweight));
-    CMIB_CALL(cmib_synchronize(ctx));
-    const auto t2 = clock::now();
-    r.shoot_seconds = std::chrono::duration<double>(t1 - t0).count();
-    r.update_seconds = std::chrono::duration<double>(t2 - t1).count();
+    for (const IterationResult &p : part) {
+      r.totweight += p.totweight;
+      for (int t = 0; t < CMIB_NUM_PACKET_TYPES; ++t) r.typecount[t] += p.typecount[t];
+      r.shoot_seconds = std::max(r.shoot_seconds, p.shoot_seconds);
+      r.update_seconds = std::max(r.update_seconds, p.update_seconds);
+    }
     return r;
   }
 
   /* IonizationSimulation::run */
   void run() {
-    if (density_grid_writer_) density_grid_writer_->write(*density_grid_, 0);
+    CartesianDensityGrid &grid = *density_grids_[0];
+    if (density_grid_writer_) density_grid_writer_->write(grid, 0);
     double shoot = 0., update = 0.;
     for (uint32_t loop = 0; loop < number_of_iterations_; ++loop) {
       if (log_) log_->write_status("Starting loop ", loop, ".");
@@ -690,9 +789,9 @@ public:
         log_->write_info("Escape fraction from diffuse helium: ", 100. * r.typecount[2] / W, "%.");
       }
       if (every_iteration_output_ && density_grid_writer_ && loop + 1 < number_of_iterations_)
-        density_grid_writer_->write(*density_grid_, loop + 1);
+        density_grid_writer_->write(grid, loop + 1);
     }
-    if (density_grid_writer_) density_grid_writer_->write(*density_grid_, number_of_iterations_);
+    if (density_grid_writer_) density_grid_writer_->write(grid, number_of_iterations_);
     if (log_) {
       log_->write_status("Total photon shooting time: ", shoot, " s.");
       log_->write_status("Total cell update time: ", update, " s.");
@@ -701,7 +800,8 @@ public:
     total_update_seconds_ = update;
   }
 
-  CartesianDensityGrid &get_density_grid() { return *density_grid_; }
+  CartesianDensityGrid &get_density_grid(size_t device_index = 0) { return *density_grids_[device_index]; }
+  size_t get_number_of_devices() const { return density_grids_.size(); }
   ParameterFile &get_parameter_file() { return parameter_file_; }
   uint32_t get_number_of_iterations() const { return number_of_iterations_; }
   uint64_t get_number_of_photons() const { return number_of_photons_; }
@@ -716,10 +816,12 @@ private:
   uint32_t number_of_iterations_;
   uint64_t number_of_photons_, number_of_photons_init_;
   Abundances abundances_;
+  std::vector<int> devices_;
   std::unique_ptr<CrossSections> cross_sections_;
   std::unique_ptr<RecombinationRates> recombination_rates_;
   std::unique_ptr<DensityFunction> density_function_;
-  std::unique_ptr<CartesianDensityGrid> density_grid_;
+  std::vector<std::unique_ptr<CartesianDensityGrid>> density_grids_;
+  std::vector<ncclComm_t> comms_;
   std::unique_ptr<PhotonSourceDistribution> photon_source_distribution_;
   std::unique_ptr<PhotonSourceSpectrum> photon_source_spectrum_;
   DiffuseReemissionHandler reemission_;

@@ -29,9 +29,14 @@ int fail(const std::exception &e) {
 struct Sim {
   Log log;
   IonizationSimulation sim;
-  Sim(const char *paramfile, int device, int write_output, int verbose)
+  static std::vector<int> device_list(int first, int n) {
+    std::vector<int> v;
+    for (int g = 0; g < (n > 0 ? n : 1); ++g) v.push_back(first + g);
+    return v;
+  }
+  Sim(const char *paramfile, int device, int ngpus, int write_output, int verbose)
       : log(verbose ? Log::INFO : Log::WARNING),
-        sim(write_output != 0, false, verbose != 0, -1, paramfile, device, &log) {}
+        sim(write_output != 0, false, verbose != 0, -1, paramfile, device_list(device, ngpus), &log) {}
 };
 } // namespace
 
@@ -49,7 +54,12 @@ const char *cmih_last_error(void) { return g_error.c_str(); }
 
 /* IonizationSimulation(write_output, false, output_statistics, -1, parameterfile, device, log) */
 int cmih_simulation_create(const char *paramfile, int device, int write_output, int verbose, void **out) {
-  CMIH_TRY(*out = new Sim(paramfile, device, write_output, verbose));
+  CMIH_TRY(*out = new Sim(paramfile, device, 1, write_output, verbose));
+}
+/* devices device .. device+ngpus-1 of this node; one NCCL all-reduce per iteration */
+int cmih_simulation_create_multi(const char *paramfile, int device, int ngpus, int write_output, int verbose,
+                                 void **out) {
+  CMIH_TRY(*out = new Sim(paramfile, device, ngpus, write_output, verbose));
 }
 int cmih_simulation_destroy(void *h) {
   delete static_cast<Sim *>(h);
@@ -81,6 +91,9 @@ int cmih_simulation_info(void *h, double *info) {
 /* the cmib_context of the simulation's grid (for cmib_download_cells etc.) */
 int cmih_simulation_context(void *h, cmib_context **ctx) {
   CMIH_TRY(*ctx = static_cast<Sim *>(h)->sim.get_density_grid().context());
+}
+int cmih_simulation_context_of(void *h, int device_index, cmib_context **ctx) {
+  CMIH_TRY(*ctx = static_cast<Sim *>(h)->sim.get_density_grid((size_t)device_index).context());
 }
 
 /* ---- parameter-file probes (parity tests against the reference's ParameterFile) ---- */
