@@ -274,6 +274,7 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     shoot_ms = []
     kernel_ms = []   # (prepare ms, march ms, rounds) per timed step, from the library's CUDA events
+    update_ms = []
 
     def step(loop, npk_total=None, timed=False):
         if npk_total is None:
@@ -292,7 +293,13 @@ def main():
                 shoot_ms.append((e0, e1))
                 kernel_ms.append(ctx.shoot_timing(want_adds=False)[:3])
             allreduce(ctx)
+            if timed:
+                u0, u1 = ev(), ev()
+                u0.record(stream)
             ctx.update_state(loop, 0.)
+            if timed:
+                u1.record(stream)
+                update_ms.append((u0, u1))
 
     def barrier():
         if world > 1:
@@ -358,6 +365,7 @@ def main():
                 "kernel_share_of_step": march_ms / ms_per_step,
                 "prepare_kernel_ms": prep_ms, "prepare_share_of_step": prep_ms / ms_per_step,
                 "shoot_ms": 1e3 * shoot_s,
+                "update_state_kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in update_ms])),
                 "atomic": {"achieved": red_rate, "peak": RED_PEAK, "unit": "FP64 RED/s", "frac": red_rate / RED_PEAK,
                            "red_per_crossing": red_ops / max(crossings, 1.),
                            "note": "64^3 working set (8 MB cells + 34 MB accumulators) is L2 resident; ncu shows the "

@@ -118,6 +118,8 @@ struct cmib_context {
   DevBuf<double> mq, rq, eq;
   DevBuf<unsigned long long> ctl;
   DevBuf<uint32_t> sort_key, sort_order, sort_hist;
+  DevBuf<unsigned long long> upd_counter; /* next unprocessed cell of update_temperature_kernel */
+  int update_blocks_per_sm[2] = {0, 0};
   int sort_mode = 0; /* 0 off (default: measured slower), 1 on, -1 auto by working set */
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
@@ -735,10 +737,31 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   /* TemperatureCalculator.cpp:948: strictly greater */
   P.solve_temperature = (ctx->tp.do_temperature && loop > ctx->tp.min_iterations) ? 1 : 0;
   const int64_t nc = ctx->geom.ncells;
-  if (ctx->acc_mode == ACC_HONLY)
+  const char *simple = getenv("CMIB_UPDATE_SIMPLE");
+  if (P.solve_temperature && !(simple && simple[0] == '1')) {
+    /* temperature solve: persistent warps with dynamic cell hand-out (kernels.cuh) */
+    if (!ctx->upd_counter.p) {
+      CUDA_OK(ctx->upd_counter.resize(1));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->update_blocks_per_sm[ACC_FULL],
+                                                            update_temperature_kernel<ACC_FULL>, 128, 0));
+      CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->update_blocks_per_sm[ACC_HONLY],
+                                                            update_temperature_kernel<ACC_HONLY>, 128, 0));
+    }
+    CUDA_OK(cudaMemsetAsync(ctx->upd_counter.p, 0, sizeof(unsigned long long), ctx->stream));
+    int bpm = ctx->update_blocks_per_sm[ctx->acc_mode];
+    if (bpm < 1) bpm = 1;
+    unsigned grid = (unsigned)(ctx->sm_count * bpm);
+    const unsigned need = blocks_for(nc, 128);
+    if (grid > need) grid = need;
+    if (ctx->acc_mode == ACC_HONLY)
+      update_temperature_kernel<ACC_HONLY><<<grid, 128, 0, ctx->stream>>>(P, ctx->upd_counter.p);
+    else
+      update_temperature_kernel<ACC_FULL><<<grid, 128, 0, ctx->stream>>>(P, ctx->upd_counter.p);
+  } else if (ctx->acc_mode == ACC_HONLY) {
     update_state_kernel<ACC_HONLY><<<blocks_for(nc, 128), 128, 0, ctx->stream>>>(P);
-  else
+  } else {
     update_state_kernel<ACC_FULL><<<blocks_for(nc, 128), 128, 0, ctx->stream>>>(P);
+  }
   ++g_launches;
   CUDA_OK(cudaGetLastError());
   ctx->reemit_prob_valid = false;

@@ -202,6 +202,119 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
   P.heat_norm[i * 2 + 1] = out.heat[1];
 }
 
+/*
+ * Temperature update with dynamic cell hand-out: every pass each lane that owns a cell evaluates
+ * the heating/cooling balance ONCE (the state machine of state.cuh), lanes whose cell converged
+ * store it and take the next unprocessed cell from a global counter.  With one thread bound to one
+ * cell (update_state_kernel) a warp runs until its slowest cell has converged and cells that need
+ * no solve (vacuum, no radiation) idle a lane for the whole time: ncu showed 17 of 32 lanes active
+ * (profiles/r01_update_state.md).
+ */
+template <int MODE>
+__global__ void __launch_bounds__(128)
+update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long long *next_cell) {
+  const int lane = threadIdx.x & 31;
+  const int64_t ncells = P.geom.ncells;
+  const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
+  const double jfac = (P.luminosity / totweight) / P.geom.cell_volume;
+  const double hfac = ((P.luminosity / totweight) * PLANCK) / P.geom.cell_volume;
+  TemperatureSolve S;
+  CellState out;
+  double j[NUM_IONS], h[NUM_HEAT];
+  double ntot = 0., midz = 0.;
+  int64_t cell = -1;
+  bool jH_zero = false, jHe_zero = false;
+  bool has = false, exhausted = false;
+
+  auto store = [&](int64_t i, double n_keep) {
+    CellOpacity c;
+    c.n = n_keep;
+    c.xH = out.x[ION_H_n];
+    c.xHe = out.x[ION_He_n];
+    c.T = out.T;
+    P.cells[i] = c;
+    P.cells_h[i] = make_double2(c.n, c.xH);
+#pragma unroll
+    for (int k = 0; k < 12; ++k) P.xmetal[i * 12 + k] = out.x[2 + k];
+    P.heat_norm[i * 2] = out.heat[0];
+    P.heat_norm[i * 2 + 1] = out.heat[1];
+  };
+
+  while (true) {
+    /* ---- hand cells to idle lanes; cells that need no solve are finished on the spot ---- */
+    for (int tries = 0; tries < 8; ++tries) {
+      const unsigned idle = __ballot_sync(0xffffffffu, !has);
+      if (idle == 0u || exhausted) break;
+      unsigned long long base = 0;
+      const int leader = __ffs(idle) - 1;
+      if (lane == leader) base = atomicAdd(next_cell, (unsigned long long)__popc(idle));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (base + __popc(idle) >= (unsigned long long)ncells) exhausted = true;
+      const int64_t i = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+      if (!has && i < ncells) {
+        double J[NUM_IONS], heat[NUM_HEAT], xprev[NUM_IONS];
+        if (MODE == ACC_HONLY) {
+#pragma unroll
+          for (int k = 0; k < NUM_IONS; ++k) J[k] = 0.;
+          J[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride];
+          heat[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride + P.honly_term_stride];
+          heat[1] = 0.;
+        } else {
+          const double *a = P.acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
+#pragma unroll
+          for (int k = 0; k < NUM_IONS; ++k) J[k] = a[k];
+          heat[0] = a[NUM_IONS];
+          heat[1] = a[NUM_IONS + 1];
+        }
+        const CellOpacity c = P.cells[i];
+        xprev[0] = c.xH;
+        xprev[1] = c.xHe;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) xprev[2 + k] = P.xmetal[i * 12 + k];
+        const double crf = P.cr_factor ? P.cr_factor[i] : -1.;
+        if (temperature_solve_begin(S, jfac, hfac, J, heat, c.n, c.T, crf, P.abund, P.rr, P.tp, xprev, j, h, out)) {
+          if (temperature_solve_continues(S, P.tp)) {
+            /* cell midpoint z (CartesianDensityGrid.hpp:85-89): anchor + cellside*iz + 0.5*cellside */
+            const int32_t iz = (int32_t)(i % P.geom.ncell[2]);
+            midz = (P.geom.anchor[2] + P.geom.cellside[2] * iz) + 0.5 * P.geom.cellside[2];
+            ntot = c.n;
+            cell = i;
+            jH_zero = (J[ION_H_n] == 0.);
+            jHe_zero = (J[ION_He_n] == 0.);
+            has = true;
+          } else {
+            temperature_solve_finish(S, J, h, out);
+            store(i, c.n);
+          }
+        } else {
+          store(i, c.n);
+        }
+      }
+    }
+    if (__ballot_sync(0xffffffffu, has) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    /* ---- one balance evaluation for every lane that owns a cell ---- */
+    if (has) {
+      double h0e, he0e, gain, loss;
+      cooling_heating_balance(h0e, he0e, gain, loss, temperature_solve_T(S), ntot, midz, j, P.abund, h,
+                              P.tp.pahfac, S.crfac, P.tp.crscale, P.rr, out.x);
+      if (temperature_solve_advance(S, h0e, he0e, gain, loss, P.tp)) {
+        /* temperature_solve_finish only looks at whether J_H / J_He are zero */
+        double Jz[NUM_IONS];
+#pragma unroll
+        for (int k = 0; k < NUM_IONS; ++k) Jz[k] = 1.;
+        if (jH_zero) Jz[ION_H_n] = 0.;
+        if (jHe_zero) Jz[ION_He_n] = 0.;
+        temperature_solve_finish(S, Jz, h, out);
+        store(cell, ntot);
+        has = false;
+      }
+    }
+  }
+}
+
 /* host SoA <-> device layout */
 __global__ void pack_cells_kernel(int64_t ncell, const double *n, const double *T, const double *x,
                                   CellOpacity *cells, double2 *cells_h, double *xmetal) {

@@ -318,92 +318,138 @@ CMIB_HD void set_neutral_T(CellState &out) {
   out.heat[HEAT_He] = 0.;
 }
 
-/* full temperature + ionization update of one cell; `xprev` = current metal
- * fractions of the cell (kept when no balance evaluation overwrites them). */
-CMIB_HD void cell_temperature(double jfac, double hfac, const double *J, const double *heat,
-                              double ntot, double Tcell, double cr_factor, double midz,
-                              const double *abund, const RecombinationModel &rr,
-                              const TemperatureParams &tp, const double *xprev, CellState &out) {
+/*
+ * Temperature solve of one cell as a resumable state machine: every step is ONE evaluation of
+ * the heating/cooling balance (the expensive part) at the temperature temperature_solve_T()
+ * names, followed by temperature_solve_advance().  TemperatureCalculator::calculate_temperature
+ * (TemperatureCalculator.cpp:567-931) evaluates the balance at 1.1 T0, 0.9 T0 and T0 per secant
+ * iteration; cells need 1 to 100 iterations.  The kernel keeps all lanes of a warp inside the
+ * balance evaluation and hands a new cell to a lane as soon as its cell has converged
+ * (update_temperature_kernel), instead of waiting for the slowest cell of the warp.
+ * cell_temperature() below runs the same pieces in a plain loop (host logic check, eval probes).
+ */
+struct TemperatureSolve {
+  double T0, crfac;
+  double gain0, loss0, gain1, loss1, gain2, loss2, h0, he0;
+  uint32_t niter;
+  int phase; /* 0: balance at 1.1 T0, 1: at 0.9 T0, 2: at T0, then the secant update */
+};
+
+/* returns false when the cell needs no solve (out is final); otherwise fills j[14], h[2] with the
+ * normalised mean intensities / heating terms, seeds out.x with the cell's current fractions */
+CMIB_HD bool temperature_solve_begin(TemperatureSolve &S, double jfac, double hfac, const double *J,
+                                     const double *heat, double ntot, double Tcell, double cr_factor,
+                                     const double *abund, const RecombinationModel &rr,
+                                     const TemperatureParams &tp, const double *xprev, double *j,
+                                     double *h, CellState &out) {
   const double jH = jfac * J[ION_H_n];
   const double jHe = jfac * J[ION_He_n];
   if ((jH == 0. && jHe == 0.) || ntot == 0.) {
     set_neutral_T(out);
-    return;
+    return false;
   }
   double crfac = tp.crfac * cr_factor;
   if (crfac < 0.) crfac = tp.crfac;
-  double h0, he0;
   if (crfac > 0.) {
+    double h0, he0;
     const double alphaH = recombination_rate(rr, ION_H_n, 8000.);
     const double alphaHe = recombination_rate(rr, ION_He_n, 8000.);
     ionization_states_hydrogen_helium(alphaH, alphaHe, jH, jHe, ntot, abund[EL_He], 8000., h0, he0);
     if (h0 > tp.crlim) {
       set_neutral_T(out);
-      return;
+      return false;
     }
   }
-  double T0 = Tcell;
-  if (Tcell <= 4000.) T0 = 8000.;
-  double j[NUM_IONS];
+  S.crfac = crfac;
+  S.T0 = Tcell;
+  if (Tcell <= 4000.) S.T0 = 8000.;
 #pragma unroll
   for (int i = 0; i < NUM_IONS; ++i) j[i] = jfac * J[i];
-  double h[NUM_HEAT];
   h[HEAT_H] = hfac * heat[HEAT_H];
   h[HEAT_He] = hfac * heat[HEAT_He];
 #pragma unroll
   for (int i = 0; i < NUM_IONS; ++i) out.x[i] = xprev[i];
+  S.niter = 0;
+  S.gain0 = 1.;
+  S.loss0 = 0.;
+  S.h0 = 0.;
+  S.he0 = 0.;
+  S.gain1 = S.loss1 = S.gain2 = S.loss2 = 0.;
+  S.phase = 0;
+  return true;
+}
 
-  uint32_t niter = 0;
-  double gain0 = 1.;
-  double loss0 = 0.;
-  h0 = 0.;
-  he0 = 0.;
-  const double logtt = log(1.1 / 0.9);
-  while (fabs(gain0 - loss0) > tp.epsilon * gain0 && niter < tp.max_iterations) {
-    ++niter;
-    const double T1 = 1.1 * T0;
-    double h01, he01, gain1, loss1;
-    cooling_heating_balance(h01, he01, gain1, loss1, T1, ntot, midz, j, abund, h, tp.pahfac, crfac,
-                            tp.crscale, rr, out.x);
-    const double T2 = 0.9 * T0;
-    double h02, he02, gain2, loss2;
-    cooling_heating_balance(h02, he02, gain2, loss2, T2, ntot, midz, j, abund, h, tp.pahfac, crfac,
-                            tp.crscale, rr, out.x);
-    cooling_heating_balance(h0, he0, gain0, loss0, T0, ntot, midz, j, abund, h, tp.pahfac, crfac,
-                            tp.crscale, rr, out.x);
-    double expgain;
-    if (gain2 > 0.) {
-      expgain = (gain1 > 0.) ? log(gain1 / gain2) : -99.;
-    } else {
-      expgain = (gain1 > 0.) ? 99. : 0.;
-    }
-    double exploss;
-    if (loss2 > 0.) {
-      exploss = (loss1 > 0.) ? log(loss1 / loss2) : -99.;
-    } else {
-      exploss = (loss1 > 0.) ? 99. : 0.;
-    }
-    const double expdiff = expgain - exploss;
-    if (gain0 > 0. && expdiff != 0.) {
-      T0 *= pow(loss0 / gain0, logtt / expdiff);
-    } else {
-      T0 = T1;
-    }
-    if (T0 < tp.min_ionized_T) {
-      T0 = 500.;
-      h0 = 1.;
-      he0 = 1.;
-      gain0 = 1.;
-      loss0 = 1.;
-    }
-    if (T0 > 1.e10) {
-      T0 = 1.e10;
-      h0 = 1.e-10;
-      he0 = 1.e-10;
-      gain0 = 1.;
-      loss0 = 1.;
-    }
+/* the loop condition of the reference (:730): true while another secant iteration is due */
+CMIB_HD bool temperature_solve_continues(const TemperatureSolve &S, const TemperatureParams &tp) {
+  return fabs(S.gain0 - S.loss0) > tp.epsilon * S.gain0 && S.niter < tp.max_iterations;
+}
+
+CMIB_HD double temperature_solve_T(const TemperatureSolve &S) {
+  return (S.phase == 0) ? 1.1 * S.T0 : ((S.phase == 1) ? 0.9 * S.T0 : S.T0);
+}
+
+/* record the balance just evaluated; after the third one do the secant update.  Returns true
+ * when the solve has finished. */
+CMIB_HD bool temperature_solve_advance(TemperatureSolve &S, double h0e, double he0e, double gain,
+                                       double loss, const TemperatureParams &tp) {
+  if (S.phase == 0) {
+    ++S.niter;
+    S.gain1 = gain;
+    S.loss1 = loss;
+    S.phase = 1;
+    return false;
   }
+  if (S.phase == 1) {
+    S.gain2 = gain;
+    S.loss2 = loss;
+    S.phase = 2;
+    return false;
+  }
+  S.h0 = h0e;
+  S.he0 = he0e;
+  S.gain0 = gain;
+  S.loss0 = loss;
+  S.phase = 0;
+  double expgain;
+  if (S.gain2 > 0.) {
+    expgain = (S.gain1 > 0.) ? log(S.gain1 / S.gain2) : -99.;
+  } else {
+    expgain = (S.gain1 > 0.) ? 99. : 0.;
+  }
+  double exploss;
+  if (S.loss2 > 0.) {
+    exploss = (S.loss1 > 0.) ? log(S.loss1 / S.loss2) : -99.;
+  } else {
+    exploss = (S.loss1 > 0.) ? 99. : 0.;
+  }
+  const double expdiff = expgain - exploss;
+  const double logtt = log(1.1 / 0.9);
+  if (S.gain0 > 0. && expdiff != 0.) {
+    S.T0 *= pow(S.loss0 / S.gain0, logtt / expdiff);
+  } else {
+    S.T0 = 1.1 * S.T0;
+  }
+  if (S.T0 < tp.min_ionized_T) {
+    S.T0 = 500.;
+    S.h0 = 1.;
+    S.he0 = 1.;
+    S.gain0 = 1.;
+    S.loss0 = 1.;
+  }
+  if (S.T0 > 1.e10) {
+    S.T0 = 1.e10;
+    S.h0 = 1.e-10;
+    S.he0 = 1.e-10;
+    S.gain0 = 1.;
+    S.loss0 = 1.;
+  }
+  return !temperature_solve_continues(S, tp);
+}
+
+/* h = the normalised heating terms of temperature_solve_begin */
+CMIB_HD void temperature_solve_finish(const TemperatureSolve &S, const double *J, const double *h,
+                                      CellState &out) {
+  double T0 = S.T0, h0 = S.h0, he0 = S.he0;
   T0 = (T0 < 30000.) ? T0 : 30000.; /* std::min(30000., T0) */
   out.T = T0;
   if (J[ION_H_n] == 0.) h0 = 1.;
@@ -416,6 +462,26 @@ CMIB_HD void cell_temperature(double jfac, double hfac, const double *J, const d
   }
   out.heat[HEAT_H] = h[HEAT_H];
   out.heat[HEAT_He] = h[HEAT_He];
+}
+
+/* full temperature + ionization update of one cell; `xprev` = current metal
+ * fractions of the cell (kept when no balance evaluation overwrites them). */
+CMIB_HD void cell_temperature(double jfac, double hfac, const double *J, const double *heat,
+                              double ntot, double Tcell, double cr_factor, double midz,
+                              const double *abund, const RecombinationModel &rr,
+                              const TemperatureParams &tp, const double *xprev, CellState &out) {
+  TemperatureSolve S;
+  double j[NUM_IONS], h[NUM_HEAT];
+  if (!temperature_solve_begin(S, jfac, hfac, J, heat, ntot, Tcell, cr_factor, abund, rr, tp, xprev, j, h, out))
+    return;
+  bool finished = !temperature_solve_continues(S, tp);
+  while (!finished) {
+    double h0e, he0e, gain, loss;
+    cooling_heating_balance(h0e, he0e, gain, loss, temperature_solve_T(S), ntot, midz, j, abund, h,
+                            tp.pahfac, S.crfac, tp.crscale, rr, out.x);
+    finished = temperature_solve_advance(S, h0e, he0e, gain, loss, tp);
+  }
+  temperature_solve_finish(S, J, h, out);
 }
 
 } // namespace cmib

@@ -243,3 +243,30 @@ PhotonSourceSpectrum:
     vac = ~gas
     assert np.array_equal(T[vac], a[1][vac])
     assert np.array_equal(x[:, vac], a[2:16][:, vac])
+
+
+def test_temperature_update_kernels_agree_bitwise(cmib):
+    """The production temperature update (persistent warps, dynamic cell hand-out,
+    update_temperature_kernel) and the one-thread-per-cell kernel run the same per-cell state
+    machine on the same accumulators: every cell must come out bit-identical."""
+    import os
+    from cmacionize_b200 import problems
+    prob = problems.lexington(20, ncell=24, n_packets=400000)
+    ctx = prob.ctx
+    for loop in range(5):
+        problems.run_iteration(prob, loop)          # reach the temperature-solve iterations (loop > 3)
+    ctx.reset_accumulators()
+    ctx.update_reemission_probabilities()
+    ctx.shoot(400000, seed=3, iteration=5)
+    n0, T0, x0, _ = ctx.download_cells()
+    results = []
+    for simple in ("0", "1"):
+        os.environ["CMIB_UPDATE_SIMPLE"] = simple
+        ctx.upload_cells(n0, T0, x0)
+        ctx.update_state(5, 0.)
+        results.append(ctx.download_cells())
+    os.environ.pop("CMIB_UPDATE_SIMPLE", None)
+    ctx.close()
+    (na, Ta, xa, ha), (nb, Tb, xb, hb) = results
+    assert (Ta[n0 > 0] > 500.).mean() > 0.3          # the solve really ran
+    assert np.array_equal(Ta, Tb) and np.array_equal(xa, xb, equal_nan=True) and np.array_equal(ha, hb)
