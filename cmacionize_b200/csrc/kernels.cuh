@@ -211,7 +211,7 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
  * (profiles/r01_update_state.md).
  */
 template <int MODE>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128) /* (128, 3) forces spills and measured slower: 10.4 vs 9.7 ms */
 update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long long *next_cell) {
   const int lane = threadIdx.x & 31;
   const int64_t ncells = P.geom.ncells;
