@@ -26,7 +26,8 @@ RECOMBINATION_FIXED_VALUE, RECOMBINATION_VERNER = 0, 1
 SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK = 0, 1
 REEMISSION_NONE, REEMISSION_PHYSICAL, REEMISSION_FIXED_VALUE = 0, 1, 2
 
-LIB_PATH = Path(__file__).resolve().parent / "libcmib.so"
+# CMIB_LIB: load another build of the same ABI (A/B timing of kernel variants)
+LIB_PATH = Path(os.environ.get("CMIB_LIB") or (Path(__file__).resolve().parent / "libcmib.so"))
 
 
 class CmibError(RuntimeError):
@@ -238,6 +239,11 @@ class Context:
         b = C.c_double(0.)
         _check(lib.cmib_shoot_statistics(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def shoot_optical_depth(self):
+        t = C.c_double(0.)
+        _check(lib.cmib_shoot_optical_depth(self._h, C.byref(t)))
+        return t.value
 
     def accumulator_buffer(self):
         ptr = _vp()

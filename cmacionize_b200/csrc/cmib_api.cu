@@ -118,6 +118,10 @@ struct cmib_context {
   DevBuf<double> mq, rq, eq;
   DevBuf<unsigned long long> ctl;
   DevBuf<uint32_t> sort_key, sort_order, sort_hist;
+  DevBuf<double> hot_acc;       /* replicated accumulators of the cells around the sources */
+  DevBuf<uint32_t> d_src_cell;  /* packed cell indices of the sources */
+  std::vector<uint32_t> h_src_cell;
+  int hot_replicas = 0;
   DevBuf<unsigned long long> upd_counter; /* next unprocessed cell of update_temperature_kernel */
   int update_blocks_per_sm[2] = {0, 0};
   int sort_mode = 0; /* 0 off (default: measured slower), 1 on, -1 auto by working set */
@@ -149,8 +153,16 @@ struct cmib_context {
     return ((size_t)geom.ncells * 128 <= l2_bytes / 2) ? 16 : 2;
   }
   int64_t honly_term_stride() const { return honly_planar() ? geom.ncells : 1; }
+  /* padded records: J_H, heat_H sit in the second half of the cell's 128-B line.  Measured on
+   * stromgren 64^3 (4e6 packets): march 1.49 ms with the pair at byte 64 of the line, 1.78 ms at
+   * byte 0 (profiles/r01_layout_experiments.md) */
+  int64_t honly_offset() const {
+    if (const char *e = getenv("CMIB_HONLY_OFFSET")) return atoi(e);
+    return (!honly_planar() && honly_cell_stride() == 16) ? 8 : 0;
+  }
   size_t acc_doubles(int mode) const {
-    return ACC_COUNTERS + (size_t)geom.ncells * (mode == ACC_HONLY ? (honly_planar() ? 2 : (size_t)honly_cell_stride()) : 16);
+    if (mode != ACC_HONLY) return ACC_COUNTERS + (size_t)geom.ncells * 16;
+    return ACC_COUNTERS + 64 + (size_t)geom.ncells * (honly_planar() ? 2 : (size_t)honly_cell_stride());
   }
 };
 
@@ -330,6 +342,14 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     if (done) break;
   }
   ctx->shoot_rounds = round;
+  if (P.hot_replicas > 0) {
+    const int n = P.src.n_sources * HOT_CELLS * HOT_STRIDE;
+    if (mode == ACC_HONLY) fold_hot_cells_kernel<ACC_HONLY><<<blocks_for(n, 128), 128, 0, s>>>(P);
+    else fold_hot_cells_kernel<ACC_FULL><<<blocks_for(n, 128), 128, 0, s>>>(P);
+    ++g_launches;
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
   for (size_t k = 0; k + 3 < ev_used; k += 4) {
     float a = 0.f, b = 0.f;
     cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
@@ -495,9 +515,9 @@ int cmib_download_accumulators(cmib_context *ctx, double *J, double *heat) {
   double *s = ctx->stage.p;
   if (ctx->acc_mode == ACC_HONLY)
     unpack_acc_kernel<ACC_HONLY><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>(
-        (int64_t)nc, ctx->acc.p, ctx->honly_cell_stride(), ctx->honly_term_stride(), s, s + 14 * nc);
+        (int64_t)nc, ctx->acc.p, ctx->honly_cell_stride(), ctx->honly_term_stride(), ctx->honly_offset(), s, s + 14 * nc);
   else
-    unpack_acc_kernel<ACC_FULL><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, 0, 0, s, s + 14 * nc);
+    unpack_acc_kernel<ACC_FULL><<<blocks_for(nc, 256), 256, 0, ctx->stream>>>((int64_t)nc, ctx->acc.p, 0, 0, 0, s, s + 14 * nc);
   ++g_launches;
   CUDA_OK(cudaGetLastError());
   if (J) CUDA_OK(cudaMemcpyAsync(J, s, nc * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -562,6 +582,30 @@ int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, cons
   CUDA_OK(ctx->d_src_pos.upload(positions, (size_t)n * 3, ctx->stream));
   CUDA_OK(ctx->d_src_cum.upload(cum.data(), (size_t)n, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  /* cell of every source, as get_cell_indices finds it (CartesianDensityGrid.cpp:152-161) */
+  ctx->h_src_cell.assign(n, 0u);
+  bool hot_ok = (n <= HOT_MAX_SOURCES);
+  for (int i = 0; i < n && hot_ok; ++i) {
+    uint32_t packed = 0;
+    for (int d = 0; d < 3; ++d) {
+      const double v = (positions[3 * i + d] - ctx->geom.anchor[d]) * ctx->geom.inv_cellside[d];
+      const long long idx = (v != v) ? -1 : (long long)v;
+      if (idx < 0 || idx >= ctx->geom.ncell[d] || idx > 1022) hot_ok = false;
+      else packed |= (uint32_t)idx << (10 * d);
+    }
+    ctx->h_src_cell[i] = packed;
+  }
+  if (const char *e = getenv("CMIB_HOT_REPLICAS")) ctx->hot_replicas = atoi(e); else ctx->hot_replicas = 64;
+  if (!hot_ok || ctx->geom.periodic[0] || ctx->geom.periodic[1] || ctx->geom.periodic[2]) ctx->hot_replicas = 0;
+  if (ctx->hot_replicas > 0) {
+    CUDA_OK(ctx->d_src_cell.upload(ctx->h_src_cell.data(), (size_t)n, ctx->stream));
+    const size_t nd = (size_t)ctx->hot_replicas * HOT_MAX_SOURCES * HOT_CELLS * HOT_STRIDE;
+    if (ctx->hot_acc.n != nd) {
+      CUDA_OK(ctx->hot_acc.resize(nd));
+      CUDA_OK(cudaMemsetAsync(ctx->hot_acc.p, 0, nd * sizeof(double), ctx->stream));
+    }
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  }
   ctx->src.n_sources = n;
   ctx->src.src_pos = ctx->d_src_pos.p;
   ctx->src.src_cum = ctx->d_src_cum.p;
@@ -683,6 +727,10 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
     P.acc = ctx->acc.p;
     P.honly_cell_stride = ctx->honly_cell_stride();
     P.honly_term_stride = ctx->honly_term_stride();
+    P.honly_offset = ctx->honly_offset();
+    P.hot_acc = ctx->hot_acc.p;
+    P.src_cell = ctx->d_src_cell.p;
+    P.hot_replicas = ctx->hot_replicas;
     P.nu_H = ctx->nu_H;
     P.nu_He = ctx->nu_He;
     P.seed = seed;
@@ -729,6 +777,7 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   P.acc = ctx->acc.p;
   P.honly_cell_stride = ctx->honly_cell_stride();
   P.honly_term_stride = ctx->honly_term_stride();
+  P.honly_offset = ctx->honly_offset();
   P.luminosity = ctx->luminosity;
   P.totweight = totweight;
   for (int k = 0; k < NUM_ELEMENTS; ++k) P.abund[k] = ctx->abund[k];
@@ -799,11 +848,20 @@ int cmib_shoot_timing(cmib_context *ctx, double *prepare_ms, double *march_ms, u
 int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions) {
   CHECK_CTX(ctx);
   if (ensure_acc(ctx)) return 1;
-  double c[8];
-  CUDA_OK(cudaMemcpyAsync(c, ctx->acc.p, 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  double c[ACC_COUNTERS];
+  CUDA_OK(cudaMemcpyAsync(c, ctx->acc.p, ACC_COUNTERS * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_OK(cudaStreamSynchronize(ctx->stream));
   if (cell_crossings) *cell_crossings = c[5];
   if (emissions) *emissions = c[6];
+  return 0;
+}
+
+int cmib_shoot_optical_depth(cmib_context *ctx, double *tau_traversed) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  if (!tau_traversed) CMIB_FAIL("null argument");
+  CUDA_OK(cudaMemcpyAsync(tau_traversed, ctx->acc.p + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

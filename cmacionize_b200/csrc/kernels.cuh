@@ -45,17 +45,17 @@ shoot_kernel(const __grid_constant__ ShootParams P) {
   const uint32_t n_steps = cnt.n_steps, n_emit = cnt.n_emit;
 
   /* IonizationPhotonShootJobMarket::update_counters: block reduce, one RED per block */
-  __shared__ double red[7][8];
+  __shared__ double red[9][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[7] = {w_tot, w_type[0], w_type[1], w_type[2], w_type[3], (double)n_steps, (double)n_emit};
+  double v[9] = {w_tot, w_type[0], w_type[1], w_type[2], w_type[3], (double)n_steps, (double)n_emit, 0., cnt.tau_sum};
 #pragma unroll
-  for (int k = 0; k < 7; ++k) {
+  for (int k = 0; k < 9; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) red[k][warp] = v[k];
   }
   __syncthreads();
-  if (threadIdx.x < 7) {
+  if (threadIdx.x < 9) {
     double sum = 0.;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[threadIdx.x][w];
     if (sum != 0.) atomicAdd(P.acc + threadIdx.x, sum);
@@ -140,7 +140,7 @@ struct UpdateParams {
   double *heat_norm;     /* [ncell][2] */
   const double *cr_factor; /* [ncell] or NULL */
   const double *acc;
-  int64_t honly_cell_stride, honly_term_stride; /* H-only accumulator layout (shoot.cuh) */
+  int64_t honly_cell_stride, honly_term_stride, honly_offset; /* H-only accumulator layout (shoot.cuh) */
   double luminosity;
   double totweight;      /* <= 0: read acc[0] */
   double abund[NUM_ELEMENTS];
@@ -166,8 +166,8 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
   if (MODE == ACC_HONLY) {
 #pragma unroll
     for (int k = 0; k < NUM_IONS; ++k) J[k] = 0.;
-    J[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride];
-    heat[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride + P.honly_term_stride];
+    J[0] = P.acc[ACC_COUNTERS + P.honly_offset + i * P.honly_cell_stride];
+    heat[0] = P.acc[ACC_COUNTERS + P.honly_offset + i * P.honly_cell_stride + P.honly_term_stride];
     heat[1] = 0.;
   } else {
 #pragma unroll
@@ -256,8 +256,8 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
         if (MODE == ACC_HONLY) {
 #pragma unroll
           for (int k = 0; k < NUM_IONS; ++k) J[k] = 0.;
-          J[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride];
-          heat[0] = P.acc[ACC_COUNTERS + i * P.honly_cell_stride + P.honly_term_stride];
+          J[0] = P.acc[ACC_COUNTERS + P.honly_offset + i * P.honly_cell_stride];
+          heat[0] = P.acc[ACC_COUNTERS + P.honly_offset + i * P.honly_cell_stride + P.honly_term_stride];
           heat[1] = 0.;
         } else {
           const double *a = P.acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
@@ -348,14 +348,14 @@ __global__ void unpack_cells_kernel(int64_t ncell, const CellOpacity *cells, con
 /* accumulators -> reference SoA view J[14][ncell], heat[2][ncell] */
 template <int MODE>
 __global__ void unpack_acc_kernel(int64_t ncell, const double *acc, int64_t honly_cell_stride,
-                                  int64_t honly_term_stride, double *J, double *heat) {
+                                  int64_t honly_term_stride, int64_t honly_offset, double *J, double *heat) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ncell) return;
   const double *a = acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
   if (MODE == ACC_HONLY) {
     for (int k = 1; k < NUM_IONS; ++k) J[k * ncell + i] = 0.;
-    J[i] = acc[ACC_COUNTERS + i * honly_cell_stride];
-    heat[i] = acc[ACC_COUNTERS + i * honly_cell_stride + honly_term_stride];
+    J[i] = acc[ACC_COUNTERS + honly_offset + i * honly_cell_stride];
+    heat[i] = acc[ACC_COUNTERS + honly_offset + i * honly_cell_stride + honly_term_stride];
     heat[ncell + i] = 0.;
   } else {
     for (int k = 0; k < NUM_IONS; ++k) J[k * ncell + i] = a[k];

@@ -29,7 +29,10 @@
 namespace cmib {
 
 enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
-constexpr int ACC_COUNTERS = 8; /* totweight, typecount[4], cell crossings, (re)emissions, accumulator adds */
+/* leading counters: totweight, typecount[4], cell crossings, (re)emissions, accumulator adds,
+ * optical depth traversed, 7 spare.  16 doubles = 128 B so that the per-cell records that follow
+ * are aligned to L2 lines (with 8 counters every cell's 16 accumulators straddled two lines) */
+constexpr int ACC_COUNTERS = 16;
 
 template <int MODE> struct AccLayout;
 template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
@@ -42,11 +45,18 @@ struct ShootParams {
   const double2 *cells_h;    /* compact (n, x_H) copy for the H-only walk: 16 B instead of 32 B per gather */
   const double *reemit_prob; /* [ncell][5] (REEMISSION_PHYSICAL) */
   double *acc;               /* counters + per-cell accumulators */
-  /* H-only layout: term k of cell c lives at acc[8 + c*honly_cell_stride + k*honly_term_stride]:
+  /* H-only layout: term k of cell c lives at
+   * acc[ACC_COUNTERS + honly_offset + c*honly_cell_stride + k*honly_term_stride]:
    * interleaved (2, 1) while the grid is L2 resident (spreads hot cells over more sectors),
    * planar (1, ncells) when it is not (halves the footprint a threshold source touches) */
-  int64_t honly_cell_stride, honly_term_stride;
+  int64_t honly_cell_stride, honly_term_stride, honly_offset;
   double nu_H, nu_He;        /* 13.6 eV, 24.6 eV in Hz (DensityGrid.hpp:219-222) */
+  /* hot-cell replication (wavefront path): the 3x3x3 cells around every source receive the first
+   * crossings of ALL its packets; their accumulators are replicated hot_replicas times
+   * (hot_acc[replica][source][27][16]) and folded into acc at the end of the shoot */
+  double *hot_acc;
+  const uint32_t *src_cell; /* packed cell indices of the sources: ix | iy << 10 | iz << 20 */
+  int hot_replicas;         /* 0: off */
   uint64_t seed;
   uint32_t iteration;
   uint64_t packet_offset;
@@ -59,6 +69,7 @@ struct ShootCounters {
   double w_type[NUM_PACKET_TYPES] = {0., 0., 0., 0.};
   uint32_t n_steps = 0, n_emit = 0; /* cell crossings, (re)emissions */
   uint32_t n_red = 0;               /* accumulator terms added (wavefront path only) */
+  double tau_sum = 0.;              /* optical depth traversed: sum of tau_cell over all crossings */
 };
 
 /* update_integrals (DensityGrid.hpp:150-197): zero increments are skipped, which
@@ -66,7 +77,8 @@ struct ShootCounters {
 /* address of accumulator term k (FULL: 0..13 J, 14 heat_H, 15 heat_He; HONLY: 0 J_H, 1 heat_H) */
 template <int MODE>
 CMIB_HD double *acc_term(const ShootParams &P, int64_t cell, int k) {
-  if (MODE == ACC_HONLY) return P.acc + ACC_COUNTERS + cell * P.honly_cell_stride + (int64_t)k * P.honly_term_stride;
+  if (MODE == ACC_HONLY)
+    return P.acc + ACC_COUNTERS + P.honly_offset + cell * P.honly_cell_stride + (int64_t)k * P.honly_term_stride;
   return P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + k;
 }
 
@@ -141,6 +153,7 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
     s.iy_ = 1. / s.dy;
     s.iz_ = 1. / s.dz;
     s.tau = -log(rng_uniform(rng));
+    const double tau0 = s.tau;
     march_locate(g, s);
     const double dnu_H = nu - P.nu_H;
     const double dnu_He = nu - P.nu_He;
@@ -154,6 +167,8 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
       if (c.n > 0.) accumulate<MODE>(add, P, cell, ds, weight, sigma, dnu_H, dnu_He);
       ++cnt.n_steps;
     }
+    /* optical depth traversed by this walk: all of it when absorbed, the used part when it left */
+    cnt.tau_sum += tau0 - ((s.tau > 0.) ? s.tau : 0.);
     if (!inside) break; /* left the box: keeps its last type */
     /* --- PhotonSource::reemit --- */
     double new_nu = 0.;

@@ -154,7 +154,18 @@ __global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_
     order[atomicAdd(&hist[key[i]], 1u)] = (uint32_t)i;
 }
 
-CMIB_D uint64_t pack_meta(uint32_t ndraw, int type) { return ((uint64_t)(uint32_t)type << 32) | ndraw; }
+/* meta word of a queue entry: uniforms consumed (32 bits) | packet type (8 bits) | source index + 1
+ * of a primary, 0 for a re-emitted packet (24 bits) */
+CMIB_D uint64_t pack_meta(uint32_t ndraw, int type, int isrc = -1) {
+  return ((uint64_t)(uint32_t)(isrc + 1) << 40) | ((uint64_t)(uint32_t)(type & 0xff) << 32) | ndraw;
+}
+CMIB_D int meta_type(uint64_t meta) { return (int)((meta >> 32) & 0xffu); }
+CMIB_D int meta_source(uint64_t meta) { return (int)(meta >> 40) - 1; }
+
+constexpr int HOT_CELLS = 27;      /* 3 x 3 x 3 neighbourhood of a source cell */
+constexpr int HOT_STRIDE = 16;     /* doubles per replicated cell record (one 128-B line) */
+constexpr int HOT_CROSSINGS = 3;   /* crossings after emission that may still be in the neighbourhood */
+constexpr int HOT_MAX_SOURCES = 64;
 
 /* number of uniforms consumed so far */
 CMIB_D uint32_t rng_save(const PacketRng &r) { return 2u * r.block - r.have; }
@@ -169,20 +180,20 @@ CMIB_D void rng_restore(PacketRng &r, uint64_t seed, uint32_t iteration, uint64_
   }
 }
 
-/* block-wide sum of per-thread counters into the 8 leading doubles of acc */
+/* block-wide sum of per-thread counters into the 9 leading doubles of acc */
 CMIB_D void reduce_counters(double *acc, const ShootCounters &cnt) {
-  __shared__ double red[8][32];
+  __shared__ double red[9][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double v[8] = {cnt.w_tot, cnt.w_type[0], cnt.w_type[1], cnt.w_type[2], cnt.w_type[3],
-                 (double)cnt.n_steps, (double)cnt.n_emit, (double)cnt.n_red};
+  double v[9] = {cnt.w_tot, cnt.w_type[0], cnt.w_type[1], cnt.w_type[2], cnt.w_type[3],
+                 (double)cnt.n_steps, (double)cnt.n_emit, (double)cnt.n_red, cnt.tau_sum};
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < 9; ++k) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
     if (lane == 0) red[k][warp] = v[k];
   }
   __syncthreads();
-  if (threadIdx.x < 8) {
+  if (threadIdx.x < 9) {
     double sum = 0.;
     for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) sum += red[threadIdx.x][w];
     if (sum != 0.) atomicAdd(acc + threadIdx.x, sum);
@@ -226,7 +237,7 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
       id = (uint64_t)__double_as_longlong(W.rq[RQ_ID * cap + w]);
       const uint64_t meta = (uint64_t)__double_as_longlong(W.rq[RQ_META * cap + w]);
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
-      type = (int)(meta >> 32);
+      type = meta_type(meta);
       if (m.reemission_kind == REEMISSION_PHYSICAL) {
         const CellOpacity c = load_cell(P.cells, cell);
         double p[NUM_REEMIT];
@@ -306,7 +317,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       id = (uint64_t)__double_as_longlong(W.eq[EQ_ID * cap + w]);
       const uint64_t meta = (uint64_t)__double_as_longlong(W.eq[EQ_META * cap + w]);
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
-      type = (int)(meta >> 32);
+      type = meta_type(meta);
     } else {
       id = P.packet_offset + next_fresh + (w - n_eq);
       rng_init(rng, P.seed, P.iteration, id);
@@ -333,7 +344,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     q[MQ_DX * cap] = dx; q[MQ_DY * cap] = dy; q[MQ_DZ * cap] = dz;
     q[MQ_NU * cap] = nu; q[MQ_TAU * cap] = tau;
     q[MQ_ID * cap] = __longlong_as_double((long long)id);
-    q[MQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type));
+    q[MQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type, isrc_key));
 #pragma unroll
     for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
     if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
@@ -367,6 +378,30 @@ __global__ void advance_after_prepare_kernel(unsigned long long *ctl, uint64_t c
 
 __global__ void advance_after_march_kernel(unsigned long long *ctl) { ctl[CTL_QCOUNT] = 0; }
 
+/* fold the hot-cell replicas into the accumulators and clear them (one thread per
+ * (source, neighbour cell, term); the replicas of one record are summed in a fixed order) */
+template <int MODE>
+__global__ void fold_hot_cells_kernel(const __grid_constant__ ShootParams P) {
+  const int n = P.src.n_sources * HOT_CELLS * HOT_STRIDE;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int k = t % HOT_STRIDE, nb = (t / HOT_STRIDE) % HOT_CELLS, isrc = t / (HOT_STRIDE * HOT_CELLS);
+  double sum = 0.;
+  for (int r = 0; r < P.hot_replicas; ++r) {
+    double *p = P.hot_acc + (((size_t)r * HOT_MAX_SOURCES + isrc) * HOT_CELLS + nb) * HOT_STRIDE + k;
+    sum += *p;
+    *p = 0.;
+  }
+  if (sum == 0.) return;
+  const uint32_t sc = P.src_cell[isrc];
+  const int ix = (int)(sc & 1023u) + nb / 9 - 1, iy = (int)((sc >> 10) & 1023u) + (nb / 3) % 3 - 1,
+            iz = (int)((sc >> 20) & 1023u) + nb % 3 - 1;
+  /* a neighbour outside the grid never received anything (the walk only visits cells inside) */
+  const int64_t cell = long_index(P.geom, ix, iy, iz);
+  if (MODE == ACC_FULL) atomicAdd(P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + k, sum);
+  else atomicAdd(acc_term<MODE>(P, cell, k), sum); /* k is 0 (J_H) or 1 (heat_H) here */
+}
+
 /* ------------------------------------------------------------------------- */
 /* march: persistent warp state machine over the march queue                  */
 /* ------------------------------------------------------------------------- */
@@ -397,6 +432,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   /* per-lane packet constants that are only touched once per packet or per accumulation */
   __shared__ double s_sig[(NMETAL > 0 ? NMETAL + 1 : 1)][MARCH_BLOCK]; /* metals, then sigma_He */
   __shared__ unsigned long long s_id[MARCH_BLOCK], s_meta[MARCH_BLOCK];
+  __shared__ double s_tau0[MARCH_BLOCK]; /* sampled optical depth, for the traversed-depth checksum */
   const ShootParams &P = W.sp;
   const GridGeom &g = P.geom;
   const uint64_t cap = W.capacity;
@@ -418,8 +454,11 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   int32_t ix = 0, iy = 0, iz = 0;
   uint32_t cell = 0;
   uint32_t mask = 0; /* metals (bits 2..13) with a non-zero cross section */
+  uint32_t hot = 0;  /* (hot record index of the packet's source + 1) << 2 | crossings made (saturating) */
+  uint32_t hot_cell = 0; /* packed cell indices of that source */
   uint32_t nacc = 0; /* accumulator terms this packet adds per crossing (diagnostic for the roofline) */
   uint32_t n_red = 0;
+  double tau_sum = 0.; /* optical depth traversed (checksum against sum_cells n (x_H J_H + A_He x_He J_He)) */
   int state = LANE_EMPTY;
   bool warp_has_zero_dir = false; /* some lane's direction has a zero component (warp-uniform) */
   uint64_t cur = 0, end = 0;      /* warp-uniform cursor into the claimed chunk */
@@ -490,8 +529,10 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         }
         if (!can_reemit) ++n_type[PACKET_ABSORBED]; /* PhotonSource::reemit without a handler (:304-306) */
       } else if (state == LANE_ESCAPED) {
-        ++n_type[(int)(s_meta[tid] >> 32)]; /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
+        ++n_type[meta_type(s_meta[tid])]; /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
       }
+      /* optical depth traversed by the walk that just ended: all of it when absorbed */
+      if (state == LANE_ABSORBED || state == LANE_ESCAPED) tau_sum += s_tau0[tid] - ((tau > 0.) ? tau : 0.);
       if (can_reemit) {
         const unsigned ab = __ballot_sync(0xffffffffu, state == LANE_ABSORBED);
         if (ab) {
@@ -506,7 +547,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             q[RQ_SIGHE * cap] = (MODE == ACC_FULL) ? s_sig[NMETAL][tid] : 0.;
             q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
             q[RQ_ID * cap] = __longlong_as_double((long long)s_id[tid]);
-            q[RQ_META * cap] = __longlong_as_double((long long)s_meta[tid]);
+            q[RQ_META * cap] = __longlong_as_double((long long)(s_meta[tid] & 0xffffffffffull));
           }
         }
       }
@@ -535,8 +576,17 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
             const double nu = q[MQ_NU * cap];
             tau = q[MQ_TAU * cap];
+            s_tau0[tid] = tau;
             s_id[tid] = (unsigned long long)__double_as_longlong(q[MQ_ID * cap]);
             s_meta[tid] = (unsigned long long)__double_as_longlong(q[MQ_META * cap]);
+            hot = 0;
+            if (P.hot_replicas > 0) {
+              const int isrc = meta_source(s_meta[tid]);
+              if (isrc >= 0) {
+                hot = (uint32_t)(isrc + 1) << 2;
+                hot_cell = P.src_cell[isrc];
+              }
+            }
             sigH = q[MQ_SIGMA * cap];
             mask = 0;
             if (MODE == ACC_FULL) {
@@ -619,12 +669,27 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           /* update_integrals (DensityGrid.hpp:150-197); zero increments are skipped (exact) */
           n_red += nacc;
           const double dsw = ds * weight;
-          double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
+          /* accumulator record of this cell: its own, or — during the first crossings of a
+           * primary, inside the 3x3x3 cells around its source — one of the replicas */
+          double *a = (MODE == ACC_FULL) ? P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC
+                                         : acc_term<MODE>(P, cell, 0);
+          int64_t ts = (MODE == ACC_FULL) ? 1 : P.honly_term_stride; /* stride between terms */
+          if (hot != 0u && (hot & 3u) < (uint32_t)HOT_CROSSINGS) {
+            const int ddx = ix - (int)(hot_cell & 1023u), ddy = iy - (int)((hot_cell >> 10) & 1023u),
+                      ddz = iz - (int)((hot_cell >> 20) & 1023u);
+            if ((unsigned)(ddx + 1) < 3u && (unsigned)(ddy + 1) < 3u && (unsigned)(ddz + 1) < 3u) {
+              const size_t rec = ((size_t)(blockIdx.x % P.hot_replicas) * HOT_MAX_SOURCES + ((hot >> 2) - 1u)) * HOT_CELLS +
+                                 (size_t)((ddx + 1) * 9 + (ddy + 1) * 3 + (ddz + 1));
+              a = P.hot_acc + rec * HOT_STRIDE;
+              ts = 1;
+            }
+            ++hot;
+          }
           const double dJH = dsw * sigH;
           if (dJH != 0.) {
-            atomicAdd(acc_term<MODE>(P, cell, ION_H_n), dJH);
+            atomicAdd(a + ION_H_n, dJH);
             const double dh = dJH * dnu_H;
-            if (dh != 0.) atomicAdd(acc_term<MODE>(P, cell, MODE == ACC_FULL ? NUM_IONS + HEAT_H : 1), dh);
+            if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : ts), dh);
           }
           if (MODE == ACC_FULL) {
             const double dJHe = dsw * s_sig[NMETAL][tid];
@@ -673,6 +738,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   ShootCounters cnt;
   cnt.n_steps = n_steps;
   cnt.n_red = n_red;
+  cnt.tau_sum = tau_sum;
 #pragma unroll
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) {
     cnt.w_type[t] = (double)n_type[t] * weight;

@@ -150,6 +150,11 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight);
  * packet-cell crossings (the unit of work of the roofline) and of
  * (re-)emissions.  No reference counterpart (gprof call counts were used there). */
 int cmib_shoot_statistics(cmib_context *ctx, double *cell_crossings, double *emissions);
+/* optical depth traversed by all packets since the last reset: sum over crossings of
+ * ds n (sigma_H x_H + A_He sigma_He x_He) (the shortened last crossing counts what was left).
+ * Checksum for the accumulation at any problem size: it must equal
+ * sum_cells n (x_H J_H + A_He x_He J_He) of the raw accumulators (unit packet weights). */
+int cmib_shoot_optical_depth(cmib_context *ctx, double *tau_traversed);
 
 /* per-kernel device times of the LAST cmib_shoot (CUDA events on the context's stream; enable with
  * cmib_set_shoot_timing before the shoot): summed prepare / march kernel milliseconds, number of
@@ -166,9 +171,9 @@ int cmib_set_shoot_algorithm(cmib_context *ctx, int algorithm);
 
 /* ---- multi-GPU plumbing ------------------------------------------------ */
 /* Device pointer + length (in doubles) of the contiguous buffer that must be
- * sum-all-reduced between cmib_shoot and cmib_update_state: 8 counters
- * (totweight, typecount[4], cell crossings, emissions, padding) followed by the
- * per-cell accumulators.
+ * sum-all-reduced between cmib_shoot and cmib_update_state: 16 counters
+ * (totweight, typecount[4], cell crossings, emissions, accumulator adds, optical depth
+ * traversed, padding to one 128-byte line) followed by the per-cell accumulators.
  * Replaces the 16 chunked MPI_Allreduce calls + 2 counter reductions of
  * src/IonizationSimulation.cpp:410-416,458-529 with ONE collective. */
 int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_doubles);

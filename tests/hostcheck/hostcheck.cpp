@@ -297,6 +297,10 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   P.acc = acc;
   P.honly_cell_stride = 2;
   P.honly_term_stride = 1;
+  P.honly_offset = 0;
+  P.hot_acc = nullptr;
+  P.src_cell = nullptr;
+  P.hot_replicas = 0;
   P.nu_H = (13.6 * ELECTRONVOLT) * (1. / PLANCK);
   P.nu_He = (24.6 * ELECTRONVOLT) * (1. / PLANCK);
   P.seed = seed;
@@ -314,6 +318,7 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) acc[1 + t] += cnt.w_type[t];
   acc[5] += cnt.n_steps;
   acc[6] += cnt.n_emit;
+  acc[8] += cnt.tau_sum;
 }
 
 } /* extern "C" */

@@ -30,7 +30,7 @@ def _shoot(lib_path, lo, cnt):
     rng = np.random.default_rng(3)
     cells = np.ascontiguousarray(np.stack([np.full(ncells, 1e8), np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), ncells)),
                                            np.full(ncells, 1e-6), np.full(ncells, 8000.)], 1))
-    acc = np.zeros(8 + ncells * 2)
+    acc = np.zeros(16 + ncells * 2)
     anchor = np.array([-5 * PC] * 3); sides = np.array([10 * PC] * 3)
     ncell = np.array([NC] * 3, np.int32); per = np.zeros(3, np.int32)
     ip = np.array([2, 0, 0, 2, 1], np.int32)          # 2 sources, mono, FixedValue, FixedValue re-emission, H-only
@@ -73,5 +73,6 @@ def test_two_rank_shoot_equals_single_rank(hostcheck, cmib, tmp_path):
     both = np.load(out)
     assert np.array_equal(both[:7], single[:7])          # weights by type, crossings, emissions: exact
     assert both[0] == NPK and both[6] > 1.05 * NPK       # re-emission happened
-    scale = np.abs(single[8:]).max()
-    assert np.abs(both[8:] - single[8:]).max() <= 1e-12 * scale
+    scale = np.abs(single[16:]).max()
+    assert np.abs(both[16:] - single[16:]).max() <= 1e-12 * scale
+    assert abs(both[8] - single[8]) <= 1e-12 * single[8]   # optical depth traversed

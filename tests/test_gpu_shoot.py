@@ -220,3 +220,45 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
             assert np.abs(J[k] - J0[k]).max() <= 1e-12 * max(J0[k].max(), 1e-300), k
         for k in range(2):
             assert np.abs(h[k] - h0[k]).max() <= 1e-12 * max(np.abs(h0[k]).max(), 1e-300), k
+
+
+@pytest.mark.parametrize("config", ["stromgren64_1e6", "lexingtonHII20_64_1e7"])
+def test_full_size_checksum_of_the_accumulation(cmib, config):
+    """BASELINE-size runs cannot be replayed by the CPU oracle in seconds; they are pinned through an
+    identity that holds for any grid and any number of packets: every crossing adds
+    ds w sigma_k to J_k of its cell and removes ds n (sigma_H x_H + A_He sigma_He x_He) from the
+    packet's optical depth, so with unit weights
+
+        sum_cells n (x_H J_H + A_He x_He J_He)  ==  optical depth traversed by all packets,
+
+    the right side being summed per packet inside the walk (cmib_shoot_optical_depth).  A lost or
+    mis-addressed atomic add breaks it (cells differ in n and x).  Plus packet conservation."""
+    from cmacionize_b200 import problems
+    if config == "stromgren64_1e6":
+        prob = problems.stromgren(ncell=64, n_packets=1_000_000)
+        A_He, npk, spin = 0., 1_000_000, 3
+    else:
+        prob = problems.lexington(20, ncell=64, n_packets=10_000_000)
+        A_He, npk, spin = 0.1, 10_000_000, 5
+    ctx = prob.ctx
+    for loop in range(spin):
+        problems.run_iteration(prob, loop, n_packets=1_000_000)
+    # make the cells pairwise different so that a mis-addressed add cannot cancel
+    n, T, x, _ = ctx.download_cells()
+    rng = np.random.default_rng(1)
+    n = n * rng.uniform(0.5, 1.5, n.size)
+    ctx.upload_cells(n, T, x)
+    ctx.reset_accumulators()
+    ctx.update_reemission_probabilities()
+    tw, tc = ctx.shoot(npk, seed=11, iteration=spin)
+    crossings, emissions = ctx.shoot_statistics()
+    tau = ctx.shoot_optical_depth()
+    J, heat = ctx.download_accumulators()
+    ctx.close()
+    assert tw == npk and tc.sum() == npk
+    assert emissions >= npk and crossings > 10 * npk
+    lhs = float(np.sum(n * (x[0] * J[0] + A_He * x[1] * J[1])))
+    assert abs(lhs - tau) <= 1e-9 * tau, (lhs, tau)
+    # mean optical depth per emission is ~1 for absorbed packets and < 1 for escaping ones
+    assert 0.05 < tau / emissions < 1.05
+    assert (J[0][n > 0] > 0).mean() > 0.2 and (heat[0] >= 0).all()

@@ -43,6 +43,7 @@ for loop in range(spin):
     problems.run_iteration(prob, loop, n_packets=int(args.spinup_packets))
 ctx.synchronize()
 ctx.set_shoot_algorithm(args.algorithm)
+ctx.set_shoot_timing(True)
 cudart = ctypes.CDLL("libcudart.so")
 stream = torch.cuda.ExternalStream(ctx.stream())
 for rep in range(args.repeat):
@@ -61,5 +62,6 @@ for rep in range(args.repeat):
     cross, emis = ctx.shoot_statistics()
     ms = e0.elapsed_time(e1)
     print(f"{args.problem}: shoot of {n} packets: {ms:.3f} ms (host {1e3*(t1-t0):.3f} ms) -> {n/ms*1e3:.3e} packets/s, "
-          f"{cross/n:.2f} crossings/packet ({cross/ms*1e3:.3e} crossings/s), {emis/n:.3f} emissions/packet")
+          f"{cross/n:.2f} crossings/packet ({cross/ms*1e3:.3e} crossings/s), {emis/n:.3f} emissions/packet; "
+          f"prepare {ctx.shoot_timing()[0]:.3f} ms, march {ctx.shoot_timing()[1]:.3f} ms, rounds {ctx.shoot_timing()[2]}")
 ctx.close()
