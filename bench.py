@@ -352,7 +352,12 @@ def main():
     alg_bytes = (crossings / world) * bytes_per_step  # per rank per iteration
     achieved = alg_bytes / (march_ms * 1e-3) / 1e9
     red_rate = (red_ops / world) / (march_ms * 1e-3)
-    RED_PEAK = 1.878e11  # scattered FP64 RED/s measured on B200 (profiles/r01_microbench_red_gather.txt)
+    RED_PEAK = 1.878e11     # scattered FP64 RED/s measured on B200 (profiles/r01_microbench_red_gather.txt)
+    GATHER_PEAK = 1.747e11  # scattered 32-B gathers/s, L2-resident table (same file)
+    red_per_crossing = red_ops / max(crossings, 1.)
+    crossing_rate = (crossings / world) / (march_ms * 1e-3)
+    # one crossing = one scattered gather + red_per_crossing scattered REDs through the same L1TEX pipe
+    crossing_bound = 1. / (1. / GATHER_PEAK + red_per_crossing / RED_PEAK)
     roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
                 "traffic": 1.142e9, "traffic_note": "dram__bytes_read+write of the first (4 Mi packet) march launch of a "
@@ -366,8 +371,12 @@ def main():
                 "prepare_kernel_ms": prep_ms, "prepare_share_of_step": prep_ms / ms_per_step,
                 "shoot_ms": 1e3 * shoot_s,
                 "update_state_kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in update_ms])),
+                "l1tex": {"achieved": crossing_rate, "peak": crossing_bound, "unit": "cell crossings/s",
+                          "frac": crossing_rate / crossing_bound,
+                          "note": "bound = 1 / (1/gathers_per_s + REDs_per_crossing/REDs_per_s) from the measured "
+                                  "scattered-gather and scattered-RED rates of the part (tools/microbench/red_bench.cu)"},
                 "atomic": {"achieved": red_rate, "peak": RED_PEAK, "unit": "FP64 RED/s", "frac": red_rate / RED_PEAK,
-                           "red_per_crossing": red_ops / max(crossings, 1.),
+                           "red_per_crossing": red_per_crossing,
                            "note": "64^3 working set (8 MB cells + 34 MB accumulators) is L2 resident; ncu shows the "
                                    "binding unit is L1TEX (scattered gather + RED lanes, 88 % busy), so the meaningful "
                                    "denominator is the measured scattered-RED ceiling, not HBM"}}

@@ -168,7 +168,7 @@ def test_shoot_is_deterministic_and_shardable(cmib):
     ctx.close()
 
 
-@pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission"])
+@pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -185,9 +185,23 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
     elif config == "lexington":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
-    else:
+    elif config == "fixed_reemission":
         prob = problems.stromgren(ncell=16, n_packets=npk)
         prob.ctx.set_reemission(capi.REEMISSION_FIXED_VALUE, 0.364, problems.ev_to_hz(19.8))
+    else:
+        # non-cubic box, periodic in x and z, three sources (one outside the box: its packets
+        # are lost immediately, as in the reference), Physical re-emission
+        ctx = cmib.Context([-1e17, -2e17, -3e17], [2e17, 5e17, 3e17], [12, 20, 9], periodic=(True, False, True))
+        ctx.set_abundances(He=0.1)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_recombination_rates(capi.RECOMBINATION_VERNER)
+        ctx.set_sources([[0., 0., 0.], [0.9e17, 2.9e17, -2.9e17], [0., 9e17, 0.]], [0.5, 0.4, 0.1], 1e49)
+        ctx.set_spectrum(capi.SPECTRUM_PLANCK, 30000.)
+        ctx.set_reemission(capi.REEMISSION_PHYSICAL)
+        nc = ctx.ncells
+        prob = problems.Problem("periodic", ctx, np.full(nc, 3e8), np.full(nc, 8000.), problems.initial_fractions(nc),
+                                npk, 1)
+        prob.upload()
     ctx = prob.ctx
     rng = np.random.default_rng(17)
     x = prob.ionic_fractions.copy()
@@ -212,6 +226,8 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     ctx.close()
     tw0, tc0, st0, J0, h0 = results[0]
     assert tw0 == npk and tc0.sum() == npk
+    if config == "periodic":
+        assert 0.05 * npk < tc0[0] < 0.5 * npk   # the 10 % emitted outside + escapes through the y faces
     if config != "stromgren":
         assert st0[1] > 1.05 * npk  # re-emission happened
     for tw, tc, st, J, h in results[1:]:
