@@ -110,8 +110,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, period: float = 0.2):
         self.device = device
+        self.period = float(os.environ.get("BENCH_CLOCK_PERIOD", period))
         self.rows = []
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -124,7 +125,7 @@ class ClockSampler:
                 self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(self.period)
 
     def __enter__(self):
         self._t.start()
