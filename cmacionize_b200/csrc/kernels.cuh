@@ -203,17 +203,32 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
 }
 
 /*
- * Temperature update with dynamic cell hand-out: every pass each lane that owns a cell evaluates
- * the heating/cooling balance ONCE (the state machine of state.cuh), lanes whose cell converged
- * store it and take the next unprocessed cell from a global counter.  With one thread bound to one
- * cell (update_state_kernel) a warp runs until its slowest cell has converged and cells that need
- * no solve (vacuum, no radiation) idle a lane for the whole time: ncu showed 17 of 32 lanes active
- * (profiles/r01_update_state.md).
+ * Temperature update: persistent warps, dynamic cell hand-out, THREE lanes per cell.
+ *
+ * A secant iteration of TemperatureCalculator::calculate_temperature evaluates the heating/cooling
+ * balance at 1.1 T0, 0.9 T0 and T0 (TemperatureCalculator.cpp:730-760): three independent
+ * evaluations of the same inputs.  A cell owns three adjacent lanes (10 cells per warp, lanes 30/31
+ * idle), lane role r evaluates temperature r, the six numbers of the secant update are exchanged
+ * with shuffles and all three lanes advance the same state.  Every pass is one balance evaluation
+ * for every lane that has a cell; a cell that converged is stored and its lanes take the next
+ * unprocessed cell from a global counter.
+ *
+ * Why: (1) with one thread bound to one cell (update_state_kernel) a warp runs until its slowest
+ * cell has converged and cells that need no solve idle a lane for the whole time — ncu: 17 of 32
+ * lanes active (profiles/r01_update_state.md); (2) a few cells at the ionisation front run the full
+ * 100 iterations; with three sequential evaluations per iteration they alone kept the kernel alive
+ * for ~20 ms after everything else had finished (profiles/r01_update_state.md) — their critical
+ * path is three times shorter here.  The arithmetic per cell is unchanged (bitwise equal to the
+ * per-cell kernel, tests/test_gpu_simulation.py).
  */
 template <int MODE>
-__global__ void __launch_bounds__(128) /* (128, 3) forces spills and measured slower: 10.4 vs 9.7 ms */
+__global__ void __launch_bounds__(128)
 update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long long *next_cell) {
   const int lane = threadIdx.x & 31;
+  const bool in_slot = lane < 30;
+  const int role = lane % 3;            /* 0: 1.1 T0, 1: 0.9 T0, 2: T0 */
+  const int slot_base = lane - role;    /* first lane of this cell's three */
+  const unsigned role0_mask = 0x09249249u; /* lanes 0, 3, ..., 27 */
   const int64_t ncells = P.geom.ncells;
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   const double jfac = (P.luminosity / totweight) / P.geom.cell_volume;
@@ -241,17 +256,18 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
   };
 
   while (true) {
-    /* ---- hand cells to idle lanes; cells that need no solve are finished on the spot ---- */
+    /* ---- hand cells to idle slots; cells that need no solve are finished on the spot ---- */
     for (int tries = 0; tries < 8; ++tries) {
-      const unsigned idle = __ballot_sync(0xffffffffu, !has);
+      const unsigned idle = __ballot_sync(0xffffffffu, in_slot && !has) & role0_mask; /* one bit per idle slot */
       if (idle == 0u || exhausted) break;
       unsigned long long base = 0;
       const int leader = __ffs(idle) - 1;
       if (lane == leader) base = atomicAdd(next_cell, (unsigned long long)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, leader);
       if (base + __popc(idle) >= (unsigned long long)ncells) exhausted = true;
-      const int64_t i = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
-      if (!has && i < ncells) {
+      const int64_t i = (int64_t)base + __popc(idle & ((1u << slot_base) - 1u));
+      if (in_slot && !has && i < ncells) {
+        /* the three lanes of the slot load the same cell and begin the same solve */
         double J[NUM_IONS], heat[NUM_HEAT], xprev[NUM_IONS];
         if (MODE == ACC_HONLY) {
 #pragma unroll
@@ -282,11 +298,11 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
             jH_zero = (J[ION_H_n] == 0.);
             jHe_zero = (J[ION_He_n] == 0.);
             has = true;
-          } else {
+          } else if (role == 2) {
             temperature_solve_finish(S, J, h, out);
             store(i, c.n);
           }
-        } else {
+        } else if (role == 2) {
           store(i, c.n);
         }
       }
@@ -295,20 +311,32 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
       if (exhausted) break;
       continue;
     }
-    /* ---- one balance evaluation for every lane that owns a cell ---- */
+    /* ---- one balance evaluation per lane: the slot's three temperatures side by side ---- */
+    double h0e = 0., he0e = 0., gain = 0., loss = 0.;
     if (has) {
-      double h0e, he0e, gain, loss;
-      cooling_heating_balance(h0e, he0e, gain, loss, temperature_solve_T(S), ntot, midz, j, P.abund, h,
-                              P.tp.pahfac, S.crfac, P.tp.crscale, P.rr, out.x);
-      if (temperature_solve_advance(S, h0e, he0e, gain, loss, P.tp)) {
-        /* temperature_solve_finish only looks at whether J_H / J_He are zero */
-        double Jz[NUM_IONS];
+      const double Te = (role == 0) ? 1.1 * S.T0 : ((role == 1) ? 0.9 * S.T0 : S.T0);
+      cooling_heating_balance(h0e, he0e, gain, loss, Te, ntot, midz, j, P.abund, h, P.tp.pahfac, S.crfac,
+                              P.tp.crscale, P.rr, out.x);
+    }
+    /* exchange within the slot (all lanes take part in the shuffles) */
+    const double gain1 = __shfl_sync(0xffffffffu, gain, slot_base), loss1 = __shfl_sync(0xffffffffu, loss, slot_base);
+    const double gain2 = __shfl_sync(0xffffffffu, gain, slot_base + 1), loss2 = __shfl_sync(0xffffffffu, loss, slot_base + 1);
+    const int l2 = in_slot ? slot_base + 2 : lane;
+    const double gain0 = __shfl_sync(0xffffffffu, gain, l2), loss0 = __shfl_sync(0xffffffffu, loss, l2);
+    const double h00 = __shfl_sync(0xffffffffu, h0e, l2), he00 = __shfl_sync(0xffffffffu, he0e, l2);
+    if (has) {
+      ++S.niter;
+      if (temperature_solve_update(S, gain1, loss1, gain2, loss2, h00, he00, gain0, loss0, P.tp)) {
+        if (role == 2) { /* this lane holds the fractions of the evaluation at T0, the last one of the reference */
+          /* temperature_solve_finish only looks at whether J_H / J_He are zero */
+          double Jz[NUM_IONS];
 #pragma unroll
-        for (int k = 0; k < NUM_IONS; ++k) Jz[k] = 1.;
-        if (jH_zero) Jz[ION_H_n] = 0.;
-        if (jHe_zero) Jz[ION_He_n] = 0.;
-        temperature_solve_finish(S, Jz, h, out);
-        store(cell, ntot);
+          for (int k = 0; k < NUM_IONS; ++k) Jz[k] = 1.;
+          if (jH_zero) Jz[ION_H_n] = 0.;
+          if (jHe_zero) Jz[ION_He_n] = 0.;
+          temperature_solve_finish(S, Jz, h, out);
+          store(cell, ntot);
+        }
         has = false;
       }
     }

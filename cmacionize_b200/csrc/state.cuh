@@ -388,27 +388,19 @@ CMIB_HD double temperature_solve_T(const TemperatureSolve &S) {
   return (S.phase == 0) ? 1.1 * S.T0 : ((S.phase == 1) ? 0.9 * S.T0 : S.T0);
 }
 
-/* record the balance just evaluated; after the third one do the secant update.  Returns true
- * when the solve has finished. */
-CMIB_HD bool temperature_solve_advance(TemperatureSolve &S, double h0e, double he0e, double gain,
-                                       double loss, const TemperatureParams &tp) {
-  if (S.phase == 0) {
-    ++S.niter;
-    S.gain1 = gain;
-    S.loss1 = loss;
-    S.phase = 1;
-    return false;
-  }
-  if (S.phase == 1) {
-    S.gain2 = gain;
-    S.loss2 = loss;
-    S.phase = 2;
-    return false;
-  }
+/* the secant update of one iteration from its three balances (1: at 1.1 T0, 2: at 0.9 T0, 0: at T0);
+ * returns true when the solve has finished */
+CMIB_HD bool temperature_solve_update(TemperatureSolve &S, double gain1, double loss1, double gain2,
+                                      double loss2, double h0e, double he0e, double gain0, double loss0,
+                                      const TemperatureParams &tp) {
+  S.gain1 = gain1;
+  S.loss1 = loss1;
+  S.gain2 = gain2;
+  S.loss2 = loss2;
   S.h0 = h0e;
   S.he0 = he0e;
-  S.gain0 = gain;
-  S.loss0 = loss;
+  S.gain0 = gain0;
+  S.loss0 = loss0;
   S.phase = 0;
   double expgain;
   if (S.gain2 > 0.) {
@@ -444,6 +436,26 @@ CMIB_HD bool temperature_solve_advance(TemperatureSolve &S, double h0e, double h
     S.loss0 = 1.;
   }
   return !temperature_solve_continues(S, tp);
+}
+
+/* record the balance just evaluated; after the third one do the secant update.  Returns true
+ * when the solve has finished. */
+CMIB_HD bool temperature_solve_advance(TemperatureSolve &S, double h0e, double he0e, double gain,
+                                       double loss, const TemperatureParams &tp) {
+  if (S.phase == 0) {
+    ++S.niter;
+    S.gain1 = gain;
+    S.loss1 = loss;
+    S.phase = 1;
+    return false;
+  }
+  if (S.phase == 1) {
+    S.gain2 = gain;
+    S.loss2 = loss;
+    S.phase = 2;
+    return false;
+  }
+  return temperature_solve_update(S, S.gain1, S.loss1, S.gain2, S.loss2, h0e, he0e, gain, loss, tp);
 }
 
 /* h = the normalised heating terms of temperature_solve_begin */
