@@ -128,6 +128,8 @@ struct cmib_context {
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2] = {0, 0};
+  int prep_blocks_per_sm[2] = {0, 0};
+  int decide_blocks_per_sm = 0;
   uint64_t shoot_rounds = 0;
   /* optional per-kernel timing of the shoot (CUDA events on the context's stream) */
   bool timing = false;
@@ -287,7 +289,15 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     if (ctx->sort_hist.n < W.nbins + 1) CUDA_OK(ctx->sort_hist.resize(W.nbins + 1));
     W.key = ctx->sort_key.p; W.order = ctx->sort_order.p; W.hist = ctx->sort_hist.p;
   }
-  const unsigned prep_grid = (unsigned)ctx->sm_count * 4;
+  /* persistent grids: exactly the CTAs that are resident at once (a partial second wave of a
+   * grid-stride kernel runs at a fraction of the machine) */
+  if (ctx->prep_blocks_per_sm[0] == 0) {
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prep_blocks_per_sm[ACC_FULL], prepare_kernel<ACC_FULL>, 256, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prep_blocks_per_sm[ACC_HONLY], prepare_kernel<ACC_HONLY>, 256, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->decide_blocks_per_sm, reemit_decide_kernel, 256, 0));
+  }
+  const unsigned prep_grid = (unsigned)(ctx->sm_count * (ctx->prep_blocks_per_sm[mode] > 0 ? ctx->prep_blocks_per_sm[mode] : 1));
+  const unsigned decide_grid = (unsigned)(ctx->sm_count * (ctx->decide_blocks_per_sm > 0 ? ctx->decide_blocks_per_sm : 1));
   int bpm = ctx->march_blocks_per_sm[mode];
   if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e);
   if (bpm < 1) bpm = 1;
@@ -311,7 +321,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     for (int k = 0; k < group; ++k, ++round) {
       stamp();
       if (P.src.reemission_kind != REEMISSION_NONE && round > 0) {
-        reemit_decide_kernel<<<prep_grid, 256, 0, s>>>(W);
+        reemit_decide_kernel<<<decide_grid, 256, 0, s>>>(W);
         ++g_launches;
       }
       if (mode == ACC_HONLY) prepare_kernel<ACC_HONLY><<<prep_grid, 256, 0, s>>>(W);

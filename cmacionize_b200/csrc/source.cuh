@@ -96,12 +96,29 @@ CMIB_HD double planck_frequency(const double *tab, PacketRng &rng) {
   return pow(10., lf) * 3.288465385e15;
 }
 
+/* Utilities::locate on two arrays of the same length at once: the two bisections are independent,
+ * running them in lock step puts their (L2-latency bound) loads in flight together */
+CMIB_HD void locate2(double x, const double *a, const double *b, uint32_t length, uint32_t &ja, uint32_t &jb) {
+  uint32_t la = 0, ua = length, lb = 0, ub = length;
+  while (ua - la > 1 || ub - lb > 1) {
+    const uint32_t ma = (ua + la) >> 1, mb = (ub + lb) >> 1;
+    const double va = a[ma], vb = b[mb];
+    if (ua - la > 1) { if (x > va) la = ma; else ua = ma; }
+    if (ub - lb > 1) { if (x > vb) lb = mb; else ub = mb; }
+  }
+  if (la == length - 1) --la;
+  if (lb == length - 1) --lb;
+  ja = la;
+  jb = lb;
+}
+
 CMIB_HD double lyc_frequency(const double *freq, const double *temp, const double *cdf, double T,
                              PacketRng &rng) {
   const uint32_t iT = locate(T, temp, LYC_NUMTEMP);
   const double x = rng_uniform(rng);
-  const uint32_t inu1 = locate(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ);
-  const uint32_t inu2 = locate(x, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ);
+  uint32_t inu1, inu2;
+  locate2(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ,
+          inu1, inu2);
   return freq[inu1] + (T - temp[iT]) * (freq[inu2] - freq[inu1]) / (temp[iT + 1] - temp[iT]);
 }
 
