@@ -105,6 +105,7 @@ struct cmib_context {
   RecombinationModel rr;
   TemperatureParams tp;
   double luminosity = 0.;
+  DevBuf<uint16_t> d_planck_guide, d_hlyc_guide, d_helyc_guide, d_he2pc_guide;
   DevBuf<double> d_src_pos, d_src_cum, d_planck, d_hlyc_freq, d_hlyc_temp, d_hlyc_cdf, d_helyc_freq,
       d_helyc_temp, d_helyc_cdf, d_he2pc_freq, d_he2pc_cdf;
   std::vector<double> h_planck, h_hlyc_freq, h_hlyc_temp, h_hlyc_cdf, h_helyc_freq, h_helyc_temp,
@@ -180,6 +181,33 @@ int ensure_acc(cmib_context *ctx) {
     CUDA_OK(ctx->acc.resize(want));
     CUDA_OK(cudaMemsetAsync(ctx->acc.p, 0, want * sizeof(double), ctx->stream));
   }
+  return 0;
+}
+
+/* build the bracket guides of `rows` CDF rows, check on the host that the guided search returns
+ * exactly what Utilities::locate returns, upload */
+int make_guides(cmib_context *ctx, const double *cdf, int rows, DevBuf<uint16_t> &dev, const uint16_t **out) {
+  std::vector<uint16_t> g((size_t)rows * (GUIDE_N + 1));
+  for (int r = 0; r < rows; ++r)
+    host::build_guide(cdf + (size_t)r * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ, GUIDE_N, g.data() + (size_t)r * (GUIDE_N + 1));
+  for (int r = 0; r < rows; ++r) {
+    const double *row = cdf + (size_t)r * SPECTRUM_NUMFREQ;
+    const uint16_t *gr = g.data() + (size_t)r * (GUIDE_N + 1);
+    for (int k = 0; k <= 4096; ++k) {
+      const double x = (k + 0.37) / 4097.;
+      if (locate_guided(x, row, SPECTRUM_NUMFREQ, gr) != locate(x, row, SPECTRUM_NUMFREQ))
+        CMIB_FAIL("internal error: guided CDF search disagrees with bisection (row %d, x %g)", r, x);
+    }
+    for (int j = 0; j < SPECTRUM_NUMFREQ; ++j) { /* exactly on the table values, and one ulp around them */
+      const double xs[3] = {row[j], nextafter(row[j], 0.), nextafter(row[j], 2.)};
+      for (double x : xs)
+        if (x >= 0. && x <= 1. && locate_guided(x, row, SPECTRUM_NUMFREQ, gr) != locate(x, row, SPECTRUM_NUMFREQ))
+          CMIB_FAIL("internal error: guided CDF search disagrees with bisection (row %d, entry %d)", r, j);
+    }
+  }
+  CUDA_OK(dev.upload(g.data(), g.size(), ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  *out = dev.p;
   return 0;
 }
 
@@ -637,6 +665,7 @@ int cmib_set_spectrum(cmib_context *ctx, int kind, double param) {
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     ctx->src.spectrum_kind = SPECTRUM_PLANCK;
     ctx->src.planck = ctx->d_planck.p;
+    if (make_guides(ctx, ctx->h_planck.data(), 1, ctx->d_planck_guide, &ctx->src.planck_guide)) return 1;
   } else {
     CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", kind);
   }
@@ -678,6 +707,9 @@ int cmib_set_reemission(cmib_context *ctx, int kind, double probability, double 
     ctx->src.helyc_cdf = ctx->d_helyc_cdf.p;
     ctx->src.he2pc_freq = ctx->d_he2pc_freq.p;
     ctx->src.he2pc_cdf = ctx->d_he2pc_cdf.p;
+    if (make_guides(ctx, ctx->h_hlyc_cdf.data(), LYC_NUMTEMP, ctx->d_hlyc_guide, &ctx->src.hlyc_guide)) return 1;
+    if (make_guides(ctx, ctx->h_helyc_cdf.data(), LYC_NUMTEMP, ctx->d_helyc_guide, &ctx->src.helyc_guide)) return 1;
+    if (make_guides(ctx, ctx->h_he2pc_cdf.data(), 1, ctx->d_he2pc_guide, &ctx->src.he2pc_guide)) return 1;
     ctx->src.reemission_kind = REEMISSION_PHYSICAL;
     CUDA_OK(ctx->reemit_prob.resize((size_t)ctx->geom.ncells * NUM_REEMIT));
     ctx->reemit_prob_valid = false;

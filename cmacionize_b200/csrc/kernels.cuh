@@ -533,7 +533,7 @@ __global__ void sample_packets_kernel(const __grid_constant__ SamplePacketsParam
   while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
   double dx, dy, dz;
   random_direction(rng, dx, dy, dz);
-  const double nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+  const double nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
   double s[NUM_IONS], sHe;
   packet_cross_sections<NUM_IONS>(m, nu, s, sHe);
   const double tau = -log(rng_uniform(rng));
@@ -552,10 +552,10 @@ __global__ void sample_spectrum_kernel(SourceModel m, int which, double T, uint6
   PacketRng rng;
   rng_init(rng, seed, 0u, (uint64_t)i);
   double v;
-  if (which == 0) v = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
-  else if (which == 1) v = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
-  else if (which == 2) v = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng);
-  else v = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+  if (which == 0) v = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
+  else if (which == 1) v = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng, m.hlyc_guide);
+  else if (which == 2) v = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng, m.helyc_guide);
+  else v = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng, m.he2pc_guide);
   nu[i] = v;
 }
 

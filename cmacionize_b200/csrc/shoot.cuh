@@ -142,7 +142,7 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
   s.py = m.src_pos[3 * isrc + 1];
   s.pz = m.src_pos[3 * isrc + 2];
   random_direction(rng, s.dx, s.dy, s.dz);
-  nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+  nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
   const double weight = m.discrete_weight;
   packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
 

@@ -57,11 +57,36 @@ struct SourceModel {
   const double *hlyc_freq, *hlyc_temp, *hlyc_cdf;    /* [1000], [100], [100][1000] */
   const double *helyc_freq, *helyc_temp, *helyc_cdf; /* same shapes */
   const double *he2pc_freq, *he2pc_cdf;              /* [1000], [1000] */
+  /* bracket guides of the CDF searches (locate_guided); NULL = plain bisection */
+  const uint16_t *planck_guide, *hlyc_guide, *helyc_guide, *he2pc_guide; /* [rows][GUIDE_N + 1] */
 };
 
 /* Utilities::locate: bisection, result clamped to [0, length-2] */
 CMIB_HD uint32_t locate(double x, const double *xarr, uint32_t length) {
   uint32_t jl = 0, ju = length;
+  while (ju - jl > 1) {
+    const uint32_t jm = (ju + jl) >> 1;
+    if (x > xarr[jm]) jl = jm; else ju = jm;
+  }
+  if (jl == length - 1) --jl;
+  return jl;
+}
+
+/*
+ * Utilities::locate with a narrowed start bracket.  For a non-decreasing array the result of the
+ * bisection does not depend on the probes: it is the largest j with xarr[j] < x, clamped to
+ * [0, length-2].  guide[g] = largest j with xarr[j] < g/GUIDE_N (0 if none), tabulated on the
+ * host for g = 0..GUIDE_N, brackets every x in [g/GUIDE_N, (g+1)/GUIDE_N): the 10 dependent loads
+ * of a 1000-entry search become ~2-3 (the searches were half of the re-emission decision kernel).
+ * x must lie in [0, 1] (a cumulative distribution is searched with a uniform deviate).
+ */
+constexpr int GUIDE_N = 256;
+CMIB_HD uint32_t locate_guided(double x, const double *xarr, uint32_t length, const uint16_t *guide) {
+  if (guide == nullptr) return locate(x, xarr, length);
+  int g = (int)(x * (double)GUIDE_N);
+  g = (g < 0) ? 0 : ((g > GUIDE_N - 1) ? GUIDE_N - 1 : g);
+  uint32_t jl = guide[g], ju = (uint32_t)guide[g + 1] + 1u;
+  if (ju > length) ju = length;
   while (ju - jl > 1) {
     const uint32_t jm = (ju + jl) >> 1;
     if (x > xarr[jm]) jl = jm; else ju = jm;
@@ -87,10 +112,10 @@ CMIB_HD void random_direction(PacketRng &rng, double &dx, double &dy, double &dz
   dz = cost;
 }
 
-CMIB_HD double planck_frequency(const double *tab, PacketRng &rng) {
+CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
   const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
-  const uint32_t ix = locate(x, cdf, SPECTRUM_NUMFREQ);
+  const uint32_t ix = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
   const double lf = (log10(x) - logcdf[ix]) / (logcdf[ix + 1] - logcdf[ix]) *
                         (lognu[ix + 1] - lognu[ix]) + lognu[ix];
   return pow(10., lf) * 3.288465385e15;
@@ -113,18 +138,25 @@ CMIB_HD void locate2(double x, const double *a, const double *b, uint32_t length
 }
 
 CMIB_HD double lyc_frequency(const double *freq, const double *temp, const double *cdf, double T,
-                             PacketRng &rng) {
+                             PacketRng &rng, const uint16_t *guide = nullptr) {
   const uint32_t iT = locate(T, temp, LYC_NUMTEMP);
   const double x = rng_uniform(rng);
   uint32_t inu1, inu2;
-  locate2(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ,
-          inu1, inu2);
+  if (guide) {
+    inu1 = locate_guided(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ, guide + (size_t)iT * (GUIDE_N + 1));
+    inu2 = locate_guided(x, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ,
+                         guide + (size_t)(iT + 1) * (GUIDE_N + 1));
+  } else {
+    locate2(x, cdf + (size_t)iT * SPECTRUM_NUMFREQ, cdf + (size_t)(iT + 1) * SPECTRUM_NUMFREQ, SPECTRUM_NUMFREQ,
+            inu1, inu2);
+  }
   return freq[inu1] + (T - temp[iT]) * (freq[inu2] - freq[inu1]) / (temp[iT + 1] - temp[iT]);
 }
 
-CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng &rng) {
+CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng &rng,
+                               const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
-  const uint32_t inu = locate(x, cdf, SPECTRUM_NUMFREQ);
+  const uint32_t inu = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
   return freq[inu] + (freq[inu + 1] - freq[inu]) * (x - cdf[inu]) / (cdf[inu + 1] - cdf[inu]);
 }
 
@@ -185,13 +217,13 @@ CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigm
   if (x <= pHabs) {
     x = rng_uniform(rng);
     if (x <= p[REEMIT_H]) {
-      nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
+      nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng, m.hlyc_guide);
       type = PACKET_DIFFUSE_HI;
     }
   } else {
     x = rng_uniform(rng);
     if (x <= p[REEMIT_HE_LYC]) {
-      nu = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng);
+      nu = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng, m.helyc_guide);
       type = PACKET_DIFFUSE_HeI;
     } else if (x <= p[REEMIT_HE_NPEEV]) {
       nu = 4.788e15;
@@ -199,7 +231,7 @@ CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigm
     } else if (x <= p[REEMIT_HE_TPC]) {
       x = rng_uniform(rng);
       if (x < 0.56) {
-        nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+        nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng, m.he2pc_guide);
         type = PACKET_DIFFUSE_HeI;
       }
     } else if (x <= p[REEMIT_HE_LYA]) {
@@ -209,13 +241,13 @@ CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigm
       if (x < pHots) {
         x = rng_uniform(rng);
         if (x <= p[REEMIT_H]) {
-          nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng);
+          nu = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng, m.hlyc_guide);
           type = PACKET_DIFFUSE_HI;
         }
       } else {
         x = rng_uniform(rng);
         if (x < 0.56) {
-          nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng);
+          nu = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng, m.he2pc_guide);
           type = PACKET_DIFFUSE_HeI;
         }
       }

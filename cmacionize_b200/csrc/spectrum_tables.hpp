@@ -102,5 +102,16 @@ inline void build_he2pc_table(std::vector<double> &freq, std::vector<double> &cd
   for (int i = 0; i < N; ++i) cdf[i] /= cdf[N - 1];
 }
 
+/* bracket guide of a non-decreasing CDF row for locate_guided (source.cuh):
+ * guide[g] = largest j with cdf[j] < g / G, 0 if there is none; g = 0 .. G */
+inline void build_guide(const double *cdf, int n, int G, uint16_t *guide) {
+  int j = 0;
+  for (int g = 0; g <= G; ++g) {
+    const double edge = (double)g / (double)G;
+    while (j + 1 < n && cdf[j + 1] < edge) ++j;
+    guide[g] = (uint16_t)((cdf[j] < edge) ? j : 0);
+  }
+}
+
 } // namespace host
 } // namespace cmib

@@ -336,7 +336,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     double sigma[NSIG];
     ++cnt.n_emit;
     random_direction(rng, dx, dy, dz);
-    if (w >= n_eq) nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng) : m.mono_frequency;
+    if (w >= n_eq) nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
     packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
     const double tau = -log(rng_uniform(rng));
     double *q = W.mq + w;
