@@ -118,7 +118,7 @@ CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_
   const uint32_t ix = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
   const double lf = (log10(x) - logcdf[ix]) / (logcdf[ix + 1] - logcdf[ix]) *
                         (lognu[ix + 1] - lognu[ix]) + lognu[ix];
-  return pow(10., lf) * 3.288465385e15;
+  return fpow(10., lf) * 3.288465385e15; /* device: exp(lf ln 10), cmib_common.cuh */
 }
 
 /* Utilities::locate on two arrays of the same length at once: the two bisections are independent,
