@@ -171,9 +171,9 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
     heat[1] = 0.;
   } else {
 #pragma unroll
-    for (int k = 0; k < NUM_IONS; ++k) J[k] = a[k];
-    heat[0] = a[NUM_IONS];
-    heat[1] = a[NUM_IONS + 1];
+    for (int k = 0; k < NUM_IONS; ++k) J[k] = a[acc_slot(k)];
+    heat[0] = a[acc_slot(NUM_IONS)];
+    heat[1] = a[acc_slot(NUM_IONS + 1)];
   }
   CellOpacity c = P.cells[i];
   CellState out;
@@ -278,9 +278,9 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
         } else {
           const double *a = P.acc + ACC_COUNTERS + i * AccLayout<MODE>::NACC;
 #pragma unroll
-          for (int k = 0; k < NUM_IONS; ++k) J[k] = a[k];
-          heat[0] = a[NUM_IONS];
-          heat[1] = a[NUM_IONS + 1];
+          for (int k = 0; k < NUM_IONS; ++k) J[k] = a[acc_slot(k)];
+          heat[0] = a[acc_slot(NUM_IONS)];
+          heat[1] = a[acc_slot(NUM_IONS + 1)];
         }
         const CellOpacity c = P.cells[i];
         xprev[0] = c.xH;
@@ -386,9 +386,9 @@ __global__ void unpack_acc_kernel(int64_t ncell, const double *acc, int64_t honl
     heat[i] = acc[ACC_COUNTERS + honly_offset + i * honly_cell_stride + honly_term_stride];
     heat[ncell + i] = 0.;
   } else {
-    for (int k = 0; k < NUM_IONS; ++k) J[k * ncell + i] = a[k];
-    heat[i] = a[NUM_IONS];
-    heat[ncell + i] = a[NUM_IONS + 1];
+    for (int k = 0; k < NUM_IONS; ++k) J[k * ncell + i] = a[acc_slot(k)];
+    heat[i] = a[acc_slot(NUM_IONS)];
+    heat[ncell + i] = a[acc_slot(NUM_IONS + 1)];
   }
 }
 

@@ -14,7 +14,7 @@
  * (tests/hostcheck, plain +=) execute the same statements.
  *
  * Accumulator layouts: after ACC_COUNTERS leading counter doubles,
- *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
+ *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He in the order of acc_slot()  (128 B = one L2 line per cell)
  *   ACC_HONLY  J_H, heat_H per cell (used when only sigma_H != 0), interleaved or as two planes
  *              (ShootParams::honly_*_stride): a monochromatic source at the threshold adds no
  *              heat, so with planes only the 8 B/cell J plane is ever touched — half the
@@ -33,6 +33,28 @@ enum AccMode : int { ACC_FULL = 0, ACC_HONLY = 1 };
  * optical depth traversed, 7 spare.  16 doubles = 128 B so that the per-cell records that follow
  * are aligned to L2 lines (with 8 counters every cell's 16 accumulators straddled two lines) */
 constexpr int ACC_COUNTERS = 16;
+
+/*
+ * Position of term k (0..13 = J of ion k, 14 = heat_H, 15 = heat_He) inside a cell's 16-double
+ * record of the full layout.  Terms that are added together share a 32-byte sector: a photon
+ * between 13.6 and 21.6 eV adds J_H, heat_H, J_O0, J_N0 — one sector instead of three — which is
+ * what an HBM-resident grid pays for (every touched sector is a read-modify-write in DRAM).
+ *   sector 0: J_H heat_H J_O0 J_N0        (thresholds 13.6, 13.6, 14.5 eV)
+ *   sector 1: J_He heat_He J_Ne0 J_S+     (24.6, 21.6, 23.3 eV)
+ *   sector 2: J_C+ J_N+ J_S++ J_O+        (24.4, 29.6, 34.8, 35.1 eV)
+ *   sector 3: J_Ne+ J_N++ J_S+++ J_C++    (41.0, 47.4, 47.2, 47.9 eV)
+ * packed as 4-bit fields of a 64-bit constant so that a run-time k costs a shift and a mask.
+ */
+constexpr uint64_t acc_slot_table() {
+  const int slot_of_term[16] = {/*H*/ 0, /*He*/ 4, /*C+*/ 8, /*C++*/ 15, /*N0*/ 3, /*N+*/ 9, /*N++*/ 13, /*O0*/ 2,
+                                /*O+*/ 11, /*Ne0*/ 6, /*Ne+*/ 12, /*S+*/ 7, /*S++*/ 10, /*S+++*/ 14,
+                                /*heat_H*/ 1, /*heat_He*/ 5};
+  uint64_t t = 0;
+  for (int k = 0; k < 16; ++k) t |= (uint64_t)slot_of_term[k] << (4 * k);
+  return t;
+}
+constexpr uint64_t ACC_SLOT_TABLE = acc_slot_table();
+CMIB_HD int acc_slot(int k) { return (int)((ACC_SLOT_TABLE >> (4 * k)) & 15u); }
 
 template <int MODE> struct AccLayout;
 template <> struct AccLayout<ACC_FULL> { static constexpr int NACC = 16; static constexpr int NSIG = 14; };
@@ -79,7 +101,7 @@ template <int MODE>
 CMIB_HD double *acc_term(const ShootParams &P, int64_t cell, int k) {
   if (MODE == ACC_HONLY)
     return P.acc + ACC_COUNTERS + P.honly_offset + cell * P.honly_cell_stride + (int64_t)k * P.honly_term_stride;
-  return P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + k;
+  return P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + acc_slot(k);
 }
 
 template <int MODE, class Adder>
@@ -98,12 +120,12 @@ CMIB_HD void accumulate(const Adder &add, const ShootParams &P, int64_t cell, do
 #pragma unroll
     for (int ion = 0; ion < NUM_IONS; ++ion) {
       const double dJ = dsw * sigma[ion];
-      if (dJ != 0.) add(a + ion, dJ);
+      if (dJ != 0.) add(a + acc_slot(ion), dJ);
     }
     const double dhH = dJH * dnu_H;
-    if (dhH != 0.) add(a + NUM_IONS + HEAT_H, dhH);
+    if (dhH != 0.) add(a + acc_slot(NUM_IONS + HEAT_H), dhH);
     const double dhHe = dJHe * dnu_He;
-    if (dhHe != 0.) add(a + NUM_IONS + HEAT_He, dhHe);
+    if (dhHe != 0.) add(a + acc_slot(NUM_IONS + HEAT_He), dhHe);
   }
 }
 

@@ -398,8 +398,10 @@ __global__ void fold_hot_cells_kernel(const __grid_constant__ ShootParams P) {
             iz = (int)((sc >> 20) & 1023u) + nb % 3 - 1;
   /* a neighbour outside the grid never received anything (the walk only visits cells inside) */
   const int64_t cell = long_index(P.geom, ix, iy, iz);
+  /* full layout: a replica record has the layout of a cell record (k is a slot); H-only: k is the
+   * term, 0 (J_H) or 1 (heat_H) */
   if (MODE == ACC_FULL) atomicAdd(P.acc + ACC_COUNTERS + cell * AccLayout<MODE>::NACC + k, sum);
-  else atomicAdd(acc_term<MODE>(P, cell, k), sum); /* k is 0 (J_H) or 1 (heat_H) here */
+  else atomicAdd(acc_term<MODE>(P, cell, k), sum);
 }
 
 /* ------------------------------------------------------------------------- */
@@ -515,16 +517,16 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         if (MODE == ACC_FULL) {
           const double dJHe = dsw * s_sig[NMETAL][tid];
           if (dJHe != 0.) {
-            atomicAdd(a + ION_He_n, dJHe);
+            atomicAdd(a + acc_slot(ION_He_n), dJHe);
             const double dh = dJHe * dnu_He;
-            if (dh != 0.) atomicAdd(a + NUM_IONS + HEAT_He, dh);
+            if (dh != 0.) atomicAdd(a + acc_slot(NUM_IONS + HEAT_He), dh);
           }
           uint32_t mm = mask;
           while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1u;
             const double dJ = dsw * s_sig[k - 2][tid];
-            if (dJ != 0.) atomicAdd(a + k, dJ);
+            if (dJ != 0.) atomicAdd(a + acc_slot(k), dJ);
           }
         }
         if (!can_reemit) ++n_type[PACKET_ABSORBED]; /* PhotonSource::reemit without a handler (:304-306) */
@@ -687,23 +689,23 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           }
           const double dJH = dsw * sigH;
           if (dJH != 0.) {
-            atomicAdd(a + ION_H_n, dJH);
+            atomicAdd(a + (MODE == ACC_FULL ? acc_slot(ION_H_n) : 0), dJH);
             const double dh = dJH * dnu_H;
-            if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? NUM_IONS + HEAT_H : ts), dh);
+            if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? (int64_t)acc_slot(NUM_IONS + HEAT_H) : ts), dh);
           }
           if (MODE == ACC_FULL) {
             const double dJHe = dsw * s_sig[NMETAL][tid];
             if (dJHe != 0.) {
-              atomicAdd(a + ION_He_n, dJHe);
+              atomicAdd(a + acc_slot(ION_He_n), dJHe);
               const double dh = dJHe * dnu_He;
-              if (dh != 0.) atomicAdd(a + NUM_IONS + HEAT_He, dh);
+              if (dh != 0.) atomicAdd(a + acc_slot(NUM_IONS + HEAT_He), dh);
             }
             uint32_t mm = mask;
             while (mm) {
               const int k = __ffs(mm) - 1;
               mm &= mm - 1u;
               const double dJ = dsw * s_sig[k - 2][tid];
-              if (dJ != 0.) atomicAdd(a + k, dJ);
+              if (dJ != 0.) atomicAdd(a + acc_slot(k), dJ);
             }
           }
         }

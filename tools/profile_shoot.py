@@ -16,7 +16,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--packets", type=float, default=4194304)
-ap.add_argument("--problem", default="lexington", choices=["lexington", "stromgren", "stromgren256", "clumpy256"])
+ap.add_argument("--problem", default="lexington", choices=["lexington", "stromgren", "stromgren256", "clumpy256", "clumpy256L"])
 ap.add_argument("--algorithm", type=int, default=0)
 ap.add_argument("--repeat", type=int, default=1)
 ap.add_argument("--spinup-packets", type=float, default=2e6)
@@ -34,6 +34,9 @@ elif args.problem == "stromgren":
     spin = 6
 elif args.problem == "stromgren256":
     prob = problems.stromgren(ncell=256, n_packets=n)
+    spin = 6
+elif args.problem == "clumpy256L":
+    prob = problems.synthetic_clumpy(ncell=256, n_packets=n, variant="Lexington")
     spin = 6
 else:
     prob = problems.synthetic_clumpy(ncell=256, n_packets=n)
