@@ -361,9 +361,10 @@ def main():
     crossing_bound = 1. / (1. / GATHER_PEAK + red_per_crossing / RED_PEAK)
     roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": 1.142e9, "traffic_note": "dram__bytes_read+write of the first (4 Mi packet) march launch of a "
-                "shoot, ncu --set full, profiles/r01_wavefront_lexington.md; algorithmic bytes of that launch are ~19 GB: "
-                "the 42 MB grid is L2 resident, DRAM only sees the packet queues",
+                "traffic": 4.604e9, "traffic_note": "dram__bytes_read+write (3.47 + 1.13 GB) of the first march launch "
+                "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
+                "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
+                "(3.4 GB read) and the re-emission queue (1.1 GB written)",
                 "peak_source": peak_src,
                 "cell_crossings_per_packet": steps_per_packet, "emissions_per_packet": emissions / n_packets,
                 "algorithmic_bytes_per_crossing": bytes_per_step, "kernel_ms": march_ms,

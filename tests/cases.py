@@ -79,3 +79,54 @@ def state_cells(golden, reps: int = 20, seed: int = 5):
     J[0, 60:80] = 0
     return (np.ascontiguousarray(J), np.ascontiguousarray(heat), np.ascontiguousarray(nd),
             np.ascontiguousarray(T))
+
+
+def wall_intersection_scenarios():
+    """The nine get_wall_intersection scenarios of the reference's own unit test
+    (/root/reference/test/testCartesianDensityGrid.cpp:310-465): unit box, 16^3 cells, a packet at
+    (0.51, 0.51, 0.51) in cell (8, 8, 8); six axis-aligned rays, a generic ray, an edge hit and a
+    corner hit.  Returned: directions, expected next_index, expected intersection, expected ds.
+    Here they are run through the walk itself: the start cell is almost transparent and every other
+    cell opaque, so the packet ends (to ~1e-23) on the first wall, in the cell next_index points to,
+    and J_H of the start cell / (w sigma_H) is ds."""
+    o = 0.51
+    lo, hi = 0.5, 0.5 + 1. / 16.
+    s3 = np.array([1., 2., -3.]) / np.sqrt(14.)
+    rows = [
+        ([1., 0., 0.], (1, 0, 0), (hi, o, o), 1. / 16. - 0.01),
+        ([-1., 0., 0.], (-1, 0, 0), (lo, o, o), 0.01),
+        ([0., 1., 0.], (0, 1, 0), (o, hi, o), 1. / 16. - 0.01),
+        ([0., -1., 0.], (0, -1, 0), (o, lo, o), 0.01),
+        ([0., 0., 1.], (0, 0, 1), (o, o, hi), 1. / 16. - 0.01),
+        ([0., 0., -1.], (0, 0, -1), (o, o, lo), 0.01),
+        (list(s3), (0, 0, -1), (o + 0.01 / 3., o + 0.02 / 3., lo), 0.0124722),
+        (list(np.array([0., 1., 1.]) / np.sqrt(2.)), (0, 1, 1), (o, hi, hi), 0.0742462),
+        (list(np.array([1., 1., 1.]) / np.sqrt(3.)), (1, 1, 1), (hi, hi, hi), 0.0909327),
+    ]
+    d = np.array([r[0] for r in rows])
+    nxt = np.array([r[1] for r in rows])
+    hit = np.array([r[2] for r in rows])
+    ds = np.array([r[3] for r in rows])
+    nc = 16 ** 3
+    start = 8 * 256 + 8 * 16 + 8   # test/testCartesianDensityGrid.cpp:65-68
+    n = np.full(nc, 1e45)   # n sigma = 1e23 per unit length: absorbed ~1e-23 behind the wall
+    n[start] = 1.
+    npk = len(rows)
+    sig = np.zeros((npk, 14)); sig[:, 0] = 1e-22
+    return dict(anchor=np.zeros(3), sides=np.ones(3), ncell=np.array([16] * 3, np.int32),
+                periodic=np.zeros(3, np.int32), n=n, xH=np.ones(nc), xHe=np.zeros(nc),
+                pos=np.full((npk, 3), o), dir=np.ascontiguousarray(d), sigma=sig, sigma_He_corr=np.zeros(npk),
+                nu=np.full(npk, 3.3e15), weight=np.ones(npk), tau=np.full(npk, 1.),
+                start=start, next_index=nxt, intersection=hit, ds=ds)
+
+
+def check_wall_intersection_scenarios(c, fpos, fcell, nsteps, trace, J):
+    start = c["start"]
+    expect_next = start + c["next_index"][:, 0] * 256 + c["next_index"][:, 1] * 16 + c["next_index"][:, 2]
+    assert (nsteps == 2).all()
+    assert (trace[:, 0] == start).all()
+    assert np.array_equal(trace[:, 1], expect_next)       # next_index, incl. the edge and corner hits
+    assert np.array_equal(fcell, expect_next)
+    assert np.abs(fpos - c["intersection"]).max() < 1e-15  # the wall point (absorbed ~1e-18 behind it)
+    # ds of the nine crossings: all nine packets add ds * w * sigma_H to the start cell
+    assert abs(J[0][start] / 1e-22 - c["ds"].sum()) < 1e-4 * c["ds"].sum()   # the reference's 1e-4 tolerance

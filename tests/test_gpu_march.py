@@ -6,7 +6,7 @@ position, and accumulate path lengths / optical depths within 1e-6 relative
 import numpy as np
 import pytest
 
-from cases import MARCH_GRIDS, march_case
+from cases import MARCH_GRIDS, check_wall_intersection_scenarios, march_case, wall_intersection_scenarios
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
@@ -84,3 +84,17 @@ def test_split_batches_equal_one_batch(cmib):
             outs.append(ctx.download_accumulators())
     scale = np.abs(outs[0][0]).max()
     assert np.abs(outs[0][0] - outs[1][0]).max() <= 1e-12 * scale
+
+
+def test_wall_intersection_scenarios_of_the_reference_unit_test(cmib):
+    """test/testCartesianDensityGrid.cpp:310-465 through the C ABI (cases.wall_intersection_scenarios)."""
+    c = wall_intersection_scenarios()
+    with cmib.Context(c["anchor"], c["sides"], c["ncell"], c["periodic"]) as ctx:
+        nc = ctx.ncells
+        x = np.zeros((14, nc)); x[0] = c["xH"]
+        ctx.upload_cells(c["n"], np.full(nc, 8000.), x)
+        ctx.reset_accumulators()
+        fpos, fcell, nsteps, trace = ctx.march_packets(c["pos"], c["dir"], c["sigma"], c["sigma_He_corr"], c["nu"],
+                                                       c["weight"], c["tau"], max_trace=4)
+        J, _ = ctx.download_accumulators()
+    check_wall_intersection_scenarios(c, fpos, fcell, nsteps, trace, J)

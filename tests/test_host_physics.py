@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from cases import ABUNDANCES, MARCH_GRIDS, march_case, state_cells
+from cases import check_wall_intersection_scenarios, wall_intersection_scenarios, ABUNDANCES, MARCH_GRIDS, march_case, state_cells
 
 
 def p(a):
@@ -153,3 +153,22 @@ def test_march_bitexact(hostcheck, ref, name):
     assert np.array_equal(fp, r["final_pos"])
     assert np.array_equal(J, r["J"]) and np.array_equal(heat, r["heat"])
     assert (ns > 0).any()
+
+
+def test_wall_intersection_scenarios_of_the_reference_unit_test(hostcheck, ref):
+    """test/testCartesianDensityGrid.cpp:310-465: the product's walk (host build) and the compiled
+    reference on the nine get_wall_intersection scenarios."""
+    from cases import check_wall_intersection_scenarios, wall_intersection_scenarios
+    c = wall_intersection_scenarios()
+    npk, nc, mt = len(c["tau"]), 16 ** 3, 4
+    r = ref.interact(c["anchor"], c["sides"], c["ncell"], c["periodic"], c["n"], c["xH"], c["xHe"], c["pos"], c["dir"],
+                     c["sigma"], c["sigma_He_corr"], c["nu"], c["weight"], c["tau"], max_trace=mt)
+    check_wall_intersection_scenarios(c, r["final_pos"], r["final_cell"], r["nsteps"], r["trace"], r["J"])
+    J = np.zeros((14, nc)); heat = np.zeros((2, nc)); fp = np.empty((npk, 3))
+    fc = np.empty(npk, np.int64); ns = np.empty(npk, np.int32); tr = np.empty((npk, mt), np.int64)
+    hostcheck.hc_march_packets(p(c["anchor"]), p(c["sides"]), p(c["ncell"]), p(c["periodic"]), p(c["n"]),
+                               p(c["xH"]), p(c["xHe"]), C.c_int64(npk), p(c["pos"]), p(c["dir"]),
+                               p(c["sigma"]), p(c["sigma_He_corr"]), p(c["nu"]), p(c["weight"]),
+                               p(c["tau"]), p(J), p(heat), p(fp), p(fc), p(ns), C.c_int32(mt), p(tr))
+    check_wall_intersection_scenarios(c, fp, fc, ns, tr, J)
+    assert np.array_equal(fp, r["final_pos"]) and np.array_equal(tr, r["trace"])
