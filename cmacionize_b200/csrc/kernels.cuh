@@ -1,14 +1,18 @@
 /*
- * kernels.cuh — the sm_100a kernels of the photoionization hot path.
+ * kernels.cuh — kernels of the photoionization hot path other than the shoot pipeline
+ * (wavefront.cuh).
  *
- *   shoot_kernel        emit -> tau -> voxel walk -> accumulate -> (re-emit)*   [hot]
- *   march_packets_kernel test hook: the same walk on caller-supplied packets
- *   reemission_probabilities_kernel, update_state_kernel   per-cell passes
- *   eval_* kernels      element-wise probes of the physics for the parity tests
+ *   shoot_kernel          one thread per packet (shoot_packet of shoot.cuh): A/B check of the pipeline
+ *   march_packets_kernel  test hook: the walk on caller-supplied packets
+ *   reemission_probabilities_kernel                          per-cell pass before a shoot
+ *   update_state_kernel        ionization-only update, one thread per cell
+ *   update_temperature_kernel  temperature solve: persistent warps, three lanes per cell
+ *   pack / unpack kernels      host SoA <-> device layouts
+ *   eval_* kernels             element-wise probes of the physics for the parity tests
  *
- * Accumulator layouts: after 8 leading counter doubles,
- *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He   (128 B = one L2 line per cell)
- *   ACC_HONLY  J_H[ncell], heat_H[ncell] planes         (used when only sigma_H != 0)
+ * Accumulator layouts: after ACC_COUNTERS leading counter doubles,
+ *   ACC_FULL   acc[cell][16] = J[14], heat_H, heat_He in acc_slot() order (one 128-B L2 line per cell)
+ *   ACC_HONLY  J_H, heat_H per cell: padded to a line, interleaved, or as planes (shoot.cuh)
  */
 #pragma once
 #include <cuda_runtime.h>

@@ -1,20 +1,23 @@
 /*
- * wavefront.cuh — the production shoot path: photon packets flow through two
+ * wavefront.cuh — the production shoot path: photon packets flow through three
  * warp-convergent kernels connected by device-resident queues.
  *
- *   prepare_kernel   (re-)emission: decides the fate of absorbed packets
- *                    (PhotonSource::reemit, src/PhotonSource.cpp:272-308), draws fresh
- *                    primaries (PhotonSource::get_random_photon, :208-249), samples the
- *                    new direction / frequency / 14 cross sections / optical depth and
- *                    appends the packet to the march queue.  All lanes of a warp
- *                    execute the pow()-heavy code together.
+ *   reemit_decide_kernel  fate of the packets absorbed in the last round (PhotonSource::reemit,
+ *                    src/PhotonSource.cpp:272-308 up to the new frequency); survivors are
+ *                    compacted into the emission queue.
+ *   prepare_kernel   emission-queue entries + fresh primaries (PhotonSource::get_random_photon,
+ *                    :208-249): new direction, frequency, 14 cross sections, optical depth;
+ *                    item w -> march-queue slot w.  All lanes of a warp execute the
+ *                    exp/log-heavy code together.
  *   march_kernel     CartesianDensityGrid::interact (src/CartesianDensityGrid.cpp:375-452)
  *                    + DensityGrid::update_integrals (src/DensityGrid.hpp:150-197) as a
  *                    persistent warp state machine: every pass all live lanes take
- *                    exactly one cell crossing; lanes whose packet ended are refilled
- *                    from the queue in batches (warp-level compaction of live packets);
- *                    packets absorbed inside the box are appended to the re-emission
- *                    queue with one warp-aggregated atomic.
+ *                    exactly one cell crossing; lanes whose packet ended are finished and
+ *                    refilled from the queue in batches (warp-level compaction of live
+ *                    packets); packets absorbed inside the box are appended to the
+ *                    re-emission queue with one warp-aggregated atomic.
+ *   fold_hot_cells_kernel  adds the replicated accumulators of the cells around the sources.
+ *   sort_*_kernel    optional coherence sort of the march queue (off: measured slower).
  *
  * Why: in a one-thread-per-packet kernel (shoot_kernel, kept as the A/B check)
  * ncu showed 3.9 active threads per warp instruction: lanes sit in different
@@ -25,6 +28,7 @@
  * up to the order of the atomic adds.
  *
  * Queue entries are structure-of-arrays with the queue capacity as the stride.
+ * Host side: shoot_wavefront() in cmib_api.cu (rounds of decide -> prepare -> march).
  */
 #pragma once
 #include "cmib_common.cuh"
