@@ -7,12 +7,15 @@
  * work requires a CUDA device and fails loudly otherwise.
  */
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
 
 #include "../../include/cmib.h"
 #include "kernels.cuh"
@@ -119,13 +122,24 @@ struct cmib_context {
   DevBuf<double> mq, rq, eq;
   DevBuf<unsigned long long> ctl;
   DevBuf<uint32_t> sort_key, sort_order, sort_hist;
+  DevBuf<uint32_t> sort_key_out, sort_iota; /* coherent march (sort mode 2): radix sort of (key, slot) pairs */
+  DevBuf<unsigned char> sort_temp;
   DevBuf<double> hot_acc;       /* replicated accumulators of the cells around the sources */
   DevBuf<uint32_t> d_src_cell;  /* packed cell indices of the sources */
   std::vector<uint32_t> h_src_cell;
   int hot_replicas = 0;
   DevBuf<unsigned long long> upd_counter; /* next unprocessed cell of update_temperature_kernel */
   int update_blocks_per_sm[2] = {0, 0};
-  int sort_mode = 0; /* 0 off (default: measured slower), 1 on, -1 auto by working set */
+  /* march-queue order: 0 emission order, 1 coarse counting sort (measured slower),
+   * 2 coherent march = fine radix sort + in-warp sums (march_kernel<MODE, true>),
+   * -1 (default) measured: grids that fit in L2 use 0 (2 loses there on every workload measured);
+   * for larger grids the two are timed on successive large shoots of this context and the faster
+   * one is kept (re-timed every 16 shoots: the ionised volume grows during a run).  Both orders
+   * shoot the same packets; only the order of the atomic adds differs. */
+  int sort_mode = -1;
+  int tune_shoots = 0;                 /* large shoots seen since the last (re)configuration */
+  double tune_ns_per_packet[3] = {0., 0., 0.}; /* indexed by order (0, 2) */
+  int tuned_order = 0;
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2] = {0, 0};
@@ -276,10 +290,14 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   if (!ctx->ctl.p) {
     CUDA_OK(ctx->ctl.resize(CTL_WORDS));
     CUDA_OK(cudaMallocHost((void **)&ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long)));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks_per_sm[ACC_FULL],
-                                                          march_kernel<ACC_FULL>, MARCH_BLOCK, 0));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->march_blocks_per_sm[ACC_HONLY],
-                                                          march_kernel<ACC_HONLY>, MARCH_BLOCK, 0));
+    /* the plain and the coherent variant of a layout run with the same grid: the smaller occupancy */
+    int occ[4] = {0, 0, 0, 0};
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], march_kernel<ACC_FULL, true>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], march_kernel<ACC_HONLY, false>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], march_kernel<ACC_HONLY, true>, MARCH_BLOCK, 0));
+    ctx->march_blocks_per_sm[ACC_FULL] = occ[0] < occ[1] ? occ[0] : occ[1];
+    ctx->march_blocks_per_sm[ACC_HONLY] = occ[2] < occ[3] ? occ[2] : occ[3];
   }
   cudaStream_t s = ctx->stream;
   memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
@@ -295,13 +313,57 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   /* coherence sort: on when the gathered + accumulated working set does not fit in L2 */
   int sort = ctx->sort_mode;
   if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
+  bool tuning = false;
   if (sort < 0) {
-    const size_t working_set = (size_t)ctx->geom.ncells * (sizeof(CellOpacity) + (mode == ACC_HONLY ? 16 : 128));
-    sort = working_set > ctx->l2_bytes ? 1 : 0;
+    const size_t working_set = (size_t)ctx->geom.ncells * ((mode == ACC_HONLY ? 16 : sizeof(CellOpacity)) + (mode == ACC_HONLY ? 16 : 128));
+    if (working_set <= ctx->l2_bytes || P.n_packets < (1ull << 20)) {
+      sort = (working_set <= ctx->l2_bytes) ? 0 : ctx->tuned_order;
+    } else {
+      const int phase = ctx->tune_shoots % 16; /* 0: warm-up (allocations), 1: time order 0, 2: time order 2 */
+      sort = (phase == 1) ? 0 : (phase == 2 ? 2 : ctx->tuned_order);
+      tuning = (phase == 1 || phase == 2);
+      ++ctx->tune_shoots;
+    }
   }
   W.sort = sort;
   W.key = nullptr; W.order = nullptr; W.hist = nullptr; W.nbins = 0; W.isrc_bits_shift = SORT_DIR_BITS;
-  if (sort) {
+  W.sort_n = 0; W.fine_dir_bits = 22; W.fine_key_bits = 22; W.chunk_stride = 1; W.agg = 1;
+  size_t sort_temp_bytes = 0;
+  bool sort_reemitted_rounds = false;
+  if (sort == 2) {
+    /* key = source | direction (wavefront.cuh): as many direction bits as the source index leaves */
+    int src_bits = 0;
+    while ((1ll << src_bits) < (long long)P.src.n_sources) ++src_bits;
+    /* 24 key bits = 3 radix passes while that leaves >= 18 direction bits (512 x 512 bins per source) */
+    int dir_bits = 23 - src_bits;
+    if (dir_bits > 22) dir_bits = 22;
+    if (dir_bits < 18) dir_bits = 18;
+    if (dir_bits + src_bits > 30) dir_bits = 30 - src_bits;
+    if (dir_bits < 2) W.sort = sort = 0; /* more than 2^28 sources: no room for a direction */
+    W.fine_dir_bits = dir_bits & ~1;
+    W.fine_key_bits = W.fine_dir_bits + src_bits;
+  }
+  if (sort == 2) {
+    W.sort = 2;
+    if (const char *e = getenv("CMIB_CHUNK_STRIDE")) W.chunk_stride = (uint32_t)atoll(e); /* e.g. the prime 1000003 */
+    if (W.chunk_stride < 1u || cap / MARCH_CHUNK >= W.chunk_stride) W.chunk_stride = 1u;
+    if (const char *e = getenv("CMIB_AGG")) W.agg = atoi(e) != 0;
+    if (const char *e = getenv("CMIB_SORT_REEMITTED")) sort_reemitted_rounds = atoi(e) != 0;
+    if (ctx->sort_key.n < cap) {
+      CUDA_OK(ctx->sort_key.resize(cap));
+      CUDA_OK(ctx->sort_order.resize(cap));
+    }
+    if (ctx->sort_key_out.n < cap) {
+      CUDA_OK(ctx->sort_key_out.resize(cap));
+      CUDA_OK(ctx->sort_iota.resize(cap));
+      iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->sort_iota.p, cap);
+    }
+    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_temp_bytes, ctx->sort_key.p, ctx->sort_key_out.p,
+                                            ctx->sort_iota.p, ctx->sort_order.p, (int64_t)cap, 0, W.fine_key_bits + 1, ctx->stream));
+    if (ctx->sort_temp.n < sort_temp_bytes) CUDA_OK(ctx->sort_temp.resize(sort_temp_bytes));
+    sort_temp_bytes = ctx->sort_temp.n;
+    W.key = ctx->sort_key.p; W.order = ctx->sort_order.p;
+  } else if (sort) {
     /* keep the number of bins <= 2^20: fewer direction bits when there are many sources */
     int shift = 6; /* 8 x 8 direction bins per source: see wavefront.cuh */
     if (const char *e = getenv("CMIB_SORT_DIR_BITS")) shift = atoi(e);
@@ -345,8 +407,22 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   ctx->prepare_ms = ctx->march_ms = 0.;
   /* upper bound: every round either emits min(remaining, room) primaries or shrinks the
    * re-emission population; 1e6 rounds cannot be reached by a sane configuration */
+  /* coherent march: what the host knows about the coming rounds (read back once per group):
+   * while primaries remain a round can fill the queue; afterwards it holds at most the packets
+   * of the round before.  Rounds without primaries (re-emitted packets start anywhere) run
+   * unsorted through the plain kernel. */
+  const int sort_cfg = W.sort;
+  if (tuning) CUDA_OK(cudaStreamSynchronize(s)); /* buffers are allocated, earlier work is done: time the shoot alone */
+  const auto tune_t0 = std::chrono::steady_clock::now();
+  uint64_t items_bound = cap;
+  bool primaries_left = true;
   while (round < 1000000) {
     for (int k = 0; k < group; ++k, ++round) {
+      if (sort_cfg == 2) {
+        W.sort = (primaries_left || sort_reemitted_rounds) ? 2 : 0;
+        W.sort_n = items_bound;
+      }
+      const int sort = W.sort;
       stamp();
       if (P.src.reemission_kind != REEMISSION_NONE && round > 0) {
         reemit_decide_kernel<<<decide_grid, 256, 0, s>>>(W);
@@ -356,16 +432,26 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
       else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
       stamp();
       advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
-      if (sort) {
+      if (sort == 1) {
         CUDA_OK(cudaMemsetAsync(W.hist, 0, (W.nbins + 1) * sizeof(uint32_t), s));
         sort_histogram_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist);
         sort_scan_kernel<<<1, 1024, 0, s>>>(W.hist, W.nbins);
         sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist, W.order);
         g_launches += 3;
       }
+      if (sort == 2) {
+        CUDA_OK(cub::DeviceRadixSort::SortPairs(ctx->sort_temp.p, sort_temp_bytes, W.key, ctx->sort_key_out.p,
+                                                ctx->sort_iota.p, W.order, (int64_t)W.sort_n, 0, W.fine_key_bits + 1, s));
+        g_launches += 2 + (W.fine_key_bits + 8) / 8; /* onesweep: histogram, scan, one pass per 8 key bits */
+      }
       stamp();
-      if (mode == ACC_HONLY) march_kernel<ACC_HONLY><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
-      else march_kernel<ACC_FULL><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      if (sort == 2 && W.agg) {
+        if (mode == ACC_HONLY) march_kernel<ACC_HONLY, true><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+        else march_kernel<ACC_FULL, true><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      } else {
+        if (mode == ACC_HONLY) march_kernel<ACC_HONLY, false><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+        else march_kernel<ACC_FULL, false><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      }
       stamp();
       advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl);
       g_launches += 4;
@@ -378,6 +464,11 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     for (int k = 0; k < group; ++k)
       if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;
     if (done) break;
+    if (ctx->h_ctl[CTL_REMAINING] == 0) {
+      primaries_left = false;
+      const uint64_t last = ctx->h_ctl[CTL_STATUS + ((round - 1) % CTL_STATUS_SLOTS)];
+      items_bound = last < cap ? last : cap;
+    }
   }
   ctx->shoot_rounds = round;
   if (P.hot_replicas > 0) {
@@ -387,6 +478,12 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     ++g_launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(s));
+  }
+  if (tuning) {
+    /* every group of rounds ends with a stream synchronisation: host time = device time here */
+    const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tune_t0).count();
+    ctx->tune_ns_per_packet[sort_cfg] = ns / (double)P.n_packets;
+    if (sort_cfg == 2) ctx->tuned_order = (ctx->tune_ns_per_packet[2] < ctx->tune_ns_per_packet[0]) ? 2 : 0;
   }
   for (size_t k = 0; k + 3 < ev_used; k += 4) {
     float a = 0.f, b = 0.f;

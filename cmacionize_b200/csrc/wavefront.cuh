@@ -77,6 +77,13 @@ struct WavefrontParams {
   uint32_t *hist;          /* [nbins + 1] */
   uint32_t nbins;
   int isrc_bits_shift;     /* key = isrc << shift | direction bin (primaries) */
+  /* sort == 2: coherent march (fine 32-bit keys, radix sort on the host side of the launch,
+   * march_kernel<MODE, true> adds same-cell contributions inside the warp first) */
+  uint64_t sort_n;         /* entries the sort covers (>= items of this round); slots beyond the items get the largest key */
+  int fine_dir_bits;       /* direction bits of a primary's key (even, <= 22) */
+  int fine_key_bits;       /* source + direction bits; bit fine_key_bits flags a re-emitted packet */
+  uint32_t chunk_stride;   /* chunk c of the ordered queue is claimed as (c * chunk_stride) % nchunks */
+  int agg;                 /* 1: march_kernel<MODE, true> (in-warp sums), 0: the plain kernel on the ordered queue */
 };
 
 /*
@@ -122,6 +129,56 @@ CMIB_D uint32_t position_bin(const GridGeom &g, double px, double py, double pz)
   const int iy = min(15, max(0, (int)((py - g.anchor[1]) / g.sides[1] * 16.)));
   const int iz = min(15, max(0, (int)((pz - g.anchor[2]) / g.sides[2] * 16.)));
   return morton3_4((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
+}
+
+/*
+ * Fine keys of the coherent march (sort == 2), fine_key_bits + 1 bits wide so that the radix sort
+ * needs 3 passes for up to 8 sources: primaries  0 | source | direction on a 2048 x 2048 octahedral
+ * map in Morton order (truncated to fine_dir_bits); re-emitted packets  1 | 1024^3 Morton bin of
+ * the start position (truncated); unused slots all ones (they tie with the last position bin at
+ * most, and the stable sort keeps them behind it: they have the largest slot numbers).  With 1.6e7 packets of one
+ * source in the queue, 32 neighbours in key order leave within ~0.003 rad of each other: they
+ * cross the same cells in lock-step for tens of cells.
+ */
+constexpr uint32_t SORT_KEY_UNUSED = 0xffffffffu;
+CMIB_D uint32_t spread2(uint32_t x) { /* 16 bits -> even bit positions */
+  x &= 0xffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+CMIB_D uint32_t spread3(uint32_t x) { /* 10 bits -> every third bit position */
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+CMIB_D uint32_t fine_direction_key(double dx, double dy, double dz) { /* 22 bits */
+  const double ax = fabs(dx), ay = fabs(dy), az = fabs(dz);
+  const double inv = 1. / fmax(ax + ay + az, 1e-300);
+  double u = dx * inv, v = dy * inv;
+  if (dz < 0.) {
+    const double uu = (1. - fabs(v)) * (u >= 0. ? 1. : -1.);
+    const double vv = (1. - fabs(u)) * (v >= 0. ? 1. : -1.);
+    u = uu; v = vv;
+  }
+  const int iu = min(2047, max(0, (int)((u * 0.5 + 0.5) * 2048.)));
+  const int iv = min(2047, max(0, (int)((v * 0.5 + 0.5) * 2048.)));
+  return spread2((uint32_t)iu) | (spread2((uint32_t)iv) << 1);
+}
+CMIB_D uint32_t fine_position_key(const GridGeom &g, double px, double py, double pz) { /* 30 bits */
+  const int ix = min(1023, max(0, (int)((px - g.anchor[0]) / g.sides[0] * 1024.)));
+  const int iy = min(1023, max(0, (int)((py - g.anchor[1]) / g.sides[1] * 1024.)));
+  const int iz = min(1023, max(0, (int)((pz - g.anchor[2]) / g.sides[2] * 1024.)));
+  return spread3((uint32_t)ix) | (spread3((uint32_t)iy) << 1) | (spread3((uint32_t)iz) << 2);
+}
+__global__ void iota_kernel(uint32_t *v, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    v[i] = (uint32_t)i;
 }
 
 /* counting sort of the march queue by key: histogram -> exclusive scan -> scatter */
@@ -352,7 +409,11 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
 #pragma unroll
     for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
     if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
-    if (W.sort) {
+    if (W.sort == 2) {
+      W.key[w] = (isrc_key >= 0)
+                     ? (((uint32_t)isrc_key << W.fine_dir_bits) | (fine_direction_key(dx, dy, dz) >> (22 - W.fine_dir_bits)))
+                     : ((1u << W.fine_key_bits) | (fine_position_key(P.geom, px, py, pz) >> (30 - W.fine_key_bits)));
+    } else if (W.sort) {
       const uint32_t nprim = (uint32_t)m.n_sources << W.isrc_bits_shift;
       uint32_t k;
       if (isrc_key >= 0) k = ((uint32_t)isrc_key << W.isrc_bits_shift) | (direction_bin(dx, dy, dz) >> (SORT_DIR_BITS - W.isrc_bits_shift));
@@ -360,6 +421,9 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       W.key[w] = k;
     }
   }
+  if (W.sort == 2) /* slots of the sorted range that hold no packet this round go last */
+    for (uint64_t w = n_items + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W.sort_n; w += stride)
+      W.key[w] = SORT_KEY_UNUSED;
   reduce_counters(P.acc, cnt);
 }
 
@@ -430,11 +494,22 @@ enum LaneState : int { LANE_EMPTY = 0, LANE_LIVE = 1, LANE_ABSORBED = 2, LANE_ES
  * incremented by +-1 (integers are exact in FP64), and the upper wall lo + cellside of
  * the reference is formed as lo + h with h = cellside (d > 0) or 0 (d < 0), x + 0 == x.
  */
-template <int MODE>
+/*
+ * AGG (coherent march, W.sort == 2): the queue is ordered so that the lanes of a warp walk
+ * through the same cells; lanes that add to the same accumulator record are found with
+ * match.any, their J_H / heat_H (/ J_O0 / J_N0: the first sector of a full record) terms are
+ * summed in registers (reduce_peers) and the lowest lane issues ONE RED per term.  The gathers of
+ * such lanes fall into one sector by themselves.  The remaining terms (photons above 21.6 eV)
+ * are added per lane as in the plain kernel.
+ */
+constexpr uint32_t AGG_METALS = (1u << ION_O_n) | (1u << ION_N_n);
+constexpr int AGG_GROUP = 8; /* lanes that are refilled together */
+template <int MODE, bool AGG>
 __global__ void __launch_bounds__(MARCH_BLOCK, 3)
 march_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   constexpr int NMETAL = (MODE == ACC_FULL) ? 12 : 0;
+  constexpr int NV = (MODE == ACC_FULL) ? 4 : 2; /* terms summed inside the warp (AGG) */
   /* per-lane packet constants that are only touched once per packet or per accumulation */
   __shared__ double s_sig[(NMETAL > 0 ? NMETAL + 1 : 1)][MARCH_BLOCK]; /* metals, then sigma_He */
   __shared__ unsigned long long s_id[MARCH_BLOCK], s_meta[MARCH_BLOCK];
@@ -468,6 +543,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   int state = LANE_EMPTY;
   bool warp_has_zero_dir = false; /* some lane's direction has a zero component (warp-uniform) */
   uint64_t cur = 0, end = 0;      /* warp-uniform cursor into the claimed chunk */
+  const uint64_t nchunks = (qcount + MARCH_CHUNK - 1) / MARCH_CHUNK;
   bool exhausted = (qcount == 0);
   uint32_t n_pass = 0;
 
@@ -483,7 +559,18 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
     const int nwait = __popc(waiting);
     /* service (finish + refill) when enough lanes wait for it or when nothing can be stepped;
      * once the queue is exhausted only lanes with a pending finish count */
-    bool service = (nwait >= MARCH_REFILL_MIN);
+    /* AGG: lanes are refilled in aligned groups of AGG_GROUP lanes, a group when all of its
+     * lanes wait, so that lane order inside a group stays queue (= key) order */
+    unsigned fill_m = waiting;
+    if (AGG) {
+      static_assert(AGG_GROUP == 8, "group mask arithmetic below is written for 8 lanes");
+      unsigned m = waiting;
+      m &= m >> 1;
+      m &= m >> 2;
+      m &= m >> 4;
+      fill_m = (m & 0x01010101u) * 0xffu;
+    }
+    bool service = AGG ? (fill_m != 0u) : (nwait >= MARCH_REFILL_MIN);
     if (service && exhausted) {
       const unsigned pend_m = __ballot_sync(0xffffffffu, state == LANE_ABSORBED || state == LANE_ESCAPED);
       if (live_m == 0u && pend_m == 0u) break;
@@ -510,6 +597,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         fpz = xadd(pz, xdiv(xmul(xsub(nwz, pz), dss), ds));
         /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
         n_red += nacc;
+        if (AGG) n_red += (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask & AGG_METALS); /* added per lane here */
         const double dsw = dss * weight;
         double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
         const double dJH = dsw * sigH;
@@ -568,14 +656,19 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           if (b >= qcount) {
             exhausted = true;
           } else {
+            /* experiment switch (CMIB_CHUNK_STRIDE, default 1 = in order): consecutive chunks of the
+             * ordered queue walk the same cone; a stride coprime to nchunks spreads the warps in
+             * flight over different cones.  Measured: in order is faster (shared L2 lines). */
+            if (W.chunk_stride > 1u) b = (((b / MARCH_CHUNK) * (uint64_t)W.chunk_stride) % nchunks) * MARCH_CHUNK;
             cur = b;
             end = (b + MARCH_CHUNK < qcount) ? b + MARCH_CHUNK : qcount;
           }
         }
         if (!exhausted) {
-          const int rank = __popc(waiting & ((1u << lane) - 1u));
+          const int rank = __popc(fill_m & ((1u << lane) - 1u));
           const uint64_t avail = end - cur;
-          if (state == LANE_EMPTY && (uint64_t)rank < avail) {
+          const int nfill = __popc(fill_m);
+          if (state == LANE_EMPTY && ((fill_m >> lane) & 1u) && (uint64_t)rank < avail) {
             const uint64_t slot = W.sort ? (uint64_t)W.order[cur + rank] : (cur + rank);
             const double *q = W.mq + slot;
             px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
@@ -607,7 +700,8 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             }
             dnu_H = nu - P.nu_H;
             dnu_He = nu - P.nu_He;
-            nacc = (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask);
+            /* AGG: the warp-summed terms are counted where they are issued */
+            nacc = AGG ? __popc(mask & ~AGG_METALS) : (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask);
             if (MODE == ACC_FULL) nacc += (s_sig[NMETAL][tid] != 0.) * (1u + (dnu_He != 0.));
             ivx = 1. / dx;
             ivy = 1. / dy;
@@ -628,7 +722,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             }
             fx = (double)ix; fy = (double)iy; fz = (double)iz;
           }
-          cur += ((uint64_t)nwait < avail) ? (uint64_t)nwait : avail;
+          cur += ((uint64_t)nfill < avail) ? (uint64_t)nfill : avail;
         }
       }
       warp_has_zero_dir = __any_sync(0xffffffffu, state == LANE_LIVE && (dx == 0. || dy == 0. || dz == 0.));
@@ -636,6 +730,13 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
     }
 
     /* ---- one cell crossing for every live lane ---- */
+    bool do_acc = false;    /* AGG: this lane holds terms for the warp-level sum */
+    double *arec = nullptr; /* its accumulator record */
+    uint32_t akey = 0;      /* ... and a 32-bit name for it: the cell, or 2^31 | hot replica record */
+    int64_t ats = 1;
+    double v[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = 0.;
     if (state == LANE_LIVE) {
       cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
       /* one gather per crossing: the 32-byte cell record is one sector; the H-only walk needs
@@ -680,6 +781,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           double *a = (MODE == ACC_FULL) ? P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC
                                          : acc_term<MODE>(P, cell, 0);
           int64_t ts = (MODE == ACC_FULL) ? 1 : P.honly_term_stride; /* stride between terms */
+          akey = cell;
           if (hot != 0u && (hot & 3u) < (uint32_t)HOT_CROSSINGS) {
             const int ddx = ix - (int)(hot_cell & 1023u), ddy = iy - (int)((hot_cell >> 10) & 1023u),
                       ddz = iz - (int)((hot_cell >> 20) & 1023u);
@@ -688,11 +790,22 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
                                  (size_t)((ddx + 1) * 9 + (ddy + 1) * 3 + (ddz + 1));
               a = P.hot_acc + rec * HOT_STRIDE;
               ts = 1;
+              akey = 0x80000000u | (uint32_t)rec;
             }
             ++hot;
           }
           const double dJH = dsw * sigH;
-          if (dJH != 0.) {
+          if constexpr (AGG) {
+            do_acc = true;
+            arec = a;
+            ats = ts;
+            v[0] = dJH;
+            v[1] = dJH * dnu_H;
+            if constexpr (MODE == ACC_FULL) {
+              v[2] = (mask & (1u << ION_O_n)) ? dsw * s_sig[ION_O_n - 2][tid] : 0.;
+              v[3] = (mask & (1u << ION_N_n)) ? dsw * s_sig[ION_N_n - 2][tid] : 0.;
+            }
+          } else if (dJH != 0.) {
             atomicAdd(a + (MODE == ACC_FULL ? acc_slot(ION_H_n) : 0), dJH);
             const double dh = dJH * dnu_H;
             if (dh != 0.) atomicAdd(a + (MODE == ACC_FULL ? (int64_t)acc_slot(NUM_IONS + HEAT_H) : ts), dh);
@@ -704,7 +817,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
               const double dh = dJHe * dnu_He;
               if (dh != 0.) atomicAdd(a + acc_slot(NUM_IONS + HEAT_He), dh);
             }
-            uint32_t mm = mask;
+            uint32_t mm = AGG ? (mask & ~AGG_METALS) : mask;
             while (mm) {
               const int k = __ffs(mm) - 1;
               mm &= mm - 1u;
@@ -738,6 +851,40 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         }
         /* tau == 0 exactly: the walk ends inside (loop condition tau > 0, :391), on the wall */
         if (state == LANE_LIVE && !(tau > 0.)) state = LANE_ABSORBED;
+      }
+    }
+    if constexpr (AGG) {
+      /* runs of neighbouring lanes with the same record (neighbours inside a group are neighbours
+       * in key order): segmented sum towards the first lane of every run, log2(group) shuffle steps */
+      const uint32_t key = do_acc ? akey : 0xffffffffu;
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+      const bool head = !do_acc || (lane & (AGG_GROUP - 1)) == 0 || key != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      if (heads != 0xffffffffu) {
+        const unsigned above = heads & (0xfffffffeu << lane);
+        const int last = above ? (__ffs(above) - 2) : 31;
+        const bool heat = __any_sync(0xffffffffu, v[1] != 0.); /* a source at the threshold adds no heat */
+#pragma unroll
+        for (int d = 1; d < AGG_GROUP; d <<= 1) {
+          const bool take = lane + d <= last;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            if (k == 1 && !heat) continue;
+            const double t = __shfl_down_sync(0xffffffffu, v[k], d);
+            if (take) v[k] += t;
+          }
+        }
+      }
+      const bool issue = do_acc && head;
+      {
+        if (issue) {
+          if (v[0] != 0.) { atomicAdd(arec + (MODE == ACC_FULL ? acc_slot(ION_H_n) : 0), v[0]); ++n_red; }
+          if (v[1] != 0.) { atomicAdd(arec + (MODE == ACC_FULL ? (int64_t)acc_slot(NUM_IONS + HEAT_H) : ats), v[1]); ++n_red; }
+          if constexpr (MODE == ACC_FULL) {
+            if (v[2] != 0.) { atomicAdd(arec + acc_slot(ION_O_n), v[2]); ++n_red; }
+            if (v[3] != 0.) { atomicAdd(arec + acc_slot(ION_N_n), v[3]); ++n_red; }
+          }
+        }
       }
     }
   }

@@ -174,8 +174,9 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
     streams: identical counters (packets by type, cell crossings, (re-)emissions) and
     accumulators equal up to the order of the atomic adds.  Small queue capacities force many
-    rounds, chunk boundaries and partially filled warps; the coherence sort only changes which
-    packets run together."""
+    rounds, chunk boundaries and partially filled warps; the coherence sorts (1: coarse counting
+    sort, 2: the coherent march = fine radix sort + in-warp sums of same-cell terms, the default)
+    only change which packets run together and in which order their terms are added."""
     import os
     from cmacionize_b200 import problems, capi
     npk = 60000
@@ -209,7 +210,8 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), ctx.ncells))
     ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
     results = []
-    for algorithm, capacity, sort in ((1, None, 0), (0, None, 0), (0, 4096, 0), (0, 1024, 0), (0, None, 1), (0, 2048, 1)):
+    for algorithm, capacity, sort in ((1, None, 0), (0, None, 0), (0, 4096, 0), (0, 1024, 0), (0, None, 1), (0, 2048, 1),
+                                      (0, None, 2), (0, 2048, 2), (0, 1024, 2)):
         if capacity is None:
             os.environ.pop("CMIB_QUEUE_CAPACITY", None)
         else:
