@@ -24,6 +24,7 @@ ION_NAMES = ["H_n", "He_n", "C_p1", "C_p2", "N_n", "N_p1", "N_p2", "O_n", "O_p1"
 CROSS_SECTIONS_FIXED_VALUE, CROSS_SECTIONS_VERNER = 0, 1
 RECOMBINATION_FIXED_VALUE, RECOMBINATION_VERNER = 0, 1
 SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK = 0, 1
+CONTINUOUS_NONE, CONTINUOUS_ISOTROPIC = 0, 1
 REEMISSION_NONE, REEMISSION_PHYSICAL, REEMISSION_FIXED_VALUE = 0, 1, 2
 
 # CMIB_LIB: load another build of the same ABI (A/B timing of kernel variants)
@@ -175,11 +176,20 @@ class Context:
         _check(lib.cmib_set_recombination_rates(self._h, C.c_int(kind), _p(f)))
 
     def set_sources(self, positions, weights, total_luminosity):
+        if positions is None or len(positions) == 0:  # PhotonSourceDistribution: None
+            _check(lib.cmib_set_sources(self._h, C.c_int32(0), None, None, C.c_double(0.)))
+            return
         pos = _f64(positions).reshape(-1, 3)
         w = _f64(weights).reshape(-1)
         assert pos.shape[0] == w.size
         _check(lib.cmib_set_sources(self._h, C.c_int32(w.size), _p(pos), _p(w),
                                     C.c_double(total_luminosity)))
+
+    def set_continuous_source(self, kind, luminosity=0., spectrum_kind=0, spectrum_param=0.):
+        """IsotropicContinuousPhotonSource + its spectrum (include/cmib.h); luminosity = total surface
+        area of the box x total flux of the spectrum."""
+        _check(lib.cmib_set_continuous_source(self._h, C.c_int(kind), C.c_double(luminosity),
+                                              C.c_int(spectrum_kind), C.c_double(spectrum_param)))
 
     def set_spectrum(self, kind, param):
         _check(lib.cmib_set_spectrum(self._h, C.c_int(kind), C.c_double(param)))

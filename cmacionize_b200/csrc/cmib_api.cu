@@ -107,7 +107,31 @@ struct cmib_context {
   SourceModel src;
   RecombinationModel rr;
   TemperatureParams tp;
-  double luminosity = 0.;
+  double luminosity = 0.; /* discrete + continuous */
+  double discrete_luminosity = 0., continuous_luminosity = 0.;
+  DevBuf<double> d_cont_planck;
+  DevBuf<uint16_t> d_cont_planck_guide;
+  std::vector<double> h_cont_planck;
+  /* PhotonSource.cpp:110-131: probability of a continuous packet and the two packet weights */
+  void update_source_weights() {
+    luminosity = discrete_luminosity + continuous_luminosity;
+    if (src.continuous_kind != CONTINUOUS_NONE && continuous_luminosity > 0.) {
+      if (src.n_sources > 0 && discrete_luminosity > 0.) {
+        src.continuous_probability = 0.5;
+        src.discrete_weight = 1.;
+        src.continuous_weight = (1. - src.continuous_probability) * continuous_luminosity /
+                                src.continuous_probability / discrete_luminosity;
+      } else {
+        src.continuous_probability = 1.;
+        src.discrete_weight = 0.;
+        src.continuous_weight = 1.;
+      }
+    } else {
+      src.continuous_probability = 0.;
+      src.discrete_weight = 1.;
+      src.continuous_weight = 0.;
+    }
+  }
   DevBuf<uint16_t> d_planck_guide, d_hlyc_guide, d_helyc_guide, d_he2pc_guide;
   DevBuf<double> d_src_pos, d_src_cum, d_planck, d_hlyc_freq, d_hlyc_temp, d_hlyc_cdf, d_helyc_freq,
       d_helyc_temp, d_helyc_cdf, d_he2pc_freq, d_he2pc_cdf;
@@ -292,10 +316,10 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     CUDA_OK(cudaMallocHost((void **)&ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long)));
     /* the plain and the coherent variant of a layout run with the same grid: the smaller occupancy */
     int occ[4] = {0, 0, 0, 0};
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false>, MARCH_BLOCK, 0));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], march_kernel<ACC_FULL, true>, MARCH_BLOCK, 0));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], march_kernel<ACC_HONLY, false>, MARCH_BLOCK, 0));
-    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], march_kernel<ACC_HONLY, true>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false, true>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], march_kernel<ACC_FULL, true, true>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], march_kernel<ACC_HONLY, false, true>, MARCH_BLOCK, 0));
+    CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], march_kernel<ACC_HONLY, true, true>, MARCH_BLOCK, 0));
     ctx->march_blocks_per_sm[ACC_FULL] = occ[0] < occ[1] ? occ[0] : occ[1];
     ctx->march_blocks_per_sm[ACC_HONLY] = occ[2] < occ[3] ? occ[2] : occ[3];
   }
@@ -412,6 +436,11 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
    * of the round before.  Rounds without primaries (re-emitted packets start anywhere) run
    * unsorted through the plain kernel. */
   const int sort_cfg = W.sort;
+  /* march_kernel<.., PRE>: request the next cell record one pass ahead.  Measured (B200): pays in the
+   * coherent kernel, whose in-warp sums sit between request and use (clumpy 256^3 30.1 -> 26.3 ms);
+   * the plain kernel is bound by L1TEX lanes, not latency (no gain; -16 % with the full layout's spills) */
+  int prefetch_cfg = -1;
+  if (const char *e = getenv("CMIB_PREFETCH")) prefetch_cfg = atoi(e) != 0;
   if (tuning) CUDA_OK(cudaStreamSynchronize(s)); /* buffers are allocated, earlier work is done: time the shoot alone */
   const auto tune_t0 = std::chrono::steady_clock::now();
   uint64_t items_bound = cap;
@@ -445,12 +474,18 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
         g_launches += 2 + (W.fine_key_bits + 8) / 8; /* onesweep: histogram, scan, one pass per 8 key bits */
       }
       stamp();
-      if (sort == 2 && W.agg) {
-        if (mode == ACC_HONLY) march_kernel<ACC_HONLY, true><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
-        else march_kernel<ACC_FULL, true><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
-      } else {
-        if (mode == ACC_HONLY) march_kernel<ACC_HONLY, false><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
-        else march_kernel<ACC_FULL, false><<<march_grid, MARCH_BLOCK, 0, s>>>(W);
+      {
+        const bool agg = (sort == 2 && W.agg);
+        const bool prefetch = prefetch_cfg < 0 ? agg : (prefetch_cfg != 0);
+#define CMIB_LAUNCH_MARCH(M, A, R) march_kernel<M, A, R><<<march_grid, MARCH_BLOCK, 0, s>>>(W)
+        if (mode == ACC_HONLY) {
+          if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, true, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, true, false); }
+          else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, false, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, false, false); }
+        } else {
+          if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, true, true); else CMIB_LAUNCH_MARCH(ACC_FULL, true, false); }
+          else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, false, true); else CMIB_LAUNCH_MARCH(ACC_FULL, false, false); }
+        }
+#undef CMIB_LAUNCH_MARCH
       }
       stamp();
       advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl);
@@ -708,7 +743,16 @@ int cmib_set_recombination_rates(cmib_context *ctx, int kind, const double *fixe
 int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, const double *weights,
                      double total_luminosity) {
   CHECK_CTX(ctx);
-  if (n <= 0 || !positions || !weights) CMIB_FAIL("need at least one discrete source");
+  if (n == 0) { /* PhotonSourceDistribution: None — only legal together with a continuous source */
+    ctx->src.n_sources = 0;
+    ctx->src.src_pos = nullptr;
+    ctx->src.src_cum = nullptr;
+    ctx->hot_replicas = 0;
+    ctx->discrete_luminosity = 0.;
+    ctx->update_source_weights();
+    return 0;
+  }
+  if (n < 0 || !positions || !weights) CMIB_FAIL("need at least one discrete source");
   /* PhotonSource.cpp:74-100 */
   std::vector<double> cum(n);
   for (int i = 0; i < n; ++i) cum[i] = (i > 0 ? cum[i - 1] : 0.) + weights[i];
@@ -744,9 +788,39 @@ int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, cons
   ctx->src.n_sources = n;
   ctx->src.src_pos = ctx->d_src_pos.p;
   ctx->src.src_cum = ctx->d_src_cum.p;
-  ctx->src.continuous_probability = 0.;
-  ctx->src.discrete_weight = 1.;
-  ctx->luminosity = total_luminosity;
+  ctx->discrete_luminosity = total_luminosity;
+  ctx->update_source_weights();
+  return 0;
+}
+
+int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, int spectrum_kind,
+                               double spectrum_param) {
+  CHECK_CTX(ctx);
+  if (kind == CMIB_CONTINUOUS_NONE) {
+    ctx->src.continuous_kind = CONTINUOUS_NONE;
+    ctx->continuous_luminosity = 0.;
+    ctx->update_source_weights();
+    return 0;
+  }
+  if (kind != CMIB_CONTINUOUS_ISOTROPIC) CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (!(luminosity > 0.)) CMIB_FAIL("the continuous source needs a positive luminosity (surface area x total flux)");
+  if (spectrum_kind == CMIB_SPECTRUM_MONOCHROMATIC) {
+    ctx->src.cont_spectrum_kind = SPECTRUM_MONOCHROMATIC;
+    ctx->src.cont_mono_frequency = spectrum_param;
+  } else if (spectrum_kind == CMIB_SPECTRUM_PLANCK) {
+    if (!(spectrum_param > 0.)) CMIB_FAIL("Planck temperature must be positive");
+    host::build_planck_table(spectrum_param, ctx->h_cont_planck);
+    CUDA_OK(ctx->d_cont_planck.upload(ctx->h_cont_planck.data(), ctx->h_cont_planck.size(), ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    ctx->src.cont_spectrum_kind = SPECTRUM_PLANCK;
+    ctx->src.cont_planck = ctx->d_cont_planck.p;
+    if (make_guides(ctx, ctx->h_cont_planck.data(), 1, ctx->d_cont_planck_guide, &ctx->src.cont_planck_guide)) return 1;
+  } else {
+    CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", spectrum_kind);
+  }
+  ctx->src.continuous_kind = CONTINUOUS_ISOTROPIC;
+  ctx->continuous_luminosity = luminosity;
+  ctx->update_source_weights();
   return 0;
 }
 
@@ -847,7 +921,7 @@ int cmib_update_reemission_probabilities(cmib_context *ctx) {
 int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, uint64_t seed,
                uint32_t iteration, double *totweight, double *typecount) {
   CHECK_CTX(ctx);
-  if (ctx->src.n_sources <= 0) CMIB_FAIL("no photon sources set");
+  if (ctx->src.n_sources <= 0 && ctx->src.continuous_kind == CONTINUOUS_NONE) CMIB_FAIL("no photon sources set");
   if (ensure_acc(ctx)) return 1;
   if (ctx->src.reemission_kind == REEMISSION_PHYSICAL && !ctx->reemit_prob_valid)
     if (cmib_update_reemission_probabilities(ctx)) return 1;
@@ -1066,12 +1140,13 @@ int cmib_sample_packets(cmib_context *ctx, int64_t n, uint64_t offset, uint64_t 
                         uint32_t iteration, double *pos, double *dir, double *nu, double *sigma,
                         double *sigma_He_corr, double *tau) {
   CHECK_CTX(ctx);
-  if (ctx->src.n_sources <= 0) CMIB_FAIL("no photon sources set");
+  if (ctx->src.n_sources <= 0 && ctx->src.continuous_kind == CONTINUOUS_NONE) CMIB_FAIL("no photon sources set");
   if (n <= 0) return 0;
   Scratch sc;
   cudaStream_t s = ctx->stream;
   SamplePacketsParams P;
   P.src = ctx->src;
+  P.geom = ctx->geom;
   P.n = n; P.offset = offset; P.seed = seed; P.iteration = iteration;
   CUDA_OK(sc.out(&P.pos, (size_t)n * 3));
   CUDA_OK(sc.out(&P.dir, (size_t)n * 3));

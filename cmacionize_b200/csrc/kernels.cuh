@@ -519,6 +519,7 @@ __global__ void __launch_bounds__(128) eval_balance_kernel(const __grid_constant
 
 struct SamplePacketsParams {
   SourceModel src;
+  GridGeom geom;
   int64_t n;
   uint64_t offset, seed;
   uint32_t iteration;
@@ -531,17 +532,13 @@ __global__ void sample_packets_kernel(const __grid_constant__ SamplePacketsParam
   const SourceModel &m = P.src;
   PacketRng rng;
   rng_init(rng, P.seed, P.iteration, P.offset + i);
-  double x = rng_uniform(rng);
-  x = rng_uniform(rng);
-  int isrc = 0;
-  while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
-  double dx, dy, dz;
-  random_direction(rng, dx, dy, dz);
-  const double nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
+  double px, py, pz, dx, dy, dz, nu;
+  int isrc;
+  emit_primary(m, P.geom, rng, px, py, pz, dx, dy, dz, nu, isrc);
   double s[NUM_IONS], sHe;
   packet_cross_sections<NUM_IONS>(m, nu, s, sHe);
   const double tau = -log(rng_uniform(rng));
-  for (int k = 0; k < 3; ++k) P.pos[3 * i + k] = m.src_pos[3 * isrc + k];
+  P.pos[3 * i] = px; P.pos[3 * i + 1] = py; P.pos[3 * i + 2] = pz;
   P.dir[3 * i] = dx; P.dir[3 * i + 1] = dy; P.dir[3 * i + 2] = dz;
   P.nu[i] = nu;
   for (int k = 0; k < NUM_IONS; ++k) P.sigma[i * NUM_IONS + k] = s[k];

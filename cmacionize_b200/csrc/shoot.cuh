@@ -155,17 +155,9 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
   double nu;
   int type = PACKET_PRIMARY;
   /* --- PhotonSource::get_random_photon --- */
-  double x = rng_uniform(rng);
-  (void)x; /* discrete vs continuous: continuous sources are not on this path */
-  x = rng_uniform(rng);
-  int isrc = 0;
-  while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
-  s.px = m.src_pos[3 * isrc];
-  s.py = m.src_pos[3 * isrc + 1];
-  s.pz = m.src_pos[3 * isrc + 2];
-  random_direction(rng, s.dx, s.dy, s.dz);
-  nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
-  const double weight = m.discrete_weight;
+  int isrc;
+  emit_primary(m, g, rng, s.px, s.py, s.pz, s.dx, s.dy, s.dz, nu, isrc);
+  const double weight = (isrc >= 0) ? m.discrete_weight : m.continuous_weight;
   packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
 
   bool alive = true;

@@ -6,6 +6,8 @@
  *   PhotonSource::get_random_direction     /root/reference/src/PhotonSource.hpp:141-148
  *   PhotonSource::set_cross_sections       /root/reference/src/PhotonSource.cpp:189-199
  *   PhotonSource::reemit                   ...:272-308
+ *   IsotropicContinuousPhotonSource::get_random_incoming_direction
+ *                                          /root/reference/src/IsotropicContinuousPhotonSource.hpp:106-180
  *   MonochromaticPhotonSourceSpectrum::get_random_frequency  MonochromaticPhotonSourceSpectrum.hpp:97-100
  *   PlanckPhotonSourceSpectrum::get_random_frequency         PlanckPhotonSourceSpectrum.cpp:149-165
  *   HydrogenLymanContinuumSpectrum::get_random_frequency     HydrogenLymanContinuumSpectrum.cpp:136-154
@@ -30,6 +32,7 @@ namespace cmib {
 
 enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
+enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
@@ -40,8 +43,16 @@ struct SourceModel {
   int n_sources;
   const double *src_pos;   /* [n_sources][3] */
   const double *src_cum;   /* cumulative probabilities, last == 1 */
-  double continuous_probability; /* 0: discrete sources only */
-  double discrete_weight;        /* 1 */
+  /* discrete vs continuous source (PhotonSource.cpp:100-131): probability 0.5 when both exist;
+   * packets of the two kinds carry different weights */
+  double continuous_probability; /* 0: discrete sources only, 1: continuous source only */
+  double discrete_weight;        /* 1 (0 without discrete sources) */
+  double continuous_weight;      /* L_continuous / L_discrete (1 without discrete sources) */
+  int continuous_kind;
+  int cont_spectrum_kind;        /* spectrum of the continuous source */
+  double cont_mono_frequency;
+  const double *cont_planck;
+  const uint16_t *cont_planck_guide;
   /* source spectrum */
   int spectrum_kind;
   double mono_frequency;
@@ -112,6 +123,49 @@ CMIB_HD void random_direction(PacketRng &rng, double &dx, double &dy, double &dz
   dz = cost;
 }
 
+/*
+ * IsotropicContinuousPhotonSource::get_random_incoming_direction (.hpp:106-180): a focus point
+ * uniform in the box (u[0..2]), an isotropic direction through it (u[3], u[4]); the packet starts
+ * where that line enters the box, moved inside the half-open box by at most one epsilon.
+ */
+CMIB_HD void isotropic_incoming(const GridGeom &g, const double *u, double &px, double &py, double &pz,
+                                double &dx, double &dy, double &dz) {
+  const double fx = g.anchor[0] + g.sides[0] * u[0];
+  const double fy = g.anchor[1] + g.sides[1] * u[1];
+  const double fz = g.anchor[2] + g.sides[2] * u[2];
+  const double cost = 2. * u[3] - 1.;
+  const double s2 = 1. - cost * cost;
+  const double sint = sqrt(s2 > 0. ? s2 : 0.);
+  const double phi = 2. * M_PI * u[4];
+  double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &sinp, &cosp);
+#else
+  cosp = cos(phi);
+  sinp = sin(phi);
+#endif
+  dx = sint * cosp;
+  dy = sint * sinp;
+  dz = cost;
+  const double tx = g.anchor[0] + g.sides[0], ty = g.anchor[1] + g.sides[1], tz = g.anchor[2] + g.sides[2];
+  const double lx = (dx < 0.) ? (tx - fx) / dx : ((dx > 0.) ? (g.anchor[0] - fx) / dx : -DBL_MAX);
+  const double ly = (dy < 0.) ? (ty - fy) / dy : ((dy > 0.) ? (g.anchor[1] - fy) / dy : -DBL_MAX);
+  const double lz = (dz < 0.) ? (tz - fz) / dz : ((dz > 0.) ? (g.anchor[2] - fz) / dz : -DBL_MAX);
+  const double lxy = (lx < ly) ? ly : lx;     /* std::max(lx, ly) */
+  const double maxl = (lxy < lz) ? lz : lxy;  /* std::max(.., lz) */
+  px = fx + maxl * dx;
+  py = fy + maxl * dy;
+  pz = fz + maxl * dz;
+  const double eps = DBL_EPSILON;
+  const double hx = tx - eps * g.sides[0], hy = ty - eps * g.sides[1], hz = tz - eps * g.sides[2];
+  px = (hx < px) ? hx : px; /* std::min(position, top - eps * side) */
+  py = (hy < py) ? hy : py;
+  pz = (hz < pz) ? hz : pz;
+  px = (px < g.anchor[0]) ? g.anchor[0] : px; /* std::max(position, anchor) */
+  py = (py < g.anchor[1]) ? g.anchor[1] : py;
+  pz = (pz < g.anchor[2]) ? g.anchor[2] : pz;
+}
+
 CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
   const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
@@ -158,6 +212,35 @@ CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng 
   const double x = rng_uniform(rng);
   const uint32_t inu = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
   return freq[inu] + (freq[inu + 1] - freq[inu]) * (x - cdf[inu]) / (cdf[inu + 1] - cdf[inu]);
+}
+
+/*
+ * PhotonSource::get_random_photon (PhotonSource.cpp:208-249) up to the cross sections: one draw
+ * decides between the discrete sources (source index, isotropic direction, frequency from their
+ * spectrum) and the continuous source (position + direction on the box surface, frequency from its
+ * own spectrum).  isrc = index of the discrete source, -1 for a packet of the continuous source.
+ */
+CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, PacketRng &rng, double &px, double &py,
+                          double &pz, double &dx, double &dy, double &dz, double &nu, int &isrc) {
+  double x = rng_uniform(rng);
+  if (x >= m.continuous_probability) {
+    x = rng_uniform(rng);
+    isrc = 0;
+    while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
+    px = m.src_pos[3 * isrc];
+    py = m.src_pos[3 * isrc + 1];
+    pz = m.src_pos[3 * isrc + 2];
+    random_direction(rng, dx, dy, dz);
+    nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
+  } else {
+    double u[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
+    isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
+    isrc = -1;
+    nu = (m.cont_spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.cont_planck, rng, m.cont_planck_guide)
+                                                   : m.cont_mono_frequency;
+  }
 }
 
 /* the five cumulative re-emission probabilities of a cell at temperature T */

@@ -215,12 +215,15 @@ __global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_
     order[atomicAdd(&hist[key[i]], 1u)] = (uint32_t)i;
 }
 
-/* meta word of a queue entry: uniforms consumed (32 bits) | packet type (8 bits) | source index + 1
- * of a primary, 0 for a re-emitted packet (24 bits) */
+/* meta word of a queue entry: uniforms consumed (32 bits) | packet type (7 bits) | emitted by the
+ * continuous source (1 bit: the packet keeps that source's weight through re-emissions) | source
+ * index + 1 of a primary of a discrete source, 0 otherwise (24 bits) */
+constexpr int META_CONTINUOUS = 0x80; /* in the type byte */
 CMIB_D uint64_t pack_meta(uint32_t ndraw, int type, int isrc = -1) {
   return ((uint64_t)(uint32_t)(isrc + 1) << 40) | ((uint64_t)(uint32_t)(type & 0xff) << 32) | ndraw;
 }
-CMIB_D int meta_type(uint64_t meta) { return (int)((meta >> 32) & 0xffu); }
+CMIB_D int meta_type(uint64_t meta) { return (int)((meta >> 32) & 0x7fu); }
+CMIB_D int meta_continuous(uint64_t meta) { return (int)((meta >> 32) & (uint64_t)META_CONTINUOUS); }
 CMIB_D int meta_source(uint64_t meta) { return (int)(meta >> 40) - 1; }
 
 constexpr int HOT_CELLS = 27;      /* 3 x 3 x 3 neighbourhood of a source cell */
@@ -288,6 +291,7 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
     double px = 0., py = 0., pz = 0., nu = 0.;
     uint64_t id = 0;
     int type = PACKET_ABSORBED;
+    int cont = 0;
     if (w < n_re) {
       px = W.rq[RQ_PX * cap + w];
       py = W.rq[RQ_PY * cap + w];
@@ -299,6 +303,7 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
       const uint64_t meta = (uint64_t)__double_as_longlong(W.rq[RQ_META * cap + w]);
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
       type = meta_type(meta);
+      cont = meta_continuous(meta);
       if (m.reemission_kind == REEMISSION_PHYSICAL) {
         const CellOpacity c = load_cell(P.cells, cell);
         double p[NUM_REEMIT];
@@ -316,9 +321,10 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
       }
       if (nu == 0.) {
         /* absorbed for good: IonizationPhotonShootJob.hpp:143-144 */
-        cnt.w_tot += m.discrete_weight;
+        const double weight = cont ? m.continuous_weight : m.discrete_weight;
+        cnt.w_tot += weight;
 #pragma unroll
-        for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? m.discrete_weight : 0.;
+        for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? weight : 0.;
       } else {
         emit = true;
       }
@@ -334,7 +340,7 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
         q[EQ_PX * cap] = px; q[EQ_PY * cap] = py; q[EQ_PZ * cap] = pz;
         q[EQ_NU * cap] = nu;
         q[EQ_ID * cap] = __longlong_as_double((long long)id);
-        q[EQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type));
+        q[EQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type | cont));
       }
     }
   }
@@ -366,10 +372,10 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_items; w += stride) {
     PacketRng rng;
-    double px, py, pz, nu;
+    double px, py, pz, nu, dx, dy, dz;
     uint64_t id;
-    int type = PACKET_PRIMARY;
-    int isrc_key = -1; /* source index of a primary, -1 for a re-emitted packet */
+    int type = PACKET_PRIMARY; /* | META_CONTINUOUS */
+    int isrc_key = -1; /* source index of a primary of a discrete source, -1 otherwise */
     if (w < n_eq) {
       px = W.eq[EQ_PX * cap + w];
       py = W.eq[EQ_PY * cap + w];
@@ -378,26 +384,17 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
       id = (uint64_t)__double_as_longlong(W.eq[EQ_ID * cap + w]);
       const uint64_t meta = (uint64_t)__double_as_longlong(W.eq[EQ_META * cap + w]);
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
-      type = meta_type(meta);
+      type = meta_type(meta) | meta_continuous(meta);
+      random_direction(rng, dx, dy, dz);
     } else {
       id = P.packet_offset + next_fresh + (w - n_eq);
       rng_init(rng, P.seed, P.iteration, id);
-      double x = rng_uniform(rng);
-      (void)x; /* discrete vs continuous draw: consumed as in the reference */
-      x = rng_uniform(rng);
-      int isrc = 0;
-      while (isrc < m.n_sources - 1 && x > m.src_cum[isrc]) ++isrc;
-      px = m.src_pos[3 * isrc];
-      py = m.src_pos[3 * isrc + 1];
-      pz = m.src_pos[3 * isrc + 2];
-      isrc_key = isrc;
-      nu = 0.;
+      emit_primary(m, P.geom, rng, px, py, pz, dx, dy, dz, nu, isrc_key);
+      if (isrc_key < 0) type |= META_CONTINUOUS;
     }
-    double dx, dy, dz, sigma_He_corr;
+    double sigma_He_corr;
     double sigma[NSIG];
     ++cnt.n_emit;
-    random_direction(rng, dx, dy, dz);
-    if (w >= n_eq) nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
     packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
     const double tau = -log(rng_uniform(rng));
     double *q = W.mq + w;
@@ -503,8 +500,16 @@ enum LaneState : int { LANE_EMPTY = 0, LANE_LIVE = 1, LANE_ABSORBED = 2, LANE_ES
  * are added per lane as in the plain kernel.
  */
 constexpr uint32_t AGG_METALS = (1u << ION_O_n) | (1u << ION_N_n);
+constexpr uint32_t MASK_METALS = 0x3ffcu;        /* bits 2..13 of a lane's mask word */
+constexpr uint32_t MASK_CONTINUOUS = 1u << 31;   /* packet of the continuous source: its weight differs */
 constexpr int AGG_GROUP = 8; /* lanes that are refilled together */
-template <int MODE, bool AGG>
+/*
+ * PRE: the cell record of the NEXT crossing is requested as soon as the packet's next cell is
+ * known (end of a crossing / end of a refill) and consumed one pass later, so that the gather's
+ * L2/DRAM latency overlaps the in-warp sums, the loop control and the wall distances of the next
+ * pass instead of stalling the optical-depth arithmetic right behind the load.
+ */
+template <int MODE, bool AGG, bool PRE>
 __global__ void __launch_bounds__(MARCH_BLOCK, 3)
 march_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
@@ -514,6 +519,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   __shared__ double s_sig[(NMETAL > 0 ? NMETAL + 1 : 1)][MARCH_BLOCK]; /* metals, then sigma_He */
   __shared__ unsigned long long s_id[MARCH_BLOCK], s_meta[MARCH_BLOCK];
   __shared__ double s_tau0[MARCH_BLOCK]; /* sampled optical depth, for the traversed-depth checksum */
+  __shared__ uint32_t s_ntype_c[NUM_PACKET_TYPES][MARCH_BLOCK]; /* ended packets of the continuous source */
   const ShootParams &P = W.sp;
   const GridGeom &g = P.geom;
   const uint64_t cap = W.capacity;
@@ -522,10 +528,18 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   const int tid = threadIdx.x;
   const bool can_reemit = (P.src.reemission_kind != REEMISSION_NONE);
   const bool any_periodic = (g.periodic[0] | g.periodic[1] | g.periodic[2]) != 0;
-  const double weight = P.src.discrete_weight;
+  const double w_discrete = P.src.discrete_weight, w_continuous = P.src.continuous_weight;
+#pragma unroll
+  for (int t = 0; t < NUM_PACKET_TYPES; ++t) s_ntype_c[t][tid] = 0u;
   const uint32_t ncx = (uint32_t)g.ncell[0], ncy = (uint32_t)g.ncell[1], ncz = (uint32_t)g.ncell[2];
   uint32_t n_type[NUM_PACKET_TYPES] = {0u, 0u, 0u, 0u};
   uint32_t n_steps = 0;
+  uint32_t mask = 0; /* metals (bits 2..13) with a non-zero cross section | MASK_CONTINUOUS */
+  /* a packet ended with type t: packets of the two kinds of source carry different weights */
+  auto count_end = [&](int t) {
+    if (mask & MASK_CONTINUOUS) ++s_ntype_c[t][tid];
+    else ++n_type[t];
+  };
 
   /* packet state */
   double px = 0., py = 0., pz = 0., dx = 1., dy = 1., dz = 1., ivx = 1., ivy = 1., ivz = 1.;
@@ -534,13 +548,25 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   double sigH = 0., sigHe_corr = 0., dnu_H = 0., dnu_He = 0.;
   int32_t ix = 0, iy = 0, iz = 0;
   uint32_t cell = 0;
-  uint32_t mask = 0; /* metals (bits 2..13) with a non-zero cross section */
   uint32_t hot = 0;  /* (hot record index of the packet's source + 1) << 2 | crossings made (saturating) */
   uint32_t hot_cell = 0; /* packed cell indices of that source */
   uint32_t nacc = 0; /* accumulator terms this packet adds per crossing (diagnostic for the roofline) */
   uint32_t n_red = 0;
   double tau_sum = 0.; /* optical depth traversed (checksum against sum_cells n (x_H J_H + A_He x_He J_He)) */
   int state = LANE_EMPTY;
+  double pre_n = 0., pre_xH = 0., pre_xHe = 0.; /* PRE: record of the cell the lane is in */
+  auto prefetch_cell = [&]() {
+    const uint32_t pc = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
+    if (MODE == ACC_HONLY) {
+      const double2 r0 = __ldg(P.cells_h + pc);
+      pre_n = r0.x; pre_xH = r0.y;
+    } else {
+      double t;
+      asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+          : "=d"(pre_n), "=d"(pre_xH), "=d"(pre_xHe), "=d"(t)
+          : "l"(P.cells + pc));
+    }
+  };
   bool warp_has_zero_dir = false; /* some lane's direction has a zero component (warp-uniform) */
   uint64_t cur = 0, end = 0;      /* warp-uniform cursor into the claimed chunk */
   const uint64_t nchunks = (qcount + MARCH_CHUNK - 1) / MARCH_CHUNK;
@@ -584,7 +610,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
          * packet has just entered (interact() returns the cell of the current index, :445-451) */
         fpx = px; fpy = py; fpz = pz;
         cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
-        if (!can_reemit) ++n_type[PACKET_ABSORBED];
+        if (!can_reemit) count_end(PACKET_ABSORBED);
       } else if (state == LANE_ABSORBED) {
         /* tau < 0 after the crossing: shorten it (CartesianDensityGrid.cpp:413-417) */
         const double nwx = xadd(px, xmul(ds, dx));
@@ -598,7 +624,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
         n_red += nacc;
         if (AGG) n_red += (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask & AGG_METALS); /* added per lane here */
-        const double dsw = dss * weight;
+        const double dsw = dss * ((mask & MASK_CONTINUOUS) ? w_continuous : w_discrete);
         double *a = P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC;
         const double dJH = dsw * sigH;
         if (dJH != 0.) {
@@ -613,7 +639,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             const double dh = dJHe * dnu_He;
             if (dh != 0.) atomicAdd(a + acc_slot(NUM_IONS + HEAT_He), dh);
           }
-          uint32_t mm = mask;
+          uint32_t mm = mask & MASK_METALS;
           while (mm) {
             const int k = __ffs(mm) - 1;
             mm &= mm - 1u;
@@ -621,9 +647,9 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             if (dJ != 0.) atomicAdd(a + acc_slot(k), dJ);
           }
         }
-        if (!can_reemit) ++n_type[PACKET_ABSORBED]; /* PhotonSource::reemit without a handler (:304-306) */
+        if (!can_reemit) count_end(PACKET_ABSORBED); /* PhotonSource::reemit without a handler (:304-306) */
       } else if (state == LANE_ESCAPED) {
-        ++n_type[meta_type(s_meta[tid])]; /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
+        count_end(meta_type(s_meta[tid])); /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
       }
       /* optical depth traversed by the walk that just ended: all of it when absorbed */
       if (state == LANE_ABSORBED || state == LANE_ESCAPED) tau_sum += s_tau0[tid] - ((tau > 0.) ? tau : 0.);
@@ -687,7 +713,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
               }
             }
             sigH = q[MQ_SIGMA * cap];
-            mask = 0;
+            mask = meta_continuous(s_meta[tid]) ? MASK_CONTINUOUS : 0u;
             if (MODE == ACC_FULL) {
               s_sig[NMETAL][tid] = q[(MQ_SIGMA + 1) * cap];
               sigHe_corr = q[(MQ_SIGMA + NSIG) * cap];
@@ -701,7 +727,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
             dnu_H = nu - P.nu_H;
             dnu_He = nu - P.nu_He;
             /* AGG: the warp-summed terms are counted where they are issued */
-            nacc = AGG ? __popc(mask & ~AGG_METALS) : (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask);
+            nacc = AGG ? __popc(mask & MASK_METALS & ~AGG_METALS) : (sigH != 0.) * (1u + (dnu_H != 0.)) + __popc(mask & MASK_METALS);
             if (MODE == ACC_FULL) nacc += (s_sig[NMETAL][tid] != 0.) * (1u + (dnu_He != 0.));
             ivx = 1. / dx;
             ivy = 1. / dy;
@@ -721,6 +747,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
               state = LANE_ESCAPED; /* emitted outside the box: interact() returns end() */
             }
             fx = (double)ix; fy = (double)iy; fz = (double)iz;
+            if (PRE && state == LANE_LIVE) prefetch_cell();
           }
           cur += ((uint64_t)nfill < avail) ? (uint64_t)nfill : avail;
         }
@@ -742,7 +769,9 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
       /* one gather per crossing: the 32-byte cell record is one sector; the H-only walk needs
        * (n, x_H) only = one 16-byte load, the full walk takes the sector as one 256-bit load */
       CellOpacity c;
-      if (MODE == ACC_HONLY) {
+      if (PRE) {
+        c.n = pre_n; c.xH = pre_xH; c.xHe = (MODE == ACC_HONLY) ? 0. : pre_xHe; c.T = 0.;
+      } else if (MODE == ACC_HONLY) {
         const double2 r0 = __ldg(P.cells_h + cell);
         c.n = r0.x; c.xH = r0.y; c.xHe = 0.; c.T = 0.;
       } else {
@@ -775,7 +804,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         if (c.n > 0.) {
           /* update_integrals (DensityGrid.hpp:150-197); zero increments are skipped (exact) */
           n_red += nacc;
-          const double dsw = ds * weight;
+          const double dsw = ds * ((mask & MASK_CONTINUOUS) ? w_continuous : w_discrete);
           /* accumulator record of this cell: its own, or — during the first crossings of a
            * primary, inside the 3x3x3 cells around its source — one of the replicas */
           double *a = (MODE == ACC_FULL) ? P.acc + ACC_COUNTERS + (size_t)cell * AccLayout<MODE>::NACC
@@ -817,7 +846,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
               const double dh = dJHe * dnu_He;
               if (dh != 0.) atomicAdd(a + acc_slot(NUM_IONS + HEAT_He), dh);
             }
-            uint32_t mm = AGG ? (mask & ~AGG_METALS) : mask;
+            uint32_t mm = AGG ? (mask & MASK_METALS & ~AGG_METALS) : (mask & MASK_METALS);
             while (mm) {
               const int k = __ffs(mm) - 1;
               mm &= mm - 1u;
@@ -851,6 +880,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
         }
         /* tau == 0 exactly: the walk ends inside (loop condition tau > 0, :391), on the wall */
         if (state == LANE_LIVE && !(tau > 0.)) state = LANE_ABSORBED;
+        if (PRE && state == LANE_LIVE) prefetch_cell();
       }
     }
     if constexpr (AGG) {
@@ -894,7 +924,7 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   cnt.tau_sum = tau_sum;
 #pragma unroll
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) {
-    cnt.w_type[t] = (double)n_type[t] * weight;
+    cnt.w_type[t] = (double)n_type[t] * w_discrete + (double)s_ntype_c[t][tid] * w_continuous;
     cnt.w_tot += cnt.w_type[t];
   }
   reduce_counters(P.acc, cnt);

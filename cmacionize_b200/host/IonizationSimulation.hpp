@@ -631,28 +631,50 @@ public:
     photon_source_spectrum_.reset(PhotonSourceSpectrum::generate("PhotonSourceSpectrum", parameter_file_, log_));
     if (photon_source_distribution_ && !photon_source_spectrum_)
       cmi_error("No spectrum provided for the discrete photon sources!");
-    if (parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None") != "None")
-      cmi_error("Continuous photon sources are not provided by the B200 backend!");
-    if (!photon_source_distribution_) cmi_error("No photon sources!");
+    /* ContinuousPhotonSourceFactory (src/ContinuousPhotonSourceFactory.hpp:69-100) and its spectrum
+     * (IonizationSimulation.cpp:164-174) */
+    const std::string continuous_type = parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None");
+    if (log_) log_->write_info("Requested ContinuousPhotonSource type: ", continuous_type, ".");
+    if (continuous_type != "None" && continuous_type != "Isotropic")
+      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic)!", continuous_type.c_str());
+    continuous_photon_source_spectrum_.reset(
+        PhotonSourceSpectrum::generate("ContinuousPhotonSourceSpectrum", parameter_file_, log_));
+    const bool has_continuous = (continuous_type == "Isotropic");
+    if (has_continuous && !continuous_photon_source_spectrum_)
+      cmi_error("No spectrum provided for the continuous photon sources!");
+    if (!photon_source_distribution_ && !has_continuous) cmi_error("No photon sources!");
+    double continuous_luminosity = 0.;
+    if (has_continuous) {
+      /* PhotonSource.cpp:101-108: total surface area (IsotropicContinuousPhotonSource.hpp:187-192) x total flux */
+      if (continuous_photon_source_spectrum_->total_flux < 0.) cmi_error("This function should not be used!");
+      const double area = 2. * box.sides[0] * box.sides[1] + 2. * box.sides[0] * box.sides[2] +
+                          2. * box.sides[1] * box.sides[2];
+      continuous_luminosity = area * continuous_photon_source_spectrum_->total_flux;
+    }
     reemission_ = DiffuseReemissionHandler::generate(parameter_file_, log_);
     const cmib_temperature_params tp = temperature_calculator_parameters(parameter_file_);
 
     /* configure every device context alike: PhotonSource ctor (PhotonSource.cpp:55-146) */
-    const size_t ns = photon_source_distribution_->get_number_of_sources();
+    const size_t ns = photon_source_distribution_ ? photon_source_distribution_->get_number_of_sources() : 0;
     std::vector<double> pos(3 * ns), w(ns);
     for (size_t i = 0; i < ns; ++i) {
       const Vec3 p = photon_source_distribution_->get_position(i);
       pos[3 * i] = p[0]; pos[3 * i + 1] = p[1]; pos[3 * i + 2] = p[2];
       w[i] = photon_source_distribution_->get_weight(i);
     }
-    total_luminosity_ = photon_source_distribution_->get_total_luminosity();
+    const double discrete_luminosity = photon_source_distribution_ ? photon_source_distribution_->get_total_luminosity() : 0.;
+    total_luminosity_ = discrete_luminosity + continuous_luminosity;
     for (auto &grid : density_grids_) {
       cmib_context *ctx = grid->context();
       CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
       CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
       CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
-      CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), total_luminosity_));
-      CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
+      CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), discrete_luminosity));
+      if (ns > 0) CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
+      if (has_continuous)
+        CMIB_CALL(cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_ISOTROPIC, continuous_luminosity,
+                                             continuous_photon_source_spectrum_->kind,
+                                             continuous_photon_source_spectrum_->param));
       CMIB_CALL(cmib_set_reemission(ctx, reemission_.kind, reemission_.probability, reemission_.frequency));
       CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
     }
@@ -824,6 +846,7 @@ private:
   std::vector<ncclComm_t> comms_;
   std::unique_ptr<PhotonSourceDistribution> photon_source_distribution_;
   std::unique_ptr<PhotonSourceSpectrum> photon_source_spectrum_;
+  std::unique_ptr<PhotonSourceSpectrum> continuous_photon_source_spectrum_;
   DiffuseReemissionHandler reemission_;
   std::unique_ptr<AsciiFileDensityGridWriter> density_grid_writer_;
   std::string output_folder_;

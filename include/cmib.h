@@ -56,6 +56,7 @@ typedef struct cmib_grid_desc {
 enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
 enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
 enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1 };
+enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1 };
 enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
 
 /* TemperatureCalculator parameters (src/TemperatureCalculator.cpp:133-160) */
@@ -118,6 +119,16 @@ int cmib_set_sources(cmib_context *ctx, int32_t n_sources, const double *positio
 /* PhotonSourceSpectrumFactory (src/PhotonSourceSpectrumFactory.hpp:84-152): param is the
  * frequency (Hz) for MONOCHROMATIC, the black-body temperature (K) for PLANCK */
 int cmib_set_spectrum(cmib_context *ctx, int kind, double param);
+/* ContinuousPhotonSourceFactory (src/ContinuousPhotonSourceFactory.hpp:69-100) + its spectrum
+ * (PhotonSourceSpectrumFactory with role "ContinuousPhotonSourceSpectrum"): kind ISOTROPIC =
+ * IsotropicContinuousPhotonSource (src/IsotropicContinuousPhotonSource.hpp:106-180: packets enter
+ * through the faces of the box); luminosity (s^-1) = total surface area x total flux of the spectrum
+ * (PhotonSource.cpp:101-108); spectrum_kind / spectrum_param as for cmib_set_spectrum.  With
+ * discrete sources present half of the packets come from the continuous source and carry the
+ * weight L_continuous / L_discrete (PhotonSource.cpp:113-131); cmib_set_sources may be called with
+ * n_sources = 0 (PhotonSourceDistribution: None) when this is set.  kind NONE removes it. */
+int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, int spectrum_kind,
+                               double spectrum_param);
 /* DiffuseReemissionHandlerFactory (src/DiffuseReemissionHandlerFactory.hpp:59-107);
  * probability / frequency (Hz) are used by FIXED_VALUE only.  Builds the H-Lyc /
  * He-Lyc / He-2-photon tables from the CURRENT cross sections, as the reference's

@@ -206,6 +206,15 @@ def sample_spectrum(which, temperature, n, seed=42):
     return nu
 
 
+def isotropic_incoming(anchor, sides, n, seed=42):
+    """(uniforms [n,5], positions [n,3], directions [n,3]) of IsotropicContinuousPhotonSource"""
+    a = np.ascontiguousarray(anchor, dtype=np.float64)
+    sd = np.ascontiguousarray(sides, dtype=np.float64)
+    u, pos, d = np.empty((n, 5)), np.empty((n, 3)), np.empty((n, 3))
+    lib().cmi_ref_isotropic_incoming(_p(a), _p(sd), C.c_int(seed), C.c_int64(n), _p(u), _p(pos), _p(d))
+    return u, pos, d
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

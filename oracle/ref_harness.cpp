@@ -48,6 +48,7 @@
 #include "HydrogenLymanContinuumSpectrum.hpp"
 #include "IonizationSimulation.hpp"
 #include "IonizationStateCalculator.hpp"
+#include "IsotropicContinuousPhotonSource.hpp"
 #include "LineCoolingData.hpp"
 #include "Photon.hpp"
 #include "PhotonSource.hpp"
@@ -572,6 +573,26 @@ void cmi_ref_sample_spectrum(int which, double temperature, int seed, int64_t n,
   } else {
     HeliumTwoPhotonContinuumSpectrum sp;
     for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, temperature);
+  }
+}
+
+/* IsotropicContinuousPhotonSource::get_random_incoming_direction (src/IsotropicContinuousPhotonSource.hpp:106-180)
+ * n times with RandomGenerator(seed); `uniforms` receives the five deviates each call consumed
+ * (a second generator with the same seed replays the stream), so that a re-implementation can be
+ * fed exactly the same numbers. */
+void cmi_ref_isotropic_incoming(const double *anchor, const double *sides, int seed, int64_t n,
+                                double *uniforms, double *pos, double *dir) {
+  const Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]),
+                  CoordinateVector<>(sides[0], sides[1], sides[2]));
+  IsotropicContinuousPhotonSource source(box);
+  RandomGenerator rg(seed), replay(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 5; ++k) uniforms[5 * i + k] = replay.get_uniform_random_double();
+    const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = pd.first[k];
+      dir[3 * i + k] = pd.second[k];
+    }
   }
 }
 

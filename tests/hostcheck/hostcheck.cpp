@@ -139,6 +139,16 @@ void hc_temperature(int64_t n, double jfac, double hfac, const double *abund, in
   }
 }
 
+void hc_isotropic_incoming(const double *anchor, const double *sides, int64_t n, const double *uniforms,
+                           double *pos, double *dir) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) { g.anchor[d] = anchor[d]; g.sides[d] = sides[d]; }
+  for (int64_t i = 0; i < n; ++i)
+    isotropic_incoming(g, uniforms + 5 * i, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1],
+                       dir[3 * i + 2]);
+}
+
 void hc_planck_tables(double temperature, double *out) {
   std::vector<double> t;
   host::build_planck_table(temperature, t);

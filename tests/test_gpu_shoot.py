@@ -168,7 +168,8 @@ def test_shoot_is_deterministic_and_shardable(cmib):
     ctx.close()
 
 
-@pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic"])
+@pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
+                                    "continuous", "continuous_only"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -189,6 +190,16 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     elif config == "fixed_reemission":
         prob = problems.stromgren(ncell=16, n_packets=npk)
         prob.ctx.set_reemission(capi.REEMISSION_FIXED_VALUE, 0.364, problems.ev_to_hz(19.8))
+    elif config == "continuous":
+        # star + isotropic external field (half of the packets each, the external ones weigh
+        # L_c / L_d = 0.25 and keep that weight through their re-emissions)
+        prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 0.25 * 4.26e49, capi.SPECTRUM_MONOCHROMATIC,
+                                       problems.ev_to_hz(13.6))
+    elif config == "continuous_only":
+        prob = problems.lexington(20, ncell=24, n_packets=npk)
+        prob.ctx.set_sources(None, None, 0.)
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 1e49, capi.SPECTRUM_PLANCK, 30000.)
     else:
         # non-cubic box, periodic in x and z, three sources (one outside the box: its packets
         # are lost immediately, as in the reference), Physical re-emission
@@ -227,13 +238,17 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     os.environ.pop("CMIB_SORT", None)
     ctx.close()
     tw0, tc0, st0, J0, h0 = results[0]
-    assert tw0 == npk and tc0.sum() == npk
+    if config == "continuous":
+        ncont = round((npk - tw0) / 0.75)  # tw = n_discrete + 0.25 n_continuous
+        assert abs(ncont - 0.5 * npk) < 5 * np.sqrt(0.25 * npk) and abs(tc0.sum() - tw0) < 1e-9 * tw0
+    else:
+        assert tw0 == npk and tc0.sum() == npk
     if config == "periodic":
         assert 0.05 * npk < tc0[0] < 0.5 * npk   # the 10 % emitted outside + escapes through the y faces
     if config != "stromgren":
         assert st0[1] > 1.05 * npk  # re-emission happened
     for tw, tc, st, J, h in results[1:]:
-        assert tw == tw0 and np.array_equal(tc, tc0) and st == st0
+        assert abs(tw - tw0) <= 1e-12 * tw0 and np.abs(tc - tc0).max() <= 1e-12 * tw0 and st == st0
         for k in range(14):
             assert np.abs(J[k] - J0[k]).max() <= 1e-12 * max(J0[k].max(), 1e-300), k
         for k in range(2):
@@ -280,3 +295,65 @@ def test_full_size_checksum_of_the_accumulation(cmib, config):
     # mean optical depth per emission is ~1 for absorbed packets and < 1 for escaping ones
     assert 0.05 < tau / emissions < 1.05
     assert (J[0][n > 0] > 0).mean() > 0.2 and (heat[0] >= 0).all()
+
+
+def test_continuous_source_shoot_equals_oracle(cmib, ref):
+    """Star + IsotropicContinuousPhotonSource (PhotonSource.cpp:113-131, 208-249: half of the packets
+    each, an external packet weighs L_c / L_d).  The exported packets, with their weights, pushed
+    through the oracle's interact() give shoot's accumulators; the external packets start on the
+    faces of the box, point inwards, and are distributed like the reference's own sampler's."""
+    from cmacionize_b200 import capi
+    anchor, sides, nc3 = [-3 * PC, -2 * PC, -1 * PC], [6 * PC, 4 * PC, 2 * PC], [24, 16, 8]
+    with cmib.Context(anchor, sides, nc3) as ctx:
+        nc = ctx.ncells
+        ctx.set_abundances(*ABUNDANCES)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_sources([[0., 0., 0.]], [1.], 1e49)
+        ctx.set_spectrum(capi.SPECTRUM_PLANCK, 40000.)
+        ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 3e48, capi.SPECTRUM_PLANCK, 25000.)
+        rng = np.random.default_rng(5)
+        n = 1e8 * np.exp(rng.normal(0, 0.5, nc))
+        x = np.zeros((14, nc))
+        x[0] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), nc))
+        x[1] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), nc))
+        ctx.upload_cells(n, np.full(nc, 8000.), x)
+        ctx.reset_accumulators()
+        npk = 40000
+        tw, tc = ctx.shoot(npk, seed=11, iteration=0)
+        J, heat = ctx.download_accumulators()
+        pk = ctx.sample_packets(npk, seed=11, iteration=0)
+        external = ~np.all(pk["pos"] == 0., axis=1)
+        w = np.where(external, 0.3, 1.)
+        assert abs(external.mean() - 0.5) < 5 * 0.5 / np.sqrt(npk)
+        assert abs(tw - w.sum()) <= 1e-9 * tw and abs(tc.sum() - tw) <= 1e-9 * tw
+        r = ref.interact(anchor, sides, nc3, [0, 0, 0], n, x[0], x[1], pk["pos"], pk["dir"], pk["sigma"],
+                         pk["sigma_He_corr"], pk["nu"], w, pk["tau"])
+        for k in range(14):
+            assert np.abs(J[k] - r["J"][k]).max() <= 1e-11 * max(r["J"][k].max(), 1e-300), k
+        for k in range(2):
+            assert np.abs(heat[k] - r["heat"][k]).max() <= 1e-11 * np.abs(r["heat"][k]).max()
+        # the two spectra: external packets are softer (25000 K vs 40000 K)
+        assert pk["nu"][external].mean() < 0.9 * pk["nu"][~external].mean()
+        # external packets only, against the reference's sampler
+        ctx.set_sources(None, None, 0.)
+        m = 400000
+        pk = ctx.sample_packets(m, seed=3)
+        a, sd = np.array(anchor), np.array(sides)
+        u, rpos, rdir = ref.isotropic_incoming(anchor, sides, m, seed=3)
+
+        def face_stats(pos, d):
+            lo = np.isclose(pos, a, rtol=0, atol=1e-9 * sd)
+            hi = np.isclose(pos, a + sd, rtol=0, atol=1e-9 * sd)
+            assert (lo | hi).any(axis=1).all()
+            inward = np.where(lo, d, np.where(hi, -d, np.nan))
+            assert np.nanmin(inward) >= 0.
+            frac = np.array([(lo[:, k] | hi[:, k]).mean() for k in range(3)])
+            mu = np.array([np.nanmean(inward[:, k]) for k in range(3)])
+            return frac, mu
+
+        assert (pk["pos"] >= a).all() and (pk["pos"] < a + sd).all()
+        f1, mu1 = face_stats(pk["pos"], pk["dir"])
+        f2, mu2 = face_stats(rpos, rdir)
+        assert np.abs(f1 - f2).max() < 5 * np.sqrt(2 * 0.25 / m)
+        assert np.abs(mu1 - mu2).max() < 5e-3
+        assert np.abs(np.linalg.norm(pk["dir"], axis=1) - 1.).max() < 1e-14

@@ -172,3 +172,21 @@ def test_wall_intersection_scenarios_of_the_reference_unit_test(hostcheck, ref):
                                p(c["tau"]), p(J), p(heat), p(fp), p(fc), p(ns), C.c_int32(mt), p(tr))
     check_wall_intersection_scenarios(c, fp, fc, ns, tr, J)
     assert np.array_equal(fp, r["final_pos"]) and np.array_equal(tr, r["trace"])
+
+
+def test_isotropic_continuous_source_bitexact(hostcheck, ref):
+    """IsotropicContinuousPhotonSource::get_random_incoming_direction fed with the reference
+    generator's own deviates: start position on the box surface and direction, bit for bit
+    (boxes off the origin, non-cubic; the start must lie in the half-open box)."""
+    for anchor, sides in (([-5., -5., -5.], [10., 10., 10.]), ([1e17, -3e17, 2e16], [2e17, 5e17, 3e17])):
+        u, pos, d = ref.isotropic_incoming(anchor, sides, 20000, seed=7)
+        pos2, d2 = np.empty_like(pos), np.empty_like(d)
+        a, sd = np.array(anchor), np.array(sides)
+        hostcheck.hc_isotropic_incoming(p(a), p(sd), C.c_int64(len(u)), p(np.ascontiguousarray(u)), p(pos2), p(d2))
+        assert np.array_equal(d2, d)
+        assert np.array_equal(pos2, pos)
+        assert (pos2 >= a).all() and (pos2 < a + sd).all()
+        on_face = (np.isclose(pos2, a, rtol=0, atol=1e-12 * sd) | np.isclose(pos2, a + sd, rtol=0, atol=1e-12 * sd)).any(axis=1)
+        assert on_face.all()
+        inward = np.where(np.isclose(pos2, a, rtol=0, atol=1e-12 * sd), d2, np.where(np.isclose(pos2, a + sd, rtol=0, atol=1e-12 * sd), -d2, 1.))
+        assert (inward >= 0.).all()
