@@ -23,7 +23,7 @@ ION_NAMES = ["H_n", "He_n", "C_p1", "C_p2", "N_n", "N_p1", "N_p2", "O_n", "O_p1"
 
 CROSS_SECTIONS_FIXED_VALUE, CROSS_SECTIONS_VERNER = 0, 1
 RECOMBINATION_FIXED_VALUE, RECOMBINATION_VERNER = 0, 1
-SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK = 0, 1
+SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK, SPECTRUM_UNIFORM, SPECTRUM_TABULATED = 0, 1, 2, 3
 CONTINUOUS_NONE, CONTINUOUS_ISOTROPIC = 0, 1
 REEMISSION_NONE, REEMISSION_PHYSICAL, REEMISSION_FIXED_VALUE = 0, 1, 2
 
@@ -184,6 +184,13 @@ class Context:
         assert pos.shape[0] == w.size
         _check(lib.cmib_set_sources(self._h, C.c_int32(w.size), _p(pos), _p(w),
                                     C.c_double(total_luminosity)))
+
+    def set_spectrum_table(self, frequencies, cumulative_distribution, role=0):
+        """A tabulated spectrum (FaucherGiguere, WMBasic, ... : include/cmib.h); role 0 = discrete sources,
+        1 = continuous source."""
+        f, c = _f64(frequencies).reshape(-1), _f64(cumulative_distribution).reshape(-1)
+        assert f.size == c.size
+        _check(lib.cmib_set_spectrum_table(self._h, C.c_int(role), C.c_int32(f.size), _p(f), _p(c)))
 
     def set_continuous_source(self, kind, luminosity=0., spectrum_kind=0, spectrum_param=0.):
         """IsotropicContinuousPhotonSource + its spectrum (include/cmib.h); luminosity = total surface

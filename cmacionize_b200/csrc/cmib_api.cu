@@ -112,6 +112,7 @@ struct cmib_context {
   DevBuf<double> d_cont_planck;
   DevBuf<uint16_t> d_cont_planck_guide;
   std::vector<double> h_cont_planck;
+  DevBuf<double> d_spec_freq[2], d_spec_cdf[2]; /* tabulated spectra: [0] discrete sources, [1] continuous source */
   /* PhotonSource.cpp:110-131: probability of a continuous packet and the two packet weights */
   void update_source_weights() {
     luminosity = discrete_luminosity + continuous_luminosity;
@@ -286,6 +287,29 @@ struct Scratch {
 
 
 namespace {
+
+/* PhotonSourceSpectrumFactory (src/PhotonSourceSpectrumFactory.hpp:84-152) for the closed-form and
+ * Planck spectra; tabulated ones come through cmib_set_spectrum_table */
+int set_spectrum_model(cmib_context *ctx, SpectrumModel &sp, std::vector<double> &h_planck, DevBuf<double> &d_planck,
+                       DevBuf<uint16_t> &d_guide, int kind, double param) {
+  if (kind == CMIB_SPECTRUM_MONOCHROMATIC) {
+    sp.kind = SPECTRUM_MONOCHROMATIC;
+    sp.mono_frequency = param;
+  } else if (kind == CMIB_SPECTRUM_PLANCK) {
+    if (!(param > 0.)) CMIB_FAIL("Planck temperature must be positive");
+    host::build_planck_table(param, h_planck);
+    CUDA_OK(d_planck.upload(h_planck.data(), h_planck.size(), ctx->stream));
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    sp.kind = SPECTRUM_PLANCK;
+    sp.planck = d_planck.p;
+    if (make_guides(ctx, h_planck.data(), 1, d_guide, &sp.planck_guide)) return 1;
+  } else if (kind == CMIB_SPECTRUM_UNIFORM) {
+    sp.kind = SPECTRUM_UNIFORM;
+  } else {
+    CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", kind);
+  }
+  return 0;
+}
 
 uint64_t default_queue_capacity() {
   const char *e = getenv("CMIB_QUEUE_CAPACITY");
@@ -585,8 +609,8 @@ int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
   memset(&ctx->src, 0, sizeof(ctx->src));
   ctx->src.discrete_weight = 1.;
   ctx->src.xs_kind = XS_VERNER;
-  ctx->src.spectrum_kind = SPECTRUM_MONOCHROMATIC;
-  ctx->src.mono_frequency = ev_to_hz(13.6);
+  ctx->src.spectrum.kind = SPECTRUM_MONOCHROMATIC;
+  ctx->src.spectrum.mono_frequency = ev_to_hz(13.6);
   ctx->src.reemission_kind = REEMISSION_NONE;
   memset(&ctx->rr, 0, sizeof(ctx->rr));
   ctx->rr.kind = RR_VERNER;
@@ -804,20 +828,11 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
   }
   if (kind != CMIB_CONTINUOUS_ISOTROPIC) CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
   if (!(luminosity > 0.)) CMIB_FAIL("the continuous source needs a positive luminosity (surface area x total flux)");
-  if (spectrum_kind == CMIB_SPECTRUM_MONOCHROMATIC) {
-    ctx->src.cont_spectrum_kind = SPECTRUM_MONOCHROMATIC;
-    ctx->src.cont_mono_frequency = spectrum_param;
-  } else if (spectrum_kind == CMIB_SPECTRUM_PLANCK) {
-    if (!(spectrum_param > 0.)) CMIB_FAIL("Planck temperature must be positive");
-    host::build_planck_table(spectrum_param, ctx->h_cont_planck);
-    CUDA_OK(ctx->d_cont_planck.upload(ctx->h_cont_planck.data(), ctx->h_cont_planck.size(), ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    ctx->src.cont_spectrum_kind = SPECTRUM_PLANCK;
-    ctx->src.cont_planck = ctx->d_cont_planck.p;
-    if (make_guides(ctx, ctx->h_cont_planck.data(), 1, ctx->d_cont_planck_guide, &ctx->src.cont_planck_guide)) return 1;
-  } else {
-    CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", spectrum_kind);
-  }
+  /* CMIB_SPECTRUM_TABULATED: the table was (or will be) given with cmib_set_spectrum_table(ctx, 1, ...) */
+  if (spectrum_kind != CMIB_SPECTRUM_TABULATED &&
+      set_spectrum_model(ctx, ctx->src.cont_spectrum, ctx->h_cont_planck, ctx->d_cont_planck, ctx->d_cont_planck_guide,
+                         spectrum_kind, spectrum_param))
+    return 1;
   ctx->src.continuous_kind = CONTINUOUS_ISOTROPIC;
   ctx->continuous_luminosity = luminosity;
   ctx->update_source_weights();
@@ -826,20 +841,25 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
 
 int cmib_set_spectrum(cmib_context *ctx, int kind, double param) {
   CHECK_CTX(ctx);
-  if (kind == CMIB_SPECTRUM_MONOCHROMATIC) {
-    ctx->src.spectrum_kind = SPECTRUM_MONOCHROMATIC;
-    ctx->src.mono_frequency = param;
-  } else if (kind == CMIB_SPECTRUM_PLANCK) {
-    if (!(param > 0.)) CMIB_FAIL("Planck temperature must be positive");
-    host::build_planck_table(param, ctx->h_planck);
-    CUDA_OK(ctx->d_planck.upload(ctx->h_planck.data(), ctx->h_planck.size(), ctx->stream));
-    CUDA_OK(cudaStreamSynchronize(ctx->stream));
-    ctx->src.spectrum_kind = SPECTRUM_PLANCK;
-    ctx->src.planck = ctx->d_planck.p;
-    if (make_guides(ctx, ctx->h_planck.data(), 1, ctx->d_planck_guide, &ctx->src.planck_guide)) return 1;
-  } else {
-    CMIB_FAIL("Unknown PhotonSourceSpectrum type: %d", kind);
-  }
+  return set_spectrum_model(ctx, ctx->src.spectrum, ctx->h_planck, ctx->d_planck, ctx->d_planck_guide, kind, param);
+}
+
+int cmib_set_spectrum_table(cmib_context *ctx, int role, int32_t n, const double *frequencies,
+                            const double *cumulative_distribution) {
+  CHECK_CTX(ctx);
+  if (role != 0 && role != 1) CMIB_FAIL("role must be 0 (PhotonSourceSpectrum) or 1 (ContinuousPhotonSourceSpectrum)");
+  if (n < 2 || !frequencies || !cumulative_distribution) CMIB_FAIL("a tabulated spectrum needs at least two frequencies");
+  for (int32_t i = 1; i < n; ++i)
+    if (cumulative_distribution[i] < cumulative_distribution[i - 1])
+      CMIB_FAIL("the cumulative distribution of a tabulated spectrum must not decrease (entry %d)", (int)i);
+  CUDA_OK(ctx->d_spec_freq[role].upload(frequencies, (size_t)n, ctx->stream));
+  CUDA_OK(ctx->d_spec_cdf[role].upload(cumulative_distribution, (size_t)n, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  SpectrumModel &sp = role ? ctx->src.cont_spectrum : ctx->src.spectrum;
+  sp.kind = SPECTRUM_TABULATED;
+  sp.n = n;
+  sp.freq = ctx->d_spec_freq[role].p;
+  sp.cdf = ctx->d_spec_cdf[role].p;
   return 0;
 }
 
@@ -1391,7 +1411,7 @@ int cmib_sample_spectrum(cmib_context *ctx, int which, double temperature, uint6
                          double *nu) {
   CHECK_CTX(ctx);
   if (n <= 0) return 0;
-  if (which != 0 && ctx->src.reemission_kind != REEMISSION_PHYSICAL)
+  if (which != 0 && which != 4 && ctx->src.reemission_kind != REEMISSION_PHYSICAL)
     CMIB_FAIL("diffuse spectra need the Physical reemission handler");
   Scratch sc;
   cudaStream_t s = ctx->stream;

@@ -553,7 +553,8 @@ __global__ void sample_spectrum_kernel(SourceModel m, int which, double T, uint6
   PacketRng rng;
   rng_init(rng, seed, 0u, (uint64_t)i);
   double v;
-  if (which == 0) v = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
+  if (which == 0) v = spectrum_frequency(m.spectrum, rng);
+  else if (which == 4) v = spectrum_frequency(m.cont_spectrum, rng);
   else if (which == 1) v = lyc_frequency(m.hlyc_freq, m.hlyc_temp, m.hlyc_cdf, T, rng, m.hlyc_guide);
   else if (which == 2) v = lyc_frequency(m.helyc_freq, m.helyc_temp, m.helyc_cdf, T, rng, m.helyc_guide);
   else v = he2pc_frequency(m.he2pc_freq, m.he2pc_cdf, rng, m.he2pc_guide);

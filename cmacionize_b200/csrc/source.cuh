@@ -30,12 +30,28 @@
 
 namespace cmib {
 
-enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1 };
+enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1, SPECTRUM_UNIFORM = 2, SPECTRUM_TABULATED = 3 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
 enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
+
+/*
+ * A PhotonSourceSpectrum as the device sees it.  MONOCHROMATIC and UNIFORM are closed forms, PLANCK
+ * keeps the reference's log-log table; TABULATED is the form every other spectrum of the reference
+ * samples from (FaucherGiguere, WMBasic, PopStar, Pegase3, CastelliKurucz, Masked: a frequency grid
+ * and its cumulative distribution, inverted with linear interpolation), so any of them runs on the
+ * device once its two arrays are handed over (cmib_set_spectrum_table).
+ */
+struct SpectrumModel {
+  int kind;
+  double mono_frequency;
+  const double *planck;         /* [3][1000]: cdf, log10 cdf, log10 nu/13.6eV */
+  const uint16_t *planck_guide; /* bracket guide of the CDF search (locate_guided); NULL = plain bisection */
+  int n;                        /* TABULATED: number of frequencies */
+  const double *freq, *cdf;     /* TABULATED: [n], [n] */
+};
 
 /* everything the emission / re-emission code needs; pointers are device pointers */
 struct SourceModel {
@@ -49,14 +65,8 @@ struct SourceModel {
   double discrete_weight;        /* 1 (0 without discrete sources) */
   double continuous_weight;      /* L_continuous / L_discrete (1 without discrete sources) */
   int continuous_kind;
-  int cont_spectrum_kind;        /* spectrum of the continuous source */
-  double cont_mono_frequency;
-  const double *cont_planck;
-  const uint16_t *cont_planck_guide;
-  /* source spectrum */
-  int spectrum_kind;
-  double mono_frequency;
-  const double *planck; /* [3][1000]: cdf, log10 cdf, log10 nu/13.6eV */
+  SpectrumModel cont_spectrum;   /* spectrum of the continuous source */
+  SpectrumModel spectrum;        /* spectrum of the discrete sources */
   /* cross sections */
   int xs_kind;
   double xs_fixed[NUM_IONS];
@@ -69,7 +79,7 @@ struct SourceModel {
   const double *helyc_freq, *helyc_temp, *helyc_cdf; /* same shapes */
   const double *he2pc_freq, *he2pc_cdf;              /* [1000], [1000] */
   /* bracket guides of the CDF searches (locate_guided); NULL = plain bisection */
-  const uint16_t *planck_guide, *hlyc_guide, *helyc_guide, *he2pc_guide; /* [rows][GUIDE_N + 1] */
+  const uint16_t *hlyc_guide, *helyc_guide, *he2pc_guide; /* [rows][GUIDE_N + 1] */
 };
 
 /* Utilities::locate: bisection, result clamped to [0, length-2] */
@@ -175,6 +185,24 @@ CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_
   return fpow(10., lf) * 3.288465385e15; /* device: exp(lf ln 10), cmib_common.cuh */
 }
 
+/* PhotonSourceSpectrum::get_random_frequency of the source spectra:
+ *   Monochromatic  MonochromaticPhotonSourceSpectrum.hpp:97-100 (no deviate consumed)
+ *   Planck         PlanckPhotonSourceSpectrum.cpp:149-165
+ *   Uniform        UniformPhotonSourceSpectrum.hpp:50-53
+ *   tabulated      e.g. FaucherGiguerePhotonSourceSpectrum.cpp:234-247, WMBasicPhotonSourceSpectrum.cpp:236-248,
+ *                  MaskedPhotonSourceSpectrum.cpp:123-135 */
+CMIB_HD double uniform_frequency(double x) { return (1. + 3. * x) * 3.289e15; }
+CMIB_HD double tabulated_frequency(const double *freq, const double *cdf, uint32_t n, double x) {
+  const uint32_t inu = locate(x, cdf, n);
+  return freq[inu] + (freq[inu + 1] - freq[inu]) * (x - cdf[inu]) / (cdf[inu + 1] - cdf[inu]);
+}
+CMIB_HD double spectrum_frequency(const SpectrumModel &sp, PacketRng &rng) {
+  if (sp.kind == SPECTRUM_PLANCK) return planck_frequency(sp.planck, rng, sp.planck_guide);
+  if (sp.kind == SPECTRUM_UNIFORM) return uniform_frequency(rng_uniform(rng));
+  if (sp.kind == SPECTRUM_TABULATED) return tabulated_frequency(sp.freq, sp.cdf, (uint32_t)sp.n, rng_uniform(rng));
+  return sp.mono_frequency;
+}
+
 /* Utilities::locate on two arrays of the same length at once: the two bisections are independent,
  * running them in lock step puts their (L2-latency bound) loads in flight together */
 CMIB_HD void locate2(double x, const double *a, const double *b, uint32_t length, uint32_t &ja, uint32_t &jb) {
@@ -231,15 +259,14 @@ CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, PacketRng &rn
     py = m.src_pos[3 * isrc + 1];
     pz = m.src_pos[3 * isrc + 2];
     random_direction(rng, dx, dy, dz);
-    nu = (m.spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.planck, rng, m.planck_guide) : m.mono_frequency;
+    nu = spectrum_frequency(m.spectrum, rng);
   } else {
     double u[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
     isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
     isrc = -1;
-    nu = (m.cont_spectrum_kind == SPECTRUM_PLANCK) ? planck_frequency(m.cont_planck, rng, m.cont_planck_guide)
-                                                   : m.cont_mono_frequency;
+    nu = spectrum_frequency(m.cont_spectrum, rng);
   }
 }
 

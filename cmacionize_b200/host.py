@@ -72,6 +72,15 @@ class ParameterFile:
         _check(lib.cmih_paramfile_used_values(self._h, buf, 1 << 16))
         return buf.value.decode()
 
+    def photon_source_spectrum(self, role="PhotonSourceSpectrum"):
+        """dict(kind, param, total_flux, freq, cdf) of the file's spectrum for `role`"""
+        info, freq, cdf = np.zeros(4), np.empty(4096), np.empty(4096)
+        vp = C.c_void_p
+        _check(lib.cmih_photon_source_spectrum(self._h, role.encode(), info.ctypes.data_as(vp), freq.ctypes.data_as(vp),
+                                               cdf.ctypes.data_as(vp), C.c_int(4096)))
+        m = int(info[3])
+        return dict(kind=int(info[0]), param=info[1], total_flux=info[2], freq=freq[:m].copy(), cdf=cdf[:m].copy())
+
     def density_function(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
         n = x.shape[0]

@@ -309,6 +309,105 @@ struct PhotonSourceSpectrum {
   int kind;     /* CMIB_SPECTRUM_* */
   double param; /* frequency (Hz) or temperature (K) */
   double total_flux = -1.;
+  /* CMIB_SPECTRUM_TABULATED: the two arrays the device samples from (cmib_set_spectrum_table) */
+  std::vector<double> frequencies, cumulative_distribution;
+
+  /* hand the spectrum to a device context: role 0 = discrete sources, 1 = continuous source */
+  int set_on(cmib_context *ctx, int role) const {
+    if (kind == CMIB_SPECTRUM_TABULATED)
+      return cmib_set_spectrum_table(ctx, role, (int32_t)frequencies.size(), frequencies.data(),
+                                     cumulative_distribution.data());
+    return role == 0 ? cmib_set_spectrum(ctx, kind, param) : 0; /* role 1: through cmib_set_continuous_source */
+  }
+
+  /* Utilities::locate (src/Utilities.hpp:726-742) */
+  static uint32_t locate(double x, const double *xarr, uint32_t length) {
+    uint32_t jl = 0, ju = length;
+    while (ju - jl > 1) {
+      const uint32_t jm = (ju + jl) >> 1;
+      if (x > xarr[jm]) jl = jm; else ju = jm;
+    }
+    if (jl == length - 1) --jl;
+    return jl;
+  }
+
+  /*
+   * FaucherGiguerePhotonSourceSpectrum (src/FaucherGiguerePhotonSourceSpectrum.cpp:40-183): the UV
+   * background of Faucher-Giguere et al. (2009, December 2011 tables) at a redshift, resampled on 100
+   * frequencies between 13.6 and 54.4 eV.  Data files: <CMIB_DATA_DIR>/fg_uvb_dec11/ (the unpacked
+   * data/fg_uvb_dec11.tar.gz of a CMacIonize checkout; the reference's build unpacks it likewise).
+   * NB the reference reads the second redshift table from the FIRST file's (exhausted) stream
+   * (:96-104), which leaves the added term undefined; it is multiplied by zero when the redshift is
+   * a multiple of 0.05, where this function is bit-identical (tests/test_host_layer.py).  In between
+   * it interpolates the two tables as the reference's comments say it intends to.
+   */
+  static PhotonSourceSpectrum *faucher_giguere(double redshift) {
+    constexpr int NUMFREQ = 100;
+    auto *s = new PhotonSourceSpectrum{CMIB_SPECTRUM_TABULATED, redshift};
+    s->frequencies.assign(NUMFREQ, 0.);
+    s->cumulative_distribution.assign(NUMFREQ, 0.);
+    std::vector<double> &freq = s->frequencies, &cdf = s->cumulative_distribution;
+    const double min_frequency = 3.289e15, max_frequency = 4. * min_frequency;
+    for (int i = 0; i < NUMFREQ; ++i) freq[i] = min_frequency + i * (max_frequency - min_frequency) / (NUMFREQ - 1.);
+    s->total_flux = 0.;
+    if (!(redshift <= 10.65)) return s; /* no UV background: all zeros, like the reference */
+    const char *dir = getenv("CMIB_DATA_DIR");
+    if (!dir) cmi_error("FaucherGiguere spectrum: set CMIB_DATA_DIR to the directory that holds fg_uvb_dec11/!");
+    auto filename = [&](double z) { /* get_filename (:194-216): integer arithmetic on z / 0.05 */
+      uint32_t iz = (uint32_t)(std::round(z / 0.05) * 5);
+      const uint32_t iz100 = iz / 100;
+      iz -= iz100 * 100;
+      const uint32_t iz10 = iz / 10;
+      iz -= iz10 * 10;
+      std::ostringstream name;
+      name << dir << "/fg_uvb_dec11/fg_uvb_dec11_z_" << iz100 << "." << iz10;
+      if (iz > 0) name << iz;
+      name << ".dat";
+      return name.str();
+    };
+    auto read = [&](double z, double fac, double *nu_out, double *ener, bool add) {
+      const std::string name = filename(z);
+      std::ifstream file(name);
+      if (!file) cmi_error("File not found: %s!", name.c_str());
+      std::string line;
+      getline(file, line);
+      getline(file, line);
+      for (int i = 0; i < 261; ++i) {
+        getline(file, line);
+        std::istringstream linestream(line);
+        double nu = 0., e = 0.;
+        linestream >> nu >> e;
+        if (nu_out) nu_out[i] = nu * 3.289e15;
+        if (add) ener[i] += fac * e; else ener[i] = fac * e;
+      }
+    };
+    double spectrum_freq[261], spectrum_ener[261];
+    const unsigned int izlo = (unsigned int)(redshift / 0.05);
+    const unsigned int izhi = izlo + 1;
+    const double zlo = izlo * 0.05, zhi = izhi * 0.05;
+    read(zlo, 20. * (zhi - redshift), spectrum_freq, spectrum_ener, false);
+    const double zhi_fac = 20. * (redshift - zlo);
+    if (zhi <= 10.65 && zhi_fac != 0.) read(zhi, zhi_fac, nullptr, spectrum_ener, true);
+    for (int i = 1; i < NUMFREQ; ++i) {
+      const double y1 = freq[i - 1];
+      const uint32_t i1 = locate(y1, spectrum_freq, 261);
+      double f = (y1 - spectrum_freq[i1]) / (spectrum_freq[i1 + 1] - spectrum_freq[i1]);
+      const double e1 = spectrum_ener[i1] + f * (spectrum_ener[i1 + 1] - spectrum_ener[i1]);
+      const double y2 = freq[i];
+      const uint32_t i2 = locate(y2, spectrum_freq, 261);
+      f = (y2 - spectrum_freq[i2]) / (spectrum_freq[i2 + 1] - spectrum_freq[i2]);
+      const double e2 = spectrum_ener[i2] + f * (spectrum_ener[i2 + 1] - spectrum_ener[i2]);
+      cdf[i] = 0.5 * (e1 / y2 + e2 / y1) * (y2 - y1);
+    }
+    for (int i = 1; i < NUMFREQ; ++i) cdf[i] += cdf[i - 1];
+    /* 1e-21 erg Hz^-1 s^-1 cm^-2 sr^-1 -> m^-2 s^-1 (:150-161) */
+    s->total_flux = 1.e-28 * cdf[NUMFREQ - 1] / 6.626070040e-34;
+    s->total_flux *= 4. * M_PI;
+    s->total_flux *= 1.e4;
+    const double norm = cdf[NUMFREQ - 1];
+    for (int i = 0; i < NUMFREQ; ++i) cdf[i] /= norm;
+    return s;
+  }
   static PhotonSourceSpectrum *generate(const std::string &role, ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>(role + ":type", "Monochromatic");
     if (log) log->write_info("Requested PhotonSourceSpectrum for ", role, ": ", type);
@@ -324,8 +423,11 @@ struct PhotonSourceSpectrum {
       s->total_flux = params.get_physical_value<QUANTITY_FLUX>(role + ":ionizing flux", "-1. m^-2 s^-1");
       return s;
     }
+    if (type == "Uniform") return new PhotonSourceSpectrum{CMIB_SPECTRUM_UNIFORM, 0.}; /* no total flux (UniformPhotonSourceSpectrum.hpp:60-63) */
+    if (type == "FaucherGiguere") return faucher_giguere(params.get_value<double>(role + ":redshift", 0.));
     if (type == "None") return nullptr;
-    cmi_error("Unknown PhotonSourceSpectrum type: \"%s\" (the B200 backend provides Monochromatic and Planck)!",
+    cmi_error("Unknown PhotonSourceSpectrum type: \"%s\" (the B200 backend provides Monochromatic, Planck, Uniform and "
+              "FaucherGiguere; any tabulated spectrum can be handed to cmib_set_spectrum_table)!",
               type.c_str());
   }
 };
@@ -670,11 +772,13 @@ public:
       CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
       CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
       CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), discrete_luminosity));
-      if (ns > 0) CMIB_CALL(cmib_set_spectrum(ctx, photon_source_spectrum_->kind, photon_source_spectrum_->param));
-      if (has_continuous)
+      if (ns > 0) CMIB_CALL(photon_source_spectrum_->set_on(ctx, 0));
+      if (has_continuous) {
+        CMIB_CALL(continuous_photon_source_spectrum_->set_on(ctx, 1));
         CMIB_CALL(cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_ISOTROPIC, continuous_luminosity,
                                              continuous_photon_source_spectrum_->kind,
                                              continuous_photon_source_spectrum_->param));
+      }
       CMIB_CALL(cmib_set_reemission(ctx, reemission_.kind, reemission_.probability, reemission_.frequency));
       CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
     }

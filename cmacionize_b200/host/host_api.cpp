@@ -158,4 +158,24 @@ int cmih_density_function(void *h, int64_t n, const double *x, double *dens, dou
   });
 }
 
+/* the parameter file's PhotonSourceSpectrum for `role` ("PhotonSourceSpectrum" /
+ * "ContinuousPhotonSourceSpectrum"): info = {kind, param, total flux, table length}; the table of a
+ * tabulated spectrum is copied to freq / cdf (capacity entries each) */
+int cmih_photon_source_spectrum(void *h, const char *role, double *info, double *freq, double *cdf, int capacity) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<PhotonSourceSpectrum> s(PhotonSourceSpectrum::generate(role, p));
+    if (!s) throw std::runtime_error("no spectrum (type None)");
+    info[0] = s->kind;
+    info[1] = s->param;
+    info[2] = s->total_flux;
+    info[3] = (double)s->frequencies.size();
+    if ((int)s->frequencies.size() > capacity) throw std::runtime_error("table capacity too small");
+    for (size_t i = 0; i < s->frequencies.size(); ++i) {
+      freq[i] = s->frequencies[i];
+      cdf[i] = s->cumulative_distribution[i];
+    }
+  });
+}
+
 } /* extern "C" */

@@ -55,7 +55,7 @@ typedef struct cmib_grid_desc {
 /* plugin selectors (the reference's `type:` strings) */
 enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
 enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
-enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1 };
+enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1, CMIB_SPECTRUM_UNIFORM = 2, CMIB_SPECTRUM_TABULATED = 3 };
 enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1 };
 enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
 
@@ -117,8 +117,17 @@ int cmib_set_recombination_rates(cmib_context *ctx, int kind, const double fixed
 int cmib_set_sources(cmib_context *ctx, int32_t n_sources, const double *positions,
                      const double *weights, double total_luminosity);
 /* PhotonSourceSpectrumFactory (src/PhotonSourceSpectrumFactory.hpp:84-152): param is the
- * frequency (Hz) for MONOCHROMATIC, the black-body temperature (K) for PLANCK */
+ * frequency (Hz) for MONOCHROMATIC, the black-body temperature (K) for PLANCK, unused for UNIFORM
+ * (src/UniformPhotonSourceSpectrum.hpp:50-53: 13.6 - 54.4 eV) */
 int cmib_set_spectrum(cmib_context *ctx, int kind, double param);
+/* Any spectrum that samples from a frequency grid and its cumulative distribution with linear
+ * interpolation — FaucherGiguere (src/FaucherGiguerePhotonSourceSpectrum.cpp:234-247), WMBasic
+ * (src/WMBasicPhotonSourceSpectrum.cpp:236-248), PopStar, Pegase3, CastelliKurucz, Masked
+ * (src/MaskedPhotonSourceSpectrum.cpp:123-135): hand over its two arrays (frequencies in Hz, cumulative
+ * distribution from 0 to 1, both [n]).  role 0 = PhotonSourceSpectrum of the discrete sources,
+ * 1 = ContinuousPhotonSourceSpectrum (then pass CMIB_SPECTRUM_TABULATED to cmib_set_continuous_source). */
+int cmib_set_spectrum_table(cmib_context *ctx, int role, int32_t n, const double *frequencies,
+                            const double *cumulative_distribution);
 /* ContinuousPhotonSourceFactory (src/ContinuousPhotonSourceFactory.hpp:69-100) + its spectrum
  * (PhotonSourceSpectrumFactory with role "ContinuousPhotonSourceSpectrum"): kind ISOTROPIC =
  * IsotropicContinuousPhotonSource (src/IsotropicContinuousPhotonSource.hpp:106-180: packets enter
@@ -244,7 +253,7 @@ int cmib_eval_temperature(cmib_context *ctx, int64_t n, double jfac, double hfac
  * 3 He-2-photon: freq[1000] cdf[1000].  Unused outputs may be NULL. */
 int cmib_get_spectrum_tables(cmib_context *ctx, int which, double *a, double *b, double *c);
 /* sample n frequencies on the device: which 0 source spectrum, 1 H-Lyc(T), 2 He-Lyc(T),
- * 3 He-2-photon */
+ * 3 He-2-photon, 4 spectrum of the continuous source */
 int cmib_sample_spectrum(cmib_context *ctx, int which, double temperature, uint64_t seed,
                          int64_t n, double *nu);
 

@@ -115,6 +115,10 @@ def generate_headers(gen: Path) -> None:
         "#ifndef VERNERRECOMBINATIONRATESDATALOCATION_HPP\n#define VERNERRECOMBINATIONRATESDATALOCATION_HPP\n"
         + decl
         + "#define VERNERRECOMBINATIONRATESDATALOCATION " + resolver % "verner_rec_data.txt" + "\n#endif\n")
+    (gen / "FaucherGiguereDataLocation.hpp").write_text(
+        "#ifndef FAUCHERGIGUEREDATALOCATION_HPP\n#define FAUCHERGIGUEREDATALOCATION_HPP\n"
+        "#include <string>\nextern \"C++\" std::string cmi_ref_data_dir(const char *sub, const char *probe_file);\n"
+        "#define FAUCHERGIGUEREDATALOCATION (cmi_ref_data_dir(\"fg_uvb_dec11\", \"fg_uvb_dec11_z_0.0.dat\"))\n#endif\n")
     (gen / "HeliumTwoPhotonContinuumDataLocation.hpp").write_text(
         "#ifndef HELIUMTWOPHOTONCONTINUUMDATALOCATION_HPP\n#define HELIUMTWOPHOTONCONTINUUMDATALOCATION_HPP\n"
         + decl
@@ -146,6 +150,10 @@ def build(force: bool = False, jobs: int | None = None) -> Path:
     for f in DATA_FILES:
         if force or not (data / f).exists():
             shutil.copyfile(REF / "data" / f, data / f)
+    if force or not (data / "fg_uvb_dec11" / "fg_uvb_dec11_z_0.0.dat").exists():
+        import tarfile
+        with tarfile.open(REF / "data" / "fg_uvb_dec11.tar.gz") as tar:  # src/CMakeLists.txt unpacks it the same way
+            tar.extractall(data)
 
     inc = [f"-I{gen}", f"-I{REF / 'src'}"]
     work: list[tuple[Path, Path]] = []

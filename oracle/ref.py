@@ -215,6 +215,24 @@ def isotropic_incoming(anchor, sides, n, seed=42):
     return u, pos, d
 
 
+def faucher_giguere(redshift, n, seed=42):
+    """dict(freq, cdf, total_flux, uniforms, nu) of FaucherGiguerePhotonSourceSpectrum(redshift)"""
+    u, nu = np.empty(n), np.empty(n)
+    freq, cdf = np.empty(4096), np.empty(4096)
+    flux = C.c_double(0.)
+    m = lib().cmi_ref_tabulated_spectrum(C.c_int(0), C.c_double(redshift), C.c_int(seed), C.c_int64(n), _p(u), _p(nu),
+                                         _p(freq), _p(cdf), C.c_int(4096), C.byref(flux))
+    assert m > 0
+    return dict(freq=freq[:m].copy(), cdf=cdf[:m].copy(), total_flux=flux.value, uniforms=u, nu=nu)
+
+
+def uniform_spectrum(n, seed=42):
+    u, nu = np.empty(n), np.empty(n)
+    lib().cmi_ref_tabulated_spectrum(C.c_int(1), C.c_double(0.), C.c_int(seed), C.c_int64(n), _p(u), _p(nu),
+                                     None, None, C.c_int(0), None)
+    return u, nu
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

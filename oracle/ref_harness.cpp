@@ -48,7 +48,9 @@
 #include "HydrogenLymanContinuumSpectrum.hpp"
 #include "IonizationSimulation.hpp"
 #include "IonizationStateCalculator.hpp"
+#include "FaucherGiguerePhotonSourceSpectrum.hpp"
 #include "IsotropicContinuousPhotonSource.hpp"
+#include "UniformPhotonSourceSpectrum.hpp"
 #include "LineCoolingData.hpp"
 #include "Photon.hpp"
 #include "PhotonSource.hpp"
@@ -65,6 +67,13 @@
 #undef protected
 
 /* ---- data-file resolver used by the generated *DataLocation.hpp headers ---- */
+std::string cmi_ref_data_file(const char *name);
+/* directory (with trailing slash) of a data set that is addressed by file-name prefix
+ * (FaucherGiguereDataLocation.hpp: fg_uvb_dec11/) */
+std::string cmi_ref_data_dir(const char *sub, const char *probe_file) {
+  const std::string probe = cmi_ref_data_file((std::string(sub) + "/" + probe_file).c_str());
+  return probe.substr(0, probe.size() - strlen(probe_file));
+}
 std::string cmi_ref_data_file(const char *name) {
   const char *env = getenv("CMI_REF_DATA_DIR");
   std::string dir;
@@ -594,6 +603,31 @@ void cmi_ref_isotropic_incoming(const double *anchor, const double *sides, int s
       dir[3 * i + k] = pd.second[k];
     }
   }
+}
+
+/* FaucherGiguerePhotonSourceSpectrum(redshift) (src/FaucherGiguerePhotonSourceSpectrum.cpp): its
+ * frequency grid and cumulative distribution (what a tabulated spectrum hands to the device),
+ * its total flux, and n samples with RandomGenerator(seed) together with the deviates they
+ * consumed (one per sample).  which = 1: UniformPhotonSourceSpectrum instead (no tables). */
+int cmi_ref_tabulated_spectrum(int which, double redshift, int seed, int64_t n, double *uniforms, double *nu,
+                               double *freq, double *cdf, int capacity, double *total_flux) {
+  RandomGenerator rg(seed), replay(seed);
+  for (int64_t i = 0; i < n; ++i) uniforms[i] = replay.get_uniform_random_double();
+  if (which == 1) {
+    UniformPhotonSourceSpectrum sp;
+    for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, 0.);
+    return 0;
+  }
+  FaucherGiguerePhotonSourceSpectrum sp(redshift);
+  const int m = (int)sp._frequencies.size();
+  if (m > capacity) return -m;
+  for (int i = 0; i < m; ++i) {
+    freq[i] = sp._frequencies[i];
+    cdf[i] = sp._cumulative_distribution[i];
+  }
+  if (total_flux) *total_flux = sp.get_total_flux();
+  for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, 0.);
+  return m;
 }
 
 /* UnitConverter::to_SI for a quantity given by its SI unit name, e.g.

@@ -149,6 +149,11 @@ void hc_isotropic_incoming(const double *anchor, const double *sides, int64_t n,
                        dir[3 * i + 2]);
 }
 
+/* tabulated (freq != NULL) or Uniform spectrum sampled with the given deviates */
+void hc_tabulated_frequency(int32_t m, const double *freq, const double *cdf, int64_t n, const double *x, double *nu) {
+  for (int64_t i = 0; i < n; ++i) nu[i] = freq ? tabulated_frequency(freq, cdf, (uint32_t)m, x[i]) : uniform_frequency(x[i]);
+}
+
 void hc_planck_tables(double temperature, double *out) {
   std::vector<double> t;
   host::build_planck_table(temperature, t);
@@ -272,13 +277,13 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   m.src_pos = src_pos;
   m.src_cum = cum.data();
   m.discrete_weight = 1.;
-  m.spectrum_kind = iparams[1];
+  m.spectrum.kind = iparams[1];
   std::vector<double> planck, hf, ht, hc, hef, het, hec, tf, tc;
-  if (m.spectrum_kind == SPECTRUM_PLANCK) {
+  if (m.spectrum.kind == SPECTRUM_PLANCK) {
     host::build_planck_table(dparams[0], planck);
-    m.planck = planck.data();
+    m.spectrum.planck = planck.data();
   } else {
-    m.mono_frequency = dparams[0];
+    m.spectrum.mono_frequency = dparams[0];
   }
   m.xs_kind = iparams[2];
   for (int k = 0; k < NUM_IONS; ++k) m.xs_fixed[k] = xs_fixed ? xs_fixed[k] : 0.;

@@ -199,7 +199,11 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     elif config == "continuous_only":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
         prob.ctx.set_sources(None, None, 0.)
-        prob.ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 1e49, capi.SPECTRUM_PLANCK, 30000.)
+        # a tabulated spectrum (the form of FaucherGiguere, WMBasic, ...: cmib_set_spectrum_table)
+        trng = np.random.default_rng(8)
+        cdf = np.concatenate([[0.], np.cumsum(trng.uniform(0.1, 1., 99) * np.exp(-np.arange(99) / 30.))])
+        prob.ctx.set_spectrum_table(np.linspace(3.289e15, 4 * 3.289e15, 100), cdf / cdf[-1], role=1)
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 1e49, capi.SPECTRUM_TABULATED)
     else:
         # non-cubic box, periodic in x and z, three sources (one outside the box: its packets
         # are lost immediately, as in the reference), Physical re-emission
@@ -357,3 +361,33 @@ def test_continuous_source_shoot_equals_oracle(cmib, ref):
         assert np.abs(f1 - f2).max() < 5 * np.sqrt(2 * 0.25 / m)
         assert np.abs(mu1 - mu2).max() < 5e-3
         assert np.abs(np.linalg.norm(pk["dir"], axis=1) - 1.).max() < 1e-14
+
+
+def test_tabulated_and_uniform_spectra_on_the_device(cmib, ref):
+    """cmib_set_spectrum_table with the reference's FaucherGiguere tables (z = 7) and the Uniform
+    spectrum, sampled on the device, against the reference's own samplers (histograms; the sampling
+    rule itself is pinned bit for bit on the CPU tier, test_host_physics.py)."""
+    from cmacionize_b200 import capi
+    n = 1_000_000
+    with cmib.Context([-1, -1, -1], [2, 2, 2], [4, 4, 4]) as ctx:
+        ctx.set_abundances(*ABUNDANCES)
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_VERNER)
+        ctx.set_sources([[0., 0., 0.]], [1.], 1e49)
+        d = ref.faucher_giguere(7., n, seed=42)
+        for role, which in ((0, 0), (1, 4)):
+            ctx.set_spectrum_table(d["freq"], d["cdf"], role=role)
+            nu = ctx.sample_spectrum(which, 0., n, seed=3)
+            assert nu.min() >= d["freq"][0] and nu.max() <= d["freq"][-1]
+            edges = np.linspace(d["freq"][0], d["freq"][-1], 81)
+            h1, _ = np.histogram(nu, edges)
+            h2, _ = np.histogram(d["nu"], edges)
+            big = h2 > 1000
+            assert big.sum() > 20
+            assert np.abs((h1[big] - h2[big]) / np.sqrt(h1[big] + h2[big])).max() < 5.
+        ctx.set_spectrum(capi.SPECTRUM_UNIFORM, 0.)
+        nu = ctx.sample_spectrum(0, 0., n, seed=4)
+        _, nu_ref = ref.uniform_spectrum(n, seed=4)
+        assert nu.min() >= 3.289e15 and nu.max() <= 4 * 3.289e15
+        assert abs(nu.mean() / nu_ref.mean() - 1.) < 2e-3 and abs(nu.std() / nu_ref.std() - 1.) < 3e-3
+        pk = ctx.sample_packets(1000, seed=1)   # emission uses it
+        assert (pk["nu"] >= 3.289e15).all() and (pk["nu"] <= 4 * 3.289e15).all() and np.unique(pk["nu"]).size > 990

@@ -163,3 +163,45 @@ def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     assert np.array_equal(dens, f[0]) and np.array_equal(temp, f[1]) and np.array_equal(xH, f[2])
     if kind == "lexington_blocks":
         assert (dens == 0).sum() > 0 and (dens > 0).sum() > 0
+
+
+def test_uniform_and_faucher_giguere_spectra_from_a_parameter_file(host, ref, tmp_path, monkeypatch):
+    """PhotonSourceSpectrumFactory types Uniform and FaucherGiguere in the host layer: the table the
+    host builds from the fg_uvb_dec11 data files (frequencies, cumulative distribution, total flux)
+    is the reference object's, bit for bit, at redshifts on the tables' 0.05 grid (in between the
+    reference reads its second table from the wrong stream, host/IonizationSimulation.hpp)."""
+    from pathlib import Path
+    data = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "data"
+    monkeypatch.setenv("CMIB_DATA_DIR", str(data))
+    for z in (0., 0.45, 3.35, 7., 10.65):
+        pf = tmp_path / f"fg_{z}.param"
+        pf.write_text(f"ContinuousPhotonSourceSpectrum:\n  type: FaucherGiguere\n  redshift: {z}\n")
+        p = host.ParameterFile(pf)
+        s = p.photon_source_spectrum("ContinuousPhotonSourceSpectrum")
+        p.close()
+        d = ref.faucher_giguere(z, 1)
+        assert s["kind"] == 3 and s["freq"].size == 100
+        assert np.array_equal(s["freq"], d["freq"])
+        assert np.array_equal(s["cdf"], d["cdf"]), z
+        assert s["total_flux"] == d["total_flux"]
+    # between two tables: a proper interpolation, bracketed by its neighbours
+    fluxes = []
+    for z in (3.35, 3.37, 3.4):
+        pf = tmp_path / f"fg_{z}.param"
+        pf.write_text(f"PhotonSourceSpectrum:\n  type: FaucherGiguere\n  redshift: {z}\n")
+        p = host.ParameterFile(pf)
+        fluxes.append(p.photon_source_spectrum()["total_flux"])
+        p.close()
+    assert min(fluxes[0], fluxes[2]) < fluxes[1] < max(fluxes[0], fluxes[2])
+    assert abs(fluxes[1] - (0.6 * fluxes[0] + 0.4 * fluxes[2])) < 1e-9 * fluxes[1]
+    pf = tmp_path / "uniform.param"
+    pf.write_text("PhotonSourceSpectrum:\n  type: Uniform\n")
+    p = host.ParameterFile(pf)
+    assert p.photon_source_spectrum()["kind"] == 2
+    p.close()
+    pf = tmp_path / "bad.param"
+    pf.write_text("PhotonSourceSpectrum:\n  type: WMBasic\n")
+    p = host.ParameterFile(pf)
+    with pytest.raises(Exception, match="Unknown PhotonSourceSpectrum type"):
+        p.photon_source_spectrum()
+    p.close()

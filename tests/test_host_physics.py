@@ -190,3 +190,20 @@ def test_isotropic_continuous_source_bitexact(hostcheck, ref):
         assert on_face.all()
         inward = np.where(np.isclose(pos2, a, rtol=0, atol=1e-12 * sd), d2, np.where(np.isclose(pos2, a + sd, rtol=0, atol=1e-12 * sd), -d2, 1.))
         assert (inward >= 0.).all()
+
+
+def test_tabulated_and_uniform_spectra_bitexact(hostcheck, ref):
+    """The sampling rule shared by the reference's tabulated spectra (FaucherGiguere here, z = 0 and
+    z = 7: FaucherGiguerePhotonSourceSpectrum.cpp:234-247) and the Uniform spectrum, fed with the
+    reference generator's own deviates and the reference object's own two arrays: bit for bit."""
+    for z in (0., 7.):
+        d = ref.faucher_giguere(z, 50000, seed=5)
+        nu = np.empty(50000)
+        hostcheck.hc_tabulated_frequency(C.c_int32(d["freq"].size), p(d["freq"]), p(d["cdf"]), C.c_int64(nu.size),
+                                         p(d["uniforms"]), p(nu))
+        assert np.array_equal(nu, d["nu"])
+        assert d["cdf"][0] == 0. and d["cdf"][-1] == 1. and (np.diff(d["cdf"]) >= 0).all()
+    u, nu_ref = ref.uniform_spectrum(50000, seed=6)
+    nu = np.empty(50000)
+    hostcheck.hc_tabulated_frequency(C.c_int32(0), None, None, C.c_int64(nu.size), p(u), p(nu))
+    assert np.array_equal(nu, nu_ref)
