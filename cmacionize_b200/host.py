@@ -38,6 +38,13 @@ def convert(value, unit_from, unit_to):
     return out.value
 
 
+def random_stream(seed, n):
+    """n deviates of the host layer's RandomGenerator (the reference's RANLUX stream)"""
+    out = np.empty(n)
+    _check(lib.cmih_random_stream(C.c_int32(seed), C.c_int64(n), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 class ParameterFile:
     def __init__(self, filename):
         self._h = C.c_void_p()
@@ -80,6 +87,15 @@ class ParameterFile:
                                                cdf.ctypes.data_as(vp), C.c_int(4096)))
         m = int(info[3])
         return dict(kind=int(info[0]), param=info[1], total_flux=info[2], freq=freq[:m].copy(), cdf=cdf[:m].copy())
+
+    def photon_source_distribution(self, capacity=4096):
+        """(positions [n,3], weights [n], total luminosity) of the file's PhotonSourceDistribution"""
+        info, pos, w = np.zeros(2), np.empty((capacity, 3)), np.empty(capacity)
+        vp = C.c_void_p
+        _check(lib.cmih_photon_source_distribution(self._h, info.ctypes.data_as(vp), pos.ctypes.data_as(vp),
+                                                   w.ctypes.data_as(vp), C.c_int(capacity)))
+        n = int(info[0])
+        return pos[:n].copy(), w[:n].copy(), info[1]
 
     def density_function(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)

@@ -50,6 +50,7 @@
 #include "../../include/cmib.h"
 #include "Error.hpp"
 #include "ParameterFile.hpp"
+#include "RandomGenerator.hpp"
 
 namespace cmi {
 
@@ -211,13 +212,81 @@ private:
   std::vector<Block> blocks_;
 };
 
+/* AsciiFileDensityFunction (src/AsciiFileDensityFunction.cpp:40-186): "x y z density" rows on a regular
+ * grid of its own (not necessarily the simulation grid); a cell takes the value of the file cell
+ * its midpoint falls in */
+class AsciiFileDensityFunction : public DensityFunction {
+public:
+  AsciiFileDensityFunction(const std::string &filename, const std::array<uint32_t, 3> &ncell, const Vec3 &anchor,
+                           const Vec3 &sides, double temperature, double length_unit_in_SI, double density_unit_in_SI)
+      : ncell_(ncell), anchor_(anchor), sides_(sides), temperature_(temperature),
+        grid_((size_t)ncell[0] * ncell[1] * ncell[2], -1.) {
+    std::ifstream file(filename);
+    if (!file.is_open()) cmi_error("Could not open file \"%s\"!", filename.c_str());
+    std::string line;
+    while (getline(file, line)) {
+      if (line[0] == '#') continue;
+      double x = 0., y = 0., z = 0., rho = 0.;
+      std::stringstream linestream(line);
+      linestream >> x >> y >> z >> rho;
+      x *= length_unit_in_SI;
+      y *= length_unit_in_SI;
+      z *= length_unit_in_SI;
+      rho *= density_unit_in_SI;
+      grid_[index({x, y, z})] = rho;
+    }
+    for (uint32_t i = 0; i < ncell_[0]; ++i)
+      for (uint32_t j = 0; j < ncell_[1]; ++j)
+        for (uint32_t k = 0; k < ncell_[2]; ++k)
+          if (grid_[((size_t)i * ncell_[1] + j) * ncell_[2] + k] < 0.)
+            cmi_error("No value found for cell [%u, %u, %u]!", i, j, k);
+  }
+  explicit AsciiFileDensityFunction(ParameterFile &params)
+      : AsciiFileDensityFunction(
+            params.get_filename("DensityFunction:filename"),
+            params.get_value<std::array<uint32_t, 3>>("DensityFunction:number of cells", {64, 64, 64}),
+            params.get_physical_vector<QUANTITY_LENGTH>("DensityFunction:box anchor", "[-5. pc, -5. pc, -5. pc]"),
+            params.get_physical_vector<QUANTITY_LENGTH>("DensityFunction:box sides", "[10. pc, 10. pc, 10. pc]"),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "8000. K"),
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:length unit", "1. m"),
+            params.get_physical_value<QUANTITY_NUMBER_DENSITY>("DensityFunction:density unit", "1. m^-3")) {}
+
+  DensityValues operator()(const Vec3 &position) override {
+    DensityValues v;
+    v.number_density = grid_[index(position)];
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = 1.e-6;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  /* (p - anchor) / sides * ncell, truncated (.cpp:82-85, 170-176); out-of-range rows are the
+   * reference's undefined behaviour: here an error */
+  size_t index(const Vec3 &p) const {
+    size_t idx[3];
+    for (int d = 0; d < 3; ++d) {
+      const double f = (p[d] - anchor_[d]) / sides_[d] * ncell_[d];
+      if (!(f >= 0.) || !(f < (double)ncell_[d]))
+        cmi_error("Position [%g m, %g m, %g m] outside the box of the AsciiFile density grid!", p[0], p[1], p[2]);
+      idx[d] = (size_t)f;
+    }
+    return (idx[0] * ncell_[1] + idx[1]) * ncell_[2] + idx[2];
+  }
+  std::array<uint32_t, 3> ncell_;
+  Vec3 anchor_, sides_;
+  double temperature_;
+  std::vector<double> grid_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
     if (log) log->write_info("Requested DensityFunction type: ", type);
     if (type == "Homogeneous") return new HomogeneousDensityFunction(params);
     if (type == "BlockSyntax") return new BlockSyntaxDensityFunction(params);
-    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous and BlockSyntax)!",
+    if (type == "AsciiFile") return new AsciiFileDensityFunction(params);
+    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax and AsciiFile)!",
               type.c_str());
   }
 };
@@ -292,14 +361,116 @@ private:
   double luminosity_ = 0.;
 };
 
+/* AsciiFilePhotonSourceDistribution (src/AsciiFilePhotonSourceDistribution.hpp:50-98): a YAML file with
+ * "number of sources" and source[i]:position / source[i]:luminosity */
+class AsciiFilePhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  explicit AsciiFilePhotonSourceDistribution(const std::string &filename) {
+    std::ifstream file(filename);
+    if (!file) cmi_error("Error while opening file \"%s\"!", filename.c_str());
+    YAMLDictionary blocks(file);
+    const uint32_t n = blocks.get_value<uint32_t>("number of sources");
+    positions_.resize(n);
+    luminosities_.resize(n);
+    for (uint32_t i = 0; i < n; ++i) {
+      const std::string name = "source[" + std::to_string(i) + "]:";
+      positions_[i] = blocks.get_physical_vector<QUANTITY_LENGTH>(name + "position");
+      luminosities_[i] = blocks.get_physical_value<QUANTITY_FREQUENCY>(name + "luminosity");
+      total_luminosity_ += luminosities_[i];
+    }
+    std::ofstream ofile(filename + ".used-values");
+    blocks.print_contents(ofile, true);
+  }
+  explicit AsciiFilePhotonSourceDistribution(ParameterFile &params)
+      : AsciiFilePhotonSourceDistribution(params.get_filename("PhotonSourceDistribution:filename", "sources.yml")) {}
+  size_t get_number_of_sources() const override { return positions_.size(); }
+  Vec3 get_position(size_t i) override { return positions_[i]; }
+  double get_weight(size_t i) const override { return luminosities_[i] / total_luminosity_; }
+  double get_total_luminosity() const override { return total_luminosity_; }
+
+private:
+  std::vector<Vec3> positions_;
+  std::vector<double> luminosities_;
+  double total_luminosity_ = 0.;
+};
+
+/* UniformRandomPhotonSourceDistribution (src/UniformRandomPhotonSourceDistribution.hpp:88-300): equal
+ * sources at positions drawn uniformly in a box with the reference's generator (RandomGenerator.hpp:
+ * same seed, same positions), each with a random remaining lifetime; the population is evolved in
+ * steps of the update interval up to the starting time (dead sources are replaced).  The
+ * time-dependent update() belongs to the radiation-hydrodynamics driver and is not provided. */
+class UniformRandomPhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  UniformRandomPhotonSourceDistribution(double source_lifetime, double source_luminosity, uint32_t number_of_sources,
+                                        const Vec3 &box_anchor, const Vec3 &box_sides, int32_t seed,
+                                        double update_interval, double starting_time)
+      : source_luminosity_(source_luminosity), anchor_(box_anchor), sides_(box_sides), random_generator_(seed) {
+    for (uint32_t i = 0; i < number_of_sources; ++i) {
+      lifetimes_.push_back(random_generator_.get_uniform_random_double() * source_lifetime);
+      positions_.push_back(generate_source_position());
+    }
+    uint32_t number_of_updates = 1;
+    while (number_of_updates * update_interval <= starting_time) {
+      size_t i = 0;
+      while (i < lifetimes_.size()) {
+        lifetimes_[i] -= update_interval;
+        if (lifetimes_[i] <= 0.) {
+          positions_.erase(positions_.begin() + i);
+          lifetimes_.erase(lifetimes_.begin() + i);
+        } else {
+          ++i;
+        }
+      }
+      for (size_t k = positions_.size(); k < number_of_sources; ++k) {
+        const double offset = random_generator_.get_uniform_random_double() * update_interval;
+        lifetimes_.push_back(source_lifetime - offset);
+        positions_.push_back(generate_source_position());
+      }
+      ++number_of_updates;
+    }
+  }
+  explicit UniformRandomPhotonSourceDistribution(ParameterFile &params)
+      : UniformRandomPhotonSourceDistribution(
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:source lifetime", "1. Myr"),
+            params.get_physical_value<QUANTITY_FREQUENCY>("PhotonSourceDistribution:source luminosity", "1.e48 s^-1"),
+            params.get_value<uint32_t>("PhotonSourceDistribution:number of sources", 1),
+            params.get_physical_vector<QUANTITY_LENGTH>("PhotonSourceDistribution:box anchor", "[-5. pc, -5. pc, -5. pc]"),
+            params.get_physical_vector<QUANTITY_LENGTH>("PhotonSourceDistribution:box sides", "[10. pc, 10. pc, 10. pc]"),
+            params.get_value<int32_t>("PhotonSourceDistribution:random seed", 42),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:update interval", "0.1 Myr"),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:starting time", "0. Myr")) {
+    if (params.get_value<bool>("PhotonSourceDistribution:output sources", false))
+      cmi_error("PhotonSourceDistribution:output sources is not provided by the B200 backend!");
+  }
+  size_t get_number_of_sources() const override { return positions_.size(); }
+  Vec3 get_position(size_t i) override { return positions_[i]; }
+  double get_weight(size_t) const override { return 1. / get_number_of_sources(); }
+  double get_total_luminosity() const override { return source_luminosity_ * get_number_of_sources(); }
+
+private:
+  Vec3 generate_source_position() {
+    Vec3 p;
+    for (int d = 0; d < 3; ++d) p[d] = anchor_[d] + random_generator_.get_uniform_random_double() * sides_[d];
+    return p;
+  }
+  double source_luminosity_;
+  Vec3 anchor_, sides_;
+  RandomGenerator random_generator_;
+  std::vector<Vec3> positions_;
+  std::vector<double> lifetimes_;
+};
+
 struct PhotonSourceDistributionFactory {
   static PhotonSourceDistribution *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("PhotonSourceDistribution:type", "SingleStar");
     if (log) log->write_info("Requested PhotonSourceDistribution type: ", type);
     if (type == "SingleStar") return new SingleStarPhotonSourceDistribution(params);
+    if (type == "AsciiFile") return new AsciiFilePhotonSourceDistribution(params);
     if (type == "AsciiFileTable") return new AsciiFileTablePhotonSourceDistribution(params);
+    if (type == "UniformRandom") return new UniformRandomPhotonSourceDistribution(params);
     if (type == "None") return nullptr;
-    cmi_error("Unknown PhotonSourceDistribution type: \"%s\" (the B200 backend provides SingleStar and AsciiFileTable)!",
+    cmi_error("Unknown PhotonSourceDistribution type: \"%s\" (the B200 backend provides SingleStar, AsciiFile, "
+              "AsciiFileTable and UniformRandom)!",
               type.c_str());
   }
 };

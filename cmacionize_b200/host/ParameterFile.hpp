@@ -271,6 +271,7 @@ template <class T> struct ConvertVec {
 template <> struct Convert<std::array<double, 3>> : ConvertVec<double> {};
 template <> struct Convert<std::array<bool, 3>> : ConvertVec<bool> {};
 template <> struct Convert<std::array<int32_t, 3>> : ConvertVec<int32_t> {};
+template <> struct Convert<std::array<uint32_t, 3>> : ConvertVec<uint32_t> {};
 
 } // namespace detail
 
@@ -447,6 +448,9 @@ public:
   /* a file name given in the parameter file; relative names are relative to the working
    * directory, as in the reference (ParameterFile::get_filename) */
   std::string get_filename(const std::string &key) { return get_value<std::string>(key); }
+  std::string get_filename(const std::string &key, const std::string &default_value) {
+    return get_value<std::string>(key, default_value);
+  }
 
   void print_contents(std::ostream &out) const {
     const time_t now = time(nullptr);

@@ -178,4 +178,30 @@ int cmih_photon_source_spectrum(void *h, const char *role, double *info, double 
   });
 }
 
+/* n deviates of the host-side RandomGenerator (RANLUX level 2, host/RandomGenerator.hpp) */
+int cmih_random_stream(int32_t seed, int64_t n, double *out) {
+  CMIH_TRY({
+    RandomGenerator rg(seed);
+    for (int64_t i = 0; i < n; ++i) out[i] = rg.get_uniform_random_double();
+  });
+}
+/* the parameter file's PhotonSourceDistribution: info = {number of sources, total luminosity};
+ * positions[capacity][3], weights[capacity] */
+int cmih_photon_source_distribution(void *h, double *info, double *positions, double *weights, int capacity) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<PhotonSourceDistribution> d(PhotonSourceDistributionFactory::generate(p));
+    if (!d) throw std::runtime_error("no distribution (type None)");
+    const size_t n = d->get_number_of_sources();
+    info[0] = (double)n;
+    info[1] = d->get_total_luminosity();
+    if ((int)n > capacity) throw std::runtime_error("capacity too small");
+    for (size_t i = 0; i < n; ++i) {
+      const Vec3 x = d->get_position(i);
+      positions[3 * i] = x[0]; positions[3 * i + 1] = x[1]; positions[3 * i + 2] = x[2];
+      weights[i] = d->get_weight(i);
+    }
+  });
+}
+
 } /* extern "C" */

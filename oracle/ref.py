@@ -233,6 +233,20 @@ def uniform_spectrum(n, seed=42):
     return u, nu
 
 
+def random_stream(seed, n):
+    out = np.empty(n)
+    lib().cmi_ref_random_stream(C.c_int(seed), C.c_int64(n), _p(out))
+    return out
+
+
+def photon_source_distribution(paramfile, capacity=4096):
+    """(positions [n,3], weights [n], total luminosity) of the reference's PhotonSourceDistributionFactory"""
+    info, pos, w = np.zeros(2), np.empty((capacity, 3)), np.empty(capacity)
+    n = lib().cmi_ref_photon_source_distribution(str(paramfile).encode(), _p(info), _p(pos), _p(w), C.c_int(capacity))
+    assert 0 <= n <= capacity
+    return pos[:n].copy(), w[:n].copy(), info[1]
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

@@ -54,6 +54,7 @@
 #include "LineCoolingData.hpp"
 #include "Photon.hpp"
 #include "PhotonSource.hpp"
+#include "PhotonSourceDistributionFactory.hpp"
 #include "PhysicalDiffuseReemissionHandler.hpp"
 #include "PlanckPhotonSourceSpectrum.hpp"
 #include "RandomGenerator.hpp"
@@ -628,6 +629,31 @@ int cmi_ref_tabulated_spectrum(int which, double redshift, int seed, int64_t n, 
   if (total_flux) *total_flux = sp.get_total_flux();
   for (int64_t i = 0; i < n; ++i) nu[i] = sp.get_random_frequency(rg, 0.);
   return m;
+}
+
+/* RandomGenerator(seed) (src/RandomGenerator.hpp): n deviates */
+void cmi_ref_random_stream(int seed, int64_t n, double *out) {
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) out[i] = rg.get_uniform_random_double();
+}
+
+/* PhotonSourceDistributionFactory::generate on a parameter file: info = {number of sources, total
+ * luminosity}; positions[capacity][3], weights[capacity].  Returns the number of sources, -1 for None. */
+int cmi_ref_photon_source_distribution(const char *paramfile, double *info, double *positions, double *weights,
+                                       int capacity) {
+  ParameterFile params(paramfile);
+  PhotonSourceDistribution *d = PhotonSourceDistributionFactory::generate(params, nullptr);
+  if (d == nullptr) return -1;
+  const int n = (int)d->get_number_of_sources();
+  info[0] = n;
+  info[1] = d->get_total_luminosity();
+  for (int i = 0; i < n && i < capacity; ++i) {
+    const CoordinateVector<> x = d->get_position(i);
+    positions[3 * i] = x.x(); positions[3 * i + 1] = x.y(); positions[3 * i + 2] = x.z();
+    weights[i] = d->get_weight(i);
+  }
+  delete d;
+  return n;
 }
 
 /* UnitConverter::to_SI for a quantity given by its SI unit name, e.g.

@@ -136,10 +136,29 @@ def test_parameter_file_same_values_and_used_values_dump(host, ref, tmp_path):
         host.ParameterFile(bad).density_function(np.zeros((1, 3)))
 
 
-@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks"])
+@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks", "ascii_file"])
 def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     nc = 12
-    if kind == "homogeneous_defaults":
+    if kind == "ascii_file":
+        # AsciiFileDensityFunction: a 6 x 4 x 3 table of its own (cell centres in pc, densities in cm^-3)
+        # sampled by the 12^3 simulation grid
+        rng = np.random.default_rng(4)
+        nf = (6, 4, 3)
+        rows = ["# x y z density"]
+        for i in range(nf[0]):
+            for j in range(nf[1]):
+                for k in range(nf[2]):
+                    c = [-5. + 10. * (q + 0.5) / n for q, n in zip((i, j, k), nf)]
+                    rows.append(f"{c[0]!r} {c[1]!r} {c[2]!r} {rng.uniform(1., 200.)!r}")
+        dfile = tmp_path / "density.txt"
+        dfile.write_text("\n".join(rows) + "\n")
+        text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+                "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+                f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n  type: AsciiFile\n  filename: {dfile}\n"
+                "  number of cells: [6, 4, 3]\n  length unit: 1. pc\n  density unit: 1. cm^-3\n  temperature: 7000. K\n"
+                "PhotonSourceSpectrum:\n  type: Monochromatic\n")
+        half = 5 * PC
+    elif kind == "homogeneous_defaults":
         text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
                 "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
                 f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n  type: Homogeneous\n"
@@ -205,3 +224,39 @@ def test_uniform_and_faucher_giguere_spectra_from_a_parameter_file(host, ref, tm
     with pytest.raises(Exception, match="Unknown PhotonSourceSpectrum type"):
         p.photon_source_spectrum()
     p.close()
+
+
+def test_random_generator_stream_is_the_reference_stream(host, ref):
+    """host/RandomGenerator.hpp (RANLUX level 2) against the compiled reference generator: every
+    deviate, several seeds including the special cases 0 (-> 1) and negative seeds."""
+    for seed in (42, 1, 0, 123456789, -7, 2 ** 31 - 1):
+        assert np.array_equal(host.random_stream(seed, 100000), ref.random_stream(seed, 100000)), seed
+
+
+def test_photon_source_distributions_give_the_reference_sources(host, ref, tmp_path):
+    """PhotonSourceDistribution types of the host layer against the reference's factory on the same
+    parameter file: positions, weights, total luminosity, bit for bit (UniformRandom draws its
+    positions from the RANLUX stream and is evolved to the starting time)."""
+    yml = tmp_path / "sources.yml"
+    yml.write_text("number of sources: 3\nsource[0]:\n  position: [0. pc, 1. pc, -2. pc]\n  luminosity: 1.e49 s^-1\n"
+                   "source[1]:\n  position: [1.e17 m, 0. m, 3. pc]\n  luminosity: 3.e48 s^-1\n"
+                   "source[2]:\n  position: [-4. pc, -4. pc, 4. pc]\n  luminosity: 4.26e49 s^-1\n")
+    cases = {
+        "ascii": f"PhotonSourceDistribution:\n  type: AsciiFile\n  filename: {yml}\n",
+        "uniform_defaults": "PhotonSourceDistribution:\n  type: UniformRandom\n  number of sources: 24\n",
+        "uniform_evolved": ("PhotonSourceDistribution:\n  type: UniformRandom\n  number of sources: 50\n  random seed: 1234\n"
+                            "  box anchor: [-3. pc, -2. pc, -1. pc]\n  box sides: [6. pc, 4. pc, 2. pc]\n"
+                            "  source lifetime: 2. Myr\n  source luminosity: 3.e48 s^-1\n  update interval: 0.05 Myr\n"
+                            "  starting time: 3.1 Myr\n"),
+        "single": "PhotonSourceDistribution:\n  type: SingleStar\n  position: [1. pc, 2. pc, 3. pc]\n  luminosity: 2.e49 s^-1\n",
+    }
+    for name, text in cases.items():
+        pf = tmp_path / f"{name}.param"
+        pf.write_text(text)
+        rp, rw, rl = ref.photon_source_distribution(pf)
+        p = host.ParameterFile(pf)
+        hp, hw, hl = p.photon_source_distribution()
+        p.close()
+        assert hp.shape == rp.shape and len(hp) > 0, name
+        assert np.array_equal(hp, rp) and np.array_equal(hw, rw) and hl == rl, name
+    assert len(hp) == 1
