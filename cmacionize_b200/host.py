@@ -97,6 +97,12 @@ class ParameterFile:
         n = int(info[0])
         return pos[:n].copy(), w[:n].copy(), info[1]
 
+    def initial_number_density(self, ncells):
+        """number density per cell after DensityFunction + DensityMask on the file's grid (no device needed)"""
+        dens = np.empty(ncells)
+        _check(lib.cmih_initial_number_density(self._h, C.c_int64(ncells), dens.ctypes.data_as(C.c_void_p)))
+        return dens
+
     def density_function(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
         n = x.shape[0]

@@ -178,6 +178,25 @@ int cmih_photon_source_spectrum(void *h, const char *role, double *info, double 
   });
 }
 
+/* the host stage of IonizationSimulation::initialize without a device: DensityFunction evaluated on
+ * the parameter file's Cartesian grid, then the DensityMask (if any) -> number density per cell */
+int cmih_initial_number_density(void *h, int64_t n, double *dens) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<DensityFunction> f(DensityFunctionFactory::generate(p));
+    std::unique_ptr<FractalDensityMask> mask(DensityMaskFactory::generate(p));
+    const SimulationBox box(p);
+    CartesianCells cells(box, p.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}));
+    if ((int64_t)cells.get_number_of_cells() != n) throw std::runtime_error("wrong number of cells");
+    f->initialize();
+    cells.set_densities(*f);
+    if (mask) {
+      mask->initialize();
+      mask->apply(cells);
+    }
+    for (int64_t i = 0; i < n; ++i) dens[i] = cells.number_density[i];
+  });
+}
 /* n deviates of the host-side RandomGenerator (RANLUX level 2, host/RandomGenerator.hpp) */
 int cmih_random_stream(int32_t seed, int64_t n, double *out) {
   CMIH_TRY({

@@ -260,3 +260,26 @@ def test_photon_source_distributions_give_the_reference_sources(host, ref, tmp_p
         assert hp.shape == rp.shape and len(hp) > 0, name
         assert np.array_equal(hp, rp) and np.array_equal(hw, rw) and hl == rl, name
     assert len(hp) == 1
+
+
+def test_fractal_density_mask_gives_the_reference_grid(host, ref, tmp_path):
+    """DensityMask: Fractal — the masked initial grid of the host layer against the grid of the
+    reference's IonizationSimulation::initialize on the same file, cell for cell, bit for bit
+    (mask box smaller than the simulation box, partly smooth gas)."""
+    nc = 16
+    text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+            "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+            f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n  type: Homogeneous\n  density: 50. cm^-3\n"
+            "DensityMask:\n  type: Fractal\n  box anchor: [-4. pc, -5. pc, -3. pc]\n  box sides: [8. pc, 10. pc, 7. pc]\n"
+            "  resolution: [12, 10, 8]\n  number of particles: 20000\n  random seed: 77\n  fractal dimension: 2.4\n"
+            "  number of levels: 3\n  fractal fraction: 0.8\nPhotonSourceSpectrum:\n  type: Monochromatic\n")
+    pf = tmp_path / "fractal.param"
+    pf.write_text(text)
+    sim = ref.Simulation(pf)
+    f = sim.fields()
+    sim.close()
+    p = host.ParameterFile(pf)
+    dens = p.initial_number_density(nc ** 3)
+    p.close()
+    assert np.array_equal(dens, f[0])
+    assert np.unique(dens).size > 100 and abs(dens.sum() / (5e7 * nc ** 3) - 1.) < 1e-12   # clumpy, atoms conserved
