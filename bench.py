@@ -222,6 +222,11 @@ def main():
     ap.add_argument("--cpu-sample", type=float, default=1e6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="lexingtonHII20",
+                    choices=["lexingtonHII20", "stromgren256", "clumpy256", "clumpy256L"],
+                    help="default: the configuration BASELINE.json's metric is quoted on; the 256^3 workloads "
+                         "(north-star target grid, BASELINE.json configs[4]) are recorded under profiles/")
+    ap.add_argument("--spinup-packets", type=float, default=None)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -237,6 +242,19 @@ def main():
               "l2_policy": "accumulators+cells (41 MB) are re-zeroed / rewritten every iteration; "
                            "each step streams 1e8 independent random rays"}
 
+    if args.workload != "lexingtonHII20":
+        if args.impl == "reference":
+            raise SystemExit("the reference arm is timed on the headline workload (lexingtonHII20) only")
+        args.ncell = 256
+        config["workload"] = {"stromgren256": "stromgren.param physics on a 256^3 grid",
+                              "clumpy256": "synthetic clumpy 256^3, 16 sources, H-only (SURVEY 8d item 5)",
+                              "clumpy256L": "synthetic clumpy 256^3, 16 sources, Planck 40000 K + Verner + metals + "
+                                            "diffuse field + temperature solve"}[args.workload]
+        config["grid"] = "256^3"
+        config["physics"] = ("monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field"
+                             if args.workload != "clumpy256L" else config["physics"].replace("20000", "40000"))
+        config["l2_policy"] = "cells + accumulators (0.5 - 2.7 GB) do not fit in L2; every step streams independent random rays"
+        args.no_cpu_baseline = True
     if args.impl == "reference":
         if rank != 0:
             return
@@ -260,7 +278,15 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    prob = problems.lexington(20, ncell=args.ncell, n_packets=n_packets, device=local_rank)
+    if args.workload == "lexingtonHII20":
+        prob = problems.lexington(20, ncell=args.ncell, n_packets=n_packets, device=local_rank)
+    elif args.workload == "stromgren256":
+        prob = problems.stromgren(ncell=256, n_packets=n_packets, device=local_rank)
+    else:
+        prob = problems.synthetic_clumpy(ncell=256, n_packets=n_packets, device=local_rank,
+                                         variant="Lexington" if args.workload == "clumpy256L" else "H")
+    spinup_packets = int(args.spinup_packets) if args.spinup_packets else (
+        1_000_000 if args.workload == "lexingtonHII20" else 16_000_000)
     ctx = prob.ctx
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 
@@ -309,7 +335,7 @@ def main():
 
     loop = 0
     for _ in range(args.spinup):
-        step(loop, npk_total=1_000_000)
+        step(loop, npk_total=spinup_packets)
         loop += 1
     for _ in range(args.warmup):
         step(loop)
@@ -359,9 +385,11 @@ def main():
     crossing_rate = (crossings / world) / (march_ms * 1e-3)
     # one crossing = one scattered gather + red_per_crossing scattered REDs through the same L1TEX pipe
     crossing_bound = 1. / (1. / GATHER_PEAK + red_per_crossing / RED_PEAK)
-    roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    full_layout = args.workload in ("lexingtonHII20", "clumpy256L")
+    roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>" if full_layout else "march_kernel<ACC_HONLY>",
+                "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": 4.604e9, "traffic_note": "dram__bytes_read+write (3.47 + 1.13 GB) of the first march launch "
+                "traffic": 4.604e9 if args.workload == "lexingtonHII20" else None, "traffic_note": "dram__bytes_read+write (3.47 + 1.13 GB) of the first march launch "
                 "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
                 "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
                 "(3.4 GB read) and the re-emission queue (1.1 GB written)",

@@ -109,6 +109,7 @@ struct cmib_context {
   TemperatureParams tp;
   double luminosity = 0.; /* discrete + continuous */
   double discrete_luminosity = 0., continuous_luminosity = 0.;
+  bool planar_geometry_set = false;
   DevBuf<double> d_cont_planck;
   DevBuf<uint16_t> d_cont_planck_guide;
   std::vector<double> h_cont_planck;
@@ -158,13 +159,20 @@ struct cmib_context {
   /* march-queue order: 0 emission order, 1 coarse counting sort (measured slower),
    * 2 coherent march = fine radix sort + in-warp sums (march_kernel<MODE, true>),
    * -1 (default) measured: grids that fit in L2 use 0 (2 loses there on every workload measured);
-   * for larger grids the two are timed on successive large shoots of this context and the faster
-   * one is kept (re-timed every 16 shoots: the ionised volume grows during a run).  Both orders
-   * shoot the same packets; only the order of the atomic adds differs. */
+   * for larger grids the two are timed on successive large shoots of this context — time per cell
+   * crossing, so that the growth of the ionised volume from one shoot to the next does not bias the
+   * comparison — and the faster one is kept (a shoot of >= 4 queue capacities times the two orders on
+   * its own rounds 1 and 2 instead and finishes in the winner).  The timed pair is repeated after 2, 4, 8 and
+   * then every 16 shoots: the regime changes quickly during the first iterations of a run (a small
+   * ionised bubble fits in L2, the converged one may not).  Both orders shoot the same packets; only
+   * the order of the atomic adds differs. */
   int sort_mode = -1;
-  int tune_shoots = 0;                 /* large shoots seen since the last (re)configuration */
-  double tune_ns_per_packet[3] = {0., 0., 0.}; /* indexed by order (0, 2) */
+  int tune_shoots = 0;                 /* large shoots seen */
+  int tune_next = 1;                   /* shoot at which the next timed pair starts */
+  int tune_interval = 2;               /* shoots between the end of a pair and the next one */
+  double tune_ns_per_crossing[3] = {0., 0., 0.}; /* indexed by order (0, 2) */
   int tuned_order = 0;
+  cudaEvent_t tune_ev[3] = {nullptr, nullptr, nullptr};
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2] = {0, 0};
@@ -361,15 +369,25 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   /* coherence sort: on when the gathered + accumulated working set does not fit in L2 */
   int sort = ctx->sort_mode;
   if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
-  bool tuning = false;
+  bool tuning = false;        /* this whole shoot is one half of a timed pair */
+  bool tune_in_shoot = false; /* rounds 1 and 2 of this shoot are the timed pair */
   if (sort < 0) {
     const size_t working_set = (size_t)ctx->geom.ncells * ((mode == ACC_HONLY ? 16 : sizeof(CellOpacity)) + (mode == ACC_HONLY ? 16 : 128));
     if (working_set <= ctx->l2_bytes || P.n_packets < (1ull << 20)) {
       sort = (working_set <= ctx->l2_bytes) ? 0 : ctx->tuned_order;
     } else {
-      const int phase = ctx->tune_shoots % 16; /* 0: warm-up (allocations), 1: time order 0, 2: time order 2 */
-      sort = (phase == 1) ? 0 : (phase == 2 ? 2 : ctx->tuned_order);
-      tuning = (phase == 1 || phase == 2);
+      /* shoot 0 is a warm-up (allocations); a timed pair = order 0, then order 2 */
+      const int phase = ctx->tune_shoots - ctx->tune_next;
+      /* a shoot of at least four full queues carries the pair itself: its rounds 1 and 2 (same grid
+       * state, same mix of primaries and re-emitted packets) run in order 0 and in order 2, the rest
+       * in the winner — one round of ~n/capacity in the slower order instead of a whole shoot */
+      tune_in_shoot = (phase == 0 && P.n_packets >= 4 * cap);
+      sort = tune_in_shoot ? 2 : ((phase == 0) ? 0 : (phase == 1 ? 2 : ctx->tuned_order));
+      tuning = !tune_in_shoot && (phase == 0 || phase == 1);
+      if (phase == 1 || tune_in_shoot) {
+        ctx->tune_next = ctx->tune_shoots + 1 + ctx->tune_interval;
+        if (ctx->tune_interval < 16) ctx->tune_interval *= 2;
+      }
       ++ctx->tune_shoots;
     }
   }
@@ -465,14 +483,24 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
    * the plain kernel is bound by L1TEX lanes, not latency (no gain; -16 % with the full layout's spills) */
   int prefetch_cfg = -1;
   if (const char *e = getenv("CMIB_PREFETCH")) prefetch_cfg = atoi(e) != 0;
-  if (tuning) CUDA_OK(cudaStreamSynchronize(s)); /* buffers are allocated, earlier work is done: time the shoot alone */
+  double tune_crossings0 = 0.;
+  if (tuning) { /* buffers are allocated; wait for earlier work: time the shoot alone */
+    CUDA_OK(cudaMemcpyAsync(&tune_crossings0, ctx->acc.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
   const auto tune_t0 = std::chrono::steady_clock::now();
   uint64_t items_bound = cap;
   bool primaries_left = true;
+  int order_now = tune_in_shoot ? ctx->tuned_order : sort_cfg;
+  if (tune_in_shoot && !ctx->tune_ev[0])
+    for (int k = 0; k < 3; ++k) CUDA_OK(cudaEventCreate(&ctx->tune_ev[k]));
   while (round < 1000000) {
     for (int k = 0; k < group; ++k, ++round) {
+      if (tune_in_shoot && round >= 1 && round <= 3) CUDA_OK(cudaEventRecord(ctx->tune_ev[round - 1], s));
       if (sort_cfg == 2) {
-        W.sort = (primaries_left || sort_reemitted_rounds) ? 2 : 0;
+        W.sort = (order_now == 2 && (primaries_left || sort_reemitted_rounds)) ? 2 : 0;
+        if (tune_in_shoot && round == 1) W.sort = 0;
+        if (tune_in_shoot && round == 2) W.sort = 2;
         W.sort_n = items_bound;
       }
       const int sort = W.sort;
@@ -523,6 +551,18 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     for (int k = 0; k < group; ++k)
       if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;
     if (done) break;
+    if (tune_in_shoot && round == (uint64_t)group) { /* the stream is idle: rounds 1 and 2 are timed */
+      float ms0 = 0.f, ms2 = 0.f;
+      cudaEventElapsedTime(&ms0, ctx->tune_ev[0], ctx->tune_ev[1]);
+      cudaEventElapsedTime(&ms2, ctx->tune_ev[1], ctx->tune_ev[2]);
+      const double n0 = (double)ctx->h_ctl[CTL_STATUS + 1], n2 = (double)ctx->h_ctl[CTL_STATUS + 2];
+      if (n0 > 0. && n2 > 0.) {
+        ctx->tune_ns_per_crossing[0] = 1e6 * ms0 / n0; /* per queue entry here */
+        ctx->tune_ns_per_crossing[2] = 1e6 * ms2 / n2;
+        ctx->tuned_order = (ms2 / n2 < ms0 / n0) ? 2 : 0;
+      }
+      order_now = ctx->tuned_order;
+    }
     if (ctx->h_ctl[CTL_REMAINING] == 0) {
       primaries_left = false;
       const uint64_t last = ctx->h_ctl[CTL_STATUS + ((round - 1) % CTL_STATUS_SLOTS)];
@@ -541,8 +581,12 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   if (tuning) {
     /* every group of rounds ends with a stream synchronisation: host time = device time here */
     const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tune_t0).count();
-    ctx->tune_ns_per_packet[sort_cfg] = ns / (double)P.n_packets;
-    if (sort_cfg == 2) ctx->tuned_order = (ctx->tune_ns_per_packet[2] < ctx->tune_ns_per_packet[0]) ? 2 : 0;
+    double crossings = 0.; /* counter 5 of the accumulator buffer: cell crossings (shoot.cuh) */
+    CUDA_OK(cudaMemcpyAsync(&crossings, ctx->acc.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_OK(cudaStreamSynchronize(s));
+    crossings -= tune_crossings0;
+    ctx->tune_ns_per_crossing[sort_cfg] = ns / (crossings > 1. ? crossings : 1.);
+    if (sort_cfg == 2) ctx->tuned_order = (ctx->tune_ns_per_crossing[2] < ctx->tune_ns_per_crossing[0]) ? 2 : 0;
   }
   for (size_t k = 0; k + 3 < ev_used; k += 4) {
     float a = 0.f, b = 0.f;
@@ -642,6 +686,8 @@ int cmib_destroy(cmib_context *ctx) {
   cudaStreamDestroy(ctx->stream);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->tune_ev)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -817,6 +863,20 @@ int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, cons
   return 0;
 }
 
+int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double intercept, const double anchor[2],
+                                    const double sides[2]) {
+  CHECK_CTX(ctx);
+  if (normal_axis < 0 || normal_axis > 2 || !anchor || !sides) CMIB_FAIL("normal axis must be 0, 1 or 2");
+  ctx->src.planar_axis = normal_axis;
+  ctx->src.planar_intercept = intercept;
+  for (int k = 0; k < 2; ++k) {
+    ctx->src.planar_anchor[k] = anchor[k];
+    ctx->src.planar_sides[k] = sides[k];
+  }
+  ctx->planar_geometry_set = true;
+  return 0;
+}
+
 int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, int spectrum_kind,
                                double spectrum_param) {
   CHECK_CTX(ctx);
@@ -826,14 +886,17 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
     ctx->update_source_weights();
     return 0;
   }
-  if (kind != CMIB_CONTINUOUS_ISOTROPIC) CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR)
+    CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (kind == CMIB_CONTINUOUS_PLANAR && !ctx->planar_geometry_set)
+    CMIB_FAIL("call cmib_set_planar_source_geometry before selecting the Planar continuous source");
   if (!(luminosity > 0.)) CMIB_FAIL("the continuous source needs a positive luminosity (surface area x total flux)");
   /* CMIB_SPECTRUM_TABULATED: the table was (or will be) given with cmib_set_spectrum_table(ctx, 1, ...) */
   if (spectrum_kind != CMIB_SPECTRUM_TABULATED &&
       set_spectrum_model(ctx, ctx->src.cont_spectrum, ctx->h_cont_planck, ctx->d_cont_planck, ctx->d_cont_planck_guide,
                          spectrum_kind, spectrum_param))
     return 1;
-  ctx->src.continuous_kind = CONTINUOUS_ISOTROPIC;
+  ctx->src.continuous_kind = (kind == CMIB_CONTINUOUS_PLANAR) ? CONTINUOUS_PLANAR : CONTINUOUS_ISOTROPIC;
   ctx->continuous_luminosity = luminosity;
   ctx->update_source_weights();
   return 0;

@@ -32,7 +32,7 @@ namespace cmib {
 
 enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1, SPECTRUM_UNIFORM = 2, SPECTRUM_TABULATED = 3 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
-enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1 };
+enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
@@ -65,6 +65,10 @@ struct SourceModel {
   double discrete_weight;        /* 1 (0 without discrete sources) */
   double continuous_weight;      /* L_continuous / L_discrete (1 without discrete sources) */
   int continuous_kind;
+  /* CONTINUOUS_PLANAR (PlanarContinuousPhotonSource.hpp:50-131): the plane coordinate[planar_axis] =
+   * planar_intercept, rectangle anchor + [0, sides) in the two other coordinates (ascending index) */
+  int planar_axis;
+  double planar_intercept, planar_anchor[2], planar_sides[2];
   SpectrumModel cont_spectrum;   /* spectrum of the continuous source */
   SpectrumModel spectrum;        /* spectrum of the discrete sources */
   /* cross sections */
@@ -176,6 +180,33 @@ CMIB_HD void isotropic_incoming(const GridGeom &g, const double *u, double &px, 
   pz = (pz < g.anchor[2]) ? g.anchor[2] : pz;
 }
 
+/* PlanarContinuousPhotonSource::get_random_incoming_direction (.hpp:179-204): a point uniform on the
+ * rectangle (u[0], u[1]), an isotropic direction (u[2], u[3]) — both half-spaces, as in the reference */
+CMIB_HD void planar_incoming(int axis, double intercept, const double *anchor, const double *sides, const double *u,
+                             double &px, double &py, double &pz, double &dx, double &dy, double &dz) {
+  const int i0 = (axis + 1) % 3, i1 = (axis + 2) % 3;
+  const int lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+  double p[3];
+  p[lo] = anchor[0] + u[0] * sides[0];
+  p[hi] = anchor[1] + u[1] * sides[1];
+  p[axis] = intercept;
+  px = p[0]; py = p[1]; pz = p[2];
+  const double cost = 2. * u[2] - 1.;
+  const double s2 = 1. - cost * cost;
+  const double sint = sqrt(s2 > 0. ? s2 : 0.);
+  const double phi = 2. * M_PI * u[3];
+  double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &sinp, &cosp);
+#else
+  cosp = cos(phi);
+  sinp = sin(phi);
+#endif
+  dx = sint * cosp;
+  dy = sint * sinp;
+  dz = cost;
+}
+
 CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
   const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
@@ -262,9 +293,15 @@ CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, PacketRng &rn
     nu = spectrum_frequency(m.spectrum, rng);
   } else {
     double u[5];
+    if (m.continuous_kind == CONTINUOUS_PLANAR) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
-    isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
+      for (int k = 0; k < 4; ++k) u[k] = rng_uniform(rng);
+      planar_incoming(m.planar_axis, m.planar_intercept, m.planar_anchor, m.planar_sides, u, px, py, pz, dx, dy, dz);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
+      isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
+    }
     isrc = -1;
     nu = spectrum_frequency(m.cont_spectrum, rng);
   }

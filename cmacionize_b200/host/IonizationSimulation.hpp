@@ -279,6 +279,139 @@ private:
   std::vector<double> grid_;
 };
 
+/* InterpolatedDensityFunction (src/InterpolatedDensityFunction.cpp:40-369): a 1-, 2- or 3-D table of
+ * number densities (a YAML header between two "---" lines names the columns and their units, rows
+ * follow with x slowest / z fastest), trilinear interpolation at the cell midpoint; an axis with
+ * fewer than two points is constant between its bounds.  Like the reference's reader this one
+ * never rewinds an axis index while reading rows (:213-247), i.e. tables with ONE non-trivial axis
+ * are what works; where the reference then writes out of bounds this reader reports an error. */
+class InterpolatedDensityFunction : public DensityFunction {
+public:
+  InterpolatedDensityFunction(const std::string &filename, double temperature) : temperature_(temperature) {
+    std::ifstream file(filename);
+    if (!file) cmi_error("Error while opening file \"%s\"!", filename.c_str());
+    std::string line;
+    while (std::getline(file, line) && line != "---") {
+    }
+    if (line != "---") cmi_error("No YAML block found in file \"%s\"!", filename.c_str());
+    std::string yaml_block;
+    while (std::getline(file, line) && line != "---") yaml_block += line + "\n";
+    if (line != "---") cmi_error("Reached end of file \"%s\" while parsing YAML block!", filename.c_str());
+    std::istringstream yaml_stream(yaml_block);
+    YAMLDictionary yaml(yaml_stream);
+    const char *axis_name[3] = {"x", "y", "z"};
+    uint32_t num[3];
+    for (int d = 0; d < 3; ++d) num[d] = yaml.get_value<uint32_t>(std::string("num_") + axis_name[d]);
+    for (int d = 0; d < 3; ++d) {
+      bounds_[d][0] = yaml.get_physical_value<QUANTITY_LENGTH>(std::string(axis_name[d]) + "min");
+      bounds_[d][1] = yaml.get_physical_value<QUANTITY_LENGTH>(std::string(axis_name[d]) + "max");
+    }
+    const uint32_t num_column = yaml.get_value<uint32_t>("num_column");
+    std::map<std::string, uint32_t> name_to_column;
+    std::vector<std::string> units(num_column);
+    for (uint32_t i = 0; i < num_column; ++i) {
+      const std::string column = "column_" + std::to_string(i) + "_";
+      const std::string name = yaml.get_value<std::string>(column + "variable");
+      units[i] = yaml.get_value<std::string>(column + "unit");
+      name_to_column[name] = i;
+    }
+    if (num[0] == 0 && num[1] == 0 && num[2] == 0)
+      cmi_error("No coordinate values provided! We need at least one non-trivial coordinate axis.");
+    const char *axis_upper[3] = {"X", "Y", "Z"};
+    for (int d = 0; d < 3; ++d)
+      if (bounds_[d][0] > bounds_[d][1]) cmi_error("Minimal %s value larger than maximal %s value!", axis_upper[d], axis_upper[d]);
+    uint32_t column_of[3] = {0, 0, 0};
+    for (int d = 0; d < 3; ++d) {
+      if (num[d] != 0) {
+        if (name_to_column.count(axis_name[d]) == 0) cmi_error("No column found containing %s values!", axis_name[d]);
+        column_of[d] = name_to_column[axis_name[d]];
+      }
+      if (num[d] > 1) {
+        coords_[d].assign(num[d], 0.);
+      } else {
+        coords_[d] = {bounds_[d][0], bounds_[d][1]};
+      }
+    }
+    if (name_to_column.count("number density") == 0) cmi_error("No column found containing number density values!");
+    const uint32_t density_column = name_to_column["number density"];
+    const size_t ny = coords_[1].size(), nz = coords_[2].size();
+    densities_.assign(coords_[0].size() * ny * nz, 0.);
+    size_t idx[3] = {0, 0, 0}, i = 0;
+    while (std::getline(file, line)) {
+      std::stringstream lstream(line);
+      std::vector<double> row(num_column);
+      for (uint32_t j = 0; j < num_column; ++j) lstream >> row[j];
+      for (int d = 0; d < 3; ++d) {
+        if (num[d] == 0) continue;
+        const double next = UnitConverter::to_SI(QUANTITY_LENGTH, row[column_of[d]], units[column_of[d]]);
+        if (i > 0 && next != coords_[d][idx[d]]) {
+          ++idx[d];
+          if (idx[d] >= coords_[d].size())
+            cmi_error("Too many different %s values in file \"%s\"!", axis_name[d], filename.c_str());
+        }
+        coords_[d][idx[d]] = next;
+      }
+      densities_[(idx[0] * ny + idx[1]) * nz + idx[2]] =
+          UnitConverter::to_SI(QUANTITY_NUMBER_DENSITY, row[density_column], units[density_column]);
+      ++i;
+    }
+    /* complete the axes that have a single value (:264-289) */
+    const size_t nx = coords_[0].size();
+    if (num[0] < 2)
+      for (size_t iy = 0; iy < ny; ++iy)
+        for (size_t iz = 0; iz < nz; ++iz) densities_[(1 * ny + iy) * nz + iz] = densities_[(0 * ny + iy) * nz + iz];
+    if (num[1] < 2)
+      for (size_t ix = 0; ix < nx; ++ix)
+        for (size_t iz = 0; iz < nz; ++iz) densities_[(ix * ny + 1) * nz + iz] = densities_[(ix * ny + 0) * nz + iz];
+    if (num[2] < 2)
+      for (size_t ix = 0; ix < nx; ++ix)
+        for (size_t iy = 0; iy < ny; ++iy) densities_[(ix * ny + iy) * nz + 1] = densities_[(ix * ny + iy) * nz + 0];
+  }
+  explicit InterpolatedDensityFunction(ParameterFile &params)
+      : InterpolatedDensityFunction(params.get_filename("DensityFunction:filename"),
+                                    params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "8000. K")) {}
+
+  DensityValues operator()(const Vec3 &position) override {
+    size_t i[3];
+    double w[3], omw[3];
+    for (int d = 0; d < 3; ++d) {
+      i[d] = locate_bin(position[d], coords_[d].data(), (uint32_t)coords_[d].size());
+      w[d] = (position[d] - coords_[d][i[d]]) / (coords_[d][i[d] + 1] - coords_[d][i[d]]);
+      omw[d] = 1. - w[d];
+    }
+    const size_t ny = coords_[1].size(), nz = coords_[2].size();
+    auto n = [&](size_t ix, size_t iy, size_t iz) { return densities_[(ix * ny + iy) * nz + iz]; };
+    const double c00 = n(i[0], i[1], i[2]) * omw[0] + n(i[0] + 1, i[1], i[2]) * w[0];
+    const double c01 = n(i[0], i[1], i[2] + 1) * omw[0] + n(i[0] + 1, i[1], i[2] + 1) * w[0];
+    const double c10 = n(i[0], i[1] + 1, i[2]) * omw[0] + n(i[0] + 1, i[1] + 1, i[2]) * w[0];
+    const double c11 = n(i[0], i[1] + 1, i[2] + 1) * omw[0] + n(i[0] + 1, i[1] + 1, i[2] + 1) * w[0];
+    const double c0 = c00 * omw[1] + c10 * w[1];
+    const double c1 = c01 * omw[1] + c11 * w[1];
+    DensityValues v;
+    v.number_density = c0 * omw[2] + c1 * w[2];
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = 1.e-6;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  /* Utilities::locate (src/Utilities.hpp:726-742) */
+  static size_t locate_bin(double x, const double *xarr, uint32_t length) {
+    uint32_t jl = 0, ju = length;
+    while (ju - jl > 1) {
+      const uint32_t jm = (ju + jl) >> 1;
+      if (x > xarr[jm]) jl = jm; else ju = jm;
+    }
+    if (jl == length - 1) --jl;
+    return jl;
+  }
+  double temperature_;
+  double bounds_[3][2];
+  std::vector<double> coords_[3];
+  std::vector<double> densities_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -286,7 +419,9 @@ struct DensityFunctionFactory {
     if (type == "Homogeneous") return new HomogeneousDensityFunction(params);
     if (type == "BlockSyntax") return new BlockSyntaxDensityFunction(params);
     if (type == "AsciiFile") return new AsciiFileDensityFunction(params);
-    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax and AsciiFile)!",
+    if (type == "Interpolated") return new InterpolatedDensityFunction(params);
+    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile and "
+              "Interpolated)!",
               type.c_str());
   }
 };
@@ -1038,17 +1173,36 @@ public:
      * (IonizationSimulation.cpp:164-174) */
     const std::string continuous_type = parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None");
     if (log_) log_->write_info("Requested ContinuousPhotonSource type: ", continuous_type, ".");
-    if (continuous_type != "None" && continuous_type != "Isotropic")
-      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic)!", continuous_type.c_str());
+    if (continuous_type != "None" && continuous_type != "Isotropic" && continuous_type != "Planar")
+      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic and Planar)!",
+                continuous_type.c_str());
+    /* PlanarContinuousPhotonSource(ParameterFile&) (src/PlanarContinuousPhotonSource.hpp:133-151) */
+    int planar_axis = 2;
+    double planar_intercept = 0., planar_anchor[2] = {0., 0.}, planar_sides[2] = {1., 1.}, planar_luminosity = 0.;
+    if (continuous_type == "Planar") {
+      const std::string axis = parameter_file_.get_value<std::string>("ContinuousPhotonSource:normal axis", "z");
+      if (axis == "x") planar_axis = 0;
+      else if (axis == "y") planar_axis = 1;
+      else if (axis == "z") planar_axis = 2;
+      else cmi_error("Unknown coordinate axis name: \"%s\"!", axis.c_str());
+      planar_intercept = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:intercept", "0. m");
+      planar_anchor[0] = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:anchor 0", "0. m");
+      planar_anchor[1] = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:anchor 1", "0. m");
+      planar_sides[0] = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:side 0", "1. m");
+      planar_sides[1] = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:side 1", "1. m");
+      planar_luminosity = parameter_file_.get_physical_value<QUANTITY_FREQUENCY>("ContinuousPhotonSource:luminosity", "1.e48 s^-1");
+    }
     continuous_photon_source_spectrum_.reset(
         PhotonSourceSpectrum::generate("ContinuousPhotonSourceSpectrum", parameter_file_, log_));
-    const bool has_continuous = (continuous_type == "Isotropic");
+    const bool has_continuous = (continuous_type != "None");
     if (has_continuous && !continuous_photon_source_spectrum_)
       cmi_error("No spectrum provided for the continuous photon sources!");
     if (!photon_source_distribution_ && !has_continuous) cmi_error("No photon sources!");
     double continuous_luminosity = 0.;
-    if (has_continuous) {
-      /* PhotonSource.cpp:101-108: total surface area (IsotropicContinuousPhotonSource.hpp:187-192) x total flux */
+    if (continuous_type == "Planar") {
+      continuous_luminosity = planar_luminosity; /* has_total_luminosity() (PhotonSource.cpp:101-103) */
+    } else if (has_continuous) {
+      /* PhotonSource.cpp:104-108: total surface area (IsotropicContinuousPhotonSource.hpp:187-192) x total flux */
       if (continuous_photon_source_spectrum_->total_flux < 0.) cmi_error("This function should not be used!");
       const double area = 2. * box.sides[0] * box.sides[1] + 2. * box.sides[0] * box.sides[2] +
                           2. * box.sides[1] * box.sides[2];
@@ -1076,7 +1230,10 @@ public:
       if (ns > 0) CMIB_CALL(photon_source_spectrum_->set_on(ctx, 0));
       if (has_continuous) {
         CMIB_CALL(continuous_photon_source_spectrum_->set_on(ctx, 1));
-        CMIB_CALL(cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_ISOTROPIC, continuous_luminosity,
+        if (continuous_type == "Planar")
+          CMIB_CALL(cmib_set_planar_source_geometry(ctx, planar_axis, planar_intercept, planar_anchor, planar_sides));
+        CMIB_CALL(cmib_set_continuous_source(ctx, continuous_type == "Planar" ? CMIB_CONTINUOUS_PLANAR : CMIB_CONTINUOUS_ISOTROPIC,
+                                             continuous_luminosity,
                                              continuous_photon_source_spectrum_->kind,
                                              continuous_photon_source_spectrum_->param));
       }

@@ -56,7 +56,7 @@ typedef struct cmib_grid_desc {
 enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
 enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
 enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1, CMIB_SPECTRUM_UNIFORM = 2, CMIB_SPECTRUM_TABULATED = 3 };
-enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1 };
+enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1, CMIB_CONTINUOUS_PLANAR = 2 };
 enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
 
 /* TemperatureCalculator parameters (src/TemperatureCalculator.cpp:133-160) */
@@ -138,6 +138,13 @@ int cmib_set_spectrum_table(cmib_context *ctx, int role, int32_t n, const double
  * n_sources = 0 (PhotonSourceDistribution: None) when this is set.  kind NONE removes it. */
 int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, int spectrum_kind,
                                double spectrum_param);
+/* geometry of a PLANAR continuous source (src/PlanarContinuousPhotonSource.hpp:101-131): an
+ * isotropically emitting rectangle in the plane coordinate[normal_axis] = intercept, spanning
+ * anchor[k] .. anchor[k] + sides[k] in the two other coordinates (in ascending coordinate order);
+ * call before cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_PLANAR, luminosity, ...), whose luminosity
+ * is the source's own (ContinuousPhotonSource:luminosity), not area x flux */
+int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double intercept, const double anchor[2],
+                                    const double sides[2]);
 /* DiffuseReemissionHandlerFactory (src/DiffuseReemissionHandlerFactory.hpp:59-107);
  * probability / frequency (Hz) are used by FIXED_VALUE only.  Builds the H-Lyc /
  * He-Lyc / He-2-photon tables from the CURRENT cross sections, as the reference's

@@ -247,6 +247,16 @@ def photon_source_distribution(paramfile, capacity=4096):
     return pos[:n].copy(), w[:n].copy(), info[1]
 
 
+def planar_incoming(axis, intercept, anchor, sides, n, seed=42):
+    """(uniforms [n,4], positions [n,3], directions [n,3]) of PlanarContinuousPhotonSource"""
+    a = np.ascontiguousarray(anchor, dtype=np.float64)
+    sd = np.ascontiguousarray(sides, dtype=np.float64)
+    u, pos, d = np.empty((n, 4)), np.empty((n, 3)), np.empty((n, 3))
+    lib().cmi_ref_planar_incoming(C.c_int(axis), C.c_double(intercept), _p(a), _p(sd), C.c_int(seed), C.c_int64(n),
+                                  _p(u), _p(pos), _p(d))
+    return u, pos, d
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

@@ -54,6 +54,7 @@
 #include "LineCoolingData.hpp"
 #include "Photon.hpp"
 #include "PhotonSource.hpp"
+#include "PlanarContinuousPhotonSource.hpp"
 #include "PhotonSourceDistributionFactory.hpp"
 #include "PhysicalDiffuseReemissionHandler.hpp"
 #include "PlanckPhotonSourceSpectrum.hpp"
@@ -598,6 +599,23 @@ void cmi_ref_isotropic_incoming(const double *anchor, const double *sides, int s
   RandomGenerator rg(seed), replay(seed);
   for (int64_t i = 0; i < n; ++i) {
     for (int k = 0; k < 5; ++k) uniforms[5 * i + k] = replay.get_uniform_random_double();
+    const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = pd.first[k];
+      dir[3 * i + k] = pd.second[k];
+    }
+  }
+}
+
+/* PlanarContinuousPhotonSource::get_random_incoming_direction (src/PlanarContinuousPhotonSource.hpp:179-204),
+ * n times, with the four deviates each call consumed */
+void cmi_ref_planar_incoming(int axis, double intercept, const double *anchor, const double *sides, int seed,
+                             int64_t n, double *uniforms, double *pos, double *dir) {
+  const char *names[3] = {"x", "y", "z"};
+  PlanarContinuousPhotonSource source(names[axis], intercept, anchor[0], anchor[1], sides[0], sides[1], 1.e48);
+  RandomGenerator rg(seed), replay(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int k = 0; k < 4; ++k) uniforms[4 * i + k] = replay.get_uniform_random_double();
     const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
     for (int k = 0; k < 3; ++k) {
       pos[3 * i + k] = pd.first[k];

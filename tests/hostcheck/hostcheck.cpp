@@ -149,6 +149,13 @@ void hc_isotropic_incoming(const double *anchor, const double *sides, int64_t n,
                        dir[3 * i + 2]);
 }
 
+void hc_planar_incoming(int axis, double intercept, const double *anchor, const double *sides, int64_t n,
+                        const double *uniforms, double *pos, double *dir) {
+  for (int64_t i = 0; i < n; ++i)
+    planar_incoming(axis, intercept, anchor, sides, uniforms + 4 * i, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2],
+                    dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+}
+
 /* tabulated (freq != NULL) or Uniform spectrum sampled with the given deviates */
 void hc_tabulated_frequency(int32_t m, const double *freq, const double *cdf, int64_t n, const double *x, double *nu) {
   for (int64_t i = 0; i < n; ++i) nu[i] = freq ? tabulated_frequency(freq, cdf, (uint32_t)m, x[i]) : uniform_frequency(x[i]);

@@ -1,7 +1,8 @@
-"""GPU tier: IsotropicContinuousPhotonSource (src/IsotropicContinuousPhotonSource.hpp,
-PhotonSource.cpp:100-131, 208-249) end to end through the C++ host driver — parameter files with
-an external radiation field alone and with a star + external field (tests/golden/continuous/), against
-two runs of the compiled reference on the same file (seeds 42 / 4242).
+"""GPU tier: continuous photon sources (src/IsotropicContinuousPhotonSource.hpp,
+src/PlanarContinuousPhotonSource.hpp, PhotonSource.cpp:100-131, 208-249) end to end through the C++ host
+driver — parameter files with an external radiation field alone, a star + external field, and an
+emitting sheet in the mid-plane (tests/golden/continuous/), against two runs of the compiled reference on
+the same file (seeds 42 / 4242).
 
 The geometry is not spherical, so cells are compared directly: the per-cell deviation from reference
 run A must not exceed the deviation between the two reference runs (Monte Carlo noise), the ionised
@@ -25,7 +26,7 @@ def make_paramfile(tmp_path, name, seed):
     return pf
 
 
-@pytest.mark.parametrize("name", ["external_field", "star_plus_external_field"])
+@pytest.mark.parametrize("name", ["external_field", "star_plus_external_field", "planar_sheet"])
 def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     nc = 32
     runs = [ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)[0] for seed in (42, 4242)]
@@ -48,7 +49,10 @@ def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     # mean neutral fraction per shell of equal depth below the nearest face
     i = np.arange(nc)
     depth1 = np.minimum(i, nc - 1 - i)
-    depth = np.minimum.reduce(np.meshgrid(depth1, depth1, depth1, indexing="ij")).ravel()
+    if name == "planar_sheet":   # distance from the sheet instead
+        depth = np.meshgrid(i, i, np.abs(i - (nc - 1) / 2.).astype(int), indexing="ij")[2].ravel()
+    else:
+        depth = np.minimum.reduce(np.meshgrid(depth1, depth1, depth1, indexing="ij")).ravel()
     for d in range(nc // 2):
         sel = depth == d
         ma, mb, mg = a[sel].mean(), b[sel].mean(), g[sel].mean()

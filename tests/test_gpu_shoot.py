@@ -169,7 +169,7 @@ def test_shoot_is_deterministic_and_shardable(cmib):
 
 
 @pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
-                                    "continuous", "continuous_only"])
+                                    "continuous", "continuous_only", "planar"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -196,6 +196,12 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
         prob.ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 0.25 * 4.26e49, capi.SPECTRUM_MONOCHROMATIC,
                                        problems.ev_to_hz(13.6))
+    elif config == "planar":
+        # PlanarContinuousPhotonSource: an emitting sheet on a cell boundary (packets start ON a wall)
+        prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
+        prob.ctx.set_sources(None, None, 0.)
+        prob.ctx.set_planar_source_geometry(2, 0., [-4 * PC, -5 * PC], [8 * PC, 10 * PC])
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_PLANAR, 3e49, capi.SPECTRUM_MONOCHROMATIC, problems.ev_to_hz(13.6))
     elif config == "continuous_only":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
         prob.ctx.set_sources(None, None, 0.)

@@ -136,10 +136,28 @@ def test_parameter_file_same_values_and_used_values_dump(host, ref, tmp_path):
         host.ParameterFile(bad).density_function(np.zeros((1, 3)))
 
 
-@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks", "ascii_file"])
+@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks", "ascii_file", "interpolated_1d"])
 def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     nc = 12
-    if kind == "ascii_file":
+    if kind.startswith("interpolated"):
+        # InterpolatedDensityFunction: a z profile (the reference's own test file format,
+        # test/test_interpolated_density.txt) sampled by the 12^3 grid
+        rng = np.random.default_rng(9)
+        # (one non-trivial axis: the reference's row bookkeeping never rewinds an axis index,
+        # InterpolatedDensityFunction.cpp:213-247, so 2-D / 3-D tables run out of bounds there)
+        zs = np.linspace(-5., 5., 23)
+        head = ("---\nnum_x: 0\nxmin: -5. pc\nxmax: 5. pc\nnum_y: 0\nymin: -5. pc\nymax: 5. pc\n"
+                "num_z: 23\nzmin: -5. pc\nzmax: 5. pc\nnum_column: 2\ncolumn_0_variable: z\ncolumn_0_unit: pc\n"
+                "column_1_variable: number density\ncolumn_1_unit: cm^-3\n---\n")
+        rows = [f"{float(z)!r} {float(rng.uniform(1., 300.))!r}" for z in zs]
+        dfile = tmp_path / "profile.txt"
+        dfile.write_text(head + "\n".join(rows) + "\n")
+        text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+                "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+                f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n  type: Interpolated\n  filename: {dfile}\n"
+                "  temperature: 6000. K\nPhotonSourceSpectrum:\n  type: Monochromatic\n")
+        half = 5 * PC
+    elif kind == "ascii_file":
         # AsciiFileDensityFunction: a 6 x 4 x 3 table of its own (cell centres in pc, densities in cm^-3)
         # sampled by the 12^3 simulation grid
         rng = np.random.default_rng(4)
@@ -149,7 +167,7 @@ def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
             for j in range(nf[1]):
                 for k in range(nf[2]):
                     c = [-5. + 10. * (q + 0.5) / n for q, n in zip((i, j, k), nf)]
-                    rows.append(f"{c[0]!r} {c[1]!r} {c[2]!r} {rng.uniform(1., 200.)!r}")
+                    rows.append(f"{c[0]!r} {c[1]!r} {c[2]!r} {float(rng.uniform(1., 200.))!r}")
         dfile = tmp_path / "density.txt"
         dfile.write_text("\n".join(rows) + "\n")
         text = ("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
@@ -180,6 +198,9 @@ def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], 1)
     dens, temp, xH = host.ParameterFile(pf).density_function(x)
     assert np.array_equal(dens, f[0]) and np.array_equal(temp, f[1]) and np.array_equal(xH, f[2])
+    assert np.isfinite(dens).all()
+    if kind in ("ascii_file", "interpolated_1d"):
+        assert np.unique(dens).size > 20 and dens.min() >= 1e6 and dens.max() <= 3e8
     if kind == "lexington_blocks":
         assert (dens == 0).sum() > 0 and (dens > 0).sum() > 0
 

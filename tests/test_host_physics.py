@@ -207,3 +207,16 @@ def test_tabulated_and_uniform_spectra_bitexact(hostcheck, ref):
     nu = np.empty(50000)
     hostcheck.hc_tabulated_frequency(C.c_int32(0), None, None, C.c_int64(nu.size), p(u), p(nu))
     assert np.array_equal(nu, nu_ref)
+
+
+def test_planar_continuous_source_bitexact(hostcheck, ref):
+    """PlanarContinuousPhotonSource::get_random_incoming_direction for the three normal axes, fed with
+    the reference generator's own deviates: position on the rectangle and direction, bit for bit."""
+    for axis in range(3):
+        anchor, sides, intercept = np.array([-1e17, 2e16]), np.array([3e17, 5e16]), 1.5e16 * (axis - 1)
+        u, pos, d = ref.planar_incoming(axis, intercept, anchor, sides, 20000, seed=11 + axis)
+        pos2, d2 = np.empty_like(pos), np.empty_like(d)
+        hostcheck.hc_planar_incoming(C.c_int(axis), C.c_double(intercept), p(anchor), p(sides), C.c_int64(len(u)),
+                                     p(np.ascontiguousarray(u)), p(pos2), p(d2))
+        assert np.array_equal(pos2, pos) and np.array_equal(d2, d)
+        assert (pos2[:, axis] == intercept).all()
