@@ -411,7 +411,8 @@ def main():
                                    "binding unit is L1TEX (scattered gather + RED lanes, 88 % busy), so the meaningful "
                                    "denominator is the measured scattered-RED ceiling, not HBM"}}
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+    metric = METRIC if args.workload == "lexingtonHII20" else METRIC.replace("lexingtonHII20", args.workload)
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "s_per_iteration": ms_per_step * 1e-3, "roofline": roofline, "gpu_launches": int(launches),
