@@ -175,7 +175,7 @@ struct cmib_context {
   cudaEvent_t tune_ev[3] = {nullptr, nullptr, nullptr};
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
-  int march_blocks_per_sm[2] = {0, 0};
+  int march_blocks_per_sm[2][2] = {{0, 0}, {0, 0}}; /* [layout][plain, coherent] */
   int prep_blocks_per_sm[2] = {0, 0};
   int decide_blocks_per_sm = 0;
   uint64_t shoot_rounds = 0;
@@ -346,14 +346,15 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   if (!ctx->ctl.p) {
     CUDA_OK(ctx->ctl.resize(CTL_WORDS));
     CUDA_OK(cudaMallocHost((void **)&ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long)));
-    /* the plain and the coherent variant of a layout run with the same grid: the smaller occupancy */
     int occ[4] = {0, 0, 0, 0};
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false, true>, MARCH_BLOCK, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], march_kernel<ACC_FULL, true, true>, MARCH_BLOCK, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], march_kernel<ACC_HONLY, false, true>, MARCH_BLOCK, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], march_kernel<ACC_HONLY, true, true>, MARCH_BLOCK, 0));
-    ctx->march_blocks_per_sm[ACC_FULL] = occ[0] < occ[1] ? occ[0] : occ[1];
-    ctx->march_blocks_per_sm[ACC_HONLY] = occ[2] < occ[3] ? occ[2] : occ[3];
+    ctx->march_blocks_per_sm[ACC_FULL][0] = occ[0];
+    ctx->march_blocks_per_sm[ACC_FULL][1] = occ[1];
+    ctx->march_blocks_per_sm[ACC_HONLY][0] = occ[2];
+    ctx->march_blocks_per_sm[ACC_HONLY][1] = occ[3];
   }
   cudaStream_t s = ctx->stream;
   memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
@@ -454,10 +455,13 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   }
   const unsigned prep_grid = (unsigned)(ctx->sm_count * (ctx->prep_blocks_per_sm[mode] > 0 ? ctx->prep_blocks_per_sm[mode] : 1));
   const unsigned decide_grid = (unsigned)(ctx->sm_count * (ctx->decide_blocks_per_sm > 0 ? ctx->decide_blocks_per_sm : 1));
-  int bpm = ctx->march_blocks_per_sm[mode];
-  if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e);
-  if (bpm < 1) bpm = 1;
-  const unsigned march_grid = (unsigned)(ctx->sm_count * bpm);
+  unsigned march_grids[2];
+  for (int a = 0; a < 2; ++a) {
+    int bpm = ctx->march_blocks_per_sm[mode][a];
+    if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e);
+    if (bpm < 1) bpm = 1;
+    march_grids[a] = (unsigned)(ctx->sm_count * bpm);
+  }
   const int group = 4;
   uint64_t round = 0;
   size_t ev_used = 0;
@@ -528,6 +532,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
       stamp();
       {
         const bool agg = (sort == 2 && W.agg);
+        const unsigned march_grid = march_grids[agg ? 1 : 0];
         const bool prefetch = prefetch_cfg < 0 ? agg : (prefetch_cfg != 0);
 #define CMIB_LAUNCH_MARCH(M, A, R) march_kernel<M, A, R><<<march_grid, MARCH_BLOCK, 0, s>>>(W)
         if (mode == ACC_HONLY) {

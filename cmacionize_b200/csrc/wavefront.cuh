@@ -509,8 +509,13 @@ constexpr int AGG_GROUP = 8; /* lanes that are refilled together */
  * L2/DRAM latency overlaps the in-warp sums, the loop control and the wall distances of the next
  * pass instead of stalling the optical-depth arithmetic right behind the load.
  */
+#ifndef CMIB_AGG_BLOCKS
+#define CMIB_AGG_BLOCKS 3 /* resident CTAs per SM the coherent variants are compiled for.  Measured with 2 (118
+                           * registers, no spills): H-only 26.9 -> 32.2 ms on clumpy 256^3, full layout 117 -> 114 ms:
+                           * the 24 warps per SM matter more than the spills */
+#endif
 template <int MODE, bool AGG, bool PRE>
-__global__ void __launch_bounds__(MARCH_BLOCK, 3)
+__global__ void __launch_bounds__(MARCH_BLOCK, (AGG ? CMIB_AGG_BLOCKS : 3))
 march_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   constexpr int NMETAL = (MODE == ACC_FULL) ? 12 : 0;
@@ -554,7 +559,11 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
   uint32_t n_red = 0;
   double tau_sum = 0.; /* optical depth traversed (checksum against sum_cells n (x_H J_H + A_He x_He J_He)) */
   int state = LANE_EMPTY;
-  double pre_n = 0., pre_xH = 0., pre_xHe = 0.; /* PRE: record of the cell the lane is in */
+  /* PRE: record of the cell the lane is in.  (ptxas waits for the outstanding request at the loop-head
+   * branch, 12 % of the stall samples, because the refill path writes these registers too; loading the
+   * first cell of a packet on the crossing path instead removed that wait but cost a branch and spills:
+   * clumpy 256^3 26.3 -> 26.9 ms, so it stays as it is.) */
+  double pre_n = 0., pre_xH = 0., pre_xHe = 0.;
   auto prefetch_cell = [&]() {
     const uint32_t pc = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
     if (MODE == ACC_HONLY) {
