@@ -45,6 +45,23 @@ def random_stream(seed, n):
     return out
 
 
+def sph_mapping(paramfile, mapping_type, x, y, z, h, m, ncell, xH_cells, box=None):
+    """(number density per cell, neutral fraction per particle) of the host layer's SPHArrayInterface: the
+    device-free half of the cmi_* C ABI (host/SPHArrayInterface.hpp)"""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, h, m, xH_cells)]
+    dens, nH = np.empty(ncell), np.empty(arrs[0].size)
+    vp = C.c_void_p
+    ba = bs = None
+    if box is not None:
+        ba, bs = (np.ascontiguousarray(b, dtype=np.float64) for b in box)
+    _check(lib.cmih_sph_mapping(str(paramfile).encode(), mapping_type.encode(),
+                                ba.ctypes.data_as(vp) if ba is not None else None,
+                                bs.ctypes.data_as(vp) if bs is not None else None, C.c_int64(arrs[0].size),
+                                *[a.ctypes.data_as(vp) for a in arrs[:5]], C.c_int64(ncell), dens.ctypes.data_as(vp),
+                                arrs[5].ctypes.data_as(vp), nH.ctypes.data_as(vp)))
+    return dens, nH
+
+
 class ParameterFile:
     def __init__(self, filename):
         self._h = C.c_void_p()

@@ -36,6 +36,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <fstream>
+#include <functional>
 #include <iomanip>
 #include <iostream>
 #include <memory>
@@ -109,11 +110,14 @@ struct DensityValues {
   double cosmic_ray_factor = -1.; /* DensityValues.hpp:65-71 */
 };
 
+class CartesianCells;
 class DensityFunction {
 public:
   virtual ~DensityFunction() {}
   virtual void initialize() {}
   virtual DensityValues operator()(const Vec3 &cell_midpoint) = 0;
+  /* a function that fills the whole grid at once (SPHArrayInterface) returns true here */
+  virtual bool set_densities(CartesianCells &) { return false; }
 };
 
 class HomogeneousDensityFunction : public DensityFunction {
@@ -886,6 +890,7 @@ public:
   const std::array<int32_t, 3> &get_number_of_cells_3d() const { return ncell_; }
   /* DensityGrid::set_densities: evaluate the DensityFunction at every cell midpoint */
   void set_densities(DensityFunction &function) {
+    if (function.set_densities(*this)) return;
     const size_t n = get_number_of_cells();
     for (size_t i = 0; i < n; ++i) {
       const DensityValues v = function(get_cell_midpoint(i));
@@ -1358,7 +1363,9 @@ public:
   }
 
   /* IonizationSimulation::run */
-  void run() {
+  /* external_writer: IonizationSimulation::run(DensityGridWriter*) (IonizationSimulation.cpp:334, 655-659):
+   * called once with the final grid (host mirror refreshed) */
+  void run(const std::function<void(CartesianDensityGrid &)> &external_writer = nullptr) {
     CartesianDensityGrid &grid = *density_grids_[0];
     if (density_grid_writer_) density_grid_writer_->write(grid, 0);
     double shoot = 0., update = 0.;
@@ -1384,6 +1391,10 @@ public:
         density_grid_writer_->write(grid, loop + 1);
     }
     if (density_grid_writer_) density_grid_writer_->write(grid, number_of_iterations_);
+    if (external_writer) {
+      grid.download();
+      external_writer(grid);
+    }
     if (log_) {
       log_->write_status("Total photon shooting time: ", shoot, " s.");
       log_->write_status("Total cell update time: ", update, " s.");

@@ -12,6 +12,7 @@
 #include <string>
 
 #include "IonizationSimulation.hpp"
+#include "SPHArrayInterface.hpp"
 
 using namespace cmi;
 
@@ -220,6 +221,117 @@ int cmih_photon_source_distribution(void *h, double *info, double *positions, do
       positions[3 * i] = x[0]; positions[3 * i + 1] = x[1]; positions[3 * i + 2] = x[2];
       weights[i] = d->get_weight(i);
     }
+  });
+}
+
+/* ---- the reference's coarse C ABI (c/cmi_c_library.h:31-56, src/CMILibrary.cpp:48-208) ----------
+ * Same names, same arguments, same global-singleton semantics, errors abort like cmac_error.  num_thread
+ * is ignored (the work runs on the GPU of CMIB_DEVICE, default 0); mapping types "M_over_V" and
+ * "centroid" (SPHArrayInterface.hpp). */
+} /* extern "C" */
+
+namespace {
+IonizationSimulation *global_ionization_simulation = nullptr;
+SPHArrayInterface *global_interface = nullptr;
+Log *global_log = nullptr;
+
+int cmi_device() {
+  const char *e = getenv("CMIB_DEVICE");
+  return e ? atoi(e) : 0;
+}
+template <class F> void cmi_guard(const char *what, F f) {
+  try {
+    f();
+  } catch (const std::exception &e) {
+    fprintf(stderr, "%s: %s\n", what, e.what());
+    abort();
+  }
+}
+void cmi_init_common(const char *parameter_file, int talk) {
+  if (talk) global_log = new Log();
+  global_ionization_simulation =
+      new IonizationSimulation(true, false, false, -1, parameter_file, cmi_device(), global_log);
+}
+template <typename TX, typename TH, typename TN>
+void cmi_compute(const TX *x, const TX *y, const TX *z, const TH *h, const TH *m, TN *nH, size_t N) {
+  cmi_guard("cmi_compute_neutral_fraction", [&]() {
+    if (!global_interface || !global_ionization_simulation) throw std::runtime_error("cmi_init has not been called");
+    global_interface->reset(x, y, z, h, m, N);
+    global_ionization_simulation->initialize(global_interface);
+    global_ionization_simulation->run([&](CartesianDensityGrid &grid) { global_interface->write(grid); });
+    global_interface->fill_array(nH);
+  });
+}
+} // namespace
+
+extern "C" {
+
+void cmi_init(const char *parameter_file, const int num_thread, const double unit_length_in_SI,
+              const double unit_mass_in_SI, const char *mapping_type, const int talk) {
+  (void)num_thread;
+  cmi_guard("cmi_init", [&]() {
+    cmi_init_common(parameter_file, talk);
+    global_interface = new SPHArrayInterface(unit_length_in_SI, unit_mass_in_SI, mapping_type);
+  });
+}
+void cmi_init_periodic_dp(const char *parameter_file, const int num_thread, const double unit_length_in_SI,
+                          const double unit_mass_in_SI, const double *box_anchor, const double *box_sides,
+                          const char *mapping_type, const int talk) {
+  (void)num_thread;
+  cmi_guard("cmi_init_periodic_dp", [&]() {
+    cmi_init_common(parameter_file, talk);
+    global_interface = new SPHArrayInterface(unit_length_in_SI, unit_mass_in_SI, box_anchor, box_sides, mapping_type);
+  });
+}
+void cmi_init_periodic_sp(const char *parameter_file, const int num_thread, const double unit_length_in_SI,
+                          const double unit_mass_in_SI, const float *box_anchor, const float *box_sides,
+                          const char *mapping_type, const int talk) {
+  (void)num_thread;
+  cmi_guard("cmi_init_periodic_sp", [&]() {
+    cmi_init_common(parameter_file, talk);
+    global_interface = new SPHArrayInterface(unit_length_in_SI, unit_mass_in_SI, box_anchor, box_sides, mapping_type);
+  });
+}
+void cmi_destroy() {
+  delete global_ionization_simulation;
+  delete global_interface;
+  delete global_log;
+  global_ionization_simulation = nullptr;
+  global_interface = nullptr;
+  global_log = nullptr;
+}
+void cmi_compute_neutral_fraction_dp(const double *x, const double *y, const double *z, const double *h,
+                                     const double *m, double *nH, const size_t N) {
+  cmi_compute(x, y, z, h, m, nH, N);
+}
+void cmi_compute_neutral_fraction_mp(const double *x, const double *y, const double *z, const float *h,
+                                     const float *m, float *nH, const size_t N) {
+  cmi_compute(x, y, z, h, m, nH, N);
+}
+void cmi_compute_neutral_fraction_sp(const float *x, const float *y, const float *z, const float *h, const float *m,
+                                     float *nH, const size_t N) {
+  cmi_compute(x, y, z, h, m, nH, N);
+}
+
+/* the device-free half of the SPH coupling, for the CPU test tier: densities the interface maps onto the
+ * parameter file's Cartesian grid, and the inverse mapping of a given neutral-fraction field.
+ * periodic: box_anchor / box_sides given (else NULL).  dens[ncell] out, xH_cells[ncell] in, nH[N] out. */
+int cmih_sph_mapping(const char *paramfile, const char *mapping_type, const double *box_anchor, const double *box_sides,
+                     int64_t N, const double *x, const double *y, const double *z, const double *h, const double *m,
+                     int64_t ncell, double *dens, const double *xH_cells, double *nH) {
+  CMIH_TRY({
+    ParameterFile p(paramfile);
+    const SimulationBox box(p);
+    CartesianCells cells(box, p.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}));
+    if ((int64_t)cells.get_number_of_cells() != ncell) throw std::runtime_error("wrong number of cells");
+    std::unique_ptr<SPHArrayInterface> sph(box_anchor ? new SPHArrayInterface(1., 1., box_anchor, box_sides, mapping_type)
+                                                      : new SPHArrayInterface(1., 1., mapping_type));
+    sph->reset(x, y, z, h, m, (size_t)N);
+    cells.set_densities(*sph);
+    for (int64_t i = 0; i < ncell; ++i) dens[i] = cells.number_density[i];
+    for (int64_t i = 0; i < ncell; ++i) cells.ionic_fraction[i] = xH_cells[i];
+    sph->write(cells);
+    sph->fill_array(nH);
   });
 }
 

@@ -49,7 +49,7 @@ PhantomSnapshotDensityFunction PhotonSource PhysicalDiffuseReemissionHandler Pla
 PopStarPhotonSourceSpectrum Signals SPHNGSnapshotDensityFunction SPHNGVoronoiGeneratorDistribution
 TemperatureCalculator VernerCrossSections VernerRecombinationRates WMBasicPhotonSourceSpectrum
 CartesianDensityGrid DensityGrid IonizationSimulation NewVoronoiCellConstructor NewVoronoiGrid
-OldVoronoiCell OldVoronoiGrid VoronoiDensityGrid
+OldVoronoiCell OldVoronoiGrid VoronoiDensityGrid SPHArrayInterface CMILibrary
 """.split()
 
 DATA_FILES = ["verner_A.dat", "verner_B.dat", "verner_C.dat",

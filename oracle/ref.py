@@ -257,6 +257,22 @@ def planar_incoming(axis, intercept, anchor, sides, n, seed=42):
     return u, pos, d
 
 
+def sph_mapping(paramfile, mapping_type, x, y, z, h, m, ncell, xH_cells, box=None):
+    """(number density per cell, neutral fraction per particle) of the reference's SPHArrayInterface"""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, h, m, xH_cells)]
+    dens, nH = np.empty(ncell), np.empty(arrs[0].size)
+    ba = bs = None
+    if box is not None:
+        ba, bs = (np.ascontiguousarray(b, dtype=np.float64) for b in box)
+    L = lib()
+    L.cmi_ref_sph_mapping.restype = C.c_int64
+    n = L.cmi_ref_sph_mapping(str(paramfile).encode(), mapping_type.encode(), _p(ba) if ba is not None else None,
+                              _p(bs) if bs is not None else None, C.c_int64(arrs[0].size), *[_p(a) for a in arrs[:5]],
+                              C.c_int64(ncell), _p(dens), _p(arrs[5]), _p(nH))
+    assert n == ncell, (n, ncell)
+    return dens, nH
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

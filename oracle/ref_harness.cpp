@@ -59,6 +59,7 @@
 #include "PhysicalDiffuseReemissionHandler.hpp"
 #include "PlanckPhotonSourceSpectrum.hpp"
 #include "RandomGenerator.hpp"
+#include "SPHArrayInterface.hpp"
 #include "TemperatureCalculator.hpp"
 #include "TerminalLog.hpp"
 #include "Tracker.hpp"
@@ -671,6 +672,33 @@ int cmi_ref_photon_source_distribution(const char *paramfile, double *info, doub
     weights[i] = d->get_weight(i);
   }
   delete d;
+  return n;
+}
+
+/* SPHArrayInterface (src/SPHArrayInterface.cpp) on the parameter file's grid: the densities
+ * IonizationSimulation::initialize(interface) maps onto the cells, and the inverse mapping
+ * (write + fill_array) of a given neutral-fraction field.  box_anchor == NULL: non-periodic interface. */
+int64_t cmi_ref_sph_mapping(const char *paramfile, const char *mapping_type, const double *box_anchor,
+                            const double *box_sides, int64_t N, const double *x, const double *y, const double *z,
+                            const double *h, const double *m, int64_t ncell, double *dens, const double *xH_cells,
+                            double *nH) {
+  SPHArrayInterface *sph = box_anchor ? new SPHArrayInterface(1., 1., box_anchor, box_sides, mapping_type)
+                                      : new SPHArrayInterface(1., 1., mapping_type);
+  IonizationSimulation sim(false, false, false, 1, paramfile, nullptr, nullptr);
+  sph->reset(x, y, z, h, m, (size_t)N);
+  sim.initialize(sph);
+  DensityGrid &grid = *sim._density_grid;
+  const int64_t n = grid.get_number_of_cells();
+  if (n == ncell) {
+    int64_t i = 0;
+    for (auto it = grid.begin(); it != grid.end(); ++it, ++i) {
+      dens[i] = it.get_ionization_variables().get_number_density();
+      it.get_ionization_variables().set_ionic_fraction(ION_H_n, xH_cells[i]);
+    }
+    sph->write(grid, 0, sim._parameter_file, 0., nullptr);
+    sph->fill_array(nH);
+  }
+  delete sph;
   return n;
 }
 

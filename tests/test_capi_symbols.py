@@ -29,6 +29,20 @@ def test_library_exports_every_declared_symbol(cmib):
     assert lib.cmib_abi_version() == 1
 
 
+def test_host_library_exports_the_reference_c_abi():
+    """include/cmi_c_library.h = the reference's c/cmi_c_library.h: every function is exported by
+    libcmih.so under the reference's name."""
+    import ctypes
+    text = (ROOT / "include" / "cmi_c_library.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    syms = sorted(set(re.findall(r"\b(cmi_[a-z0-9_]+)\s*\(", text)))
+    assert syms == ["cmi_compute_neutral_fraction_dp", "cmi_compute_neutral_fraction_mp",
+                    "cmi_compute_neutral_fraction_sp", "cmi_destroy", "cmi_init", "cmi_init_periodic_dp",
+                    "cmi_init_periodic_sp"]
+    lib = ctypes.CDLL(str(ROOT / "cmacionize_b200" / "libcmih.so"))
+    assert not [s for s in syms if not hasattr(lib, s)]
+
+
 def test_no_cpu_fallback(cmib):
     """Without a CUDA device the product must fail loudly, never compute on the host."""
     import torch

@@ -1,0 +1,102 @@
+"""GPU tier: the reference's coarse C ABI (include/cmi_c_library.h = c/cmi_c_library.h) served by
+libcmih.so, end to end, in the scenario of the reference's own test/testCMILibrary.cpp (1000 particles
+on a lattice, periodic box, mapping M_over_V) and with the centroid mapping on random particles:
+the neutral fractions the SPH code gets back, against the reference's own library (compiled into
+the oracle) on the same arrays.  Monte Carlo runs with different generators: compared within the
+spread of two reference runs (seeds 42 / 4242)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+PC = 3.086e16
+ROOT = Path(__file__).resolve().parents[1]
+PARAM = """SimulationBox:
+  anchor: [-5. pc, -5. pc, -5. pc]
+  sides: [10. pc, 10. pc, 10. pc]
+  periodicity: [false, false, false]
+DensityGrid:
+  type: Cartesian
+  number of cells: [16, 16, 16]
+Abundances:
+  helium: 0.
+TemperatureCalculator:
+  do temperature calculation: false
+PhotonSourceDistribution:
+  type: SingleStar
+  position: [0. pc, 0. pc, 0. pc]
+  luminosity: 4.26e49 s^-1
+PhotonSourceSpectrum:
+  type: Planck
+  temperature: 40000. K
+IonizationSimulation:
+  number of photons: 200000
+  number of iterations: 8
+  random seed: {seed}
+  output folder: {folder}
+DensityGridWriter:
+  type: AsciiFile
+  prefix: cmi_{seed}_
+"""
+
+
+def call(lib, pf, mapping, x, y, z, h, m, box):
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    nH = np.zeros(x.size)
+    if box is None:
+        lib.cmi_init(str(pf).encode(), C.c_int(4), C.c_double(1.), C.c_double(1.), mapping.encode(), C.c_int(0))
+    else:
+        ba, bs = np.array(box[0], dtype=np.float64), np.array(box[1], dtype=np.float64)
+        lib.cmi_init_periodic_dp(str(pf).encode(), C.c_int(4), C.c_double(1.), C.c_double(1.), p(ba), p(bs),
+                                 mapping.encode(), C.c_int(0))
+    lib.cmi_compute_neutral_fraction_dp(p(x), p(y), p(z), p(h), p(m), p(nH), C.c_size_t(x.size))
+    lib.cmi_destroy()
+    return nH
+
+
+@pytest.mark.parametrize("mapping", ["M_over_V", "centroid"])
+def test_cmi_library_gives_the_reference_neutral_fractions(cmib, ref, tmp_path, monkeypatch, mapping):
+    monkeypatch.chdir(tmp_path)   # the reference writes time-log files into the working directory
+    if mapping == "M_over_V":     # test/testCMILibrary.cpp:36-62
+        g = (np.arange(10) + 0.5) / 10.
+        X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+        x, y, z = (-5 * PC + 10 * PC * a.ravel() for a in (X, Y, Z))
+        h = np.full(1000, 0.2 * 10 * PC)
+        m = np.full(1000, 4.9e30)
+        box = ([-5 * PC] * 3, [10 * PC] * 3)
+    else:
+        rng = np.random.default_rng(21)
+        n = 4000
+        x, y, z = (rng.uniform(-5 * PC, 5 * PC, n) for _ in range(3))
+        h = np.full(n, 1.4 * PC)
+        m = np.full(n, 1.3e30)          # ~ 110 cm^-3 on average
+        box = None
+    x, y, z, h, m = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z, h, m))
+    files = {}
+    for seed in (42, 4242):
+        pf = tmp_path / f"cmi_{seed}.param"
+        pf.write_text(PARAM.format(seed=seed, folder=tmp_path))
+        files[seed] = pf
+    reflib = C.CDLL(str(ROOT / "oracle" / "_ref" / "libcmi_ref.so"))
+    a = call(reflib, files[42], mapping, x, y, z, h, m, box)
+    b = call(reflib, files[4242], mapping, x, y, z, h, m, box)
+    ours = C.CDLL(str(ROOT / "cmacionize_b200" / "libcmih.so"))
+    g1 = call(ours, files[42], mapping, x, y, z, h, m, box)
+    g2 = call(ours, files[42], mapping, x, y, z, h, m, box)      # the library can be re-initialised
+    assert np.array_equal(g1, g2)
+    assert (g1 <= 1.).all()
+    if mapping == "M_over_V":
+        assert (g1 >= 0.).all()   # (the centroid inverse mapping is not normalised: it goes negative in the reference too)
+    # particles the star ionises / leaves neutral
+    ia, ib, ig = a < 0.5, b < 0.5, g1 < 0.5
+    assert 10 <= ia.sum() < 0.95 * x.size
+    assert abs(int(ig.sum()) - int(ia.sum())) <= max(3 * abs(int(ia.sum()) - int(ib.sum())), 0.03 * ia.sum() + 2)
+    assert (ig != ia).sum() <= max(3 * (ia != ib).sum(), 0.05 * ia.sum() + 2)
+    # values: mean absolute deviation from reference run A against the spread of the two reference runs
+    noise = np.abs(a - b).mean()
+    dev = np.abs(g1 - a).mean()
+    assert dev <= 2. * noise + 1e-3, (dev, noise)
+    assert abs(g1.mean() - a.mean()) <= max(3. * abs(b.mean() - a.mean()), 2e-3)

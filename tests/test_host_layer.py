@@ -304,3 +304,37 @@ def test_fractal_density_mask_gives_the_reference_grid(host, ref, tmp_path):
     p.close()
     assert np.array_equal(dens, f[0])
     assert np.unique(dens).size > 100 and abs(dens.sum() / (5e7 * nc ** 3) - 1.) < 1e-12   # clumpy, atoms conserved
+
+
+@pytest.mark.parametrize("mapping,periodic", [("centroid", False), ("centroid", True), ("M_over_V", True), ("M_over_V", False)])
+def test_sph_array_interface_maps_like_the_reference(host, ref, tmp_path, mapping, periodic):
+    """The device-free half of the coarse C ABI (cmi_compute_neutral_fraction_*): SPH particles ->
+    densities on the parameter file's Cartesian grid (SPHArrayInterface::operator()) and a
+    neutral-fraction field -> particles (the inverse mapping of SPHArrayInterface::write), against
+    the reference's SPHArrayInterface on the same arrays.  The reference walks an octree, the host
+    layer scatters particles over cells: same pairs, other summation order."""
+    nc = 12
+    pf = tmp_path / "sph.param"
+    pf.write_text("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+                  f"  periodicity: [{'true' if periodic else 'false'}, {'true' if periodic else 'false'}, "
+                  f"{'true' if periodic else 'false'}]\nDensityGrid:\n  type: Cartesian\n"
+                  f"  number of cells: [{nc}, {nc}, {nc}]\nPhotonSourceSpectrum:\n  type: Monochromatic\n")
+    rng = np.random.default_rng(12)
+    N = 3000
+    pos = rng.uniform(-5 * PC, 5 * PC, (N, 3))
+    pos[:50] = rng.uniform(-4.9 * PC, -4.0 * PC, (50, 3))       # a clump in a corner (wraps when periodic)
+    h = np.exp(rng.uniform(np.log(0.3 * PC), np.log(1.6 * PC), N))
+    m = np.full(N, 4.9e30) if mapping == "M_over_V" else rng.uniform(1e30, 9e30, N)
+    xH = np.exp(rng.uniform(np.log(1e-5), 0., nc ** 3))
+    box = ([-5 * PC] * 3, [10 * PC] * 3) if periodic else None
+    args = (pf, mapping, pos[:, 0], pos[:, 1], pos[:, 2], h, m, nc ** 3, xH)
+    rd, rn = ref.sph_mapping(*args, box=box)
+    hd, hn = host.sph_mapping(*args, box=box)
+    assert np.abs(hd / rd - 1.).max() < 1e-13
+    assert np.abs(hn - rn).max() < 1e-12
+    if mapping == "centroid":
+        assert np.unique(hd).size > 0.9 * nc ** 3 and (hn < 0.999).mean() > 0.5   # small-h particles reach no midpoint
+        # mean density ~ total mass / volume (SPH estimate at 1728 sample points)
+        assert abs(hd.mean() * 1.6737236e-27 * (10 * PC) ** 3 / m.sum() - 1.) < 0.1
+    else:
+        assert np.unique(hd).size == 1 and np.array_equal(hn, rn)
