@@ -86,7 +86,7 @@ def test_cmi_library_gives_the_reference_neutral_fractions(cmib, ref, tmp_path, 
     ours = C.CDLL(str(ROOT / "cmacionize_b200" / "libcmih.so"))
     g1 = call(ours, files[42], mapping, x, y, z, h, m, box)
     g2 = call(ours, files[42], mapping, x, y, z, h, m, box)      # the library can be re-initialised
-    assert np.array_equal(g1, g2)
+    assert np.abs(g1 - g2).max() < 1e-6                      # same packets; atomic adds in another order
     assert (g1 <= 1.).all()
     if mapping == "M_over_V":
         assert (g1 >= 0.).all()   # (the centroid inverse mapping is not normalised: it goes negative in the reference too)
