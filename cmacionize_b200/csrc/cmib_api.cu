@@ -367,7 +367,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   W.rq = ctx->rq.p;
   W.eq = ctx->eq.p;
   W.capacity = cap;
-  /* coherence sort: on when the gathered + accumulated working set does not fit in L2 */
+  /* order of the march queue (cmib_context::sort_mode; CMIB_SORT overrides for A/B runs) */
   int sort = ctx->sort_mode;
   if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
   bool tuning = false;        /* this whole shoot is one half of a timed pair */
