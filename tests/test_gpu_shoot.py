@@ -397,3 +397,49 @@ def test_tabulated_and_uniform_spectra_on_the_device(cmib, ref):
         assert abs(nu.mean() / nu_ref.mean() - 1.) < 2e-3 and abs(nu.std() / nu_ref.std() - 1.) < 3e-3
         pk = ctx.sample_packets(1000, seed=1)   # emission uses it
         assert (pk["nu"] >= 3.289e15).all() and (pk["nu"] <= 4 * 3.289e15).all() and np.unique(pk["nu"]).size > 990
+
+
+@pytest.mark.parametrize("capacity", [None, 262144])
+def test_measured_queue_order_changes_nothing(cmib, capacity):
+    """Grids that do not fit in L2 choose the order of the march queue by measurement (cmib_api.cu,
+    sort_mode -1): a warm-up shoot, then the two orders timed either on two successive shoots or
+    — when a shoot holds at least four queue capacities — on rounds 1 and 2 of one shoot, then the
+    winner.  Whatever it picks, every shoot must give the sums of the plain order on the same
+    packets (order of the atomic adds aside)."""
+    import os
+    from cmacionize_b200 import problems
+    npk = 1_200_000
+    prob = problems.lexington(20, ncell=128, n_packets=npk)      # 128^3 x 160 B = 335 MB > L2
+    ctx = prob.ctx
+    rng = np.random.default_rng(3)
+    x = prob.ionic_fractions.copy()
+    x[0] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-3), ctx.ncells))
+    x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), ctx.ncells))
+    ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
+    ctx.update_reemission_probabilities()
+    if capacity is None:
+        os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+    else:
+        os.environ["CMIB_QUEUE_CAPACITY"] = str(capacity)
+    try:
+        for it in range(5):
+            out = []
+            for order in (None, "0"):
+                if order is None:
+                    os.environ.pop("CMIB_SORT", None)
+                else:
+                    os.environ["CMIB_SORT"] = order
+                ctx.reset_accumulators()
+                tw, tc = ctx.shoot(npk, seed=5, iteration=it)
+                J, heat = ctx.download_accumulators()
+                out.append((tw, tc, ctx.shoot_statistics(), J, heat))
+            (tw, tc, st, J, h), (tw0, tc0, st0, J0, h0) = out
+            assert tw == tw0 and np.array_equal(tc, tc0) and st == st0, it
+            for k in range(14):
+                assert np.abs(J[k] - J0[k]).max() <= 1e-12 * max(J0[k].max(), 1e-300), (it, k)
+            for k in range(2):
+                assert np.abs(h[k] - h0[k]).max() <= 1e-12 * max(np.abs(h0[k]).max(), 1e-300), (it, k)
+    finally:
+        os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+        os.environ.pop("CMIB_SORT", None)
+        ctx.close()
