@@ -133,12 +133,12 @@ class ParameterFile:
 class IonizationSimulation:
     """cmi::IonizationSimulation (host/IonizationSimulation.hpp) on one GPU."""
 
-    def __init__(self, parameterfile, device=0, write_output=False, verbose=False, ngpus=1):
+    def __init__(self, parameterfile, device=0, write_output=False, verbose=False, ngpus=1, task_based=False):
         self._h = C.c_void_p()
         self.ngpus = ngpus
-        _check(lib.cmih_simulation_create_multi(str(parameterfile).encode(), C.c_int(device), C.c_int(ngpus),
-                                                C.c_int(1 if write_output else 0), C.c_int(1 if verbose else 0),
-                                                C.byref(self._h)))
+        create = lib.cmih_simulation_create_task_based if task_based else lib.cmih_simulation_create_multi
+        _check(create(str(parameterfile).encode(), C.c_int(device), C.c_int(ngpus), C.c_int(1 if write_output else 0),
+                      C.c_int(1 if verbose else 0), C.byref(self._h)))
         info = (C.c_double * 4)()
         _check(lib.cmih_simulation_info(self._h, info))
         self.ncells = int(info[0])

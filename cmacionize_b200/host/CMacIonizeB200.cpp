@@ -4,12 +4,14 @@
  * (/root/reference/src/CMacIonize.cpp:100-377, default branch :348-362):
  *
  *     CMacIonizeB200 --params <file> [--threads N] [--device D] [--gpus G] [--every-iteration-output]
- *                    [--output-statistics] [--dry-run] [--verbose]
+ *                    [--output-statistics] [--dry-run] [--verbose] [--task-based]
  *
  * --threads is accepted for command-line compatibility and ignored.  --gpus G uses devices
- * D .. D+G-1 of this node (packets split by global id, one ncclAllReduce per iteration).  Other modes of the
- * reference (--rhd, --dusty-radiative-transfer, --emission, --task-based) are outside the
- * accelerated path and are rejected with an error.
+ * D .. D+G-1 of this node (packets split by global id, one ncclAllReduce per iteration).  --task-based
+ * (:304-338) reads the `TaskBasedIonizationSimulation:` parameter block instead of `IonizationSimulation:`
+ * (host/IonizationSimulation.hpp) and runs the same GPU path.  Other modes of the reference (--rhd,
+ * --dusty-radiative-transfer, --emission, --task-based-rhd) are outside the accelerated path and are rejected
+ * with an error.
  */
 #include <cstring>
 #include <iostream>
@@ -19,7 +21,7 @@
 int main(int argc, char **argv) {
   std::string params;
   int device = 0, gpus = 1;
-  bool every = false, stats = false, dry = false, verbose = false;
+  bool every = false, stats = false, dry = false, verbose = false, task_based = false;
   for (int i = 1; i < argc; ++i) {
     const std::string a = argv[i];
     if (a == "--params" && i + 1 < argc) params = argv[++i];
@@ -30,7 +32,8 @@ int main(int argc, char **argv) {
     else if (a == "--output-statistics") stats = true;
     else if (a == "--dry-run") dry = true;
     else if (a == "--verbose") verbose = true;
-    else if (a == "--rhd" || a == "--dusty-radiative-transfer" || a == "--emission" || a == "--task-based") {
+    else if (a == "--task-based") task_based = true;
+    else if (a == "--rhd" || a == "--dusty-radiative-transfer" || a == "--emission" || a == "--task-based-rhd") {
       std::cerr << "CMacIonizeB200: mode " << a << " is not part of the accelerated path\n";
       return 1;
     } else {
@@ -47,7 +50,7 @@ int main(int argc, char **argv) {
     cmi::Log log(verbose ? cmi::Log::INFO : cmi::Log::STATUS);
     std::vector<int> devices;
     for (int g = 0; g < (gpus > 0 ? gpus : 1); ++g) devices.push_back(device + g);
-    cmi::IonizationSimulation sim(true, every, stats, -1, params, devices, &log);
+    cmi::IonizationSimulation sim(true, every, stats, -1, params, devices, &log, task_based);
     if (dry) {
       log.write_warning("Dry run requested. Program will now halt.");
       return 0;

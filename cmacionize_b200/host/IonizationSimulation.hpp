@@ -1149,22 +1149,45 @@ public:
    * accumulator buffers replaces the reference's 16 chunked MPI_Allreduce + counter reductions
    * (IonizationSimulation.cpp:410-416, 458-529); the state update is then run on every device
    * (replicated), so no gather is needed (:540-618). */
+  /* task_based = true: the parameter surface of the reference's other driver (`CMacIonize --task-based`,
+   * TaskBasedIonizationSimulation.cpp:190-370) on the same GPU path: Monte Carlo parameters come from the
+   * `TaskBasedIonizationSimulation:` block (number of iterations 10, number of photons 1e6, random seed,
+   * output folder, diffuse field), the periodicity from `DensitySubGridCreator:periodicity`, and the
+   * diffuse re-emission handler exists only when `diffuse field` is true (:338-346).  The task queues,
+   * buffers, subgrids and source copies of that driver are CPU scheduling and have no counterpart here
+   * (their keys are read so that they show up in the used-values file).  The packet conventions that
+   * differ inside the reference's task-based code (abundance-weighted cross sections carried by the
+   * packet, DensitySubGrid.hpp:593-612) describe the same physics; results agree with either reference
+   * driver within Monte Carlo noise (tests/test_gpu_benchmarks.py). */
   IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
-                       const std::string &parameterfile, const std::vector<int> &devices, Log *log = nullptr)
+                       const std::string &parameterfile, const std::vector<int> &devices, Log *log = nullptr,
+                       bool task_based = false)
       : every_iteration_output_(every_iteration_output), output_statistics_(output_statistics), log_(log),
-        parameter_file_(parameterfile),
-        number_of_iterations_(parameter_file_.get_value<uint32_t>("IonizationSimulation:number of iterations", 10)),
-        number_of_photons_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons", 100000)),
-        number_of_photons_init_(parameter_file_.get_value<uint64_t>("IonizationSimulation:number of photons first loop",
-                                                                    number_of_photons_)),
+        parameter_file_(parameterfile), block_(task_based ? "TaskBasedIonizationSimulation:" : "IonizationSimulation:"),
+        number_of_iterations_(parameter_file_.get_value<uint32_t>(block_ + "number of iterations", 10)),
+        number_of_photons_(parameter_file_.get_value<uint64_t>(block_ + "number of photons", task_based ? 1000000 : 100000)),
+        number_of_photons_init_(task_based ? number_of_photons_
+                                           : parameter_file_.get_value<uint64_t>(block_ + "number of photons first loop",
+                                                                                 number_of_photons_)),
         abundances_(Abundances::generate(parameter_file_, log)), devices_(devices) {
     (void)num_thread;
     if (devices_.empty()) cmi_error("No device given!");
+    if (task_based) {
+      (void)parameter_file_.get_value<uint32_t>(block_ + "source copy level", 4);
+      (void)parameter_file_.get_value<uint64_t>(block_ + "number of buffers", 50000);
+      (void)parameter_file_.get_value<uint64_t>(block_ + "queue size per thread", 10000);
+      (void)parameter_file_.get_value<uint64_t>(block_ + "shared queue size", 100000);
+      (void)parameter_file_.get_value<uint64_t>(block_ + "number of tasks", 500000);
+    }
     cross_sections_.reset(CrossSections::generate(parameter_file_, log_));
     recombination_rates_.reset(RecombinationRates::generate(parameter_file_, log_));
     density_function_.reset(DensityFunctionFactory::generate(parameter_file_, log_));
     density_mask_.reset(DensityMaskFactory::generate(parameter_file_, log_));
-    const SimulationBox box(parameter_file_);
+    SimulationBox box(parameter_file_);
+    if (task_based) { /* DensitySubGridCreator(box, params) (DensitySubGridCreator.hpp:106-117) */
+      (void)parameter_file_.get_value<std::array<int32_t, 3>>("DensitySubGridCreator:number of subgrids", {8, 8, 8});
+      box.periodicity = parameter_file_.get_value<std::array<bool, 3>>("DensitySubGridCreator:periodicity", {false, false, false});
+    }
     const std::string grid_type = parameter_file_.get_value<std::string>("DensityGrid:type", "Cartesian");
     if (grid_type != "Cartesian")
       cmi_error("Unknown DensityGrid type: \"%s\" (the B200 backend provides Cartesian)!", grid_type.c_str());
@@ -1213,7 +1236,11 @@ public:
                           2. * box.sides[1] * box.sides[2];
       continuous_luminosity = area * continuous_photon_source_spectrum_->total_flux;
     }
-    reemission_ = DiffuseReemissionHandler::generate(parameter_file_, log_);
+    /* classic driver: always through the factory; task-based driver: only when the diffuse field is switched
+     * on (TaskBasedIonizationSimulation.cpp:338-346; the second condition deals with old parameter files) */
+    if (!task_based || parameter_file_.get_value<bool>(block_ + "diffuse field", false) ||
+        parameter_file_.has_value("PhotonSource:diffuse field"))
+      reemission_ = DiffuseReemissionHandler::generate(parameter_file_, log_);
     const cmib_temperature_params tp = temperature_calculator_parameters(parameter_file_);
 
     /* configure every device context alike: PhotonSource ctor (PhotonSource.cpp:55-146) */
@@ -1251,15 +1278,15 @@ public:
         cmi_error("ncclCommInitAll failed for %zu devices!", devices_.size());
     }
 
-    output_folder_ = parameter_file_.get_value<std::string>("IonizationSimulation:output folder", ".");
+    output_folder_ = parameter_file_.get_value<std::string>(block_ + "output folder", ".");
     if (write_output) {
       const std::string wtype = parameter_file_.get_value<std::string>("DensityGridWriter:type", "AsciiFile");
       if (wtype != "AsciiFile" && log_)
         log_->write_warning("DensityGridWriter type ", wtype, " needs HDF5; writing the AsciiFile layout instead.");
       density_grid_writer_.reset(new AsciiFileDensityGridWriter(output_folder_, parameter_file_));
     }
-    random_seed_ = parameter_file_.get_value<int32_t>("IonizationSimulation:random seed", 42);
-    if (parameter_file_.get_value<bool>("IonizationSimulation:enable trackers", false))
+    random_seed_ = parameter_file_.get_value<int32_t>(block_ + "random seed", 42);
+    if (parameter_file_.get_value<bool>(block_ + "enable trackers", false))
       cmi_error("Trackers are not provided by the B200 backend!");
     if (write_output) {
       std::ofstream pfile(parameterfile + ".used-values");
@@ -1269,9 +1296,9 @@ public:
   }
 
   IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
-                       const std::string &parameterfile, int device = 0, Log *log = nullptr)
+                       const std::string &parameterfile, int device = 0, Log *log = nullptr, bool task_based = false)
       : IonizationSimulation(write_output, every_iteration_output, output_statistics, num_thread, parameterfile,
-                             std::vector<int>{device}, log) {}
+                             std::vector<int>{device}, log, task_based) {}
 
   ~IonizationSimulation() {
     for (ncclComm_t c : comms_) NcclApi::get().CommDestroy(c);
@@ -1416,6 +1443,7 @@ private:
   bool every_iteration_output_, output_statistics_;
   Log *log_;
   ParameterFile parameter_file_;
+  std::string block_; /* "IonizationSimulation:" or "TaskBasedIonizationSimulation:" */
   uint32_t number_of_iterations_;
   uint64_t number_of_photons_, number_of_photons_init_;
   Abundances abundances_;

@@ -35,9 +35,9 @@ struct Sim {
     for (int g = 0; g < (n > 0 ? n : 1); ++g) v.push_back(first + g);
     return v;
   }
-  Sim(const char *paramfile, int device, int ngpus, int write_output, int verbose)
+  Sim(const char *paramfile, int device, int ngpus, int write_output, int verbose, bool task_based = false)
       : log(verbose ? Log::INFO : Log::WARNING),
-        sim(write_output != 0, false, verbose != 0, -1, paramfile, device_list(device, ngpus), &log) {}
+        sim(write_output != 0, false, verbose != 0, -1, paramfile, device_list(device, ngpus), &log, task_based) {}
 };
 } // namespace
 
@@ -61,6 +61,11 @@ int cmih_simulation_create(const char *paramfile, int device, int write_output, 
 int cmih_simulation_create_multi(const char *paramfile, int device, int ngpus, int write_output, int verbose,
                                  void **out) {
   CMIH_TRY(*out = new Sim(paramfile, device, ngpus, write_output, verbose));
+}
+/* the `CMacIonize --task-based` parameter surface (TaskBasedIonizationSimulation: block) on the same path */
+int cmih_simulation_create_task_based(const char *paramfile, int device, int ngpus, int write_output, int verbose,
+                                      void **out) {
+  CMIH_TRY(*out = new Sim(paramfile, device, ngpus, write_output, verbose, true));
 }
 int cmih_simulation_destroy(void *h) {
   delete static_cast<Sim *>(h);

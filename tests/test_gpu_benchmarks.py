@@ -38,20 +38,24 @@ def make_paramfile(tmp_path, name, seed):
     ov = CASES[name]["override"]
     if ov:
         extra += f"  number of photons: {ov[0]}\n  number of iterations: {ov[1]}\n"
+    extra += f"\nTaskBasedIonizationSimulation:\n  random seed: {seed}\n  output folder: {tmp_path}\n"
     pf = tmp_path / f"{name}_{seed}.param"
     pf.write_text(text + extra)
     return pf
 
 
-@pytest.mark.parametrize("name", list(CASES))
-def test_benchmark_parameter_file(host, ref, tmp_path, name):  # noqa: F811
+@pytest.mark.parametrize("name,task_based", [(n, False) for n in CASES] + [("stromgren_diffuse", True)])
+def test_benchmark_parameter_file(host, ref, tmp_path, name, task_based):  # noqa: F811
+    """task_based: the same file through the `CMacIonize --task-based` parameter surface
+    (TaskBasedIonizationSimulation: block, diffuse field switch) — same problem, same reference runs."""
     case = CASES[name]
     nc = 64
     runs = []
     for seed in (42, 4242):
         fields, _ = ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)
         runs.append(fields)
-    sim = host.IonizationSimulation(make_paramfile(tmp_path, name, 42))
+    sim = host.IonizationSimulation(make_paramfile(tmp_path, name, 42), task_based=task_based)
+    assert sim.number_of_photons == (1_000_000 if case["override"] is None else case["override"][0])
     assert sim.ncells == nc ** 3
     sim.initialize()
     n0 = sim.fields()[0]
