@@ -389,7 +389,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>" if full_layout else "march_kernel<ACC_HONLY>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": 4.604e9 if args.workload == "lexingtonHII20" else None, "traffic_note": "dram__bytes_read+write (3.47 + 1.13 GB) of the first march launch "
+                "traffic": 4.546e9 if args.workload == "lexingtonHII20" else None, "traffic_note": "dram__bytes_read+write (3.45 + 1.09 GB) of the first march launch "
                 "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
                 "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
                 "(3.4 GB read) and the re-emission queue (1.1 GB written)",
