@@ -296,6 +296,14 @@ class Context:
                                       _p(nsteps), C.c_int32(max_trace), _p(trace)))
         return fpos, fcell, nsteps, trace
 
+    def integrate_optical_depth(self, pos, direction, sigma_H, sigma_He_corr):
+        """DensityGrid::integrate_optical_depth for explicit packets (include/cmib.h)"""
+        pos, d = _f64(pos).reshape(-1, 3), _f64(direction).reshape(-1, 3)
+        sh, she = _f64(sigma_H).reshape(-1), _f64(sigma_He_corr).reshape(-1)
+        out = np.empty(sh.size)
+        _check(lib.cmib_integrate_optical_depth(self._h, C.c_int64(sh.size), _p(pos), _p(d), _p(sh), _p(she), _p(out)))
+        return out
+
     def sample_packets(self, n, offset=0, seed=42, iteration=0):
         pos = np.empty((n, 3)); d = np.empty((n, 3)); nu = np.empty(n)
         sigma = np.empty((n, NUM_IONS)); she = np.empty(n); tau = np.empty(n)

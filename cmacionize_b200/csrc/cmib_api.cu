@@ -1224,6 +1224,28 @@ int cmib_march_packets(cmib_context *ctx, int64_t np, const double *pos, const d
   return 0;
 }
 
+int cmib_integrate_optical_depth(cmib_context *ctx, int64_t np, const double *pos, const double *dir,
+                                 const double *sigma_H, const double *sigma_He_corr, double *optical_depth) {
+  CHECK_CTX(ctx);
+  if (np <= 0) return 0;
+  if (!pos || !dir || !sigma_H || !sigma_He_corr || !optical_depth) CMIB_FAIL("null argument");
+  Scratch sc;
+  cudaStream_t s = ctx->stream;
+  double *d_pos, *d_dir, *d_sh, *d_she, *d_tau;
+  CUDA_OK(sc.in(&d_pos, pos, (size_t)np * 3, s));
+  CUDA_OK(sc.in(&d_dir, dir, (size_t)np * 3, s));
+  CUDA_OK(sc.in(&d_sh, sigma_H, (size_t)np, s));
+  CUDA_OK(sc.in(&d_she, sigma_He_corr, (size_t)np, s));
+  CUDA_OK(sc.out(&d_tau, (size_t)np));
+  integrate_optical_depth_kernel<<<blocks_for(np, 128), 128, 0, s>>>(ctx->geom, ctx->cells.p, np, d_pos, d_dir, d_sh, d_she,
+                                                                    d_tau);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(sc.back(optical_depth, d_tau, (size_t)np, s));
+  CUDA_OK(cudaStreamSynchronize(s));
+  return 0;
+}
+
 int cmib_sample_packets(cmib_context *ctx, int64_t n, uint64_t offset, uint64_t seed,
                         uint32_t iteration, double *pos, double *dir, double *nu, double *sigma,
                         double *sigma_He_corr, double *tau) {

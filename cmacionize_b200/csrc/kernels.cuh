@@ -123,6 +123,19 @@ march_packets_kernel(const __grid_constant__ MarchPacketsParams P) {
     for (int32_t k = nsteps; k < P.max_trace; ++k) P.trace[p * P.max_trace + k] = -1;
 }
 
+/* DensityGrid::integrate_optical_depth for caller-supplied packets, one thread per packet */
+__global__ void __launch_bounds__(128)
+integrate_optical_depth_kernel(GridGeom g, const CellOpacity *cells, int64_t np, const double *pos, const double *dir,
+                               const double *sigma_H, const double *sigma_He_corr, double *tau) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  MarchState s;
+  s.px = pos[3 * p]; s.py = pos[3 * p + 1]; s.pz = pos[3 * p + 2];
+  s.dx = dir[3 * p]; s.dy = dir[3 * p + 1]; s.dz = dir[3 * p + 2];
+  const int64_t limit = 1ll << 22; /* only a ray that never leaves a periodic box gets here */
+  tau[p] = integrate_optical_depth(g, s, sigma_H[p], sigma_He_corr[p], [cells](int64_t c) { return cells[c]; }, limit);
+}
+
 /* ------------------------------------------------------------------------- */
 /* per-cell passes                                                            */
 /* ------------------------------------------------------------------------- */

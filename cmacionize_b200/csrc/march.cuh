@@ -129,4 +129,29 @@ CMIB_HD double march_step(const GridGeom &g, MarchState &s, double n, double xH,
   return ds;
 }
 
+/*
+ * CartesianDensityGrid::integrate_optical_depth (CartesianDensityGrid.cpp:328-363): optical depth
+ * from the packet's position to the edge of the box, summed crossing by crossing in the
+ * reference's order (get_optical_depth per cell, DensityGrid.hpp:117-140).  `cell_at(long index)`
+ * returns the cell record.  A direction along a periodic axis never leaves the box — the reference
+ * loops forever there — so the walk stops after max_crossings and returns what it has.
+ */
+template <class CellAt>
+CMIB_HD double integrate_optical_depth(const GridGeom &g, MarchState s, double sigH, double sigHe, const CellAt &cell_at,
+                                       int64_t max_crossings) {
+  double optical_depth = 0.;
+  s.ix_ = 1. / s.dx;
+  s.iy_ = 1. / s.dy;
+  s.iz_ = 1. / s.dz;
+  s.tau = DBL_MAX; /* never exhausted: march_step always goes to the wall */
+  march_locate(g, s);
+  for (int64_t k = 0; k < max_crossings && march_inside(g, s); ++k) {
+    const CellOpacity c = cell_at(long_index(g, s.ix, s.iy, s.iz));
+    const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigH, sigHe);
+    s.tau = DBL_MAX;
+    optical_depth = xadd(optical_depth, xmul(xmul(ds, c.n), xadd(xmul(sigH, c.xH), xmul(sigHe, c.xHe))));
+  }
+  return optical_depth;
+}
+
 } // namespace cmib

@@ -218,6 +218,12 @@ int cmib_march_packets(cmib_context *ctx, int64_t np, const double *pos, const d
                        const double *sigma, const double *sigma_He_corr, const double *nu,
                        const double *weight, const double *tau, double *final_pos,
                        int64_t *final_cell, int32_t *nsteps, int32_t max_trace, int64_t *trace);
+/* replaces: DensityGrid::integrate_optical_depth(const Photon&) (src/DensityGrid.hpp:392,
+ * src/CartesianDensityGrid.cpp:328-363): optical depth from each packet's position to the edge of
+ * the box along its direction, for np packets given as pos[np][3], dir[np][3], sigma_H[np] and
+ * A_He*sigma_He[np]; same crossing order and arithmetic as the reference */
+int cmib_integrate_optical_depth(cmib_context *ctx, int64_t np, const double *pos, const double *dir,
+                                 const double *sigma_H, const double *sigma_He_corr, double *optical_depth);
 /* PhotonSource::get_random_photon for packets [offset, offset+n): pos, dir [n][3],
  * nu [n], sigma [n][14], sigma_He_corr [n], tau [n] (the first optical depth). */
 int cmib_sample_packets(cmib_context *ctx, int64_t n, uint64_t offset, uint64_t seed,

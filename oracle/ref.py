@@ -273,6 +273,17 @@ def sph_mapping(paramfile, mapping_type, x, y, z, h, m, ncell, xH_cells, box=Non
     return dens, nH
 
 
+def integrate_optical_depth(anchor, sides, ncell, periodic, n, xH, xHe, pos, direction, sigma_H, sigma_He_corr):
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (anchor, sides, n, xH, xHe, pos, direction, sigma_H, sigma_He_corr)]
+    nc = np.ascontiguousarray(ncell, dtype=np.int32)
+    per = np.ascontiguousarray(periodic, dtype=np.int32)
+    npk = a[7].size
+    out = np.empty(npk)
+    lib().cmi_ref_integrate_optical_depth(_p(a[0]), _p(a[1]), _p(nc), _p(per), _p(a[2]), _p(a[3]), _p(a[4]), C.c_int64(npk),
+                                          _p(a[5]), _p(a[6]), _p(a[7]), _p(a[8]), _p(out))
+    return out
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

@@ -248,6 +248,32 @@ int cmi_ref_interact(const double *anchor, const double *sides, const int32_t *n
   return 0;
 }
 
+/* CartesianDensityGrid::integrate_optical_depth (src/CartesianDensityGrid.cpp:328-363) for np photons
+ * on a grid given cell by cell (same arguments as cmi_ref_interact) */
+int cmi_ref_integrate_optical_depth(const double *anchor, const double *sides, const int32_t *ncell,
+                                    const int32_t *periodic, const double *cell_n, const double *cell_xH,
+                                    const double *cell_xHe, int64_t np, const double *pos, const double *dir,
+                                    const double *sigma_H, const double *sigma_He_corr, double *optical_depth) {
+  Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]), CoordinateVector<>(sides[0], sides[1], sides[2]));
+  CartesianDensityGrid grid(box, CoordinateVector<int_fast32_t>(ncell[0], ncell[1], ncell[2]),
+                            CoordinateVector<bool>(periodic[0] != 0, periodic[1] != 0, periodic[2] != 0), false, nullptr);
+  const int64_t nc = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  for (int64_t i = 0; i < nc; ++i) {
+    IonizationVariables &iv = grid._ionization_variables[i];
+    iv.set_number_density(cell_n[i]);
+    iv.set_ionic_fraction(ION_H_n, cell_xH[i]);
+    iv.set_ionic_fraction(ION_He_n, cell_xHe ? cell_xHe[i] : 0.);
+  }
+  for (int64_t p = 0; p < np; ++p) {
+    Photon photon(CoordinateVector<>(pos[3 * p], pos[3 * p + 1], pos[3 * p + 2]),
+                  CoordinateVector<>(dir[3 * p], dir[3 * p + 1], dir[3 * p + 2]), 3.3e15);
+    photon.set_cross_section(ION_H_n, sigma_H[p]);
+    photon.set_cross_section_He_corr(sigma_He_corr[p]);
+    optical_depth[p] = grid.integrate_optical_depth(photon);
+  }
+  return 0;
+}
+
 /* ---------------------------------------------------------------------------
  * a1: IonizationSimulation (IonizationSimulation.cpp:101-679) on a parameter
  * file, with an in-process DensityGridWriter that captures every field.

@@ -149,6 +149,30 @@ void hc_isotropic_incoming(const double *anchor, const double *sides, int64_t n,
                        dir[3 * i + 2]);
 }
 
+void hc_integrate_optical_depth(const double *anchor, const double *sides, const int32_t *ncell, const int32_t *periodic,
+                                const double *cell_n, const double *cell_xH, const double *cell_xHe, int64_t np,
+                                const double *pos, const double *dir, const double *sigma_H, const double *sigma_He_corr,
+                                double *out) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = anchor[d]; g.sides[d] = sides[d]; g.ncell[d] = ncell[d]; g.periodic[d] = periodic[d];
+    g.cellside[d] = sides[d] / ncell[d];
+    g.inv_cellside[d] = 1. / g.cellside[d];
+  }
+  g.ncells = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  for (int64_t p = 0; p < np; ++p) {
+    MarchState s;
+    s.px = pos[3 * p]; s.py = pos[3 * p + 1]; s.pz = pos[3 * p + 2];
+    s.dx = dir[3 * p]; s.dy = dir[3 * p + 1]; s.dz = dir[3 * p + 2];
+    out[p] = integrate_optical_depth(g, s, sigma_H[p], sigma_He_corr[p], [&](int64_t c) {
+      CellOpacity r;
+      r.n = cell_n[c]; r.xH = cell_xH[c]; r.xHe = cell_xHe[c]; r.T = 0.;
+      return r;
+    }, 1ll << 22);
+  }
+}
+
 void hc_planar_incoming(int axis, double intercept, const double *anchor, const double *sides, int64_t n,
                         const double *uniforms, double *pos, double *dir) {
   for (int64_t i = 0; i < n; ++i)

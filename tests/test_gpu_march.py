@@ -98,3 +98,25 @@ def test_wall_intersection_scenarios_of_the_reference_unit_test(cmib):
                                                        c["weight"], c["tau"], max_trace=4)
         J, _ = ctx.download_accumulators()
     check_wall_intersection_scenarios(c, fpos, fcell, nsteps, trace, J)
+
+
+@pytest.mark.parametrize("grid", ["unit16", "stromgren64_corner", "vacuum_holes", "noncubic_periodic_xz"])
+def test_integrate_optical_depth_equals_the_reference(cmib, ref, grid):
+    """cmib_integrate_optical_depth = DensityGrid::integrate_optical_depth (CartesianDensityGrid.cpp:328-363):
+    no libm on this path and every operation separately rounded, so the device result is the reference's
+    bit for bit."""
+    c = march_case(grid, 4000)
+    pos, d = c["pos"], c["dir"]
+    if c["periodic"].any():
+        keep = np.abs(d[:, 1]) > 0.2
+        pos, d = np.ascontiguousarray(pos[keep]), np.ascontiguousarray(d[keep])
+    sh = np.ascontiguousarray(c["sigma"][: len(pos), 0])
+    she = np.ascontiguousarray(c["sigma_He_corr"][: len(pos)])
+    r = ref.integrate_optical_depth(c["anchor"], c["sides"], c["ncell"], c["periodic"], c["n"], c["xH"], c["xHe"],
+                                    pos, d, sh, she)
+    with cmib.Context(c["anchor"], c["sides"], c["ncell"], c["periodic"]) as ctx:
+        nc = ctx.ncells
+        x = np.zeros((14, nc)); x[0] = c["xH"]; x[1] = c["xHe"]
+        ctx.upload_cells(c["n"], np.full(nc, 8000.), x)
+        out = ctx.integrate_optical_depth(pos, d, sh, she)
+    assert np.array_equal(out, r)

@@ -220,3 +220,25 @@ def test_planar_continuous_source_bitexact(hostcheck, ref):
                                      p(np.ascontiguousarray(u)), p(pos2), p(d2))
         assert np.array_equal(pos2, pos) and np.array_equal(d2, d)
         assert (pos2[:, axis] == intercept).all()
+
+
+@pytest.mark.parametrize("grid", ["unit16", "stromgren64_corner", "vacuum_holes", "single_cell", "noncubic_periodic_xz"])
+def test_integrate_optical_depth_bitexact(hostcheck, ref, grid):
+    """CartesianDensityGrid::integrate_optical_depth (optical depth to the edge of the box) on explicit
+    packets: the host build of march.cuh against the reference, bit for bit (corner starts, axis-aligned
+    and diagonal rays, vacuum cells; on the periodic grid only rays that leave through the y faces —
+    the others never end in the reference either)."""
+    c = march_case(grid, 3000)
+    pos, d = c["pos"], c["dir"]
+    if c["periodic"].any():
+        keep = np.abs(d[:, 1]) > 0.2
+        pos, d = np.ascontiguousarray(pos[keep]), np.ascontiguousarray(d[keep])
+    sh = np.ascontiguousarray(c["sigma"][: len(pos), 0])
+    she = np.ascontiguousarray(c["sigma_He_corr"][: len(pos)])
+    r = ref.integrate_optical_depth(c["anchor"], c["sides"], c["ncell"], c["periodic"], c["n"], c["xH"], c["xHe"],
+                                    pos, d, sh, she)
+    out = np.empty(len(pos))
+    hostcheck.hc_integrate_optical_depth(p(c["anchor"]), p(c["sides"]), p(c["ncell"]), p(c["periodic"]), p(c["n"]),
+                                         p(c["xH"]), p(c["xHe"]), C.c_int64(len(pos)), p(pos), p(d), p(sh), p(she), p(out))
+    assert np.array_equal(out, r)
+    assert (r >= 0).all() and (r > 0).mean() > 0.9
