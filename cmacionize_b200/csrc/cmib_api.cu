@@ -109,7 +109,7 @@ struct cmib_context {
   TemperatureParams tp;
   double luminosity = 0.; /* discrete + continuous */
   double discrete_luminosity = 0., continuous_luminosity = 0.;
-  bool planar_geometry_set = false;
+  bool planar_geometry_set = false, star_position_set = false;
   DevBuf<double> d_cont_planck;
   DevBuf<uint16_t> d_cont_planck_guide;
   std::vector<double> h_cont_planck;
@@ -868,6 +868,21 @@ int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, cons
   return 0;
 }
 
+int cmib_set_distant_star_position(cmib_context *ctx, const double position[3]) {
+  CHECK_CTX(ctx);
+  if (!position) CMIB_FAIL("null argument");
+  int num_exposed = 0;
+  for (int d = 0; d < 3; ++d) {
+    const double bottom = ctx->geom.anchor[d], top = ctx->geom.anchor[d] + ctx->geom.sides[d];
+    ctx->src.star_position[d] = position[d];
+    ctx->src.star_exposed[d] = (position[d] < bottom) ? -1 : ((position[d] > top) ? 1 : 0);
+    num_exposed += (ctx->src.star_exposed[d] != 0);
+  }
+  if (num_exposed == 0) CMIB_FAIL("External stellar source lies inside the simulation box. This will not work!");
+  ctx->star_position_set = true;
+  return 0;
+}
+
 int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double intercept, const double anchor[2],
                                     const double sides[2]) {
   CHECK_CTX(ctx);
@@ -891,8 +906,10 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
     ctx->update_source_weights();
     return 0;
   }
-  if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR)
+  if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR && kind != CMIB_CONTINUOUS_DISTANT_STAR)
     CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (kind == CMIB_CONTINUOUS_DISTANT_STAR && !ctx->star_position_set)
+    CMIB_FAIL("call cmib_set_distant_star_position before selecting the DistantStar continuous source");
   if (kind == CMIB_CONTINUOUS_PLANAR && !ctx->planar_geometry_set)
     CMIB_FAIL("call cmib_set_planar_source_geometry before selecting the Planar continuous source");
   if (!(luminosity > 0.)) CMIB_FAIL("the continuous source needs a positive luminosity (surface area x total flux)");
@@ -901,7 +918,8 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
       set_spectrum_model(ctx, ctx->src.cont_spectrum, ctx->h_cont_planck, ctx->d_cont_planck, ctx->d_cont_planck_guide,
                          spectrum_kind, spectrum_param))
     return 1;
-  ctx->src.continuous_kind = (kind == CMIB_CONTINUOUS_PLANAR) ? CONTINUOUS_PLANAR : CONTINUOUS_ISOTROPIC;
+  ctx->src.continuous_kind = (kind == CMIB_CONTINUOUS_PLANAR) ? CONTINUOUS_PLANAR
+                             : (kind == CMIB_CONTINUOUS_DISTANT_STAR ? CONTINUOUS_DISTANT_STAR : CONTINUOUS_ISOTROPIC);
   ctx->continuous_luminosity = luminosity;
   ctx->update_source_weights();
   return 0;

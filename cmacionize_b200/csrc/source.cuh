@@ -32,7 +32,7 @@ namespace cmib {
 
 enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1, SPECTRUM_UNIFORM = 2, SPECTRUM_TABULATED = 3 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
-enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2 };
+enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2, CONTINUOUS_DISTANT_STAR = 3 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
@@ -69,6 +69,10 @@ struct SourceModel {
    * planar_intercept, rectangle anchor + [0, sides) in the two other coordinates (ascending index) */
   int planar_axis;
   double planar_intercept, planar_anchor[2], planar_sides[2];
+  /* CONTINUOUS_DISTANT_STAR (DistantStarContinuousPhotonSource.hpp:60-90): a star outside the box;
+   * star_exposed[d] = -1 / +1 / 0: the star lies below / above / within the box along d */
+  double star_position[3];
+  int star_exposed[3];
   SpectrumModel cont_spectrum;   /* spectrum of the continuous source */
   SpectrumModel spectrum;        /* spectrum of the discrete sources */
   /* cross sections */
@@ -207,6 +211,53 @@ CMIB_HD void planar_incoming(int axis, double intercept, const double *anchor, c
   dz = cost;
 }
 
+/*
+ * DistantStarContinuousPhotonSource::get_random_incoming_direction (.hpp:164-192) with enters_box
+ * (:125-155): isotropic directions from the star (the first one mirrored towards the box) are drawn
+ * until one hits an exposed face within the face's bounds; the packet starts at that intersection
+ * point.  `uniform()` supplies the deviates (two per trial).  Kept as in the reference: only the
+ * first trial is mirrored; the start is exactly ON the face, so for a face at the top anchor
+ * get_cell_indices can put it one cell outside and the packet is lost (Isotropic guards against
+ * that with its epsilon, this source does not).
+ */
+template <class Uniform>
+CMIB_HD void distant_star_incoming(const GridGeom &g, const double *star, const int *exposed, Uniform &&uniform,
+                                   double &px, double &py, double &pz, double &dx, double &dy, double &dz) {
+  const double bottom[3] = {g.anchor[0], g.anchor[1], g.anchor[2]};
+  const double top[3] = {g.anchor[0] + g.sides[0], g.anchor[1] + g.sides[1], g.anchor[2] + g.sides[2]};
+  double d[3], fp[3] = {0., 0., 0.};
+  for (int trial = 0; trial < (1 << 24); ++trial) {
+    const double cost = 2. * uniform() - 1.;
+    const double s2 = 1. - cost * cost;
+    const double sint = sqrt(s2 > 0. ? s2 : 0.);
+    const double phi = 2. * M_PI * uniform();
+    double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+    sincos(phi, &sinp, &cosp);
+#else
+    cosp = cos(phi);
+    sinp = sin(phi);
+#endif
+    d[0] = sint * cosp; d[1] = sint * sinp; d[2] = cost;
+    if (trial == 0)
+      for (int i = 0; i < 3; ++i)
+        if (exposed[i] * d[i] > 0.) d[i] = -d[i];
+    bool enters = false;
+    for (int i = 0; i < 3 && !enters; ++i) {
+      if (exposed[i] * d[i] < 0.) {
+        const double plane = (exposed[i] < 0) ? bottom[i] : top[i];
+        const double l = (plane - star[i]) / d[i];
+        for (int k = 0; k < 3; ++k) fp[k] = star[k] + l * d[k];
+        const int j1 = (i + 1) % 3, j2 = (i + 2) % 3;
+        enters = fp[j1] >= bottom[j1] && fp[j1] <= top[j1] && fp[j2] >= bottom[j2] && fp[j2] <= top[j2];
+      }
+    }
+    if (enters) break;
+  }
+  px = fp[0]; py = fp[1]; pz = fp[2];
+  dx = d[0]; dy = d[1]; dz = d[2];
+}
+
 CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
   const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
@@ -293,7 +344,9 @@ CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, PacketRng &rn
     nu = spectrum_frequency(m.spectrum, rng);
   } else {
     double u[5];
-    if (m.continuous_kind == CONTINUOUS_PLANAR) {
+    if (m.continuous_kind == CONTINUOUS_DISTANT_STAR) {
+      distant_star_incoming(g, m.star_position, m.star_exposed, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
+    } else if (m.continuous_kind == CONTINUOUS_PLANAR) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) u[k] = rng_uniform(rng);
       planar_incoming(m.planar_axis, m.planar_intercept, m.planar_anchor, m.planar_sides, u, px, py, pz, dx, dy, dz);

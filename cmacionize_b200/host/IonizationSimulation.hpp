@@ -1201,9 +1201,24 @@ public:
      * (IonizationSimulation.cpp:164-174) */
     const std::string continuous_type = parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None");
     if (log_) log_->write_info("Requested ContinuousPhotonSource type: ", continuous_type, ".");
-    if (continuous_type != "None" && continuous_type != "Isotropic" && continuous_type != "Planar")
-      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic and Planar)!",
+    if (continuous_type != "None" && continuous_type != "Isotropic" && continuous_type != "Planar" &&
+        continuous_type != "DistantStar")
+      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic, Planar and DistantStar)!",
                 continuous_type.c_str());
+    /* DistantStarContinuousPhotonSource(box, params) (src/DistantStarContinuousPhotonSource.hpp:92-97) */
+    Vec3 star_position = {0., 0., 0.};
+    double star_area = 0.;
+    if (continuous_type == "DistantStar") {
+      star_position = parameter_file_.get_physical_vector<QUANTITY_LENGTH>("ContinuousPhotonSource:position");
+      /* get_total_surface_area (:194-212): the faces turned towards the star */
+      const bool ex[3] = {star_position[0] < box.anchor[0] || star_position[0] > box.anchor[0] + box.sides[0],
+                          star_position[1] < box.anchor[1] || star_position[1] > box.anchor[1] + box.sides[1],
+                          star_position[2] < box.anchor[2] || star_position[2] > box.anchor[2] + box.sides[2]};
+      if (ex[0]) star_area += box.sides[1] * box.sides[2];
+      if (ex[1]) star_area += box.sides[0] * box.sides[2];
+      if (ex[2]) star_area += box.sides[0] * box.sides[1];
+      if (!ex[0] && !ex[1] && !ex[2]) cmi_error("External stellar source lies inside the simulation box. This will not work!");
+    }
     /* PlanarContinuousPhotonSource(ParameterFile&) (src/PlanarContinuousPhotonSource.hpp:133-151) */
     int planar_axis = 2;
     double planar_intercept = 0., planar_anchor[2] = {0., 0.}, planar_sides[2] = {1., 1.}, planar_luminosity = 0.;
@@ -1232,8 +1247,10 @@ public:
     } else if (has_continuous) {
       /* PhotonSource.cpp:104-108: total surface area (IsotropicContinuousPhotonSource.hpp:187-192) x total flux */
       if (continuous_photon_source_spectrum_->total_flux < 0.) cmi_error("This function should not be used!");
-      const double area = 2. * box.sides[0] * box.sides[1] + 2. * box.sides[0] * box.sides[2] +
-                          2. * box.sides[1] * box.sides[2];
+      const double area = (continuous_type == "DistantStar")
+                              ? star_area
+                              : 2. * box.sides[0] * box.sides[1] + 2. * box.sides[0] * box.sides[2] +
+                                    2. * box.sides[1] * box.sides[2];
       continuous_luminosity = area * continuous_photon_source_spectrum_->total_flux;
     }
     /* classic driver: always through the factory; task-based driver: only when the diffuse field is switched
@@ -1264,7 +1281,11 @@ public:
         CMIB_CALL(continuous_photon_source_spectrum_->set_on(ctx, 1));
         if (continuous_type == "Planar")
           CMIB_CALL(cmib_set_planar_source_geometry(ctx, planar_axis, planar_intercept, planar_anchor, planar_sides));
-        CMIB_CALL(cmib_set_continuous_source(ctx, continuous_type == "Planar" ? CMIB_CONTINUOUS_PLANAR : CMIB_CONTINUOUS_ISOTROPIC,
+        if (continuous_type == "DistantStar") CMIB_CALL(cmib_set_distant_star_position(ctx, star_position.data()));
+        CMIB_CALL(cmib_set_continuous_source(ctx,
+                                             continuous_type == "Planar" ? CMIB_CONTINUOUS_PLANAR
+                                             : continuous_type == "DistantStar" ? CMIB_CONTINUOUS_DISTANT_STAR
+                                                                                : CMIB_CONTINUOUS_ISOTROPIC,
                                              continuous_luminosity,
                                              continuous_photon_source_spectrum_->kind,
                                              continuous_photon_source_spectrum_->param));

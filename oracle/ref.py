@@ -284,6 +284,16 @@ def integrate_optical_depth(anchor, sides, ncell, periodic, n, xH, xHe, pos, dir
     return out
 
 
+def distant_star_incoming(anchor, sides, star, n, seed=42):
+    """(positions [n,3], directions [n,3], exposed area) of DistantStarContinuousPhotonSource with RandomGenerator(seed)"""
+    a, sd, st = (np.ascontiguousarray(v, dtype=np.float64) for v in (anchor, sides, star))
+    pos, d = np.empty((n, 3)), np.empty((n, 3))
+    L = lib()
+    L.cmi_ref_distant_star_incoming.restype = C.c_double
+    area = L.cmi_ref_distant_star_incoming(_p(a), _p(sd), _p(st), C.c_int(seed), C.c_int64(n), _p(pos), _p(d))
+    return pos, d, area
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

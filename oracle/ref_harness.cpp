@@ -39,6 +39,7 @@
 #include "Abundances.hpp"
 #include "CartesianDensityGrid.hpp"
 #include "ChargeTransferRates.hpp"
+#include "DistantStarContinuousPhotonSource.hpp"
 #include "DensityGridWriter.hpp"
 #include "FixedValueCrossSections.hpp"
 #include "FixedValueRecombinationRates.hpp"
@@ -649,6 +650,23 @@ void cmi_ref_planar_incoming(int axis, double intercept, const double *anchor, c
       dir[3 * i + k] = pd.second[k];
     }
   }
+}
+
+/* DistantStarContinuousPhotonSource::get_random_incoming_direction (src/DistantStarContinuousPhotonSource.hpp:164-192)
+ * n times with RandomGenerator(seed); also the exposed surface area */
+double cmi_ref_distant_star_incoming(const double *anchor, const double *sides, const double *star, int seed, int64_t n,
+                                     double *pos, double *dir) {
+  const Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]), CoordinateVector<>(sides[0], sides[1], sides[2]));
+  DistantStarContinuousPhotonSource source(CoordinateVector<>(star[0], star[1], star[2]), box);
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = pd.first[k];
+      dir[3 * i + k] = pd.second[k];
+    }
+  }
+  return source.get_total_surface_area();
 }
 
 /* FaucherGiguerePhotonSourceSpectrum(redshift) (src/FaucherGiguerePhotonSourceSpectrum.cpp): its

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../cmacionize_b200/host/RandomGenerator.hpp"
 #include "../../cmacionize_b200/csrc/march.cuh"
 #include "../../cmacionize_b200/csrc/shoot.cuh"
 #include "../../cmacionize_b200/csrc/source.cuh"
@@ -171,6 +172,22 @@ void hc_integrate_optical_depth(const double *anchor, const double *sides, const
       return r;
     }, 1ll << 22);
   }
+}
+
+/* deviates from the host layer's RANLUX generator (the reference's stream, bit for bit) */
+void hc_distant_star_incoming(const double *anchor, const double *sides, const double *star, int seed, int64_t n,
+                              double *pos, double *dir) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  int exposed[3];
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = anchor[d]; g.sides[d] = sides[d];
+    exposed[d] = (star[d] < anchor[d]) ? -1 : ((star[d] > anchor[d] + sides[d]) ? 1 : 0);
+  }
+  cmi::RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i)
+    distant_star_incoming(g, star, exposed, [&rg]() { return rg.get_uniform_random_double(); }, pos[3 * i], pos[3 * i + 1],
+                          pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
 }
 
 void hc_planar_incoming(int axis, double intercept, const double *anchor, const double *sides, int64_t n,

@@ -26,7 +26,7 @@ def make_paramfile(tmp_path, name, seed):
     return pf
 
 
-@pytest.mark.parametrize("name", ["external_field", "star_plus_external_field", "planar_sheet"])
+@pytest.mark.parametrize("name", ["external_field", "star_plus_external_field", "planar_sheet", "distant_star"])
 def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     nc = 32
     runs = [ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)[0] for seed in (42, 4242)]
@@ -51,6 +51,8 @@ def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     depth1 = np.minimum(i, nc - 1 - i)
     if name == "planar_sheet":   # distance from the sheet instead
         depth = np.meshgrid(i, i, np.abs(i - (nc - 1) / 2.).astype(int), indexing="ij")[2].ravel()
+    elif name == "distant_star":  # depth below the two lit faces (x low, y low)
+        depth = np.minimum(*np.meshgrid(i, i, i, indexing="ij")[:2]).ravel() // 2
     else:
         depth = np.minimum.reduce(np.meshgrid(depth1, depth1, depth1, indexing="ij")).ravel()
     for d in range(nc // 2):

@@ -169,7 +169,7 @@ def test_shoot_is_deterministic_and_shardable(cmib):
 
 
 @pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
-                                    "continuous", "continuous_only", "planar"])
+                                    "continuous", "continuous_only", "planar", "distant_star"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -202,6 +202,12 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         prob.ctx.set_sources(None, None, 0.)
         prob.ctx.set_planar_source_geometry(2, 0., [-4 * PC, -5 * PC], [8 * PC, 10 * PC])
         prob.ctx.set_continuous_source(capi.CONTINUOUS_PLANAR, 3e49, capi.SPECTRUM_MONOCHROMATIC, problems.ev_to_hz(13.6))
+    elif config == "distant_star":
+        # DistantStarContinuousPhotonSource: rejection sampling, a variable number of deviates per packet
+        prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
+        prob.ctx.set_distant_star_position([-9 * PC, -7 * PC, 1 * PC])
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_DISTANT_STAR, 0.5 * 4.26e49, capi.SPECTRUM_MONOCHROMATIC,
+                                       problems.ev_to_hz(13.6))
     elif config == "continuous_only":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
         prob.ctx.set_sources(None, None, 0.)
@@ -248,8 +254,9 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     os.environ.pop("CMIB_SORT", None)
     ctx.close()
     tw0, tc0, st0, J0, h0 = results[0]
-    if config == "continuous":
-        ncont = round((npk - tw0) / 0.75)  # tw = n_discrete + 0.25 n_continuous
+    if config in ("continuous", "distant_star"):
+        wc = 0.25 if config == "continuous" else 0.5
+        ncont = round((npk - tw0) / (1. - wc))  # tw = n_discrete + wc n_continuous
         assert abs(ncont - 0.5 * npk) < 5 * np.sqrt(0.25 * npk) and abs(tc0.sum() - tw0) < 1e-9 * tw0
     else:
         assert tw0 == npk and tc0.sum() == npk

@@ -242,3 +242,20 @@ def test_integrate_optical_depth_bitexact(hostcheck, ref, grid):
                                          p(c["xH"]), p(c["xHe"]), C.c_int64(len(pos)), p(pos), p(d), p(sh), p(she), p(out))
     assert np.array_equal(out, r)
     assert (r >= 0).all() and (r > 0).mean() > 0.9
+
+
+def test_distant_star_continuous_source_bitexact(hostcheck, ref):
+    """DistantStarContinuousPhotonSource::get_random_incoming_direction (rejection sampling, a variable
+    number of deviates per packet) driven by the RANLUX stream on both sides: every start position and
+    direction bit for bit — one, two and three exposed faces, below and above the box."""
+    anchor, sides = np.array([-1e17, -2e17, -1.5e17]), np.array([2e17, 4e17, 3e17])
+    for star in ([-6e17, 0., 0.], [3e17, 5e17, 0.5e17], [-4e17, -7e17, 6e17], [0.2e17, 0.3e17, 9e17]):
+        st = np.array(star)
+        pos, d, area = ref.distant_star_incoming(anchor, sides, st, 5000, seed=9)
+        pos2, d2 = np.empty_like(pos), np.empty_like(d)
+        hostcheck.hc_distant_star_incoming(p(anchor), p(sides), p(st), C.c_int(9), C.c_int64(len(pos)), p(pos2), p(d2))
+        assert np.array_equal(d2, d) and np.array_equal(pos2, pos)
+        exposed = (st < anchor) | (st > anchor + sides)
+        assert area == sum(sides[(k + 1) % 3] * sides[(k + 2) % 3] for k in range(3) if exposed[k])
+        on_face = (np.isclose(pos2, anchor, rtol=0, atol=1e-9 * sides) | np.isclose(pos2, anchor + sides, rtol=0, atol=1e-9 * sides))
+        assert (on_face & exposed).any(axis=1).all()
