@@ -171,6 +171,10 @@ class Context:
         f = _f64(fixed, (NUM_IONS,)) if fixed is not None else None
         _check(lib.cmib_set_cross_sections(self._h, C.c_int(kind), _p(f)))
 
+    def set_bimodal_cross_sections(self, frequency_limit, low, high):
+        lo, hi = _f64(low, (NUM_IONS,)), _f64(high, (NUM_IONS,))
+        _check(lib.cmib_set_bimodal_cross_sections(self._h, C.c_double(frequency_limit), _p(lo), _p(hi)))
+
     def set_recombination_rates(self, kind, fixed=None):
         f = _f64(fixed, (NUM_IONS,)) if fixed is not None else None
         _check(lib.cmib_set_recombination_rates(self._h, C.c_int(kind), _p(f)))

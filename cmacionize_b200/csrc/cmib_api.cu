@@ -187,9 +187,9 @@ struct cmib_context {
 
   int pick_acc_mode() const {
     if (force_full) return ACC_FULL;
-    if (src.xs_kind != XS_FIXED) return ACC_FULL;
+    if (src.xs_kind == XS_VERNER) return ACC_FULL;
     for (int k = 1; k < NUM_IONS; ++k)
-      if (src.xs_fixed[k] != 0.) return ACC_FULL;
+      if (src.xs_fixed[k] != 0. || (src.xs_kind == XS_BIMODAL && src.xs_high[k] != 0.)) return ACC_FULL;
     return ACC_HONLY;
   }
   /* H-only accumulator layout: planes when cells_h + accumulators do not fit in L2 */
@@ -787,6 +787,18 @@ int cmib_set_abundances(cmib_context *ctx, const double *abundances) {
   return 0;
 }
 
+int cmib_set_bimodal_cross_sections(cmib_context *ctx, double frequency_limit, const double *low, const double *high) {
+  CHECK_CTX(ctx);
+  if (!low || !high) CMIB_FAIL("Bimodal cross sections need 14 values below and 14 above the limit");
+  ctx->src.xs_kind = XS_BIMODAL;
+  ctx->src.xs_limit = frequency_limit;
+  for (int k = 0; k < NUM_IONS; ++k) {
+    ctx->src.xs_fixed[k] = low[k];
+    ctx->src.xs_high[k] = high[k];
+  }
+  return ensure_acc(ctx);
+}
+
 int cmib_set_cross_sections(cmib_context *ctx, int kind, const double *fixed) {
   CHECK_CTX(ctx);
   if (kind == CMIB_CROSS_SECTIONS_VERNER) {
@@ -961,7 +973,9 @@ int cmib_set_reemission(cmib_context *ctx, int kind, double probability, double 
     const SourceModel m = ctx->src;
     auto sigma_of = [m](int ion) {
       return [m, ion](double nu) {
-        return m.xs_kind == XS_VERNER ? verner_cross_section(ion, nu) : m.xs_fixed[ion];
+        if (m.xs_kind == XS_VERNER) return verner_cross_section(ion, nu);
+        if (m.xs_kind == XS_BIMODAL) return nu < m.xs_limit ? m.xs_fixed[ion] : m.xs_high[ion];
+        return m.xs_fixed[ion];
       };
     };
     host::build_lyc_table(0, sigma_of(ION_H_n), ctx->h_hlyc_freq, ctx->h_hlyc_temp, ctx->h_hlyc_cdf);

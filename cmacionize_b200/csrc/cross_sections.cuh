@@ -21,7 +21,7 @@
 
 namespace cmib {
 
-enum CrossSectionKind : int { XS_FIXED = 0, XS_VERNER = 1 };
+enum CrossSectionKind : int { XS_FIXED = 0, XS_VERNER = 1, XS_BIMODAL = 2 };
 
 /* A * x^a * z^b.  Host build: the reference's expression with two pow(), left to right, so that
  * the table transcription and the re-emission spectra tabulated from it are pinned bit for bit

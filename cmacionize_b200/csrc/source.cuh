@@ -77,7 +77,9 @@ struct SourceModel {
   SpectrumModel spectrum;        /* spectrum of the discrete sources */
   /* cross sections */
   int xs_kind;
-  double xs_fixed[NUM_IONS];
+  double xs_fixed[NUM_IONS];     /* FixedValue; Bimodal: the values below the frequency limit */
+  double xs_high[NUM_IONS];      /* Bimodal (BimodalCrossSections.hpp:247-254): at and above xs_limit */
+  double xs_limit;
   double A_He;
   /* diffuse re-emission */
   int reemission_kind;
@@ -394,6 +396,11 @@ CMIB_HD void packet_cross_sections(const SourceModel &m, double nu, double *sigm
       if (ion == ION_He_n) sHe = s;
     }
     sigma_He_corr = m.A_He * sHe;
+  } else if (m.xs_kind == XS_BIMODAL) {
+    const bool low = nu < m.xs_limit;
+#pragma unroll
+    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = low ? m.xs_fixed[ion] : m.xs_high[ion];
+    sigma_He_corr = m.A_He * (low ? m.xs_fixed[ION_He_n] : m.xs_high[ION_He_n]);
   } else {
 #pragma unroll
     for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = m.xs_fixed[ion];

@@ -120,6 +120,19 @@ class ParameterFile:
         _check(lib.cmih_initial_number_density(self._h, C.c_int64(ncells), dens.ctypes.data_as(C.c_void_p)))
         return dens
 
+    def abundances(self):
+        out = np.empty(6)
+        _check(lib.cmih_abundances(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def cross_sections(self, nu):
+        """sigma [n,14] of the file's FixedValue / Bimodal CrossSections at the frequencies nu"""
+        nu = np.ascontiguousarray(nu, dtype=np.float64).reshape(-1)
+        out = np.empty((nu.size, 14))
+        _check(lib.cmih_parameter_cross_sections(self._h, C.c_int64(nu.size), nu.ctypes.data_as(C.c_void_p),
+                                                 out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def density_function(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1, 3)
         n = x.shape[0]

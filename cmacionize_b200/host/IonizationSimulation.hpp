@@ -743,8 +743,14 @@ struct PhotonSourceSpectrum {
 };
 
 struct CrossSections {
-  int kind;
+  int kind; /* CMIB_CROSS_SECTIONS_*; 2 = Bimodal (two constant values per ion) */
   double fixed[CMIB_NUM_IONS] = {0.};
+  double high[CMIB_NUM_IONS] = {0.};
+  double frequency_limit = 0.;
+  int set_on(cmib_context *ctx) const {
+    if (kind == 2) return cmib_set_bimodal_cross_sections(ctx, frequency_limit, fixed, high);
+    return cmib_set_cross_sections(ctx, kind, fixed);
+  }
   static CrossSections *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("CrossSections:type", "Verner");
     if (log) log->write_info("Requested CrossSections type: ", type);
@@ -759,6 +765,25 @@ struct CrossSections {
       for (int i = 0; i < CMIB_NUM_IONS; ++i)
         c->fixed[i] = params.get_physical_value<QUANTITY_SURFACE_AREA>(std::string("CrossSections:") + keys[i],
                                                                       i == 0 ? "6.3e-18 cm^2" : "0. m^2");
+    } else if (type == "Bimodal") {
+      /* BiModalCrossSections(ParameterFile&) (src/BimodalCrossSections.hpp:174-245), kept as it is: the
+       * frequency limit is read from the key "frequency limit:" (no block), and the member initialisers
+       * swap the two values of oxygen_0 and of sulphur_1 (:132, :138 / :151, :157): "oxygen_0_high" is
+       * what applies BELOW the limit */
+      c->kind = 2;
+      c->frequency_limit = params.get_physical_value<QUANTITY_FREQUENCY>("frequency limit:", "15. eV");
+      static const char *keys[CMIB_NUM_IONS] = {"hydrogen_0", "helium_0", "carbon_1", "carbon_2", "nitrogen_0",
+                                                "nitrogen_1", "nitrogen_2", "oxygen_0", "oxygen_1", "neon_0",
+                                                "neon_1", "sulphur_1", "sulphur_2", "sulphur_3"};
+      for (int i = 0; i < CMIB_NUM_IONS; ++i) {
+        const double low = params.get_physical_value<QUANTITY_SURFACE_AREA>(std::string("CrossSections:") + keys[i] + "_low",
+                                                                            i == 0 ? "6.3e-18 cm^2" : "0. m^2");
+        const double high = params.get_physical_value<QUANTITY_SURFACE_AREA>(std::string("CrossSections:") + keys[i] + "_high",
+                                                                             i == 0 ? "6.3e-18 cm^2" : "0. m^2");
+        const bool swapped = (i == 7 || i == 11); /* oxygen_0, sulphur_1 */
+        c->fixed[i] = swapped ? high : low;
+        c->high[i] = swapped ? low : high;
+      }
     } else {
       delete c;
       cmi_error("Unknown CrossSections type: \"%s\"!", type.c_str());
@@ -812,8 +837,25 @@ struct Abundances {
       }
     }
     const std::string type = params.get_value<std::string>("AbundanceModel:type", "FixedValue");
-    if (type != "FixedValue") cmi_error("Unknown AbundanceModel type: \"%s\"!", type.c_str());
     Abundances a;
+    if (type == "SolarMetallicity") {
+      /* SolarMetallicityAbundanceModel (src/SolarMetallicityAbundanceModel.hpp:46-121): log10 abundances
+       * scaled with the oxygen abundance (N with its secondary-production break at -4) */
+      const double metallicity = params.get_value<double>("AbundanceModel:metallicity", -3.31);
+      const double solar_He = -1.07, solar_C = -3.57, solar_N = -4.17, solar_O = -3.31, solar_Ne = -4.07, solar_S = -4.88;
+      double actual_C = solar_C, actual_N = solar_N, actual_Ne = solar_Ne, actual_S = solar_S;
+      if (metallicity != solar_O) {
+        const double Odiff = metallicity - solar_O;
+        actual_C = solar_C + Odiff;
+        actual_Ne = solar_Ne + Odiff;
+        actual_S = solar_S + Odiff;
+        actual_N = (metallicity <= -4.) ? metallicity - 1.6 : metallicity + 0.6 * (metallicity + 4.) - 1.6;
+      }
+      const double logs[CMIB_NUM_ELEMENTS] = {solar_He, actual_C, actual_N, metallicity, actual_Ne, actual_S};
+      for (int i = 0; i < CMIB_NUM_ELEMENTS; ++i) a.abundance[i] = std::pow(10., logs[i]);
+      return a;
+    }
+    if (type != "FixedValue") cmi_error("Unknown AbundanceModel type: \"%s\"!", type.c_str());
     for (int i = 0; i < CMIB_NUM_ELEMENTS; ++i)
       a.abundance[i] = params.get_value<double>(std::string("AbundanceModel:") + element_name(i), 0.);
     return a;
@@ -1273,7 +1315,7 @@ public:
     for (auto &grid : density_grids_) {
       cmib_context *ctx = grid->context();
       CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
-      CMIB_CALL(cmib_set_cross_sections(ctx, cross_sections_->kind, cross_sections_->fixed));
+      CMIB_CALL(cross_sections_->set_on(ctx));
       CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
       CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), discrete_luminosity));
       if (ns > 0) CMIB_CALL(photon_source_spectrum_->set_on(ctx, 0));

@@ -203,6 +203,24 @@ int cmih_initial_number_density(void *h, int64_t n, double *dens) {
     for (int64_t i = 0; i < n; ++i) dens[i] = cells.number_density[i];
   });
 }
+/* AbundanceModelFactory on the parameter file -> He C N O Ne S relative to H */
+int cmih_abundances(void *h, double *out) {
+  CMIH_TRY({
+    const Abundances a = Abundances::generate(*static_cast<ParameterFile *>(h));
+    for (int i = 0; i < CMIB_NUM_ELEMENTS; ++i) out[i] = a.abundance[i];
+  });
+}
+/* CrossSectionsFactory on the parameter file for the types that are plain parameters (FixedValue,
+ * Bimodal): sigma[n][14] at the n frequencies; Verner is evaluated on the device (cmib_eval_cross_sections) */
+int cmih_parameter_cross_sections(void *h, int64_t n, const double *nu, double *sigma) {
+  CMIH_TRY({
+    std::unique_ptr<CrossSections> c(CrossSections::generate(*static_cast<ParameterFile *>(h)));
+    if (c->kind == CMIB_CROSS_SECTIONS_VERNER) throw std::runtime_error("Verner cross sections live on the device");
+    for (int64_t i = 0; i < n; ++i)
+      for (int k = 0; k < CMIB_NUM_IONS; ++k)
+        sigma[i * CMIB_NUM_IONS + k] = (c->kind == 2 && !(nu[i] < c->frequency_limit)) ? c->high[k] : c->fixed[k];
+  });
+}
 /* n deviates of the host-side RandomGenerator (RANLUX level 2, host/RandomGenerator.hpp) */
 int cmih_random_stream(int32_t seed, int64_t n, double *out) {
   CMIH_TRY({

@@ -109,6 +109,10 @@ int cmib_set_abundances(cmib_context *ctx, const double abundances[CMIB_NUM_ELEM
 /* CrossSectionsFactory (src/CrossSectionsFactory.hpp:60-80); fixed[14] in m^2 is read
  * for FIXED_VALUE (src/FixedValueCrossSections.hpp), ignored for VERNER */
 int cmib_set_cross_sections(cmib_context *ctx, int kind, const double fixed[CMIB_NUM_IONS]);
+/* CrossSections:type Bimodal (src/BimodalCrossSections.hpp:247-254): low[ion] below the frequency limit (Hz),
+ * high[ion] at and above it, both in m^2 */
+int cmib_set_bimodal_cross_sections(cmib_context *ctx, double frequency_limit, const double low[CMIB_NUM_IONS],
+                                    const double high[CMIB_NUM_IONS]);
 /* RecombinationRatesFactory (src/RecombinationRatesFactory.hpp:59-72); fixed[14] m^3 s^-1 */
 int cmib_set_recombination_rates(cmib_context *ctx, int kind, const double fixed[CMIB_NUM_IONS]);
 /* PhotonSourceDistribution -> PhotonSource (src/PhotonSource.cpp:55-146): positions

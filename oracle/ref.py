@@ -294,6 +294,19 @@ def distant_star_incoming(anchor, sides, star, n, seed=42):
     return pos, d, area
 
 
+def abundances(paramfile):
+    out = np.empty(6)
+    lib().cmi_ref_abundances(str(paramfile).encode(), _p(out))
+    return out
+
+
+def parameter_cross_sections(paramfile, nu):
+    nu = np.ascontiguousarray(nu, dtype=np.float64).reshape(-1)
+    out = np.empty((nu.size, 14))
+    lib().cmi_ref_parameter_cross_sections(str(paramfile).encode(), C.c_int64(nu.size), _p(nu), _p(out))
+    return out
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

@@ -37,6 +37,8 @@
 #define private public
 #define protected public
 #include "Abundances.hpp"
+#include "AbundanceModelFactory.hpp"
+#include "CrossSectionsFactory.hpp"
 #include "CartesianDensityGrid.hpp"
 #include "ChargeTransferRates.hpp"
 #include "DistantStarContinuousPhotonSource.hpp"
@@ -667,6 +669,24 @@ double cmi_ref_distant_star_incoming(const double *anchor, const double *sides, 
     }
   }
   return source.get_total_surface_area();
+}
+
+/* AbundanceModelFactory::generate on a parameter file -> He C N O Ne S */
+void cmi_ref_abundances(const char *paramfile, double *out) {
+  ParameterFile params(paramfile);
+  AbundanceModel *model = AbundanceModelFactory::generate(params, nullptr);
+  const Abundances a = model->get_abundances();
+  for (int i = 0; i < NUMBER_OF_ELEMENTNAMES; ++i) out[i] = a.get_abundance(i);
+  delete model;
+}
+
+/* CrossSectionsFactory::generate on a parameter file, evaluated at n frequencies -> sigma[n][14] */
+void cmi_ref_parameter_cross_sections(const char *paramfile, int64_t n, const double *nu, double *sigma) {
+  ParameterFile params(paramfile);
+  CrossSections *xs = CrossSectionsFactory::generate(params, nullptr);
+  for (int64_t i = 0; i < n; ++i)
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) sigma[i * NUMBER_OF_IONNAMES + ion] = xs->get_cross_section(ion, nu[i]);
+  delete xs;
 }
 
 /* FaucherGiguerePhotonSourceSpectrum(redshift) (src/FaucherGiguerePhotonSourceSpectrum.cpp): its

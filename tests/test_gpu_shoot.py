@@ -169,7 +169,7 @@ def test_shoot_is_deterministic_and_shardable(cmib):
 
 
 @pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
-                                    "continuous", "continuous_only", "planar", "distant_star"])
+                                    "continuous", "continuous_only", "planar", "distant_star", "bimodal"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -208,6 +208,18 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         prob.ctx.set_distant_star_position([-9 * PC, -7 * PC, 1 * PC])
         prob.ctx.set_continuous_source(capi.CONTINUOUS_DISTANT_STAR, 0.5 * 4.26e49, capi.SPECTRUM_MONOCHROMATIC,
                                        problems.ev_to_hz(13.6))
+    elif config == "bimodal":
+        # CrossSections: Bimodal (two constant values per ion, split at a frequency limit) with the diffuse field
+        prob = problems.lexington(20, ncell=24, n_packets=npk)
+        low, high = np.zeros(14), np.zeros(14)
+        low[0], high[0] = 6.3e-22, 2.5e-22
+        high[1] = 7.e-22
+        low[7], high[7], low[4], high[9] = 3e-22, 1e-22, 2e-22, 4e-22
+        prob.ctx.set_bimodal_cross_sections(problems.ev_to_hz(20.), low, high)
+        prob.ctx.set_reemission(capi.REEMISSION_PHYSICAL)        # rebuilds its tables from these cross sections
+        nu_probe = problems.ev_to_hz(np.array([13.7, 19.99, 20.0, 30.]))
+        sig = prob.ctx.eval_cross_sections(nu_probe)
+        assert np.array_equal(sig[:2], np.tile(low, (2, 1))) and np.array_equal(sig[2:], np.tile(high, (2, 1)))
     elif config == "continuous_only":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
         prob.ctx.set_sources(None, None, 0.)
@@ -450,3 +462,31 @@ def test_measured_queue_order_changes_nothing(cmib, capacity):
         os.environ.pop("CMIB_QUEUE_CAPACITY", None)
         os.environ.pop("CMIB_SORT", None)
         ctx.close()
+
+
+def test_source_configuration_errors(cmib):
+    """Misuse is reported with the reference's messages (and never computes): no sources at all, a
+    distant star inside the box (DistantStarContinuousPhotonSource.hpp:78-81), geometry forgotten,
+    unknown types, a non-monotonic tabulated spectrum, zero luminosity."""
+    from cmacionize_b200 import capi
+    with cmib.Context([-1., -1., -1.], [2., 2., 2.], [4, 4, 4]) as ctx:
+        with pytest.raises(cmib.CmibError, match="no photon sources set"):
+            ctx.shoot(10)
+        with pytest.raises(cmib.CmibError, match="lies inside the simulation box"):
+            ctx.set_distant_star_position([0.5, 0., 0.])
+        with pytest.raises(cmib.CmibError, match="cmib_set_distant_star_position before"):
+            ctx.set_continuous_source(capi.CONTINUOUS_DISTANT_STAR, 1e49, capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
+        with pytest.raises(cmib.CmibError, match="cmib_set_planar_source_geometry before"):
+            ctx.set_continuous_source(capi.CONTINUOUS_PLANAR, 1e49, capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
+        with pytest.raises(cmib.CmibError, match="Unknown ContinuousPhotonSource type"):
+            ctx.set_continuous_source(7, 1e49, capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
+        with pytest.raises(cmib.CmibError, match="Unknown PhotonSourceSpectrum type"):
+            ctx.set_spectrum(9, 0.)
+        with pytest.raises(cmib.CmibError, match="positive luminosity"):
+            ctx.set_continuous_source(capi.CONTINUOUS_ISOTROPIC, 0., capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
+        with pytest.raises(cmib.CmibError, match="must not decrease"):
+            ctx.set_spectrum_table([3.3e15, 4e15, 5e15], [0., 0.7, 0.5])
+        with pytest.raises(cmib.CmibError, match="at least two frequencies"):
+            ctx.set_spectrum_table([3.3e15], [1.])
+        with pytest.raises(cmib.CmibError, match="do not sum to 1"):
+            ctx.set_sources([[0., 0., 0.], [0.1, 0., 0.]], [0.5, 0.4], 1e49)

@@ -338,3 +338,33 @@ def test_sph_array_interface_maps_like_the_reference(host, ref, tmp_path, mappin
         assert abs(hd.mean() * 1.6737236e-27 * (10 * PC) ** 3 / m.sum() - 1.) < 0.1
     else:
         assert np.unique(hd).size == 1 and np.array_equal(hn, rn)
+
+
+def test_solar_metallicity_abundances_and_bimodal_cross_sections(host, ref, tmp_path):
+    """AbundanceModel: SolarMetallicity and CrossSections: Bimodal from a parameter file, against the
+    reference's factories: the six abundances and sigma[14](nu) on both sides of the frequency limit,
+    bit for bit — including the reference's swapped oxygen_0 / sulphur_1 members and its odd
+    "frequency limit:" key."""
+    for Z in (None, -3.31, -3.0, -4.5):
+        pf = tmp_path / f"abund_{Z}.param"
+        pf.write_text("AbundanceModel:\n  type: SolarMetallicity\n" + ("" if Z is None else f"  metallicity: {Z}\n"))
+        p = host.ParameterFile(pf)
+        a = p.abundances()
+        p.close()
+        assert np.array_equal(a, ref.abundances(pf)), Z
+        assert 0.08 < a[0] < 0.09 and (a[1:] > 0).all()
+    rng = np.random.default_rng(2)
+    keys = ["hydrogen_0", "helium_0", "carbon_1", "carbon_2", "nitrogen_0", "nitrogen_1", "nitrogen_2", "oxygen_0",
+            "oxygen_1", "neon_0", "neon_1", "sulphur_1", "sulphur_2", "sulphur_3"]
+    body = "".join(f"  {k}_low: {float(rng.uniform(1, 9)):.6f}e-18 cm^2\n  {k}_high: {float(rng.uniform(1, 9)):.6f}e-19 cm^2\n"
+                   for k in keys)
+    pf = tmp_path / "bimodal.param"
+    pf.write_text("frequency limit: 20. eV\nCrossSections:\n  type: Bimodal\n" + body)
+    nu = 3.288e15 * np.array([1.0, 1.05, 1.1029, 1.1030, 1.2, 1.4705, 1.4706, 1.5, 2.0, 3.9])
+    p = host.ParameterFile(pf)
+    sig = p.cross_sections(nu)
+    p.close()
+    r = ref.parameter_cross_sections(pf, nu)
+    assert np.array_equal(sig, r)
+    assert np.unique(sig[:, 0]).size == 2                       # both branches are exercised
+    assert sig[0, 7] < sig[-1, 7] and sig[0, 0] > sig[-1, 0]    # oxygen_0 is swapped, hydrogen_0 is not
