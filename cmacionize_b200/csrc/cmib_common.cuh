@@ -21,8 +21,8 @@
 #define CMIB_D inline
 #endif
 
-#if !defined(__CUDACC__)
-/* host build of the shared headers (tests/hostcheck): CUDA's vector type */
+#if !defined(__CUDACC__) && !defined(__VECTOR_TYPES_H__)
+/* host build of the shared headers without the CUDA headers (tests/hostcheck): CUDA's vector type */
 struct double2 { double x, y; };
 #endif
 

@@ -260,13 +260,16 @@ CMIB_HD void distant_star_incoming(const GridGeom &g, const double *star, const 
   dx = d[0]; dy = d[1]; dz = d[2];
 }
 
-CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
-  const double x = rng_uniform(rng);
+/* PlanckPhotonSourceSpectrum::get_random_frequency (PlanckPhotonSourceSpectrum.cpp:149-165) for the deviate x */
+CMIB_HD double planck_frequency_at(const double *tab, double x, const uint16_t *guide = nullptr) {
   const double *cdf = tab, *logcdf = tab + SPECTRUM_NUMFREQ, *lognu = tab + 2 * SPECTRUM_NUMFREQ;
   const uint32_t ix = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
   const double lf = (log10(x) - logcdf[ix]) / (logcdf[ix + 1] - logcdf[ix]) *
                         (lognu[ix + 1] - lognu[ix]) + lognu[ix];
   return fpow(10., lf) * 3.288465385e15; /* device: exp(lf ln 10), cmib_common.cuh */
+}
+CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
+  return planck_frequency_at(tab, rng_uniform(rng), guide);
 }
 
 /* PhotonSourceSpectrum::get_random_frequency of the source spectra:

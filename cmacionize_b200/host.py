@@ -98,12 +98,18 @@ class ParameterFile:
 
     def photon_source_spectrum(self, role="PhotonSourceSpectrum"):
         """dict(kind, param, total_flux, freq, cdf) of the file's spectrum for `role`"""
-        info, freq, cdf = np.zeros(4), np.empty(4096), np.empty(4096)
+        info, freq, cdf = np.zeros(4), np.empty(65536), np.empty(65536)
         vp = C.c_void_p
         _check(lib.cmih_photon_source_spectrum(self._h, role.encode(), info.ctypes.data_as(vp), freq.ctypes.data_as(vp),
-                                               cdf.ctypes.data_as(vp), C.c_int(4096)))
+                                               cdf.ctypes.data_as(vp), C.c_int(65536)))
         m = int(info[3])
         return dict(kind=int(info[0]), param=info[1], total_flux=info[2], freq=freq[:m].copy(), cdf=cdf[:m].copy())
+
+    def sample_spectrum(self, n, seed=42, role="PhotonSourceSpectrum"):
+        """n frequencies sampled on the host with RandomGenerator(seed) from the file's spectrum"""
+        nu = np.empty(n)
+        _check(lib.cmih_sample_spectrum(self._h, role.encode(), C.c_int32(seed), C.c_int64(n), nu.ctypes.data_as(C.c_void_p)))
+        return nu
 
     def photon_source_distribution(self, capacity=4096):
         """(positions [n,3], weights [n], total luminosity) of the file's PhotonSourceDistribution"""

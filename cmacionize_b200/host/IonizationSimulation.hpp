@@ -52,6 +52,7 @@
 #include "Error.hpp"
 #include "ParameterFile.hpp"
 #include "RandomGenerator.hpp"
+#include "../csrc/spectrum_tables.hpp" /* host-side table builders + the samplers the device uses (plain C++) */
 
 namespace cmi {
 
@@ -630,6 +631,59 @@ struct PhotonSourceSpectrum {
     return role == 0 ? cmib_set_spectrum(ctx, kind, param) : 0; /* role 1: through cmib_set_continuous_source */
   }
 
+  /* get_random_frequency on the host, with the reference's generator: the same functions the device
+   * runs (csrc/source.cuh), used to build a Masked spectrum */
+  double sample(RandomGenerator &random_generator) {
+    if (kind == CMIB_SPECTRUM_MONOCHROMATIC) return param;
+    const double x = random_generator.get_uniform_random_double();
+    if (kind == CMIB_SPECTRUM_PLANCK) {
+      if (planck_table_.empty()) cmib::host::build_planck_table(param, planck_table_);
+      return cmib::planck_frequency_at(planck_table_.data(), x);
+    }
+    if (kind == CMIB_SPECTRUM_UNIFORM) return cmib::uniform_frequency(x);
+    return cmib::tabulated_frequency(frequencies.data(), cumulative_distribution.data(), (uint32_t)frequencies.size(), x);
+  }
+  std::vector<double> planck_table_;
+
+  /*
+   * MaskedPhotonSourceSpectrum (src/MaskedPhotonSourceSpectrum.cpp:40-122): another spectrum seen through
+   * a frequency-dependent mask.  The unmasked spectrum is sampled `mask number of samples` times with
+   * RandomGenerator() (seed 42) into `mask number of bins` bins between 13.6 and 54.4 eV, every bin is
+   * multiplied by the mask (Linear: 1 at 13.6 eV falling to 0 at 54.4 eV,
+   * LinearPhotonSourceSpectrumMask.hpp:42-49), the result is made cumulative and normalised: a tabulated
+   * spectrum for the device.  Same generator, same samplers: the table is the reference's bit for bit.
+   */
+  static PhotonSourceSpectrum *masked(const std::string &role, ParameterFile &params, Log *log) {
+    const std::string unmasked_type = params.get_value<std::string>(role + ":masked type", "Planck");
+    if (unmasked_type == "Masked") cmi_error("A Masked spectrum cannot mask itself!");
+    std::unique_ptr<PhotonSourceSpectrum> unmasked(generate_from_type(unmasked_type, role, params, log));
+    if (!unmasked) cmi_error("No spectrum to mask!");
+    const std::string mask_type = params.get_value<std::string>(role + ":PhotonSourceSpectrumMask:type", "Linear");
+    if (mask_type != "Linear") cmi_error("Unknown PhotonSourceSpectrumMask type: \"%s\"!", mask_type.c_str());
+    const uint32_t number_of_bins = params.get_value<uint32_t>(role + ":mask number of bins", 1000);
+    const uint32_t number_of_samples = params.get_value<uint32_t>(role + ":mask number of samples", 10000000);
+    auto *s = new PhotonSourceSpectrum{CMIB_SPECTRUM_TABULATED, 0.};
+    std::vector<double> &freq = s->frequencies, &cdf = s->cumulative_distribution;
+    freq.assign(number_of_bins, 0.);
+    cdf.assign(number_of_bins, 0.);
+    const double min_frequency = 3.289e15, max_frequency = 4. * min_frequency;
+    const double frequency_bin_size = (max_frequency - min_frequency) / (number_of_bins - 1.);
+    for (uint32_t i = 0; i < number_of_bins; ++i) freq[i] = min_frequency + i * frequency_bin_size;
+    RandomGenerator random_generator;
+    for (uint32_t i = 0; i < number_of_samples; ++i) {
+      const double random_frequency = unmasked->sample(random_generator);
+      const uint32_t index = (uint32_t)((random_frequency - min_frequency) / frequency_bin_size);
+      if (index < number_of_bins) cdf[index] += 1.; /* the reference writes out of bounds otherwise */
+    }
+    for (uint32_t i = 0; i < number_of_bins; ++i) cdf[i] *= 1. - (freq[i] - min_frequency) / (max_frequency - min_frequency);
+    for (uint32_t i = 1; i < number_of_bins; ++i) cdf[i] += cdf[i - 1];
+    const double norm = cdf.back();
+    const double norm_inv = 1. / norm;
+    for (uint32_t i = 0; i < number_of_bins; ++i) cdf[i] *= norm_inv;
+    s->total_flux = norm * unmasked->total_flux / number_of_samples;
+    return s;
+  }
+
   /* Utilities::locate (src/Utilities.hpp:726-742) */
   static uint32_t locate(double x, const double *xarr, uint32_t length) {
     uint32_t jl = 0, ju = length;
@@ -721,6 +775,12 @@ struct PhotonSourceSpectrum {
   static PhotonSourceSpectrum *generate(const std::string &role, ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>(role + ":type", "Monochromatic");
     if (log) log->write_info("Requested PhotonSourceSpectrum for ", role, ": ", type);
+    return generate_from_type(type, role, params, log);
+  }
+  /* PhotonSourceSpectrumFactory::generate_from_type (src/PhotonSourceSpectrumFactory.hpp:84-119) */
+  static PhotonSourceSpectrum *generate_from_type(const std::string &type, const std::string &role, ParameterFile &params,
+                                                  Log *log = nullptr) {
+    if (type == "Masked") return masked(role, params, log);
     if (type == "Monochromatic") {
       auto *s = new PhotonSourceSpectrum{CMIB_SPECTRUM_MONOCHROMATIC,
                                          params.get_physical_value<QUANTITY_FREQUENCY>(role + ":frequency", "13.6 eV")};
@@ -736,8 +796,8 @@ struct PhotonSourceSpectrum {
     if (type == "Uniform") return new PhotonSourceSpectrum{CMIB_SPECTRUM_UNIFORM, 0.}; /* no total flux (UniformPhotonSourceSpectrum.hpp:60-63) */
     if (type == "FaucherGiguere") return faucher_giguere(params.get_value<double>(role + ":redshift", 0.));
     if (type == "None") return nullptr;
-    cmi_error("Unknown PhotonSourceSpectrum type: \"%s\" (the B200 backend provides Monochromatic, Planck, Uniform and "
-              "FaucherGiguere; any tabulated spectrum can be handed to cmib_set_spectrum_table)!",
+    cmi_error("Unknown PhotonSourceSpectrum type: \"%s\" (the B200 backend provides Monochromatic, Planck, Uniform, "
+              "FaucherGiguere and Masked; any tabulated spectrum can be handed to cmib_set_spectrum_table)!",
               type.c_str());
   }
 };

@@ -221,6 +221,17 @@ int cmih_parameter_cross_sections(void *h, int64_t n, const double *nu, double *
         sigma[i * CMIB_NUM_IONS + k] = (c->kind == 2 && !(nu[i] < c->frequency_limit)) ? c->high[k] : c->fixed[k];
   });
 }
+/* n frequencies sampled on the HOST from the parameter file's spectrum for `role` with RandomGenerator(seed):
+ * the samplers of csrc/source.cuh driven by the reference's stream (used to build Masked spectra) */
+int cmih_sample_spectrum(void *h, const char *role, int32_t seed, int64_t n, double *nu) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<PhotonSourceSpectrum> s(PhotonSourceSpectrum::generate(role, p));
+    if (!s) throw std::runtime_error("no spectrum (type None)");
+    RandomGenerator rg(seed);
+    for (int64_t i = 0; i < n; ++i) nu[i] = s->sample(rg);
+  });
+}
 /* n deviates of the host-side RandomGenerator (RANLUX level 2, host/RandomGenerator.hpp) */
 int cmih_random_stream(int32_t seed, int64_t n, double *out) {
   CMIH_TRY({

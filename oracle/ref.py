@@ -307,6 +307,14 @@ def parameter_cross_sections(paramfile, nu):
     return out
 
 
+def masked_spectrum(paramfile, role="PhotonSourceSpectrum"):
+    freq, cdf = np.empty(65536), np.empty(65536)
+    flux = C.c_double(0.)
+    n = lib().cmi_ref_masked_spectrum(str(paramfile).encode(), role.encode(), _p(freq), _p(cdf), C.c_int(65536), C.byref(flux))
+    assert n > 0
+    return dict(freq=freq[:n].copy(), cdf=cdf[:n].copy(), total_flux=flux.value)
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

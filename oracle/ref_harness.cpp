@@ -55,6 +55,8 @@
 #include "IsotropicContinuousPhotonSource.hpp"
 #include "UniformPhotonSourceSpectrum.hpp"
 #include "LineCoolingData.hpp"
+#include "MaskedPhotonSourceSpectrum.hpp"
+#include "PhotonSourceSpectrumFactory.hpp"
 #include "Photon.hpp"
 #include "PhotonSource.hpp"
 #include "PlanarContinuousPhotonSource.hpp"
@@ -687,6 +689,26 @@ void cmi_ref_parameter_cross_sections(const char *paramfile, int64_t n, const do
   for (int64_t i = 0; i < n; ++i)
     for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) sigma[i * NUMBER_OF_IONNAMES + ion] = xs->get_cross_section(ion, nu[i]);
   delete xs;
+}
+
+/* PhotonSourceSpectrumFactory::generate(role, params) of type Masked on a parameter file: its frequency
+ * bins, cumulative distribution and total flux; returns the number of bins (or -needed) */
+int cmi_ref_masked_spectrum(const char *paramfile, const char *role, double *freq, double *cdf, int capacity,
+                            double *total_flux) {
+  ParameterFile params(paramfile);
+  PhotonSourceSpectrum *sp = PhotonSourceSpectrumFactory::generate(role, params, nullptr);
+  MaskedPhotonSourceSpectrum *m = dynamic_cast<MaskedPhotonSourceSpectrum *>(sp);
+  if (m == nullptr) return 0;
+  const int n = (int)m->_frequency_bins.size();
+  if (n <= capacity) {
+    for (int i = 0; i < n; ++i) {
+      freq[i] = m->_frequency_bins[i];
+      cdf[i] = m->_cumulative_distribution[i];
+    }
+    *total_flux = m->get_total_flux();
+  }
+  delete sp;
+  return n <= capacity ? n : -n;
 }
 
 /* FaucherGiguerePhotonSourceSpectrum(redshift) (src/FaucherGiguerePhotonSourceSpectrum.cpp): its

@@ -368,3 +368,28 @@ def test_solar_metallicity_abundances_and_bimodal_cross_sections(host, ref, tmp_
     assert np.array_equal(sig, r)
     assert np.unique(sig[:, 0]).size == 2                       # both branches are exercised
     assert sig[0, 7] < sig[-1, 7] and sig[0, 0] > sig[-1, 0]    # oxygen_0 is swapped, hydrogen_0 is not
+
+
+def test_planck_sampler_and_masked_spectrum_bitexact(host, ref, tmp_path):
+    """(1) The Planck sampler the device runs (csrc/source.cuh planck_frequency_at), driven on the host by
+    the RANLUX stream, returns the reference's frequencies bit for bit (PlanckPhotonSourceSpectrum.cpp:149-165).
+    (2) PhotonSourceSpectrum: Masked (a Planck spectrum behind the Linear mask): the tabulated spectrum the
+    host layer hands to the device — bins, cumulative distribution, total flux — is the reference's."""
+    for T in (20000., 40000.):
+        pf = tmp_path / f"planck_{T}.param"
+        pf.write_text(f"PhotonSourceSpectrum:\n  type: Planck\n  temperature: {T} K\n")
+        p = host.ParameterFile(pf)
+        nu = p.sample_spectrum(200000, seed=17)
+        p.close()
+        assert np.array_equal(nu, ref.sample_spectrum(0, T, 200000, seed=17))
+    pf = tmp_path / "masked.param"
+    pf.write_text("PhotonSourceSpectrum:\n  type: Masked\n  masked type: Planck\n  temperature: 35000. K\n"
+                  "  ionizing flux: 1.e12 m^-2 s^-1\n  mask number of bins: 500\n  mask number of samples: 2000000\n")
+    p = host.ParameterFile(pf)
+    s = p.photon_source_spectrum()
+    p.close()
+    r = ref.masked_spectrum(pf)
+    assert s["kind"] == 3 and s["freq"].size == 500
+    assert np.array_equal(s["freq"], r["freq"]) and np.array_equal(s["cdf"], r["cdf"])
+    assert s["total_flux"] == r["total_flux"] and 0. < s["total_flux"] < 1e12
+    assert s["cdf"][-1] == 1. and (np.diff(s["cdf"]) >= 0).all()
