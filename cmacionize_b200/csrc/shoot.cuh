@@ -141,14 +141,13 @@ CMIB_HD CellOpacity load_cell(const CellOpacity *cells, int64_t cell) {
 #endif
 }
 
-/* packet `i` of this call (global id P.packet_offset + i) */
-template <int MODE, class Adder>
-CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, ShootCounters &cnt) {
+/* the life of one packet drawing from `rng`: the kernels pass the packet's own Philox stream, the CPU-tier
+ * test passes the reference's RANLUX stream shared by all packets of a thread, as IonizationPhotonShootJob does */
+template <int MODE, class Adder, class Rng>
+CMIB_HD void shoot_packet_from(const ShootParams &P, Rng &rng, const Adder &add, ShootCounters &cnt) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   const GridGeom &g = P.geom;
   const SourceModel &m = P.src;
-  PacketRng rng;
-  rng_init(rng, P.seed, P.iteration, P.packet_offset + i);
   MarchState s;
   double sigma[NSIG];
   double sigma_He_corr;
@@ -215,6 +214,14 @@ CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, Sh
   cnt.w_tot += weight;
 #pragma unroll
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? weight : 0.;
+}
+
+/* packet `i` of this call (global id P.packet_offset + i) */
+template <int MODE, class Adder>
+CMIB_HD void shoot_packet(const ShootParams &P, uint64_t i, const Adder &add, ShootCounters &cnt) {
+  PacketRng rng;
+  rng_init(rng, P.seed, P.iteration, P.packet_offset + i);
+  shoot_packet_from<MODE>(P, rng, add, cnt);
 }
 
 } // namespace cmib

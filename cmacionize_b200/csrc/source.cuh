@@ -126,7 +126,11 @@ CMIB_HD uint32_t locate_guided(double x, const double *xarr, uint32_t length, co
   return jl;
 }
 
-CMIB_HD void random_direction(PacketRng &rng, double &dx, double &dy, double &dz) {
+/* The samplers below are templates over the generator: the device passes the packet's Philox stream
+ * (PacketRng, rng.cuh), the CPU-tier tests pass the reference's RANLUX stream (host/RandomGenerator.hpp)
+ * and must then reproduce the reference bit for bit.  A generator is anything with rng_uniform(g). */
+template <class Rng>
+CMIB_HD void random_direction(Rng &rng, double &dx, double &dy, double &dz) {
   const double cost = 2. * rng_uniform(rng) - 1.;
   const double s2 = 1. - cost * cost;
   const double sint = sqrt(s2 > 0. ? s2 : 0.);
@@ -268,7 +272,8 @@ CMIB_HD double planck_frequency_at(const double *tab, double x, const uint16_t *
                         (lognu[ix + 1] - lognu[ix]) + lognu[ix];
   return fpow(10., lf) * 3.288465385e15; /* device: exp(lf ln 10), cmib_common.cuh */
 }
-CMIB_HD double planck_frequency(const double *tab, PacketRng &rng, const uint16_t *guide = nullptr) {
+template <class Rng>
+CMIB_HD double planck_frequency(const double *tab, Rng &rng, const uint16_t *guide = nullptr) {
   return planck_frequency_at(tab, rng_uniform(rng), guide);
 }
 
@@ -283,7 +288,8 @@ CMIB_HD double tabulated_frequency(const double *freq, const double *cdf, uint32
   const uint32_t inu = locate(x, cdf, n);
   return freq[inu] + (freq[inu + 1] - freq[inu]) * (x - cdf[inu]) / (cdf[inu + 1] - cdf[inu]);
 }
-CMIB_HD double spectrum_frequency(const SpectrumModel &sp, PacketRng &rng) {
+template <class Rng>
+CMIB_HD double spectrum_frequency(const SpectrumModel &sp, Rng &rng) {
   if (sp.kind == SPECTRUM_PLANCK) return planck_frequency(sp.planck, rng, sp.planck_guide);
   if (sp.kind == SPECTRUM_UNIFORM) return uniform_frequency(rng_uniform(rng));
   if (sp.kind == SPECTRUM_TABULATED) return tabulated_frequency(sp.freq, sp.cdf, (uint32_t)sp.n, rng_uniform(rng));
@@ -306,8 +312,9 @@ CMIB_HD void locate2(double x, const double *a, const double *b, uint32_t length
   jb = lb;
 }
 
+template <class Rng>
 CMIB_HD double lyc_frequency(const double *freq, const double *temp, const double *cdf, double T,
-                             PacketRng &rng, const uint16_t *guide = nullptr) {
+                             Rng &rng, const uint16_t *guide = nullptr) {
   const uint32_t iT = locate(T, temp, LYC_NUMTEMP);
   const double x = rng_uniform(rng);
   uint32_t inu1, inu2;
@@ -322,7 +329,8 @@ CMIB_HD double lyc_frequency(const double *freq, const double *temp, const doubl
   return freq[inu1] + (T - temp[iT]) * (freq[inu2] - freq[inu1]) / (temp[iT + 1] - temp[iT]);
 }
 
-CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng &rng,
+template <class Rng>
+CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, Rng &rng,
                                const uint16_t *guide = nullptr) {
   const double x = rng_uniform(rng);
   const uint32_t inu = locate_guided(x, cdf, SPECTRUM_NUMFREQ, guide);
@@ -335,7 +343,8 @@ CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, PacketRng 
  * spectrum) and the continuous source (position + direction on the box surface, frequency from its
  * own spectrum).  isrc = index of the discrete source, -1 for a packet of the continuous source.
  */
-CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, PacketRng &rng, double &px, double &py,
+template <class Rng>
+CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, Rng &rng, double &px, double &py,
                           double &pz, double &dx, double &dy, double &dz, double &nu, int &isrc) {
   double x = rng_uniform(rng);
   if (x >= m.continuous_probability) {
@@ -416,8 +425,9 @@ CMIB_HD void packet_cross_sections(const SourceModel &m, double nu, double *sigm
  * cell, p = its 5 cumulative probabilities.  Returns the new frequency (0 =
  * packet absorbed) and the new packet type.
  */
+template <class Rng>
 CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigma_He, double xH,
-                               double xHe, double T, const double *p, PacketRng &rng, int &type) {
+                               double xHe, double T, const double *p, Rng &rng, int &type) {
   double nu = 0.;
   const double nH0anuH0 = xH * sigma_H;
   const double nHe0anuHe0 = xHe * m.A_He * sigma_He;

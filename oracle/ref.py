@@ -315,6 +315,25 @@ def masked_spectrum(paramfile, role="PhotonSourceSpectrum"):
     return dict(freq=freq[:n].copy(), cdf=cdf[:n].copy(), total_flux=flux.value)
 
 
+def random_photons(paramfile, n, seed=42):
+    """n x PhotonSource::get_random_photon of the parameter file's source with RandomGenerator(seed)"""
+    pos, d, nu = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+    sigma, she, w = np.empty((n, 14)), np.empty(n), np.empty(n)
+    lib().cmi_ref_random_photons(str(paramfile).encode(), C.c_int(seed), C.c_int64(n), _p(pos), _p(d), _p(nu), _p(sigma),
+                                 _p(she), _p(w))
+    return dict(pos=pos, dir=d, nu=nu, sigma=sigma, sigma_He_corr=she, weight=w)
+
+
+def reemit_sequence(paramfile, xH, xHe, T, nu_in, seed=42):
+    """n x PhotonSource::reemit with RandomGenerator(seed) -> (new frequency or 0, packet type, new direction)"""
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (xH, xHe, T, nu_in)]
+    n = a[0].size
+    nu, typ, d = np.empty(n), np.empty(n, dtype=np.int32), np.empty((n, 3))
+    lib().cmi_ref_reemit_sequence(str(paramfile).encode(), C.c_int(seed), C.c_int64(n), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]),
+                                  _p(nu), _p(typ), _p(d))
+    return nu, typ, d
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

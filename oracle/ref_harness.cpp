@@ -39,6 +39,8 @@
 #include "Abundances.hpp"
 #include "AbundanceModelFactory.hpp"
 #include "CrossSectionsFactory.hpp"
+#include "ContinuousPhotonSourceFactory.hpp"
+#include "SimulationBox.hpp"
 #include "CartesianDensityGrid.hpp"
 #include "ChargeTransferRates.hpp"
 #include "DistantStarContinuousPhotonSource.hpp"
@@ -709,6 +711,80 @@ int cmi_ref_masked_spectrum(const char *paramfile, const char *role, double *fre
   }
   delete sp;
   return n <= capacity ? n : -n;
+}
+
+/* A PhotonSource wired from a parameter file exactly as IonizationSimulation does it
+ * (src/IonizationSimulation.cpp:150-181). */
+namespace {
+struct RefPhotonSource {
+  ParameterFile params;
+  SimulationBox box;
+  AbundanceModel *abundance_model;
+  Abundances abundances;
+  CrossSections *cross_sections;
+  PhotonSourceDistribution *distribution;
+  PhotonSourceSpectrum *spectrum;
+  ContinuousPhotonSource *continuous;
+  PhotonSourceSpectrum *continuous_spectrum;
+  PhotonSource *source;
+  explicit RefPhotonSource(const char *paramfile)
+      : params(paramfile), box(params), abundance_model(AbundanceModelFactory::generate(params, nullptr)),
+        abundances(abundance_model->get_abundances()), cross_sections(CrossSectionsFactory::generate(params, nullptr)),
+        distribution(PhotonSourceDistributionFactory::generate(params, nullptr)),
+        spectrum(PhotonSourceSpectrumFactory::generate("PhotonSourceSpectrum", params, nullptr)),
+        continuous(ContinuousPhotonSourceFactory::generate(box.get_box(), params, nullptr)),
+        continuous_spectrum(PhotonSourceSpectrumFactory::generate("ContinuousPhotonSourceSpectrum", params, nullptr)),
+        source(new PhotonSource(distribution, spectrum, continuous, continuous_spectrum, abundances, *cross_sections,
+                                params, nullptr)) {}
+  ~RefPhotonSource() {
+    delete source;
+    delete continuous_spectrum;
+    delete continuous;
+    delete spectrum;
+    delete distribution;
+    delete cross_sections;
+    delete abundance_model;
+  }
+};
+} // namespace
+
+/* n x PhotonSource::get_random_photon (src/PhotonSource.cpp:208-249) with RandomGenerator(seed) */
+void cmi_ref_random_photons(const char *paramfile, int seed, int64_t n, double *pos, double *dir, double *nu,
+                            double *sigma, double *she, double *weight) {
+  RefPhotonSource s(paramfile);
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    Photon ph = s.source->get_random_photon(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = ph.get_position()[k];
+      dir[3 * i + k] = ph.get_direction()[k];
+    }
+    nu[i] = ph.get_energy();
+    for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) sigma[i * NUMBER_OF_IONNAMES + ion] = ph.get_cross_section(ion);
+    she[i] = ph.get_cross_section_He_corr();
+    weight[i] = ph.get_weight();
+  }
+}
+
+/* n x PhotonSource::reemit (src/PhotonSource.cpp:272-308) with RandomGenerator(seed): packet i was absorbed at
+ * frequency nu_in[i] in a cell with (xH, xHe, T)[i] */
+void cmi_ref_reemit_sequence(const char *paramfile, int seed, int64_t n, const double *xH, const double *xHe,
+                             const double *T, const double *nu_in, double *nu_out, int32_t *type_out, double *dir) {
+  RefPhotonSource s(paramfile);
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    Photon ph(CoordinateVector<>(0.), CoordinateVector<>(1., 0., 0.), nu_in[i]);
+    s.source->set_cross_sections(ph, nu_in[i]);
+    IonizationVariables iv;
+    iv.set_temperature(T[i]);
+    iv.set_ionic_fraction(ION_H_n, xH[i]);
+    iv.set_ionic_fraction(ION_He_n, xHe[i]);
+    s.source->_reemission_handler->set_reemission_probabilities(iv);
+    const bool ok = s.source->reemit(ph, iv, rg);
+    nu_out[i] = ok ? ph.get_energy() : 0.;
+    type_out[i] = (int32_t)ph.get_type();
+    for (int k = 0; k < 3; ++k) dir[3 * i + k] = ok ? ph.get_direction()[k] : 0.;
+  }
 }
 
 /* FaucherGiguerePhotonSourceSpectrum(redshift) (src/FaucherGiguerePhotonSourceSpectrum.cpp): its

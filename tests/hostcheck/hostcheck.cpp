@@ -20,6 +20,14 @@
 #include "../../cmacionize_b200/csrc/spectrum_tables.hpp"
 #include "../../cmacionize_b200/csrc/state.cuh"
 
+/* the reference's RANLUX stream as a generator for the samplers of source.cuh (rng_uniform is found
+ * by argument-dependent lookup when the templates are instantiated) */
+struct RanluxRng {
+  cmi::RandomGenerator g;
+  explicit RanluxRng(int seed) : g(seed) {}
+};
+inline double rng_uniform(RanluxRng &r) { return r.g.get_uniform_random_double(); }
+
 using namespace cmib;
 
 extern "C" {
@@ -190,6 +198,92 @@ void hc_distant_star_incoming(const double *anchor, const double *sides, const d
                           pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
 }
 
+/* PhotonSource::get_random_photon with the RANLUX stream: n_sources discrete sources with a Planck (T) or
+ * monochromatic (nu) spectrum, optionally an isotropic continuous source with its own Planck spectrum
+ * (continuous_luminosity > 0), Verner cross sections.  Outputs per packet: pos, dir, nu, sigma[14],
+ * A_He sigma_He, weight. */
+void hc_random_photons(const double *anchor, const double *sides, int n_sources, const double *src_pos,
+                       const double *src_weights, double discrete_luminosity, int spectrum_kind, double spectrum_param,
+                       double continuous_luminosity, double continuous_temperature, double A_He, int seed, int64_t n,
+                       double *pos, double *dir, double *nu, double *sigma, double *she, double *weight) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) { g.anchor[d] = anchor[d]; g.sides[d] = sides[d]; }
+  SourceModel m;
+  memset(&m, 0, sizeof(m));
+  m.n_sources = n_sources;
+  std::vector<double> cum(n_sources > 0 ? n_sources : 1, 1.);
+  for (int i = 0; i < n_sources; ++i) cum[i] = (i ? cum[i - 1] : 0.) + src_weights[i];
+  if (n_sources > 0) cum[n_sources - 1] = 1.;
+  m.src_pos = src_pos;
+  m.src_cum = cum.data();
+  std::vector<double> planck, cplanck;
+  m.spectrum.kind = spectrum_kind;
+  if (spectrum_kind == SPECTRUM_PLANCK) {
+    host::build_planck_table(spectrum_param, planck);
+    m.spectrum.planck = planck.data();
+  } else {
+    m.spectrum.mono_frequency = spectrum_param;
+  }
+  /* PhotonSource.cpp:110-131 */
+  if (continuous_luminosity > 0.) {
+    m.continuous_kind = CONTINUOUS_ISOTROPIC;
+    host::build_planck_table(continuous_temperature, cplanck);
+    m.cont_spectrum.kind = SPECTRUM_PLANCK;
+    m.cont_spectrum.planck = cplanck.data();
+    if (discrete_luminosity > 0.) {
+      m.continuous_probability = 0.5;
+      m.discrete_weight = 1.;
+      m.continuous_weight = (1. - m.continuous_probability) * continuous_luminosity / m.continuous_probability / discrete_luminosity;
+    } else {
+      m.continuous_probability = 1.;
+      m.discrete_weight = 0.;
+      m.continuous_weight = 1.;
+    }
+  } else {
+    m.discrete_weight = 1.;
+  }
+  m.xs_kind = XS_VERNER;
+  m.A_He = A_He;
+  RanluxRng rng(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    int isrc;
+    emit_primary(m, g, rng, pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2], nu[i], isrc);
+    packet_cross_sections<NUM_IONS>(m, nu[i], sigma + i * NUM_IONS, she[i]);
+    weight[i] = (isrc >= 0) ? m.discrete_weight : m.continuous_weight;
+  }
+}
+
+/* PhotonSource::reemit with the Physical handler and the RANLUX stream, one call per entry: the packet was
+ * absorbed at frequency nu_in[i] in a cell with (xH, xHe, T)[i].  Outputs: new frequency (0 = absorbed for
+ * good), packet type, new direction (zeros when absorbed). */
+void hc_reemit_sequence(double A_He, int seed, int64_t n, const double *xH, const double *xHe, const double *T,
+                        const double *nu_in, double *nu_out, int32_t *type_out, double *dir) {
+  SourceModel m;
+  memset(&m, 0, sizeof(m));
+  m.xs_kind = XS_VERNER;
+  m.A_He = A_He;
+  m.reemission_kind = REEMISSION_PHYSICAL;
+  std::vector<double> hf, ht, hc, hef, het, hec, tf, tc;
+  host::build_lyc_table(0, [](double nu) { return verner_cross_section(ION_H_n, nu); }, hf, ht, hc);
+  host::build_lyc_table(1, [](double nu) { return verner_cross_section(ION_He_n, nu); }, hef, het, hec);
+  host::build_he2pc_table(tf, tc);
+  m.hlyc_freq = hf.data(); m.hlyc_temp = ht.data(); m.hlyc_cdf = hc.data();
+  m.helyc_freq = hef.data(); m.helyc_temp = het.data(); m.helyc_cdf = hec.data();
+  m.he2pc_freq = tf.data(); m.he2pc_cdf = tc.data();
+  RanluxRng rng(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    double sigma[NUM_IONS], she, p[NUM_REEMIT];
+    packet_cross_sections<NUM_IONS>(m, nu_in[i], sigma, she);
+    reemission_probabilities(T[i], p);
+    int type = PACKET_ABSORBED;
+    nu_out[i] = physical_reemit(m, sigma[ION_H_n], sigma[ION_He_n], xH[i], xHe[i], T[i], p, rng, type);
+    type_out[i] = type;
+    dir[3 * i] = dir[3 * i + 1] = dir[3 * i + 2] = 0.;
+    if (nu_out[i] != 0.) random_direction(rng, dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+  }
+}
+
 void hc_planar_incoming(int axis, double intercept, const double *anchor, const double *sides, int64_t n,
                         const double *uniforms, double *pos, double *dir) {
   for (int64_t i = 0; i < n; ++i)
@@ -284,7 +378,7 @@ void hc_march_packets(const double *anchor, const double *sides, const int32_t *
 
 /* the product's shoot_packet (shoot.cuh) executed on the host with plain adds: logic check of
  * emission / walk / re-emission for the CPU tier.  cells [nc][4] = n, xH, xHe, T.
- * iparams: n_sources, spectrum_kind, xs_kind, reemission_kind, acc_mode(0 full,1 H-only)
+ * iparams: n_sources, spectrum_kind, xs_kind, reemission_kind, acc_mode(0 full,1 H-only), ranlux(0/1)
  * dparams: spectrum param, A_He, fixed reemission probability, fixed reemission frequency
  * acc: ACC_COUNTERS + nc*NACC doubles, accumulated into */
 struct HostAdder {
@@ -372,7 +466,12 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   P.n_packets = n_packets;
   ShootCounters cnt;
   const HostAdder add;
-  if (iparams[4] == ACC_HONLY) {
+  if (iparams[5] != 0) {
+    /* iparams[5]: all packets draw from ONE RANLUX stream seeded with `seed`, in order — what a
+     * single-threaded IonizationPhotonShootJob does (IonizationPhotonShootJob.hpp:117-146) */
+    RanluxRng rng((int)seed);
+    for (uint64_t i = 0; i < n_packets; ++i) shoot_packet_from<ACC_FULL>(P, rng, add, cnt);
+  } else if (iparams[4] == ACC_HONLY) {
     for (uint64_t i = 0; i < n_packets; ++i) shoot_packet<ACC_HONLY>(P, i, add, cnt);
   } else {
     for (uint64_t i = 0; i < n_packets; ++i) shoot_packet<ACC_FULL>(P, i, add, cnt);

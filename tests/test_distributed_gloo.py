@@ -33,7 +33,7 @@ def _shoot(lib_path, lo, cnt):
     acc = np.zeros(16 + ncells * 2)
     anchor = np.array([-5 * PC] * 3); sides = np.array([10 * PC] * 3)
     ncell = np.array([NC] * 3, np.int32); per = np.zeros(3, np.int32)
-    ip = np.array([2, 0, 0, 2, 1], np.int32)          # 2 sources, mono, FixedValue, FixedValue re-emission, H-only
+    ip = np.array([2, 0, 0, 2, 1, 0], np.int32)       # 2 sources, mono, FixedValue, FixedValue re-emission, H-only, Philox
     dp = np.array([(13.6 * 1.6021766208e-19) * (1 / 6.626070040e-34), 0., 0.364, 3.4e15])
     sp = np.array([0., 0., 0., PC, -PC, 0.5 * PC]); sw = np.array([0.3, 0.7])
     xs = np.zeros(14); xs[0] = 6.3e-22

@@ -259,3 +259,129 @@ def test_distant_star_continuous_source_bitexact(hostcheck, ref):
         assert area == sum(sides[(k + 1) % 3] * sides[(k + 2) % 3] for k in range(3) if exposed[k])
         on_face = (np.isclose(pos2, anchor, rtol=0, atol=1e-9 * sides) | np.isclose(pos2, anchor + sides, rtol=0, atol=1e-9 * sides))
         assert (on_face & exposed).any(axis=1).all()
+
+
+def _source_paramfile(tmp_path, continuous):
+    yml = tmp_path / "sources.yml"
+    yml.write_text("number of sources: 3\nsource[0]:\n  position: [0. pc, 0. pc, 0. pc]\n  luminosity: 2.e49 s^-1\n"
+                   "source[1]:\n  position: [1. pc, -2. pc, 0.5 pc]\n  luminosity: 1.e49 s^-1\n"
+                   "source[2]:\n  position: [-3. pc, 3. pc, -1. pc]\n  luminosity: 1.e49 s^-1\n")
+    text = ("SimulationBox:\n  anchor: [-5. pc, -4. pc, -3. pc]\n  sides: [10. pc, 8. pc, 6. pc]\n  periodicity: [false, false, false]\n"
+            f"PhotonSourceDistribution:\n  type: AsciiFile\n  filename: {yml}\n"
+            "PhotonSourceSpectrum:\n  type: Planck\n  temperature: 40000. K\n"
+            "AbundanceModel:\n  type: FixedValue\n  He: 0.1\n"
+            "CrossSections:\n  type: Verner\nDiffuseReemissionHandler:\n  type: Physical\n")
+    if continuous:
+        text += ("ContinuousPhotonSource:\n  type: Isotropic\nContinuousPhotonSourceSpectrum:\n  type: Planck\n"
+                 "  temperature: 25000. K\n  ionizing flux: 1.e14 m^-2 s^-1\n")
+    pf = tmp_path / f"source_{int(continuous)}.param"
+    pf.write_text(text)
+    return pf
+
+
+@pytest.mark.parametrize("continuous", [False, True])
+def test_emission_with_the_reference_stream_is_bitexact(hostcheck, ref, tmp_path, continuous):
+    """PhotonSource::get_random_photon (PhotonSource.cpp:208-249) with the reference's own random stream:
+    the device's emission code (emit_primary + packet_cross_sections, source.cuh), compiled for the host and
+    fed by the RANLUX generator, returns the reference's packets — source pick, direction, Planck frequency,
+    14 Verner cross sections, weight — bit for bit; with an isotropic continuous source mixed in (half of the
+    packets, other spectrum, other weight, five more deviates) as well.  The production path replaces the
+    stream by per-packet Philox streams; this pins everything else."""
+    pf = _source_paramfile(tmp_path, continuous)
+    n = 20000
+    r = ref.random_photons(pf, n, seed=31)
+    PC = 3.086e16
+    anchor, sides = np.array([-5 * PC, -4 * PC, -3 * PC]), np.array([10 * PC, 8 * PC, 6 * PC])
+    src = np.array([[0., 0., 0.], [1 * PC, -2 * PC, 0.5 * PC], [-3 * PC, 3 * PC, -1 * PC]])
+    ref_src, ref_w, ref_L = ref.photon_source_distribution(pf)
+    assert np.array_equal(ref_src, src)
+    area = 2 * (sides[0] * sides[1] + sides[0] * sides[2] + sides[1] * sides[2])
+    Lc = area * 1e14 if continuous else 0.
+    pos, d, nu = np.empty((n, 3)), np.empty((n, 3)), np.empty(n)
+    sig, she, w = np.empty((n, 14)), np.empty(n), np.empty(n)
+    hostcheck.hc_random_photons(p(anchor), p(sides), C.c_int(3), p(np.ascontiguousarray(ref_src)), p(ref_w), C.c_double(ref_L),
+                                C.c_int(1), C.c_double(40000.), C.c_double(Lc), C.c_double(25000.), C.c_double(0.1),
+                                C.c_int(31), C.c_int64(n), p(pos), p(d), p(nu), p(sig), p(she), p(w))
+    assert np.array_equal(pos, r["pos"]) and np.array_equal(d, r["dir"])
+    assert np.array_equal(nu, r["nu"])
+    assert np.array_equal(sig, r["sigma"]) and np.array_equal(she, r["sigma_He_corr"])
+    assert np.array_equal(w, r["weight"])
+    if continuous:
+        assert 0.45 < (w != 1.).mean() < 0.55 and np.unique(w).size == 2
+    else:
+        assert (w == 1.).all() and abs(np.all(pos == 0., axis=1).mean() - 0.5) < 0.02
+
+
+def test_reemission_with_the_reference_stream_is_bitexact(hostcheck, ref, tmp_path):
+    """PhotonSource::reemit + PhysicalDiffuseReemissionHandler::reemit (PhotonSource.cpp:272-308,
+    PhysicalDiffuseReemissionHandler.cpp:219-370) with the reference's own random stream: absorbed by H or He,
+    channel, new frequency from the H-Lyc / He-Lyc / two-photon tables, new direction — 50000 absorptions
+    over a wide range of cells and frequencies, every outcome bit for bit (a different number of deviates per
+    branch: one wrong branch would derail the rest of the sequence)."""
+    pf = _source_paramfile(tmp_path, False)
+    rng = np.random.default_rng(8)
+    n = 50000
+    xH = np.exp(rng.uniform(np.log(1e-5), 0., n))
+    xHe = np.exp(rng.uniform(np.log(1e-5), 0., n))
+    T = np.exp(rng.uniform(np.log(3000.), np.log(25000.), n))
+    nu_in = 3.288465385e15 * np.exp(rng.uniform(np.log(1.001), np.log(3.9), n))
+    r_nu, r_type, r_dir = ref.reemit_sequence(pf, xH, xHe, T, nu_in, seed=77)
+    nu, typ, d = np.empty(n), np.empty(n, dtype=np.int32), np.empty((n, 3))
+    hostcheck.hc_reemit_sequence(C.c_double(0.1), C.c_int(77), C.c_int64(n), p(xH), p(xHe), p(T), p(nu_in), p(nu), p(typ), p(d))
+    assert np.array_equal(typ, r_type)
+    assert np.array_equal(nu, r_nu) and np.array_equal(d, r_dir)
+    assert set(np.unique(typ)) == {1, 2, 3} and 0.2 < (nu > 0).mean() < 0.8      # H-diffuse, He-diffuse, absorbed
+
+
+def test_whole_shoot_with_the_reference_stream_is_bitexact(hostcheck, ref, tmp_path):
+    """One complete shoot of the reference (IonizationSimulation iteration 0, one thread:
+    IonizationPhotonShootJob::execute, IonizationPhotonShootJob.hpp:117-146) against the product's
+    shoot_packet logic (shoot.cuh) compiled for the host and fed by the same RANLUX stream: emission,
+    optical depth, voxel walk, accumulation, Physical re-emission chain of 20000 packets on a 12^3 grid
+    with Planck + Verner + He — the 14 mean-intensity accumulators of every cell, the total weight and the
+    packet-type counters come out bit for bit.  With this, the only parts of the production path that are
+    not bit-identical to the reference are the random stream (per-packet Philox, by design), the order of the
+    atomic adds and CUDA's libm."""
+    PC = 3.086e16
+    nc = 12
+    pf = tmp_path / "shoot.param"
+    pf.write_text(
+        "SimulationBox:\n  anchor: [-3. pc, -3. pc, -3. pc]\n  sides: [6. pc, 6. pc, 6. pc]\n  periodicity: [false, false, false]\n"
+        f"DensityGrid:\n  type: Cartesian\n  number of cells: [{nc}, {nc}, {nc}]\n"
+        "DensityFunction:\n  type: Homogeneous\n  density: 100. cm^-3\n  temperature: 8000. K\n  neutral fraction H: 2.e-3\n"
+        "PhotonSourceDistribution:\n  type: SingleStar\n  position: [0.2 pc, -0.1 pc, 0.3 pc]\n  luminosity: 1.e49 s^-1\n"
+        "PhotonSourceSpectrum:\n  type: Planck\n  temperature: 40000. K\n"
+        "AbundanceModel:\n  type: FixedValue\n  He: 0.1\n  C: 2.2e-4\n  N: 4.e-5\n  O: 3.3e-4\n  Ne: 5.e-5\n  S: 9.e-6\n"
+        "CrossSections:\n  type: Verner\nRecombinationRates:\n  type: Verner\nDiffuseReemissionHandler:\n  type: Physical\n"
+        "TemperatureCalculator:\n  do temperature calculation: false\n"
+        f"IonizationSimulation:\n  number of photons: 20000\n  number of iterations: 1\n  random seed: 123\n  output folder: {tmp_path}\n")
+    sim = ref.Simulation(pf, num_threads=1)
+    f0 = sim.fields()
+    # a state with real opacity in H and He, the same on both sides
+    rng = np.random.default_rng(4)
+    x = f0[2:16].copy()
+    x[0] = np.exp(rng.uniform(np.log(1e-5), np.log(2e-3), nc ** 3))
+    x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-2), nc ** 3))
+    T = rng.uniform(6000., 12000., nc ** 3)
+    sim.set_state(f0[0], T, x)
+    npk = 20000
+    out = sim.iteration(0, npk)
+    f1 = sim.fields()
+    sim.close()
+    cells = np.ascontiguousarray(np.stack([f0[0], x[0], x[1], T], 1))
+    anchor, sides = np.array([-3 * PC] * 3), np.array([6 * PC] * 3)
+    ncell, per = np.array([nc] * 3, np.int32), np.zeros(3, np.int32)
+    ip = np.array([1, 1, 1, 1, 0, 1], np.int32)      # 1 source, Planck, Verner, Physical, full layout, RANLUX stream
+    dp = np.array([40000., 0.1, 0., 0.])
+    sp, sw = np.array([[0.2 * PC, -0.1 * PC, 0.3 * PC]]), np.array([1.])
+    acc = np.zeros(16 + 16 * nc ** 3)
+    hostcheck.hc_shoot(p(anchor), p(sides), p(ncell), p(per), p(cells), p(ip), p(dp), p(sp), p(sw), None, C.c_uint64(npk),
+                       C.c_uint64(0), C.c_uint64(123), C.c_uint32(0), p(acc))
+    assert acc[0] == out["totweight"] == npk
+    assert np.array_equal(acc[1:5], out["typecount"])
+    assert acc[6] > 1.2 * npk                         # re-emissions happened
+    slot = [0, 4, 8, 15, 3, 9, 13, 2, 11, 6, 12, 7, 10, 14]   # acc_slot() of the 14 ions (shoot.cuh)
+    rec = acc[16:].reshape(nc ** 3, 16)
+    for ion in range(14):
+        assert np.array_equal(rec[:, slot[ion]], f1[16 + ion]), ion
+    assert (f1[16] > 0).mean() > 0.9 and out["typecount"][0] + out["typecount"][1] + out["typecount"][2] > 0.05 * npk   # some escape too
