@@ -343,6 +343,31 @@ CMIB_HD double he2pc_frequency(const double *freq, const double *cdf, Rng &rng,
  * spectrum) and the continuous source (position + direction on the box surface, frequency from its
  * own spectrum).  isrc = index of the discrete source, -1 for a packet of the continuous source.
  */
+/* the continuous-source branch of get_random_photon, kept out of line on the device: it is rarely taken
+ * and its code (a rejection loop, three geometries) must not set the register budget of prepare_kernel */
+#if defined(__CUDACC__)
+#define CMIB_HD_OUT_OF_LINE __host__ __device__ __noinline__
+#else
+#define CMIB_HD_OUT_OF_LINE inline
+#endif
+template <class Rng>
+CMIB_HD_OUT_OF_LINE void emit_continuous(const SourceModel &m, const GridGeom &g, Rng &rng, double &px, double &py, double &pz,
+                                         double &dx, double &dy, double &dz, double &nu) {
+    double u[5];
+    if (m.continuous_kind == CONTINUOUS_DISTANT_STAR) {
+      distant_star_incoming(g, m.star_position, m.star_exposed, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
+    } else if (m.continuous_kind == CONTINUOUS_PLANAR) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = rng_uniform(rng);
+      planar_incoming(m.planar_axis, m.planar_intercept, m.planar_anchor, m.planar_sides, u, px, py, pz, dx, dy, dz);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
+      isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
+    }
+  nu = spectrum_frequency(m.cont_spectrum, rng);
+}
+
 template <class Rng>
 CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, Rng &rng, double &px, double &py,
                           double &pz, double &dx, double &dy, double &dz, double &nu, int &isrc) {
@@ -357,20 +382,8 @@ CMIB_HD void emit_primary(const SourceModel &m, const GridGeom &g, Rng &rng, dou
     random_direction(rng, dx, dy, dz);
     nu = spectrum_frequency(m.spectrum, rng);
   } else {
-    double u[5];
-    if (m.continuous_kind == CONTINUOUS_DISTANT_STAR) {
-      distant_star_incoming(g, m.star_position, m.star_exposed, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
-    } else if (m.continuous_kind == CONTINUOUS_PLANAR) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = rng_uniform(rng);
-      planar_incoming(m.planar_axis, m.planar_intercept, m.planar_anchor, m.planar_sides, u, px, py, pz, dx, dy, dz);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 5; ++k) u[k] = rng_uniform(rng);
-      isotropic_incoming(g, u, px, py, pz, dx, dy, dz);
-    }
+    emit_continuous(m, g, rng, px, py, pz, dx, dy, dz, nu);
     isrc = -1;
-    nu = spectrum_frequency(m.cont_spectrum, rng);
   }
 }
 

@@ -356,7 +356,9 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
  * (PhotonSource.hpp:141-148), evaluate the 14 cross sections (set_cross_sections, :189-199) and the
  * optical depth tau = -ln u (IonizationPhotonShootJob.hpp:135). */
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3) /* 3 CTAs per SM: without the bound the rarely taken continuous-source
+                                           * branches of emit_primary push it to 104 registers (2 CTAs, +2 ms per
+                                           * lexingtonHII20 step) */
 prepare_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   const ShootParams &P = W.sp;
