@@ -306,10 +306,9 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
       cont = meta_continuous(meta);
       if (m.reemission_kind == REEMISSION_PHYSICAL) {
         const CellOpacity c = load_cell(P.cells, cell);
-        double p[NUM_REEMIT];
-#pragma unroll
-        for (int k = 0; k < NUM_REEMIT; ++k) p[k] = P.reemit_prob[cell * NUM_REEMIT + k];
-        nu = physical_reemit(m, sigH, sigHe, c.xH, c.xHe, c.T, p, rng, type);
+        /* the five cumulative probabilities are read where the decision needs them: an absorption by
+         * hydrogen (most of them) looks at the first one only */
+        nu = physical_reemit(m, sigH, sigHe, c.xH, c.xHe, c.T, P.reemit_prob + cell * NUM_REEMIT, rng, type);
       } else { /* REEMISSION_FIXED (REEMISSION_NONE never queues) */
         const double u = rng_uniform(rng);
         if (u < m.fixed_reemission_probability) {
