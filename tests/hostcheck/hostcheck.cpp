@@ -483,4 +483,108 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   acc[8] += cnt.tau_sum;
 }
 
+/*
+ * A whole simulation on the reference's random stream: the loop body of IonizationSimulation::run
+ * (IonizationSimulation.cpp:359-643) for n_iter iterations — reset, re-emission probabilities, shoot of
+ * n_packets packets from ONE RANLUX generator that lives across the iterations (as the single job of a
+ * single-threaded reference run does), state update of every cell (ionization-only while loop <= 3, the
+ * temperature solve afterwards) — composed from the product's shared physics headers exactly as the
+ * kernels compose them (shoot_packet_from; update_state_kernel's per-cell body).  One discrete source,
+ * Planck spectrum, Verner cross sections and rates, Physical re-emission.  cells: [ncell][4] = n, xH, xHe, T
+ * (in/out); xmetal: [ncell][12] (in/out).
+ */
+void hc_simulation(const double *anchor, const double *sides, const int32_t *ncell, const double *src_pos,
+                   double luminosity, double planck_temperature, const double *abund, const double *tparams,
+                   int do_temperature, uint32_t n_iter, uint64_t n_packets, int seed, double *cells, double *xmetal) {
+  ShootParams P;
+  GridGeom &g = P.geom;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) {
+    g.anchor[d] = anchor[d];
+    g.sides[d] = sides[d];
+    g.ncell[d] = ncell[d];
+    g.cellside[d] = sides[d] / ncell[d];
+    g.inv_cellside[d] = 1. / g.cellside[d];
+  }
+  g.cell_volume = g.cellside[0] * g.cellside[1] * g.cellside[2];
+  g.ncells = (int64_t)ncell[0] * ncell[1] * ncell[2];
+  const int64_t nc = g.ncells;
+  std::vector<CellOpacity> cell_rec(nc);
+  SourceModel &m = P.src;
+  memset(&m, 0, sizeof(m));
+  m.n_sources = 1;
+  const double cum = 1.;
+  m.src_pos = src_pos;
+  m.src_cum = &cum;
+  m.discrete_weight = 1.;
+  std::vector<double> planck, hf, ht, hc, hef, het, hec, tf, tc;
+  host::build_planck_table(planck_temperature, planck);
+  m.spectrum.kind = SPECTRUM_PLANCK;
+  m.spectrum.planck = planck.data();
+  m.xs_kind = XS_VERNER;
+  m.A_He = abund[EL_He];
+  m.reemission_kind = REEMISSION_PHYSICAL;
+  host::build_lyc_table(0, [](double nu) { return verner_cross_section(ION_H_n, nu); }, hf, ht, hc);
+  host::build_lyc_table(1, [](double nu) { return verner_cross_section(ION_He_n, nu); }, hef, het, hec);
+  host::build_he2pc_table(tf, tc);
+  m.hlyc_freq = hf.data(); m.hlyc_temp = ht.data(); m.hlyc_cdf = hc.data();
+  m.helyc_freq = hef.data(); m.helyc_temp = het.data(); m.helyc_cdf = hec.data();
+  m.he2pc_freq = tf.data(); m.he2pc_cdf = tc.data();
+  std::vector<double> prob(nc * NUM_REEMIT), acc(ACC_COUNTERS + nc * NUM_ACC);
+  P.cells = cell_rec.data();
+  P.cells_h = nullptr;
+  P.reemit_prob = prob.data();
+  P.acc = acc.data();
+  P.honly_cell_stride = 2; P.honly_term_stride = 1; P.honly_offset = 0;
+  P.hot_acc = nullptr; P.src_cell = nullptr; P.hot_replicas = 0;
+  P.nu_H = (13.6 * ELECTRONVOLT) * (1. / PLANCK);
+  P.nu_He = (24.6 * ELECTRONVOLT) * (1. / PLANCK);
+  P.seed = 0; P.iteration = 0; P.packet_offset = 0; P.n_packets = n_packets;
+  const RecombinationModel rr = make_rr(RR_VERNER, nullptr);
+  TemperatureParams tp;
+  tp.do_temperature = do_temperature;
+  tp.min_iterations = 3;
+  tp.pahfac = tparams[0]; tp.crfac = tparams[1]; tp.crlim = tparams[2]; tp.crscale = tparams[3];
+  tp.min_ionized_T = tparams[4]; tp.epsilon = tparams[5]; tp.max_iterations = (uint32_t)tparams[6];
+  RanluxRng rng(seed);
+  const HostAdder add;
+  for (uint32_t loop = 0; loop < n_iter; ++loop) {
+    for (int64_t i = 0; i < nc; ++i) {
+      cell_rec[i].n = cells[4 * i]; cell_rec[i].xH = cells[4 * i + 1];
+      cell_rec[i].xHe = cells[4 * i + 2]; cell_rec[i].T = cells[4 * i + 3];
+      reemission_probabilities(cell_rec[i].T, &prob[i * NUM_REEMIT]);
+    }
+    std::fill(acc.begin(), acc.end(), 0.);
+    ShootCounters cnt;
+    for (uint64_t k = 0; k < n_packets; ++k) shoot_packet_from<ACC_FULL>(P, rng, add, cnt);
+    /* update_state_kernel, cell by cell (kernels.cuh) */
+    const double jfac0 = luminosity / cnt.w_tot, hfac0 = jfac0 * PLANCK;
+    const double jfac = jfac0 / g.cell_volume, hfac = hfac0 / g.cell_volume;
+    const bool solve_T = do_temperature && loop > tp.min_iterations;
+    for (int64_t i = 0; i < nc; ++i) {
+      const double *a = acc.data() + ACC_COUNTERS + i * NUM_ACC;
+      double J[NUM_IONS], heat[NUM_HEAT];
+      for (int k = 0; k < NUM_IONS; ++k) J[k] = a[acc_slot(k)];
+      heat[0] = a[acc_slot(NUM_IONS)];
+      heat[1] = a[acc_slot(NUM_IONS + 1)];
+      CellState out;
+      if (solve_T) {
+        double xprev[NUM_IONS];
+        xprev[0] = cells[4 * i + 1];
+        xprev[1] = cells[4 * i + 2];
+        for (int k = 0; k < 12; ++k) xprev[2 + k] = xmetal[i * 12 + k];
+        const int32_t iz = (int32_t)(i % g.ncell[2]);
+        const double midz = (g.anchor[2] + g.cellside[2] * iz) + 0.5 * g.cellside[2];
+        cell_temperature(jfac, hfac, J, heat, cells[4 * i], cells[4 * i + 3], -1., midz, abund, rr, tp, xprev, out);
+      } else {
+        cell_ionization_state(jfac, hfac, J, heat, cells[4 * i], cells[4 * i + 3], abund, rr, out);
+      }
+      cells[4 * i + 1] = out.x[ION_H_n];
+      cells[4 * i + 2] = out.x[ION_He_n];
+      cells[4 * i + 3] = out.T;
+      for (int k = 0; k < 12; ++k) xmetal[i * 12 + k] = out.x[2 + k];
+    }
+  }
+}
+
 } /* extern "C" */

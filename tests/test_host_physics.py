@@ -385,3 +385,43 @@ def test_whole_shoot_with_the_reference_stream_is_bitexact(hostcheck, ref, tmp_p
     for ion in range(14):
         assert np.array_equal(rec[:, slot[ion]], f1[16 + ion]), ion
     assert (f1[16] > 0).mean() > 0.9 and out["typecount"][0] + out["typecount"][1] + out["typecount"][2] > 0.05 * npk   # some escape too
+
+
+def test_whole_simulation_with_the_reference_stream_is_bitexact(hostcheck, ref, tmp_path):
+    """The reference's IonizationSimulation, one thread, 6 iterations of 20000 packets on a 10^3 Lexington-type
+    grid (Planck star, Verner cross sections and rates, He and metals, Physical diffuse field, the temperature
+    solve with line cooling from iteration 4 on) against the same loop composed from the product's physics
+    headers on the host, fed by the reference's own random stream: the final temperature and all 14 ionic
+    fractions of every cell are the reference's, bit for bit.  (State update arithmetic uses pow() in the host
+    build, as the reference does; the device uses exp(a ln x), see test_gpu_physics.py for its bounds.)"""
+    PC = 3.086e16
+    nc = 10
+    pf = tmp_path / "sim.param"
+    pf.write_text(
+        "SimulationBox:\n  anchor: [-3. pc, -3. pc, -3. pc]\n  sides: [6. pc, 6. pc, 6. pc]\n  periodicity: [false, false, false]\n"
+        f"DensityGrid:\n  type: Cartesian\n  number of cells: [{nc}, {nc}, {nc}]\n"
+        "DensityFunction:\n  type: Homogeneous\n  density: 100. cm^-3\n  temperature: 8000. K\n"
+        "PhotonSourceDistribution:\n  type: SingleStar\n  position: [0.1 pc, 0.2 pc, -0.1 pc]\n  luminosity: 1.e49 s^-1\n"
+        "PhotonSourceSpectrum:\n  type: Planck\n  temperature: 40000. K\n"
+        "AbundanceModel:\n  type: FixedValue\n  He: 0.1\n  C: 2.2e-4\n  N: 4.e-5\n  O: 3.3e-4\n  Ne: 5.e-5\n  S: 9.e-6\n"
+        "CrossSections:\n  type: Verner\nRecombinationRates:\n  type: Verner\nDiffuseReemissionHandler:\n  type: Physical\n"
+        "TemperatureCalculator:\n  do temperature calculation: true\n"
+        f"IonizationSimulation:\n  number of photons: 20000\n  number of iterations: 6\n  random seed: 321\n  output folder: {tmp_path}\n")
+    sim = ref.Simulation(pf, num_threads=1)
+    f0 = sim.fields()
+    for loop in range(6):
+        sim.iteration(loop, 20000)
+    f1 = sim.fields()
+    sim.close()
+    cells = np.ascontiguousarray(np.stack([f0[0], f0[2], f0[3], f0[1]], 1))
+    xmetal = np.ascontiguousarray(f0[4:16].T)
+    anchor, sides, ncell = np.array([-3 * PC] * 3), np.array([6 * PC] * 3), np.array([nc] * 3, np.int32)
+    src = np.array([0.1 * PC, 0.2 * PC, -0.1 * PC])
+    abund = np.array([0.1, 2.2e-4, 4e-5, 3.3e-4, 5e-5, 9e-6])
+    tpar = np.array([0., 0., 0.75, ref.convert(1.33333, "kpc", "m"), 4000., 1e-3, 100.])
+    hostcheck.hc_simulation(p(anchor), p(sides), p(ncell), p(src), C.c_double(1e49), C.c_double(40000.), p(abund), p(tpar),
+                            C.c_int(1), C.c_uint32(6), C.c_uint64(20000), C.c_int(321), p(cells), p(xmetal))
+    assert np.array_equal(cells[:, 3], f1[1])                  # temperature
+    assert np.array_equal(cells[:, 1], f1[2]) and np.array_equal(cells[:, 2], f1[3])   # x_H, x_He
+    assert np.array_equal(xmetal.T, f1[4:16])                  # the 12 metal fractions
+    assert (f1[1] > 4000.).mean() > 0.3 and np.unique(f1[1]).size > 100     # the temperature solve really ran
