@@ -417,6 +417,150 @@ private:
   std::vector<double> densities_;
 };
 
+/* ---- analytic density profiles (each a closed form per cell midpoint; operation order of the
+ * reference, so that the initial grid is the same doubles) ---- */
+
+/* isothermal gas in the potential of a cored dark-matter halo
+ * (CoredDMProfileDensityFunction.hpp:84-156) */
+class CoredDMProfileDensityFunction : public DensityFunction {
+public:
+  CoredDMProfileDensityFunction(double r0, double vinf, double rho0, double temperature, double neutral_fraction,
+                                double gamma = 1.)
+      : r0inv_(1. / r0), vratio_(gamma * vinf * vinf / sound_speed_squared(neutral_fraction, temperature)),
+        n0_(rho0 / mean_particle_mass(neutral_fraction)), temperature_(temperature / gamma),
+        neutral_fraction_(neutral_fraction) {}
+  explicit CoredDMProfileDensityFunction(ParameterFile &params)
+      : CoredDMProfileDensityFunction(
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:core radius", "300. pc"),
+            params.get_physical_value<QUANTITY_VELOCITY>("DensityFunction:maximum circular velocity", "21.1 km s^-1"),
+            params.get_physical_value<QUANTITY_DENSITY>("DensityFunction:central density", "9.48e-21 g cm^-3"),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "500. K"),
+            params.get_value<double>("DensityFunction:neutral fraction", 1.),
+            params.get_value<double>("DensityFunction:polytropic index", 1.)) {}
+  DensityValues operator()(const Vec3 &x) override {
+    const double r = std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const double ksi = r * r0inv_;
+    DensityValues v;
+    v.number_density = n0_ * std::exp(-vratio_ * (0.5 * std::log(1. + ksi * ksi) + std::atan(ksi) / ksi - 1.));
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = neutral_fraction_;
+    return v;
+  }
+
+private:
+  static double mean_particle_mass(double neutral_fraction) {
+    return 0.5 * constants::proton_mass * (1. + neutral_fraction);
+  }
+  static double sound_speed_squared(double neutral_fraction, double temperature) {
+    return constants::boltzmann * temperature / mean_particle_mass(neutral_fraction);
+  }
+  double r0inv_, vratio_, n0_, temperature_, neutral_fraction_;
+};
+
+/* power-law envelope around a point mass, scaled by its Bondi radius (DiscICDensityFunction.hpp:123-186);
+ * the rotation velocity of that profile belongs to the hydro and is not part of the grid here */
+class DiscICDensityFunction : public DensityFunction {
+public:
+  DiscICDensityFunction(double mass, double temperature, double rho_B, double gamma_rho)
+      : R_B_(0.5 * constants::newton_constant * mass * mean_particle_mass(temperature) /
+             (constants::boltzmann * temperature)),
+        n_B_(rho_B / mean_particle_mass(temperature)), gamma_rho_(gamma_rho), temperature_(temperature),
+        neutral_fraction_H_(temperature < 1.e4 ? 1. : 1.e-6) {}
+  explicit DiscICDensityFunction(ParameterFile &params)
+      : DiscICDensityFunction(params.get_physical_value<QUANTITY_MASS>("DensityFunction:mass", "20. Msol"),
+                              params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "500. K"),
+                              params.get_physical_value<QUANTITY_DENSITY>("DensityFunction:Bondi density", "3.1e3 g m^-3"),
+                              params.get_value<double>("DensityFunction:density power", 1.5)) {
+    params.get_physical_value<QUANTITY_VELOCITY>("DensityFunction:Bondi velocity", "2.873 km s^-1");
+    params.get_value<double>("DensityFunction:velocity power", 0.5);
+  }
+  DensityValues operator()(const Vec3 &x) override {
+    const double rinv = R_B_ / std::sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    DensityValues v;
+    v.number_density = n_B_ * std::pow(rinv, gamma_rho_);
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = neutral_fraction_H_;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  static double mean_particle_mass(double temperature) {
+    return temperature < 1.e4 ? constants::proton_mass : 0.5 * constants::proton_mass;
+  }
+  double R_B_, n_B_, gamma_rho_, temperature_, neutral_fraction_H_;
+};
+
+/* vertical gas profile of a patch of a galactic disc in equilibrium with a stellar sech^2 disc
+ * (DiscPatchDensityFunction.hpp:120-176) */
+class DiscPatchDensityFunction : public DensityFunction {
+public:
+  DiscPatchDensityFunction(double disc_z, double surface_density, double scale_height, double gas_fraction,
+                           double temperature, double neutral_fraction)
+      : disc_z_(disc_z), b_inv_(1. / scale_height),
+        exponent_(-2. * scale_height / gas_disc_scale_height(surface_density, temperature, neutral_fraction)),
+        density_norm_(0.5 * gas_fraction * surface_density * mass_fraction_factor(exponent_) * b_inv_ /
+                      constants::proton_mass),
+        temperature_(temperature), neutral_fraction_(neutral_fraction) {}
+  explicit DiscPatchDensityFunction(ParameterFile &params)
+      : DiscPatchDensityFunction(
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:disc z", "0. m"),
+            params.get_physical_value<QUANTITY_SURFACE_DENSITY>("DensityFunction:surface density", "30. Msol pc^-2"),
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:scale height", "200. pc"),
+            params.get_value<double>("DensityFunction:gas fraction", 0.1),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "1.e4 K"),
+            params.get_value<double>("DensityFunction:neutral fraction", 1e-6)) {}
+  DensityValues operator()(const Vec3 &x) override {
+    const double dz = x[2] - disc_z_;
+    DensityValues v;
+    v.number_density = density_norm_ * std::pow(std::cosh(dz * b_inv_), exponent_);
+    v.temperature = temperature_;
+    v.ionic_fraction[0] = neutral_fraction_;
+    return v;
+  }
+
+private:
+  static double gas_disc_scale_height(double surface_density, double temperature, double neutral_fraction) {
+    return (constants::boltzmann * temperature) /
+           (0.5 * constants::proton_mass * (1. + neutral_fraction) * M_PI * constants::newton_constant * surface_density);
+  }
+  /* the reference's cubic fit (in log10) of the mass integral of cosh^exponent */
+  static double mass_fraction_factor(double exponent) {
+    const double x = std::log10(-0.5 * exponent);
+    const double x2 = x * x;
+    const double y = 0.01499337 * x2 * x - 0.08454788 * x2 + 0.63503798 * x - 0.01018254;
+    return std::pow(10., y);
+  }
+  double disc_z_, b_inv_, exponent_, density_norm_, temperature_, neutral_fraction_;
+};
+
+/* double-exponential disc of a spiral galaxy, cut at 15 kpc (SpiralGalaxyDensityFunction.hpp:69-131).
+ * As in the reference the central *number* density is multiplied by 1.674e-27 (a hydrogen mass in kg)
+ * before it is stored as the cells' number density, the gas is neutral and the temperature is 0. */
+class SpiralGalaxyDensityFunction : public DensityFunction {
+public:
+  SpiralGalaxyDensityFunction(double r_ISM, double h_ISM, double n_0)
+      : r_ISM_(r_ISM), h_ISM_(h_ISM), n_0_(1.674e-27 * n_0), kpc_(3.086e19) {}
+  explicit SpiralGalaxyDensityFunction(ParameterFile &params)
+      : SpiralGalaxyDensityFunction(
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:scale length ISM", "6. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:scale height ISM", "0.22 kpc"),
+            params.get_physical_value<QUANTITY_NUMBER_DENSITY>("DensityFunction:central density", "1. cm^-3")) {}
+  DensityValues operator()(const Vec3 &x) override {
+    const double w = std::sqrt(x[0] * x[0] + x[1] * x[1]);
+    DensityValues v;
+    if (w < 15. * kpc_ && std::abs(x[2]) < 15. * kpc_)
+      v.number_density = n_0_ * std::exp(-w / r_ISM_) * std::exp(-std::abs(x[2]) / h_ISM_);
+    v.temperature = 0.;
+    v.ionic_fraction[0] = 1.;
+    v.ionic_fraction[1] = 0.;
+    return v;
+  }
+
+private:
+  double r_ISM_, h_ISM_, n_0_, kpc_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -425,8 +569,12 @@ struct DensityFunctionFactory {
     if (type == "BlockSyntax") return new BlockSyntaxDensityFunction(params);
     if (type == "AsciiFile") return new AsciiFileDensityFunction(params);
     if (type == "Interpolated") return new InterpolatedDensityFunction(params);
-    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile and "
-              "Interpolated)!",
+    if (type == "CoredDMProfile") return new CoredDMProfileDensityFunction(params);
+    if (type == "DiscIC") return new DiscICDensityFunction(params);
+    if (type == "DiscPatch") return new DiscPatchDensityFunction(params);
+    if (type == "SpiralGalaxy") return new SpiralGalaxyDensityFunction(params);
+    cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile, "
+              "Interpolated, CoredDMProfile, DiscIC, DiscPatch and SpiralGalaxy)!",
               type.c_str());
   }
 };
@@ -600,6 +748,182 @@ private:
   std::vector<double> lifetimes_;
 };
 
+/* Sources that are born at random and die after a fixed lifetime, evolved in steps of the update
+ * interval up to the starting time: every step each of `average_number` slots gives birth with
+ * probability update interval / lifetime (DiscPatchPhotonSourceDistribution.hpp:131-204,
+ * DwarfGalaxyPhotonSourceDistribution.hpp:126-197: the two differ in where a source is put). */
+class StochasticPhotonSourcePopulation : public PhotonSourceDistribution {
+public:
+  size_t get_number_of_sources() const override { return positions_.size(); }
+  Vec3 get_position(size_t i) override { return positions_[i]; }
+  double get_weight(size_t) const override { return 1. / get_number_of_sources(); }
+  double get_total_luminosity() const override { return source_luminosity_ * get_number_of_sources(); }
+
+protected:
+  StochasticPhotonSourcePopulation(double source_luminosity, int32_t seed)
+      : source_luminosity_(source_luminosity), random_generator_(seed) {}
+  virtual Vec3 generate_source_position() = 0;
+  /* called by the concrete class once its position parameters are in place */
+  void populate(double source_lifetime, uint32_t average_number, double update_interval, double starting_time) {
+    const double source_probability = update_interval / source_lifetime;
+    for (uint32_t i = 0; i < average_number; ++i) {
+      lifetimes_.push_back(random_generator_.get_uniform_random_double() * source_lifetime);
+      positions_.push_back(generate_source_position());
+    }
+    uint32_t number_of_updates = 1;
+    while (number_of_updates * update_interval <= starting_time) {
+      size_t i = 0;
+      while (i < lifetimes_.size()) {
+        lifetimes_[i] -= update_interval;
+        if (lifetimes_[i] <= 0.) {
+          positions_.erase(positions_.begin() + i);
+          lifetimes_.erase(lifetimes_.begin() + i);
+        } else {
+          ++i;
+        }
+      }
+      for (uint32_t k = 0; k < average_number; ++k) {
+        if (random_generator_.get_uniform_random_double() <= source_probability) {
+          const double offset = random_generator_.get_uniform_random_double() * update_interval;
+          lifetimes_.push_back(source_lifetime - offset);
+          positions_.push_back(generate_source_position());
+        }
+      }
+      ++number_of_updates;
+    }
+  }
+  static void no_source_output(ParameterFile &params) {
+    if (params.get_value<bool>("PhotonSourceDistribution:output sources", false))
+      cmi_error("PhotonSourceDistribution:output sources is not provided by the B200 backend!");
+  }
+  /* one Box-Muller deviate: scale * sqrt(-2 ln u1) * cos(2 pi u2) */
+  double gaussian(double scale) {
+    const double rho = scale * std::sqrt(-2. * std::log(random_generator_.get_uniform_random_double()));
+    return rho * std::cos(2. * M_PI * random_generator_.get_uniform_random_double());
+  }
+  double source_luminosity_;
+  RandomGenerator random_generator_;
+  std::vector<Vec3> positions_;
+  std::vector<double> lifetimes_;
+};
+
+/* uniform in x and y over a rectangle, Gaussian in z */
+class DiscPatchPhotonSourceDistribution : public StochasticPhotonSourcePopulation {
+public:
+  DiscPatchPhotonSourceDistribution(double source_lifetime, double source_luminosity, uint32_t average_number,
+                                    double anchor_x, double sides_x, double anchor_y, double sides_y, double origin_z,
+                                    double scaleheight_z, int32_t seed, double update_interval, double starting_time)
+      : StochasticPhotonSourcePopulation(source_luminosity, seed), anchor_x_(anchor_x), sides_x_(sides_x),
+        anchor_y_(anchor_y), sides_y_(sides_y), origin_z_(origin_z), scaleheight_z_(scaleheight_z) {
+    populate(source_lifetime, average_number, update_interval, starting_time);
+  }
+  explicit DiscPatchPhotonSourceDistribution(ParameterFile &params)
+      : DiscPatchPhotonSourceDistribution(
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:source lifetime", "20. Myr"),
+            params.get_physical_value<QUANTITY_FREQUENCY>("PhotonSourceDistribution:source luminosity", "3.125e49 s^-1"),
+            params.get_value<uint32_t>("PhotonSourceDistribution:average number of sources", 24),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:anchor x", "-1. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:sides x", "2. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:anchor y", "-1. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:sides y", "2. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:origin z", "0. pc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:scaleheight z", "63. pc"),
+            params.get_value<int32_t>("PhotonSourceDistribution:random seed", 42),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:update interval", "0.1 Myr"),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:starting time", "0. Myr")) {
+    no_source_output(params);
+  }
+
+protected:
+  Vec3 generate_source_position() override {
+    Vec3 p;
+    p[0] = anchor_x_ + random_generator_.get_uniform_random_double() * sides_x_;
+    p[1] = anchor_y_ + random_generator_.get_uniform_random_double() * sides_y_;
+    p[2] = gaussian(scaleheight_z_) + origin_z_;
+    return p;
+  }
+
+private:
+  double anchor_x_, sides_x_, anchor_y_, sides_y_, origin_z_, scaleheight_z_;
+};
+
+/* Gaussian blob: (x, y) from one Box-Muller pair, z from a second one.  The reference reads a
+ * `center` but never adds it to the positions (DwarfGalaxyPhotonSourceDistribution.hpp:98-119);
+ * neither does this class. */
+class DwarfGalaxyPhotonSourceDistribution : public StochasticPhotonSourcePopulation {
+public:
+  DwarfGalaxyPhotonSourceDistribution(double source_lifetime, double source_luminosity, uint32_t average_number,
+                                      double scale_radius, int32_t seed, double update_interval, double starting_time)
+      : StochasticPhotonSourcePopulation(source_luminosity, seed), scale_radius_(scale_radius) {
+    populate(source_lifetime, average_number, update_interval, starting_time);
+  }
+  explicit DwarfGalaxyPhotonSourceDistribution(ParameterFile &params)
+      : DwarfGalaxyPhotonSourceDistribution(
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:source lifetime", "20. Myr"),
+            params.get_physical_value<QUANTITY_FREQUENCY>("PhotonSourceDistribution:source luminosity", "3.125e49 s^-1"),
+            params.get_value<uint32_t>("PhotonSourceDistribution:average number of sources", 52),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:scale radius", "300. pc"),
+            params.get_value<int32_t>("PhotonSourceDistribution:random seed", 42),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:update interval", "0.01 Gyr"),
+            params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:starting time", "0. Gyr")) {
+    params.get_physical_vector<QUANTITY_LENGTH>("PhotonSourceDistribution:center", "[0. kpc, 0. kpc, 0. kpc]");
+    no_source_output(params);
+  }
+
+protected:
+  Vec3 generate_source_position() override {
+    const double rho1 = scale_radius_ * std::sqrt(-2. * std::log(random_generator_.get_uniform_random_double()));
+    const double phi1 = 2. * M_PI * random_generator_.get_uniform_random_double();
+    const double rho2 = scale_radius_ * std::sqrt(-2. * std::log(random_generator_.get_uniform_random_double()));
+    const double phi2 = 2. * M_PI * random_generator_.get_uniform_random_double();
+    return Vec3{rho1 * std::cos(phi1), rho1 * std::sin(phi1), rho2 * std::cos(phi2)};
+  }
+
+private:
+  double scale_radius_;
+};
+
+/* A fixed number of equal sources, uniform in x and y, Gaussian in z; a position is drawn when
+ * it is asked for (SILCCPhotonSourceDistribution.hpp:159-187), so asking twice gives two answers. */
+class SILCCPhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  SILCCPhotonSourceDistribution(uint32_t num_sources, double anchor_x, double sides_x, double anchor_y, double sides_y,
+                                double origin_z, double scaleheight_z, double luminosity, int32_t seed)
+      : num_sources_(num_sources), anchor_x_(anchor_x), sides_x_(sides_x), anchor_y_(anchor_y), sides_y_(sides_y),
+        origin_z_(origin_z), scaleheight_z_(scaleheight_z), luminosity_(luminosity), random_generator_(seed) {}
+  explicit SILCCPhotonSourceDistribution(ParameterFile &params)
+      : SILCCPhotonSourceDistribution(
+            params.get_value<uint32_t>("PhotonSourceDistribution:number of sources", 24),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:anchor x", "-1. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:sides x", "2. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:anchor y", "-1. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:sides y", "2. kpc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:origin z", "0. pc"),
+            params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:scaleheight z", "63. pc"),
+            params.get_physical_value<QUANTITY_FREQUENCY>("PhotonSourceDistribution:luminosity", "3.125e49 s^-1"),
+            params.get_value<int32_t>("PhotonSourceDistribution:random seed", 42)) {
+    if (params.get_value<bool>("PhotonSourceDistribution:output sources", false))
+      cmi_error("PhotonSourceDistribution:output sources is not provided by the B200 backend!");
+  }
+  size_t get_number_of_sources() const override { return num_sources_; }
+  Vec3 get_position(size_t index) override {
+    if (index > num_sources_) cmi_error("Source index out of range!");
+    Vec3 p;
+    p[0] = anchor_x_ + random_generator_.get_uniform_random_double() * sides_x_;
+    p[1] = anchor_y_ + random_generator_.get_uniform_random_double() * sides_y_;
+    const double rho = scaleheight_z_ * std::sqrt(-2. * std::log(random_generator_.get_uniform_random_double()));
+    p[2] = rho * std::cos(2. * M_PI * random_generator_.get_uniform_random_double()) + origin_z_;
+    return p;
+  }
+  double get_weight(size_t) const override { return 1. / num_sources_; }
+  double get_total_luminosity() const override { return num_sources_ * luminosity_; }
+
+private:
+  uint32_t num_sources_;
+  double anchor_x_, sides_x_, anchor_y_, sides_y_, origin_z_, scaleheight_z_, luminosity_;
+  RandomGenerator random_generator_;
+};
+
 struct PhotonSourceDistributionFactory {
   static PhotonSourceDistribution *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("PhotonSourceDistribution:type", "SingleStar");
@@ -608,9 +932,12 @@ struct PhotonSourceDistributionFactory {
     if (type == "AsciiFile") return new AsciiFilePhotonSourceDistribution(params);
     if (type == "AsciiFileTable") return new AsciiFileTablePhotonSourceDistribution(params);
     if (type == "UniformRandom") return new UniformRandomPhotonSourceDistribution(params);
+    if (type == "DiscPatch") return new DiscPatchPhotonSourceDistribution(params);
+    if (type == "DwarfGalaxy") return new DwarfGalaxyPhotonSourceDistribution(params);
+    if (type == "SILCC") return new SILCCPhotonSourceDistribution(params);
     if (type == "None") return nullptr;
     cmi_error("Unknown PhotonSourceDistribution type: \"%s\" (the B200 backend provides SingleStar, AsciiFile, "
-              "AsciiFileTable and UniformRandom)!",
+              "AsciiFileTable, UniformRandom, DiscPatch, DwarfGalaxy and SILCC)!",
               type.c_str());
   }
 };

@@ -46,12 +46,14 @@ constexpr double boltzmann = 1.38064852e-23;
 constexpr double lightspeed = 299792458.;
 constexpr double electronvolt = 1.6021766208e-19;
 constexpr double proton_mass = 1.672621898e-27;
+constexpr double newton_constant = 6.67408e-11;
 } // namespace constants
 
 enum Quantity {
   QUANTITY_ACCELERATION, QUANTITY_ANGLE, QUANTITY_DENSITY, QUANTITY_ENERGY, QUANTITY_FLUX,
   QUANTITY_FREQUENCY, QUANTITY_LENGTH, QUANTITY_MASS, QUANTITY_NUMBER_DENSITY, QUANTITY_REACTION_RATE,
-  QUANTITY_SURFACE_AREA, QUANTITY_TEMPERATURE, QUANTITY_TIME, QUANTITY_VELOCITY, QUANTITY_VOLUME
+  QUANTITY_SURFACE_AREA, QUANTITY_TEMPERATURE, QUANTITY_TIME, QUANTITY_VELOCITY, QUANTITY_VOLUME,
+  QUANTITY_SURFACE_DENSITY /* appended: the integer values are part of the cmih_paramfile_get_physical probe */
 };
 
 /* a unit = SI value of one unit + exponents of (length, time, mass, temperature, angle) */
@@ -115,6 +117,7 @@ public:
     case QUANTITY_NUMBER_DENSITY: return "m^-3";
     case QUANTITY_REACTION_RATE: return "m^3 s^-1";
     case QUANTITY_SURFACE_AREA: return "m^2";
+    case QUANTITY_SURFACE_DENSITY: return "kg m^-2";
     case QUANTITY_TEMPERATURE: return "K";
     case QUANTITY_TIME: return "s";
     case QUANTITY_VELOCITY: return "m s^-1";

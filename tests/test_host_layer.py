@@ -136,10 +136,39 @@ def test_parameter_file_same_values_and_used_values_dump(host, ref, tmp_path):
         host.ParameterFile(bad).density_function(np.zeros((1, 3)))
 
 
-@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks", "ascii_file", "interpolated_1d"])
+ANALYTIC_PROFILES = {
+    # type -> (DensityFunction block, box half size in pc); defaults and non-default values
+    "cored_dm_defaults": ("  type: CoredDMProfile\n", 500.),
+    "cored_dm": ("  type: CoredDMProfile\n  core radius: 120. pc\n  maximum circular velocity: 15. km s^-1\n"
+                 "  central density: 2.e-21 g cm^-3\n  temperature: 8000. K\n  neutral fraction: 0.3\n"
+                 "  polytropic index: 1.4\n", 500.),
+    "disc_ic_defaults": ("  type: DiscIC\n", 5.e-4),
+    "disc_ic_hot": ("  type: DiscIC\n  mass: 12. Msol\n  temperature: 2.e4 K\n  Bondi density: 1.e-18 g cm^-3\n"
+                    "  density power: 1.2\n", 5.e-4),
+    "disc_patch_defaults": ("  type: DiscPatch\n", 1000.),
+    "disc_patch": ("  type: DiscPatch\n  disc z: 50. pc\n  surface density: 12. Msol pc^-2\n  scale height: 350. pc\n"
+                   "  gas fraction: 0.25\n  temperature: 6000. K\n  neutral fraction: 0.5\n", 1000.),
+    "spiral_galaxy_defaults": ("  type: SpiralGalaxy\n", 16000.),
+    "spiral_galaxy": ("  type: SpiralGalaxy\n  scale length ISM: 4. kpc\n  scale height ISM: 0.5 kpc\n"
+                      "  central density: 3. cm^-3\n", 16000.),
+}
+
+
+@pytest.mark.parametrize("kind", ["homogeneous_defaults", "lexington_blocks", "ascii_file", "interpolated_1d",
+                                  *ANALYTIC_PROFILES])
 def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     nc = 12
-    if kind.startswith("interpolated"):
+    if kind in ANALYTIC_PROFILES:
+        # closed-form profiles: CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy (exp / log / atan / pow / cosh
+        # per cell midpoint; the same libm on both sides, so the grids must be the same doubles)
+        block, half_pc = ANALYTIC_PROFILES[kind]
+        text = (f"SimulationBox:\n  anchor: [-{half_pc!r} pc, -{half_pc!r} pc, -{half_pc!r} pc]\n"
+                f"  sides: [{2 * half_pc!r} pc, {2 * half_pc!r} pc, {2 * half_pc!r} pc]\n"
+                "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+                f"  number of cells: [{nc}, {nc}, {nc}]\nDensityFunction:\n{block}"
+                "PhotonSourceSpectrum:\n  type: Monochromatic\n")
+        half = None
+    elif kind.startswith("interpolated"):
         # InterpolatedDensityFunction: a z profile (the reference's own test file format,
         # test/test_interpolated_density.txt) sampled by the 12^3 grid
         rng = np.random.default_rng(9)
@@ -192,13 +221,21 @@ def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     sim = ref.Simulation(pf)
     f = sim.fields()
     sim.close()
-    cs = 2 * half / nc
-    m = -half + cs * np.arange(nc) + 0.5 * cs      # CartesianDensityGrid::get_cell_midpoint
+    if half is None:
+        # the box as the parameter file's unit conversion gives it (anchor = -half_pc pc, sides = 2 half_pc pc)
+        a = ref.convert(-half_pc, "pc", "m")
+        cs = ref.convert(2 * half_pc, "pc", "m") / nc
+        m = a + cs * np.arange(nc) + 0.5 * cs
+    else:
+        cs = 2 * half / nc
+        m = -half + cs * np.arange(nc) + 0.5 * cs      # CartesianDensityGrid::get_cell_midpoint
     X, Y, Z = np.meshgrid(m, m, m, indexing="ij")
     x = np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], 1)
     dens, temp, xH = host.ParameterFile(pf).density_function(x)
     assert np.array_equal(dens, f[0]) and np.array_equal(temp, f[1]) and np.array_equal(xH, f[2])
     assert np.isfinite(dens).all()
+    if kind in ANALYTIC_PROFILES:
+        assert np.unique(dens).size > 5 and dens.max() > 0
     if kind in ("ascii_file", "interpolated_1d"):
         assert np.unique(dens).size > 20 and dens.min() >= 1e6 and dens.max() <= 3e8
     if kind == "lexington_blocks":
@@ -269,6 +306,23 @@ def test_photon_source_distributions_give_the_reference_sources(host, ref, tmp_p
                             "  box anchor: [-3. pc, -2. pc, -1. pc]\n  box sides: [6. pc, 4. pc, 2. pc]\n"
                             "  source lifetime: 2. Myr\n  source luminosity: 3.e48 s^-1\n  update interval: 0.05 Myr\n"
                             "  starting time: 3.1 Myr\n"),
+        # sources born at random and evolved to the starting time (rectangle x Gaussian height / Gaussian blob),
+        # and the SILCC set (positions drawn when asked for): all on the RANLUX stream
+        "disc_patch_defaults": "PhotonSourceDistribution:\n  type: DiscPatch\n",
+        "disc_patch_evolved": ("PhotonSourceDistribution:\n  type: DiscPatch\n  source lifetime: 5. Myr\n"
+                               "  source luminosity: 1.e49 s^-1\n  average number of sources: 40\n  anchor x: -200. pc\n"
+                               "  sides x: 400. pc\n  anchor y: -100. pc\n  sides y: 300. pc\n  origin z: 10. pc\n"
+                               "  scaleheight z: 40. pc\n  random seed: 77\n  update interval: 0.2 Myr\n"
+                               "  starting time: 12.3 Myr\n"),
+        "dwarf_galaxy_defaults": "PhotonSourceDistribution:\n  type: DwarfGalaxy\n",
+        "dwarf_galaxy_evolved": ("PhotonSourceDistribution:\n  type: DwarfGalaxy\n  source lifetime: 8. Myr\n"
+                                 "  average number of sources: 30\n  center: [10. pc, 20. pc, 30. pc]\n"
+                                 "  scale radius: 150. pc\n  random seed: 5\n  update interval: 0.5 Myr\n"
+                                 "  starting time: 0.031 Gyr\n"),
+        "silcc_defaults": "PhotonSourceDistribution:\n  type: SILCC\n",
+        "silcc": ("PhotonSourceDistribution:\n  type: SILCC\n  number of sources: 100\n  anchor x: -0.5 kpc\n"
+                  "  sides x: 1. kpc\n  anchor y: -0.25 kpc\n  sides y: 0.5 kpc\n  origin z: 5. pc\n"
+                  "  scaleheight z: 30. pc\n  luminosity: 1.e48 s^-1\n  random seed: 9\n"),
         "single": "PhotonSourceDistribution:\n  type: SingleStar\n  position: [1. pc, 2. pc, 3. pc]\n  luminosity: 2.e49 s^-1\n",
     }
     for name, text in cases.items():
