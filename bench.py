@@ -164,6 +164,7 @@ def cpu_reference_measure(full_packets: int, sample_packets: int, steps: int, wa
     probabilities / state update do not depend on it, so the full-size figure is
         N_full / (N_full / rate_shoot + t_prep + t_update)."""
     import oracle.ref as ref
+    ref.use_all_host_threads()  # under torchrun OMP_NUM_THREADS is 1: the reference gets all the host's cores anyway
     warmup = max(warmup, 5)
     with tempfile.TemporaryDirectory() as d:
         yml = Path(d) / "lexingtonHII20.yml"

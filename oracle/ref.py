@@ -334,6 +334,18 @@ def reemit_sequence(paramfile, xH, xHe, T, nu_in, seed=42):
     return nu, typ, d
 
 
+def use_all_host_threads():
+    """Let the reference's OpenMP regions use every core this process may run on, whatever OMP_NUM_THREADS
+    says: `torch.distributed.run` exports OMP_NUM_THREADS=1 to its workers, and the reference clamps its
+    thread count to omp_get_max_threads() (WorkEnvironment.hpp:63-76).  Acts on the libgomp the reference
+    library is linked against.  Returns the thread count."""
+    import os
+    lib()
+    n = len(os.sched_getaffinity(0))
+    C.CDLL("libgomp.so.1").omp_set_num_threads(C.c_int(n))
+    return n
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 
