@@ -420,25 +420,33 @@ def main():
             "clocks": clocks.summary()}
 
     # ---- e2e: the same iteration through the C ABI with HOST buffers ----
-    if rank == 0 and not args.no_e2e and world == 1:
+    # every rank uploads its replica of the cells from pinned host memory, shoots its shard, joins the
+    # all-reduce, updates and reads the result back; wall clock between barriers, max over ranks
+    if not args.no_e2e:
         nc = ctx.ncells
         pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
         n_h, T_h, x_h, heat_h = pin(nc), pin(nc), pin(14, nc), pin(2, nc)
         n0, T0, x0, _ = ctx.download_cells()
         n_h[:] = n0; T_h[:] = T0; x_h[:] = x0
         e2e_steps = max(2, min(args.steps, 3))
-        torch.cuda.synchronize()
+        barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            ctx.upload_cells(n_h, T_h, x_h)                       # H2D: 16 doubles per cell
-            problems.run_iteration(prob, loop)
-            ctx.download_cells_into(n_h, T_h, x_h, heat_h)        # D2H: 18 doubles per cell
+            with torch.cuda.stream(stream):
+                ctx.upload_cells(n_h, T_h, x_h)                       # H2D: 16 doubles per cell
+                problems.run_iteration(prob, loop, n_packets=cnt, packet_offset=lo,
+                                       allreduce=allreduce if world > 1 else None)
+                ctx.download_cells_into(n_h, T_h, x_h, heat_h)        # D2H: 18 doubles per cell
             loop += 1
-        torch.cuda.synchronize()
+        barrier()
         dt = time.perf_counter() - t0
-        line["e2e"] = {"value": n_packets * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * 8 * nc,
-                       "d2h_bytes_per_step": 18 * 8 * nc, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
-    elif rank == 0:
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        line["e2e"] = {"value": n_packets * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * 8 * nc * world,
+                       "d2h_bytes_per_step": 18 * 8 * nc * world, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+    else:
         line["e2e"] = None
 
     if rank == 0 and not args.no_cpu_baseline and world == 1:
