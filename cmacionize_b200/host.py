@@ -126,6 +126,19 @@ class ParameterFile:
         _check(lib.cmih_initial_number_density(self._h, C.c_int64(ncells), dens.ctypes.data_as(C.c_void_p)))
         return dens
 
+    def write_snapshot(self, output_folder, iteration, number_density, temperature, ionic_fractions, time=0.):
+        """the file's DensityGridWriter (Gadget HDF5 by default, AsciiFile) on given cell arrays (no device
+        needed) -> name of the snapshot file"""
+        n = np.ascontiguousarray(number_density, dtype=np.float64).reshape(-1)
+        T = np.ascontiguousarray(temperature, dtype=np.float64).reshape(-1)
+        x = np.ascontiguousarray(ionic_fractions, dtype=np.float64).reshape(14, -1)
+        assert T.size == n.size and x.shape[1] == n.size
+        name = C.create_string_buffer(4096)
+        _check(lib.cmih_write_snapshot(self._h, str(output_folder).encode(), C.c_uint32(iteration), C.c_double(time),
+                                       C.c_int64(n.size), n.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p),
+                                       x.ctypes.data_as(C.c_void_p), name, C.c_int(4096)))
+        return name.value.decode()
+
     def abundances(self):
         out = np.empty(6)
         _check(lib.cmih_abundances(self._h, out.ctypes.data_as(C.c_void_p)))

@@ -46,10 +46,12 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <sys/utsname.h>
 #include <nccl.h> /* types only: the library is bound at run time, see NcclApi */
 
 #include "../../include/cmib.h"
 #include "Error.hpp"
+#include "HDF5Writer.hpp"
 #include "ParameterFile.hpp"
 #include "RandomGenerator.hpp"
 #include "../csrc/spectrum_tables.hpp" /* host-side table builders + the samplers the device uses (plain C++) */
@@ -87,6 +89,11 @@ private:
 inline const char *ion_name(int ion) {
   static const char *names[CMIB_NUM_IONS] = {"H_n", "He_n", "C_p1", "C_p2", "N_n", "N_p1", "N_p2",
                                              "O_n", "O_p1", "Ne_n", "Ne_p1", "S_p1", "S_p2", "S_p3"};
+  return names[ion];
+}
+/* get_ion_name (ElementNames.hpp:210-240): the names snapshot fields carry (NeutralFractionH, NeutralFractionC+, ...) */
+inline const char *ion_symbol(int ion) {
+  static const char *names[CMIB_NUM_IONS] = {"H", "He", "C+", "C++", "N", "N+", "N++", "O", "O+", "Ne", "Ne+", "S+", "S++", "S+++"};
   return names[ion];
 }
 inline const char *element_name(int el) {
@@ -1317,6 +1324,8 @@ public:
   }
   double get_cell_volume() const { return cellside_[0] * cellside_[1] * cellside_[2]; }
   const std::array<int32_t, 3> &get_number_of_cells_3d() const { return ncell_; }
+  const Vec3 &get_box_anchor() const { return anchor_; }
+  const Vec3 &get_box_sides() const { return sides_; }
   /* DensityGrid::set_densities: evaluate the DensityFunction at every cell midpoint */
   void set_densities(DensityFunction &function) {
     if (function.set_densities(*this)) return;
@@ -1496,8 +1505,17 @@ struct DensityMaskFactory {
   }
 };
 
-/* ---- writer: the reference's ASCII snapshot layout, optionally with every field ---- */
-class AsciiFileDensityGridWriter {
+/* ---- writers ---- */
+class DensityGridWriter {
+public:
+  virtual ~DensityGridWriter() {}
+  /* DensityGridWriter::write(grid, iteration, params, time) (DensityGridWriter.hpp); works on the host mirror
+   * of the cells: the caller refreshes it (CartesianDensityGrid::download) */
+  virtual void write(CartesianCells &grid, uint32_t iteration, ParameterFile &params, double time = 0.) = 0;
+};
+
+/* the reference's ASCII snapshot layout, optionally with every field */
+class AsciiFileDensityGridWriter : public DensityGridWriter {
 public:
   AsciiFileDensityGridWriter(std::string prefix, std::string output_folder, bool all_fields = false)
       : prefix_(std::move(prefix)), folder_(std::move(output_folder)), all_fields_(all_fields) {}
@@ -1509,8 +1527,8 @@ public:
     snprintf(num, sizeof(num), "%03u", iteration);
     return folder_ + "/" + prefix_ + num + ".txt";
   }
-  void write(CartesianDensityGrid &grid, uint32_t iteration) {
-    grid.download();
+  void write(CartesianCells &grid, uint32_t iteration, ParameterFile &, double = 0.) override { write(grid, iteration); }
+  void write(CartesianCells &grid, uint32_t iteration) {
     std::ofstream file(filename(iteration));
     if (!file) cmi_error("Unable to open snapshot file \"%s\"!", filename(iteration).c_str());
     const size_t n = grid.get_number_of_cells();
@@ -1540,6 +1558,140 @@ public:
 private:
   std::string prefix_, folder_;
   bool all_fields_;
+};
+
+/* Which cell properties a snapshot holds: the `DensityGridWriterFields:` block
+ * (DensityGridWriterFields.hpp:790-835).  Without hydro the defaults are Coordinates, NumberDensity and
+ * NeutralFractionH; every `NeutralFraction<ion>` and `Temperature` can be switched on.  As in the reference a
+ * flagged ion also switches on the ions before it (`ion_present` shifts the flag word, :843-846). */
+struct DensityGridWriterFields {
+  bool coordinates, number_density, temperature;
+  uint32_t neutral_fraction = 0;
+  explicit DensityGridWriterFields(ParameterFile &params) {
+    coordinates = params.get_value<uint32_t>("DensityGridWriterFields:Coordinates", 1) > 0;
+    number_density = params.get_value<uint32_t>("DensityGridWriterFields:NumberDensity", 1) > 0;
+    temperature = params.get_value<uint32_t>("DensityGridWriterFields:Temperature", 0) > 0;
+    for (int ion = 0; ion < CMIB_NUM_IONS; ++ion)
+      neutral_fraction += params.get_value<uint32_t>(std::string("DensityGridWriterFields:NeutralFraction") + ion_symbol(ion),
+                                                     ion == 0 ? 1u : 0u)
+                          << ion;
+    if (params.get_value<uint32_t>("DensityGridWriterFields:CosmicRayFactor", 0) > 0)
+      cmi_error("DensityGridWriterFields:CosmicRayFactor is not provided by the B200 backend!");
+  }
+  bool ion_present(int ion) const { return (neutral_fraction >> ion) > 0; }
+};
+
+/* Gadget-style HDF5 snapshot, group for group and attribute for attribute what GadgetDensityGridWriter::write
+ * produces (GadgetDensityGridWriter.cpp:122-300): /Header, /Code, /Configuration, /Parameters (the used values),
+ * /RuntimePars, /Units (SI) and /PartType0 with Coordinates (relative to the box anchor), NumberDensity,
+ * Temperature and NeutralFraction<ion>, so that the reference's benchmark analysis scripts read it
+ * unchanged.  Written by host/HDF5Writer.hpp; datasets are contiguous, never compressed. */
+class GadgetDensityGridWriter : public DensityGridWriter {
+public:
+  GadgetDensityGridWriter(std::string prefix, std::string output_folder, const DensityGridWriterFields &fields,
+                          uint32_t padding = 3)
+      : prefix_(std::move(prefix)), folder_(std::move(output_folder)), fields_(fields), padding_(padding) {}
+  GadgetDensityGridWriter(const std::string &output_folder, ParameterFile &params)
+      : GadgetDensityGridWriter(params.get_value<std::string>("DensityGridWriter:prefix", "snapshot"), output_folder,
+                                DensityGridWriterFields(params), params.get_value<uint32_t>("DensityGridWriter:padding", 3)) {
+    if (params.get_value<bool>("DensityGridWriter:compression", false))
+      cmi_error("DensityGridWriter:compression is not provided by the B200 backend!");
+  }
+  /* Utilities::compose_filename: folder/prefixNNN.hdf5 */
+  std::string filename(uint32_t iteration) const {
+    char num[32];
+    snprintf(num, sizeof(num), "%0*u", (int)padding_, iteration);
+    return folder_ + "/" + prefix_ + num + ".hdf5";
+  }
+  void write(CartesianCells &grid, uint32_t iteration, ParameterFile &params, double time = 0.) override {
+    const size_t n = grid.get_number_of_cells();
+    hdf5::HDF5File file;
+    hdf5::Group &header = file.root().create_group("Header");
+    header.write_attribute("BoxSize", grid.get_box_sides());
+    header.write_attribute("Dimension", int32_t(3));
+    header.write_attribute("Flag_Entropy_ICs", std::vector<uint32_t>(6, 0));
+    header.write_attribute("MassTable", std::vector<double>(6, 0.));
+    header.write_attribute("NumFilesPerSnapshot", int32_t(1));
+    std::vector<uint32_t> numpart(6, 0);
+    numpart[0] = (uint32_t)n;
+    header.write_attribute("NumPart_ThisFile", numpart);
+    header.write_attribute("NumPart_Total", numpart);
+    header.write_attribute("NumPart_Total_HighWord", std::vector<uint32_t>(6, 0));
+    header.write_attribute("Time", time);
+
+    hdf5::Group &code = file.root().create_group("Code");
+    struct utsname os;
+    if (uname(&os) != 0) memset(&os, 0, sizeof(os));
+    code.write_attribute("Git version", "cmacionize_b200 (C ABI " + std::to_string(cmib_abi_version()) + ")");
+    code.write_attribute("Compilation date", __DATE__);
+    code.write_attribute("Compilation time", __TIME__);
+    code.write_attribute("Compiler", std::string("GNU ") + __VERSION__);
+    code.write_attribute("Operating system", os.sysname);
+    code.write_attribute("Kernel name", std::string(os.sysname) + " " + os.release);
+    code.write_attribute("Hardware name", os.machine);
+    code.write_attribute("Host name", os.nodename);
+
+    hdf5::Group &configuration = file.root().create_group("Configuration");
+    configuration.write_attribute("BACKEND", "B200 (sm_100a) photoionization hot path, libcmib.so");
+    configuration.write_attribute("HAVE_HDF5", "False (built-in writer: host/HDF5Writer.hpp)");
+    configuration.write_attribute("NUMBER_OF_IONNAMES", std::to_string(CMIB_NUM_IONS));
+
+    hdf5::Group &parameters = file.root().create_group("Parameters");
+    for (const auto &kv : params.used_values()) parameters.write_attribute(kv.first, kv.second);
+
+    hdf5::Group &runtime = file.root().create_group("RuntimePars");
+    {
+      char stamp[64];
+      const time_t now = ::time(nullptr);
+      struct tm tmv;
+      localtime_r(&now, &tmv);
+      strftime(stamp, sizeof(stamp), "%d/%m/%Y, %H:%M:%S", &tmv); /* Utilities::get_timestamp */
+      runtime.write_attribute("Creation time", stamp);
+    }
+    runtime.write_attribute("Iteration", uint32_t(iteration));
+
+    hdf5::Group &units = file.root().create_group("Units");
+    units.write_attribute("Unit current in cgs (U_I)", 1.);
+    units.write_attribute("Unit length in cgs (U_L)", 100.);
+    units.write_attribute("Unit mass in cgs (U_M)", 1000.);
+    units.write_attribute("Unit temperature in cgs (U_T)", 1.);
+    units.write_attribute("Unit time in cgs (U_t)", 1.);
+
+    hdf5::Group &part = file.root().create_group("PartType0");
+    std::vector<double> coordinates;
+    if (fields_.coordinates) {
+      coordinates.resize(3 * n);
+      const Vec3 &anchor = grid.get_box_anchor();
+      for (size_t i = 0; i < n; ++i) {
+        const Vec3 x = grid.get_cell_midpoint(i);
+        for (int k = 0; k < 3; ++k) coordinates[3 * i + k] = x[k] - anchor[k];
+      }
+      part.create_dataset("Coordinates", hdf5::Type::F64, {n, 3}, coordinates.data());
+    }
+    if (fields_.number_density) part.create_dataset("NumberDensity", hdf5::Type::F64, {n}, grid.number_density.data());
+    if (fields_.temperature) part.create_dataset("Temperature", hdf5::Type::F64, {n}, grid.temperature.data());
+    for (int ion = 0; ion < CMIB_NUM_IONS; ++ion)
+      if (fields_.ion_present(ion))
+        part.create_dataset(std::string("NeutralFraction") + ion_symbol(ion), hdf5::Type::F64, {n},
+                            grid.ionic_fraction.data() + (size_t)ion * n);
+    file.write(filename(iteration));
+  }
+
+private:
+  std::string prefix_, folder_;
+  DensityGridWriterFields fields_;
+  uint32_t padding_;
+};
+
+struct DensityGridWriterFactory {
+  /* DensityGridWriterFactory.hpp:86-110; the default type is Gadget, as in the reference */
+  static DensityGridWriter *generate(const std::string &output_folder, ParameterFile &params, Log *log = nullptr) {
+    const std::string type = params.get_value<std::string>("DensityGridWriter:type", "Gadget");
+    if (log) log->write_info("Requested DensityGridWriter type: ", type);
+    if (type == "AsciiFile") return new AsciiFileDensityGridWriter(output_folder, params);
+    if (type == "Gadget") return new GadgetDensityGridWriter(output_folder, params);
+    cmi_error("Unknown DensityGridWriter type: \"%s\".", type.c_str());
+  }
 };
 
 /* ---- NCCL, bound at run time ----
@@ -1730,10 +1882,7 @@ public:
 
     output_folder_ = parameter_file_.get_value<std::string>(block_ + "output folder", ".");
     if (write_output) {
-      const std::string wtype = parameter_file_.get_value<std::string>("DensityGridWriter:type", "AsciiFile");
-      if (wtype != "AsciiFile" && log_)
-        log_->write_warning("DensityGridWriter type ", wtype, " needs HDF5; writing the AsciiFile layout instead.");
-      density_grid_writer_.reset(new AsciiFileDensityGridWriter(output_folder_, parameter_file_));
+      density_grid_writer_.reset(DensityGridWriterFactory::generate(output_folder_, parameter_file_, log_));
     }
     random_seed_ = parameter_file_.get_value<int32_t>(block_ + "random seed", 42);
     if (parameter_file_.get_value<bool>(block_ + "enable trackers", false))
@@ -1844,7 +1993,7 @@ public:
    * called once with the final grid (host mirror refreshed) */
   void run(const std::function<void(CartesianDensityGrid &)> &external_writer = nullptr) {
     CartesianDensityGrid &grid = *density_grids_[0];
-    if (density_grid_writer_) density_grid_writer_->write(grid, 0);
+    if (density_grid_writer_) { grid.download(); density_grid_writer_->write(grid, 0, parameter_file_); }
     double shoot = 0., update = 0.;
     for (uint32_t loop = 0; loop < number_of_iterations_; ++loop) {
       if (log_) log_->write_status("Starting loop ", loop, ".");
@@ -1865,9 +2014,9 @@ public:
         log_->write_info("Escape fraction from diffuse helium: ", 100. * r.typecount[2] / W, "%.");
       }
       if (every_iteration_output_ && density_grid_writer_ && loop + 1 < number_of_iterations_)
-        density_grid_writer_->write(grid, loop + 1);
+      { grid.download(); density_grid_writer_->write(grid, loop + 1, parameter_file_); }
     }
-    if (density_grid_writer_) density_grid_writer_->write(grid, number_of_iterations_);
+    if (density_grid_writer_) { grid.download(); density_grid_writer_->write(grid, number_of_iterations_, parameter_file_); }
     if (external_writer) {
       grid.download();
       external_writer(grid);
@@ -1908,7 +2057,7 @@ private:
   std::unique_ptr<PhotonSourceSpectrum> continuous_photon_source_spectrum_;
   std::unique_ptr<FractalDensityMask> density_mask_;
   DiffuseReemissionHandler reemission_;
-  std::unique_ptr<AsciiFileDensityGridWriter> density_grid_writer_;
+  std::unique_ptr<DensityGridWriter> density_grid_writer_;
   std::string output_folder_;
   double total_luminosity_ = 0.;
   int32_t random_seed_ = 42;

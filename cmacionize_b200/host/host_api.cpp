@@ -203,6 +203,27 @@ int cmih_initial_number_density(void *h, int64_t n, double *dens) {
     for (int64_t i = 0; i < n; ++i) dens[i] = cells.number_density[i];
   });
 }
+/* the parameter file's DensityGridWriter on given cell arrays (no device): number density [n], temperature [n],
+ * ionic fractions [14][n] on the parameter file's Cartesian grid -> writes the snapshot, returns its file name */
+int cmih_write_snapshot(void *h, const char *output_folder, uint32_t iteration, double time, int64_t n, const double *dens,
+                        const double *temp, const double *fractions, char *filename, int nfilename) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    const SimulationBox box(p);
+    CartesianCells cells(box, p.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}));
+    if ((int64_t)cells.get_number_of_cells() != n) throw std::runtime_error("wrong number of cells");
+    std::copy(dens, dens + n, cells.number_density.begin());
+    std::copy(temp, temp + n, cells.temperature.begin());
+    std::copy(fractions, fractions + (size_t)CMIB_NUM_IONS * n, cells.ionic_fraction.begin());
+    std::unique_ptr<DensityGridWriter> writer(DensityGridWriterFactory::generate(output_folder, p));
+    writer->write(cells, iteration, p, time);
+    std::string name;
+    if (auto *g = dynamic_cast<GadgetDensityGridWriter *>(writer.get())) name = g->filename(iteration);
+    if (auto *a = dynamic_cast<AsciiFileDensityGridWriter *>(writer.get())) name = a->filename(iteration);
+    strncpy(filename, name.c_str(), nfilename - 1);
+    filename[nfilename - 1] = 0;
+  });
+}
 /* AbundanceModelFactory on the parameter file -> He C N O Ne S relative to H */
 int cmih_abundances(void *h, double *out) {
   CMIH_TRY({

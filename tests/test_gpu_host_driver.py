@@ -77,6 +77,45 @@ IonizationSimulation:
     assert bad.returncode != 0
 
 
+def test_command_line_program_writes_gadget_hdf5_snapshots(host, tmp_path):
+    """DensityGridWriter type Gadget (the reference's default): the run leaves <prefix>NNN.hdf5 files that hold what
+    the reference's analysis scripts read; here the steps of benchmarks/stromgren.py:70-100 (h5py replaced by the
+    reader of tests/h5mini.py, which is pinned on files of the real library in tests/test_hdf5_writer.py)."""
+    import h5mini
+    from conftest import ROOT
+    from test_hdf5_writer import check_structure
+    nc, npk, nit = 32, 300000, 6
+    pf = tmp_path / "run.param"
+    pf.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=3, extra=f"""DensityGridWriter:
+  type: Gadget
+  prefix: stromgren_
+  padding: 3
+DensityGridWriterFields:
+  NumberDensity: 0
+IonizationSimulation:
+  output folder: {tmp_path}
+"""))
+    exe = ROOT / "cmacionize_b200" / "bin" / "CMacIonizeB200"
+    out = subprocess.run([str(exe), "--params", str(pf)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    names = sorted(q.name for q in tmp_path.glob("stromgren_*.hdf5"))
+    assert names == ["stromgren_000.hdf5", f"stromgren_{nit:03d}.hdf5"]
+    f = h5mini.File(tmp_path / names[-1])
+    check_structure(f)
+    box = np.array(f["Header"].attrs["BoxSize"])
+    assert np.array_equal(box, [10 * PC] * 3) and f["RuntimePars"].attrs["Iteration"] == nit
+    assert set(f["PartType0"].links()) == {"Coordinates", "NeutralFractionH"}
+    assert f["Parameters"].attrs["PhotonSourceDistribution:luminosity"].startswith("4.26e+49")
+    coords = f["PartType0"]["Coordinates"].read()
+    nfracH = f["PartType0"]["NeutralFractionH"].read()
+    radius = np.sqrt(((coords - 0.5 * box) ** 2).sum(1))
+    Rs = (0.75 * 4.26e49 / (np.pi * (1e8) ** 2 * 4e-19)) ** (1. / 3.)
+    assert nfracH[radius < 0.6 * Rs].max() < 0.05 and nfracH[radius > 1.3 * Rs].min() > 0.9
+    assert abs(stromgren_radius(nfracH, radius) - Rs) < 10 * PC / nc
+    x0 = h5mini.File(tmp_path / names[0])["PartType0"]["NeutralFractionH"].read()
+    assert (x0 == 1e-6).all()
+
+
 def test_two_gpu_driver_equals_one_gpu(host, tmp_path):
     """C++ driver on 2 GPUs (packets split by global id, one ncclAllReduce per iteration, replicated
     state update) == the same parameter file on 1 GPU: same packets, sums equal up to order."""

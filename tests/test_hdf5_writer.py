@@ -1,0 +1,292 @@
+"""Gadget-style HDF5 snapshots written by the host layer (host/HDF5Writer.hpp, GadgetDensityGridWriter) without
+an HDF5 library (reference: GadgetDensityGridWriter.cpp:122-300 through HDF5Tools.hpp / libhdf5).
+
+There is no HDF5 library in the image either, so the chain of evidence is:
+  1. tests/h5mini.py (a reader written from the file-format specification) is pinned on files written by the
+     real library: the reference's test/test.hdf5 against the values its own testHDF5Tools.cpp asserts, and
+     test/taskbased.hdf5, a snapshot written by the reference's GadgetDensityGridWriter;
+  2. the writer's files are read back with that reader (every field bit for bit, every attribute);
+  3. the writer's object-header messages are compared BYTE FOR BYTE with the messages the real library wrote for
+     the same content (attributes of /Header, /Units, /RuntimePars in taskbased.hdf5; dataspace, datatype,
+     fill-value and layout messages of a contiguous dataset in test/python_test.hdf5);
+  4. a structural check of everything a reader follows (sizes, alignment, sorted symbol tables, B-tree keys,
+     heap free list, end-of-file address).
+"""
+import struct
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import h5mini
+from conftest import ROOT
+
+GOLD = ROOT / "tests" / "golden" / "hdf5"
+PC = 3.086e16
+
+
+@pytest.fixture(scope="module")
+def host():
+    subprocess.check_call([sys.executable, "-c", "from cmacionize_b200 import build as b; b.build_host()"], cwd=str(ROOT))
+    from cmacionize_b200 import host as h
+    return h
+
+
+def test_reader_reads_what_the_reference_asserts_about_its_own_file():
+    """test/testHDF5Tools.cpp:48-157 on test/test.hdf5"""
+    f = h5mini.File(GOLD / "test.hdf5")
+    assert "HydroScheme" in f and "NonExistingGroup" not in f
+    g = f["HydroScheme"]
+    assert len(g.attrs) == 15
+    assert g.attrs["CFL parameter"][0] == np.float32(0.1) or abs(g.attrs["CFL parameter"][0] - 0.1) < 1e-7
+    assert g.attrs["Dimension"][0] == 3
+    assert g.attrs["Scheme"] == "Gadget-2 version of SPH (Springel 2005)"
+    h = f["Header"]
+    assert np.array_equal(h.attrs["BoxSize"], [1., 1., 1.])
+    assert np.array_equal(h.attrs["NumPart_ThisFile"], [100, 0, 0, 0, 1, 0])
+    assert np.array_equal(h.attrs["MassTable"], np.zeros(6))
+    p = f["PartType0"]
+    density = p["Density"].read()
+    assert density.shape == (100,) and abs(density[0] / 0.12052436 - 1.) < 1e-8
+    assert abs(density[31] - 0.2861183) < 1e-7 * 0.2861183 + 1e-9
+    ids = p["ParticleIDs"].read()
+    assert ids.shape == (100,) and ids[0] == 47
+    x = p["Coordinates"].read()
+    assert x.shape == (100, 3)
+    assert np.allclose(x[0], [0.09859136052607954, 0.1422694476979986, 0.10086706479716455], rtol=1e-15, atol=0)
+
+
+def test_reader_on_a_snapshot_written_by_the_reference():
+    f = h5mini.File(GOLD / "taskbased.hdf5")
+    assert f.link_order == ["Code", "Configuration", "Header", "Parameters", "PartType0", "RuntimePars", "Units"]
+    h = f["Header"].attrs
+    assert np.array_equal(h["BoxSize"], [3.086e17] * 3) and h["Dimension"] == 3 and h["NumFilesPerSnapshot"] == 1
+    assert np.array_equal(h["NumPart_ThisFile"], [4096, 0, 0, 0, 0, 0])
+    assert f["RuntimePars"].attrs["Iteration"] == 20
+    assert f["Units"].attrs["Unit length in cgs (U_L)"] == 100.
+    assert set(f["PartType0"].links()) == {"NeutralFractionH", "NumberDensity", "Temperature"}
+    assert f["PartType0"]["NumberDensity"].space.shape == (4096,)
+    assert f["Parameters"].attrs["SimulationBox:sides"] == "[3.086e+17 m, 3.086e+17 m, 3.086e+17 m]"
+
+
+def _messages(obj, mtype):
+    b = obj.f.buf
+    return [bytes(b[body:body + size]) for t, body, size, _ in obj.messages if t == mtype]
+
+
+def _attribute_message(obj, name):
+    for m in _messages(obj, 0x000C):
+        nsize = struct.unpack_from("<H", m, 2)[0]
+        if m[8:8 + nsize].split(b"\0")[0].decode() == name:
+            return m
+    raise KeyError(name)
+
+
+def check_structure(f):
+    """Everything a reader follows, checked against the format rules (superblock v0 / object header v1)."""
+    b = f.buf
+    eof = len(b)
+    assert f.eof == eof and f.base == 0 and f.leaf_k == 4 and f.internal_k == 16
+    seen = []
+
+    def check_header(o):
+        version, _, nmsg, refcount, hsize = struct.unpack_from("<BBHII", b, o.addr)
+        assert version == 1 and refcount == 1 and o.addr % 8 == 0
+        assert o.addr + 16 + hsize <= eof
+        total = 0
+        for t, body, size, flags in o.messages:
+            assert size % 8 == 0 and t != 0x0010        # one chunk, no continuation
+            total += 8 + size
+        assert total == hsize and len(o.messages) == nmsg
+        seen.append((o.addr, o.addr + 16 + hsize))
+
+    def check_group(o, path):
+        check_header(o)
+        btree, heap = o.symtab
+        assert btree % 8 == 0 and heap % 8 == 0
+        assert bytes(b[heap:heap + 4]) == b"HEAP" and b[heap + 4] == 0
+        dsize, free, daddr = struct.unpack_from("<QQQ", b, heap + 8)
+        assert daddr + dsize <= eof and dsize % 8 == 0
+        assert bytes(b[daddr:daddr + 8]) == b"\0" * 8                 # the empty name of B-tree key 0
+        assert free + 16 <= dsize
+        nxt, fsize = struct.unpack_from("<QQ", b, daddr + free)
+        assert nxt == 1 and free + fsize == dsize                     # one free block, up to the end
+        assert bytes(b[btree:btree + 4]) == b"TREE"
+        ntype, level, used = struct.unpack_from("<BBH", b, btree + 4)
+        left, right = struct.unpack_from("<QQ", b, btree + 8)
+        assert ntype == 0 and level == 0 and left == h5mini.UNDEF and right == h5mini.UNDEF and used <= 32
+        seen.append((btree, btree + 24 + 33 * 8 + 32 * 8))
+        seen.append((heap, heap + 32))
+        seen.append((daddr, daddr + dsize))
+
+        def name_at(off):
+            e = b.index(b"\0", daddr + off)
+            assert e < daddr + free
+            return bytes(b[daddr + off:e])
+
+        names = []
+        prev_key = struct.unpack_from("<Q", b, btree + 24)[0]
+        assert prev_key == 0
+        for k in range(used):
+            child, key = struct.unpack_from("<QQ", b, btree + 32 + 16 * k)
+            assert bytes(b[child:child + 4]) == b"SNOD" and b[child + 4] == 1
+            nsym = struct.unpack_from("<H", b, child + 6)[0]
+            assert 1 <= nsym <= 8
+            seen.append((child, child + 8 + 8 * 40))
+            these = []
+            for i in range(nsym):
+                noff, oaddr, ctype, _ = struct.unpack_from("<QQII", b, child + 8 + 40 * i)
+                these.append(name_at(noff))
+                sub = h5mini.Obj(f, oaddr)
+                if sub.symtab is not None:
+                    assert ctype == 1 and struct.unpack_from("<QQ", b, child + 8 + 40 * i + 24) == sub.symtab
+                else:
+                    assert ctype == 0
+            assert name_at(key) == these[-1]                          # key k+1 = largest name in child k
+            if names:
+                assert these[0] > names[-1]
+            names += these
+        assert names == sorted(names) and len(set(names)) == len(names)
+        for nm, addr in o.links().items():
+            sub = h5mini.Obj(f, addr)
+            if sub.symtab is not None:
+                check_group(sub, path + "/" + nm)
+            else:
+                check_header(sub)
+                assert [t for t, *_ in sub.messages] == [0x0001, 0x0003, 0x0005, 0x0008, 0x0012]
+                kind, a, s = sub.layout
+                n = int(np.prod(sub.space.shape)) * sub.dtype.size
+                assert kind == "contiguous" and s == n and a % 8 == 0 and a + n <= eof
+                seen.append((a, a + ((n + 7) & ~7)))
+
+    root_name_off, root_addr, ctype, _ = f.root_entry
+    assert root_name_off == 0 and ctype == 1 and root_addr == 96
+    assert struct.unpack_from("<QQ", b, 56 + 24) == f.symtab
+    check_group(f, "")
+    # the blocks tile the file exactly: no overlap, no hole
+    seen.sort()
+    assert seen[0][0] == 96
+    for (a0, a1), (b0, b1) in zip(seen, seen[1:]):
+        assert a1 == b0, (a0, a1, b0, b1)
+    assert seen[-1][1] == eof
+
+
+def _paramfile(tmp_path, ncell, extra=""):
+    pf = tmp_path / "snap.param"
+    pf.write_text("SimulationBox:\n  anchor: [-5. pc, -5. pc, -5. pc]\n  sides: [10. pc, 10. pc, 10. pc]\n"
+                  "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n"
+                  f"  number of cells: [{ncell[0]}, {ncell[1]}, {ncell[2]}]\n" + extra)
+    return pf
+
+
+def test_default_snapshot_is_the_reference_layout_and_reads_back_bit_for_bit(host, tmp_path):
+    ncell = (6, 5, 4)
+    n = int(np.prod(ncell))
+    rng = np.random.default_rng(3)
+    dens, T, x = rng.uniform(1e6, 1e9, n), rng.uniform(100., 3e4, n), rng.uniform(0., 1., (14, n))
+    p = host.ParameterFile(_paramfile(tmp_path, ncell))
+    name = p.write_snapshot(tmp_path, 20, dens, T, x)
+    p.close()
+    assert name == str(tmp_path / "snapshot020.hdf5")          # Utilities::compose_filename, padding 3
+    f = h5mini.File(name)
+    check_structure(f)
+    ref = h5mini.File(GOLD / "taskbased.hdf5")
+    assert f.link_order == ref.link_order                      # the reference's seven groups
+    # default fields without hydro: Coordinates, NumberDensity, NeutralFractionH (DensityGridWriterFields.hpp:176-230)
+    pt = f["PartType0"]
+    assert set(pt.links()) == {"Coordinates", "NumberDensity", "NeutralFractionH"}
+    assert np.array_equal(pt["NumberDensity"].read(), dens)
+    assert np.array_equal(pt["NeutralFractionH"].read(), x[0])
+    # Coordinates = cell midpoint - box anchor, cell order ix*ny*nz + iy*nz + iz
+    cs = [10. * PC / k for k in ncell]
+    ix, iy, iz = np.meshgrid(*[np.arange(k) for k in ncell], indexing="ij")
+    mid = np.stack([(-5. * PC + cs[d] * i.reshape(-1) + 0.5 * cs[d]) - (-5. * PC) for d, i in enumerate((ix, iy, iz))], 1)
+    assert np.array_equal(pt["Coordinates"].read(), mid)
+    h = f["Header"].attrs
+    assert list(f["Header"].attr_order) == list(ref["Header"].attr_order)
+    assert np.array_equal(h["NumPart_ThisFile"], [n, 0, 0, 0, 0, 0]) and np.array_equal(h["NumPart_Total"], [n, 0, 0, 0, 0, 0])
+    assert h["Time"] == 0.
+    assert list(f["Units"].attr_order) == list(ref["Units"].attr_order) and f["Units"].attrs == ref["Units"].attrs
+    assert list(f["RuntimePars"].attr_order) == ["Creation time", "Iteration"] and f["RuntimePars"].attrs["Iteration"] == 20
+    par = f["Parameters"].attrs
+    assert par["DensityGrid:number of cells"] == "[6, 5, 4]" and par["DensityGridWriter:type"] == "Gadget"
+    assert par["SimulationBox:sides"] == ref["Parameters"].attrs["SimulationBox:sides"]
+    # byte for byte what libhdf5 wrote for the same attributes (same box, same iteration)
+    for group, names in (("Header", ["BoxSize", "Dimension", "Flag_Entropy_ICs", "MassTable", "NumFilesPerSnapshot",
+                                     "NumPart_Total_HighWord", "Time"]),
+                         ("Units", list(ref["Units"].attr_order)), ("RuntimePars", ["Iteration"]),
+                         ("Parameters", ["SimulationBox:sides", "SimulationBox:periodicity"])):
+        for nm in names:
+            assert _attribute_message(f[group], nm) == _attribute_message(ref[group], nm), (group, nm)
+    # a string attribute of the same length as the reference's time stamp has the same encoding around the text
+    mine, theirs = _attribute_message(f["RuntimePars"], "Creation time"), _attribute_message(ref["RuntimePars"], "Creation time")
+    assert len(mine) == len(theirs) and mine[:40] == theirs[:40]
+    # group object headers: the symbol-table message has the library's encoding
+    assert _messages(f["Header"], 0x0011)[0][:0] == b"" and len(_messages(f["Header"], 0x0011)[0]) == 16
+
+
+def test_dataset_headers_are_byte_identical_to_a_contiguous_dataset_of_the_library(host, tmp_path):
+    """test/python_test.hdf5 holds /PartType0/Coordinates (64 x 3 doubles, contiguous): a 4 x 4 x 4 grid gives the
+    same shape, so dataspace, datatype and fill-value messages must be the same bytes, the layout message the same
+    up to the address."""
+    ncell = (4, 4, 4)
+    p = host.ParameterFile(_paramfile(tmp_path, ncell))
+    name = p.write_snapshot(tmp_path, 1, np.ones(64), np.ones(64), np.ones((14, 64)))
+    p.close()
+    f = h5mini.File(name)
+    check_structure(f)
+    mine, lib = f["PartType0"]["Coordinates"], h5mini.File(GOLD / "python_test.hdf5")["PartType0"]["Coordinates"]
+    assert lib.layout[0] == "contiguous" and lib.space.shape == (64, 3)
+    for mtype in (0x0001, 0x0003, 0x0005):
+        assert _messages(mine, mtype) == _messages(lib, mtype), hex(mtype)
+    a, b_ = _messages(mine, 0x0008)[0], _messages(lib, 0x0008)[0]
+    assert a[:2] == b_[:2] and a[10:] == b_[10:] and len(a) == len(b_)   # version 3, contiguous, size 1536, padding
+    flags = {t: fl for t, _, _, fl in mine.messages}
+    assert flags == {t: fl for t, _, _, fl in lib.messages if t in flags}
+
+
+def test_all_fields_and_the_ion_flag_quirk(host, tmp_path):
+    ncell = (7, 3, 5)
+    n = int(np.prod(ncell))
+    rng = np.random.default_rng(8)
+    dens, T, x = rng.uniform(1e6, 1e9, n), rng.uniform(100., 3e4, n), rng.uniform(0., 1., (14, n))
+    # S+++ is the last ion: its flag switches on every ion before it (ion_present shifts the flag word)
+    p = host.ParameterFile(_paramfile(tmp_path, ncell, "DensityGridWriter:\n  prefix: lex_\n  padding: 5\n"
+                                      "DensityGridWriterFields:\n  Temperature: 1\n  NeutralFractionS+++: 1\n"))
+    name = p.write_snapshot(tmp_path, 3, dens, T, x, time=2.5)
+    p.close()
+    assert name.endswith("lex_00003.hdf5")
+    f = h5mini.File(name)
+    check_structure(f)
+    pt = f["PartType0"]
+    ions = ["H", "He", "C+", "C++", "N", "N+", "N++", "O", "O+", "Ne", "Ne+", "S+", "S++", "S+++"]
+    assert set(pt.links()) == {"Coordinates", "NumberDensity", "Temperature"} | {"NeutralFraction" + i for i in ions}
+    assert len(f.btree_keys[pt.addr][0]) == 4                      # 17 links = 3 symbol nodes
+    for k, ion in enumerate(ions):
+        assert np.array_equal(pt["NeutralFraction" + ion].read(), x[k]), ion
+    assert np.array_equal(pt["Temperature"].read(), T) and f["Header"].attrs["Time"] == 2.5
+    # only He flagged: H (before it) comes along, nothing after it
+    p = host.ParameterFile(_paramfile(tmp_path, ncell, "DensityGridWriterFields:\n  NeutralFractionH: 0\n  NeutralFractionHe: 1\n"
+                                      "  Coordinates: 0\n"))
+    name = p.write_snapshot(tmp_path, 0, dens, T, x)
+    p.close()
+    f = h5mini.File(name)
+    check_structure(f)
+    assert set(f["PartType0"].links()) == {"NumberDensity", "NeutralFractionH", "NeutralFractionHe"}
+
+
+def test_writer_errors_and_ascii_type(host, tmp_path):
+    ncell = (2, 2, 2)
+    one = np.ones(8)
+    p = host.ParameterFile(_paramfile(tmp_path, ncell, "DensityGridWriter:\n  type: AsciiFile\n"))
+    name = p.write_snapshot(tmp_path, 2, one, one, np.ones((14, 8)))
+    p.close()
+    assert name.endswith("snapshot002.txt") and open(name).readline().startswith("#x (m)")
+    for block, msg in (("DensityGridWriter:\n  type: Gadget\n  compression: true\n", "compression"),
+                       ("DensityGridWriter:\n  type: Nope\n", "Unknown DensityGridWriter type"),
+                       ("DensityGridWriterFields:\n  CosmicRayFactor: 1\n", "CosmicRayFactor")):
+        p = host.ParameterFile(_paramfile(tmp_path, ncell, block))
+        with pytest.raises(Exception, match=msg):
+            p.write_snapshot(tmp_path, 0, one, one, np.ones((14, 8)))
+        p.close()
