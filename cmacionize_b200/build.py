@@ -67,9 +67,9 @@ def build_host(force: bool = False) -> Path:
     HOST_BIN.parent.mkdir(exist_ok=True)
     common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-pthread",
               "-I/usr/local/cuda/include"]  # nccl.h needs cuda_runtime.h for cudaStream_t
-    link = [f"-L{HERE}", "-lcmib", "-ldl", "-Wl,-rpath,$ORIGIN"]  # NCCL is dlopen-ed on demand
+    link = [f"-L{HERE}", "-lcmib", "-ldl", "-lz", "-Wl,-rpath,$ORIGIN"]  # NCCL is dlopen-ed on demand
     subprocess.check_call(common + ["-shared", str(HOST / "host_api.cpp"), "-o", str(HOST_LIB)] + link)
-    link_bin = [f"-L{HERE}", "-lcmib", "-ldl", "-Wl,-rpath,$ORIGIN/.."]
+    link_bin = [f"-L{HERE}", "-lcmib", "-ldl", "-lz", "-Wl,-rpath,$ORIGIN/.."]
     subprocess.check_call(common + [str(HOST / "CMacIonizeB200.cpp"), "-o", str(HOST_BIN)] + link_bin)
     print(f"built {HOST_LIB} and {HOST_BIN}")
     return HOST_LIB

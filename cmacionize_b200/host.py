@@ -212,3 +212,42 @@ class IonizationSimulation:
         if rc != 0:
             raise HostError(capi.lib.cmib_last_error().decode())
         return n, T, x, heat
+
+
+class HDF5Input:
+    """host/HDF5Reader.hpp through the C probes of libcmih (tests)."""
+
+    def __init__(self, filename):
+        self.filename = str(filename).encode()
+
+    def exists(self, path):
+        out = C.c_int(0)
+        _check(lib.cmih_hdf5_exists(self.filename, path.encode(), C.byref(out)))
+        return bool(out.value)
+
+    def attribute_names(self, path):
+        buf = C.create_string_buffer(1 << 18)
+        _check(lib.cmih_hdf5_attribute_names(self.filename, path.encode(), buf, C.c_int(1 << 18)))
+        return [l for l in buf.value.decode().split("\n") if l]
+
+    def string_attribute(self, path, name):
+        buf = C.create_string_buffer(1 << 16)
+        n = C.c_int(0)
+        _check(lib.cmih_hdf5_attribute(self.filename, path.encode(), name.encode(), 0, buf, C.c_int(1 << 16), None, 0, C.byref(n)))
+        return buf.value.decode()
+
+    def numeric_attribute(self, path, name):
+        v = np.empty(64)
+        n = C.c_int(0)
+        _check(lib.cmih_hdf5_attribute(self.filename, path.encode(), name.encode(), 1, None, 0,
+                                       v.ctypes.data_as(C.c_void_p), 64, C.byref(n)))
+        return v[:n.value].copy()
+
+    def dataset(self, path):
+        dims = (C.c_int64 * 4)()
+        ndim, count = C.c_int(0), C.c_int64(0)
+        _check(lib.cmih_hdf5_dataset(self.filename, path.encode(), None, C.c_int64(0), dims, C.byref(ndim), C.byref(count)))
+        out = np.empty(count.value)
+        _check(lib.cmih_hdf5_dataset(self.filename, path.encode(), out.ctypes.data_as(C.c_void_p), C.c_int64(count.value), dims,
+                                     C.byref(ndim), C.byref(count)))
+        return out.reshape([dims[k] for k in range(ndim.value)])

@@ -51,6 +51,7 @@
 
 #include "../../include/cmib.h"
 #include "Error.hpp"
+#include "HDF5Reader.hpp"
 #include "HDF5Writer.hpp"
 #include "ParameterFile.hpp"
 #include "RandomGenerator.hpp"
@@ -568,6 +569,130 @@ private:
   double r_ISM_, h_ISM_, n_0_, kpc_;
 };
 
+/* A snapshot of an earlier run as initial condition (CMacIonizeSnapshotDensityFunction.cpp:108-470, :504-523):
+ * reads /Parameters (box, number of cells, grid type), /Units and /PartType0/{Coordinates, NumberDensity,
+ * Temperature, NeutralFraction<ion>} of a Gadget-style snapshot written by the reference or by this host layer
+ * (host/HDF5Reader.hpp, no HDF5 library) and returns, for a position, the values of the snapshot cell that
+ * contains it.  Cartesian snapshots place a cell by its coordinates, task-based ones by the subgrid order of
+ * the cells; snapshots of AMR / Voronoi grids are refused (those grids are outside the accelerated path), and
+ * so are the hydro variants (`use density`, `use pressure`). */
+class CMacIonizeSnapshotDensityFunction : public DensityFunction {
+public:
+  CMacIonizeSnapshotDensityFunction(std::string filename, bool use_density, bool use_pressure,
+                                    double initial_neutral_fraction)
+      : filename_(std::move(filename)), initial_neutral_fraction_(initial_neutral_fraction) {
+    if (use_density || use_pressure)
+      cmi_error("DensityFunction:use density / use pressure read hydro snapshots, which the B200 backend does not provide!");
+  }
+  explicit CMacIonizeSnapshotDensityFunction(ParameterFile &params)
+      : CMacIonizeSnapshotDensityFunction(params.get_filename("DensityFunction:filename"),
+                                          params.get_value<bool>("DensityFunction:use density", false),
+                                          params.get_value<bool>("DensityFunction:use pressure", false),
+                                          params.get_value<double>("DensityFunction:initial neutral fraction", 1.e-6)) {}
+  void initialize() override {
+    hdf5::HDF5Input file(filename_);
+    YAMLDictionary parameters;
+    for (const std::string &name : file.get_attribute_names("/Parameters"))
+      parameters.add_value(name, file.read_string_attribute("/Parameters", name));
+    anchor_ = parameters.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:anchor");
+    sides_ = parameters.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:sides");
+    ncell_ = parameters.get_value<std::array<uint32_t, 3>>("DensityGrid:number of cells");
+    const std::string type = parameters.has_value("DensityGrid:type") ? parameters.get_value<std::string>("DensityGrid:type")
+                                                                       : std::string("TaskBased");
+    if (type != "Cartesian" && type != "TaskBased")
+      cmi_error("Snapshot \"%s\" holds a %s grid; the B200 backend reads Cartesian and TaskBased snapshots!",
+                filename_.c_str(), type.c_str());
+    double unit_length_in_SI = 1., unit_density_in_SI = 1., unit_temperature_in_SI = 1.;
+    if (file.exists("/Units")) {
+      const double unit_length_in_cgs = file.read_double_attribute("/Units", "Unit length in cgs (U_L)")[0];
+      unit_temperature_in_SI = file.read_double_attribute("/Units", "Unit temperature in cgs (U_T)")[0];
+      unit_length_in_SI = UnitConverter::to_SI(QUANTITY_LENGTH, unit_length_in_cgs, "cm");
+      unit_density_in_SI = 1. / unit_length_in_SI / unit_length_in_SI / unit_length_in_SI;
+    }
+    if (!file.exists("/PartType0/NumberDensity"))
+      cmi_error("Snapshot \"%s\" holds no NumberDensity (hydro snapshots are not provided by the B200 backend)!", filename_.c_str());
+    if (!file.exists("/PartType0/Temperature"))
+      cmi_error("Snapshot \"%s\" holds no Temperature (switch on DensityGridWriterFields:Temperature in the run that writes it)!",
+                filename_.c_str());
+    std::vector<double> densities = file.read_dataset("/PartType0/NumberDensity");
+    std::vector<double> temperatures = file.read_dataset("/PartType0/Temperature");
+    const size_t n = densities.size();
+    const size_t ntot = (size_t)ncell_[0] * ncell_[1] * ncell_[2];
+    if (n != ntot || temperatures.size() != n)
+      cmi_error("Snapshot \"%s\": %zu cells in /PartType0, %zu in /Parameters!", filename_.c_str(), n, ntot);
+    std::vector<std::vector<double>> fractions(CMIB_NUM_IONS);
+    for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) {
+      const std::string name = std::string("/PartType0/NeutralFraction") + ion_symbol(ion);
+      if (file.exists(name)) fractions[ion] = file.read_dataset(name);
+      else fractions[ion].assign(n, initial_neutral_fraction_);
+      if (fractions[ion].size() != n) cmi_error("Snapshot \"%s\": %s has the wrong size!", filename_.c_str(), name.c_str());
+    }
+    for (size_t i = 0; i < n; ++i) {
+      densities[i] *= unit_density_in_SI;
+      temperatures[i] *= unit_temperature_in_SI;
+    }
+    /* slot of snapshot cell i in the ix*ny*nz + iy*nz + iz order */
+    std::vector<size_t> slot(n);
+    if (type == "Cartesian") {
+      std::vector<uint64_t> dims;
+      std::vector<double> x = file.read_dataset("/PartType0/Coordinates", &dims);
+      if (dims.size() != 2 || dims[0] != n || dims[1] != 3) cmi_error("Snapshot \"%s\": bad Coordinates!", filename_.c_str());
+      for (size_t i = 0; i < n; ++i) {
+        size_t idx[3];
+        for (int k = 0; k < 3; ++k) {
+          idx[k] = (size_t)(ncell_[k] * (x[3 * i + k] * unit_length_in_SI) / sides_[k]);
+          if (idx[k] >= ncell_[k]) cmi_error("Snapshot \"%s\": cell %zu lies outside the box!", filename_.c_str(), i);
+        }
+        slot[i] = (idx[0] * ncell_[1] + idx[1]) * ncell_[2] + idx[2];
+      }
+    } else {
+      const auto nsub = parameters.get_value<std::array<uint32_t, 3>>("DensitySubGridCreator:number of subgrids");
+      const size_t nb[3] = {ncell_[0] / nsub[0], ncell_[1] / nsub[1], ncell_[2] / nsub[2]};
+      const size_t nbtot = nb[0] * nb[1] * nb[2];
+      for (size_t six = 0; six < nsub[0]; ++six)
+        for (size_t siy = 0; siy < nsub[1]; ++siy)
+          for (size_t siz = 0; siz < nsub[2]; ++siz) {
+            const size_t subgrid = (six * nsub[1] + siy) * nsub[2] + siz;
+            for (size_t cix = 0; cix < nb[0]; ++cix)
+              for (size_t ciy = 0; ciy < nb[1]; ++ciy)
+                for (size_t ciz = 0; ciz < nb[2]; ++ciz) {
+                  const size_t cell = subgrid * nbtot + (cix * nb[1] + ciy) * nb[2] + ciz;
+                  if (cell >= n) cmi_error("Snapshot \"%s\": subgrids do not match the number of cells!", filename_.c_str());
+                  slot[cell] = ((six * nb[0] + cix) * ncell_[1] + (siy * nb[1] + ciy)) * ncell_[2] + (siz * nb[2] + ciz);
+                }
+          }
+    }
+    values_.assign(n, DensityValues());
+    std::vector<char> filled(n, 0);
+    for (size_t i = 0; i < n; ++i) {
+      DensityValues &v = values_[slot[i]];
+      v.number_density = densities[i];
+      v.temperature = temperatures[i];
+      for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) v.ionic_fraction[ion] = fractions[ion][i];
+      filled[slot[i]] = 1;
+    }
+    for (size_t i = 0; i < n; ++i)
+      if (!filled[i])
+        cmi_error("No values found for cell (%zu, %zu, %zu)!", i / ((size_t)ncell_[1] * ncell_[2]),
+                  (i / ncell_[2]) % ncell_[1], i % ncell_[2]);
+  }
+  DensityValues operator()(const Vec3 &x) override {
+    size_t idx[3];
+    for (int k = 0; k < 3; ++k) {
+      idx[k] = (size_t)(ncell_[k] * (x[k] - anchor_[k]) / sides_[k]);
+      if (idx[k] >= ncell_[k]) cmi_error("Position outside the box of snapshot \"%s\"!", filename_.c_str());
+    }
+    return values_[(idx[0] * ncell_[1] + idx[1]) * ncell_[2] + idx[2]];
+  }
+
+private:
+  std::string filename_;
+  double initial_neutral_fraction_;
+  Vec3 anchor_, sides_;
+  std::array<uint32_t, 3> ncell_;
+  std::vector<DensityValues> values_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -580,8 +705,9 @@ struct DensityFunctionFactory {
     if (type == "DiscIC") return new DiscICDensityFunction(params);
     if (type == "DiscPatch") return new DiscPatchDensityFunction(params);
     if (type == "SpiralGalaxy") return new SpiralGalaxyDensityFunction(params);
+    if (type == "CMacIonizeSnapshot") return new CMacIonizeSnapshotDensityFunction(params);
     cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile, "
-              "Interpolated, CoredDMProfile, DiscIC, DiscPatch and SpiralGalaxy)!",
+              "Interpolated, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy and CMacIonizeSnapshot)!",
               type.c_str());
   }
 };

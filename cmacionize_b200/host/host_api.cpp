@@ -210,6 +210,7 @@ int cmih_write_snapshot(void *h, const char *output_folder, uint32_t iteration, 
   CMIH_TRY({
     ParameterFile &p = *static_cast<ParameterFile *>(h);
     const SimulationBox box(p);
+    p.get_value<std::string>("DensityGrid:type", "Cartesian"); /* as the driver does: part of the used values */
     CartesianCells cells(box, p.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}));
     if ((int64_t)cells.get_number_of_cells() != n) throw std::runtime_error("wrong number of cells");
     std::copy(dens, dens + n, cells.number_density.begin());
@@ -222,6 +223,51 @@ int cmih_write_snapshot(void *h, const char *output_folder, uint32_t iteration, 
     if (auto *a = dynamic_cast<AsciiFileDensityGridWriter *>(writer.get())) name = a->filename(iteration);
     strncpy(filename, name.c_str(), nfilename - 1);
     filename[nfilename - 1] = 0;
+  });
+}
+/* host/HDF5Reader.hpp probes: a dataset as doubles (returns its element count; shape in dims[0..ndim)) ... */
+int cmih_hdf5_dataset(const char *filename, const char *path, double *out, int64_t capacity, int64_t *dims, int *ndim,
+                      int64_t *count) {
+  CMIH_TRY({
+    hdf5::HDF5Input file(filename);
+    std::vector<uint64_t> shape;
+    const std::vector<double> v = file.read_dataset(path, &shape);
+    *count = (int64_t)v.size();
+    *ndim = (int)shape.size();
+    for (size_t k = 0; k < shape.size() && k < 4; ++k) dims[k] = (int64_t)shape[k];
+    if ((int64_t)v.size() <= capacity) std::copy(v.begin(), v.end(), out);
+  });
+}
+/* ... the attribute names of an object, one per line ... */
+int cmih_hdf5_attribute_names(const char *filename, const char *path, char *out, int n) {
+  CMIH_TRY({
+    hdf5::HDF5Input file(filename);
+    std::string all;
+    for (const std::string &name : file.get_attribute_names(path)) all += name + "\n";
+    strncpy(out, all.c_str(), n - 1);
+    out[n - 1] = 0;
+  });
+}
+/* ... and one attribute: kind 0 = string -> text, kind 1 = numbers -> values[0..count) */
+int cmih_hdf5_attribute(const char *filename, const char *path, const char *name, int kind, char *text, int ntext,
+                        double *values, int capacity, int *count) {
+  CMIH_TRY({
+    hdf5::HDF5Input file(filename);
+    if (kind == 0) {
+      const std::string v = file.read_string_attribute(path, name);
+      strncpy(text, v.c_str(), ntext - 1);
+      text[ntext - 1] = 0;
+    } else {
+      const std::vector<double> v = file.read_double_attribute(path, name);
+      *count = (int)v.size();
+      for (int k = 0; k < *count && k < capacity; ++k) values[k] = v[k];
+    }
+  });
+}
+int cmih_hdf5_exists(const char *filename, const char *path, int *out) {
+  CMIH_TRY({
+    hdf5::HDF5Input file(filename);
+    *out = file.exists(path) ? 1 : 0;
   });
 }
 /* AbundanceModelFactory on the parameter file -> He C N O Ne S relative to H */

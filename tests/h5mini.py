@@ -219,6 +219,19 @@ class Obj:
             return False
 
     # ---- datasets ----
+    def _filters(self):
+        """ids of the filter pipeline (message 0x000B, version 1), in pipeline order"""
+        b = self.f.buf
+        for mtype, body, _, _ in self.messages:
+            if mtype == 0x000B:
+                n, q, ids = b[body + 1], body + 8, []
+                for _k in range(n):
+                    fid, nlen, _fl, ncd = struct.unpack_from("<HHHH", b, q)
+                    ids.append(fid)
+                    q += 8 + _pad8(nlen) + 4 * (ncd + (ncd & 1))
+                return ids
+        return []
+
     def read(self):
         if self.layout is None or self.dtype is None or self.space is None:
             raise H5Error("not a dataset")
@@ -254,9 +267,15 @@ class Obj:
                     walk(child)
                     continue
                 raw = bytes(b[child:child + csize])
-                if any(m[0] == 0x000B for m in self.messages) and fmask == 0:
-                    import zlib
-                    raw = zlib.decompress(raw)   # the reference's writer only ever adds deflate
+                for fid in reversed(self._filters()):
+                    if fid == 1:
+                        import zlib
+                        raw = zlib.decompress(raw)
+                    elif fid == 2:   # shuffle: byte b of element i sits at b * count + i
+                        es = self.dtype.size
+                        raw = np.frombuffer(raw, dtype=np.uint8).reshape(es, -1).T.tobytes()
+                    else:
+                        raise H5Error(f"filter {fid} not supported")
                 if len(raw) != int(np.prod(cdims[:nd])) * self.dtype.size:
                     raise H5Error("unsupported chunk filter")
                 c = np.frombuffer(raw, dtype=self.dtype.dtype).reshape(cdims[:nd])

@@ -116,6 +116,39 @@ IonizationSimulation:
     assert (x0 == 1e-6).all()
 
 
+def test_run_restarts_from_its_own_snapshot(host, tmp_path):
+    """DensityFunction type CMacIonizeSnapshot (CMacIonizeSnapshotDensityFunction.cpp) on a snapshot this backend
+    wrote: the initial grid of the second run is the final grid of the first, cell for cell."""
+    nc, npk, nit = 16, 100000, 4
+    first = tmp_path / "first.param"
+    first.write_text(STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=5, extra=f"""DensityGridWriter:
+  type: Gadget
+  prefix: first_
+DensityGridWriterFields:
+  Temperature: 1
+IonizationSimulation:
+  output folder: {tmp_path}
+"""))
+    sim = host.IonizationSimulation(first, write_output=True)
+    sim.initialize()
+    sim.run()
+    n1, T1, x1, _ = sim.fields()
+    sim.close()
+    snap = tmp_path / f"first_{nit:03d}.hdf5"
+    assert snap.exists()
+    second = tmp_path / "second.param"
+    text = STROMGREN_PARAM.format(nc=nc, npk=npk, nit=1, seed=6, extra="")
+    block = "  type: Homogeneous\n  density: 100. cm^-3\n  temperature: 8000. K\n"
+    assert block in text
+    second.write_text(text.replace(block, f"  type: CMacIonizeSnapshot\n  filename: {snap}\n"))
+    sim = host.IonizationSimulation(second)
+    sim.initialize()
+    n2, T2, x2, _ = sim.fields()
+    sim.close()
+    assert np.array_equal(n2, n1) and np.array_equal(T2, T1) and np.array_equal(x2[0], x1[0])
+    assert x2[0].min() < 1e-3 and x2[0].max() > 0.9
+
+
 def test_two_gpu_driver_equals_one_gpu(host, tmp_path):
     """C++ driver on 2 GPUs (packets split by global id, one ncclAllReduce per iteration, replicated
     state update) == the same parameter file on 1 GPU: same packets, sums equal up to order."""

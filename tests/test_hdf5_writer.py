@@ -290,3 +290,109 @@ def test_writer_errors_and_ascii_type(host, tmp_path):
         with pytest.raises(Exception, match=msg):
             p.write_snapshot(tmp_path, 0, one, one, np.ones((14, 8)))
         p.close()
+
+
+# ---------------------------------------------------------------- reading snapshots (host/HDF5Reader.hpp)
+def test_cpp_reader_equals_the_python_reader_on_files_of_the_real_library(host):
+    """chunked + shuffle + deflate datasets of a snapshot written by the reference, chunked and attribute data of
+    test/test.hdf5 (float32 / uint64 / 2-D), contiguous data of test/python_test.hdf5"""
+    for name, paths in (("taskbased.hdf5", ["/PartType0/NumberDensity", "/PartType0/NeutralFractionH", "/PartType0/Temperature"]),
+                        ("test.hdf5", ["/PartType0/Density", "/PartType0/ParticleIDs", "/PartType0/Coordinates",
+                                       "/PartType0/Velocities", "/PartType4/Coordinates"]),
+                        ("python_test.hdf5", ["/PartType0/Coordinates"])):
+        f, h = h5mini.File(GOLD / name), host.HDF5Input(GOLD / name)
+        for p in paths:
+            a = f[p].read()
+            b = h.dataset(p)
+            assert a.shape == b.shape and np.array_equal(a.astype(np.float64), b), (name, p)
+    h, f = host.HDF5Input(GOLD / "test.hdf5"), h5mini.File(GOLD / "test.hdf5")
+    assert h.exists("/HydroScheme") and h.exists("/PartType0/Density") and not h.exists("/NonExistingGroup")
+    assert h.attribute_names("/HydroScheme") == f["HydroScheme"].attr_order and len(h.attribute_names("/HydroScheme")) == 15
+    assert h.string_attribute("/HydroScheme", "Scheme") == "Gadget-2 version of SPH (Springel 2005)"
+    assert np.array_equal(h.numeric_attribute("/Header", "NumPart_ThisFile"), [100, 0, 0, 0, 1, 0])
+    assert abs(h.numeric_attribute("/HydroScheme", "CFL parameter")[0] - 0.1) < 1e-7
+    t = host.HDF5Input(GOLD / "taskbased.hdf5")
+    assert t.string_attribute("/Parameters", "SimulationBox:sides") == "[3.086e+17 m, 3.086e+17 m, 3.086e+17 m]"
+    x = t.dataset("/PartType0/NeutralFractionH")
+    assert t.dataset("/PartType0/NumberDensity").tolist() == [1e8] * 4096 and 0. < x.min() < 1e-5 and x.max() == 1.
+    with pytest.raises(Exception, match="does not exist"):
+        h.dataset("/PartType0/Nope")
+    with pytest.raises(Exception, match="not an HDF5 file"):
+        host.HDF5Input(ROOT / "tests" / "golden" / "reference_fixtures.npz").exists("/x")
+
+
+def _midpoints(ncell, half):
+    cs = [2 * half / k for k in ncell]
+    ix, iy, iz = np.meshgrid(*[np.arange(k) for k in ncell], indexing="ij")
+    return np.stack([-half + cs[d] * i.reshape(-1) + 0.5 * cs[d] for d, i in enumerate((ix, iy, iz))], 1)
+
+
+def test_snapshot_density_function_round_trip_and_resampling(host, tmp_path):
+    """DensityFunction type CMacIonizeSnapshot on a snapshot of this host layer: the same grid gets its cells back
+    bit for bit; a coarser grid gets the snapshot cell that contains each midpoint
+    (CMacIonizeSnapshotDensityFunction.cpp:504-523)."""
+    ncell = (6, 4, 8)
+    n = int(np.prod(ncell))
+    rng = np.random.default_rng(21)
+    dens, T, x = rng.uniform(1e6, 1e9, n), rng.uniform(100., 3e4, n), rng.uniform(0., 1., (14, n))
+    p = host.ParameterFile(_paramfile(tmp_path, ncell, "DensityGridWriterFields:\n  Temperature: 1\n  NeutralFractionHe: 1\n"))
+    snap = p.write_snapshot(tmp_path, 4, dens, T, x)
+    p.close()
+    again = tmp_path / "again.param"
+    again.write_text(_paramfile(tmp_path, ncell).read_text() + f"DensityFunction:\n  type: CMacIonizeSnapshot\n  filename: {snap}\n")
+    p = host.ParameterFile(again)
+    d2, T2, x2 = p.density_function(_midpoints(ncell, 5 * PC))
+    p.close()
+    assert np.array_equal(d2, dens) and np.array_equal(T2, T) and np.array_equal(x2, x[0])
+    coarse = (3, 2, 2)
+    p = host.ParameterFile(again)
+    d3, T3, x3 = p.density_function(_midpoints(coarse, 5 * PC))
+    p.close()
+    m = _midpoints(coarse, 5 * PC)
+    idx = [np.floor((m[:, d] + 5 * PC) / (10 * PC) * ncell[d]).astype(int) for d in range(3)]
+    flat = (idx[0] * ncell[1] + idx[1]) * ncell[2] + idx[2]
+    assert np.array_equal(d3, dens[flat]) and np.array_equal(T3, T[flat]) and np.array_equal(x3, x[0][flat])
+    # a snapshot without temperatures cannot restart a run: said so
+    p = host.ParameterFile(_paramfile(tmp_path, ncell))
+    bare = p.write_snapshot(tmp_path, 9, dens, T, x)
+    p.close()
+    bad = tmp_path / "bad.param"
+    bad.write_text(_paramfile(tmp_path, ncell).read_text() + f"DensityFunction:\n  type: CMacIonizeSnapshot\n  filename: {bare}\n")
+    p = host.ParameterFile(bad)
+    with pytest.raises(Exception, match="holds no Temperature"):
+        p.density_function(_midpoints(ncell, 5 * PC))
+    p.close()
+
+
+def test_snapshot_density_function_on_a_snapshot_of_the_reference(host, tmp_path):
+    """test/taskbased.hdf5: written by the reference's task-based driver (subgrid cell order, chunked + shuffled +
+    deflated datasets): a Stromgren sphere comes back, ionised at the source and neutral in the corners."""
+    f = h5mini.File(GOLD / "taskbased.hdf5")
+    par = f["Parameters"].attrs
+    nsub = [int(v) for v in par["DensitySubGridCreator:number of subgrids"].strip("[]").split(",")]
+    ncell = [int(v) for v in par["DensityGrid:number of cells"].strip("[]").split(",")]
+    assert "DensityGrid:type" not in par and ncell == [16, 16, 16]
+    pf = tmp_path / "restart.param"
+    pf.write_text(f"SimulationBox:\n  anchor: {par['SimulationBox:anchor']}\n  sides: {par['SimulationBox:sides']}\n"
+                  "  periodicity: [false, false, false]\nDensityGrid:\n  type: Cartesian\n  number of cells: [16, 16, 16]\n"
+                  f"DensityFunction:\n  type: CMacIonizeSnapshot\n  filename: {GOLD / 'taskbased.hdf5'}\n")
+    half = 0.5 * 3.086e17
+    m = _midpoints(ncell, half)
+    p = host.ParameterFile(pf)
+    dens, T, xH = p.density_function(m)
+    p.close()
+    assert (dens == 1e8).all() and (T == 8000.).all()
+    raw = f["PartType0"]["NeutralFractionH"].read()
+    # the subgrid order of TaskBased snapshots (CMacIonizeSnapshotDensityFunction.cpp:372-418)
+    nb = [ncell[d] // nsub[d] for d in range(3)]
+    grid = np.empty(ncell)
+    k = 0
+    for six in range(nsub[0]):
+        for siy in range(nsub[1]):
+            for siz in range(nsub[2]):
+                blk = raw[k:k + nb[0] * nb[1] * nb[2]].reshape(nb)
+                grid[six * nb[0]:(six + 1) * nb[0], siy * nb[1]:(siy + 1) * nb[1], siz * nb[2]:(siz + 1) * nb[2]] = blk
+                k += blk.size
+    assert np.array_equal(xH, grid.reshape(-1))
+    r = np.sqrt((m ** 2).sum(1))
+    assert xH[r < 0.3 * half].max() < 1e-3 and xH[r > 1.2 * half].min() > 0.9
