@@ -184,10 +184,18 @@ def cpu_reference_measure(full_packets: int, sample_packets: int, steps: int, wa
         threads = sim.threads
         sim.close()
     shoot, update, prep = float(np.mean(shoot)), float(np.mean(update)), float(np.mean(prep))
+    cpu_model = "unknown"
+    try:
+        for l in open("/proc/cpuinfo"):
+            if l.startswith("model name"):
+                cpu_model = l.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
     rate_shoot = sample_packets / shoot
     t_full = full_packets / rate_shoot + update + prep
     return {
-        "value": full_packets / t_full, "unit": UNIT, "cores": threads, "kind": "reference",
+        "value": full_packets / t_full, "unit": UNIT, "cores": threads, "cpu_model": cpu_model, "kind": "reference",
         "sample": (f"unmodified reference (oracle/_ref, OpenMP, {threads} threads) on lexingtonHII20 64^3: "
                    f"{steps} steady-state iterations of {sample_packets:.0e} packets after {warmup} warm-up "
                    f"iterations (shoot {shoot:.3f} s = {rate_shoot:.3e} packets/s, state update {update:.3f} s, "
