@@ -214,6 +214,23 @@ class IonizationSimulation:
         return n, T, x, heat
 
 
+def write_particle_snapshot(filename, pos, m, h, rho, T=None, xH=None, periodic=-1, boxsize=(0., 0., 0.),
+                            units_cgs=(0., 0., 0.), unit_time_cgs=1., time=0., sfr=None, stars=None):
+    """a Gadget-style SPH snapshot from particle arrays (host/HDF5Writer.hpp): input for the GadgetSnapshot
+    density function and source distribution.  periodic < 0: no /RuntimePars group; units_cgs = (0, 0, 0): no /Units
+    group; stars = (positions, formation times, masses) -> /PartType4; sfr -> /PartType0/StarFormationRate"""
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+    pos, m, h, rho, T, xH, sfr = f(pos), f(m), f(h), f(rho), f(T), f(xH), f(sfr)
+    sp, sf, sm = (f(a) for a in stars) if stars is not None else (None, None, None)
+    vp = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    box = np.ascontiguousarray(boxsize, dtype=np.float64)
+    _check(lib.cmih_write_particle_snapshot(str(filename).encode(), C.c_int64(m.size), vp(pos), vp(m), vp(h), vp(rho), vp(T),
+                                            vp(xH), C.c_int(periodic), vp(box), C.c_double(units_cgs[0]),
+                                            C.c_double(units_cgs[1]), C.c_double(units_cgs[2]), C.c_double(unit_time_cgs),
+                                            C.c_double(time), vp(sfr), C.c_int64(0 if sm is None else sm.size), vp(sp), vp(sf),
+                                            vp(sm)))
+
+
 class HDF5Input:
     """host/HDF5Reader.hpp through the C probes of libcmih (tests)."""
 

@@ -90,7 +90,7 @@ public:
     std::vector<double> out(n);
     const uint64_t esize = o.type.size;
     if (o.layout_class == 1 || o.layout_class == 0) {
-      if (o.layout_class == 1 && o.layout_address == UNDEFINED) fail("dataset \"" + path + "\" has no storage");
+      if (o.layout_class == 1 && o.layout_address == UNDEFINED) return out; /* never written: the fill value (0) */
       if (o.layout_size < n * esize) fail("dataset \"" + path + "\": layout smaller than the dataspace");
       check(o.layout_address, n * esize);
       convert(o.type, data_ + o.layout_address, n, out.data());

@@ -30,6 +30,7 @@
  */
 #pragma once
 #include <array>
+#include <cfloat>
 #include <chrono>
 #include <cinttypes>
 #include <cmath>
@@ -693,6 +694,222 @@ private:
   std::vector<DensityValues> values_;
 };
 
+/* SPH snapshot as initial condition (GadgetSnapshotDensityFunction.cpp:60-372): gas particles of a Gadget / SWIFT
+ * style HDF5 snapshot (/PartType0/{Coordinates, Masses, SmoothingLength, Density, [Temperature], [NeutralFractionH]},
+ * /Units, /RuntimePars:PeriodicBoundariesOn, /Header:BoxSize; fallback units from the parameter file), read with
+ * host/HDF5Reader.hpp.  A cell gets the cubic-spline kernel sums at its midpoint (:315-359):
+ *   density = sum_i m_i W(r_i / h_i, h_i) / 1.6737236e-27,  T = sum_i m_i W T_i / rho_i,  x_H = sum_i m_i W x_i / density
+ * over the particles whose kernel contains the midpoint.  The reference finds those with an octree, one cell at a
+ * time; here particles are binned on a uniform grid of the largest smoothing length, a query visits the 27 bins
+ * around it (same particles, other order of the sum: rounding-level differences, tests/test_hdf5_writer.py). */
+class GadgetSnapshotDensityFunction : public DensityFunction {
+public:
+  GadgetSnapshotDensityFunction(const std::string &name, bool fallback_periodic, double fallback_unit_length_in_SI,
+                                double fallback_unit_mass_in_SI, double fallback_unit_temperature_in_SI,
+                                bool use_neutral_fraction, double fallback_temperature, bool comoving_integration,
+                                double hubble_parameter, Log *log = nullptr) {
+    hdf5::HDF5Input file(name);
+    periodic_ = fallback_periodic;
+    if (file.exists("/RuntimePars")) {
+      periodic_ = file.read_double_attribute("/RuntimePars", "PeriodicBoundariesOn")[0] != 0.;
+    } else if (log) {
+      log->write_warning("No RuntimePars found!");
+    }
+    Vec3 sides = {0., 0., 0.};
+    if (periodic_) {
+      const std::vector<double> boxsize = file.read_double_attribute("/Header", "BoxSize");
+      /* a scalar BoxSize stands for a cube (HDF5Tools::read_attribute< CoordinateVector<> > needs 3 values) */
+      if (boxsize.size() != 3) cmi_error("Snapshot \"%s\": /Header:BoxSize must hold 3 values!", name.c_str());
+      sides = {boxsize[0], boxsize[1], boxsize[2]};
+    }
+    double unit_length_in_SI = fallback_unit_length_in_SI, unit_mass_in_SI = fallback_unit_mass_in_SI,
+           unit_temperature_in_SI = fallback_unit_temperature_in_SI;
+    if (file.exists("/Units")) {
+      const double unit_length_in_cgs = file.read_double_attribute("/Units", "Unit length in cgs (U_L)")[0];
+      const double unit_mass_in_cgs = file.read_double_attribute("/Units", "Unit mass in cgs (U_M)")[0];
+      unit_temperature_in_SI = file.read_double_attribute("/Units", "Unit temperature in cgs (U_T)")[0];
+      unit_length_in_SI = UnitConverter::to_SI(QUANTITY_LENGTH, unit_length_in_cgs, "cm");
+      unit_mass_in_SI = UnitConverter::to_SI(QUANTITY_MASS, unit_mass_in_cgs, "g");
+    } else {
+      if (log) log->write_warning("No Units group found! Using fallback units.");
+      if (unit_length_in_SI == 0.) unit_length_in_SI = 1.;
+      if (unit_mass_in_SI == 0.) unit_mass_in_SI = 1.;
+      if (unit_temperature_in_SI == 0.) unit_temperature_in_SI = 1.;
+    }
+    if (comoving_integration) {
+      unit_length_in_SI /= hubble_parameter;
+      unit_mass_in_SI /= hubble_parameter;
+    }
+    const double unit_length_in_SI_squared = unit_length_in_SI * unit_length_in_SI;
+    const double unit_density_in_SI = unit_mass_in_SI / unit_length_in_SI / unit_length_in_SI_squared;
+    std::vector<uint64_t> dims;
+    positions_ = file.read_dataset("/PartType0/Coordinates", &dims);
+    if (dims.size() != 2 || dims[1] != 3) cmi_error("Snapshot \"%s\": bad /PartType0/Coordinates!", name.c_str());
+    const size_t n = dims[0];
+    masses_ = file.read_dataset("/PartType0/Masses");
+    smoothing_lengths_ = file.read_dataset("/PartType0/SmoothingLength");
+    densities_ = file.read_dataset("/PartType0/Density");
+    if (file.exists("/PartType0/Temperature")) {
+      temperatures_ = file.read_dataset("/PartType0/Temperature");
+    } else {
+      if (fallback_temperature == 0.) fallback_temperature = 8000.;
+      temperatures_.assign(n, fallback_temperature);
+    }
+    if (use_neutral_fraction && file.exists("/PartType0/NeutralFractionH"))
+      neutral_fractions_ = file.read_dataset("/PartType0/NeutralFractionH");
+    if (masses_.size() != n || smoothing_lengths_.size() != n || densities_.size() != n || temperatures_.size() != n ||
+        (!neutral_fractions_.empty() && neutral_fractions_.size() != n))
+      cmi_error("Snapshot \"%s\": the gas datasets have different lengths!", name.c_str());
+    for (size_t i = 0; i < n; ++i) {
+      for (int k = 0; k < 3; ++k) positions_[3 * i + k] *= unit_length_in_SI;
+      masses_[i] *= unit_mass_in_SI;
+      smoothing_lengths_[i] *= unit_length_in_SI;
+      densities_[i] *= unit_density_in_SI;
+      temperatures_[i] *= unit_temperature_in_SI;
+    }
+    for (int k = 0; k < 3; ++k) sides_[k] = sides[k] * unit_length_in_SI;
+    build_bins();
+  }
+  explicit GadgetSnapshotDensityFunction(ParameterFile &params, Log *log = nullptr)
+      : GadgetSnapshotDensityFunction(
+            params.get_filename("DensityFunction:filename"),
+            params.get_value<bool>("DensityFunction:fallback periodic flag", false),
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:fallback unit length", "0. m"),
+            params.get_physical_value<QUANTITY_MASS>("DensityFunction:fallback unit mass", "0. kg"),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:fallback unit temperature", "0. K"),
+            params.get_value<bool>("DensityFunction:use neutral fraction", false),
+            params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:fallback initial temperature", "0. K"),
+            params.get_value<bool>("DensityFunction:comoving integration flag", false),
+            params.get_value<double>("DensityFunction:hubble parameter", 0.7), log) {}
+
+  /* CubicSplineKernel::kernel_evaluate (CubicSplineKernel.hpp:44-59) */
+  static double kernel_evaluate(double u, double h) {
+    const double KC1 = 2.546479089470, KC2 = 15.278874536822, KC5 = 5.092958178941;
+    if (u < 1.) {
+      if (u < 0.5) return (KC1 + KC2 * (u - 1.) * u * u) / (h * h * h);
+      return KC5 * (1. - u) * (1. - u) * (1. - u) / (h * h * h);
+    }
+    return 0.;
+  }
+  DensityValues operator()(const Vec3 &x) override {
+    double density = 0., temperature = 0., neutral_fraction = neutral_fractions_.empty() ? -1. : 0.;
+    /* per axis: the bins that can hold a particle whose kernel reaches x (its own bin and the two next to it) */
+    int list[3][3], nlist[3];
+    for (int k = 0; k < 3; ++k) {
+      const int bq = (int)std::floor((x[k] - bin_anchor_[k]) / bin_side_[k]);
+      nlist[k] = 0;
+      if (periodic_) {
+        for (int d = -1; d <= 1; ++d) {
+          const int b = wrap(bq + d, k);
+          bool seen = false;
+          for (int q = 0; q < nlist[k]; ++q) seen = seen || list[k][q] == b;
+          if (!seen) list[k][nlist[k]++] = b;
+        }
+      } else if (bq >= -1 && bq <= nbin_[k] + 1) { /* the last bin also holds the particles up to the upper edge */
+        const int cq = std::min(std::max(bq, 0), nbin_[k] - 1);
+        for (int b = std::max(cq - 1, 0); b <= std::min(cq + 1, nbin_[k] - 1); ++b) list[k][nlist[k]++] = b;
+      }
+    }
+    for (int a = 0; a < nlist[0]; ++a)
+      for (int b = 0; b < nlist[1]; ++b)
+        for (int c3 = 0; c3 < nlist[2]; ++c3) {
+          const size_t bin = ((size_t)list[0][a] * nbin_[1] + list[1][b]) * nbin_[2] + list[2][c3];
+          for (size_t p = bin_start_[bin]; p < bin_start_[bin + 1]; ++p) {
+            const size_t i = bin_particles_[p];
+            double c[3];
+            for (int k = 0; k < 3; ++k) {
+              c[k] = x[k] - positions_[3 * i + k];
+              if (periodic_) { /* Box::periodic_distance (Box.hpp:114-127) */
+                if (2 * c[k] < -sides_[k]) c[k] += sides_[k];
+                if (2 * c[k] >= sides_[k]) c[k] -= sides_[k];
+              }
+            }
+            const double r = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+            const double h = smoothing_lengths_[i];
+            const double u = r / h;
+            if (!(u < 1.)) continue;
+            const double splineval = masses_[i] * kernel_evaluate(u, h);
+            density += splineval;
+            temperature += splineval * temperatures_[i] / densities_[i];
+            if (neutral_fraction >= 0.) neutral_fraction += splineval * neutral_fractions_[i];
+          }
+        }
+    DensityValues v;
+    v.number_density = density / 1.6737236e-27;
+    v.temperature = temperature;
+    v.ionic_fraction[0] = (neutral_fraction >= 0.) ? neutral_fraction / density : 1.e-6;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+  /* GadgetSnapshotDensityFunction::get_total_hydrogen_number (:366-372) */
+  double get_total_hydrogen_number() const {
+    double mtot = 0.;
+    for (double m : masses_) mtot += m;
+    return mtot / 1.6737236e-27;
+  }
+  size_t get_number_of_particles() const { return masses_.size(); }
+
+private:
+  int wrap(int b, int k) const {
+    if (!periodic_) return b;
+    const int n = nbin_[k];
+    return ((b % n) + n) % n;
+  }
+  /* bins of side >= the largest smoothing length: the kernel of a particle reaches at most the neighbouring bins.
+   * Periodic boxes are tiled exactly (per-axis bin side = box side / number of bins). */
+  void build_bins() {
+    const size_t n = masses_.size();
+    double hmax = 0.;
+    Vec3 lo = {DBL_MAX, DBL_MAX, DBL_MAX}, hi = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (size_t i = 0; i < n; ++i) {
+      hmax = std::max(hmax, smoothing_lengths_[i]);
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = std::min(lo[k], positions_[3 * i + k]);
+        hi[k] = std::max(hi[k], positions_[3 * i + k]);
+      }
+    }
+    if (n == 0 || !(hmax > 0.)) cmi_error("The snapshot holds no gas particles with a smoothing length!");
+    if (periodic_) {
+      for (int k = 0; k < 3; ++k) {
+        lo[k] = 0.;
+        hi[k] = sides_[k];
+      }
+    }
+    /* at most ~8 bins per particle: memory stays O(n) when the largest kernel is tiny against the box */
+    double side = hmax;
+    const double volume = (hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    if (volume > 0.) side = std::max(side, std::cbrt(volume / (8. * (double)n)));
+    for (int k = 0; k < 3; ++k) {
+      nbin_[k] = std::max(1, (int)std::floor((hi[k] - lo[k]) / side));
+      bin_side_[k] = periodic_ ? sides_[k] / nbin_[k] : side;
+    }
+    bin_anchor_ = lo;
+    const size_t nb = (size_t)nbin_[0] * nbin_[1] * nbin_[2];
+    std::vector<size_t> count(nb + 1, 0), which(n);
+    for (size_t i = 0; i < n; ++i) {
+      int b[3];
+      for (int k = 0; k < 3; ++k) {
+        b[k] = (int)std::floor((positions_[3 * i + k] - bin_anchor_[k]) / bin_side_[k]);
+        b[k] = periodic_ ? wrap(b[k], k) : std::min(std::max(b[k], 0), nbin_[k] - 1);
+      }
+      which[i] = ((size_t)b[0] * nbin_[1] + b[1]) * nbin_[2] + b[2];
+      ++count[which[i] + 1];
+    }
+    for (size_t b = 0; b < nb; ++b) count[b + 1] += count[b];
+    bin_start_ = count;
+    bin_particles_.resize(n);
+    std::vector<size_t> fill(bin_start_.begin(), bin_start_.end() - 1);
+    for (size_t i = 0; i < n; ++i) bin_particles_[fill[which[i]]++] = i;
+  }
+
+  bool periodic_ = false;
+  Vec3 sides_ = {0., 0., 0.};
+  std::vector<double> positions_, masses_, smoothing_lengths_, densities_, temperatures_, neutral_fractions_;
+  Vec3 bin_side_ = {0., 0., 0.}, bin_anchor_ = {0., 0., 0.};
+  int nbin_[3] = {1, 1, 1};
+  std::vector<size_t> bin_start_, bin_particles_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -706,8 +923,9 @@ struct DensityFunctionFactory {
     if (type == "DiscPatch") return new DiscPatchDensityFunction(params);
     if (type == "SpiralGalaxy") return new SpiralGalaxyDensityFunction(params);
     if (type == "CMacIonizeSnapshot") return new CMacIonizeSnapshotDensityFunction(params);
+    if (type == "GadgetSnapshot") return new GadgetSnapshotDensityFunction(params, log);
     cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile, "
-              "Interpolated, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy and CMacIonizeSnapshot)!",
+              "Interpolated, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy, CMacIonizeSnapshot and GadgetSnapshot)!",
               type.c_str());
   }
 };
@@ -1057,6 +1275,101 @@ private:
   RandomGenerator random_generator_;
 };
 
+/* Sources from an SPH snapshot (GadgetSnapshotPhotonSourceDistribution.cpp:60-325): the star particles of
+ * /PartType4 inside the simulation box (or, with `use gas`, the star-forming gas particles of /PartType0 with a
+ * stellar mass SFR x cutoff age), each with the UV luminosity of its age and mass.  UVLuminosityFunction:
+ * RateBased (RateBasedUVLuminosityFunction.hpp: mass x rate while younger than the cutoff age, the factory's
+ * default); IMFBased needs the stellar-population sampling of the RHD drivers and is refused.  Read with
+ * host/HDF5Reader.hpp. */
+class GadgetSnapshotPhotonSourceDistribution : public PhotonSourceDistribution {
+public:
+  explicit GadgetSnapshotPhotonSourceDistribution(ParameterFile &params, Log *log = nullptr) {
+    const std::string filename = params.get_filename("PhotonSourceDistribution:filename");
+    const std::string formation_time_name =
+        params.get_value<std::string>("PhotonSourceDistribution:formation time name", "FormationTime");
+    const Vec3 anchor = params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:anchor");
+    const Vec3 sides = params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:sides");
+    const std::string lf_type = params.get_value<std::string>("UVLuminosityFunction:type", "RateBased");
+    if (lf_type != "RateBased")
+      cmi_error("Unknown UVLuminosityFunction type: \"%s\" (the B200 backend provides RateBased).", lf_type.c_str());
+    const double UV_rate_per_mass_unit =
+        params.get_physical_value<QUANTITY_FREQUENCY_PER_MASS>("UVLuminosityFunction:UV rate per mass unit", "2.49428e16 s^-1 kg^-1");
+    const double lf_cutoff_age = params.get_physical_value<QUANTITY_TIME>("UVLuminosityFunction:cutoff age", "5. Myr");
+    const double fallback_unit_length_in_SI = params.get_physical_value<QUANTITY_LENGTH>("PhotonSourceDistribution:fallback unit length", "0. m");
+    const double fallback_unit_time_in_SI = params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:fallback unit time", "0. s");
+    const double fallback_unit_mass_in_SI = params.get_physical_value<QUANTITY_MASS>("PhotonSourceDistribution:fallback unit mass", "0. kg");
+    const double cutoff_age = params.get_physical_value<QUANTITY_TIME>("PhotonSourceDistribution:cutoff age", "5. Myr");
+    const bool use_gas = params.get_value<bool>("PhotonSourceDistribution:use gas", false);
+    const double SFR_unit = params.get_physical_value<QUANTITY_MASS_RATE>("PhotonSourceDistribution:SFR unit", "0. kg s^-1");
+    const bool comoving_integration = params.get_value<bool>("PhotonSourceDistribution:comoving integration flag", false);
+    const double hubble_parameter = params.get_value<double>("PhotonSourceDistribution:hubble parameter", 0.7);
+    auto luminosity_function = [&](double age, double mass) { return age <= lf_cutoff_age ? mass * UV_rate_per_mass_unit : 0.; };
+
+    hdf5::HDF5Input file(filename);
+    const double snaptime = file.read_double_attribute("/Header", "Time")[0];
+    double unit_length_in_SI = fallback_unit_length_in_SI, unit_time_in_SI = fallback_unit_time_in_SI,
+           unit_mass_in_SI = fallback_unit_mass_in_SI;
+    if (file.exists("/Units")) {
+      unit_length_in_SI = UnitConverter::to_SI(QUANTITY_LENGTH, file.read_double_attribute("/Units", "Unit length in cgs (U_L)")[0], "cm");
+      unit_time_in_SI = file.read_double_attribute("/Units", "Unit time in cgs (U_t)")[0];
+      unit_mass_in_SI = UnitConverter::to_SI(QUANTITY_MASS, file.read_double_attribute("/Units", "Unit mass in cgs (U_M)")[0], "g");
+    } else {
+      if (log) log->write_warning("No Units group found! Using fallback units.");
+      if (unit_length_in_SI == 0.) unit_length_in_SI = 1.;
+      if (unit_time_in_SI == 0.) unit_time_in_SI = 1.;
+      if (unit_mass_in_SI == 0.) unit_mass_in_SI = 1.;
+    }
+    if (comoving_integration) {
+      unit_length_in_SI /= hubble_parameter;
+      unit_mass_in_SI /= hubble_parameter;
+      unit_time_in_SI /= hubble_parameter;
+    }
+    auto inside = [&](const Vec3 &v) { /* Box::inside (Box.hpp:191-195) */
+      return v[0] >= anchor[0] && v[0] < anchor[0] + sides[0] && v[1] >= anchor[1] && v[1] < anchor[1] + sides[1] &&
+             v[2] >= anchor[2] && v[2] < anchor[2] + sides[2];
+    };
+    total_luminosity_ = 0.;
+    const std::string group = use_gas ? "/PartType0" : "/PartType4";
+    std::vector<uint64_t> dims;
+    const std::vector<double> x = file.read_dataset(group + "/Coordinates", &dims);
+    if (dims.size() != 2 || dims[1] != 3) cmi_error("Snapshot \"%s\": bad %s/Coordinates!", filename.c_str(), group.c_str());
+    const size_t n = dims[0];
+    std::vector<double> a, b;
+    if (use_gas) {
+      a = file.read_dataset("/PartType0/StarFormationRate");
+    } else {
+      a = file.read_dataset("/PartType4/" + formation_time_name);
+      b = file.read_dataset("/PartType4/Masses");
+    }
+    if (a.size() != n || (!use_gas && b.size() != n)) cmi_error("Snapshot \"%s\": datasets of %s differ in length!", filename.c_str(), group.c_str());
+    const double unit_SFR_in_SI = (SFR_unit == 0.) ? unit_mass_in_SI / unit_time_in_SI : SFR_unit;
+    for (size_t i = 0; i < n; ++i) {
+      const Vec3 position = {x[3 * i] * unit_length_in_SI, x[3 * i + 1] * unit_length_in_SI, x[3 * i + 2] * unit_length_in_SI};
+      double UV_luminosity = 0.;
+      if (use_gas) {
+        if (a[i] > 0. && inside(position)) UV_luminosity = luminosity_function(0., a[i] * unit_SFR_in_SI * cutoff_age);
+      } else if (inside(position)) {
+        UV_luminosity = luminosity_function((snaptime - a[i]) * unit_time_in_SI, b[i] * unit_mass_in_SI);
+      }
+      if (UV_luminosity > 0.) {
+        positions_.push_back(position);
+        luminosities_.push_back(UV_luminosity);
+        total_luminosity_ += UV_luminosity;
+      }
+    }
+    if (log) log->write_status("Found ", positions_.size(), " active sources, with a total luminosity of ", total_luminosity_, " s^-1.");
+  }
+  size_t get_number_of_sources() const override { return positions_.size(); }
+  Vec3 get_position(size_t i) override { return positions_[i]; }
+  double get_weight(size_t i) const override { return luminosities_[i] / total_luminosity_; }
+  double get_total_luminosity() const override { return total_luminosity_; }
+
+private:
+  std::vector<Vec3> positions_;
+  std::vector<double> luminosities_;
+  double total_luminosity_ = 0.;
+};
+
 struct PhotonSourceDistributionFactory {
   static PhotonSourceDistribution *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("PhotonSourceDistribution:type", "SingleStar");
@@ -1068,9 +1381,10 @@ struct PhotonSourceDistributionFactory {
     if (type == "DiscPatch") return new DiscPatchPhotonSourceDistribution(params);
     if (type == "DwarfGalaxy") return new DwarfGalaxyPhotonSourceDistribution(params);
     if (type == "SILCC") return new SILCCPhotonSourceDistribution(params);
+    if (type == "GadgetSnapshot") return new GadgetSnapshotPhotonSourceDistribution(params, log);
     if (type == "None") return nullptr;
     cmi_error("Unknown PhotonSourceDistribution type: \"%s\" (the B200 backend provides SingleStar, AsciiFile, "
-              "AsciiFileTable, UniformRandom, DiscPatch, DwarfGalaxy and SILCC)!",
+              "AsciiFileTable, UniformRandom, DiscPatch, DwarfGalaxy, SILCC and GadgetSnapshot)!",
               type.c_str());
   }
 };

@@ -53,7 +53,8 @@ enum Quantity {
   QUANTITY_ACCELERATION, QUANTITY_ANGLE, QUANTITY_DENSITY, QUANTITY_ENERGY, QUANTITY_FLUX,
   QUANTITY_FREQUENCY, QUANTITY_LENGTH, QUANTITY_MASS, QUANTITY_NUMBER_DENSITY, QUANTITY_REACTION_RATE,
   QUANTITY_SURFACE_AREA, QUANTITY_TEMPERATURE, QUANTITY_TIME, QUANTITY_VELOCITY, QUANTITY_VOLUME,
-  QUANTITY_SURFACE_DENSITY /* appended: the integer values are part of the cmih_paramfile_get_physical probe */
+  QUANTITY_SURFACE_DENSITY, /* appended: the integer values are part of the cmih_paramfile_get_physical probe */
+  QUANTITY_MASS_RATE, QUANTITY_FREQUENCY_PER_MASS
 };
 
 /* a unit = SI value of one unit + exponents of (length, time, mass, temperature, angle) */
@@ -118,6 +119,8 @@ public:
     case QUANTITY_REACTION_RATE: return "m^3 s^-1";
     case QUANTITY_SURFACE_AREA: return "m^2";
     case QUANTITY_SURFACE_DENSITY: return "kg m^-2";
+    case QUANTITY_MASS_RATE: return "kg s^-1";
+    case QUANTITY_FREQUENCY_PER_MASS: return "Hz kg^-1";
     case QUANTITY_TEMPERATURE: return "K";
     case QUANTITY_TIME: return "s";
     case QUANTITY_VELOCITY: return "m s^-1";

@@ -225,6 +225,49 @@ int cmih_write_snapshot(void *h, const char *output_folder, uint32_t iteration, 
     filename[nfilename - 1] = 0;
   });
 }
+/* a Gadget-style SPH snapshot from particle arrays through host/HDF5Writer.hpp (test input for GadgetSnapshot):
+ * periodic < 0 leaves /RuntimePars out, unit_length_in_cgs == 0 leaves /Units out; xH may be null */
+int cmih_write_particle_snapshot(const char *filename, int64_t N, const double *pos, const double *m, const double *h,
+                                 const double *rho, const double *T, const double *xH, int periodic, const double *boxsize,
+                                 double unit_length_in_cgs, double unit_mass_in_cgs, double unit_temperature_in_cgs,
+                                 double unit_time_in_cgs, double time, const double *sfr, int64_t Nstar, const double *star_pos,
+                                 const double *star_formation_time, const double *star_mass) {
+  CMIH_TRY({
+    hdf5::HDF5File file;
+    hdf5::Group &header = file.root().create_group("Header");
+    header.write_attribute("BoxSize", std::array<double, 3>{boxsize[0], boxsize[1], boxsize[2]});
+    std::vector<uint32_t> numpart(6, 0);
+    numpart[0] = (uint32_t)N;
+    numpart[4] = (uint32_t)Nstar;
+    header.write_attribute("NumPart_ThisFile", numpart);
+    header.write_attribute("Time", time);
+    if (periodic >= 0) file.root().create_group("RuntimePars").write_attribute("PeriodicBoundariesOn", int32_t(periodic));
+    if (unit_length_in_cgs != 0.) {
+      hdf5::Group &units = file.root().create_group("Units");
+      units.write_attribute("Unit length in cgs (U_L)", unit_length_in_cgs);
+      units.write_attribute("Unit mass in cgs (U_M)", unit_mass_in_cgs);
+      units.write_attribute("Unit temperature in cgs (U_T)", unit_temperature_in_cgs);
+      units.write_attribute("Unit time in cgs (U_t)", unit_time_in_cgs);
+    }
+    hdf5::Group &gas = file.root().create_group("PartType0");
+    const uint64_t n = (uint64_t)N;
+    gas.create_dataset("Coordinates", hdf5::Type::F64, {n, 3}, pos);
+    gas.create_dataset("Masses", hdf5::Type::F64, {n}, m);
+    gas.create_dataset("SmoothingLength", hdf5::Type::F64, {n}, h);
+    gas.create_dataset("Density", hdf5::Type::F64, {n}, rho);
+    if (T) gas.create_dataset("Temperature", hdf5::Type::F64, {n}, T);
+    if (xH) gas.create_dataset("NeutralFractionH", hdf5::Type::F64, {n}, xH);
+    if (sfr) gas.create_dataset("StarFormationRate", hdf5::Type::F64, {n}, sfr);
+    if (Nstar > 0) {
+      hdf5::Group &stars = file.root().create_group("PartType4");
+      const uint64_t ns = (uint64_t)Nstar;
+      stars.create_dataset("Coordinates", hdf5::Type::F64, {ns, 3}, star_pos);
+      stars.create_dataset("FormationTime", hdf5::Type::F64, {ns}, star_formation_time);
+      stars.create_dataset("Masses", hdf5::Type::F64, {ns}, star_mass);
+    }
+    file.write(filename);
+  });
+}
 /* host/HDF5Reader.hpp probes: a dataset as doubles (returns its element count; shape in dims[0..ndim)) ... */
 int cmih_hdf5_dataset(const char *filename, const char *path, double *out, int64_t capacity, int64_t *dims, int *ndim,
                       int64_t *count) {

@@ -346,6 +346,19 @@ def use_all_host_threads():
     return n
 
 
+def gadget_kernel_sums(pos, m, h, rho, T, xH, periodic, box_sides, queries):
+    """GadgetSnapshotDensityFunction::operator() composed from the reference's Octree + CubicSplineKernel on particle
+    arrays (SI) -> (number density, temperature, neutral fraction or -1) at the query points"""
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    pos, m, h, rho, T, q = f(pos), f(m), f(h), f(rho), f(T), f(queries)
+    xH = None if xH is None else f(xH)
+    box = f(box_sides)
+    out = np.empty((len(q), 3))
+    lib().cmi_ref_gadget_kernel_sums(C.c_int64(m.size), _p(pos), _p(m), _p(h), _p(rho), _p(T), None if xH is None else _p(xH),
+                                     C.c_int(1 if periodic else 0), _p(box), C.c_int64(len(q)), _p(q), _p(out))
+    return out[:, 0].copy(), out[:, 1].copy(), out[:, 2].copy()
+
+
 def convert(value, unit_from, unit_to):
     return float(lib().cmi_ref_convert(C.c_double(value), unit_from.encode(), unit_to.encode()))
 

@@ -40,6 +40,8 @@
 #include "AbundanceModelFactory.hpp"
 #include "CrossSectionsFactory.hpp"
 #include "ContinuousPhotonSourceFactory.hpp"
+#include "CubicSplineKernel.hpp"
+#include "Octree.hpp"
 #include "SimulationBox.hpp"
 #include "CartesianDensityGrid.hpp"
 #include "ChargeTransferRates.hpp"
@@ -862,6 +864,54 @@ int64_t cmi_ref_sph_mapping(const char *paramfile, const char *mapping_type, con
   }
   delete sph;
   return n;
+}
+
+/* The SPH kernel sum of GadgetSnapshotDensityFunction::operator() (GadgetSnapshotDensityFunction.cpp:315-359)
+ * on particle arrays handed in directly (the class itself only reads HDF5 files, and this build has no HDF5):
+ * the reference's Octree (built as the constructor does, :226-251, periodic or in the 1 % padded bounding box)
+ * finds the particles whose kernel contains a point, the reference's CubicSplineKernel weighs them.
+ * out[3q..3q+3) = number density, temperature, neutral fraction (or -1 without neutral fractions). */
+void cmi_ref_gadget_kernel_sums(int64_t N, const double *pos, const double *m, const double *h, const double *rho,
+                                const double *T, const double *xH, int periodic, const double *box_sides, int64_t nq,
+                                const double *q, double *out) {
+  std::vector< CoordinateVector<> > positions(N);
+  std::vector< double > hs(h, h + N);
+  CoordinateVector<> minpos(DBL_MAX), maxpos(-DBL_MAX);
+  for (int64_t i = 0; i < N; ++i) {
+    positions[i] = CoordinateVector<>(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+    minpos = CoordinateVector<>::min(minpos, positions[i]);
+    maxpos = CoordinateVector<>::max(maxpos, positions[i]);
+  }
+  Box<> pbox;
+  if (periodic) pbox = Box<>(CoordinateVector<>(), CoordinateVector<>(box_sides[0], box_sides[1], box_sides[2]));
+  Box<> box(pbox);
+  if (!periodic) {
+    CoordinateVector<> sides = maxpos - minpos;
+    const CoordinateVector<> anchor = minpos - 0.005 * sides;
+    sides *= 1.01;
+    box = Box<>(anchor, sides);
+  }
+  Octree octree(positions, box, periodic != 0);
+  octree.set_auxiliaries(hs, Octree::max< double >);
+  for (int64_t k = 0; k < nq; ++k) {
+    const CoordinateVector<> position(q[3 * k], q[3 * k + 1], q[3 * k + 2]);
+    double density = 0., temperature = 0., neutral_fraction = xH ? 0. : -1.;
+    const std::vector< uint_fast32_t > ngbs = octree.get_ngbs(position);
+    for (size_t i = 0; i < ngbs.size(); ++i) {
+      const uint_fast32_t index = ngbs[i];
+      double r;
+      if (!pbox.get_sides().x()) r = (position - positions[index]).norm();
+      else r = pbox.periodic_distance(position, positions[index]).norm();
+      const double u = r / hs[index];
+      const double splineval = m[index] * CubicSplineKernel::kernel_evaluate(u, hs[index]);
+      density += splineval;
+      temperature += splineval * T[index] / rho[index];
+      if (neutral_fraction >= 0.) neutral_fraction += splineval * xH[index];
+    }
+    out[3 * k] = density / 1.6737236e-27;
+    out[3 * k + 1] = temperature;
+    out[3 * k + 2] = (neutral_fraction >= 0.) ? neutral_fraction / density : -1.;
+  }
 }
 
 /* UnitConverter::to_SI for a quantity given by its SI unit name, e.g.

@@ -396,3 +396,140 @@ def test_snapshot_density_function_on_a_snapshot_of_the_reference(host, tmp_path
     assert np.array_equal(xH, grid.reshape(-1))
     r = np.sqrt((m ** 2).sum(1))
     assert xH[r < 0.3 * half].max() < 1e-3 and xH[r > 1.2 * half].min() > 0.9
+
+
+# ---------------------------------------------------------------- SPH snapshots (DensityFunction GadgetSnapshot)
+def _gadget_param(tmp_path, snapshot, anchor, sides, ncell, extra=""):
+    pf = tmp_path / "gadget.param"
+    pf.write_text(f"SimulationBox:\n  anchor: [{anchor[0]!r} m, {anchor[1]!r} m, {anchor[2]!r} m]\n"
+                  f"  sides: [{sides[0]!r} m, {sides[1]!r} m, {sides[2]!r} m]\n  periodicity: [false, false, false]\n"
+                  f"DensityGrid:\n  type: Cartesian\n  number of cells: [{ncell[0]}, {ncell[1]}, {ncell[2]}]\n"
+                  f"DensityFunction:\n  type: GadgetSnapshot\n  filename: {snapshot}\n" + extra)
+    return pf
+
+
+def _grid_midpoints(anchor, sides, ncell):
+    ax = [anchor[d] + sides[d] / ncell[d] * (np.arange(ncell[d]) + 0.5) for d in range(3)]
+    X, Y, Z = np.meshgrid(*ax, indexing="ij")
+    return np.stack([X.reshape(-1), Y.reshape(-1), Z.reshape(-1)], 1)
+
+
+def test_gadget_snapshot_density_function_on_the_reference_test_file(host, ref, tmp_path):
+    """test/test.hdf5 is the file of the reference's testGadgetSnapshotDensityFunction.cpp (100 gas particles,
+    periodic unit box, SI-like units, float32 data, a Temperature dataset that was never written): the kernel sums
+    at the cell midpoints against the reference's Octree + CubicSplineKernel composed as operator() does, and the
+    assertions of that test (hydrogen number of the 32^3 grid = that of the particles; average temperature 0)."""
+    f = h5mini.File(GOLD / "test.hdf5")
+    gas = f["PartType0"]
+    UL, UM = 100. * 0.01, 1000. * 0.001                           # Units group -> SI (cm, g)
+    pos = gas["Coordinates"].read().astype(np.float64) * UL
+    m = gas["Masses"].read().astype(np.float64) * UM
+    h = gas["SmoothingLength"].read().astype(np.float64) * UL
+    rho = gas["Density"].read().astype(np.float64) * (UM / UL / (UL * UL))
+    T = gas["Temperature"].read().astype(np.float64)
+    assert len(m) == 100 and (T == 0).all() and f["RuntimePars"].attrs["PeriodicBoundariesOn"][0] == 1
+    ncell = (12, 12, 12)
+    q = _grid_midpoints((0., 0., 0.), (1., 1., 1.), ncell)
+    p = host.ParameterFile(_gadget_param(tmp_path, GOLD / "test.hdf5", (0., 0., 0.), (1., 1., 1.), ncell))
+    dens, temp, xH = p.density_function(q)
+    p.close()
+    rd, rT, rx = ref.gadget_kernel_sums(pos, m, h, rho, np.ones(100), None, True, (1., 1., 1.), q)
+    assert (rd > 0).all() and (rx == -1).all()
+    assert np.abs(dens / rd - 1.).max() < 1e-13                    # same particles, another order of the sum
+    assert (temp == 0.).all() and (xH == 1e-6).all()
+    # testGadgetSnapshotDensityFunction.cpp:53-57 on its 32^3 grid
+    ncell = (32, 32, 32)
+    p = host.ParameterFile(_gadget_param(tmp_path, GOLD / "test.hdf5", (0., 0., 0.), (1., 1., 1.), ncell))
+    dens, temp, _ = p.density_function(_grid_midpoints((0., 0., 0.), (1., 1., 1.), ncell))
+    p.close()
+    total = (dens * (1. / 32) ** 3).sum()
+    assert abs(total / (m.sum() / 1.6737236e-27) - 1.) < 1e-4 and temp.mean() == 0.
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_gadget_snapshot_density_function_on_synthetic_particles(host, ref, tmp_path, periodic):
+    """clustered particles with a wide range of smoothing lengths, temperatures and neutral fractions, unit
+    conversion through /Units (kpc, 1e10 Msol: GADGET units), cells partly outside the particle cloud"""
+    rng = np.random.default_rng(17)
+    N = 3000
+    KPC, M10 = 3.086e19, 1.98855e40
+    box = np.array([8., 6., 5.])                                   # snapshot units (kpc)
+    centres = rng.uniform(1., 4., (6, 3))
+    pos = (centres[rng.integers(0, 6, N)] + rng.normal(0., 0.5, (N, 3)))
+    if periodic:
+        pos = np.mod(pos, box)
+    h = rng.uniform(0.05, 0.9, N)
+    m = rng.uniform(0.5, 2., N) * 1e-6
+    rho = rng.uniform(0.1, 10., N) * 1e-4
+    T = rng.uniform(1e2, 1e5, N)
+    xH = rng.uniform(0., 1., N)
+    snap = tmp_path / "sph.hdf5"
+    host.write_particle_snapshot(snap, pos, m, h, rho, T, xH, periodic=1 if periodic else -1, boxsize=box,
+                                 units_cgs=(KPC * 100., M10 * 1000., 1.))
+    UL, UM = (KPC * 100.) * 0.01, (M10 * 1000.) * 0.001           # what UnitConverter::to_SI does with cm, g
+    sp, sm, sh, srho = pos * UL, m * UM, h * UL, rho * (UM / UL / (UL * UL))
+    anchor = (0., 0., 0.) if periodic else tuple((pos.min(0) - 0.3) * UL)
+    sides = tuple(box * UL) if periodic else tuple((pos.max(0) - pos.min(0) + 0.6) * UL)
+    ncell = (14, 11, 9)
+    q = _grid_midpoints(anchor, sides, ncell)
+    for use_x in (False, True):
+        p = host.ParameterFile(_gadget_param(tmp_path, snap, anchor, sides, ncell,
+                                             "  use neutral fraction: true\n" if use_x else ""))
+        dens, temp, x = p.density_function(q)
+        p.close()
+        rd, rT, rx = ref.gadget_kernel_sums(sp, sm, sh, srho, T, xH if use_x else None, periodic, tuple(box * UL), q)
+        inside = rd > 0
+        assert inside.sum() > 0.3 * len(q) and (periodic or (~inside).sum() > 0)
+        assert np.array_equal(dens == 0, ~inside)
+        assert np.abs(dens[inside] / rd[inside] - 1.).max() < 1e-12
+        assert np.abs(temp[inside] / rT[inside] - 1.).max() < 1e-12 and (temp[~inside] == 0).all()
+        if use_x:
+            assert np.abs(x[inside] / rx[inside] - 1.).max() < 1e-12
+        else:
+            assert (x == 1e-6).all()
+
+
+def test_gadget_snapshot_source_distribution(host, tmp_path):
+    """testGadgetSnapshotPhotonSourceDistribution.cpp:89-107 on test/test.hdf5 (one star of unit mass in the middle
+    of the unit box, RateBased luminosity function with rate 2 and cutoff age 2 -> one source of luminosity 2), then
+    stars and star-forming gas of a synthetic snapshot against the rule written out in numpy."""
+    pf = tmp_path / "stars.param"
+    pf.write_text("SimulationBox:\n  anchor: [0. m, 0. m, 0. m]\n  sides: [1. m, 1. m, 1. m]\n"
+                  f"PhotonSourceDistribution:\n  type: GadgetSnapshot\n  filename: {GOLD / 'test.hdf5'}\n"
+                  "UVLuminosityFunction:\n  type: RateBased\n  UV rate per mass unit: 2. s^-1 kg^-1\n  cutoff age: 2. s\n")
+    p = host.ParameterFile(pf)
+    pos, w, lum = p.photon_source_distribution()
+    p.close()
+    assert pos.tolist() == [[0.5, 0.5, 0.5]] and w.tolist() == [1.] and lum == 2.
+    rng = np.random.default_rng(5)
+    N, NS = 400, 300
+    KPC, M10, MYR = 3.086e19, 1.98855e40, 3.154e13
+    gpos, spos = rng.uniform(-1., 11., (N, 3)), rng.uniform(-1., 11., (NS, 3))
+    sfr = np.where(rng.uniform(size=N) < 0.3, rng.uniform(0.1, 2., N), 0.)
+    form, smass = rng.uniform(0., 30., NS), rng.uniform(1e-7, 1e-6, NS)
+    snap = tmp_path / "galaxy.hdf5"
+    host.write_particle_snapshot(snap, gpos, np.ones(N), np.ones(N), np.ones(N), units_cgs=(KPC * 100., M10 * 1000., 1.),
+                                 unit_time_cgs=MYR, time=30., sfr=sfr, stars=(spos, form, smass))
+    UL, UM, UT = (KPC * 100.) * 0.01, (M10 * 1000.) * 0.001, MYR
+    box_lo, box_hi = np.zeros(3), np.full(3, 10. * KPC)
+    rate, cut = 2.49428e16, 5. * MYR
+    for use_gas in (False, True):
+        pf.write_text("SimulationBox:\n  anchor: [0. kpc, 0. kpc, 0. kpc]\n  sides: [10. kpc, 10. kpc, 10. kpc]\n"
+                      f"PhotonSourceDistribution:\n  type: GadgetSnapshot\n  filename: {snap}\n"
+                      + ("  use gas: true\n" if use_gas else ""))
+        p = host.ParameterFile(pf)
+        pos, w, lum = p.photon_source_distribution()
+        p.close()
+        if use_gas:
+            x = gpos * UL
+            L = np.where(sfr > 0, sfr * (UM / UT) * cut * rate, 0.)
+        else:
+            x = spos * UL
+            L = np.where((30. - form) * UT <= cut, smass * UM * rate, 0.)
+        keep = (L > 0) & ((x >= box_lo) & (x < box_hi)).all(1)
+        assert 5 < keep.sum() < len(keep)
+        assert np.array_equal(pos, x[keep])
+        tot = 0.
+        for v in L[keep]:
+            tot += v
+        assert lum == tot and np.array_equal(w, L[keep] / tot)
