@@ -24,7 +24,7 @@ ION_NAMES = ["H_n", "He_n", "C_p1", "C_p2", "N_n", "N_p1", "N_p2", "O_n", "O_p1"
 CROSS_SECTIONS_FIXED_VALUE, CROSS_SECTIONS_VERNER = 0, 1
 RECOMBINATION_FIXED_VALUE, RECOMBINATION_VERNER = 0, 1
 SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK, SPECTRUM_UNIFORM, SPECTRUM_TABULATED = 0, 1, 2, 3
-CONTINUOUS_NONE, CONTINUOUS_ISOTROPIC, CONTINUOUS_PLANAR, CONTINUOUS_DISTANT_STAR = 0, 1, 2, 3
+CONTINUOUS_NONE, CONTINUOUS_ISOTROPIC, CONTINUOUS_PLANAR, CONTINUOUS_DISTANT_STAR, CONTINUOUS_EXTENDED_DISC = 0, 1, 2, 3, 4
 REEMISSION_NONE, REEMISSION_PHYSICAL, REEMISSION_FIXED_VALUE = 0, 1, 2
 
 # CMIB_LIB: load another build of the same ABI (A/B timing of kernel variants)
@@ -199,6 +199,9 @@ class Context:
     def set_distant_star_position(self, position):
         pos = _f64(position).reshape(3)
         _check(lib.cmib_set_distant_star_position(self._h, _p(pos)))
+
+    def set_extended_disc_geometry(self, normal_axis, origin, scale_height):
+        _check(lib.cmib_set_extended_disc_geometry(self._h, C.c_int(normal_axis), C.c_double(origin), C.c_double(scale_height)))
 
     def set_planar_source_geometry(self, normal_axis, intercept, anchor, sides):
         a, sd = _f64(anchor).reshape(2), _f64(sides).reshape(2)

@@ -109,7 +109,7 @@ struct cmib_context {
   TemperatureParams tp;
   double luminosity = 0.; /* discrete + continuous */
   double discrete_luminosity = 0., continuous_luminosity = 0.;
-  bool planar_geometry_set = false, star_position_set = false;
+  bool planar_geometry_set = false, star_position_set = false, disc_geometry_set = false;
   DevBuf<double> d_cont_planck;
   DevBuf<uint16_t> d_cont_planck_guide;
   std::vector<double> h_cont_planck;
@@ -906,6 +906,23 @@ int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double i
     ctx->src.planar_sides[k] = sides[k];
   }
   ctx->planar_geometry_set = true;
+  ctx->disc_geometry_set = false; /* the two geometries share the axis and the intercept */
+  return 0;
+}
+
+int cmib_set_extended_disc_geometry(cmib_context *ctx, int normal_axis, double origin, double scale_height) {
+  CHECK_CTX(ctx);
+  if (normal_axis < 0 || normal_axis > 2) CMIB_FAIL("normal axis must be 0, 1 or 2");
+  if (!(scale_height > 0.)) CMIB_FAIL("the scale height of the disc must be positive");
+  /* a disc whose Gaussian never reaches the box would redraw forever: ask for 10 sigma at most */
+  const double bottom = ctx->geom.anchor[normal_axis], top = bottom + ctx->geom.sides[normal_axis];
+  if (origin < bottom - 10. * scale_height || origin > top + 10. * scale_height)
+    CMIB_FAIL("the disc lies more than 10 scale heights outside the simulation box");
+  ctx->src.planar_axis = normal_axis;
+  ctx->src.planar_intercept = origin;
+  ctx->src.disc_scale_height = scale_height;
+  ctx->disc_geometry_set = true;
+  ctx->planar_geometry_set = false; /* the two geometries share the axis and the intercept */
   return 0;
 }
 
@@ -918,8 +935,11 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
     ctx->update_source_weights();
     return 0;
   }
-  if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR && kind != CMIB_CONTINUOUS_DISTANT_STAR)
+  if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR && kind != CMIB_CONTINUOUS_DISTANT_STAR &&
+      kind != CMIB_CONTINUOUS_EXTENDED_DISC)
     CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (kind == CMIB_CONTINUOUS_EXTENDED_DISC && !ctx->disc_geometry_set)
+    CMIB_FAIL("call cmib_set_extended_disc_geometry before selecting the ExtendedDisc continuous source");
   if (kind == CMIB_CONTINUOUS_DISTANT_STAR && !ctx->star_position_set)
     CMIB_FAIL("call cmib_set_distant_star_position before selecting the DistantStar continuous source");
   if (kind == CMIB_CONTINUOUS_PLANAR && !ctx->planar_geometry_set)
@@ -931,7 +951,9 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
                          spectrum_kind, spectrum_param))
     return 1;
   ctx->src.continuous_kind = (kind == CMIB_CONTINUOUS_PLANAR) ? CONTINUOUS_PLANAR
-                             : (kind == CMIB_CONTINUOUS_DISTANT_STAR ? CONTINUOUS_DISTANT_STAR : CONTINUOUS_ISOTROPIC);
+                             : (kind == CMIB_CONTINUOUS_DISTANT_STAR)
+                                   ? CONTINUOUS_DISTANT_STAR
+                                   : (kind == CMIB_CONTINUOUS_EXTENDED_DISC ? CONTINUOUS_EXTENDED_DISC : CONTINUOUS_ISOTROPIC);
   ctx->continuous_luminosity = luminosity;
   ctx->update_source_weights();
   return 0;

@@ -32,7 +32,8 @@ namespace cmib {
 
 enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1, SPECTRUM_UNIFORM = 2, SPECTRUM_TABULATED = 3 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
-enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2, CONTINUOUS_DISTANT_STAR = 3 };
+enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2, CONTINUOUS_DISTANT_STAR = 3,
+                             CONTINUOUS_EXTENDED_DISC = 4 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
@@ -69,6 +70,10 @@ struct SourceModel {
    * planar_intercept, rectangle anchor + [0, sides) in the two other coordinates (ascending index) */
   int planar_axis;
   double planar_intercept, planar_anchor[2], planar_sides[2];
+  /* CONTINUOUS_EXTENDED_DISC (ExtendedDiscContinuousPhotonSource.hpp:60-210): emission from the volume of a disc:
+   * coordinate[planar_axis] Gaussian around planar_intercept with this scale height, uniform over the box in the
+   * two other coordinates */
+  double disc_scale_height;
   /* CONTINUOUS_DISTANT_STAR (DistantStarContinuousPhotonSource.hpp:60-90): a star outside the box;
    * star_exposed[d] = -1 / +1 / 0: the star lies below / above / within the box along d */
   double star_position[3];
@@ -205,6 +210,42 @@ CMIB_HD void planar_incoming(int axis, double intercept, const double *anchor, c
   const double s2 = 1. - cost * cost;
   const double sint = sqrt(s2 > 0. ? s2 : 0.);
   const double phi = 2. * M_PI * u[3];
+  double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &sinp, &cosp);
+#else
+  cosp = cos(phi);
+  sinp = sin(phi);
+#endif
+  dx = sint * cosp;
+  dy = sint * sinp;
+  dz = cost;
+}
+
+/*
+ * ExtendedDiscContinuousPhotonSource::get_random_incoming_direction (.hpp:148-197): a point uniform over the
+ * box in the two in-plane coordinates (ascending index), a Gaussian height (Box-Muller, one deviate pair per
+ * trial, redrawn while it falls outside the box), then an isotropic direction.  `uniform()` supplies the deviates.
+ */
+template <class Uniform>
+CMIB_HD void extended_disc_incoming(const GridGeom &g, int axis, double origin, double scale_height, Uniform &&uniform,
+                                    double &px, double &py, double &pz, double &dx, double &dy, double &dz) {
+  const int i0 = (axis + 1) % 3, i1 = (axis + 2) % 3;
+  const int lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+  double p[3];
+  p[lo] = g.anchor[lo] + uniform() * g.sides[lo];
+  p[hi] = g.anchor[hi] + uniform() * g.sides[hi];
+  const double bottom = g.anchor[axis], top = g.anchor[axis] + g.sides[axis];
+  for (int trial = 0; trial < (1 << 24); ++trial) {
+    const double rho = scale_height * sqrt(-2. * log(uniform()));
+    p[axis] = rho * cos(2. * M_PI * uniform()) + origin;
+    if (!(p[axis] < bottom || p[axis] > top)) break;
+  }
+  px = p[0]; py = p[1]; pz = p[2];
+  const double cost = 2. * uniform() - 1.;
+  const double s2 = 1. - cost * cost;
+  const double sint = sqrt(s2 > 0. ? s2 : 0.);
+  const double phi = 2. * M_PI * uniform();
   double sinp, cosp;
 #if defined(__CUDA_ARCH__)
   sincos(phi, &sinp, &cosp);
@@ -356,6 +397,9 @@ CMIB_HD_OUT_OF_LINE void emit_continuous(const SourceModel &m, const GridGeom &g
     double u[5];
     if (m.continuous_kind == CONTINUOUS_DISTANT_STAR) {
       distant_star_incoming(g, m.star_position, m.star_exposed, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
+    } else if (m.continuous_kind == CONTINUOUS_EXTENDED_DISC) {
+      extended_disc_incoming(g, m.planar_axis, m.planar_intercept, m.disc_scale_height, [&rng]() { return rng_uniform(rng); },
+                             px, py, pz, dx, dy, dz);
     } else if (m.continuous_kind == CONTINUOUS_PLANAR) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) u[k] = rng_uniform(rng);

@@ -2223,8 +2223,9 @@ public:
     const std::string continuous_type = parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None");
     if (log_) log_->write_info("Requested ContinuousPhotonSource type: ", continuous_type, ".");
     if (continuous_type != "None" && continuous_type != "Isotropic" && continuous_type != "Planar" &&
-        continuous_type != "DistantStar")
-      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic, Planar and DistantStar)!",
+        continuous_type != "DistantStar" && continuous_type != "ExtendedDisc")
+      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic, Planar, DistantStar and "
+                "ExtendedDisc)!",
                 continuous_type.c_str());
     /* DistantStarContinuousPhotonSource(box, params) (src/DistantStarContinuousPhotonSource.hpp:92-97) */
     Vec3 star_position = {0., 0., 0.};
@@ -2256,6 +2257,18 @@ public:
       planar_sides[1] = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:side 1", "1. m");
       planar_luminosity = parameter_file_.get_physical_value<QUANTITY_FREQUENCY>("ContinuousPhotonSource:luminosity", "1.e48 s^-1");
     }
+    /* ExtendedDiscContinuousPhotonSource(box, params) (src/ExtendedDiscContinuousPhotonSource.hpp:102-117) */
+    double disc_scale_height = 0.;
+    if (continuous_type == "ExtendedDisc") {
+      const std::string axis = parameter_file_.get_value<std::string>("ContinuousPhotonSource:normal axis", "z");
+      if (axis == "x") planar_axis = 0;
+      else if (axis == "y") planar_axis = 1;
+      else if (axis == "z") planar_axis = 2;
+      else cmi_error("Unknown coordinate axis name: \"%s\"!", axis.c_str());
+      planar_intercept = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:intercept", "0. m");
+      disc_scale_height = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:scale height", "200. pc");
+      planar_luminosity = parameter_file_.get_physical_value<QUANTITY_FREQUENCY>("ContinuousPhotonSource:luminosity", "1.e48 s^-1");
+    }
     continuous_photon_source_spectrum_.reset(
         PhotonSourceSpectrum::generate("ContinuousPhotonSourceSpectrum", parameter_file_, log_));
     const bool has_continuous = (continuous_type != "None");
@@ -2263,7 +2276,7 @@ public:
       cmi_error("No spectrum provided for the continuous photon sources!");
     if (!photon_source_distribution_ && !has_continuous) cmi_error("No photon sources!");
     double continuous_luminosity = 0.;
-    if (continuous_type == "Planar") {
+    if (continuous_type == "Planar" || continuous_type == "ExtendedDisc") {
       continuous_luminosity = planar_luminosity; /* has_total_luminosity() (PhotonSource.cpp:101-103) */
     } else if (has_continuous) {
       /* PhotonSource.cpp:104-108: total surface area (IsotropicContinuousPhotonSource.hpp:187-192) x total flux */
@@ -2303,9 +2316,12 @@ public:
         if (continuous_type == "Planar")
           CMIB_CALL(cmib_set_planar_source_geometry(ctx, planar_axis, planar_intercept, planar_anchor, planar_sides));
         if (continuous_type == "DistantStar") CMIB_CALL(cmib_set_distant_star_position(ctx, star_position.data()));
+        if (continuous_type == "ExtendedDisc")
+          CMIB_CALL(cmib_set_extended_disc_geometry(ctx, planar_axis, planar_intercept, disc_scale_height));
         CMIB_CALL(cmib_set_continuous_source(ctx,
                                              continuous_type == "Planar" ? CMIB_CONTINUOUS_PLANAR
                                              : continuous_type == "DistantStar" ? CMIB_CONTINUOUS_DISTANT_STAR
+                                             : continuous_type == "ExtendedDisc" ? CMIB_CONTINUOUS_EXTENDED_DISC
                                                                                 : CMIB_CONTINUOUS_ISOTROPIC,
                                              continuous_luminosity,
                                              continuous_photon_source_spectrum_->kind,

@@ -56,7 +56,8 @@ typedef struct cmib_grid_desc {
 enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
 enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
 enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1, CMIB_SPECTRUM_UNIFORM = 2, CMIB_SPECTRUM_TABULATED = 3 };
-enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1, CMIB_CONTINUOUS_PLANAR = 2, CMIB_CONTINUOUS_DISTANT_STAR = 3 };
+enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1, CMIB_CONTINUOUS_PLANAR = 2, CMIB_CONTINUOUS_DISTANT_STAR = 3,
+       CMIB_CONTINUOUS_EXTENDED_DISC = 4 };
 enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
 
 /* TemperatureCalculator parameters (src/TemperatureCalculator.cpp:133-160) */
@@ -152,6 +153,11 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
  * cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_DISTANT_STAR, luminosity, ...) with luminosity = exposed
  * surface area x total flux (PhotonSource.cpp:104-108, get_total_surface_area :194-212) */
 int cmib_set_distant_star_position(cmib_context *ctx, const double position[3]);
+/* ExtendedDiscContinuousPhotonSource(box, params) (src/ExtendedDiscContinuousPhotonSource.hpp:102-117): emission from
+ * the volume of a disc, Gaussian with `scale_height` around coordinate[normal_axis] = origin, uniform over the box in
+ * the two other coordinates; call before cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_EXTENDED_DISC, luminosity, ...),
+ * whose luminosity is the source's own `luminosity` key (has_total_luminosity(), PhotonSource.cpp:101-103). */
+int cmib_set_extended_disc_geometry(cmib_context *ctx, int normal_axis, double origin, double scale_height);
 int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double intercept, const double anchor[2],
                                     const double sides[2]);
 /* DiffuseReemissionHandlerFactory (src/DiffuseReemissionHandlerFactory.hpp:59-107);

@@ -294,6 +294,15 @@ def distant_star_incoming(anchor, sides, star, n, seed=42):
     return pos, d, area
 
 
+def extended_disc_incoming(anchor, sides, axis, origin, scale_height, n, seed=42):
+    """(positions [n,3], directions [n,3]) of ExtendedDiscContinuousPhotonSource with RandomGenerator(seed); axis 'x'/'y'/'z'"""
+    a, sd = (np.ascontiguousarray(v, dtype=np.float64) for v in (anchor, sides))
+    pos, d = np.empty((n, 3)), np.empty((n, 3))
+    lib().cmi_ref_extended_disc_incoming(_p(a), _p(sd), axis.encode(), C.c_double(origin), C.c_double(scale_height),
+                                         C.c_int(seed), C.c_int64(n), _p(pos), _p(d))
+    return pos, d
+
+
 def abundances(paramfile):
     out = np.empty(6)
     lib().cmi_ref_abundances(str(paramfile).encode(), _p(out))

@@ -46,6 +46,7 @@
 #include "CartesianDensityGrid.hpp"
 #include "ChargeTransferRates.hpp"
 #include "DistantStarContinuousPhotonSource.hpp"
+#include "ExtendedDiscContinuousPhotonSource.hpp"
 #include "DensityGridWriter.hpp"
 #include "FixedValueCrossSections.hpp"
 #include "FixedValueRecombinationRates.hpp"
@@ -675,6 +676,22 @@ double cmi_ref_distant_star_incoming(const double *anchor, const double *sides, 
     }
   }
   return source.get_total_surface_area();
+}
+
+/* ExtendedDiscContinuousPhotonSource::get_random_incoming_direction (src/ExtendedDiscContinuousPhotonSource.hpp:148-197)
+ * n times with RandomGenerator(seed) */
+void cmi_ref_extended_disc_incoming(const double *anchor, const double *sides, const char *axis, double origin,
+                                    double scale_height, int seed, int64_t n, double *pos, double *dir) {
+  const Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]), CoordinateVector<>(sides[0], sides[1], sides[2]));
+  ExtendedDiscContinuousPhotonSource source(box, axis, origin, scale_height, 1.e48);
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = pd.first[k];
+      dir[3 * i + k] = pd.second[k];
+    }
+  }
 }
 
 /* AbundanceModelFactory::generate on a parameter file -> He C N O Ne S */

@@ -198,6 +198,17 @@ void hc_distant_star_incoming(const double *anchor, const double *sides, const d
                           pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
 }
 
+void hc_extended_disc_incoming(const double *anchor, const double *sides, int axis, double origin, double scale_height,
+                               int seed, int64_t n, double *pos, double *dir) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) { g.anchor[d] = anchor[d]; g.sides[d] = sides[d]; }
+  cmi::RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i)
+    extended_disc_incoming(g, axis, origin, scale_height, [&rg]() { return rg.get_uniform_random_double(); }, pos[3 * i],
+                           pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+}
+
 /* PhotonSource::get_random_photon with the RANLUX stream: n_sources discrete sources with a Planck (T) or
  * monochromatic (nu) spectrum, optionally an isotropic continuous source with its own Planck spectrum
  * (continuous_luminosity > 0), Verner cross sections.  Outputs per packet: pos, dir, nu, sigma[14],

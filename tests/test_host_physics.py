@@ -261,6 +261,21 @@ def test_distant_star_continuous_source_bitexact(hostcheck, ref):
         assert (on_face & exposed).any(axis=1).all()
 
 
+def test_extended_disc_continuous_source_bitexact(hostcheck, ref):
+    """ExtendedDiscContinuousPhotonSource::get_random_incoming_direction (a Gaussian height redrawn while it falls
+    outside the box: a variable number of deviates per packet) driven by the RANLUX stream on both sides: every
+    start position and direction bit for bit — every axis, discs inside, off centre and beyond the box."""
+    anchor, sides = np.array([-1e17, -2e17, -1.5e17]), np.array([2e17, 4e17, 3e17])
+    for axis, origin, height in ((2, 0., 0.4e17), (0, 0.6e17, 1e17), (1, -2.5e17, 0.5e17), (2, 0.2e17, 8e17)):
+        pos, d = ref.extended_disc_incoming(anchor, sides, "xyz"[axis], origin, height, 5000, seed=11)
+        pos2, d2 = np.empty_like(pos), np.empty_like(d)
+        hostcheck.hc_extended_disc_incoming(p(anchor), p(sides), C.c_int(axis), C.c_double(origin), C.c_double(height),
+                                            C.c_int(11), C.c_int64(len(pos)), p(pos2), p(d2))
+        assert np.array_equal(d2, d) and np.array_equal(pos2, pos)
+        assert ((pos2 >= anchor) & (pos2 <= anchor + sides)).all()
+        assert np.unique(pos2[:, axis]).size > 4000 and abs(np.linalg.norm(d2, axis=1) - 1.).max() < 1e-15
+
+
 def _source_paramfile(tmp_path, continuous):
     yml = tmp_path / "sources.yml"
     yml.write_text("number of sources: 3\nsource[0]:\n  position: [0. pc, 0. pc, 0. pc]\n  luminosity: 2.e49 s^-1\n"
