@@ -25,6 +25,7 @@ CROSS_SECTIONS_FIXED_VALUE, CROSS_SECTIONS_VERNER = 0, 1
 RECOMBINATION_FIXED_VALUE, RECOMBINATION_VERNER = 0, 1
 SPECTRUM_MONOCHROMATIC, SPECTRUM_PLANCK, SPECTRUM_UNIFORM, SPECTRUM_TABULATED = 0, 1, 2, 3
 CONTINUOUS_NONE, CONTINUOUS_ISOTROPIC, CONTINUOUS_PLANAR, CONTINUOUS_DISTANT_STAR, CONTINUOUS_EXTENDED_DISC = 0, 1, 2, 3, 4
+CONTINUOUS_SPIRAL_GALAXY = 5
 REEMISSION_NONE, REEMISSION_PHYSICAL, REEMISSION_FIXED_VALUE = 0, 1, 2
 
 # CMIB_LIB: load another build of the same ABI (A/B timing of kernel variants)
@@ -202,6 +203,10 @@ class Context:
 
     def set_extended_disc_geometry(self, normal_axis, origin, scale_height):
         _check(lib.cmib_set_extended_disc_geometry(self._h, C.c_int(normal_axis), C.c_double(origin), C.c_double(scale_height)))
+
+    def set_spiral_galaxy_geometry(self, scale_length_stars, scale_height_stars, bulge_over_total_ratio):
+        _check(lib.cmib_set_spiral_galaxy_geometry(self._h, C.c_double(scale_length_stars), C.c_double(scale_height_stars),
+                                                   C.c_double(bulge_over_total_ratio)))
 
     def set_planar_source_geometry(self, normal_axis, intercept, anchor, sides):
         a, sd = _f64(anchor).reshape(2), _f64(sides).reshape(2)

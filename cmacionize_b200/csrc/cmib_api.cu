@@ -109,7 +109,8 @@ struct cmib_context {
   TemperatureParams tp;
   double luminosity = 0.; /* discrete + continuous */
   double discrete_luminosity = 0., continuous_luminosity = 0.;
-  bool planar_geometry_set = false, star_position_set = false, disc_geometry_set = false;
+  bool planar_geometry_set = false, star_position_set = false, disc_geometry_set = false, galaxy_geometry_set = false;
+  DevBuf<double> d_galaxy_tables; /* [2][GALAXY_NBIN + 1]: radius, cumulative disc luminosity */
   DevBuf<double> d_cont_planck;
   DevBuf<uint16_t> d_cont_planck_guide;
   std::vector<double> h_cont_planck;
@@ -926,6 +927,26 @@ int cmib_set_extended_disc_geometry(cmib_context *ctx, int normal_axis, double o
   return 0;
 }
 
+int cmib_set_spiral_galaxy_geometry(cmib_context *ctx, double scale_length_stars, double scale_height_stars,
+                                    double bulge_over_total_ratio) {
+  CHECK_CTX(ctx);
+  if (!(scale_length_stars > 0.) || !(scale_height_stars > 0.)) CMIB_FAIL("the scale length and height of the stellar disc must be positive");
+  if (!(bulge_over_total_ratio >= 0.) || bulge_over_total_ratio > 1.) CMIB_FAIL("the bulge over total ratio must lie in [0, 1]");
+  /* the galaxy sits at the origin: a box that does not hold the origin would reject (nearly) every position */
+  for (int d = 0; d < 3; ++d)
+    if (ctx->geom.anchor[d] > 0. || ctx->geom.anchor[d] + ctx->geom.sides[d] <= 0.)
+      CMIB_FAIL("the SpiralGalaxy source is centred on the origin, which lies outside the simulation box");
+  std::vector<double> tables(2 * (GALAXY_NBIN + 1));
+  build_galaxy_model(ctx->geom.anchor, scale_length_stars, scale_height_stars, bulge_over_total_ratio, ctx->src.galaxy,
+                     tables.data(), tables.data() + GALAXY_NBIN + 1);
+  CUDA_OK(ctx->d_galaxy_tables.upload(tables.data(), tables.size(), ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->src.galaxy_w = ctx->d_galaxy_tables.p;
+  ctx->src.galaxy_cdf = ctx->d_galaxy_tables.p + GALAXY_NBIN + 1;
+  ctx->galaxy_geometry_set = true;
+  return 0;
+}
+
 int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, int spectrum_kind,
                                double spectrum_param) {
   CHECK_CTX(ctx);
@@ -936,8 +957,10 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
     return 0;
   }
   if (kind != CMIB_CONTINUOUS_ISOTROPIC && kind != CMIB_CONTINUOUS_PLANAR && kind != CMIB_CONTINUOUS_DISTANT_STAR &&
-      kind != CMIB_CONTINUOUS_EXTENDED_DISC)
+      kind != CMIB_CONTINUOUS_EXTENDED_DISC && kind != CMIB_CONTINUOUS_SPIRAL_GALAXY)
     CMIB_FAIL("Unknown ContinuousPhotonSource type: %d", kind);
+  if (kind == CMIB_CONTINUOUS_SPIRAL_GALAXY && !ctx->galaxy_geometry_set)
+    CMIB_FAIL("call cmib_set_spiral_galaxy_geometry before selecting the SpiralGalaxy continuous source");
   if (kind == CMIB_CONTINUOUS_EXTENDED_DISC && !ctx->disc_geometry_set)
     CMIB_FAIL("call cmib_set_extended_disc_geometry before selecting the ExtendedDisc continuous source");
   if (kind == CMIB_CONTINUOUS_DISTANT_STAR && !ctx->star_position_set)
@@ -953,7 +976,9 @@ int cmib_set_continuous_source(cmib_context *ctx, int kind, double luminosity, i
   ctx->src.continuous_kind = (kind == CMIB_CONTINUOUS_PLANAR) ? CONTINUOUS_PLANAR
                              : (kind == CMIB_CONTINUOUS_DISTANT_STAR)
                                    ? CONTINUOUS_DISTANT_STAR
-                                   : (kind == CMIB_CONTINUOUS_EXTENDED_DISC ? CONTINUOUS_EXTENDED_DISC : CONTINUOUS_ISOTROPIC);
+                                   : (kind == CMIB_CONTINUOUS_EXTENDED_DISC)
+                                         ? CONTINUOUS_EXTENDED_DISC
+                                         : (kind == CMIB_CONTINUOUS_SPIRAL_GALAXY ? CONTINUOUS_SPIRAL_GALAXY : CONTINUOUS_ISOTROPIC);
   ctx->continuous_luminosity = luminosity;
   ctx->update_source_weights();
   return 0;

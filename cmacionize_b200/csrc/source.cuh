@@ -33,7 +33,7 @@ namespace cmib {
 enum SpectrumKind : int { SPECTRUM_MONOCHROMATIC = 0, SPECTRUM_PLANCK = 1, SPECTRUM_UNIFORM = 2, SPECTRUM_TABULATED = 3 };
 enum ReemissionKind : int { REEMISSION_NONE = 0, REEMISSION_PHYSICAL = 1, REEMISSION_FIXED = 2 };
 enum ContinuousKind : int { CONTINUOUS_NONE = 0, CONTINUOUS_ISOTROPIC = 1, CONTINUOUS_PLANAR = 2, CONTINUOUS_DISTANT_STAR = 3,
-                             CONTINUOUS_EXTENDED_DISC = 4 };
+                             CONTINUOUS_EXTENDED_DISC = 4, CONTINUOUS_SPIRAL_GALAXY = 5 };
 
 constexpr int SPECTRUM_NUMFREQ = 1000; /* all tabulated spectra use 1000 frequency bins */
 constexpr int LYC_NUMTEMP = 100;
@@ -55,6 +55,32 @@ struct SpectrumModel {
 };
 
 /* everything the emission / re-emission code needs; pointers are device pointers */
+constexpr int GALAXY_NBIN = 1000;
+/* the constants of SpiralGalaxyContinuousPhotonSource (constructor, .hpp:78-105) */
+struct GalaxyModel {
+  double rJ, h_stars, bulge_to_total_ratio, rB_over_rJ_plus_rB, rC_over_rJ_plus_rC;
+};
+/* the constructor's arithmetic: bulge radii 0.2 / 2 / 0.4 kpc, the bulge fraction corrected for the core, and the
+ * cumulative disc luminosity 1 - (1 + w / r_stars) exp(-w / r_stars) on 1000 bins up to 1.2 |box anchor| */
+inline void build_galaxy_model(const double *box_anchor, double r_stars, double h_stars, double B_over_T, GalaxyModel &m,
+                               double *w_table, double *cdf_table) {
+  const double kpc = 3.086e19, rC = 0.2 * kpc, rB = 2. * kpc;
+  m.rJ = 0.4 * kpc;
+  m.h_stars = h_stars;
+  m.rB_over_rJ_plus_rB = rB / (rB + m.rJ);
+  m.rC_over_rJ_plus_rC = rC / (rC + m.rJ);
+  m.bulge_to_total_ratio = B_over_T * (1. - m.rC_over_rJ_plus_rC / m.rB_over_rJ_plus_rB);
+  const double rmax = 1.2 * sqrt(box_anchor[0] * box_anchor[0] + box_anchor[1] * box_anchor[1] + box_anchor[2] * box_anchor[2]);
+  for (int i = 0; i < GALAXY_NBIN; ++i) {
+    const double w = i * rmax / GALAXY_NBIN;
+    w_table[i] = w;
+    const double x = w / r_stars;
+    cdf_table[i] = 1. - (1. + x) * exp(-x);
+  }
+  w_table[GALAXY_NBIN] = rmax;
+  cdf_table[GALAXY_NBIN] = 1.;
+}
+
 struct SourceModel {
   /* discrete sources (PhotonSource.cpp:74-100) */
   int n_sources;
@@ -74,6 +100,10 @@ struct SourceModel {
    * coordinate[planar_axis] Gaussian around planar_intercept with this scale height, uniform over the box in the
    * two other coordinates */
   double disc_scale_height;
+  /* CONTINUOUS_SPIRAL_GALAXY (SpiralGalaxyContinuousPhotonSource.hpp:46-195): a Jaffe-like bulge + a double
+   * exponential stellar disc around the origin; galaxy_w / galaxy_cdf = the cumulative radial luminosity of the disc */
+  GalaxyModel galaxy;
+  const double *galaxy_w, *galaxy_cdf; /* [GALAXY_NBIN + 1] each */
   /* CONTINUOUS_DISTANT_STAR (DistantStarContinuousPhotonSource.hpp:60-90): a star outside the box;
    * star_exposed[d] = -1 / +1 / 0: the star lies below / above / within the box along d */
   double star_position[3];
@@ -259,6 +289,75 @@ CMIB_HD void extended_disc_incoming(const GridGeom &g, int axis, double origin, 
 }
 
 /*
+ * SpiralGalaxyContinuousPhotonSource::get_random_incoming_direction (.hpp:131-190): positions are drawn from the
+ * bulge (with probability bulge_to_total_ratio: r = rJ / (1 / A - 1), A uniform between the two bulge constants,
+ * isotropic) or from the disc (exponential height, radius from the tabulated cumulative luminosity) until one
+ * lies inside the box (Box::inside: anchor <= x < anchor + sides), then an isotropic direction.
+ */
+template <class Uniform>
+CMIB_HD void spiral_galaxy_incoming(const GridGeom &g, const GalaxyModel &m, const double *w_table, const double *cdf_table,
+                                    Uniform &&uniform, double &px, double &py, double &pz, double &dx, double &dy, double &dz) {
+  double p[3] = {g.anchor[0] - g.sides[0], g.anchor[1] - g.sides[1], g.anchor[2] - g.sides[2]};
+  for (int trial = 0; trial < (1 << 24); ++trial) {
+    const double x_bulge = uniform();
+    if (x_bulge <= m.bulge_to_total_ratio) {
+      const double u = uniform();
+      const double A = u * m.rB_over_rJ_plus_rB + (1. - u) * m.rC_over_rJ_plus_rC;
+      const double r = m.rJ / (1. / A - 1.);
+      const double phi = 2. * M_PI * uniform();
+      const double cost = 2. * uniform() - 1.;
+      const double s2 = 1. - cost * cost;
+      const double sint = sqrt(s2 > 0. ? s2 : 0.);
+      double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+      sincos(phi, &sinp, &cosp);
+#else
+      cosp = cos(phi);
+      sinp = sin(phi);
+#endif
+      p[0] = r * sint * cosp;
+      p[1] = r * sint * sinp;
+      p[2] = r * cost;
+    } else {
+      const double u1 = 2. * uniform() - 1.;
+      const double z = (u1 > 0.) ? -m.h_stars * log(u1) : m.h_stars * log(-u1);
+      const double phi = 2. * M_PI * uniform();
+      const double u2 = uniform();
+      const uint32_t i = locate(u2, cdf_table, GALAXY_NBIN + 1);
+      const double w = w_table[i] + (u2 - cdf_table[i]) / (cdf_table[i + 1] - cdf_table[i]) * (w_table[i + 1] - w_table[i]);
+      double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+      sincos(phi, &sinp, &cosp);
+#else
+      cosp = cos(phi);
+      sinp = sin(phi);
+#endif
+      p[0] = w * cosp;
+      p[1] = w * sinp;
+      p[2] = z;
+    }
+    if (p[0] >= g.anchor[0] && p[0] < g.anchor[0] + g.sides[0] && p[1] >= g.anchor[1] && p[1] < g.anchor[1] + g.sides[1] &&
+        p[2] >= g.anchor[2] && p[2] < g.anchor[2] + g.sides[2])
+      break;
+  }
+  px = p[0]; py = p[1]; pz = p[2];
+  const double cost = 2. * uniform() - 1.;
+  const double s2 = 1. - cost * cost;
+  const double sint = sqrt(s2 > 0. ? s2 : 0.);
+  const double phi = 2. * M_PI * uniform();
+  double sinp, cosp;
+#if defined(__CUDA_ARCH__)
+  sincos(phi, &sinp, &cosp);
+#else
+  cosp = cos(phi);
+  sinp = sin(phi);
+#endif
+  dx = sint * cosp;
+  dy = sint * sinp;
+  dz = cost;
+}
+
+/*
  * DistantStarContinuousPhotonSource::get_random_incoming_direction (.hpp:164-192) with enters_box
  * (:125-155): isotropic directions from the star (the first one mirrored towards the box) are drawn
  * until one hits an exposed face within the face's bounds; the packet starts at that intersection
@@ -397,6 +496,8 @@ CMIB_HD_OUT_OF_LINE void emit_continuous(const SourceModel &m, const GridGeom &g
     double u[5];
     if (m.continuous_kind == CONTINUOUS_DISTANT_STAR) {
       distant_star_incoming(g, m.star_position, m.star_exposed, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
+    } else if (m.continuous_kind == CONTINUOUS_SPIRAL_GALAXY) {
+      spiral_galaxy_incoming(g, m.galaxy, m.galaxy_w, m.galaxy_cdf, [&rng]() { return rng_uniform(rng); }, px, py, pz, dx, dy, dz);
     } else if (m.continuous_kind == CONTINUOUS_EXTENDED_DISC) {
       extended_disc_incoming(g, m.planar_axis, m.planar_intercept, m.disc_scale_height, [&rng]() { return rng_uniform(rng); },
                              px, py, pz, dx, dy, dz);

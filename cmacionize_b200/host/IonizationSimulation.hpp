@@ -2223,9 +2223,9 @@ public:
     const std::string continuous_type = parameter_file_.get_value<std::string>("ContinuousPhotonSource:type", "None");
     if (log_) log_->write_info("Requested ContinuousPhotonSource type: ", continuous_type, ".");
     if (continuous_type != "None" && continuous_type != "Isotropic" && continuous_type != "Planar" &&
-        continuous_type != "DistantStar" && continuous_type != "ExtendedDisc")
-      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic, Planar, DistantStar and "
-                "ExtendedDisc)!",
+        continuous_type != "DistantStar" && continuous_type != "ExtendedDisc" && continuous_type != "SpiralGalaxy")
+      cmi_error("Unknown ContinuousPhotonSource type: \"%s\" (the B200 backend provides Isotropic, Planar, DistantStar, "
+                "ExtendedDisc and SpiralGalaxy)!",
                 continuous_type.c_str());
     /* DistantStarContinuousPhotonSource(box, params) (src/DistantStarContinuousPhotonSource.hpp:92-97) */
     Vec3 star_position = {0., 0., 0.};
@@ -2269,6 +2269,13 @@ public:
       disc_scale_height = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:scale height", "200. pc");
       planar_luminosity = parameter_file_.get_physical_value<QUANTITY_FREQUENCY>("ContinuousPhotonSource:luminosity", "1.e48 s^-1");
     }
+    /* SpiralGalaxyContinuousPhotonSource(box, params) (src/SpiralGalaxyContinuousPhotonSource.hpp:107-120) */
+    double galaxy_r_stars = 0., galaxy_h_stars = 0., galaxy_B_over_T = 0.;
+    if (continuous_type == "SpiralGalaxy") {
+      galaxy_r_stars = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:scale length stars", "5. kpc");
+      galaxy_h_stars = parameter_file_.get_physical_value<QUANTITY_LENGTH>("ContinuousPhotonSource:scale height stars", "0.6 kpc");
+      galaxy_B_over_T = parameter_file_.get_value<double>("ContinuousPhotonSource:bulge over total ratio", 0.2);
+    }
     continuous_photon_source_spectrum_.reset(
         PhotonSourceSpectrum::generate("ContinuousPhotonSourceSpectrum", parameter_file_, log_));
     const bool has_continuous = (continuous_type != "None");
@@ -2283,6 +2290,8 @@ public:
       if (continuous_photon_source_spectrum_->total_flux < 0.) cmi_error("This function should not be used!");
       const double area = (continuous_type == "DistantStar")
                               ? star_area
+                          : (continuous_type == "SpiralGalaxy")
+                              ? 1. /* SpiralGalaxyContinuousPhotonSource::get_total_surface_area (:194) */
                               : 2. * box.sides[0] * box.sides[1] + 2. * box.sides[0] * box.sides[2] +
                                     2. * box.sides[1] * box.sides[2];
       continuous_luminosity = area * continuous_photon_source_spectrum_->total_flux;
@@ -2318,10 +2327,13 @@ public:
         if (continuous_type == "DistantStar") CMIB_CALL(cmib_set_distant_star_position(ctx, star_position.data()));
         if (continuous_type == "ExtendedDisc")
           CMIB_CALL(cmib_set_extended_disc_geometry(ctx, planar_axis, planar_intercept, disc_scale_height));
+        if (continuous_type == "SpiralGalaxy")
+          CMIB_CALL(cmib_set_spiral_galaxy_geometry(ctx, galaxy_r_stars, galaxy_h_stars, galaxy_B_over_T));
         CMIB_CALL(cmib_set_continuous_source(ctx,
                                              continuous_type == "Planar" ? CMIB_CONTINUOUS_PLANAR
                                              : continuous_type == "DistantStar" ? CMIB_CONTINUOUS_DISTANT_STAR
                                              : continuous_type == "ExtendedDisc" ? CMIB_CONTINUOUS_EXTENDED_DISC
+                                             : continuous_type == "SpiralGalaxy" ? CMIB_CONTINUOUS_SPIRAL_GALAXY
                                                                                 : CMIB_CONTINUOUS_ISOTROPIC,
                                              continuous_luminosity,
                                              continuous_photon_source_spectrum_->kind,

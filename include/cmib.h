@@ -57,7 +57,7 @@ enum { CMIB_CROSS_SECTIONS_FIXED_VALUE = 0, CMIB_CROSS_SECTIONS_VERNER = 1 };
 enum { CMIB_RECOMBINATION_FIXED_VALUE = 0, CMIB_RECOMBINATION_VERNER = 1 };
 enum { CMIB_SPECTRUM_MONOCHROMATIC = 0, CMIB_SPECTRUM_PLANCK = 1, CMIB_SPECTRUM_UNIFORM = 2, CMIB_SPECTRUM_TABULATED = 3 };
 enum { CMIB_CONTINUOUS_NONE = 0, CMIB_CONTINUOUS_ISOTROPIC = 1, CMIB_CONTINUOUS_PLANAR = 2, CMIB_CONTINUOUS_DISTANT_STAR = 3,
-       CMIB_CONTINUOUS_EXTENDED_DISC = 4 };
+       CMIB_CONTINUOUS_EXTENDED_DISC = 4, CMIB_CONTINUOUS_SPIRAL_GALAXY = 5 };
 enum { CMIB_REEMISSION_NONE = 0, CMIB_REEMISSION_PHYSICAL = 1, CMIB_REEMISSION_FIXED_VALUE = 2 };
 
 /* TemperatureCalculator parameters (src/TemperatureCalculator.cpp:133-160) */
@@ -158,6 +158,12 @@ int cmib_set_distant_star_position(cmib_context *ctx, const double position[3]);
  * the two other coordinates; call before cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_EXTENDED_DISC, luminosity, ...),
  * whose luminosity is the source's own `luminosity` key (has_total_luminosity(), PhotonSource.cpp:101-103). */
 int cmib_set_extended_disc_geometry(cmib_context *ctx, int normal_axis, double origin, double scale_height);
+/* SpiralGalaxyContinuousPhotonSource(box, params) (src/SpiralGalaxyContinuousPhotonSource.hpp:78-120): stellar bulge +
+ * double exponential disc around the origin (scale length and height of the disc, bulge over total ratio); the radial
+ * luminosity table is built here.  Call before cmib_set_continuous_source(ctx, CMIB_CONTINUOUS_SPIRAL_GALAXY,
+ * luminosity, ...) with luminosity = get_total_surface_area() (= 1 m^2, :194) x total flux of the spectrum. */
+int cmib_set_spiral_galaxy_geometry(cmib_context *ctx, double scale_length_stars, double scale_height_stars,
+                                    double bulge_over_total_ratio);
 int cmib_set_planar_source_geometry(cmib_context *ctx, int normal_axis, double intercept, const double anchor[2],
                                     const double sides[2]);
 /* DiffuseReemissionHandlerFactory (src/DiffuseReemissionHandlerFactory.hpp:59-107);

@@ -303,6 +303,15 @@ def extended_disc_incoming(anchor, sides, axis, origin, scale_height, n, seed=42
     return pos, d
 
 
+def spiral_galaxy_incoming(anchor, sides, r_stars, h_stars, B_over_T, n, seed=42):
+    """(positions [n,3], directions [n,3]) of SpiralGalaxyContinuousPhotonSource with RandomGenerator(seed)"""
+    a, sd = (np.ascontiguousarray(v, dtype=np.float64) for v in (anchor, sides))
+    pos, d = np.empty((n, 3)), np.empty((n, 3))
+    lib().cmi_ref_spiral_galaxy_incoming(_p(a), _p(sd), C.c_double(r_stars), C.c_double(h_stars), C.c_double(B_over_T),
+                                         C.c_int(seed), C.c_int64(n), _p(pos), _p(d))
+    return pos, d
+
+
 def abundances(paramfile):
     out = np.empty(6)
     lib().cmi_ref_abundances(str(paramfile).encode(), _p(out))

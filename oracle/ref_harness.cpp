@@ -70,6 +70,7 @@
 #include "PlanckPhotonSourceSpectrum.hpp"
 #include "RandomGenerator.hpp"
 #include "SPHArrayInterface.hpp"
+#include "SpiralGalaxyContinuousPhotonSource.hpp"
 #include "TemperatureCalculator.hpp"
 #include "TerminalLog.hpp"
 #include "Tracker.hpp"
@@ -684,6 +685,22 @@ void cmi_ref_extended_disc_incoming(const double *anchor, const double *sides, c
                                     double scale_height, int seed, int64_t n, double *pos, double *dir) {
   const Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]), CoordinateVector<>(sides[0], sides[1], sides[2]));
   ExtendedDiscContinuousPhotonSource source(box, axis, origin, scale_height, 1.e48);
+  RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i) {
+    const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);
+    for (int k = 0; k < 3; ++k) {
+      pos[3 * i + k] = pd.first[k];
+      dir[3 * i + k] = pd.second[k];
+    }
+  }
+}
+
+/* SpiralGalaxyContinuousPhotonSource::get_random_incoming_direction (src/SpiralGalaxyContinuousPhotonSource.hpp:131-190)
+ * n times with RandomGenerator(seed) */
+void cmi_ref_spiral_galaxy_incoming(const double *anchor, const double *sides, double r_stars, double h_stars,
+                                    double B_over_T, int seed, int64_t n, double *pos, double *dir) {
+  const Box<> box(CoordinateVector<>(anchor[0], anchor[1], anchor[2]), CoordinateVector<>(sides[0], sides[1], sides[2]));
+  SpiralGalaxyContinuousPhotonSource source(box, r_stars, h_stars, B_over_T);
   RandomGenerator rg(seed);
   for (int64_t i = 0; i < n; ++i) {
     const std::pair<CoordinateVector<>, CoordinateVector<>> pd = source.get_random_incoming_direction(rg);

@@ -209,6 +209,19 @@ void hc_extended_disc_incoming(const double *anchor, const double *sides, int ax
                            pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
 }
 
+void hc_spiral_galaxy_incoming(const double *anchor, const double *sides, double r_stars, double h_stars, double B_over_T,
+                               int seed, int64_t n, double *pos, double *dir, double *tables) {
+  GridGeom g;
+  memset(&g, 0, sizeof(g));
+  for (int d = 0; d < 3; ++d) { g.anchor[d] = anchor[d]; g.sides[d] = sides[d]; }
+  GalaxyModel m;
+  build_galaxy_model(anchor, r_stars, h_stars, B_over_T, m, tables, tables + GALAXY_NBIN + 1);
+  cmi::RandomGenerator rg(seed);
+  for (int64_t i = 0; i < n; ++i)
+    spiral_galaxy_incoming(g, m, tables, tables + GALAXY_NBIN + 1, [&rg]() { return rg.get_uniform_random_double(); },
+                           pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]);
+}
+
 /* PhotonSource::get_random_photon with the RANLUX stream: n_sources discrete sources with a Planck (T) or
  * monochromatic (nu) spectrum, optionally an isotropic continuous source with its own Planck spectrum
  * (continuous_luminosity > 0), Verner cross sections.  Outputs per packet: pos, dir, nu, sigma[14],

@@ -1,6 +1,7 @@
 """GPU tier: continuous photon sources (src/IsotropicContinuousPhotonSource.hpp,
 src/PlanarContinuousPhotonSource.hpp, src/DistantStarContinuousPhotonSource.hpp,
-src/ExtendedDiscContinuousPhotonSource.hpp, PhotonSource.cpp:100-131, 208-249) end to end through the C++ host
+src/ExtendedDiscContinuousPhotonSource.hpp, src/SpiralGalaxyContinuousPhotonSource.hpp,
+PhotonSource.cpp:100-131, 208-249) end to end through the C++ host
 driver — parameter files with an external radiation field alone, a star + external field, and an
 emitting sheet in the mid-plane (tests/golden/continuous/), against two runs of the compiled reference on
 the same file (seeds 42 / 4242).
@@ -28,7 +29,7 @@ def make_paramfile(tmp_path, name, seed):
 
 
 @pytest.mark.parametrize("name", ["external_field", "star_plus_external_field", "planar_sheet", "distant_star",
-                                  "extended_disc"])
+                                  "extended_disc", "spiral_galaxy"])
 def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     nc = 32
     runs = [ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)[0] for seed in (42, 4242)]
@@ -51,7 +52,7 @@ def test_external_radiation_field(host, ref, tmp_path, name):  # noqa: F811
     # mean neutral fraction per shell of equal depth below the nearest face
     i = np.arange(nc)
     depth1 = np.minimum(i, nc - 1 - i)
-    if name in ("planar_sheet", "extended_disc"):   # distance from the sheet / the mid-plane of the disc instead
+    if name in ("planar_sheet", "extended_disc", "spiral_galaxy"):   # distance from the sheet / the mid-plane of the disc instead
         depth = np.meshgrid(i, i, np.abs(i - (nc - 1) / 2.).astype(int), indexing="ij")[2].ravel()
     elif name == "distant_star":  # depth below the two lit faces (x low, y low)
         depth = np.minimum(*np.meshgrid(i, i, i, indexing="ij")[:2]).ravel() // 2

@@ -169,7 +169,7 @@ def test_shoot_is_deterministic_and_shardable(cmib):
 
 
 @pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
-                                    "continuous", "continuous_only", "planar", "distant_star", "extended_disc", "bimodal"])
+                                    "continuous", "continuous_only", "planar", "distant_star", "extended_disc", "spiral_galaxy", "bimodal"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -214,6 +214,13 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         prob.ctx.set_sources(None, None, 0.)
         prob.ctx.set_extended_disc_geometry(1, 3 * PC, 1.5 * PC)
         prob.ctx.set_continuous_source(capi.CONTINUOUS_EXTENDED_DISC, 3e49, capi.SPECTRUM_MONOCHROMATIC, problems.ev_to_hz(13.6))
+    elif config == "spiral_galaxy":
+        # SpiralGalaxyContinuousPhotonSource: bulge / disc positions redrawn until inside the box (the bulge radii are
+        # hard-wired kpc, so in this pc-sized box every bulge draw is rejected: a variable number of deviates per packet)
+        prob = problems.stromgren(ncell=32, n_packets=npk, diffuse=True)
+        prob.ctx.set_sources(None, None, 0.)
+        prob.ctx.set_spiral_galaxy_geometry(3 * PC, 0.5 * PC, 0.001)
+        prob.ctx.set_continuous_source(capi.CONTINUOUS_SPIRAL_GALAXY, 3e49, capi.SPECTRUM_MONOCHROMATIC, problems.ev_to_hz(13.6))
     elif config == "bimodal":
         # CrossSections: Bimodal (two constant values per ion, split at a frequency limit) with the diffuse field
         prob = problems.lexington(20, ncell=24, n_packets=npk)
@@ -490,6 +497,10 @@ def test_source_configuration_errors(cmib):
             ctx.set_extended_disc_geometry(2, 5., 0.1)
         with pytest.raises(cmib.CmibError, match="scale height of the disc must be positive"):
             ctx.set_extended_disc_geometry(2, 0., 0.)
+        with pytest.raises(cmib.CmibError, match="cmib_set_spiral_galaxy_geometry before"):
+            ctx.set_continuous_source(capi.CONTINUOUS_SPIRAL_GALAXY, 1e49, capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
+        with pytest.raises(cmib.CmibError, match="bulge over total ratio must lie in"):
+            ctx.set_spiral_galaxy_geometry(1., 0.1, 1.5)
         with pytest.raises(cmib.CmibError, match="Unknown ContinuousPhotonSource type"):
             ctx.set_continuous_source(7, 1e49, capi.SPECTRUM_MONOCHROMATIC, 3.3e15)
         with pytest.raises(cmib.CmibError, match="Unknown PhotonSourceSpectrum type"):

@@ -276,6 +276,27 @@ def test_extended_disc_continuous_source_bitexact(hostcheck, ref):
         assert np.unique(pos2[:, axis]).size > 4000 and abs(np.linalg.norm(d2, axis=1) - 1.).max() < 1e-15
 
 
+def test_spiral_galaxy_continuous_source_bitexact(hostcheck, ref):
+    """SpiralGalaxyContinuousPhotonSource::get_random_incoming_direction (bulge or disc positions redrawn until one
+    lies in the box, the disc radius from a tabulated cumulative luminosity) driven by the RANLUX stream on both sides:
+    every start position and direction bit for bit — a box around the whole galaxy, a thin slab, an off-centre box
+    that rejects most of the disc, bulge-only and disc-only mixtures."""
+    KPC = 3.086e19
+    for anchor, sides, rs, hs, bt in (([-12., -12., -12.], [24., 24., 24.], 5., 0.6, 0.2),
+                                      ([-6., -6., -0.4], [12., 12., 0.8], 3., 0.3, 0.5),
+                                      ([-1., -2., -3.], [9., 4., 5.], 5., 0.6, 0.2),
+                                      ([-4., -4., -4.], [8., 8., 8.], 2., 0.2, 0.),
+                                      ([-4., -4., -4.], [8., 8., 8.], 2., 0.2, 1.)):
+        a, sd = np.array(anchor) * KPC, np.array(sides) * KPC
+        pos, d = ref.spiral_galaxy_incoming(a, sd, rs * KPC, hs * KPC, bt, 5000, seed=13)
+        pos2, d2, tables = np.empty_like(pos), np.empty_like(d), np.empty(2002)
+        hostcheck.hc_spiral_galaxy_incoming(p(a), p(sd), C.c_double(rs * KPC), C.c_double(hs * KPC), C.c_double(bt), C.c_int(13),
+                                            C.c_int64(len(pos)), p(pos2), p(d2), p(tables))
+        assert np.array_equal(d2, d) and np.array_equal(pos2, pos)
+        assert ((pos2 >= a) & (pos2 < a + sd)).all() and abs(np.linalg.norm(d2, axis=1) - 1.).max() < 1e-15
+        assert tables[1000] == 1.2 * np.sqrt((a ** 2).sum()) and tables[2001] == 1. and (np.diff(tables[1001:]) >= 0).all()
+
+
 def _source_paramfile(tmp_path, continuous):
     yml = tmp_path / "sources.yml"
     yml.write_text("number of sources: 3\nsource[0]:\n  position: [0. pc, 0. pc, 0. pc]\n  luminosity: 2.e49 s^-1\n"
