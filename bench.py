@@ -395,13 +395,21 @@ def main():
     # one crossing = one scattered gather + red_per_crossing scattered REDs through the same L1TEX pipe
     crossing_bound = 1. / (1. / GATHER_PEAK + red_per_crossing / RED_PEAK)
     full_layout = args.workload in ("lexingtonHII20", "clumpy256L")
+    # dram__bytes_read.sum + dram__bytes_write.sum of ONE march launch (16 Mi packets) from the ncu --set full captures
+    TRAFFIC = {
+        "lexingtonHII20": (4.546e9, "dram__bytes_read+write (3.45 + 1.09 GB) of the first march launch "
+                           "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
+                           "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
+                           "(3.4 GB read) and the re-emission queue (1.1 GB written)"),
+        "clumpy256": (5.244e10, "dram__bytes_read+write (46.99 + 5.45 GB) of one coherent march launch (16 Mi packets, 2.44e9 "
+                      "crossings = 58.6 GB algorithmic), ncu --set full, profiles/r01_coherent_march.md: 21 DRAM bytes per "
+                      "crossing against 24 algorithmic ones (L2 reuse inside the cone of an ordered chunk); 92 B per crossing "
+                      "in emission order"),
+    }
     roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>" if full_layout else "march_kernel<ACC_HONLY>",
                 "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": 4.546e9 if args.workload == "lexingtonHII20" else None, "traffic_note": "dram__bytes_read+write (3.45 + 1.09 GB) of the first march launch "
-                "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
-                "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
-                "(3.4 GB read) and the re-emission queue (1.1 GB written)",
+                "traffic": TRAFFIC.get(args.workload, (None, None))[0], "traffic_note": TRAFFIC.get(args.workload, (None, None))[1],
                 "peak_source": peak_src,
                 "cell_crossings_per_packet": steps_per_packet, "emissions_per_packet": emissions / n_packets,
                 "algorithmic_bytes_per_crossing": bytes_per_step, "kernel_ms": march_ms,
