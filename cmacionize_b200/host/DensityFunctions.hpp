@@ -806,6 +806,119 @@ private:
   std::vector<size_t> bin_start_, bin_particles_;
 };
 
+/* Lambert W function on (-1/e, 0), branches 0 and -1 (LambertW.hpp:44-110): a 5th order series as first guess
+ * (mirrored around W = -1 for the lower branch), then Newton steps to a relative tolerance of 1e-10 */
+inline double lambert_w(double r, int branch) {
+  if (r >= 0. || r < -1. / M_E) cmi_error("Input value for Lambert W outside supported range: %g!", r);
+  const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2, r5 = r4 * r;
+  const double w = r - r2 + 1.5 * r3 - (8. / 3.) * r4 + (125. / 24.) * r5;
+  auto newton_step = [r](double w_) {
+    const double expw = std::exp(w_);
+    const double wexpw = w_ * expw;
+    return w_ - (wexpw - r) / (expw + wexpw);
+  };
+  double w0 = (branch == 0) ? w : -2. - w;
+  double w1 = newton_step(w0);
+  while (std::abs(w0 - w1) > std::abs(w0 + w1) * 1.e-10) {
+    w0 = w1;
+    w1 = newton_step(w0);
+  }
+  return w1;
+}
+
+/* Spherical Bondi accretion onto a point mass, optionally with an ionised inner region in pressure balance
+ * (BondiProfile.hpp:82-236, BondiProfileDensityFunction.hpp:52-117): density and pressure of the analytic flow,
+ * temperature = m_p P / (k rho), halved where the profile is ionised.  The velocities of the profile belong to
+ * the hydro and are not part of the grid here. */
+class BondiProfileDensityFunction : public DensityFunction {
+public:
+  BondiProfileDensityFunction(double central_mass, double bondi_density, double sound_speed, double ionisation_radius,
+                              double pressure_contrast, const Vec3 &center, double neutral_fraction)
+      : bondi_radius_(0.5 * constants::newton_constant * central_mass / (sound_speed * sound_speed)),
+        bondi_density_(bondi_density), sound_speed_(sound_speed), ionisation_radius_(ionisation_radius),
+        pressure_contrast_(pressure_contrast), center_(center), neutral_fraction_(neutral_fraction) {
+    if (ionisation_radius_ > 0. && pressure_contrast_ > 0.) {
+      const double rBI = bondi_radius_ / ionisation_radius_;
+      const double rBI2 = rBI * rBI;
+      const double lambertarg = -rBI2 * rBI2 * std::exp(3. - 4. * rBI);
+      double v_RI = std::sqrt(-lambert_w(lambertarg, -1));
+      const double rho_RI = rBI2 * bondi_density_ / v_RI;
+      v_RI *= -sound_speed_;
+      const double vRI2_Pccs2 = v_RI * v_RI / (pressure_contrast_ * sound_speed_ * sound_speed_);
+      const double Pc_inv = 1. / pressure_contrast_;
+      const double sum = vRI2_Pccs2 + Pc_inv;
+      const double Gamma = 0.5 * (sum - std::sqrt(sum * sum - 4. * vRI2_Pccs2));
+      rho_I_ = Gamma * rho_RI;
+      v_I_ = v_RI / Gamma;
+    }
+  }
+  explicit BondiProfileDensityFunction(ParameterFile &params)
+      : BondiProfileDensityFunction(
+            params.get_physical_value<QUANTITY_MASS>("DensityFunction:central mass", "18. Msol"),
+            params.get_physical_value<QUANTITY_DENSITY>("DensityFunction:Bondi density", "1.e-19 g cm^-3"),
+            params.get_physical_value<QUANTITY_VELOCITY>("DensityFunction:sound speed", "2.031 km s^-1"),
+            params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:ionisation radius", "0. m"),
+            params.get_value<double>("DensityFunction:pressure contrast", 32.),
+            params.get_physical_vector<QUANTITY_LENGTH>("DensityFunction:center", "[0. m, 0. m, 0. m]"),
+            params.get_value<double>("DensityFunction:neutral fraction", 1.)) {
+    params.get_physical_value<QUANTITY_LENGTH>("DensityFunction:vprof radius", "0. m");
+    params.get_physical_value<QUANTITY_VELOCITY>("DensityFunction:vprof velocity", "0. m s^-1");
+  }
+  DensityValues operator()(const Vec3 &x) override {
+    const Vec3 relpos = {x[0] - center_[0], x[1] - center_[1], x[2] - center_[2]};
+    const double radius = std::sqrt(relpos[0] * relpos[0] + relpos[1] * relpos[1] + relpos[2] * relpos[2]);
+    const double inverse_radius = 1. / radius;
+    double density, pressure, profile_neutral_fraction;
+    const double rB = bondi_radius_ * inverse_radius;
+    if (rB < 184.5) { /* the solution diverges for very small radii (BondiProfile.hpp:171-175) */
+      const double rB2 = rB * rB;
+      const double lambertarg = -rB2 * rB2 * std::exp(3. - 4. * rB);
+      double v_cs;
+      if (radius > bondi_radius_) {
+        v_cs = std::sqrt(-lambert_w(lambertarg, 0));
+      } else if (radius < ionisation_radius_) {
+        const double RIr = ionisation_radius_ * inverse_radius;
+        const double RIr2 = RIr * RIr;
+        const double vI2_Pccs2 = v_I_ * v_I_ / (pressure_contrast_ * sound_speed_ * sound_speed_);
+        const double lambertarg2 =
+            -RIr2 * RIr2 * vI2_Pccs2 *
+            std::exp(4. * bondi_radius_ / pressure_contrast_ * (1. / ionisation_radius_ - inverse_radius) - vI2_Pccs2);
+        v_cs = std::sqrt(-pressure_contrast_ * lambert_w(lambertarg2, -1));
+      } else {
+        v_cs = std::sqrt(-lambert_w(lambertarg, -1));
+      }
+      const double vB = -v_cs * sound_speed_;
+      if (radius < ionisation_radius_) {
+        density = rho_I_ * ionisation_radius_ * ionisation_radius_ * v_I_ / (radius * radius * vB);
+        pressure = sound_speed_ * sound_speed_ * pressure_contrast_ * density;
+        profile_neutral_fraction = 0.;
+      } else {
+        density = rB2 * bondi_density_ / v_cs;
+        pressure = sound_speed_ * sound_speed_ * density;
+        profile_neutral_fraction = 1.;
+      }
+    } else {
+      density = bondi_density_;
+      pressure = sound_speed_ * sound_speed_ * density;
+      profile_neutral_fraction = 1.;
+    }
+    DensityValues v;
+    v.number_density = density / constants::proton_mass;
+    double temperature = constants::proton_mass * pressure / (constants::boltzmann * density);
+    if (profile_neutral_fraction < 0.5) temperature *= 0.5; /* ionised gas has a lower mean molecular mass */
+    v.temperature = temperature;
+    v.ionic_fraction[0] = neutral_fraction_;
+    v.ionic_fraction[1] = 1.e-6;
+    return v;
+  }
+
+private:
+  double bondi_radius_, bondi_density_, sound_speed_, ionisation_radius_, pressure_contrast_;
+  double rho_I_ = 0., v_I_ = 0.;
+  Vec3 center_;
+  double neutral_fraction_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -814,6 +927,7 @@ struct DensityFunctionFactory {
     if (type == "BlockSyntax") return new BlockSyntaxDensityFunction(params);
     if (type == "AsciiFile") return new AsciiFileDensityFunction(params);
     if (type == "Interpolated") return new InterpolatedDensityFunction(params);
+    if (type == "BondiProfile") return new BondiProfileDensityFunction(params);
     if (type == "CoredDMProfile") return new CoredDMProfileDensityFunction(params);
     if (type == "DiscIC") return new DiscICDensityFunction(params);
     if (type == "DiscPatch") return new DiscPatchDensityFunction(params);
@@ -821,7 +935,7 @@ struct DensityFunctionFactory {
     if (type == "CMacIonizeSnapshot") return new CMacIonizeSnapshotDensityFunction(params);
     if (type == "GadgetSnapshot") return new GadgetSnapshotDensityFunction(params, log);
     cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile, "
-              "Interpolated, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy, CMacIonizeSnapshot and GadgetSnapshot)!",
+              "Interpolated, BondiProfile, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy, CMacIonizeSnapshot and GadgetSnapshot)!",
               type.c_str());
   }
 };

@@ -138,6 +138,12 @@ def test_parameter_file_same_values_and_used_values_dump(host, ref, tmp_path):
 
 ANALYTIC_PROFILES = {
     # type -> (DensityFunction block, box half size in pc); defaults and non-default values
+    # BondiProfile: Lambert W on both branches (inside / outside the Bondi radius), with and without the ionised core
+    "bondi_defaults": ("  type: BondiProfile\n", 0.02),
+    # the ionised profile of the reference's testBondiProfile.cpp:56 (30 au ionisation radius, pressure contrast 32)
+    "bondi_ionised_core": ("  type: BondiProfile\n  central mass: 18. Msol\n  Bondi density: 1.e-16 kg m^-3\n"
+                           "  sound speed: 2.031 km s^-1\n  ionisation radius: 30. au\n  pressure contrast: 32.\n"
+                           "  center: [3. au, -5. au, 1. au]\n  neutral fraction: 0.9\n", 5.e-4),
     "cored_dm_defaults": ("  type: CoredDMProfile\n", 500.),
     "cored_dm": ("  type: CoredDMProfile\n  core radius: 120. pc\n  maximum circular velocity: 15. km s^-1\n"
                  "  central density: 2.e-21 g cm^-3\n  temperature: 8000. K\n  neutral fraction: 0.3\n"
@@ -236,6 +242,8 @@ def test_density_function_gives_the_reference_grid(host, ref, tmp_path, kind):
     assert np.isfinite(dens).all()
     if kind in ANALYTIC_PROFILES:
         assert np.unique(dens).size > 5 and dens.max() > 0
+    if kind == "bondi_ionised_core":   # cells inside and outside the ionised core: two temperatures
+        assert 20 < (temp > 4000.).sum() < temp.size and abs(temp.max() / temp.min() - 16.) < 1e-6   # P contrast 32, mu 1/2
     if kind in ("ascii_file", "interpolated_1d"):
         assert np.unique(dens).size > 20 and dens.min() >= 1e6 and dens.max() <= 3e8
     if kind == "lexington_blocks":
