@@ -139,6 +139,15 @@ class ParameterFile:
                                        x.ctypes.data_as(C.c_void_p), name, C.c_int(4096)))
         return name.value.decode()
 
+    def initial_grid(self, ncells):
+        """(number density, temperature, neutral H fraction) per cell after DensityFunction + DensityMask on the file's
+        grid: the path IonizationSimulation::initialize takes (whole-grid fills included), no device needed"""
+        dens, temp, xH = np.empty(ncells), np.empty(ncells), np.empty(ncells)
+        vp = C.c_void_p
+        _check(lib.cmih_initial_grid(self._h, C.c_int64(ncells), dens.ctypes.data_as(vp), temp.ctypes.data_as(vp),
+                                     xH.ctypes.data_as(vp)))
+        return dens, temp, xH
+
     def abundances(self):
         out = np.empty(6)
         _check(lib.cmih_abundances(self._h, out.ctypes.data_as(C.c_void_p)))

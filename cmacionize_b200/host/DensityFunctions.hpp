@@ -737,6 +737,10 @@ public:
     v.ionic_fraction[1] = 1.e-6;
     return v;
   }
+  /* the whole grid at once: particles are scattered over the cells their kernels reach (defined in DensityGrid.hpp).
+   * Same sums as operator() cell by cell, in particle order; the cost is the number of non-zero contributions,
+   * whatever the spread of the smoothing lengths */
+  bool set_densities(CartesianCells &grid) override;
   /* GadgetSnapshotDensityFunction::get_total_hydrogen_number (:366-372) */
   double get_total_hydrogen_number() const {
     double mtot = 0.;

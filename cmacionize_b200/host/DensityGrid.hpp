@@ -98,6 +98,71 @@ private:
   cmib_context *ctx_ = nullptr;
 };
 
+inline bool GadgetSnapshotDensityFunction::set_densities(CartesianCells &grid) {
+  const size_t ncell = grid.get_number_of_cells();
+  const std::array<int32_t, 3> &nc = grid.get_number_of_cells_3d();
+  const Vec3 &anchor = grid.get_box_anchor(), &sides = grid.get_box_sides();
+  const double cs[3] = {sides[0] / nc[0], sides[1] / nc[1], sides[2] / nc[2]};
+  const bool with_x = !neutral_fractions_.empty();
+  std::vector<double> density(ncell, 0.), temperature(ncell, 0.), neutral(with_x ? ncell : 0, 0.);
+  const size_t n = masses_.size();
+  const int kmax = periodic_ ? 1 : 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double h = smoothing_lengths_[i], m = masses_[i];
+    const double p[3] = {positions_[3 * i], positions_[3 * i + 1], positions_[3 * i + 2]};
+    for (int kx = -kmax; kx <= kmax; ++kx)
+      for (int ky = -kmax; ky <= kmax; ++ky)
+        for (int kz = -kmax; kz <= kmax; ++kz) {
+          const int k[3] = {kx, ky, kz};
+          /* cells whose midpoints anchor + (j + 1/2) cs can lie within h of this image of the particle */
+          long lo[3], hi[3];
+          bool empty = false;
+          for (int d = 0; d < 3; ++d) {
+            const double q = p[d] + k[d] * sides_[d];
+            lo[d] = (long)std::ceil((q - h - anchor[d]) / cs[d] - 0.5) - 1; /* one cell of slack against rounding */
+            hi[d] = (long)std::floor((q + h - anchor[d]) / cs[d] - 0.5) + 1;
+            lo[d] = std::max(lo[d], 0l);
+            hi[d] = std::min(hi[d], (long)nc[d] - 1);
+            empty = empty || lo[d] > hi[d];
+          }
+          if (empty) continue;
+          for (long ix = lo[0]; ix <= hi[0]; ++ix)
+            for (long iy = lo[1]; iy <= hi[1]; ++iy)
+              for (long iz = lo[2]; iz <= hi[2]; ++iz) {
+                const size_t cell = ((size_t)ix * nc[1] + iy) * nc[2] + iz;
+                const Vec3 x = grid.get_cell_midpoint(cell);
+                double c[3];
+                bool nearest = true;
+                for (int d = 0; d < 3; ++d) {
+                  c[d] = x[d] - p[d];
+                  if (periodic_) { /* Box::periodic_distance; the pair counts for the image it picks */
+                    const double c0 = c[d];
+                    if (2 * c[d] < -sides_[d]) c[d] += sides_[d];
+                    if (2 * c[d] >= sides_[d]) c[d] -= sides_[d];
+                    nearest = nearest && (int)std::lround((c0 - c[d]) / sides_[d]) == k[d];
+                  }
+                }
+                if (!nearest) continue;
+                const double r = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+                const double u = r / h;
+                if (!(u < 1.)) continue;
+                const double splineval = m * kernel_evaluate(u, h);
+                density[cell] += splineval;
+                temperature[cell] += splineval * temperatures_[i] / densities_[i];
+                if (with_x) neutral[cell] += splineval * neutral_fractions_[i];
+              }
+        }
+  }
+  for (size_t cidx = 0; cidx < ncell; ++cidx) {
+    grid.number_density[cidx] = density[cidx] / 1.6737236e-27;
+    grid.temperature[cidx] = temperature[cidx];
+    for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) grid.ionic_fraction[(size_t)ion * ncell + cidx] = 0.;
+    grid.ionic_fraction[cidx] = with_x ? neutral[cidx] / density[cidx] : 1.e-6;
+    grid.ionic_fraction[ncell + cidx] = 1.e-6;
+  }
+  return true;
+}
+
 /* ---- DensityMask ---- */
 /*
  * FractalDensityMask (src/FractalDensityMask.hpp:60-470, Elmegreen 1997): N^levels points placed by a

@@ -313,6 +313,28 @@ int cmih_hdf5_exists(const char *filename, const char *path, int *out) {
     *out = file.exists(path) ? 1 : 0;
   });
 }
+/* as cmih_initial_number_density, with the temperature and the neutral fraction of hydrogen of every cell */
+int cmih_initial_grid(void *h, int64_t n, double *dens, double *temp, double *xH) {
+  CMIH_TRY({
+    ParameterFile &p = *static_cast<ParameterFile *>(h);
+    std::unique_ptr<DensityFunction> f(DensityFunctionFactory::generate(p));
+    std::unique_ptr<FractalDensityMask> mask(DensityMaskFactory::generate(p));
+    const SimulationBox box(p);
+    CartesianCells cells(box, p.get_value<std::array<int32_t, 3>>("DensityGrid:number of cells", {64, 64, 64}));
+    if ((int64_t)cells.get_number_of_cells() != n) throw std::runtime_error("wrong number of cells");
+    f->initialize();
+    cells.set_densities(*f);
+    if (mask) {
+      mask->initialize();
+      mask->apply(cells);
+    }
+    for (int64_t i = 0; i < n; ++i) {
+      dens[i] = cells.number_density[i];
+      temp[i] = cells.temperature[i];
+      xH[i] = cells.ionic_fraction[i];
+    }
+  });
+}
 /* AbundanceModelFactory on the parameter file -> He C N O Ne S relative to H */
 int cmih_abundances(void *h, double *out) {
   CMIH_TRY({

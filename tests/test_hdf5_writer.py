@@ -401,6 +401,7 @@ def test_snapshot_density_function_on_a_snapshot_of_the_reference(host, tmp_path
 # ---------------------------------------------------------------- SPH snapshots (DensityFunction GadgetSnapshot)
 def _gadget_param(tmp_path, snapshot, anchor, sides, ncell, extra=""):
     pf = tmp_path / "gadget.param"
+    anchor, sides = [float(v) for v in anchor], [float(v) for v in sides]
     pf.write_text(f"SimulationBox:\n  anchor: [{anchor[0]!r} m, {anchor[1]!r} m, {anchor[2]!r} m]\n"
                   f"  sides: [{sides[0]!r} m, {sides[1]!r} m, {sides[2]!r} m]\n  periodicity: [false, false, false]\n"
                   f"DensityGrid:\n  type: Cartesian\n  number of cells: [{ncell[0]}, {ncell[1]}, {ncell[2]}]\n"
@@ -487,6 +488,14 @@ def test_gadget_snapshot_density_function_on_synthetic_particles(host, ref, tmp_
             assert np.abs(x[inside] / rx[inside] - 1.).max() < 1e-12
         else:
             assert (x == 1e-6).all()
+        # the grid fill of a run (particles scattered over the cells) gives the same cells as the point queries
+        p = host.ParameterFile(_gadget_param(tmp_path, snap, anchor, sides, ncell,
+                                             "  use neutral fraction: true\n" if use_x else ""))
+        gd, gT, gx = p.initial_grid(len(q))
+        p.close()
+        assert np.array_equal(gd == 0, dens == 0) and np.abs(gd[inside] / dens[inside] - 1.).max() < 1e-12
+        assert np.abs(gT[inside] / temp[inside] - 1.).max() < 1e-12 and (gT[~inside] == 0).all()
+        assert np.abs(gx[inside] / x[inside] - 1.).max() < 1e-12
 
 
 def test_gadget_snapshot_source_distribution(host, tmp_path):
