@@ -149,6 +149,57 @@ IonizationSimulation:
     assert x2[0].min() < 1e-3 and x2[0].max() > 0.9
 
 
+def test_sph_snapshot_in_hdf5_snapshot_out(host, tmp_path):
+    """The post-processing workflow of the reference on an SPH snapshot: gas particles -> grid (DensityFunction
+    GadgetSnapshot), star particles -> sources (PhotonSourceDistribution GadgetSnapshot, RateBased luminosities), the
+    iteration on the GPU, a Gadget-style HDF5 snapshot out.  Synthetic particles of uniform mean density around one
+    star: the Stromgren sphere of that density comes out."""
+    import h5mini
+    rng = np.random.default_rng(12)
+    N, L = 40000, 10 * PC
+    pos = rng.uniform(0., L, (N, 3))
+    m_H = 1.6737236e-27
+    mass = np.full(N, 1e8 * m_H * L ** 3 / N)                        # mean density 100 cm^-3
+    h = np.full(N, 2.2 * L / N ** (1. / 3.))
+    rho = np.full(N, 1e8 * m_H)
+    rate = 2.49428e16
+    snap = tmp_path / "sph.hdf5"
+    host.write_particle_snapshot(snap, pos, mass, h, rho, T=np.full(N, 8000.), periodic=1, boxsize=(L, L, L),
+                                 units_cgs=(100., 1000., 1.), time=1., stars=([[0.5 * L] * 3], [1.], [4.26e49 / rate]))
+    nc, npk, nit = 32, 300000, 6
+    text = STROMGREN_PARAM.format(nc=nc, npk=npk, nit=nit, seed=8, extra=f"""DensityGridWriter:
+  type: Gadget
+  prefix: sph_
+IonizationSimulation:
+  output folder: {tmp_path}
+""")
+    text = text.replace("anchor: [-5. pc, -5. pc, -5. pc]", "anchor: [0. pc, 0. pc, 0. pc]")
+    block = "  type: Homogeneous\n  density: 100. cm^-3\n  temperature: 8000. K\n"
+    assert block in text and "type: SingleStar" in text
+    text = text.replace(block, f"  type: GadgetSnapshot\n  filename: {snap}\n")
+    head, tail = text.split("PhotonSourceDistribution:", 1)
+    rest = tail.split("\n")
+    k = next(i for i, line in enumerate(rest[1:], 1) if line and not line.startswith(" "))
+    text = head + f"PhotonSourceDistribution:\n  type: GadgetSnapshot\n  filename: {snap}\n" + "\n".join(rest[k:])
+    pf = tmp_path / "sph.param"
+    pf.write_text(text)
+    sim = host.IonizationSimulation(pf, write_output=True)
+    assert sim.total_luminosity == 4.26e49
+    sim.initialize()
+    n0, T0, x0, _ = sim.fields()
+    # (the particles carry the nominal density, so the kernel-weighted temperature follows the local density)
+    assert abs(n0.mean() / 1e8 - 1.) < 0.02 and 0.05 < n0.std() / n0.mean() < 0.5 and abs(T0.mean() / 8000. - 1.) < 0.02
+    sim.run()
+    sim.close()
+    f = h5mini.File(tmp_path / f"sph_{nit:03d}.hdf5")
+    coords, xH = f["PartType0"]["Coordinates"].read(), f["PartType0"]["NeutralFractionH"].read()
+    assert np.array_equal(f["PartType0"]["NumberDensity"].read(), n0)
+    radius = np.sqrt(((coords - 0.5 * L) ** 2).sum(1))
+    Rs = (0.75 * 4.26e49 / (np.pi * (1e8) ** 2 * 4e-19)) ** (1. / 3.)
+    assert xH[radius < 0.5 * Rs].max() < 0.05 and np.median(xH[radius > 1.4 * Rs]) > 0.9
+    assert abs(stromgren_radius(xH, radius) - Rs) < 1.5 * L / nc    # clumpy SPH density: the front is rougher
+
+
 def test_two_gpu_driver_equals_one_gpu(host, tmp_path):
     """C++ driver on 2 GPUs (packets split by global id, one ncclAllReduce per iteration, replicated
     state update) == the same parameter file on 1 GPU: same packets, sums equal up to order."""
