@@ -923,6 +923,97 @@ private:
   double neutral_fraction_;
 };
 
+/* Block-structured AMR snapshot of FLASH (FLASHSnapshotDensityFunction.cpp:60-215, :228-241): the leaf blocks
+ * (node type 1) of "bounding box" / "dens" / "temp" with the box and block counts of the runtime parameter tables,
+ * CGS units; a position gets the values of the FLASH cell that contains it (the reference inserts every cell into
+ * an AMR tree by the key of its centre and looks positions up in that tree: the same cell).  `temperature` > 0
+ * overrides the snapshot's temperatures; the cosmic-ray heating variant needs the AMR neighbour search and is refused. */
+class FLASHSnapshotDensityFunction : public DensityFunction {
+public:
+  FLASHSnapshotDensityFunction(std::string filename, double temperature, bool read_cosmic_ray_heating)
+      : filename_(std::move(filename)), temperature_(temperature) {
+    if (read_cosmic_ray_heating)
+      cmi_error("DensityFunction:read cosmic ray heating is not provided by the B200 backend!");
+  }
+  explicit FLASHSnapshotDensityFunction(ParameterFile &params)
+      : FLASHSnapshotDensityFunction(params.get_filename("DensityFunction:filename"),
+                                     params.get_physical_value<QUANTITY_TEMPERATURE>("DensityFunction:temperature", "-1. K"),
+                                     params.get_value<bool>("DensityFunction:read cosmic ray heating", false)) {}
+  void initialize() override {
+    hdf5::HDF5Input file(filename_);
+    const double unit_length_in_SI = UnitConverter::to_SI(QUANTITY_LENGTH, 1., "cm");
+    const double unit_density_in_SI = UnitConverter::to_SI(QUANTITY_DENSITY, 1., "g cm^-3");
+    const std::map<std::string, double> real_pars = file.read_dictionary("real runtime parameters");
+    auto par = [&](const char *name) {
+      const auto it = real_pars.find(name);
+      if (it == real_pars.end()) cmi_error("Snapshot \"%s\": no runtime parameter \"%s\"!", filename_.c_str(), name);
+      return it->second;
+    };
+    const char *lo_names[3] = {"xmin", "ymin", "zmin"}, *hi_names[3] = {"xmax", "ymax", "zmax"};
+    for (int d = 0; d < 3; ++d) {
+      anchor_[d] = par(lo_names[d]) * unit_length_in_SI;
+      top_[d] = par(hi_names[d]) * unit_length_in_SI;
+    }
+    std::vector<uint64_t> edims, ddims;
+    const std::vector<double> extents = file.read_dataset("bounding box", &edims);
+    densities_ = file.read_dataset("dens", &ddims);
+    if (temperature_ <= 0.) temperatures_ = file.read_dataset("temp");
+    const std::vector<double> nodetypes = file.read_dataset("node type");
+    if (edims.size() != 3 || edims[1] != 3 || edims[2] != 2 || ddims.size() != 4 || ddims[0] != edims[0] ||
+        nodetypes.size() != edims[0] || (temperature_ <= 0. && temperatures_.size() != densities_.size()))
+      cmi_error("Snapshot \"%s\" does not have the layout of a FLASH file!", filename_.c_str());
+    for (int d = 0; d < 3; ++d) ncell_[d] = ddims[3 - d]; /* "dens" is [block][z][y][x] */
+    for (size_t i = 0; i < edims[0]; ++i) {
+      if (nodetypes[i] != 1.) continue;
+      Block b;
+      b.index = i;
+      for (int d = 0; d < 3; ++d) {
+        b.anchor[d] = extents[(i * 3 + d) * 2] * unit_length_in_SI;
+        b.sides[d] = extents[(i * 3 + d) * 2 + 1] * unit_length_in_SI - b.anchor[d];
+      }
+      blocks_.push_back(b);
+    }
+    if (blocks_.empty()) cmi_error("Snapshot \"%s\" holds no leaf blocks!", filename_.c_str());
+    for (double &rho : densities_) rho *= unit_density_in_SI;
+  }
+  DensityValues operator()(const Vec3 &x) override {
+    for (const Block &b : blocks_) {
+      size_t c[3];
+      bool inside = true;
+      for (int d = 0; d < 3 && inside; ++d) {
+        const double f = (x[d] - b.anchor[d]) / b.sides[d];
+        inside = f >= 0. && f < 1.;
+        if (inside) c[d] = std::min((size_t)(f * ncell_[d]), (size_t)ncell_[d] - 1);
+      }
+      if (!inside) continue;
+      const size_t at = ((b.index * ncell_[2] + c[2]) * ncell_[1] + c[1]) * ncell_[0] + c[0];
+      DensityValues v;
+      v.number_density = densities_[at] / 1.6737236e-27;
+      v.temperature = (temperature_ <= 0.) ? temperatures_[at] : temperature_;
+      v.ionic_fraction[0] = 1.e-6;
+      v.ionic_fraction[1] = 1.e-6;
+      return v;
+    }
+    cmi_error("Position [%g m, %g m, %g m] lies outside the blocks of snapshot \"%s\"!", x[0], x[1], x[2], filename_.c_str());
+  }
+  size_t get_number_of_leaf_blocks() const { return blocks_.size(); }
+  /* the whole grid at once: every leaf block hands its cells to the grid cells whose midpoints it contains (defined
+   * in DensityGrid.hpp); same cells as operator(), without a search over the blocks per cell */
+  bool set_densities(CartesianCells &grid) override;
+
+private:
+  struct Block {
+    size_t index;
+    double anchor[3], sides[3];
+  };
+  std::string filename_;
+  double temperature_;
+  Vec3 anchor_ = {0., 0., 0.}, top_ = {0., 0., 0.};
+  uint64_t ncell_[3] = {1, 1, 1};
+  std::vector<Block> blocks_;
+  std::vector<double> densities_, temperatures_;
+};
+
 struct DensityFunctionFactory {
   static DensityFunction *generate(ParameterFile &params, Log *log = nullptr) {
     const std::string type = params.get_value<std::string>("DensityFunction:type", "Homogeneous");
@@ -938,8 +1029,9 @@ struct DensityFunctionFactory {
     if (type == "SpiralGalaxy") return new SpiralGalaxyDensityFunction(params);
     if (type == "CMacIonizeSnapshot") return new CMacIonizeSnapshotDensityFunction(params);
     if (type == "GadgetSnapshot") return new GadgetSnapshotDensityFunction(params, log);
+    if (type == "FLASHSnapshot") return new FLASHSnapshotDensityFunction(params);
     cmi_error("Unknown DensityFunction type: \"%s\" (the B200 backend provides Homogeneous, BlockSyntax, AsciiFile, "
-              "Interpolated, BondiProfile, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy, CMacIonizeSnapshot and GadgetSnapshot)!",
+              "Interpolated, BondiProfile, CoredDMProfile, DiscIC, DiscPatch, SpiralGalaxy, CMacIonizeSnapshot, GadgetSnapshot and FLASHSnapshot)!",
               type.c_str());
   }
 };

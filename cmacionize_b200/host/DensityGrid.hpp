@@ -163,6 +163,52 @@ inline bool GadgetSnapshotDensityFunction::set_densities(CartesianCells &grid) {
   return true;
 }
 
+inline bool FLASHSnapshotDensityFunction::set_densities(CartesianCells &grid) {
+  const size_t ncell = grid.get_number_of_cells();
+  const std::array<int32_t, 3> &nc = grid.get_number_of_cells_3d();
+  const Vec3 &anchor = grid.get_box_anchor(), &sides = grid.get_box_sides();
+  const double cs[3] = {sides[0] / nc[0], sides[1] / nc[1], sides[2] / nc[2]};
+  std::vector<char> filled(ncell, 0);
+  for (const Block &b : blocks_) {
+    long lo[3], hi[3];
+    bool empty = false;
+    for (int d = 0; d < 3; ++d) { /* midpoints anchor + (j + 1/2) cs inside [b.anchor, b.anchor + b.sides), one cell of slack */
+      lo[d] = std::max((long)std::ceil((b.anchor[d] - anchor[d]) / cs[d] - 0.5) - 1, 0l);
+      hi[d] = std::min((long)std::floor((b.anchor[d] + b.sides[d] - anchor[d]) / cs[d] - 0.5) + 1, (long)nc[d] - 1);
+      empty = empty || lo[d] > hi[d];
+    }
+    if (empty) continue;
+    for (long ix = lo[0]; ix <= hi[0]; ++ix)
+      for (long iy = lo[1]; iy <= hi[1]; ++iy)
+        for (long iz = lo[2]; iz <= hi[2]; ++iz) {
+          const size_t cell = ((size_t)ix * nc[1] + iy) * nc[2] + iz;
+          if (filled[cell]) continue; /* operator() takes the first block that contains the position */
+          const Vec3 x = grid.get_cell_midpoint(cell);
+          size_t c[3];
+          bool inside = true;
+          for (int d = 0; d < 3 && inside; ++d) {
+            const double f = (x[d] - b.anchor[d]) / b.sides[d];
+            inside = f >= 0. && f < 1.;
+            if (inside) c[d] = std::min((size_t)(f * ncell_[d]), (size_t)ncell_[d] - 1);
+          }
+          if (!inside) continue;
+          const size_t at = ((b.index * ncell_[2] + c[2]) * ncell_[1] + c[1]) * ncell_[0] + c[0];
+          grid.number_density[cell] = densities_[at] / 1.6737236e-27;
+          grid.temperature[cell] = (temperature_ <= 0.) ? temperatures_[at] : temperature_;
+          for (int ion = 0; ion < CMIB_NUM_IONS; ++ion) grid.ionic_fraction[(size_t)ion * ncell + cell] = 0.;
+          grid.ionic_fraction[cell] = 1.e-6;
+          grid.ionic_fraction[ncell + cell] = 1.e-6;
+          filled[cell] = 1;
+        }
+  }
+  for (size_t cell = 0; cell < ncell; ++cell)
+    if (!filled[cell]) {
+      const Vec3 x = grid.get_cell_midpoint(cell);
+      cmi_error("Position [%g m, %g m, %g m] lies outside the blocks of snapshot \"%s\"!", x[0], x[1], x[2], filename_.c_str());
+    }
+  return true;
+}
+
 /* ---- DensityMask ---- */
 /*
  * FractalDensityMask (src/FractalDensityMask.hpp:60-470, Elmegreen 1997): N^levels points placed by a

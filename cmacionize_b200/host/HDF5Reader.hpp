@@ -80,6 +80,32 @@ public:
     convert(a.type, data_ + a.data, a.count, out.data());
     return out;
   }
+  /* HDF5Tools::read_dictionary (HDF5Tools.hpp:1228-1333): a 1-D dataset of {name, value} compounds (the runtime
+   * parameter tables of FLASH) as a map; trailing blanks of the names are stripped */
+  std::map<std::string, double> read_dictionary(const std::string &path) const {
+    const Object o = open_object(path);
+    if (!o.has_layout || !o.has_type || !o.has_space || o.type.cls != 6 || o.type.members.size() != 2 ||
+        o.type.members[0].cls != 3 || (o.type.members[1].cls != 0 && o.type.members[1].cls != 1))
+      fail("\"" + path + "\" is not a {name, value} table");
+    if (o.layout_class != 1 || o.layout_address == UNDEFINED) fail("\"" + path + "\": only contiguous tables are read");
+    uint64_t n = 1;
+    for (uint64_t d : o.dims) n *= d;
+    check(o.layout_address, n * o.type.size);
+    std::map<std::string, double> out;
+    const Member &key = o.type.members[0], &val = o.type.members[1];
+    Datatype vt;
+    vt.cls = val.cls; vt.size = val.size; vt.is_signed = val.is_signed;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint8_t *e = data_ + o.layout_address + i * o.type.size;
+      const char *name = reinterpret_cast<const char *>(e + key.offset);
+      std::string k(name, strnlen(name, key.size));
+      while (!k.empty() && k.back() == ' ') k.pop_back();
+      double v;
+      convert(vt, e + val.offset, 1, &v);
+      out[k] = v;
+    }
+    return out;
+  }
   /* a dataset as doubles (whatever numeric type it has on disk), row major; dims gets its shape */
   std::vector<double> read_dataset(const std::string &path, std::vector<uint64_t> *dims = nullptr) const {
     const Object o = open_object(path);
@@ -109,10 +135,19 @@ public:
 
 private:
   static constexpr uint64_t UNDEFINED = ~uint64_t(0);
+  struct Datatype;
+  struct Member {
+    std::string name;
+    uint32_t offset = 0;
+    int cls = -1; /* the member's own (simple) type */
+    uint32_t size = 0;
+    bool is_signed = false;
+  };
   struct Datatype {
     int cls = -1;
     uint32_t size = 0;
     bool is_signed = false;
+    std::vector<Member> members; /* class 6 (compound, version 1) with simple members */
   };
   struct Attribute {
     std::string name;
@@ -154,8 +189,30 @@ private:
       t.is_signed = (bits0 & 8) != 0;
       if (t.cls == 1 && t.size != 8 && t.size != 4) fail("a floating point type that is not 4 or 8 bytes");
       if (t.cls == 0 && t.size != 1 && t.size != 2 && t.size != 4 && t.size != 8) fail("an unusual integer size");
+    } else if (t.cls == 6) {
+      /* compound, version 1: per member a name padded to 8 bytes, byte offset, dimensionality (+ 31 bytes of
+       * array information), then the member's own datatype message */
+      if ((u8(o) >> 4) != 1) fail("compound datatype version " + std::to_string(u8(o) >> 4));
+      const uint16_t nmembers = u16(o + 1);
+      uint64_t q = o + 8;
+      for (uint16_t k = 0; k < nmembers; ++k) {
+        Member m;
+        check(q, 1);
+        const char *name = reinterpret_cast<const char *>(data_ + q);
+        const size_t len = strnlen(name, size_ - q);
+        m.name.assign(name, len);
+        q += pad8(len + 1);
+        m.offset = u32(q);
+        if (u8(q + 4) != 0) fail("array members of compound datatypes");
+        q += 32;
+        const Datatype mt = parse_datatype(q);
+        if (mt.cls == 6) fail("nested compound datatypes");
+        m.cls = mt.cls; m.size = mt.size; m.is_signed = mt.is_signed;
+        q += 8 + (mt.cls == 0 ? 4 : (mt.cls == 1 ? 12 : 0));
+        t.members.push_back(m);
+      }
     } else if (t.cls != 3) {
-      fail("datatype class " + std::to_string(t.cls) + " (only integers, floats and fixed-length strings are read)");
+      fail("datatype class " + std::to_string(t.cls) + " (only integers, floats, fixed-length strings and compounds of those are read)");
     }
     return t;
   }

@@ -542,3 +542,39 @@ def test_gadget_snapshot_source_distribution(host, tmp_path):
         for v in L[keep]:
             tot += v
         assert lum == tot and np.array_equal(w, L[keep] / tot)
+
+
+def test_flash_snapshot_density_function_reproduces_the_reference_test(host, tmp_path):
+    """testFLASHSnapshotDensityFunction.cpp:52-73 on test/FLASHtest.hdf5 (82 blocks of 8^3 cells, float32 data, the box
+    and the block counts in {name, value} compound tables): the same 128 positions, the same statistic against the
+    analytic density the file was made from (the reference asserts xi2 = 0.0106294), temperature 4000 K everywhere.
+    Then the grid fill of a run against the point queries, cell for cell."""
+    f = h5mini.File(GOLD / "FLASHtest.hdf5")
+    assert f["node type"].read().shape == (82,) and f["dens"].space.shape == (82, 8, 8, 8)
+    pf = tmp_path / "flash.param"
+    # (a box slightly inside the snapshot's, so that no cell midpoint sits exactly on a FLASH cell boundary)
+    pf.write_text("SimulationBox:\n  anchor: [1.3e-4 m, 0.7e-4 m, 0.9e-4 m]\n  sides: [0.0195 m, 0.0097 m, 0.0096 m]\n"
+                  "  periodicity: [false, false, false]\n"
+                  "DensityGrid:\n  type: Cartesian\n  number of cells: [21, 13, 11]\n"
+                  f"DensityFunction:\n  type: FLASHSnapshot\n  filename: {GOLD / 'FLASHtest.hdf5'}\n")
+    i = np.arange(128)
+    q = np.stack([(i + 0.5) * 0.02 / 128, (i + 0.5) * 0.01 / 128, (i + 0.5) * 0.01 / 128], 1)
+    p = host.ParameterFile(pf)
+    dens, T, xH = p.density_function(q)
+    expected = (1. + 100. * q[:, 0] + 100. * q[:, 1] + 100. * q[:, 2]) * 1.e3 / 1.6737236e-27
+    xi2 = (((dens - expected) / (dens + expected)) ** 2).sum()
+    assert abs(xi2 / 0.0106294 - 1.) < 1e-5 and (T == 4000.).all() and (xH == 1e-6).all()
+    m = _grid_midpoints((1.3e-4, 0.7e-4, 0.9e-4), (0.0195, 0.0097, 0.0096), (21, 13, 11))
+    d1, T1, x1 = p.density_function(m)
+    d2, T2, x2 = p.initial_grid(len(m))
+    p.close()
+    assert np.array_equal(d1, d2) and np.array_equal(T1, T2) and np.array_equal(x1, x2) and np.unique(d2).size > 50
+    pf.write_text(pf.read_text() + "  temperature: 7500. K\n")
+    p = host.ParameterFile(pf)
+    assert (p.initial_grid(len(m))[1] == 7500.).all()
+    p.close()
+    pf.write_text(pf.read_text().replace("sides: [0.0195 m,", "sides: [0.03 m,"))
+    p = host.ParameterFile(pf)
+    with pytest.raises(Exception, match="lies outside the blocks"):
+        p.initial_grid(len(m))
+    p.close()
