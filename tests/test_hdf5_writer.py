@@ -578,3 +578,25 @@ def test_flash_snapshot_density_function_reproduces_the_reference_test(host, tmp
     with pytest.raises(Exception, match="lies outside the blocks"):
         p.initial_grid(len(m))
     p.close()
+
+
+@pytest.mark.parametrize("hrange", [(0.05, 0.3), (0.3, 0.45), (0.5, 0.9)])
+def test_gadget_snapshot_periodic_box_with_kernels_as_large_as_the_box(host, ref, tmp_path, hrange):
+    """periodic unit box, smoothing lengths up to 0.9 of the box side (3, 2 and 1 search bins per axis; beyond half the
+    box only the nearest image counts, Box::periodic_distance): point queries and the grid fill against the reference's
+    Octree + CubicSplineKernel"""
+    rng = np.random.default_rng(3)
+    N = 300
+    pos, h = rng.uniform(0., 1., (N, 3)), rng.uniform(hrange[0], hrange[1], N)
+    m, rho, T, xH = rng.uniform(1., 2., N), rng.uniform(1., 2., N), rng.uniform(10., 100., N), rng.uniform(0., 1., N)
+    snap = tmp_path / "periodic.hdf5"
+    host.write_particle_snapshot(snap, pos, m, h, rho, T, xH, periodic=1, boxsize=(1., 1., 1.))
+    ncell = (7, 6, 5)
+    q = _grid_midpoints((0., 0., 0.), (1., 1., 1.), ncell)
+    p = host.ParameterFile(_gadget_param(tmp_path, snap, (0., 0., 0.), (1., 1., 1.), ncell, "  use neutral fraction: true\n"))
+    dens, temp, x = p.density_function(q)
+    gd, gT, gx = p.initial_grid(len(q))
+    p.close()
+    rd, rT, rx = ref.gadget_kernel_sums(pos, m, h, rho, T, xH, True, (1., 1., 1.), q)
+    for mine, theirs in ((dens, rd), (temp, rT), (x, rx), (gd, rd), (gT, rT), (gx, rx)):
+        assert np.abs(mine / theirs - 1.).max() < 1e-13
