@@ -2,7 +2,8 @@
 
 Reads what the reference's snapshot files and `host/HDF5Writer.hpp` contain: superblock version 0,
 symbol-table groups (B-tree v1 + SNOD + local heap), version-1 object headers with continuation
-blocks, attributes (version 1 messages), fixed-point / IEEE float / fixed-length string datatypes,
+blocks, attributes (version 1 messages), fixed-point / IEEE float / fixed-length string datatypes and compounds of
+those,
 simple and scalar dataspaces, contiguous, compact and unfiltered chunked layouts.
 
 Pinned on files written by the real library: `tests/golden/hdf5/` holds copies of the reference's own
@@ -49,6 +50,24 @@ class Datatype:
             self.dtype = np.dtype("S" + str(self.size))
             self.padding = self.bits[0] & 0x0F
             self.nbytes = 8
+        elif self.cls == 6:     # compound, version 1, simple members: a numpy structured type
+            if self.version != 1:
+                raise H5Error(f"compound datatype version {self.version}")
+            nmembers = struct.unpack_from("<H", buf, off + 1)[0]
+            q, names, formats, offsets = off + 8, [], [], []
+            for _ in range(nmembers):
+                end = buf.index(b"\0", q)
+                names.append(bytes(buf[q:end]).decode())
+                q += _pad8(end - q + 1)
+                offsets.append(struct.unpack_from("<I", buf, q)[0])
+                if buf[q + 4] != 0:
+                    raise H5Error("array members of compound datatypes not supported")
+                q += 32
+                m = Datatype(buf, q)
+                formats.append(m.dtype)
+                q += m.nbytes
+            self.dtype = np.dtype({"names": names, "formats": formats, "offsets": offsets, "itemsize": self.size})
+            self.nbytes = q - off
         else:
             raise H5Error(f"datatype class {self.cls} not supported")
 

@@ -551,6 +551,9 @@ def test_flash_snapshot_density_function_reproduces_the_reference_test(host, tmp
     Then the grid fill of a run against the point queries, cell for cell."""
     f = h5mini.File(GOLD / "FLASHtest.hdf5")
     assert f["node type"].read().shape == (82,) and f["dens"].space.shape == (82, 8, 8, 8)
+    real = {r["name"].decode().strip(): float(r["value"]) for r in f["real runtime parameters"].read()}
+    integer = {r["name"].decode().strip(): int(r["value"]) for r in f["integer runtime parameters"].read()}
+    assert (real["xmin"], real["xmax"], real["ymax"], real["zmax"]) == (0., 2., 1., 1.) and integer["nblockx"] == 2
     pf = tmp_path / "flash.param"
     # (a box slightly inside the snapshot's, so that no cell midpoint sits exactly on a FLASH cell boundary)
     pf.write_text("SimulationBox:\n  anchor: [1.3e-4 m, 0.7e-4 m, 0.9e-4 m]\n  sides: [0.0195 m, 0.0097 m, 0.0096 m]\n"
