@@ -324,6 +324,7 @@ private:
   std::map<std::string, uint64_t> links(const Object &g) const {
     std::map<std::string, uint64_t> out;
     if (!g.is_group) fail("a path component that is not a group");
+    check(g.heap, 32);
     if (memcmp(data_ + g.heap, "HEAP", 4) != 0) fail("a bad local heap");
     const uint64_t segment = u64(g.heap + 24);
     if (g.btree != UNDEFINED) walk_group_node(g.btree, segment, out, 0);
