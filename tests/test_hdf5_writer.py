@@ -603,3 +603,57 @@ def test_gadget_snapshot_periodic_box_with_kernels_as_large_as_the_box(host, ref
     rd, rT, rx = ref.gadget_kernel_sums(pos, m, h, rho, T, xH, True, (1., 1., 1.), q)
     for mine, theirs in ((dens, rd), (temp, rT), (x, rx), (gd, rd), (gT, rT), (gx, rx)):
         assert np.abs(mine / theirs - 1.).max() < 1e-13
+
+
+FUZZ = r"""
+import sys, pathlib, numpy as np
+sys.path.insert(0, sys.argv[1])
+from cmacionize_b200 import host
+src, tmp, rng = pathlib.Path(sys.argv[2]).read_bytes(), pathlib.Path(sys.argv[3]), np.random.default_rng(int(sys.argv[4]))
+errors = 0
+for k in range(int(sys.argv[5])):
+    b = bytearray(src)
+    mode = rng.integers(0, 3)
+    if mode == 0:
+        b = b[:int(rng.integers(96, len(b)))]
+    elif mode == 1:
+        for _ in range(int(rng.integers(1, 8))):
+            b[int(rng.integers(8, min(len(b), 20000)))] = int(rng.integers(0, 256))
+    else:
+        for _ in range(int(rng.integers(1, 4))):
+            p = int(rng.integers(8, min(len(b), 20000) - 8))
+            b[p:p + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+    f = tmp / f"mutant{k}.hdf5"
+    f.write_bytes(bytes(b))
+    h = host.HDF5Input(f)
+    for path in ("/PartType0/Coordinates", "/PartType0/Density", "/PartType0/NumberDensity", "/PartType0/Temperature", "/dens"):
+        try:
+            if h.exists(path):
+                h.dataset(path)
+        except (host.HostError, UnicodeDecodeError):
+            errors += 1
+    for g in ("/Header", "/Parameters", "/Units"):
+        try:
+            for a in (h.attribute_names(g)[:5] if h.exists(g) else []):
+                try:
+                    h.numeric_attribute(g, a)
+                except (host.HostError, UnicodeDecodeError):
+                    errors += 1
+        except (host.HostError, UnicodeDecodeError):
+            errors += 1
+    f.unlink()
+print("survived", errors)
+"""
+
+
+@pytest.mark.parametrize("name", ["test.hdf5", "taskbased.hdf5", "FLASHtest.hdf5"])
+def test_reader_survives_truncated_and_corrupted_files(host, tmp_path, name):
+    """Snapshots come from other codes and from interrupted runs: a truncated file, flipped bytes or garbage addresses
+    must end in an error message, never in a crash of the process that holds the GPU context (every offset and size the
+    reader follows is checked against the mapped file).  80 mutants per file, in a child process."""
+    script = tmp_path / "fuzz.py"
+    script.write_text(FUZZ)
+    out = subprocess.run([sys.executable, str(script), str(ROOT), str(GOLD / name), str(tmp_path), "7", "80"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stderr[-1500:])
+    assert out.stdout.strip().startswith("survived") and int(out.stdout.split()[-1]) > 0
