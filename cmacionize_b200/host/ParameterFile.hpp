@@ -304,10 +304,12 @@ public:
           if (indent > levels.back()) {
             levels.push_back(indent);
           } else {
-            while (indent < levels.back()) {
+            while (!levels.empty() && indent < levels.back()) {
               levels.pop_back();
+              if (groups.empty()) cmi_error("Line has a different indentation than expected: \"%s\"!", line.c_str());
               groups.pop_back();
             }
+            if (levels.empty()) cmi_error("Line has a different indentation than expected: \"%s\"!", line.c_str());
           }
         } else {
           levels.push_back(indent);

@@ -455,3 +455,47 @@ def test_planck_sampler_and_masked_spectrum_bitexact(host, ref, tmp_path):
     assert np.array_equal(s["freq"], r["freq"]) and np.array_equal(s["cdf"], r["cdf"])
     assert s["total_flux"] == r["total_flux"] and 0. < s["total_flux"] < 1e12
     assert s["cdf"][-1] == 1. and (np.diff(s["cdf"]) >= 0).all()
+
+
+def test_malformed_parameter_files_end_in_errors_not_crashes(host, tmp_path):
+    """A parameter file with broken indentation or stray characters is reported (the reference aborts with
+    "Line has a different indentation than expected" / "no ':' found"); it must never take the process down:
+    the reference's lexingtonHII20 file with 1-11 random edits, 200 mutants, in a child process."""
+    import subprocess, sys
+    from conftest import ROOT
+    script = tmp_path / "fuzz.py"
+    script.write_text(f"""
+import sys, pathlib, numpy as np
+sys.path.insert(0, {str(ROOT)!r})
+from cmacionize_b200 import host
+src = pathlib.Path({str(ROOT / 'tests' / 'golden' / 'benchmarks' / 'lexingtonHII20.param')!r}).read_text()
+rng, tmp, errors = np.random.default_rng(5), pathlib.Path({str(tmp_path)!r}), 0
+for k in range(200):
+    b = list(src)
+    for _ in range(int(rng.integers(1, 12))):
+        p, m = int(rng.integers(0, len(b))), rng.integers(0, 4)
+        if m == 0: b[p] = chr(int(rng.integers(32, 127)))
+        elif m == 1: del b[p]
+        elif m == 2: b.insert(p, "\\n")
+        else: b.insert(p, ":")
+    f = tmp / "mutant.param"
+    f.write_text("".join(b))
+    try:
+        q = host.ParameterFile(f)
+        try:
+            q.photon_source_distribution(); q.abundances(); q.initial_number_density(64 ** 3)
+        except (host.HostError, UnicodeDecodeError):
+            errors += 1
+        q.close()
+    except (host.HostError, UnicodeDecodeError):
+        errors += 1
+print("survived", errors)
+""")
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, (out.returncode, out.stderr[-1500:])
+    assert out.stdout.strip().startswith("survived") and int(out.stdout.split()[-1]) > 20
+    # the case that used to walk off the indentation stack
+    bad = tmp_path / "bad.param"
+    bad.write_text("A:\n    b: 1\n  c: 2\n")
+    with pytest.raises(host.HostError, match="different indentation"):
+        host.ParameterFile(bad)
