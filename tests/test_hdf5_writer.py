@@ -657,3 +657,22 @@ def test_reader_survives_truncated_and_corrupted_files(host, tmp_path, name):
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, (out.returncode, out.stderr[-1500:])
     assert out.stdout.strip().startswith("survived") and int(out.stdout.split()[-1]) > 0
+
+
+def test_benchmark_parameter_file_writes_the_fields_its_analysis_script_reads(host, tmp_path):
+    """benchmarks/lexingtonHII20.param (unmodified copy, grid shrunk): the snapshot is named as benchmarks/lexingtonHII20.py
+    globs it and holds exactly the datasets that script opens (Coordinates, Temperature, NeutralFraction<ion> of the 14
+    ions: its DensityGridWriterFields block switches NumberDensity off and the rest on)."""
+    text = (ROOT / "tests" / "golden" / "benchmarks" / "lexingtonHII20.param").read_text()
+    assert "[64, 64, 64]" in text
+    pf = tmp_path / "lexingtonHII20.param"
+    pf.write_text(text.replace("[64, 64, 64]", "[4, 4, 4]"))
+    p = host.ParameterFile(pf)
+    name = p.write_snapshot(tmp_path, 20, np.ones(64), np.full(64, 7500.), np.full((14, 64), 0.25))
+    p.close()
+    assert name.endswith("/lexingtonHII20_020.hdf5")
+    f = h5mini.File(name)
+    check_structure(f)
+    ions = ["H", "He", "C+", "C++", "N", "N+", "N++", "O", "O+", "Ne", "Ne+", "S+", "S++", "S+++"]
+    assert set(f["PartType0"].links()) == {"Coordinates", "Temperature"} | {"NeutralFraction" + i for i in ions}
+    assert (f["PartType0"]["Temperature"].read() == 7500.).all() and np.array_equal(f["Header"].attrs["BoxSize"], [6 * PC] * 3)
