@@ -20,6 +20,7 @@
 #include "../../include/cmib.h"
 #include "kernels.cuh"
 #include "wavefront.cuh"
+#include "march_coherent.cuh"
 #include "spectrum_tables.hpp"
 
 using namespace cmib;
@@ -177,6 +178,7 @@ struct cmib_context {
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2][2] = {{0, 0}, {0, 0}}; /* [layout][plain, coherent] */
+  int lean_grid[2][2][2][2] = {};                   /* resident CTAs per SM of the march_lean_kernel variants */
   int prep_blocks_per_sm[2] = {0, 0};
   int decide_blocks_per_sm = 0;
   uint64_t shoot_rounds = 0;
@@ -368,6 +370,10 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   W.rq = ctx->rq.p;
   W.eq = ctx->eq.p;
   W.capacity = cap;
+  W.acc_j = P.acc + ACC_COUNTERS + P.honly_offset;
+  for (int d = 0; d < 3; ++d) W.lean_n16[d] = 16u * (uint32_t)P.geom.ncell[d];
+  W.lean_k[0] = P.geom.ncell[1] * P.geom.ncell[2];
+  W.lean_k[1] = P.geom.ncell[2];
   /* order of the march queue (cmib_context::sort_mode; CMIB_SORT overrides for A/B runs) */
   int sort = ctx->sort_mode;
   if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
@@ -483,6 +489,17 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
    * of the round before.  Rounds without primaries (re-emitted packets start anywhere) run
    * unsorted through the plain kernel. */
   const int sort_cfg = W.sort;
+  /* H-only coherent walk: march_lean_kernel (CMIB_LEAN=0: the r01 kernel, for A/B runs) */
+  int lean_cfg = 1, lean_steps = 3;
+  if (const char *e = getenv("CMIB_LEAN")) lean_cfg = atoi(e) != 0;
+  if (const char *e = getenv("CMIB_LEAN_STEPS")) lean_steps = atoi(e) == 2 ? 2 : 3;
+  const size_t lean_smem = lean_smem_bytes(P.geom);
+  if (lean_smem > 200 * 1024) lean_cfg = 0; /* wall tables of > ~11000 cells per axis sum: the r01 kernel */
+  /* a heat term exists unless every packet of the shoot sits exactly at the threshold: a monochromatic
+   * source at nu_H without re-emission (then nu - nu_H == 0 and the r01 kernel skipped the add at run time) */
+  const int lean_heat = !(P.src.spectrum.kind == SPECTRUM_MONOCHROMATIC && P.src.spectrum.mono_frequency == P.nu_H &&
+                          P.src.reemission_kind == REEMISSION_NONE && P.src.continuous_kind == CONTINUOUS_NONE);
+  const int lean_periodic = (P.geom.periodic[0] | P.geom.periodic[1] | P.geom.periodic[2]) ? 1 : 0;
   /* march_kernel<.., PRE>: request the next cell record one pass ahead.  Measured (B200): pays in the
    * coherent kernel, whose in-warp sums sit between request and use (clumpy 256^3 30.1 -> 26.3 ms);
    * the plain kernel is bound by L1TEX lanes, not latency (no gain; -16 % with the full layout's spills) */
@@ -535,6 +552,28 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
         const bool agg = (sort == 2 && W.agg);
         const unsigned march_grid = march_grids[agg ? 1 : 0];
         const bool prefetch = prefetch_cfg < 0 ? agg : (prefetch_cfg != 0);
+        if (agg && mode == ACC_HONLY && lean_cfg) {
+          /* march_coherent.cuh: the H-only coherent walk, variant by what the packets of this shoot can carry */
+          using K = void (*)(const WavefrontParams);
+          static const K variants[2][2][2][2] = {
+#define CMIB_LEAN_V(H, PER, PR) {march_lean_kernel<H, PER, PR, 2>, march_lean_kernel<H, PER, PR, 3>}
+              {{CMIB_LEAN_V(false, false, false), CMIB_LEAN_V(false, false, true)},
+               {CMIB_LEAN_V(false, true, false), CMIB_LEAN_V(false, true, true)}},
+              {{CMIB_LEAN_V(true, false, false), CMIB_LEAN_V(true, false, true)},
+               {CMIB_LEAN_V(true, true, false), CMIB_LEAN_V(true, true, true)}}};
+#undef CMIB_LEAN_V
+          K k = variants[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
+          if (ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] == 0) {
+            CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem));
+            int occ = 0;
+            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, MARCH_BLOCK, lean_smem));
+            if (occ < 1) CMIB_FAIL("march_lean_kernel does not fit on an SM with %zu bytes of wall tables", lean_smem);
+            ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] = occ;
+          }
+          int bpm = ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
+          if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e) > 0 ? atoi(e) : bpm;
+          k<<<(unsigned)(ctx->sm_count * bpm), MARCH_BLOCK, lean_smem, s>>>(W);
+        } else
 #define CMIB_LAUNCH_MARCH(M, A, R) march_kernel<M, A, R><<<march_grid, MARCH_BLOCK, 0, s>>>(W)
         if (mode == ACC_HONLY) {
           if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, true, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, true, false); }

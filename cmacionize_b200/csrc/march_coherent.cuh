@@ -1,0 +1,430 @@
+/*
+ * march_coherent.cuh — the voxel walk of the H-only layout on the ORDERED march queue
+ * (W.sort == 2), rewritten around the instruction budget of one cell crossing.
+ *
+ * Same contract as march_kernel (wavefront.cuh): CartesianDensityGrid::interact
+ * (src/CartesianDensityGrid.cpp:375-452) + DensityGrid::update_integrals
+ * (src/DensityGrid.hpp:150-197), one crossing per pass for every live lane, arithmetic of
+ * march_step (march.cuh) operation for operation.  What changed, and why (ncu on
+ * march_kernel<ACC_HONLY, AGG, PRE>, profiles/r01_coherent_march.md: 230 warp instructions per
+ * pass, issue slots 72 % busy at 24 warps per SM, DRAM 24 %: the kernel is bound by instruction
+ * issue, not by memory):
+ *
+ *  - cell walls come from shared-memory tables lo[i] = anchor + cellside * i and
+ *    hi[i] = lo[i] + cellside (the reference's get_cell, :170-176, evaluated once per CTA with
+ *    the same two roundings) instead of 3 x (DMUL + 2 DADD + select) per pass and three
+ *    double-precision shadows of the cell indices;
+ *  - per-packet constants that a crossing does not touch (id, meta, sampled tau, weight, frequency
+ *    offset) live in shared memory; ds and tau_cell of an absorbed packet are parked there too,
+ *    so that the loop fits in 64 registers = 4 CTAs (32 warps) per SM instead of 3;
+ *  - the service test (finish + refill) runs once per LEAN_UNROLL crossings;
+ *  - the heat term is a compile-time variant: a source at the ionisation threshold adds none
+ *    (host side: monochromatic spectrum at nu_H and no re-emission);
+ *  - hot-cell bookkeeping is a countdown that is zero after the first three crossings;
+ *  - the accumulator address is formed by the run leaders only, after the in-warp sums.
+ */
+#pragma once
+#include "wavefront.cuh"
+
+namespace cmib {
+
+#ifndef CMIB_LEAN_BLOCKS
+#define CMIB_LEAN_BLOCKS 4
+#endif
+#ifndef CMIB_LEAN_UNROLL
+#define CMIB_LEAN_UNROLL 2
+#endif
+
+/* explicit shared-memory accesses: a 32-bit shared address + immediate offset (one LDS / STS), so that
+ * the per-thread base is ONE register the compiler cannot rematerialise inside the loop (it recomputed
+ * SR_TID / SR_CgaCtaId based addresses at every use under the 64-register bound) */
+template <int OFF> CMIB_D double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF> CMIB_D void sts_f64(uint32_t a, double v) {
+  asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v));
+}
+template <int OFF> CMIB_D unsigned long long lds_u64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(a), "n"(OFF));
+  return v;
+}
+template <int OFF> CMIB_D void sts_u64(uint32_t a, unsigned long long v) {
+  asm volatile("st.shared.u64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "l"(v));
+}
+CMIB_D uint32_t opaque_u32(uint32_t v) {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+  return r;
+}
+
+/* per-thread fields in shared memory: [field][MARCH_BLOCK] 8-byte slots */
+enum LeanField : int {
+  PT_ID = 0, PT_META, PT_TAU0, PT_W, PT_DNU, PT_DS, PT_TC, PT_TAUSUM, PT_SIGH,
+  PT_NTYPE, /* NUM_PACKET_TYPES slots: ended packets of type t, discrete (low word) | continuous (high word) */
+  PT_NFIELDS = PT_NTYPE + NUM_PACKET_TYPES
+};
+constexpr int PT_STRIDE = MARCH_BLOCK * 8;
+constexpr int LEAN_PT_BYTES = PT_NFIELDS * PT_STRIDE;
+
+/* dynamic shared memory: per-thread fields, then the wall tables (16 bytes per cell index and axis) */
+inline size_t lean_smem_bytes(const GridGeom &g) {
+  return (size_t)LEAN_PT_BYTES + (size_t)(g.ncell[0] + g.ncell[1] + g.ncell[2]) * 16;
+}
+
+/*
+ * HEAT     the packets may carry nu != nu_H (heat term v1 = dJ_H * (nu - nu_H))
+ * PERIODIC some axis is periodic
+ * PRE      request the record of the next cell at the end of a crossing
+ * STEPS    shuffle steps of the in-warp sum: runs of up to 2^STEPS lanes are summed (<= 3)
+ */
+template <bool HEAT, bool PERIODIC, bool PRE, int STEPS>
+__global__ void __launch_bounds__(MARCH_BLOCK, CMIB_LEAN_BLOCKS)
+march_lean_kernel(const __grid_constant__ WavefrontParams W) {
+  extern __shared__ double2 s_dyn[];
+  __shared__ uint32_t s_hot_base;
+  const ShootParams &P = W.sp;
+  const GridGeom &g = P.geom;
+  const uint64_t cap = W.capacity;
+  const uint64_t qcount = W.ctl[CTL_QCOUNT];
+  const int lane = threadIdx.x & 31;
+  const bool can_reemit = (P.src.reemission_kind != REEMISSION_NONE);
+  const uint32_t ncx = (uint32_t)g.ncell[0], ncy = (uint32_t)g.ncell[1], ncz = (uint32_t)g.ncell[2];
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(s_dyn);
+  /* this thread's slot of field 0; field k is at + k * PT_STRIDE */
+  const uint32_t pt = opaque_u32(smem0 + threadIdx.x * 8u);
+  const uint32_t wall0 = opaque_u32(smem0 + (uint32_t)LEAN_PT_BYTES);
+  {
+    /* get_cell (CartesianDensityGrid.cpp:170-176): lo = anchor + cellside * i, hi = lo + cellside */
+    double2 *wt = s_dyn + LEAN_PT_BYTES / 16;
+    for (uint32_t i = threadIdx.x; i < ncx + ncy + ncz; i += MARCH_BLOCK) {
+      const int a = (i < ncx) ? 0 : (i < ncx + ncy ? 1 : 2);
+      const uint32_t k = i - (a == 0 ? 0u : (a == 1 ? ncx : ncx + ncy));
+      const double lo = xadd(g.anchor[a], xmul(g.cellside[a], (double)k));
+      wt[i] = make_double2(lo, xadd(lo, g.cellside[a]));
+    }
+    unsigned long long *f = reinterpret_cast<unsigned long long *>(s_dyn);
+#pragma unroll
+    for (int k = 0; k < PT_NFIELDS; ++k) f[k * MARCH_BLOCK + threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) s_hot_base = (P.hot_replicas > 0) ? (blockIdx.x % P.hot_replicas) * HOT_MAX_SOURCES : 0u;
+  }
+  __syncthreads();
+
+  /* packet state */
+  double px = 0., py = 0., pz = 0., dx = 1., dy = 1., dz = 1., ivx = 1., ivy = 1., ivz = 1.;
+  double tau = 0.;
+  /* per axis: the shared address of the wall the packet moves towards, wall0 + 16 * (axis offset + i) + 8 * (d >= 0),
+   * and the step of the cell index per crossing of that axis (+-1); the cell index itself is only implicit */
+  uint32_t ax = 0, ay = 0, az = 0;
+  int32_t sx = 1, sy = 1, sz = 1;
+  uint32_t cell = 0;
+  /* table addresses of index 0 and table sizes in bytes, per axis (uniform) */
+  const uint32_t ux = wall0, uy = wall0 + 16u * ncx, uz = wall0 + 16u * (ncx + ncy);
+  const uint32_t ncx16 = W.lean_n16[0], ncy16 = W.lean_n16[1], ncz16 = W.lean_n16[2]; /* 16 * ncell */
+  const int32_t kx = W.lean_k[0], ky = W.lean_k[1];                                  /* ncy * ncz, ncz */
+  uint32_t hot = 0; /* (source + 1) << 2 | crossings made; 0 = the neighbourhood rule no longer applies */
+  uint32_t n_steps = 0, n_red = 0;
+  int state = LANE_EMPTY;
+  double pre_n = 0., pre_xH = 0.;
+  uint64_t cur = 0, end = 0;
+  bool exhausted = (qcount == 0);
+  uint32_t n_pass = 0;
+  const bool group_lane0 = ((lane & ((1 << STEPS) - 1)) == 0);
+  const uint32_t cell_stride = (uint32_t)P.honly_cell_stride;
+
+  while (true) {
+    if (++n_pass > (1u << 26)) {
+      if (lane == 0) atomicExch(&W.ctl[CTL_ERROR], 1ull);
+      break;
+    }
+    const unsigned live_m = __ballot_sync(0xffffffffu, state == LANE_LIVE);
+    const unsigned waiting = ~live_m;
+    unsigned fill_m;
+    {
+      static_assert(AGG_GROUP == 8, "group mask arithmetic below is written for 8 lanes");
+      unsigned m = waiting;
+      m &= m >> 1;
+      m &= m >> 2;
+      m &= m >> 4;
+      fill_m = (m & 0x01010101u) * 0xffu;
+    }
+    bool service = (fill_m != 0u);
+    if (service && exhausted) {
+      const unsigned pend_m = __ballot_sync(0xffffffffu, state == LANE_ABSORBED || state == LANE_ESCAPED);
+      if (live_m == 0u && pend_m == 0u) break;
+      service = (pend_m != 0u) && (__popc(pend_m) >= MARCH_REFILL_MIN || live_m == 0u);
+    }
+    if (service) {
+      /* ---- finish ---- */
+      double fpx = 0., fpy = 0., fpz = 0.;
+      const unsigned long long meta_old = lds_u64<PT_META * PT_STRIDE>(pt);
+      const uint32_t one_of_kind = meta_continuous(meta_old) ? 0x10000u : 1u; /* counters: two 16-bit... */
+      int end_type = -1;
+      if (state == LANE_ABSORBED && !(tau < 0.)) {
+        /* tau == 0 exactly after a full crossing: the walk ends on the wall, in the cell the packet has
+         * just entered (interact() returns the cell of the current index, :445-451); `cell` is that cell */
+        fpx = px; fpy = py; fpz = pz;
+        if (!can_reemit) end_type = PACKET_ABSORBED;
+      } else if (state == LANE_ABSORBED) {
+        /* tau < 0 after the crossing: shorten it (CartesianDensityGrid.cpp:413-417) */
+        const double ds = lds_f64<PT_DS * PT_STRIDE>(pt), tau_cell = lds_f64<PT_TC * PT_STRIDE>(pt);
+        const double nwx = xadd(px, xmul(ds, dx));
+        const double nwy = xadd(py, xmul(ds, dy));
+        const double nwz = xadd(pz, xmul(ds, dz));
+        const double Scorr = xdiv(xmul(ds, tau), tau_cell);
+        const double dss = xadd(ds, Scorr);
+        fpx = xadd(px, xdiv(xmul(xsub(nwx, px), dss), ds));
+        fpy = xadd(py, xdiv(xmul(xsub(nwy, py), dss), ds));
+        fpz = xadd(pz, xdiv(xmul(xsub(nwz, pz), dss), ds));
+        /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
+        const double dJH = (dss * lds_f64<PT_W * PT_STRIDE>(pt)) * lds_f64<PT_SIGH * PT_STRIDE>(pt);
+        if (dJH != 0.) {
+          atomicAdd(acc_term<ACC_HONLY>(P, cell, 0), dJH);
+          ++n_red;
+          if (HEAT) {
+            const double dh = dJH * lds_f64<PT_DNU * PT_STRIDE>(pt);
+            if (dh != 0.) { atomicAdd(acc_term<ACC_HONLY>(P, cell, 1), dh); ++n_red; }
+          }
+        }
+        if (!can_reemit) end_type = PACKET_ABSORBED; /* PhotonSource::reemit without a handler (:304-306) */
+      } else if (state == LANE_ESCAPED) {
+        end_type = meta_type(meta_old); /* keeps its last type (IonizationPhotonShootJob.hpp:143-144) */
+      }
+      if (end_type >= 0) {
+        /* one 64-bit slot per type: discrete count in the low word, continuous in the high word */
+        const uint32_t a = pt + (uint32_t)(PT_NTYPE + end_type) * PT_STRIDE;
+        sts_u64<0>(a, lds_u64<0>(a) + (meta_continuous(meta_old) ? (1ull << 32) : 1ull));
+      }
+      (void)one_of_kind;
+      if (state == LANE_ABSORBED || state == LANE_ESCAPED)
+        sts_f64<PT_TAUSUM * PT_STRIDE>(pt, lds_f64<PT_TAUSUM * PT_STRIDE>(pt) +
+                                               (lds_f64<PT_TAU0 * PT_STRIDE>(pt) - ((tau > 0.) ? tau : 0.)));
+      if (can_reemit) {
+        const unsigned ab = __ballot_sync(0xffffffffu, state == LANE_ABSORBED);
+        if (ab) {
+          unsigned long long base = 0;
+          const int leader = __ffs(ab) - 1;
+          if (lane == leader) base = atomicAdd(&W.ctl[CTL_RQCOUNT], (unsigned long long)__popc(ab));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (state == LANE_ABSORBED) {
+            double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
+            q[RQ_PX * cap] = fpx; q[RQ_PY * cap] = fpy; q[RQ_PZ * cap] = fpz;
+            q[RQ_SIGH * cap] = lds_f64<PT_SIGH * PT_STRIDE>(pt);
+            q[RQ_SIGHE * cap] = 0.;
+            q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
+            q[RQ_ID * cap] = __longlong_as_double((long long)lds_u64<PT_ID * PT_STRIDE>(pt));
+            q[RQ_META * cap] = __longlong_as_double((long long)(meta_old & 0xffffffffffull));
+          }
+        }
+      }
+      if (state != LANE_LIVE) state = LANE_EMPTY;
+
+      /* ---- refill: hand queue entries to the empty lanes of the waiting groups ---- */
+      if (!exhausted) {
+        if (cur == end) {
+          unsigned long long b = 0;
+          if (lane == 0) b = atomicAdd(&W.ctl[CTL_HEAD], (unsigned long long)MARCH_CHUNK);
+          b = __shfl_sync(0xffffffffu, b, 0);
+          if (b >= qcount) {
+            exhausted = true;
+          } else {
+            cur = b;
+            end = (b + MARCH_CHUNK < qcount) ? b + MARCH_CHUNK : qcount;
+          }
+        }
+        if (!exhausted) {
+          const int rank = __popc(fill_m & ((1u << lane) - 1u));
+          const uint64_t avail = end - cur;
+          const int nfill = __popc(fill_m);
+          if (state == LANE_EMPTY && ((fill_m >> lane) & 1u) && (uint64_t)rank < avail) {
+            const uint64_t slot = (uint64_t)W.order[cur + rank];
+            const double *q = W.mq + slot;
+            px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
+            dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
+            const double nu = q[MQ_NU * cap];
+            tau = q[MQ_TAU * cap];
+            sts_f64<PT_TAU0 * PT_STRIDE>(pt, tau);
+            sts_u64<PT_ID * PT_STRIDE>(pt, (unsigned long long)__double_as_longlong(q[MQ_ID * cap]));
+            const unsigned long long meta = (unsigned long long)__double_as_longlong(q[MQ_META * cap]);
+            sts_u64<PT_META * PT_STRIDE>(pt, meta);
+            hot = 0;
+            if (P.hot_replicas > 0) {
+              const int isrc = meta_source(meta);
+              if (isrc >= 0) hot = (uint32_t)(isrc + 1) << 2;
+            }
+            sts_f64<PT_SIGH * PT_STRIDE>(pt, q[MQ_SIGMA * cap]);
+            sts_f64<PT_W * PT_STRIDE>(pt, meta_continuous(meta) ? P.src.continuous_weight : P.src.discrete_weight);
+            if (HEAT) sts_f64<PT_DNU * PT_STRIDE>(pt, nu - P.nu_H);
+            /* a zero direction component: the reference's wall distance is DBL_MAX (:289-309).  Here the
+             * packet "moves towards" the upper wall with 1/d = +inf: (hi - p) * inf = +inf, which is never
+             * the minimum and never equal to it — the same selection, without a test per crossing
+             * (hi - p > 0: p lies in the cell of its truncated index and never moves along this axis) */
+            const bool upx = (dx >= 0.), upy = (dy >= 0.), upz = (dz >= 0.);
+            ivx = 1. / ((dx == 0.) ? 0. : dx);
+            ivy = 1. / ((dy == 0.) ? 0. : dy);
+            ivz = 1. / ((dz == 0.) ? 0. : dz);
+            sx = upx ? 1 : -1;
+            sy = upy ? 1 : -1;
+            sz = upz ? 1 : -1;
+            /* get_cell_indices (CartesianDensityGrid.cpp:152-161) */
+            int32_t ix = trunc_index(xmul(xsub(px, g.anchor[0]), g.inv_cellside[0]));
+            int32_t iy = trunc_index(xmul(xsub(py, g.anchor[1]), g.inv_cellside[1]));
+            int32_t iz = trunc_index(xmul(xsub(pz, g.anchor[2]), g.inv_cellside[2]));
+            state = LANE_LIVE;
+            if (PERIODIC) {
+              MarchState ms;
+              ms.px = px; ms.py = py; ms.pz = pz; ms.ix = ix; ms.iy = iy; ms.iz = iz;
+              const bool in = march_inside(g, ms);
+              px = ms.px; py = ms.py; pz = ms.pz; ix = ms.ix; iy = ms.iy; iz = ms.iz;
+              if (!in) state = LANE_ESCAPED;
+            } else if ((uint32_t)ix >= ncx || (uint32_t)iy >= ncy || (uint32_t)iz >= ncz) {
+              state = LANE_ESCAPED; /* emitted outside the box: interact() returns end() */
+            }
+            ax = ux + 16u * (uint32_t)ix + (upx ? 8u : 0u);
+            ay = uy + 16u * (uint32_t)iy + (upy ? 8u : 0u);
+            az = uz + 16u * (uint32_t)iz + (upz ? 8u : 0u);
+            if (state == LANE_LIVE) {
+              cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
+              if (PRE) {
+                const double2 r0 = __ldg(P.cells_h + cell);
+                pre_n = r0.x; pre_xH = r0.y;
+              }
+            }
+          }
+          cur += ((uint64_t)nfill < avail) ? (uint64_t)nfill : avail;
+        }
+      }
+      continue;
+    }
+
+#pragma unroll
+    for (int u = 0; u < CMIB_LEAN_UNROLL; ++u) {
+      /* ---- one cell crossing for every live lane ---- */
+      uint32_t akey = 0xffffffffu; /* accumulator record this lane adds to: the cell, 2^31 | hot replica record,
+                                    * or all ones = nothing to add */
+      double v0 = 0., v1 = 0.;
+      if (state == LANE_LIVE) {
+        double n, xH;
+        if (PRE) {
+          n = pre_n; xH = pre_xH;
+        } else {
+          const double2 r0 = __ldg(P.cells_h + cell);
+          n = r0.x; xH = r0.y;
+        }
+        /* get_wall_intersection (CartesianDensityGrid.cpp:280-318) on the tabulated walls */
+        const double wx = xmul(xsub(lds_f64<0>(ax), px), ivx);
+        const double wy = xmul(xsub(lds_f64<0>(ay), py), ivy);
+        const double wz = xmul(xsub(lds_f64<0>(az), pz), ivz);
+        const double sigH = lds_f64<PT_SIGH * PT_STRIDE>(pt);
+        const double myz = (wz < wy) ? wz : wy;
+        const double ds = (myz < wx) ? myz : wx;
+        /* ds * n * (sigma_H * x_H) (DensityGrid.hpp:129-133; the helium term of the H-only layout is
+         * sigma * 0 + 0 = +0, and t + 0 == t) */
+        const double tau_cell = xmul(xmul(ds, n), xmul(sigH, xH));
+        tau = xsub(tau, tau_cell);
+        ++n_steps;
+        if (tau < 0.) {
+          state = LANE_ABSORBED; /* position and tau stay as they are for the deferred finish */
+          sts_f64<PT_DS * PT_STRIDE>(pt, ds);
+          sts_f64<PT_TC * PT_STRIDE>(pt, tau_cell);
+        } else {
+          if (n > 0.) {
+            /* update_integrals (DensityGrid.hpp:150-197) */
+            akey = cell;
+            if (hot != 0u) {
+              /* first crossings of a primary, inside the 3x3x3 cells around its source: a replica */
+              const uint32_t hc = P.src_cell[(hot >> 2) - 1u];
+              const int ddx = (int)((ax - ux) >> 4) - (int)(hc & 1023u), ddy = (int)((ay - uy) >> 4) - (int)((hc >> 10) & 1023u),
+                        ddz = (int)((az - uz) >> 4) - (int)((hc >> 20) & 1023u);
+              if ((unsigned)(ddx + 1) < 3u && (unsigned)(ddy + 1) < 3u && (unsigned)(ddz + 1) < 3u)
+                akey = 0x80000000u | ((s_hot_base + ((hot >> 2) - 1u)) * HOT_CELLS +
+                                      (uint32_t)((ddx + 1) * 9 + (ddy + 1) * 3 + (ddz + 1)));
+              ++hot;
+              if ((hot & 3u) == (uint32_t)HOT_CROSSINGS) hot = 0u;
+            }
+            v0 = (ds * lds_f64<PT_W * PT_STRIDE>(pt)) * sigH;
+            if (HEAT) v1 = v0 * lds_f64<PT_DNU * PT_STRIDE>(pt);
+          }
+          /* move to the wall, step the indices of every axis whose wall was hit */
+          px = xadd(px, xmul(ds, dx));
+          py = xadd(py, xmul(ds, dy));
+          pz = xadd(pz, xmul(ds, dz));
+          /* if (w == ds) { a += 16 * s; cell += k * s; } as one compare and two predicated multiply-adds */
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
+              : "+r"(ax), "+r"(cell) : "d"(wx), "d"(ds), "r"(sx), "r"(kx));
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
+              : "+r"(ay), "+r"(cell) : "d"(wy), "d"(ds), "r"(sy), "r"(ky));
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p add.s32 %1, %1, %4;\n\t}"
+              : "+r"(az), "+r"(cell) : "d"(wz), "d"(ds), "r"(sz));
+          if (PERIODIC) {
+            MarchState ms;
+            ms.px = px; ms.py = py; ms.pz = pz;
+            ms.ix = (int32_t)(ax - ux) >> 4; ms.iy = (int32_t)(ay - uy) >> 4; ms.iz = (int32_t)(az - uz) >> 4;
+            const int32_t jx = ms.ix, jy = ms.iy, jz = ms.iz;
+            const bool in = march_inside(g, ms);
+            px = ms.px; py = ms.py; pz = ms.pz;
+            ax += 16u * (uint32_t)(ms.ix - jx); ay += 16u * (uint32_t)(ms.iy - jy); az += 16u * (uint32_t)(ms.iz - jz);
+            cell = ((uint32_t)ms.ix * ncy + (uint32_t)ms.iy) * ncz + (uint32_t)ms.iz;
+            if (!in) state = LANE_ESCAPED;
+          } else if ((ax - ux) >= ncx16 || (ay - uy) >= ncy16 || (az - uz) >= ncz16) {
+            /* the address offsets are 16 * i + 8 * (d >= 0): an index of -1 wraps to a huge unsigned value */
+            state = LANE_ESCAPED;
+          }
+          if (state == LANE_LIVE) {
+            /* tau == 0 exactly: the walk ends inside (loop condition tau > 0, :391), on the wall */
+            if (!(tau > 0.)) state = LANE_ABSORBED;
+            else if (PRE) {
+              const double2 r0 = __ldg(P.cells_h + cell);
+              pre_n = r0.x; pre_xH = r0.y;
+            }
+          }
+        }
+      }
+      /* runs of neighbouring lanes with the same record (neighbours inside a group are neighbours
+       * in key order): segmented sum towards the first lane of every run */
+      const uint32_t prev = __shfl_up_sync(0xffffffffu, akey, 1);
+      const bool head = group_lane0 || akey != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      if (heads != 0xffffffffu) {
+        /* bit d-1 of hs: lane + d starts a run (lane 32 counts as one) */
+        const unsigned hs = ((heads >> 1) | 0x80000000u) >> lane;
+#pragma unroll
+        for (int d = 1; d < (1 << STEPS); d <<= 1) {
+          /* if no run starts among the next d lanes: v += v of lane + d */
+          const double t0 = __shfl_down_sync(0xffffffffu, v0, d);
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v0) : "d"(t0), "r"(hs & ((1u << d) - 1u)));
+          if (HEAT) {
+            const double t1 = __shfl_down_sync(0xffffffffu, v1, d);
+            asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v1) : "d"(t1), "r"(hs & ((1u << d) - 1u)));
+          }
+        }
+      }
+      if (head && akey != 0xffffffffu) {
+        /* the record: the cell's, or a hot-cell replica (2^31 | record, HOT_STRIDE doubles each) */
+        const bool is_hot = (akey & 0x80000000u) != 0u;
+        const double *base = is_hot ? P.hot_acc : W.acc_j;
+        const uint32_t idx = is_hot ? (akey << 4) : akey * cell_stride;
+        static_assert(HOT_STRIDE == 16, "hot record index -> doubles is a shift by 4");
+        double *a = const_cast<double *>(base) + idx;
+        if (v0 != 0.) { atomicAdd(a, v0); ++n_red; }
+        if (HEAT && v1 != 0.) { atomicAdd(a + (is_hot ? (int64_t)1 : P.honly_term_stride), v1); ++n_red; }
+      }
+    }
+  }
+  ShootCounters cnt;
+  cnt.n_steps = n_steps;
+  cnt.n_red = n_red;
+  cnt.tau_sum = lds_f64<PT_TAUSUM * PT_STRIDE>(pt);
+  const double w_discrete = P.src.discrete_weight, w_continuous = P.src.continuous_weight;
+#pragma unroll
+  for (int t = 0; t < NUM_PACKET_TYPES; ++t) {
+    const unsigned long long c = lds_u64<0>(pt + (uint32_t)(PT_NTYPE + t) * PT_STRIDE);
+    cnt.w_type[t] = (double)(uint32_t)c * w_discrete + (double)(uint32_t)(c >> 32) * w_continuous;
+    cnt.w_tot += cnt.w_type[t];
+  }
+  reduce_counters(P.acc, cnt);
+}
+
+} // namespace cmib

@@ -84,6 +84,9 @@ struct WavefrontParams {
   int fine_key_bits;       /* source + direction bits; bit fine_key_bits flags a re-emitted packet */
   uint32_t chunk_stride;   /* chunk c of the ordered queue is claimed as (c * chunk_stride) % nchunks */
   int agg;                 /* 1: march_kernel<MODE, true> (in-warp sums), 0: the plain kernel on the ordered queue */
+  uint32_t lean_n16[3];    /* march_lean_kernel: 16 * ncell per axis */
+  int32_t lean_k[2];       /* ... and the cell-index strides ncy * ncz, ncz */
+  double *acc_j;           /* H-only layout: accumulator J_H of cell 0 (sp.acc + ACC_COUNTERS + sp.honly_offset) */
 };
 
 /*

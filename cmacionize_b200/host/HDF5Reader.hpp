@@ -71,6 +71,7 @@ public:
   std::string read_string_attribute(const std::string &path, const std::string &name) const {
     const Attribute &a = attribute(path, name);
     if (a.type.cls != 3) fail("attribute \"" + name + "\" is not a string");
+    check(a.data, a.type.size); /* a zero-sized dataspace checked nothing when the attribute was parsed */
     const char *s = reinterpret_cast<const char *>(data_ + a.data);
     return std::string(s, strnlen(s, a.type.size));
   }
@@ -88,11 +89,12 @@ public:
         o.type.members[0].cls != 3 || (o.type.members[1].cls != 0 && o.type.members[1].cls != 1))
       fail("\"" + path + "\" is not a {name, value} table");
     if (o.layout_class != 1 || o.layout_address == UNDEFINED) fail("\"" + path + "\": only contiguous tables are read");
-    uint64_t n = 1;
-    for (uint64_t d : o.dims) n *= d;
-    check(o.layout_address, n * o.type.size);
+    const uint64_t n = element_count(o.dims);
+    check(o.layout_address, mul(n, o.type.size));
     std::map<std::string, double> out;
     const Member &key = o.type.members[0], &val = o.type.members[1];
+    if ((uint64_t)key.offset + key.size > o.type.size || (uint64_t)val.offset + val.size > o.type.size)
+      fail("\"" + path + "\": a compound member outside its record");
     Datatype vt;
     vt.cls = val.cls; vt.size = val.size; vt.is_signed = val.is_signed;
     for (uint64_t i = 0; i < n; ++i) {
@@ -111,14 +113,20 @@ public:
     const Object o = open_object(path);
     if (!o.has_layout || !o.has_type || !o.has_space) fail("\"" + path + "\" is not a dataset");
     if (dims) *dims = o.dims;
-    uint64_t n = 1;
-    for (uint64_t d : o.dims) n *= d;
-    std::vector<double> out(n);
+    const uint64_t n = element_count(o.dims);
     const uint64_t esize = o.type.size;
+    const uint64_t nbytes = mul(n, esize);
+    if (n > MAX_ELEMENTS) fail("dataset \"" + path + "\": a dataspace of more than 2^34 elements (corrupted?)");
+    /* contiguous / compact data must be in the file before anything is allocated for it */
+    if ((o.layout_class == 1 && o.layout_address != UNDEFINED) || o.layout_class == 0) {
+      if (o.layout_size < nbytes) fail("dataset \"" + path + "\": layout smaller than the dataspace");
+      check(o.layout_address, nbytes);
+    }
+    /* chunked (possibly deflated) data: no chunk can inflate by more than ~1000 */
+    if (o.layout_class == 2 && nbytes / 4096 > size_) fail("dataset \"" + path + "\": a dataspace far larger than the file (corrupted?)");
+    std::vector<double> out(n);
     if (o.layout_class == 1 || o.layout_class == 0) {
       if (o.layout_class == 1 && o.layout_address == UNDEFINED) return out; /* never written: the fill value (0) */
-      if (o.layout_size < n * esize) fail("dataset \"" + path + "\": layout smaller than the dataspace");
-      check(o.layout_address, n * esize);
       convert(o.type, data_ + o.layout_address, n, out.data());
       return out;
     }
@@ -126,10 +134,13 @@ public:
     const size_t nd = o.chunk_dims.size() - 1;
     if (nd != o.dims.size() || nd == 0 || nd > 2) fail("dataset \"" + path + "\": only 1-D and 2-D chunked datasets are read");
     uint64_t chunk_elements = 1;
-    for (size_t k = 0; k < nd; ++k) chunk_elements *= o.chunk_dims[k];
+    for (size_t k = 0; k < nd; ++k) chunk_elements = mul(chunk_elements, o.chunk_dims[k]);
+    if (chunk_elements == 0 || mul(chunk_elements, esize) > (uint64_t(1) << 32))
+      fail("dataset \"" + path + "\": chunks of zero or more than 4 GiB (corrupted?)");
     std::vector<uint8_t> raw(chunk_elements * esize), tmp;
     std::vector<double> cvals(chunk_elements);
-    if (o.layout_address != UNDEFINED) read_chunks(o, o.layout_address, nd, chunk_elements, raw, tmp, cvals, out);
+    if (o.layout_address != UNDEFINED)
+      read_chunks(o, o.layout_address, nd, chunk_elements, raw, tmp, cvals, out, 0, -1);
     return out;
   }
 
@@ -178,6 +189,20 @@ private:
   uint32_t u32(uint64_t o) const { check(o, 4); uint32_t v; memcpy(&v, data_ + o, 4); return v; }
   uint64_t u64(uint64_t o) const { check(o, 8); uint64_t v; memcpy(&v, data_ + o, 8); return v; }
   static uint64_t pad8(uint64_t n) { return (n + 7) & ~uint64_t(7); }
+  /* products of sizes that come from the file: overflow is an error, not a wrap-around */
+  uint64_t mul(uint64_t a, uint64_t b) const {
+    uint64_t r;
+    if (__builtin_mul_overflow(a, b, &r)) fail("sizes whose product overflows (corrupted?)");
+    return r;
+  }
+  uint64_t element_count(const std::vector<uint64_t> &dims) const {
+    uint64_t n = 1;
+    for (uint64_t d : dims) n = mul(n, d);
+    return n;
+  }
+  /* largest dataset this reader materialises (doubles): nothing the reference writes comes near, and a corrupted
+   * dataspace must give an error, not std::bad_alloc */
+  static constexpr uint64_t MAX_ELEMENTS = uint64_t(1) << 34;
 
   Datatype parse_datatype(uint64_t o) const {
     Datatype t;
@@ -208,6 +233,7 @@ private:
         const Datatype mt = parse_datatype(q);
         if (mt.cls == 6) fail("nested compound datatypes");
         m.cls = mt.cls; m.size = mt.size; m.is_signed = mt.is_signed;
+        if ((uint64_t)m.offset + m.size > t.size) fail("a compound member that does not fit in its record");
         q += 8 + (mt.cls == 0 ? 4 : (mt.cls == 1 ? 12 : 0));
         t.members.push_back(m);
       }
@@ -256,8 +282,16 @@ private:
       check(p, blocks[ib].second);
       while (p + 8 <= end && seen < nmsg) {
         const uint16_t type = u16(p), size = u16(p + 2);
+        const uint8_t flags = u8(p + 4);
         const uint64_t body = p + 8;
         ++seen;
+        /* bit 1: the body is a reference to a shared message elsewhere in the file, not the message itself */
+        if ((flags & 2) && type != 0x0000) {
+          if (type == 0x0001 || type == 0x0003 || type == 0x0008 || type == 0x000B || type == 0x0011)
+            fail("shared object header messages");
+          p = body + size; /* a shared attribute (or anything else) is skipped like an unknown one */
+          continue;
+        }
         switch (type) {
         case 0x0010: blocks.push_back({u64(body), u64(body + 8)}); break;
         case 0x0011: o.is_group = true; o.btree = u64(body); o.heap = u64(body + 8); break;
@@ -302,10 +336,10 @@ private:
             q += pad8(name_size);
             a.type = parse_datatype(q);
             q += pad8(type_size);
-            for (uint64_t d : parse_dataspace(q)) a.count *= d;
+            a.count = element_count(parse_dataspace(q));
             q += pad8(space_size);
             a.data = q;
-            check(q, a.count * a.type.size);
+            check(q, mul(a.count, a.type.size));
             o.attributes.push_back(a);
           } catch (const Error &) {
           }
@@ -379,10 +413,14 @@ private:
   }
 
   void read_chunks(const Object &o, uint64_t node, size_t nd, uint64_t chunk_elements, std::vector<uint8_t> &raw,
-                   std::vector<uint8_t> &tmp, std::vector<double> &cvals, std::vector<double> &out) const {
+                   std::vector<uint8_t> &tmp, std::vector<double> &cvals, std::vector<double> &out, int depth,
+                   int expected_level) const {
     check(node, 24);
     if (memcmp(data_ + node, "TREE", 4) != 0 || u8(node + 4) != 1) fail("a bad chunk B-tree node");
     const uint8_t level = u8(node + 5);
+    /* a child sits exactly one level below its parent: a node that points at itself or upwards is a cycle */
+    if (depth > 16 || (expected_level >= 0 && level != expected_level))
+      fail("a chunk B-tree that is too deep or cyclic");
     const uint16_t used = u16(node + 6);
     const uint64_t key_size = 8 + 8 * (nd + 1);
     const uint64_t esize = o.type.size;
@@ -390,7 +428,7 @@ private:
       const uint64_t key = node + 24 + (uint64_t)k * (key_size + 8);
       const uint64_t child = u64(key + key_size);
       if (level > 0) {
-        read_chunks(o, child, nd, chunk_elements, raw, tmp, cvals, out);
+        read_chunks(o, child, nd, chunk_elements, raw, tmp, cvals, out, depth + 1, (int)level - 1);
         continue;
       }
       const uint32_t nbytes = u32(key), mask = u32(key + 4);
@@ -418,12 +456,14 @@ private:
       }
       if (have != chunk_elements * esize) fail("a chunk whose size does not match its dimensions");
       convert(o.type, src, chunk_elements, cvals.data());
+      /* chunk offsets come from the file: they must lie inside the dataspace (no wrap-around in the index) */
+      if (offset[0] >= o.dims[0] || (nd > 1 && offset[1] >= o.dims[1])) fail("a chunk outside its dataspace");
       if (nd == 1) {
-        for (uint64_t i = 0; i < o.chunk_dims[0] && offset[0] + i < o.dims[0]; ++i) out[offset[0] + i] = cvals[i];
+        for (uint64_t i = 0; i < o.chunk_dims[0] && offset[0] + i < o.dims[0]; ++i) out.at(offset[0] + i) = cvals[i];
       } else {
         for (uint64_t i = 0; i < o.chunk_dims[0] && offset[0] + i < o.dims[0]; ++i)
           for (uint64_t j = 0; j < o.chunk_dims[1] && offset[1] + j < o.dims[1]; ++j)
-            out[(offset[0] + i) * o.dims[1] + offset[1] + j] = cvals[i * o.chunk_dims[1] + j];
+            out.at((offset[0] + i) * o.dims[1] + offset[1] + j) = cvals[i * o.chunk_dims[1] + j];
       }
     }
   }

@@ -659,6 +659,58 @@ def test_reader_survives_truncated_and_corrupted_files(host, tmp_path, name):
     assert out.stdout.strip().startswith("survived") and int(out.stdout.split()[-1]) > 0
 
 
+TARGETED = r"""
+import sys, pathlib, struct
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import h5mini
+from cmacionize_b200 import host
+src, tmp = pathlib.Path(sys.argv[2]), pathlib.Path(sys.argv[3])
+f = h5mini.File(src)
+chunked = [n for n in f["PartType0"].links() if f["PartType0"][n].layout and f["PartType0"][n].layout[0] == "chunked"]
+assert chunked, "the fixture has a chunked dataset"
+errors = 0
+for name in chunked[:2]:
+    d = f["PartType0"][name]
+    node = d.layout[1]
+    raw = src.read_bytes()
+    assert raw[node:node + 4] == b"TREE" and raw[node + 4] == 1
+    nd = len(d.layout[2]) - 1
+    key_size = 8 + 8 * (nd + 1)
+    # (1) a node that claims to be an internal node and whose first child is the node itself: a cycle
+    b = bytearray(raw); b[node + 5] = 1; b[node + 24 + key_size:node + 24 + key_size + 8] = struct.pack("<Q", node)
+    # (2) a dataspace of 2^32 x 2^32 (x ...) elements: the element count wraps to 0
+    space = [body for t, body, _, _ in d.messages if t == 0x0001][0]
+    c = bytearray(raw); p0 = space + (8 if c[space] == 1 else 4)
+    for k in range(c[space + 1]): c[p0 + 8 * k:p0 + 8 * k + 8] = struct.pack("<Q", 1 << 32)
+    # (3) huge but not wrapping: must be an error message, not std::bad_alloc / an out-of-bounds scatter
+    e = bytearray(raw); e[p0:p0 + 8] = struct.pack("<Q", 1 << 40)
+    # (4) a chunk offset outside the dataspace
+    g = bytearray(raw); g[node + 24 + 8:node + 24 + 16] = struct.pack("<Q", (1 << 63) + 5)
+    for k, m in enumerate((b, c, e, g)):
+        mf = tmp / f"targeted{k}.hdf5"
+        mf.write_bytes(bytes(m))
+        try:
+            host.HDF5Input(mf).dataset("/PartType0/" + name)
+        except host.HostError as err:
+            errors += 1
+        mf.unlink()
+print("survived", errors)
+"""
+
+
+def test_reader_refuses_cyclic_chunk_trees_and_overflowing_dataspaces(host, tmp_path):
+    """The two crashes the round-1 review found by hand (a chunk B-tree node whose child is itself: stack overflow; a
+    dataspace of 2^32 x 2^32 elements whose product wraps to 0: out-of-bounds scatter), plus a huge dataspace and a chunk
+    offset outside the dataspace: each must raise the reader's error in a process that keeps running."""
+    script = tmp_path / "targeted.py"
+    script.write_text(TARGETED)
+    out = subprocess.run([sys.executable, str(script), str(ROOT), str(GOLD / "test.hdf5"), str(tmp_path)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stderr[-1500:])
+    n = int(out.stdout.split()[-1])
+    assert n >= 4 and n % 4 == 0, out.stdout   # every mutant of every chunked dataset ended in an error
+
+
 def test_benchmark_parameter_file_writes_the_fields_its_analysis_script_reads(host, tmp_path):
     """benchmarks/lexingtonHII20.param (unmodified copy, grid shrunk): the snapshot is named as benchmarks/lexingtonHII20.py
     globs it and holds exactly the datasets that script opens (Coordinates, Temperature, NeutralFraction<ion> of the 14
