@@ -1,24 +1,28 @@
 #!/usr/bin/env python3
-"""bench.py — headline benchmark of the photoionization hot path.
+"""bench.py — benchmark of the photoionization hot path.
 
-Metric (BASELINE.json): photon packets/s on lexingtonHII20 and wall time per
-ionization iteration.  A *step* is one full iteration of
-IonizationSimulation::run's loop body (reference src/IonizationSimulation.cpp:359-643)
-on the Lexington HII20 benchmark (64^3 cells, 1e8 packets per iteration, Planck
-20 000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse
-re-emission, temperature solve with line cooling):
+Headline metric (BASELINE.json): photon packets/s on lexingtonHII20 and wall time per ionization iteration.
+A *step* is one full iteration of IonizationSimulation::run's loop body (reference
+src/IonizationSimulation.cpp:359-643) on the Lexington HII20 benchmark (64^3 cells, 1e8 packets per iteration,
+Planck 20 000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse re-emission, temperature solve
+with line cooling):
 
-    reset accumulators -> re-emission probabilities -> shoot -> [all-reduce] -> state update
+    reset accumulators -> re-emission probabilities -> shoot -> exchange (N > 1) -> state update
 
-Usage:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-N>1 is launched by torch.distributed.run (one rank per GPU, NCCL).  Scaling is WEAK:
-every GPU shoots the benchmark's 1e8 packets per iteration (global packet ids
-[rank*1e8, (rank+1)*1e8), so N GPUs draw N x 1e8 distinct packets and the Monte Carlo
-noise drops by sqrt(N)); the grid is replicated, the per-cell accumulators are
-combined by ONE all-reduce per iteration, and every rank runs the state update.
+After the headline the same loop is timed on the two north-star grids (BASELINE.json configs[4] and the 256^3
+Stroemgren grid of the target) and attached under `workloads.{stromgren256, clumpy256}`; each entry carries its own
+`value`, `ms_per_step`, `roofline` (HBM: these grids do not fit in L2), `phases_ms` and `clocks`.
 
-One JSON line is printed by rank 0 (schema: task contract + `roofline`,
-`cpu_baseline`, `e2e`, `clocks`, `gpu_launches`).
+Usage:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads a,b,...]
+N > 1 is launched by torch.distributed.run (one rank per GPU).  Scaling is STRONG, as in the reference
+(IonizationSimulation.cpp:392-397 -> MPICommunicator::distribute): the iteration keeps the configuration's packet
+count and the ranks split it by global packet id; the grid is replicated; the exchange between shoot and update is
+the product's own NCCL code behind the C ABI (include/cmib.h cmib_comm_exchange_and_update: the accumulators are
+summed onto the owners of the cell blocks, every rank updates its block, the opacity records are gathered) — the
+same calls the C++ driver `CMacIonizeB200 --gpus` makes.  `weak` (N > 1) adds the figure with N x the packets.
+
+One JSON line is printed by rank 0 (schema: task contract + `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches`, `phases_ms`, `workloads`).
 """
 from __future__ import annotations
 
@@ -39,6 +43,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "photon packets/s on lexingtonHII20 (whole iteration: shoot + state update)"
 UNIT = "packets/s"
+FULL_PACKETS = 100_000_000
 
 LEXINGTON_PARAM = """AbundanceModel:
   type: FixedValue
@@ -93,6 +98,23 @@ block[1]:
   initial temperature: 0. K
 """
 
+WORKLOADS = {
+    "lexingtonHII20": dict(grid=64, layout="full", label="benchmarks/lexingtonHII20.param",
+                           physics="Planck 20000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse "
+                                   "re-emission, temperature solve with line cooling",
+                           spinup_packets=1_000_000),
+    "stromgren256": dict(grid=256, layout="honly", label="stromgren.param physics on a 256^3 grid (north-star target grid)",
+                         physics="monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field",
+                         spinup_packets=16_000_000),
+    "clumpy256": dict(grid=256, layout="honly", label="synthetic clumpy 256^3, 16 sources, H-only (BASELINE.json configs[4])",
+                      physics="monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field",
+                      spinup_packets=16_000_000),
+    "clumpy256L": dict(grid=256, layout="full", label="synthetic clumpy 256^3, 16 sources, Lexington physics",
+                       physics="Planck 40000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse "
+                               "re-emission, temperature solve with line cooling",
+                       spinup_packets=16_000_000),
+}
+
 
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -102,6 +124,18 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu summaries
+    (profiles/traffic.json, written by tools/ncu_traffic.py from a named .ncu-rep): bytes per cell crossing."""
+    p = ROOT / "profiles" / "traffic.json"
+    if not p.exists():
+        return None
+    try:
+        return json.loads(p.read_text()).get(workload)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -155,14 +189,12 @@ class ClockSampler:
 def cpu_reference_measure(full_packets: int, sample_packets: int, steps: int, warmup: int):
     """Steady-state cost per iteration of the UNMODIFIED reference on this host's cores.
 
-    The reference's IonizationSimulation is built from the Lexington HII20 parameter file
-    and its loop body (IonizationSimulation.cpp:359-643) is executed one iteration at a
-    time on the reference's own objects (oracle probe cmi_ref_sim_iteration), each phase
-    under its own timer.  `warmup` (>= 5: the temperature solve starts at the 5th iteration,
-    TemperatureCalculator.cpp:948) untimed iterations, then `steps` timed ones of
-    `sample_packets` packets.  Shoot time is linear in the packet count, reset / re-emission
-    probabilities / state update do not depend on it, so the full-size figure is
-        N_full / (N_full / rate_shoot + t_prep + t_update)."""
+    The reference's IonizationSimulation is built from the Lexington HII20 parameter file and its loop body
+    (IonizationSimulation.cpp:359-643) is executed one iteration at a time on the reference's own objects (oracle
+    probe cmi_ref_sim_iteration), each phase under its own timer.  `warmup` (>= 5: the temperature solve starts at
+    the 5th iteration, TemperatureCalculator.cpp:948) untimed iterations, then `steps` timed ones of
+    `sample_packets` packets.  Shoot time is linear in the packet count, reset / re-emission probabilities / state
+    update do not depend on it, so the full-size figure is N_full / (N_full / rate_shoot + t_prep + t_update)."""
     import oracle.ref as ref
     ref.use_all_host_threads()  # under torchrun OMP_NUM_THREADS is 1: the reference gets all the host's cores anyway
     warmup = max(warmup, 5)
@@ -206,147 +238,91 @@ def cpu_reference_measure(full_packets: int, sample_packets: int, steps: int, wa
     }
 
 
-# --------------------------------------------------------------------------- our arm
 def _claim_stdout():
-    """Libraries (NCCL's version banner, torchrun's OMP notice) write to fd 1; the contract is ONE JSON
-    line on stdout.  Point fd 1 at stderr for the duration of the run and keep the real stdout for the
-    result line."""
+    """Libraries (NCCL's version banner, torchrun's OMP notice) write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the duration of the run and keep the real stdout for the result line."""
     sys.stdout.flush()
     real = os.dup(1)
     os.dup2(2, 1)
     return os.fdopen(real, "w")
 
 
-def main():
-    result_out = _claim_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--packets", type=float, default=1e8, help="packets per iteration PER GPU (benchmark: 1e8)")
-    ap.add_argument("--ncell", type=int, default=64)
-    ap.add_argument("--spinup", type=int, default=6, help="untimed iterations (1e6 packets) that bring the "
-                    "grid to the ionised steady state and past the 4 ionization-only iterations")
-    ap.add_argument("--cpu-sample", type=float, default=1e6)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="lexingtonHII20",
-                    choices=["lexingtonHII20", "stromgren256", "clumpy256", "clumpy256L"],
-                    help="default: the configuration BASELINE.json's metric is quoted on; the 256^3 workloads "
-                         "(north-star target grid, BASELINE.json configs[4]) are recorded under profiles/")
-    ap.add_argument("--spinup-packets", type=float, default=None)
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    per_gpu = int(args.packets)
-    n_packets = per_gpu * (world if args.impl == "ours" else max(args.gpus, 1))
+def config_of(name, n_packets, world, scaling="strong"):
+    w = WORKLOADS[name]
+    nc = w["grid"]
+    return {"workload": name, "description": w["label"], "grid": f"{nc}^3", "packets_per_iteration": n_packets,
+            "physics": w["physics"],
+            "parallelism": (f"{world} GPU(s): {scaling} scaling, packets split by global id "
+                            "(MPICommunicator::distribute), replicated grid, accumulators reduced onto cell-block "
+                            "owners, block-wise state update, opacity records gathered (NCCL behind the C ABI)"),
+            "l2_policy": ("cells + accumulators (41 MB) are L2 resident and re-zeroed / rewritten every iteration; each "
+                          "step streams 1e8 independent random rays (1.5 - 5 GB of packet queues per round: larger than L2)"
+                          if nc == 64 else
+                          "cells + accumulators (0.5 - 2.7 GB) do not fit in L2; every step streams independent random rays")}
 
-    config = {"workload": "lexingtonHII20", "grid": f"{args.ncell}^3", "packets_per_iteration": n_packets,
-              "physics": "Planck 20000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse "
-                         "re-emission, temperature solve with line cooling",
-              "packets_per_iteration_per_gpu": per_gpu,
-              "parallelism": f"{world} GPU(s) x {per_gpu:.0e} packets, replicated grid, one all-reduce per iteration",
-              "l2_policy": "accumulators+cells (41 MB) are re-zeroed / rewritten every iteration; "
-                           "each step streams 1e8 independent random rays"}
 
-    if args.workload != "lexingtonHII20":
-        if args.impl == "reference":
-            raise SystemExit("the reference arm is timed on the headline workload (lexingtonHII20) only")
-        args.ncell = 256
-        config["workload"] = {"stromgren256": "stromgren.param physics on a 256^3 grid",
-                              "clumpy256": "synthetic clumpy 256^3, 16 sources, H-only (SURVEY 8d item 5)",
-                              "clumpy256L": "synthetic clumpy 256^3, 16 sources, Planck 40000 K + Verner + metals + "
-                                            "diffuse field + temperature solve"}[args.workload]
-        config["grid"] = "256^3"
-        config["physics"] = ("monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field"
-                             if args.workload != "clumpy256L" else config["physics"].replace("20000", "40000"))
-        config["l2_policy"] = "cells + accumulators (0.5 - 2.7 GB) do not fit in L2; every step streams independent random rays"
-        args.no_cpu_baseline = True
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        cb = cpu_reference_measure(n_packets, int(args.cpu_sample), args.steps, args.warmup)
-        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": max(args.warmup, 5),
-                "ms_per_step": 1e3 * cb["s_per_iteration_at_full_size"], "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": config, "cpu_baseline": cb,
-                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), file=result_out, flush=True)
-        return
-
+# --------------------------------------------------------------------------- our arm
+def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, spinup, want_e2e, scatter_rates):
+    """Time `steps` iterations of workload `name` at `n_packets` packets per iteration (whole job, split over the
+    ranks).  Returns the result record of rank 0 (every rank returns the same numbers after the max-reductions)."""
     import torch
     import torch.distributed as dist
     from cmacionize_b200 import capi, problems
+    from cmacionize_b200.distributed import cell_block, init_communicator, shard_packets
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200; there is no CPU path")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    if args.workload == "lexingtonHII20":
-        prob = problems.lexington(20, ncell=args.ncell, n_packets=n_packets, device=local_rank)
-    elif args.workload == "stromgren256":
+    w = WORKLOADS[name]
+    if name == "lexingtonHII20":
+        prob = problems.lexington(20, ncell=w["grid"], n_packets=n_packets, device=local_rank)
+    elif name == "stromgren256":
         prob = problems.stromgren(ncell=256, n_packets=n_packets, device=local_rank)
     else:
         prob = problems.synthetic_clumpy(ncell=256, n_packets=n_packets, device=local_rank,
-                                         variant="Lexington" if args.workload == "clumpy256L" else "H")
-    spinup_packets = int(args.spinup_packets) if args.spinup_packets else (
-        1_000_000 if args.workload == "lexingtonHII20" else 16_000_000)
+                                         variant="Lexington" if name == "clumpy256L" else "H")
     ctx = prob.ctx
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
-
-    from cmacionize_b200.distributed import accumulator_tensor, allreduce_sum, shard_packets
-    # accumulator buffer as a torch tensor (zero copy) for the NCCL all-reduce
-    acc = accumulator_tensor(ctx, torch.device("cuda", local_rank))
-    lo, cnt = shard_packets(n_packets, rank, world)   # shard packets by global id
-
-    def allreduce(_ctx):
-        allreduce_sum(acc)
-
+    init_communicator(ctx)                       # no-op for one rank
+    lo, cnt = shard_packets(n_packets, rank, world)
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    shoot_ms = []
+    marks = []       # per timed step: events (start, after reset+probabilities, after shoot, after exchange+update)
     kernel_ms = []   # (prepare ms, march ms, rounds) per timed step, from the library's CUDA events
-    update_ms = []
+    exch_ms = []     # (reduce, update, gather) of the exchange, N > 1
 
     def step(loop, npk_total=None, timed=False):
-        if npk_total is None:
-            my_lo, my_cnt = lo, cnt
-        else:
-            my_lo, my_cnt = shard_packets(npk_total, rank, world)
+        my_lo, my_cnt = (lo, cnt) if npk_total is None else shard_packets(npk_total, rank, world)
         with torch.cuda.stream(stream):
+            e = [ev() for _ in range(4)] if timed else None
+            if timed: e[0].record(stream)
             ctx.reset_accumulators()
             ctx.update_reemission_probabilities()
-            if timed:
-                e0, e1 = ev(), ev()
-                e0.record(stream)
+            if timed: e[1].record(stream)
             ctx.shoot(my_cnt, packet_offset=my_lo, seed=prob.seed, iteration=loop, want_counters=False)
             if timed:
-                e1.record(stream)
-                shoot_ms.append((e0, e1))
+                e[2].record(stream)
                 kernel_ms.append(ctx.shoot_timing(want_adds=False)[:3])
-            allreduce(ctx)
+            ctx.exchange_and_update(loop)        # N == 1: the state update alone
             if timed:
-                u0, u1 = ev(), ev()
-                u0.record(stream)
-            ctx.update_state(loop, 0.)
-            if timed:
-                u1.record(stream)
-                update_ms.append((u0, u1))
+                e[3].record(stream)
+                marks.append(e)
+                if world > 1:
+                    exch_ms.append(ctx.exchange_timing())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     loop = 0
-    for _ in range(args.spinup):
-        step(loop, npk_total=spinup_packets)
+    for _ in range(spinup):
+        step(loop, npk_total=w["spinup_packets"])
         loop += 1
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(loop)
         loop += 1
     barrier()
@@ -356,116 +332,213 @@ def main():
         t0e, t1e = ev(), ev()
         with torch.cuda.stream(stream):
             t0e.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step(loop, timed=True)
             loop += 1
         with torch.cuda.stream(stream):
             t1e.record(stream)
         barrier()
     launches = capi.kernel_launch_count() - launches0
-    elapsed = t0e.elapsed_time(t1e) * 1e-3
-    crossings, emissions = ctx.shoot_statistics()  # of the last step, summed over ranks by the all-reduce
-    if world > 1:
-        t = torch.tensor([elapsed], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed = float(t.item())
-    ms_per_step = 1e3 * elapsed / args.steps
-    value = n_packets * args.steps / elapsed
-    shoot_s = float(np.mean([a.elapsed_time(b) for a, b in shoot_ms])) * 1e-3
+    elapsed = max_over_ranks(t0e.elapsed_time(t1e) * 1e-3)
+    ms_per_step = 1e3 * elapsed / steps
+    value = n_packets * steps / elapsed
+    # counters of the last step: after the exchange every rank holds the sums over the ranks
+    crossings, emissions = ctx.shoot_statistics()
+    _, _, _, red_ops = ctx.shoot_timing()
+    mean = lambda xs: float(np.mean(xs))
+    prep_ms, march_ms, rounds = (mean([k[i] for k in kernel_ms]) for i in range(3))
+    phases = {"reset_and_reemission_probabilities": mean([m[0].elapsed_time(m[1]) for m in marks]),
+              "shoot": mean([m[1].elapsed_time(m[2]) for m in marks]),
+              "shoot_prepare_kernels": prep_ms, "shoot_march_kernels": march_ms,
+              "exchange_and_update": mean([m[2].elapsed_time(m[3]) for m in marks])}
+    if exch_ms:
+        phases["exchange_reduce"], phases["exchange_update_block"], phases["exchange_gather"] = (
+            mean([x[i] for x in exch_ms]) for i in range(3))
+    phases = {k: max_over_ranks(v) for k, v in phases.items()}
+    prep_ms, march_ms = phases["shoot_prepare_kernels"], phases["shoot_march_kernels"]
 
-    # ---- roofline of the dominant kernel (march_kernel: voxel walk + accumulation) ----
-    # unit of work = one packet-cell crossing; algorithmic bytes per crossing from SURVEY.md §8(d)
-    # (152 B: 24 B gather + 16 x 8 B accumulate).  One step launches the kernel once per round of the
-    # wavefront pipeline; bytes and time are summed over the rounds of a step, which gives the same
-    # ratio as per-launch averages.  Times are CUDA events recorded by the library on its own stream.
+    # ---- roofline of the dominant kernel (the voxel walk + accumulation) ----
+    # unit of work = one packet-cell crossing.  One step launches the kernel once per round of the wavefront
+    # pipeline; bytes and time are summed over the rounds of a step (same ratio as per-launch averages).  Times
+    # are CUDA events recorded by the library on its own stream.  All counts are per rank.
     peak, peak_src = measured_peaks()
-    _, _, _, red_ops = ctx.shoot_timing()            # accumulator adds of the last step (all ranks after all-reduce)
-    prep_ms = float(np.mean([k[0] for k in kernel_ms]))
-    march_ms = float(np.mean([k[1] for k in kernel_ms]))
-    rounds = float(np.mean([k[2] for k in kernel_ms]))
-    steps_per_packet = crossings / n_packets
-    bytes_per_step = prob.bytes_per_step
-    alg_bytes = (crossings / world) * bytes_per_step  # per rank per iteration
-    achieved = alg_bytes / (march_ms * 1e-3) / 1e9
-    red_rate = (red_ops / world) / (march_ms * 1e-3)
-    RED_PEAK = 1.878e11     # scattered FP64 RED/s measured on B200 (profiles/r01_microbench_red_gather.txt)
-    GATHER_PEAK = 1.747e11  # scattered 32-B gathers/s, L2-resident table (same file)
+    my_crossings, my_reds = crossings / world, red_ops / world
     red_per_crossing = red_ops / max(crossings, 1.)
-    crossing_rate = (crossings / world) / (march_ms * 1e-3)
-    # one crossing = one scattered gather + red_per_crossing scattered REDs through the same L1TEX pipe
-    crossing_bound = 1. / (1. / GATHER_PEAK + red_per_crossing / RED_PEAK)
-    full_layout = args.workload in ("lexingtonHII20", "clumpy256L")
-    # dram__bytes_read.sum + dram__bytes_write.sum of ONE march launch (16 Mi packets) from the ncu --set full captures
-    TRAFFIC = {
-        "lexingtonHII20": (4.546e9, "dram__bytes_read+write (3.45 + 1.09 GB) of the first march launch "
-                           "(16 Mi primaries) of a shoot, ncu --set full, profiles/r01_wavefront_lexington_final.md; the algorithmic "
-                           "bytes of that launch are ~70 GB: the 42 MB grid is L2 resident, DRAM only sees the packet queues "
-                           "(3.4 GB read) and the re-emission queue (1.1 GB written)"),
-        "clumpy256": (5.244e10, "dram__bytes_read+write (46.99 + 5.45 GB) of one coherent march launch (16 Mi packets, 2.44e9 "
-                      "crossings = 58.6 GB algorithmic), ncu --set full, profiles/r01_coherent_march.md: 21 DRAM bytes per "
-                      "crossing against 24 algorithmic ones (L2 reuse inside the cone of an ordered chunk); 92 B per crossing "
-                      "in emission order"),
+    crossing_rate = my_crossings / (march_ms * 1e-3)
+    full_layout = w["layout"] == "full"
+    gather_bytes = 32. if full_layout else 16.
+    survey_bytes = prob.bytes_per_step                      # 152 B (full layout), 24 B (H-only)
+    issued_bytes = gather_bytes + 8. * red_per_crossing     # what the kernel really moves per crossing
+    l2_resident = w["grid"] <= 64
+    red_peak, gather_peak = scatter_rates
+    lane_bound = 1. / (1. / gather_peak + red_per_crossing / red_peak)
+    hbm_achieved = my_crossings * (issued_bytes if l2_resident else survey_bytes) / (march_ms * 1e-3) / 1e9
+    traffic = measured_traffic(name)
+    roofline = {
+        "kernel": ("march_kernel<ACC_FULL>" if full_layout else
+                   ("march_kernel<ACC_HONLY>" if l2_resident else "march_lean_kernel (H-only coherent walk)")),
+        "cell_crossings_per_packet": crossings / n_packets, "emissions_per_packet": emissions / n_packets,
+        "accumulator_adds_per_crossing": red_per_crossing,
+        "algorithmic_bytes_per_crossing": {"survey_8d": survey_bytes, "issued": issued_bytes,
+                                           "note": "issued = record gathered + 8 B per accumulator term actually "
+                                                   "added (zero terms are skipped, in-warp sums merge same-cell terms); "
+                                                   "both counted on the device in this run"},
+        "kernel_ms": march_ms, "kernel_launches_per_step": rounds, "kernel_share_of_step": march_ms / ms_per_step,
+        "peak_source": peak_src,
+        "traffic": None, "traffic_note": None,
     }
-    roofline = {"bound": "hbm", "kernel": "march_kernel<ACC_FULL>" if full_layout else "march_kernel<ACC_HONLY>",
-                "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak,
-                "traffic": TRAFFIC.get(args.workload, (None, None))[0], "traffic_note": TRAFFIC.get(args.workload, (None, None))[1],
-                "peak_source": peak_src,
-                "cell_crossings_per_packet": steps_per_packet, "emissions_per_packet": emissions / n_packets,
-                "algorithmic_bytes_per_crossing": bytes_per_step, "kernel_ms": march_ms,
-                "kernel_launches_per_step": rounds,
-                "kernel_share_of_step": march_ms / ms_per_step,
-                "prepare_kernel_ms": prep_ms, "prepare_share_of_step": prep_ms / ms_per_step,
-                "shoot_ms": 1e3 * shoot_s,
-                "update_state_kernel_ms": float(np.mean([a.elapsed_time(b) for a, b in update_ms])),
-                "l1tex": {"achieved": crossing_rate, "peak": crossing_bound, "unit": "cell crossings/s",
-                          "frac": crossing_rate / crossing_bound,
-                          "note": "bound = 1 / (1/gathers_per_s + REDs_per_crossing/REDs_per_s) from the measured "
-                                  "scattered-gather and scattered-RED rates of the part (tools/microbench/red_bench.cu)"},
-                "atomic": {"achieved": red_rate, "peak": RED_PEAK, "unit": "FP64 RED/s", "frac": red_rate / RED_PEAK,
-                           "red_per_crossing": red_per_crossing,
-                           "note": "64^3 working set (8 MB cells + 34 MB accumulators) is L2 resident; ncu shows the "
-                                   "binding unit is L1TEX (scattered gather + RED lanes, 88 % busy), so the meaningful "
-                                   "denominator is the measured scattered-RED ceiling, not HBM"}}
-
-    metric = METRIC if args.workload == "lexingtonHII20" else METRIC.replace("lexingtonHII20", args.workload)
-    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "s_per_iteration": ms_per_step * 1e-3, "roofline": roofline, "gpu_launches": int(launches),
-            "clocks": clocks.summary()}
+    if traffic:
+        roofline["traffic"] = traffic["dram_bytes_per_crossing"] * my_crossings / max(rounds, 1.)
+        roofline["traffic_note"] = (f"{traffic['dram_bytes_per_crossing']:.2f} DRAM bytes per crossing "
+                                    f"(dram__bytes_read.sum + dram__bytes_write.sum of {traffic['kernel']} in "
+                                    f"{traffic['report']}, ncu --set full) x the crossings of one launch of this run")
+    if l2_resident:
+        # the working set (8 MB cells + 34 MB accumulators) is L2 resident: the binding unit is the L1TEX lane
+        # throughput of scattered gathers and REDs, measured on this device in this run
+        roofline.update({
+            "bound": "l1tex-lane", "achieved": crossing_rate, "peak": lane_bound, "unit": "cell crossings/s",
+            "frac": crossing_rate / lane_bound,
+            "peak_note": (f"1 / (1/gathers_per_s + REDs_per_crossing/REDs_per_s) with {gather_peak:.3e} scattered "
+                          f"16-B gathers/s and {red_peak:.3e} scattered FP64 RED/s measured on this device in this run "
+                          "(cmib_measure_scatter_rates: every lane of a warp in a different 128-B line)"),
+            "hbm": {"achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+                    "note": "issued bytes / kernel time against the HBM copy peak: not the binding roof here "
+                            "(ncu: DRAM sees the packet queues only)"}})
+    else:
+        roofline.update({
+            "bound": "hbm", "achieved": hbm_achieved, "peak": peak, "unit": "GB/s", "frac": hbm_achieved / peak,
+            "issued_bytes_frac": my_crossings * issued_bytes / (march_ms * 1e-3) / 1e9 / peak,
+            "l1tex_lane": {"achieved": crossing_rate, "peak": lane_bound, "unit": "cell crossings/s",
+                           "frac": crossing_rate / lane_bound,
+                           "note": "scattered-lane bound of a walk WITHOUT coherence (one gather + the REDs per lane); "
+                                   "the coherent walk may exceed it: its lanes share sectors and sum in registers"}})
+    rec = {"value": value, "unit": UNIT, "ms_per_step": ms_per_step, "s_per_iteration": ms_per_step * 1e-3,
+           "steps": steps, "warmup": warmup, "config": config_of(name, n_packets, world),
+           "roofline": roofline, "phases_ms": phases, "gpu_launches": int(launches), "clocks": clocks.summary()}
 
     # ---- e2e: the same iteration through the C ABI with HOST buffers ----
-    # every rank uploads its replica of the cells from pinned host memory, shoots its shard, joins the
-    # all-reduce, updates and reads the result back; wall clock between barriers, max over ranks
-    if not args.no_e2e:
+    # every rank uploads ITS cell block from pinned host memory, the blocks are gathered over NVLink, the rank
+    # shoots its packets, joins the exchange and reads its block of the result back; wall clock between
+    # barriers, max over ranks
+    if want_e2e:
         nc = ctx.ncells
+        b0, b1 = cell_block(nc, rank, world)
+        nb = b1 - b0
         pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
-        n_h, T_h, x_h, heat_h = pin(nc), pin(nc), pin(14, nc), pin(2, nc)
+        n_h, T_h, x_h, heat_h = pin(nb), pin(nb), pin(14, nb), pin(2, nb)
+        if world > 1:
+            ctx.comm_gather_state()
         n0, T0, x0, _ = ctx.download_cells()
-        n_h[:] = n0; T_h[:] = T0; x_h[:] = x0
-        e2e_steps = max(2, min(args.steps, 3))
+        n_h[:] = n0[b0:b1]; T_h[:] = T0[b0:b1]; x_h[:] = x0[:, b0:b1]
+        del n0, T0, x0
+        e2e_steps = max(2, min(steps, 3))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             with torch.cuda.stream(stream):
-                ctx.upload_cells(n_h, T_h, x_h)                       # H2D: 16 doubles per cell
-                problems.run_iteration(prob, loop, n_packets=cnt, packet_offset=lo,
-                                       allreduce=allreduce if world > 1 else None)
-                ctx.download_cells_into(n_h, T_h, x_h, heat_h)        # D2H: 18 doubles per cell
+                ctx.upload_cells_block(b0, b1, n_h, T_h, x_h)             # H2D: 16 doubles per cell of the block
+                ctx.comm_gather_cells_all()                               # N > 1: replicate what was uploaded
+                step(loop)
+                ctx.download_cells_block_into(b0, b1, n_h, T_h, x_h, heat_h)  # D2H: 18 doubles per cell of the block
             loop += 1
         barrier()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        line["e2e"] = {"value": n_packets * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * 8 * nc * world,
-                       "d2h_bytes_per_step": 18 * 8 * nc * world, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+        dt = max_over_ranks(time.perf_counter() - t0)
+        rec["e2e"] = {"value": n_packets * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * 8 * nc,
+                      "d2h_bytes_per_step": 18 * 8 * nc, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+                      "note": "bytes are totals over the ranks: every rank moves its own cell block"}
     else:
-        line["e2e"] = None
+        rec["e2e"] = None
+    if world > 1:
+        ctx.comm_finalize()
+    ctx.close()
+    return rec
 
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
+
+def main():
+    result_out = _claim_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--packets", type=float, default=FULL_PACKETS, help="packets per iteration of the whole job (benchmark: 1e8)")
+    ap.add_argument("--spinup", type=int, default=6, help="untimed iterations with fewer packets that bring the grid to the "
+                    "ionised steady state and past the 4 ionization-only iterations")
+    ap.add_argument("--cpu-sample", type=float, default=1e6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-weak", action="store_true")
+    ap.add_argument("--workload", default="lexingtonHII20", choices=sorted(WORKLOADS),
+                    help="the workload of the top-level keys (default: the configuration BASELINE.json's metric is quoted on)")
+    ap.add_argument("--workloads", default="stromgren256,clumpy256",
+                    help="comma-separated extra workloads attached under `workloads` ('' = none)")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_packets = int(args.packets)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if args.workload != "lexingtonHII20":
+            raise SystemExit("the reference arm is timed on the headline workload (lexingtonHII20) only")
+        cb = cpu_reference_measure(n_packets, int(args.cpu_sample), args.steps, args.warmup)
+        line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": max(args.warmup, 5),
+                "ms_per_step": 1e3 * cb["s_per_iteration_at_full_size"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config_of("lexingtonHII20", n_packets, max(args.gpus, 1)), "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), file=result_out, flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from cmacionize_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # scattered-lane ceilings of this device, measured now (denominators of the l1tex-lane roofline)
+    with capi.Context([0, 0, 0], [1, 1, 1], [64, 64, 64], device=local_rank) as probe:
+        scatter_l2 = probe.measure_scatter_rates(64 ** 3)
+        scatter_hbm = probe.measure_scatter_rates(256 ** 3)
+
+    head = run_workload(args.workload, n_packets, args, rank, world, local_rank, args.steps, args.warmup, args.spinup,
+                        not args.no_e2e, scatter_l2 if WORKLOADS[args.workload]["grid"] <= 64 else scatter_hbm)
+    metric = METRIC if args.workload == "lexingtonHII20" else METRIC.replace("lexingtonHII20", args.workload)
+    line = {"metric": metric, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": head["config"],
+            "s_per_iteration": head["s_per_iteration"], "roofline": head["roofline"], "phases_ms": head["phases_ms"],
+            "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "e2e": head["e2e"],
+            "scatter_rates_measured": {"l2_resident_table_64^3": {"red_per_s": scatter_l2[0], "gather_per_s": scatter_l2[1]},
+                                       "hbm_resident_table_256^3": {"red_per_s": scatter_hbm[0], "gather_per_s": scatter_hbm[1]}}}
+
+    if world > 1 and not args.no_weak:
+        # the weak figure (every GPU shoots the configuration's packet count: N x 1e8 distinct packets per iteration)
+        wk = run_workload(args.workload, n_packets * world, args, rank, world, local_rank, 2, 1, args.spinup, False,
+                          scatter_l2 if WORKLOADS[args.workload]["grid"] <= 64 else scatter_hbm)
+        line["weak"] = {"value": wk["value"], "unit": UNIT, "ms_per_step": wk["ms_per_step"],
+                        "packets_per_iteration": n_packets * world, "steps": 2, "phases_ms": wk["phases_ms"]}
+
+    extra = [x for x in args.workloads.split(",") if x and x != args.workload]
+    if extra:
+        line["workloads"] = {}
+        for name in extra:
+            rec = run_workload(name, n_packets, args, rank, world, local_rank, args.extra_steps, 2, args.spinup,
+                               not args.no_e2e, scatter_l2 if WORKLOADS[name]["grid"] <= 64 else scatter_hbm)
+            rec["metric"] = METRIC.replace("lexingtonHII20", name)
+            rec["n_gpus"] = world
+            rec["scaling"] = "strong"
+            line["workloads"][name] = rec
+
+    if rank == 0 and not args.no_cpu_baseline and world == 1 and args.workload == "lexingtonHII20":
         try:
             line["cpu_baseline"] = cpu_reference_measure(n_packets, int(args.cpu_sample), 2, 5)
         except Exception as exc:  # the oracle is optional evidence, never part of the product path
@@ -473,8 +546,8 @@ def main():
 
     if rank == 0:
         print(json.dumps(line), file=result_out, flush=True)
-    ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

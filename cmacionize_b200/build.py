@@ -65,8 +65,7 @@ def build_host(force: bool = False) -> Path:
     if not force and not stale:
         return HOST_LIB
     HOST_BIN.parent.mkdir(exist_ok=True)
-    common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-pthread",
-              "-I/usr/local/cuda/include"]  # nccl.h needs cuda_runtime.h for cudaStream_t
+    common = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-ffp-contract=off", "-fPIC", "-pthread"]
     link = [f"-L{HERE}", "-lcmib", "-ldl", "-lz", "-Wl,-rpath,$ORIGIN"]  # NCCL is dlopen-ed on demand
     subprocess.check_call(common + ["-shared", str(HOST / "host_api.cpp"), "-o", str(HOST_LIB)] + link)
     link_bin = [f"-L{HERE}", "-lcmib", "-ldl", "-lz", "-Wl,-rpath,$ORIGIN/.."]

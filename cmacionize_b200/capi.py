@@ -61,6 +61,11 @@ def _load() -> C.CDLL:
     lib = C.CDLL(str(LIB_PATH))
     lib.cmib_last_error.restype = C.c_char_p
     lib.cmib_kernel_launch_count.restype = C.c_uint64
+    lib.cmib_distribute.restype = C.c_uint64
+    lib.cmib_distribute.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    lib.cmib_distribute_block.restype = None
+    lib.cmib_distribute_block.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
+                                          C.POINTER(C.c_uint64)]
     if lib.cmib_abi_version() != 1:
         raise ImportError("libcmib.so ABI version mismatch")
     lib.cmib_set_abort_on_error(1 if os.environ.get("CMIB_ABORT_ON_ERROR") == "1" else 0)
@@ -96,6 +101,25 @@ def _check(rc: int) -> None:
 
 def kernel_launch_count() -> int:
     return int(lib.cmib_kernel_launch_count())
+
+
+def distribute(number: int, size: int, rank: int) -> int:
+    """MPICommunicator::distribute (src/MPICommunicator.hpp:207-222); no GPU needed"""
+    return int(lib.cmib_distribute(number, size, rank))
+
+
+def distribute_block(rank: int, size: int, begin: int, end: int):
+    """MPICommunicator::distribute_block (src/MPICommunicator.hpp:237-255); no GPU needed"""
+    lo, hi = C.c_uint64(), C.c_uint64()
+    lib.cmib_distribute_block(rank, size, begin, end, C.byref(lo), C.byref(hi))
+    return int(lo.value), int(hi.value)
+
+
+def comm_unique_id() -> bytes:
+    """128 bytes that rank 0 hands to the other ranks before Context.comm_init_rank"""
+    buf = C.create_string_buffer(128)
+    _check(lib.cmib_comm_unique_id(buf))
+    return buf.raw
 
 
 class Context:
@@ -281,6 +305,54 @@ class Context:
         t = C.c_double(0.)
         _check(lib.cmib_shoot_optical_depth(self._h, C.byref(t)))
         return t.value
+
+    # ---- multi-GPU (include/cmib.h: the reference's MPICommunicator for this path) -------------
+    def comm_init_rank(self, size: int, rank: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        _check(lib.cmib_comm_init_rank(self._h, C.c_int32(size), C.c_int32(rank), C.c_char_p(unique_id)))
+
+    def comm_finalize(self):
+        _check(lib.cmib_comm_finalize(self._h))
+
+    def comm_info(self):
+        """(rank, size, first cell, one past the last cell of this rank's block)"""
+        r, n = C.c_int32(), C.c_int32()
+        lo, hi = C.c_uint64(), C.c_uint64()
+        _check(lib.cmib_comm_info(self._h, C.byref(r), C.byref(n), C.byref(lo), C.byref(hi)))
+        return int(r.value), int(n.value), int(lo.value), int(hi.value)
+
+    def exchange_and_update(self, loop, allreduce=False):
+        """sum the accumulators over the ranks, update this rank's cell block, gather the opacity records"""
+        _check(lib.cmib_comm_exchange_and_update(self._h, C.c_uint32(loop), C.c_int(1 if allreduce else 0)))
+
+    def exchange_timing(self):
+        ms = (C.c_double * 3)()
+        _check(lib.cmib_comm_exchange_timing(self._h, ms))
+        return tuple(ms)
+
+    def comm_gather_state(self):
+        _check(lib.cmib_comm_gather_state(self._h))
+
+    def comm_gather_cells_all(self):
+        _check(lib.cmib_comm_gather_cells_all(self._h))
+
+    def update_state_block(self, loop, totweight, cell_begin, cell_end):
+        _check(lib.cmib_update_state_block(self._h, C.c_uint32(loop), C.c_double(totweight), C.c_uint64(cell_begin),
+                                           C.c_uint64(cell_end)))
+
+    def upload_cells_block(self, cell_begin, cell_end, n, T, x):
+        """host arrays hold ONLY the block: n, T [nb], x [14][nb]"""
+        _check(lib.cmib_upload_cells_block(self._h, C.c_uint64(cell_begin), C.c_uint64(cell_end), _p(n), _p(T), _p(x)))
+
+    def download_cells_block_into(self, cell_begin, cell_end, n, T, x, heat):
+        _check(lib.cmib_download_cells_block(self._h, C.c_uint64(cell_begin), C.c_uint64(cell_end), _p(n), _p(T), _p(x),
+                                             _p(heat)))
+
+    def measure_scatter_rates(self, n_cells=None):
+        """(scattered FP64 RED/s, scattered 16-byte gathers/s) of this device, measured now"""
+        a, b = C.c_double(), C.c_double()
+        _check(lib.cmib_measure_scatter_rates(self._h, C.c_uint64(n_cells or self.ncells), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def accumulator_buffer(self):
         ptr = _vp()

@@ -15,7 +15,9 @@
 #include <string>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <nccl.h> /* types only: libnccl.so.2 is bound at run time (NcclApi), nothing is linked */
+
 
 #include "../../include/cmib.h"
 #include "kernels.cuh"
@@ -90,6 +92,51 @@ inline unsigned blocks_for(int64_t n, int bs) { return (unsigned)((n + bs - 1) /
 
 } // namespace
 
+/* NCCL entry points, resolved on first use.  A python process that imported torch has torch's bundled
+ * libnccl.so.2 loaded already and dlopen returns that one; otherwise the system library. */
+struct NcclApi {
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclReduce) Reduce = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string error;
+  static NcclApi &get() {
+    static NcclApi api = load();
+    return api;
+  }
+
+private:
+  static NcclApi load() {
+    NcclApi a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      a.error = std::string("multi-GPU runs need NCCL: ") + dlerror();
+      return a;
+    }
+#define CMIB_NCCL_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name))
+    CMIB_NCCL_SYM(GetUniqueId); CMIB_NCCL_SYM(CommInitRank); CMIB_NCCL_SYM(CommInitAll); CMIB_NCCL_SYM(CommDestroy);
+    CMIB_NCCL_SYM(AllReduce); CMIB_NCCL_SYM(Reduce); CMIB_NCCL_SYM(Broadcast); CMIB_NCCL_SYM(GroupStart);
+    CMIB_NCCL_SYM(GroupEnd); CMIB_NCCL_SYM(GetErrorString);
+#undef CMIB_NCCL_SYM
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommInitAll || !a.CommDestroy || !a.AllReduce || !a.Reduce ||
+        !a.Broadcast || !a.GroupStart || !a.GroupEnd || !a.GetErrorString)
+      a.error = "libnccl lacks the expected entry points";
+    return a;
+  }
+};
+#define NCCL_OK(expr)                                                                                      \
+  do {                                                                                                     \
+    ncclResult_t r_ = (expr);                                                                              \
+    if (r_ != ncclSuccess) CMIB_FAIL("%s failed: %s", #expr, NcclApi::get().GetErrorString(r_));          \
+  } while (0)
+
 struct cmib_context {
   int device = 0;
   int sm_count = 0;
@@ -149,32 +196,25 @@ struct cmib_context {
   int queue_mode = -1;
   DevBuf<double> mq, rq, eq;
   DevBuf<unsigned long long> ctl;
-  DevBuf<uint32_t> sort_key, sort_order, sort_hist;
-  DevBuf<uint32_t> sort_key_out, sort_iota; /* coherent march (sort mode 2): radix sort of (key, slot) pairs */
-  DevBuf<unsigned char> sort_temp;
-  DevBuf<double> hot_acc;       /* replicated accumulators of the cells around the sources */
+  DevBuf<uint32_t> sort_key, sort_rank, sort_order, sort_hist, sort_offs, sort_block_sums; /* coherent march: counting sort */
   DevBuf<uint32_t> d_src_cell;  /* packed cell indices of the sources */
   std::vector<uint32_t> h_src_cell;
   int hot_replicas = 0;
   DevBuf<unsigned long long> upd_counter; /* next unprocessed cell of update_temperature_kernel */
   int update_blocks_per_sm[2] = {0, 0};
-  /* march-queue order: 0 emission order, 1 coarse counting sort (measured slower),
-   * 2 coherent march = fine radix sort + in-warp sums (march_kernel<MODE, true>),
-   * -1 (default) measured: grids that fit in L2 use 0 (2 loses there on every workload measured);
-   * for larger grids the two are timed on successive large shoots of this context — time per cell
-   * crossing, so that the growth of the ionised volume from one shoot to the next does not bias the
-   * comparison — and the faster one is kept (a shoot of >= 4 queue capacities times the two orders on
-   * its own rounds 1 and 2 instead and finishes in the winner).  The timed pair is repeated after 2, 4, 8 and
-   * then every 16 shoots: the regime changes quickly during the first iterations of a run (a small
-   * ionised bubble fits in L2, the converged one may not).  Both orders shoot the same packets; only
-   * the order of the atomic adds differs. */
+  /* march-queue order: 0 emission order, 2 coherent march = queue read in key order + in-warp sums,
+   * -1 (default) by rule: 2 when cells + accumulators do not fit in L2 and the shoot is large, else 0.
+   * (Round 1 timed the two orders against each other inside live shoots because its coherent H-only kernel
+   * lost on single-source grids; march_lean_kernel wins on every HBM-resident grid measured, so the choice
+   * is a deterministic function of the working set: step times are reproducible.)  Both orders shoot the
+   * same packets; only the order of the atomic adds differs. */
   int sort_mode = -1;
-  int tune_shoots = 0;                 /* large shoots seen */
-  int tune_next = 1;                   /* shoot at which the next timed pair starts */
-  int tune_interval = 2;               /* shoots between the end of a pair and the next one */
-  double tune_ns_per_crossing[3] = {0., 0., 0.}; /* indexed by order (0, 2) */
-  int tuned_order = 0;
-  cudaEvent_t tune_ev[3] = {nullptr, nullptr, nullptr};
+  /* multi-GPU (MPICommunicator of the reference): one communicator rank per context */
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double exchange_ms[3] = {0., 0., 0.};
+  double walk_cells = 0.; /* mean walk length (cells) of the last large shoot: sizes the direction bins of the sort key */
   size_t l2_bytes = 0;
   unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2][2] = {{0, 0}, {0, 0}}; /* [layout][plain, coherent] */
@@ -213,10 +253,17 @@ struct cmib_context {
     if (const char *e = getenv("CMIB_HONLY_OFFSET")) return atoi(e);
     return (!honly_planar() && honly_cell_stride() == 16) ? 8 : 0;
   }
-  size_t acc_doubles(int mode) const {
-    if (mode != ACC_HONLY) return ACC_COUNTERS + (size_t)geom.ncells * 16;
-    return ACC_COUNTERS + 64 + (size_t)geom.ncells * (honly_planar() ? 2 : (size_t)honly_cell_stride());
+  /* the accumulator buffer: counters + per-cell accumulators (acc_main_doubles: what collectives move and callers
+   * see), then the hot-cell replicas of the shoot (hot_doubles; always zero outside a shoot).  One allocation, so
+   * that the walk forms every accumulator address from one base and a 32-bit index (march_coherent.cuh). */
+  size_t acc_main_doubles(int mode) const {
+    size_t n = (mode != ACC_HONLY) ? ACC_COUNTERS + (size_t)geom.ncells * 16
+                                   : ACC_COUNTERS + 64 + (size_t)geom.ncells * (honly_planar() ? 2 : (size_t)honly_cell_stride());
+    return (n + 15) & ~(size_t)15;
   }
+  size_t hot_doubles() const { return hot_replicas > 0 ? (size_t)hot_replicas * HOT_MAX_SOURCES * HOT_CELLS * HOT_STRIDE : 0; }
+  size_t acc_doubles(int mode) const { return acc_main_doubles(mode) + hot_doubles(); }
+  double *hot_acc() const { return hot_replicas > 0 ? acc.p + acc_main_doubles(acc_mode) : nullptr; }
 };
 
 namespace {
@@ -322,20 +369,31 @@ int set_spectrum_model(cmib_context *ctx, SpectrumModel &sp, std::vector<double>
   return 0;
 }
 
-uint64_t default_queue_capacity() {
+/* packets per round of the wavefront pipeline.  Emission order: 16 Mi (5 GB of queues in the full layout; measured
+ * 124 -> 117 ms per lexingtonHII20 step against 4 Mi).  Coherent march: 64 Mi — the sort key has ~log2(packets per
+ * round / 4) bits to spend on source, direction and optical depth, so larger rounds order many-source problems
+ * finer (clumpy 256^3, 16 sources: 7.7e8 -> 9.1e8 packets/s from 16 Mi to 64 Mi, profiles/r02_lean_march.md) */
+uint64_t default_queue_capacity(bool coherent) {
   const char *e = getenv("CMIB_QUEUE_CAPACITY");
   if (e) {
     const long long v = atoll(e);
     if (v >= 1024) return (uint64_t)v;
   }
-  return 1ull << 24; /* 16 Mi packets: 5 GB of queues (full layout); measured 124 -> 117 ms per lexingtonHII20 step vs 4 Mi */
+  return coherent ? (1ull << 26) : (1ull << 24);
 }
 
 /* one cmib_shoot call on the wavefront path: rounds of prepare -> march until the
  * queues run dry.  The host only reads back the march-queue sizes every few rounds. */
 int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   const int mode = ctx->acc_mode;
-  uint64_t cap = default_queue_capacity();
+  /* order of the march queue (cmib_context::sort_mode; CMIB_SORT overrides for A/B runs) */
+  int sort = ctx->sort_mode;
+  if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
+  if (sort < 0) {
+    const size_t working_set = (size_t)ctx->geom.ncells * ((mode == ACC_HONLY ? 16 : sizeof(CellOpacity)) + (mode == ACC_HONLY ? 16 : 128));
+    sort = (working_set > ctx->l2_bytes && P.n_packets >= (1ull << 20)) ? 2 : 0;
+  }
+  uint64_t cap = default_queue_capacity(sort != 0);
   if (P.n_packets < cap) cap = (P.n_packets + 1023) / 1024 * 1024;
   const int nf = (mode == ACC_HONLY) ? MarchQueueLayout<ACC_HONLY>::NFIELDS : MarchQueueLayout<ACC_FULL>::NFIELDS;
   if (ctx->queue_capacity < cap || ctx->queue_mode != mode) {
@@ -363,6 +421,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
   ctx->h_ctl[CTL_REMAINING] = P.n_packets;
   CUDA_OK(cudaMemcpyAsync(ctx->ctl.p, ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
+  shoot_begin_kernel<<<1, 1, 0, s>>>(ctx->ctl.p, P.acc);
   WavefrontParams W;
   W.sp = P;
   W.ctl = ctx->ctl.p;
@@ -371,87 +430,71 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   W.eq = ctx->eq.p;
   W.capacity = cap;
   W.acc_j = P.acc + ACC_COUNTERS + P.honly_offset;
+  W.hot_index0 = P.hot_acc ? (uint32_t)(P.hot_acc - W.acc_j) : 0xffffffffu;
   for (int d = 0; d < 3; ++d) W.lean_n16[d] = 16u * (uint32_t)P.geom.ncell[d];
   W.lean_k[0] = P.geom.ncell[1] * P.geom.ncell[2];
   W.lean_k[1] = P.geom.ncell[2];
-  /* order of the march queue (cmib_context::sort_mode; CMIB_SORT overrides for A/B runs) */
-  int sort = ctx->sort_mode;
-  if (const char *e = getenv("CMIB_SORT")) sort = atoi(e);
-  bool tuning = false;        /* this whole shoot is one half of a timed pair */
-  bool tune_in_shoot = false; /* rounds 1 and 2 of this shoot are the timed pair */
-  if (sort < 0) {
-    const size_t working_set = (size_t)ctx->geom.ncells * ((mode == ACC_HONLY ? 16 : sizeof(CellOpacity)) + (mode == ACC_HONLY ? 16 : 128));
-    if (working_set <= ctx->l2_bytes || P.n_packets < (1ull << 20)) {
-      sort = (working_set <= ctx->l2_bytes) ? 0 : ctx->tuned_order;
-    } else {
-      /* shoot 0 is a warm-up (allocations); a timed pair = order 0, then order 2 */
-      const int phase = ctx->tune_shoots - ctx->tune_next;
-      /* a shoot of at least four full queues carries the pair itself: its rounds 1 and 2 (same grid
-       * state, same mix of primaries and re-emitted packets) run in order 0 and in order 2, the rest
-       * in the winner — one round of ~n/capacity in the slower order instead of a whole shoot */
-      tune_in_shoot = (phase == 0 && P.n_packets >= 4 * cap);
-      sort = tune_in_shoot ? 2 : ((phase == 0) ? 0 : (phase == 1 ? 2 : ctx->tuned_order));
-      tuning = !tune_in_shoot && (phase == 0 || phase == 1);
-      if (phase == 1 || tune_in_shoot) {
-        ctx->tune_next = ctx->tune_shoots + 1 + ctx->tune_interval;
-        if (ctx->tune_interval < 16) ctx->tune_interval *= 2;
-      }
-      ++ctx->tune_shoots;
-    }
-  }
+  W.agg = 1;
+  if (sort == 1) { sort = 2; W.agg = 0; } /* A/B: ordered queue, plain kernel */
   W.sort = sort;
-  W.key = nullptr; W.order = nullptr; W.hist = nullptr; W.nbins = 0; W.isrc_bits_shift = SORT_DIR_BITS;
-  W.sort_n = 0; W.fine_dir_bits = 22; W.fine_key_bits = 22; W.chunk_stride = 1; W.agg = 1;
-  size_t sort_temp_bytes = 0;
+  W.key = W.rank = W.order = W.hist = W.offs = W.block_sums = nullptr;
+  W.nbins = 0; W.fine_dir_bits = 22; W.fine_key_bits = 22; W.tau_bits = 0; W.chunk_stride = 1;
   bool sort_reemitted_rounds = false;
   if (sort == 2) {
-    /* key = source | direction (wavefront.cuh): as many direction bits as the source index leaves */
+    /* key = source | direction (wavefront.cuh): as many direction bits as the source index leaves of
+     * SORT_MAX_KEY_BITS; 0 | key for primaries, 1 | position key for re-emitted packets */
     int src_bits = 0;
     while ((1ll << src_bits) < (long long)P.src.n_sources) ++src_bits;
-    /* 24 key bits = 3 radix passes while that leaves >= 18 direction bits (512 x 512 bins per source) */
-    int dir_bits = 23 - src_bits;
+    /* how many direction bins?  Packets of one bin should still cross the same cells at the END of their walk:
+     * bin width x walk length ~ one cell, i.e. 4 pi L^2 bins per source for walks of L cells.  L comes from the
+     * previous large shoot of this context (cell crossings per walk / 1.5: an isotropic direction crosses
+     * |dx| + |dy| + |dz| = 1.5 walls per cell of path on average), else half the grid.  Measured (B200, 1.6e7
+     * packets per round): stromgren 256^3, L = 85: 16 direction + 6 depth bits 11.0 ms, 18 + 4 11.5, 22 + 0 13.1;
+     * clumpy 256^3, 16 sources, L = 106: 18 + 0 19.7 ms, 16 + 2 20.2, 14 + 4 22.2 (profiles/r02_lean_march.md).
+     * The bits that are left (of ~log2(packets per round / 4)) order the packets of a direction bin by sampled
+     * optical depth, so that the 8 lanes of a refill group are absorbed close together. */
+    double walk = 0.5 * (double)std::max(P.geom.ncell[0], std::max(P.geom.ncell[1], P.geom.ncell[2]));
+    if (ctx->walk_cells > 0.) walk = ctx->walk_cells;
+    int dir_bits = 2 * (int)std::lround(0.5 * std::log2(4. * 3.14159265358979 * walk * walk)); /* nearest even */
+    if (const char *e = getenv("CMIB_DIR_BITS")) dir_bits = atoi(e) & ~1;
     if (dir_bits > 22) dir_bits = 22;
-    if (dir_bits < 18) dir_bits = 18;
-    if (dir_bits + src_bits > 30) dir_bits = 30 - src_bits;
-    if (dir_bits < 2) W.sort = sort = 0; /* more than 2^28 sources: no room for a direction */
-    W.fine_dir_bits = dir_bits & ~1;
-    W.fine_key_bits = W.fine_dir_bits + src_bits;
+    if (dir_bits < 8) dir_bits = 8;
+    int budget = 2; /* ~4 packets per bin */
+    while ((1ull << budget) < (P.n_packets < cap ? P.n_packets : cap)) ++budget;
+    budget -= 2;
+    if (budget > SORT_MAX_KEY_BITS) budget = SORT_MAX_KEY_BITS;
+    if (const char *e = getenv("CMIB_KEY_BITS")) budget = atoi(e) > SORT_MAX_KEY_BITS ? SORT_MAX_KEY_BITS : atoi(e);
+    if (src_bits + dir_bits > SORT_MAX_KEY_BITS) dir_bits = (SORT_MAX_KEY_BITS - src_bits) & ~1;
+    int tau_bits = budget - src_bits - dir_bits;
+    if (const char *e = getenv("CMIB_TAU_BITS")) tau_bits = atoi(e);
+    if (tau_bits < 0) tau_bits = 0;
+    if (tau_bits > 8) tau_bits = 8;
+    if (src_bits + dir_bits + tau_bits > SORT_MAX_KEY_BITS) tau_bits = SORT_MAX_KEY_BITS - src_bits - dir_bits;
+    if (dir_bits < 2) W.sort = sort = 0; /* no room for a direction next to that many sources */
+    W.fine_dir_bits = dir_bits;
+    W.tau_bits = tau_bits;
+    W.fine_key_bits = dir_bits + src_bits + tau_bits;
+    if (W.fine_key_bits < 12) W.fine_key_bits = 12; /* nbins a multiple of the scan tile */
   }
   if (sort == 2) {
-    W.sort = 2;
     if (const char *e = getenv("CMIB_CHUNK_STRIDE")) W.chunk_stride = (uint32_t)atoll(e); /* e.g. the prime 1000003 */
     if (W.chunk_stride < 1u || cap / MARCH_CHUNK >= W.chunk_stride) W.chunk_stride = 1u;
     if (const char *e = getenv("CMIB_AGG")) W.agg = atoi(e) != 0;
     if (const char *e = getenv("CMIB_SORT_REEMITTED")) sort_reemitted_rounds = atoi(e) != 0;
+    W.nbins = 2u << W.fine_key_bits;
     if (ctx->sort_key.n < cap) {
       CUDA_OK(ctx->sort_key.resize(cap));
+      CUDA_OK(ctx->sort_rank.resize(cap));
       CUDA_OK(ctx->sort_order.resize(cap));
     }
-    if (ctx->sort_key_out.n < cap) {
-      CUDA_OK(ctx->sort_key_out.resize(cap));
-      CUDA_OK(ctx->sort_iota.resize(cap));
-      iota_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->sort_iota.p, cap);
+    if (ctx->sort_hist.n < W.nbins) {
+      CUDA_OK(ctx->sort_hist.resize(W.nbins));
+      CUDA_OK(ctx->sort_offs.resize(W.nbins));
+      CUDA_OK(ctx->sort_block_sums.resize(SORT_MAX_TILES));
+      CUDA_OK(cudaMemsetAsync(ctx->sort_hist.p, 0, W.nbins * sizeof(uint32_t), ctx->stream));
     }
-    CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, sort_temp_bytes, ctx->sort_key.p, ctx->sort_key_out.p,
-                                            ctx->sort_iota.p, ctx->sort_order.p, (int64_t)cap, 0, W.fine_key_bits + 1, ctx->stream));
-    if (ctx->sort_temp.n < sort_temp_bytes) CUDA_OK(ctx->sort_temp.resize(sort_temp_bytes));
-    sort_temp_bytes = ctx->sort_temp.n;
-    W.key = ctx->sort_key.p; W.order = ctx->sort_order.p;
-  } else if (sort) {
-    /* keep the number of bins <= 2^20: fewer direction bits when there are many sources */
-    int shift = 6; /* 8 x 8 direction bins per source: see wavefront.cuh */
-    if (const char *e = getenv("CMIB_SORT_DIR_BITS")) shift = atoi(e);
-    if (shift < 0) shift = 0;
-    if (shift > SORT_DIR_BITS) shift = SORT_DIR_BITS;
-    while (shift > 0 && ((uint64_t)P.src.n_sources << shift) > (1ull << 20)) --shift;
-    W.isrc_bits_shift = shift;
-    W.nbins = (uint32_t)(((uint64_t)P.src.n_sources << shift) + SORT_POS_BINS);
-    if (ctx->sort_key.n < cap) {
-      CUDA_OK(ctx->sort_key.resize(cap));
-      CUDA_OK(ctx->sort_order.resize(cap));
-    }
-    if (ctx->sort_hist.n < W.nbins + 1) CUDA_OK(ctx->sort_hist.resize(W.nbins + 1));
-    W.key = ctx->sort_key.p; W.order = ctx->sort_order.p; W.hist = ctx->sort_hist.p;
+    W.key = ctx->sort_key.p; W.rank = ctx->sort_rank.p; W.order = ctx->sort_order.p;
+    W.hist = ctx->sort_hist.p; W.offs = ctx->sort_offs.p; W.block_sums = ctx->sort_block_sums.p;
   }
   /* persistent grids: exactly the CTAs that are resident at once (a partial second wave of a
    * grid-stride kernel runs at a fraction of the machine) */
@@ -500,31 +543,28 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   const int lean_heat = !(P.src.spectrum.kind == SPECTRUM_MONOCHROMATIC && P.src.spectrum.mono_frequency == P.nu_H &&
                           P.src.reemission_kind == REEMISSION_NONE && P.src.continuous_kind == CONTINUOUS_NONE);
   const int lean_periodic = (P.geom.periodic[0] | P.geom.periodic[1] | P.geom.periodic[2]) ? 1 : 0;
+  /* ... and then every packet carries the same sigma_H (FixedValue / Bimodal tables, source.cuh packet_cross_sections:
+   * the H-only layout excludes Verner) and the weight of the discrete sources */
+  W.uni_sigH = (P.src.xs_kind == XS_BIMODAL && !(P.src.spectrum.mono_frequency < P.src.xs_limit)) ? P.src.xs_high[0] : P.src.xs_fixed[0];
+  W.uni_w = P.src.discrete_weight;
   /* march_kernel<.., PRE>: request the next cell record one pass ahead.  Measured (B200): pays in the
    * coherent kernel, whose in-warp sums sit between request and use (clumpy 256^3 30.1 -> 26.3 ms);
    * the plain kernel is bound by L1TEX lanes, not latency (no gain; -16 % with the full layout's spills) */
   int prefetch_cfg = -1;
   if (const char *e = getenv("CMIB_PREFETCH")) prefetch_cfg = atoi(e) != 0;
-  double tune_crossings0 = 0.;
-  if (tuning) { /* buffers are allocated; wait for earlier work: time the shoot alone */
-    CUDA_OK(cudaMemcpyAsync(&tune_crossings0, ctx->acc.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-  }
-  const auto tune_t0 = std::chrono::steady_clock::now();
-  uint64_t items_bound = cap;
   bool primaries_left = true;
-  int order_now = tune_in_shoot ? ctx->tuned_order : sort_cfg;
-  if (tune_in_shoot && !ctx->tune_ev[0])
-    for (int k = 0; k < 3; ++k) CUDA_OK(cudaEventCreate(&ctx->tune_ev[k]));
-  while (round < 1000000) {
+  /* on any failure below the hot-cell replicas must not leak into the next shoot */
+  auto fail_cleanup = [&]() {
+    if (P.hot_replicas > 0 && P.hot_acc) cudaMemsetAsync(P.hot_acc, 0, ctx->hot_doubles() * sizeof(double), s);
+    if (W.hist) cudaMemsetAsync(W.hist, 0, W.nbins * sizeof(uint32_t), s); /* bin counts are zero between rounds */
+  };
+  bool done = false;
+  const uint64_t max_rounds = 100000;  /* every round emits min(remaining, room) primaries or shrinks the
+                                        * re-emission population; a sane configuration stays far below */
+  while (!done && round < max_rounds) {
     for (int k = 0; k < group; ++k, ++round) {
-      if (tune_in_shoot && round >= 1 && round <= 3) CUDA_OK(cudaEventRecord(ctx->tune_ev[round - 1], s));
-      if (sort_cfg == 2) {
-        W.sort = (order_now == 2 && (primaries_left || sort_reemitted_rounds)) ? 2 : 0;
-        if (tune_in_shoot && round == 1) W.sort = 0;
-        if (tune_in_shoot && round == 2) W.sort = 2;
-        W.sort_n = items_bound;
-      }
+      /* rounds without primaries (re-emitted packets start anywhere) run unsorted through the plain kernel */
+      if (sort_cfg == 2) W.sort = (primaries_left || sort_reemitted_rounds) ? 2 : 0;
       const int sort = W.sort;
       stamp();
       if (P.src.reemission_kind != REEMISSION_NONE && round > 0) {
@@ -535,17 +575,14 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
       else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
       stamp();
       advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
-      if (sort == 1) {
-        CUDA_OK(cudaMemsetAsync(W.hist, 0, (W.nbins + 1) * sizeof(uint32_t), s));
-        sort_histogram_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist);
-        sort_scan_kernel<<<1, 1024, 0, s>>>(W.hist, W.nbins);
-        sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.hist, W.order);
-        g_launches += 3;
-      }
       if (sort == 2) {
-        CUDA_OK(cub::DeviceRadixSort::SortPairs(ctx->sort_temp.p, sort_temp_bytes, W.key, ctx->sort_key_out.p,
-                                                ctx->sort_iota.p, W.order, (int64_t)W.sort_n, 0, W.fine_key_bits + 1, s));
-        g_launches += 2 + (W.fine_key_bits + 8) / 8; /* onesweep: histogram, scan, one pass per 8 key bits */
+        /* counting sort: prepare_kernel counted the bins and handed out tickets */
+        const unsigned ntiles = W.nbins / SORT_SCAN_TILE;
+        sort_scan_tiles_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(W.hist, W.block_sums);
+        sort_scan_sums_kernel<<<1, SORT_SCAN_BLOCK, 0, s>>>(W.block_sums, ntiles);
+        sort_scan_offsets_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(W.hist, W.block_sums, W.offs);
+        sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.rank, W.offs, W.order);
+        g_launches += 4;
       }
       stamp();
       {
@@ -585,36 +622,30 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
 #undef CMIB_LAUNCH_MARCH
       }
       stamp();
-      advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl);
+      advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl, P.acc);
       g_launches += 4;
     }
-    CUDA_OK(cudaGetLastError());
+    if (cudaGetLastError() != cudaSuccess) { fail_cleanup(); CMIB_FAIL("a kernel launch of the shoot failed"); }
     CUDA_OK(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl.p, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     CUDA_OK(cudaStreamSynchronize(s));
-    if (ctx->h_ctl[CTL_ERROR]) CMIB_FAIL("march kernel exceeded its pass limit (internal error)");
-    bool done = false;
+    if (ctx->h_ctl[CTL_ERROR]) { fail_cleanup(); CMIB_FAIL("march kernel exceeded its pass limit (internal error)"); }
     for (int k = 0; k < group; ++k)
       if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;
-    if (done) break;
-    if (tune_in_shoot && round == (uint64_t)group) { /* the stream is idle: rounds 1 and 2 are timed */
-      float ms0 = 0.f, ms2 = 0.f;
-      cudaEventElapsedTime(&ms0, ctx->tune_ev[0], ctx->tune_ev[1]);
-      cudaEventElapsedTime(&ms2, ctx->tune_ev[1], ctx->tune_ev[2]);
-      const double n0 = (double)ctx->h_ctl[CTL_STATUS + 1], n2 = (double)ctx->h_ctl[CTL_STATUS + 2];
-      if (n0 > 0. && n2 > 0.) {
-        ctx->tune_ns_per_crossing[0] = 1e6 * ms0 / n0; /* per queue entry here */
-        ctx->tune_ns_per_crossing[2] = 1e6 * ms2 / n2;
-        ctx->tuned_order = (ms2 / n2 < ms0 / n0) ? 2 : 0;
-      }
-      order_now = ctx->tuned_order;
-    }
-    if (ctx->h_ctl[CTL_REMAINING] == 0) {
-      primaries_left = false;
-      const uint64_t last = ctx->h_ctl[CTL_STATUS + ((round - 1) % CTL_STATUS_SLOTS)];
-      items_bound = last < cap ? last : cap;
-    }
+    if (ctx->h_ctl[CTL_REMAINING] == 0) primaries_left = false;
+  }
+  if (!done) {
+    fail_cleanup();
+    CMIB_FAIL("the shoot did not finish in %llu rounds: packets are still queued (a re-emission probability of 1 "
+              "in a box that cannot be left?)", (unsigned long long)max_rounds);
   }
   ctx->shoot_rounds = round;
+  {
+    /* mean walk length of this shoot, for the key layout of the next one */
+    double c0, c1, e0, e1;
+    memcpy(&c0, &ctx->h_ctl[CTL_CROSSINGS0], 8); memcpy(&c1, &ctx->h_ctl[CTL_CROSSINGS], 8);
+    memcpy(&e0, &ctx->h_ctl[CTL_EMISSIONS0], 8); memcpy(&e1, &ctx->h_ctl[CTL_EMISSIONS], 8);
+    if (P.n_packets >= (1ull << 20) && e1 > e0) ctx->walk_cells = (c1 - c0) / (e1 - e0) / 1.5;
+  }
   if (P.hot_replicas > 0) {
     const int n = P.src.n_sources * HOT_CELLS * HOT_STRIDE;
     if (mode == ACC_HONLY) fold_hot_cells_kernel<ACC_HONLY><<<blocks_for(n, 128), 128, 0, s>>>(P);
@@ -622,16 +653,6 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     ++g_launches;
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(s));
-  }
-  if (tuning) {
-    /* every group of rounds ends with a stream synchronisation: host time = device time here */
-    const double ns = std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - tune_t0).count();
-    double crossings = 0.; /* counter 5 of the accumulator buffer: cell crossings (shoot.cuh) */
-    CUDA_OK(cudaMemcpyAsync(&crossings, ctx->acc.p + 5, sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    crossings -= tune_crossings0;
-    ctx->tune_ns_per_crossing[sort_cfg] = ns / (crossings > 1. ? crossings : 1.);
-    if (sort_cfg == 2) ctx->tuned_order = (ctx->tune_ns_per_crossing[2] < ctx->tune_ns_per_crossing[0]) ? 2 : 0;
   }
   for (size_t k = 0; k + 3 < ev_used; k += 4) {
     float a = 0.f, b = 0.f;
@@ -731,8 +752,9 @@ int cmib_destroy(cmib_context *ctx) {
   cudaStreamDestroy(ctx->stream);
   if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
   for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
-  for (cudaEvent_t e : ctx->tune_ev)
+  for (cudaEvent_t e : ctx->xev)
     if (e) cudaEventDestroy(e);
+  if (ctx->comm) NcclApi::get().CommDestroy(ctx->comm);
   delete ctx;
   return 0;
 }
@@ -905,13 +927,10 @@ int cmib_set_sources(cmib_context *ctx, int32_t n, const double *positions, cons
   if (!hot_ok || ctx->geom.periodic[0] || ctx->geom.periodic[1] || ctx->geom.periodic[2]) ctx->hot_replicas = 0;
   if (ctx->hot_replicas > 0) {
     CUDA_OK(ctx->d_src_cell.upload(ctx->h_src_cell.data(), (size_t)n, ctx->stream));
-    const size_t nd = (size_t)ctx->hot_replicas * HOT_MAX_SOURCES * HOT_CELLS * HOT_STRIDE;
-    if (ctx->hot_acc.n != nd) {
-      CUDA_OK(ctx->hot_acc.resize(nd));
-      CUDA_OK(cudaMemsetAsync(ctx->hot_acc.p, 0, nd * sizeof(double), ctx->stream));
-    }
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
   }
+  /* the replicas live at the end of the accumulator buffer: (re)size it for the new source list */
+  if (ctx->acc.p && ensure_acc(ctx)) return 1;
   ctx->src.n_sources = n;
   ctx->src.src_pos = ctx->d_src_pos.p;
   ctx->src.src_cum = ctx->d_src_cum.p;
@@ -1147,7 +1166,7 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
     P.honly_cell_stride = ctx->honly_cell_stride();
     P.honly_term_stride = ctx->honly_term_stride();
     P.honly_offset = ctx->honly_offset();
-    P.hot_acc = ctx->hot_acc.p;
+    P.hot_acc = ctx->hot_acc();
     P.src_cell = ctx->d_src_cell.p;
     P.hot_replicas = ctx->hot_replicas;
     P.nu_H = ctx->nu_H;
@@ -1185,7 +1204,14 @@ int cmib_shoot(cmib_context *ctx, uint64_t n_packets, uint64_t packet_offset, ui
 
 int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   CHECK_CTX(ctx);
+  return cmib_update_state_block(ctx, loop, totweight, 0, (uint64_t)ctx->geom.ncells);
+}
+
+int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, uint64_t cell_begin, uint64_t cell_end) {
+  CHECK_CTX(ctx);
   if (ensure_acc(ctx)) return 1;
+  if (cell_end > (uint64_t)ctx->geom.ncells || cell_begin > cell_end) CMIB_FAIL("cell block outside the grid");
+  if (cell_begin == cell_end) return 0;
   UpdateParams P;
   P.geom = ctx->geom;
   P.cells = ctx->cells.p;
@@ -1204,7 +1230,9 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   P.tp = ctx->tp;
   /* TemperatureCalculator.cpp:948: strictly greater */
   P.solve_temperature = (ctx->tp.do_temperature && loop > ctx->tp.min_iterations) ? 1 : 0;
-  const int64_t nc = ctx->geom.ncells;
+  P.cell_begin = (int64_t)cell_begin;
+  P.cell_end = (int64_t)cell_end;
+  const int64_t nc = (int64_t)(cell_end - cell_begin);
   const char *simple = getenv("CMIB_UPDATE_SIMPLE");
   if (P.solve_temperature && !(simple && simple[0] == '1')) {
     /* temperature solve: persistent warps with dynamic cell hand-out (kernels.cuh) */
@@ -1215,7 +1243,8 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->update_blocks_per_sm[ACC_HONLY],
                                                             update_temperature_kernel<ACC_HONLY>, 128, 0));
     }
-    CUDA_OK(cudaMemsetAsync(ctx->upd_counter.p, 0, sizeof(unsigned long long), ctx->stream));
+    const unsigned long long first = cell_begin;
+    CUDA_OK(cudaMemcpyAsync(ctx->upd_counter.p, &first, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
     int bpm = ctx->update_blocks_per_sm[ctx->acc_mode];
     if (bpm < 1) bpm = 1;
     unsigned grid = (unsigned)(ctx->sm_count * bpm);
@@ -1288,7 +1317,289 @@ int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_do
   CHECK_CTX(ctx);
   if (ensure_acc(ctx)) return 1;
   if (device_ptr) *device_ptr = ctx->acc.p;
-  if (n_doubles) *n_doubles = ctx->acc.n;
+  if (n_doubles) *n_doubles = ctx->acc_main_doubles(ctx->acc_mode);
+  return 0;
+}
+
+/* ---- multi-GPU: MPICommunicator of the reference for this path ----------------------------- */
+
+uint64_t cmib_distribute(uint64_t number, int32_t size, int32_t rank) {
+  /* MPICommunicator::distribute (MPICommunicator.hpp:207-222) */
+  if (size <= 1) return number;
+  const uint64_t quotient = number / (uint64_t)size, remainder = number % (uint64_t)size;
+  return quotient + (((uint64_t)rank < remainder) ? 1u : 0u);
+}
+
+void cmib_distribute_block(int32_t rank, int32_t size, uint64_t begin, uint64_t end, uint64_t *block_begin,
+                           uint64_t *block_end) {
+  /* MPICommunicator::distribute_block (MPICommunicator.hpp:237-255) */
+  const uint64_t block_size = end - begin;
+  const uint64_t quotient = block_size / (uint64_t)size, remainder = block_size % (uint64_t)size;
+  const uint64_t r = (uint64_t)rank;
+  if (block_begin) *block_begin = begin + r * quotient + (r < remainder ? r : remainder);
+  if (block_end) *block_end = begin + (r + 1) * quotient + (r + 1 < remainder ? r + 1 : remainder);
+}
+
+int cmib_comm_unique_id(void *id128) {
+  if (!id128) CMIB_FAIL("null argument");
+  NcclApi &nccl = NcclApi::get();
+  if (!nccl.error.empty()) CMIB_FAIL("%s", nccl.error.c_str());
+  static_assert(sizeof(ncclUniqueId) == 128, "the C ABI hands the NCCL unique id around as 128 bytes");
+  ncclUniqueId id;
+  NCCL_OK(nccl.GetUniqueId(&id));
+  memcpy(id128, &id, sizeof(id));
+  return 0;
+}
+
+int cmib_comm_init_rank(cmib_context *ctx, int32_t size, int32_t rank, const void *id128) {
+  CHECK_CTX(ctx);
+  if (!id128 || size < 1 || rank < 0 || rank >= size) CMIB_FAIL("bad communicator arguments (rank %d of %d)", rank, size);
+  if (ctx->comm) CMIB_FAIL("the context already has a communicator");
+  NcclApi &nccl = NcclApi::get();
+  if (!nccl.error.empty()) CMIB_FAIL("%s", nccl.error.c_str());
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NCCL_OK(nccl.CommInitRank(&ctx->comm, size, id, rank));
+  ctx->comm_rank = rank;
+  ctx->comm_size = size;
+  return 0;
+}
+
+int cmib_comm_init_all(cmib_context **ctxs, int32_t size) {
+  if (!ctxs || size < 1) CMIB_FAIL("bad communicator arguments");
+  NcclApi &nccl = NcclApi::get();
+  if (!nccl.error.empty()) CMIB_FAIL("%s", nccl.error.c_str());
+  std::vector<int> devices(size);
+  for (int r = 0; r < size; ++r) {
+    if (!ctxs[r]) CMIB_FAIL("null context");
+    if (ctxs[r]->comm) CMIB_FAIL("context %d already has a communicator", r);
+    devices[r] = ctxs[r]->device;
+  }
+  std::vector<ncclComm_t> comms(size);
+  NCCL_OK(nccl.CommInitAll(comms.data(), size, devices.data()));
+  for (int r = 0; r < size; ++r) {
+    ctxs[r]->comm = comms[r];
+    ctxs[r]->comm_rank = r;
+    ctxs[r]->comm_size = size;
+  }
+  return 0;
+}
+
+int cmib_comm_finalize(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (ctx->comm) {
+    CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    NcclApi::get().CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->comm_rank = 0;
+  ctx->comm_size = 1;
+  return 0;
+}
+
+int cmib_comm_info(cmib_context *ctx, int32_t *rank, int32_t *size, uint64_t *cell_begin, uint64_t *cell_end) {
+  CHECK_CTX(ctx);
+  if (rank) *rank = ctx->comm_rank;
+  if (size) *size = ctx->comm_size;
+  cmib_distribute_block(ctx->comm_rank, ctx->comm_size, 0, (uint64_t)ctx->geom.ncells, cell_begin, cell_end);
+  return 0;
+}
+
+} /* extern "C" */
+
+namespace {
+
+/* all-gather of a per-cell array with `per_cell` elements of T per cell, blocks of distribute_block: one in-place
+ * broadcast per rank inside a group (the blocks differ by at most one cell, so ncclAllGather's equal counts do not fit) */
+template <typename T>
+int gather_blocks(cmib_context *ctx, T *array, size_t per_cell) {
+  NcclApi &nccl = NcclApi::get();
+  NCCL_OK(nccl.GroupStart());
+  for (int r = 0; r < ctx->comm_size; ++r) {
+    uint64_t lo, hi;
+    cmib_distribute_block(r, ctx->comm_size, 0, (uint64_t)ctx->geom.ncells, &lo, &hi);
+    if (hi == lo) continue;
+    T *blk = array + lo * per_cell;
+    NCCL_OK(nccl.Broadcast(blk, blk, (hi - lo) * per_cell * sizeof(T), ncclChar, r, ctx->comm, ctx->stream));
+  }
+  NCCL_OK(nccl.GroupEnd());
+  return 0;
+}
+
+/* sum over the ranks: every rank gets the sums of its own cell block (+ the 16 counters on all ranks) */
+int reduce_scatter_accumulators(cmib_context *ctx) {
+  NcclApi &nccl = NcclApi::get();
+  const uint64_t nc = (uint64_t)ctx->geom.ncells;
+  double *acc = ctx->acc.p;
+  NCCL_OK(nccl.GroupStart());
+  NCCL_OK(nccl.AllReduce(acc, acc, ACC_COUNTERS, ncclDouble, ncclSum, ctx->comm, ctx->stream));
+  for (int r = 0; r < ctx->comm_size; ++r) {
+    uint64_t lo, hi;
+    cmib_distribute_block(r, ctx->comm_size, 0, nc, &lo, &hi);
+    if (hi == lo) continue;
+    if (ctx->acc_mode == ACC_FULL) {
+      double *blk = acc + ACC_COUNTERS + lo * 16;
+      NCCL_OK(nccl.Reduce(blk, blk, (hi - lo) * 16, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
+    } else if (ctx->honly_planar()) {
+      for (int term = 0; term < 2; ++term) {
+        double *blk = acc + ACC_COUNTERS + ctx->honly_offset() + lo + (uint64_t)term * (uint64_t)ctx->honly_term_stride();
+        NCCL_OK(nccl.Reduce(blk, blk, hi - lo, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
+      }
+    } else { /* interleaved / padded records of honly_cell_stride doubles */
+      double *blk = acc + ACC_COUNTERS + lo * (uint64_t)ctx->honly_cell_stride();
+      uint64_t n = (hi - lo) * (uint64_t)ctx->honly_cell_stride();
+      if (r == ctx->comm_size - 1) n = ctx->acc_main_doubles(ACC_HONLY) - (ACC_COUNTERS + lo * (uint64_t)ctx->honly_cell_stride()); /* + the offset tail */
+      NCCL_OK(nccl.Reduce(blk, blk, n, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
+    }
+  }
+  NCCL_OK(nccl.GroupEnd());
+  return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int cmib_comm_exchange_and_update(cmib_context *ctx, uint32_t loop, int allreduce) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  if (!ctx->comm || ctx->comm_size == 1) return cmib_update_state(ctx, loop, 0.);
+  cudaStream_t s = ctx->stream;
+  if (!ctx->xev[0])
+    for (int k = 0; k < 4; ++k) CUDA_OK(cudaEventCreate(&ctx->xev[k]));
+  CUDA_OK(cudaEventRecord(ctx->xev[0], s));
+  if (allreduce) {
+    NCCL_OK(NcclApi::get().AllReduce(ctx->acc.p, ctx->acc.p, ctx->acc_main_doubles(ctx->acc_mode), ncclDouble, ncclSum, ctx->comm, s));
+  } else if (reduce_scatter_accumulators(ctx)) {
+    return 1;
+  }
+  CUDA_OK(cudaEventRecord(ctx->xev[1], s));
+  uint64_t lo, hi;
+  cmib_distribute_block(ctx->comm_rank, ctx->comm_size, 0, (uint64_t)ctx->geom.ncells, &lo, &hi);
+  if (cmib_update_state_block(ctx, loop, 0., lo, hi)) return 1; /* totweight: the reduced counter on the device */
+  CUDA_OK(cudaEventRecord(ctx->xev[2], s));
+  if (gather_blocks(ctx, ctx->cells.p, 1)) return 1;
+  /* the compact (n, x_H) copy of the other ranks' blocks: rebuilt from the gathered records (HBM is ~10x NVLink) */
+  const int64_t nc = ctx->geom.ncells;
+  if (lo > 0) rebuild_cells_h_kernel<<<blocks_for((int64_t)lo, 256), 256, 0, s>>>(0, (int64_t)lo, ctx->cells.p, ctx->cells_h.p);
+  if ((int64_t)hi < nc) rebuild_cells_h_kernel<<<blocks_for(nc - (int64_t)hi, 256), 256, 0, s>>>((int64_t)hi, nc, ctx->cells.p, ctx->cells_h.p);
+  g_launches += 2;
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaEventRecord(ctx->xev[3], s));
+  ctx->reemit_prob_valid = false;
+  return 0;
+}
+
+int cmib_comm_exchange_timing(cmib_context *ctx, double ms[3]) {
+  CHECK_CTX(ctx);
+  if (!ms) CMIB_FAIL("null argument");
+  ms[0] = ms[1] = ms[2] = 0.;
+  if (!ctx->xev[0]) return 0;
+  CUDA_OK(cudaEventSynchronize(ctx->xev[3]));
+  for (int k = 0; k < 3; ++k) {
+    float f = 0.f;
+    CUDA_OK(cudaEventElapsedTime(&f, ctx->xev[k], ctx->xev[k + 1]));
+    ms[k] = f;
+  }
+  return 0;
+}
+
+int cmib_comm_gather_state(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (!ctx->comm || ctx->comm_size == 1) return 0;
+  if (gather_blocks(ctx, ctx->xmetal.p, 12)) return 1;
+  if (gather_blocks(ctx, ctx->heat_norm.p, 2)) return 1;
+  return 0;
+}
+
+int cmib_comm_gather_cells_all(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (!ctx->comm || ctx->comm_size == 1) return 0;
+  if (gather_blocks(ctx, ctx->cells.p, 1)) return 1;
+  if (gather_blocks(ctx, ctx->cells_h.p, 1)) return 1;
+  if (gather_blocks(ctx, ctx->xmetal.p, 12)) return 1;
+  ctx->reemit_prob_valid = false;
+  return 0;
+}
+
+int cmib_upload_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cell_end, const double *n, const double *T,
+                            const double *x) {
+  CHECK_CTX(ctx);
+  if (!n || !T || !x) CMIB_FAIL("null cell array");
+  if (cell_end > (uint64_t)ctx->geom.ncells || cell_begin > cell_end) CMIB_FAIL("cell block outside the grid");
+  const size_t nb = (size_t)(cell_end - cell_begin);
+  if (nb == 0) return 0;
+  if (ctx->stage.n < nb * 18) CUDA_OK(ctx->stage.resize(nb * 18));
+  double *s = ctx->stage.p;
+  CUDA_OK(cudaMemcpyAsync(s, n, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + nb, T, nb * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + 2 * nb, x, nb * 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  pack_cells_kernel<<<blocks_for(nb, 256), 256, 0, ctx->stream>>>((int64_t)nb, s, s + nb, s + 2 * nb, ctx->cells.p + cell_begin,
+                                                                  ctx->cells_h.p + cell_begin, ctx->xmetal.p + cell_begin * 12);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  ctx->reemit_prob_valid = false;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream)); /* host arrays may be reused on return */
+  return 0;
+}
+
+int cmib_download_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cell_end, double *n, double *T, double *x,
+                              double *heat) {
+  CHECK_CTX(ctx);
+  if (cell_end > (uint64_t)ctx->geom.ncells || cell_begin > cell_end) CMIB_FAIL("cell block outside the grid");
+  const size_t nb = (size_t)(cell_end - cell_begin);
+  if (nb == 0) return 0;
+  if (ctx->stage.n < nb * 18) CUDA_OK(ctx->stage.resize(nb * 18));
+  double *s = ctx->stage.p;
+  unpack_cells_kernel<<<blocks_for(nb, 256), 256, 0, ctx->stream>>>((int64_t)nb, ctx->cells.p + cell_begin,
+                                                                    ctx->xmetal.p + cell_begin * 12,
+                                                                    ctx->heat_norm.p + cell_begin * 2, s, s + nb, s + 2 * nb,
+                                                                    s + 16 * nb);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  if (n) CUDA_OK(cudaMemcpyAsync(n, s, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (T) CUDA_OK(cudaMemcpyAsync(T, s + nb, nb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (x) CUDA_OK(cudaMemcpyAsync(x, s + 2 * nb, nb * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (heat) CUDA_OK(cudaMemcpyAsync(heat, s + 16 * nb, nb * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+/* ---- measured ceilings of the part ------------------------------------------------------------ */
+int cmib_measure_scatter_rates(cmib_context *ctx, uint64_t n_cells, double *red_per_s, double *gather_per_s) {
+  CHECK_CTX(ctx);
+  if (n_cells == 0) CMIB_FAIL("empty table");
+  DevBuf<double> table;
+  DevBuf<double> out;
+  CUDA_OK(table.resize((size_t)n_cells * 2)); /* 16-byte records, as the H-only walk gathers them */
+  CUDA_OK(out.resize(1));
+  cudaStream_t s = ctx->stream;
+  CUDA_OK(cudaMemsetAsync(table.p, 0, (size_t)n_cells * 16, s));
+  const int bs = 256, grid = ctx->sm_count * 8, iters = 64;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  double best[2] = {1e30, 1e30};
+  for (int rep = 0; rep < 4; ++rep) { /* the first repetition is the warm-up */
+    for (int which = 0; which < 2; ++which) {
+      CUDA_OK(cudaEventRecord(e0, s));
+      if (which == 0) measure_scatter_red_kernel<<<grid, bs, 0, s>>>(table.p, n_cells, iters);
+      else measure_scatter_gather_kernel<<<grid, bs, 0, s>>>(reinterpret_cast<const double2 *>(table.p), n_cells, iters, out.p);
+      CUDA_OK(cudaEventRecord(e1, s));
+      CUDA_OK(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+      if (rep > 0 && ms < best[which]) best[which] = ms;
+    }
+  }
+  g_launches += 8;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  table.resize(0);
+  out.resize(0);
+  const double ops = (double)bs * grid * iters;
+  if (red_per_s) *red_per_s = ops / (best[0] * 1e-3);
+  if (gather_per_s) *gather_per_s = ops / (best[1] * 1e-3);
   return 0;
 }
 

@@ -164,13 +164,14 @@ struct UpdateParams {
   RecombinationModel rr;
   TemperatureParams tp;
   int solve_temperature;
+  int64_t cell_begin, cell_end; /* the cell block this launch updates (MPICommunicator::distribute_block) */
 };
 
 template <int MODE>
 __global__ void __launch_bounds__(128)
 update_state_kernel(const __grid_constant__ UpdateParams P) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.geom.ncells) return;
+  const int64_t i = P.cell_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.cell_end) return;
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   /* jfac = L / W, hfac = jfac * h, both divided by the cell volume per cell
    * (IonizationStateCalculator.cpp:519-521, .hpp:135-139) */
@@ -246,7 +247,7 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
   const int role = lane % 3;            /* 0: 1.1 T0, 1: 0.9 T0, 2: T0 */
   const int slot_base = lane - role;    /* first lane of this cell's three */
   const unsigned role0_mask = 0x09249249u; /* lanes 0, 3, ..., 27 */
-  const int64_t ncells = P.geom.ncells;
+  const int64_t ncells = P.cell_end; /* next_cell starts at P.cell_begin */
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   const double jfac = (P.luminosity / totweight) / P.geom.cell_volume;
   const double hfac = ((P.luminosity / totweight) * PLANCK) / P.geom.cell_volume;
@@ -388,6 +389,37 @@ __global__ void unpack_cells_kernel(int64_t ncell, const CellOpacity *cells, con
   for (int k = 0; k < 12; ++k) x[(2 + k) * ncell + i] = xmetal[i * 12 + k];
   heat[i] = heat_norm[2 * i];
   heat[ncell + i] = heat_norm[2 * i + 1];
+}
+
+/* compact (n, x_H) copy of the opacity records of cells [lo, hi): rebuilt locally after a gather of the records */
+__global__ void rebuild_cells_h_kernel(int64_t lo, int64_t hi, const CellOpacity *cells, double2 *cells_h) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const CellOpacity c = cells[i];
+  cells_h[i] = make_double2(c.n, c.xH);
+}
+
+/* cmib_measure_scatter_rates: one FP64 RED / one 16-byte gather per lane and iteration, every lane in a different line */
+CMIB_D uint32_t mb_hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+CMIB_D uint64_t mb_cell(uint32_t tid, uint32_t it, uint64_t ncell) {
+  const uint32_t a = mb_hash32(tid * 0x9E3779B9u + it), b = mb_hash32(a ^ 0x85ebca6bu);
+  return (((uint64_t)a << 32) | b) % ncell;
+}
+__global__ void measure_scatter_red_kernel(double *table, uint64_t ncell, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  for (int it = 0; it < iters; ++it) atomicAdd(table + mb_cell(tid, it, ncell) * 2, 1.0);
+}
+__global__ void measure_scatter_gather_kernel(const double2 *table, uint64_t ncell, int iters, double *out) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.;
+  for (int it = 0; it < iters; ++it) {
+    const double2 a = __ldg(table + mb_cell(tid, it, ncell));
+    s += a.x + a.y;
+  }
+  if (s == 12345.678) out[0] = s;
 }
 
 /* accumulators -> reference SoA view J[14][ncell], heat[2][ncell] */

@@ -75,7 +75,11 @@ inline size_t lean_smem_bytes(const GridGeom &g) {
 }
 
 /*
- * HEAT     the packets may carry nu != nu_H (heat term v1 = dJ_H * (nu - nu_H))
+ * HEAT     the packets may carry nu != nu_H (heat term v1 = dJ_H * (nu - nu_H)).  false = the host established
+ *          that every packet of the shoot is a primary of a discrete source at exactly nu_H (monochromatic
+ *          spectrum at the threshold, no re-emission, no continuous source): then sigma_H and the weight are the
+ *          same for all packets and come from the launch parameters (W.uni_sigH, W.uni_w) instead of two shared
+ *          loads per crossing
  * PERIODIC some axis is periodic
  * PRE      request the record of the next cell at the end of a crossing
  * STEPS    shuffle steps of the in-warp sum: runs of up to 2^STEPS lanes are summed (<= 3)
@@ -97,13 +101,18 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
   const uint32_t pt = opaque_u32(smem0 + threadIdx.x * 8u);
   const uint32_t wall0 = opaque_u32(smem0 + (uint32_t)LEAN_PT_BYTES);
   {
-    /* get_cell (CartesianDensityGrid.cpp:170-176): lo = anchor + cellside * i, hi = lo + cellside */
+    /* get_cell (CartesianDensityGrid.cpp:170-176): lo = anchor + cellside * i, hi = lo + cellside.  Entry k of an
+     * axis holds (hi[k], lo[n - 1 - k]): a packet that moves up reads hi of its index i at entry i, one that
+     * moves down reads lo at entry n - 1 - i, so that BOTH step to the next entry per crossing of the axis and
+     * leave the grid at entry n */
     double2 *wt = s_dyn + LEAN_PT_BYTES / 16;
     for (uint32_t i = threadIdx.x; i < ncx + ncy + ncz; i += MARCH_BLOCK) {
       const int a = (i < ncx) ? 0 : (i < ncx + ncy ? 1 : 2);
       const uint32_t k = i - (a == 0 ? 0u : (a == 1 ? ncx : ncx + ncy));
-      const double lo = xadd(g.anchor[a], xmul(g.cellside[a], (double)k));
-      wt[i] = make_double2(lo, xadd(lo, g.cellside[a]));
+      const uint32_t n = (a == 0) ? ncx : (a == 1 ? ncy : ncz);
+      const double lo_up = xadd(g.anchor[a], xmul(g.cellside[a], (double)k));
+      const double lo_dn = xadd(g.anchor[a], xmul(g.cellside[a], (double)(n - 1u - k)));
+      wt[i] = make_double2(xadd(lo_up, g.cellside[a]), lo_dn);
     }
     unsigned long long *f = reinterpret_cast<unsigned long long *>(s_dyn);
 #pragma unroll
@@ -115,15 +124,16 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
   /* packet state */
   double px = 0., py = 0., pz = 0., dx = 1., dy = 1., dz = 1., ivx = 1., ivy = 1., ivz = 1.;
   double tau = 0.;
-  /* per axis: the shared address of the wall the packet moves towards, wall0 + 16 * (axis offset + i) + 8 * (d >= 0),
-   * and the step of the cell index per crossing of that axis (+-1); the cell index itself is only implicit */
+  /* per axis: the shared address of the wall the packet moves towards (entry i, or entry n - 1 - i plus 8 bytes,
+   * see above) and the step of the cell index per crossing of that axis (+-1, 0 never); the cell indices
+   * themselves are only implicit */
   uint32_t ax = 0, ay = 0, az = 0;
   int32_t sx = 1, sy = 1, sz = 1;
   uint32_t cell = 0;
-  /* table addresses of index 0 and table sizes in bytes, per axis (uniform) */
-  const uint32_t ux = wall0, uy = wall0 + 16u * ncx, uz = wall0 + 16u * (ncx + ncy);
-  const uint32_t ncx16 = W.lean_n16[0], ncy16 = W.lean_n16[1], ncz16 = W.lean_n16[2]; /* 16 * ncell */
-  const int32_t kx = W.lean_k[0], ky = W.lean_k[1];                                  /* ncy * ncz, ncz */
+  /* table addresses of entry 0 and of entry n (= outside), per axis (uniform) */
+  const uint32_t ux = wall0, uy = wall0 + W.lean_n16[0], uz = uy + W.lean_n16[1];
+  const uint32_t ex = uy, ey = uz, ez = uz + W.lean_n16[2];
+  const int32_t kx = W.lean_k[0], ky = W.lean_k[1]; /* ncy * ncz, ncz */
   uint32_t hot = 0; /* (source + 1) << 2 | crossings made; 0 = the neighbourhood rule no longer applies */
   uint32_t n_steps = 0, n_red = 0;
   int state = LANE_EMPTY;
@@ -131,7 +141,6 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
   uint64_t cur = 0, end = 0;
   bool exhausted = (qcount == 0);
   uint32_t n_pass = 0;
-  const bool group_lane0 = ((lane & ((1 << STEPS) - 1)) == 0);
   const uint32_t cell_stride = (uint32_t)P.honly_cell_stride;
 
   while (true) {
@@ -179,7 +188,7 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
         fpy = xadd(py, xdiv(xmul(xsub(nwy, py), dss), ds));
         fpz = xadd(pz, xdiv(xmul(xsub(nwz, pz), dss), ds));
         /* accumulate the shortened crossing; the cell has n > 0 (tau_cell > 0) */
-        const double dJH = (dss * lds_f64<PT_W * PT_STRIDE>(pt)) * lds_f64<PT_SIGH * PT_STRIDE>(pt);
+        const double dJH = HEAT ? (dss * lds_f64<PT_W * PT_STRIDE>(pt)) * lds_f64<PT_SIGH * PT_STRIDE>(pt) : (dss * W.uni_w) * W.uni_sigH;
         if (dJH != 0.) {
           atomicAdd(acc_term<ACC_HONLY>(P, cell, 0), dJH);
           ++n_red;
@@ -211,7 +220,7 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
           if (state == LANE_ABSORBED) {
             double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
             q[RQ_PX * cap] = fpx; q[RQ_PY * cap] = fpy; q[RQ_PZ * cap] = fpz;
-            q[RQ_SIGH * cap] = lds_f64<PT_SIGH * PT_STRIDE>(pt);
+            q[RQ_SIGH * cap] = HEAT ? lds_f64<PT_SIGH * PT_STRIDE>(pt) : W.uni_sigH;
             q[RQ_SIGHE * cap] = 0.;
             q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
             q[RQ_ID * cap] = __longlong_as_double((long long)lds_u64<PT_ID * PT_STRIDE>(pt));
@@ -254,9 +263,11 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
               const int isrc = meta_source(meta);
               if (isrc >= 0) hot = (uint32_t)(isrc + 1) << 2;
             }
-            sts_f64<PT_SIGH * PT_STRIDE>(pt, q[MQ_SIGMA * cap]);
-            sts_f64<PT_W * PT_STRIDE>(pt, meta_continuous(meta) ? P.src.continuous_weight : P.src.discrete_weight);
-            if (HEAT) sts_f64<PT_DNU * PT_STRIDE>(pt, nu - P.nu_H);
+            if (HEAT) {
+              sts_f64<PT_SIGH * PT_STRIDE>(pt, q[MQ_SIGMA * cap]);
+              sts_f64<PT_W * PT_STRIDE>(pt, meta_continuous(meta) ? P.src.continuous_weight : P.src.discrete_weight);
+              sts_f64<PT_DNU * PT_STRIDE>(pt, nu - P.nu_H);
+            }
             /* a zero direction component: the reference's wall distance is DBL_MAX (:289-309).  Here the
              * packet "moves towards" the upper wall with 1/d = +inf: (hi - p) * inf = +inf, which is never
              * the minimum and never equal to it — the same selection, without a test per crossing
@@ -282,9 +293,9 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
             } else if ((uint32_t)ix >= ncx || (uint32_t)iy >= ncy || (uint32_t)iz >= ncz) {
               state = LANE_ESCAPED; /* emitted outside the box: interact() returns end() */
             }
-            ax = ux + 16u * (uint32_t)ix + (upx ? 8u : 0u);
-            ay = uy + 16u * (uint32_t)iy + (upy ? 8u : 0u);
-            az = uz + 16u * (uint32_t)iz + (upz ? 8u : 0u);
+            ax = ux + (upx ? 16u * (uint32_t)ix : 16u * (ncx - 1u - (uint32_t)ix) + 8u);
+            ay = uy + (upy ? 16u * (uint32_t)iy : 16u * (ncy - 1u - (uint32_t)iy) + 8u);
+            az = uz + (upz ? 16u * (uint32_t)iz : 16u * (ncz - 1u - (uint32_t)iz) + 8u);
             if (state == LANE_LIVE) {
               cell = ((uint32_t)ix * ncy + (uint32_t)iy) * ncz + (uint32_t)iz;
               if (PRE) {
@@ -302,8 +313,8 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
 #pragma unroll
     for (int u = 0; u < CMIB_LEAN_UNROLL; ++u) {
       /* ---- one cell crossing for every live lane ---- */
-      uint32_t akey = 0xffffffffu; /* accumulator record this lane adds to: the cell, 2^31 | hot replica record,
-                                    * or all ones = nothing to add */
+      uint32_t akey = 0xffffffffu; /* accumulator record this lane adds to, as its index in doubles from W.acc_j (a
+                                    * cell's J_H, or a hot replica record behind the cells); all ones = nothing to add */
       double v0 = 0., v1 = 0.;
       if (state == LANE_LIVE) {
         double n, xH;
@@ -317,7 +328,7 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
         const double wx = xmul(xsub(lds_f64<0>(ax), px), ivx);
         const double wy = xmul(xsub(lds_f64<0>(ay), py), ivy);
         const double wz = xmul(xsub(lds_f64<0>(az), pz), ivz);
-        const double sigH = lds_f64<PT_SIGH * PT_STRIDE>(pt);
+        const double sigH = HEAT ? lds_f64<PT_SIGH * PT_STRIDE>(pt) : W.uni_sigH;
         const double myz = (wz < wy) ? wz : wy;
         const double ds = (myz < wx) ? myz : wx;
         /* ds * n * (sigma_H * x_H) (DensityGrid.hpp:129-133; the helium term of the H-only layout is
@@ -332,45 +343,54 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
         } else {
           if (n > 0.) {
             /* update_integrals (DensityGrid.hpp:150-197) */
-            akey = cell;
+            akey = cell * cell_stride;
             if (hot != 0u) {
               /* first crossings of a primary, inside the 3x3x3 cells around its source: a replica */
               const uint32_t hc = P.src_cell[(hot >> 2) - 1u];
-              const int ddx = (int)((ax - ux) >> 4) - (int)(hc & 1023u), ddy = (int)((ay - uy) >> 4) - (int)((hc >> 10) & 1023u),
-                        ddz = (int)((az - uz) >> 4) - (int)((hc >> 20) & 1023u);
+              const int jx = (int)((ax - ux) >> 4), jy = (int)((ay - uy) >> 4), jz = (int)((az - uz) >> 4);
+              const int ddx = (sx > 0 ? jx : (int)ncx - 1 - jx) - (int)(hc & 1023u),
+                        ddy = (sy > 0 ? jy : (int)ncy - 1 - jy) - (int)((hc >> 10) & 1023u),
+                        ddz = (sz > 0 ? jz : (int)ncz - 1 - jz) - (int)((hc >> 20) & 1023u);
               if ((unsigned)(ddx + 1) < 3u && (unsigned)(ddy + 1) < 3u && (unsigned)(ddz + 1) < 3u)
-                akey = 0x80000000u | ((s_hot_base + ((hot >> 2) - 1u)) * HOT_CELLS +
-                                      (uint32_t)((ddx + 1) * 9 + (ddy + 1) * 3 + (ddz + 1)));
+                akey = W.hot_index0 + (uint32_t)HOT_STRIDE * ((s_hot_base + ((hot >> 2) - 1u)) * HOT_CELLS +
+                                                              (uint32_t)((ddx + 1) * 9 + (ddy + 1) * 3 + (ddz + 1)));
               ++hot;
               if ((hot & 3u) == (uint32_t)HOT_CROSSINGS) hot = 0u;
             }
-            v0 = (ds * lds_f64<PT_W * PT_STRIDE>(pt)) * sigH;
+            v0 = (ds * (HEAT ? lds_f64<PT_W * PT_STRIDE>(pt) : W.uni_w)) * sigH;
             if (HEAT) v1 = v0 * lds_f64<PT_DNU * PT_STRIDE>(pt);
           }
           /* move to the wall, step the indices of every axis whose wall was hit */
           px = xadd(px, xmul(ds, dx));
           py = xadd(py, xmul(ds, dy));
           pz = xadd(pz, xmul(ds, dz));
-          /* if (w == ds) { a += 16 * s; cell += k * s; } as one compare and two predicated multiply-adds */
-          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
+          /* if (w == ds) { a += 16; cell += k * s; } as one compare and two predicated integer operations */
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p add.u32 %0, %0, 16;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
               : "+r"(ax), "+r"(cell) : "d"(wx), "d"(ds), "r"(sx), "r"(kx));
-          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p add.u32 %0, %0, 16;\n\t@p mad.lo.s32 %1, %4, %5, %1;\n\t}"
               : "+r"(ay), "+r"(cell) : "d"(wy), "d"(ds), "r"(sy), "r"(ky));
-          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p mad.lo.s32 %0, %4, 16, %0;\n\t@p add.s32 %1, %1, %4;\n\t}"
+          asm("{\n\t.reg .pred p;\n\tsetp.eq.f64 p, %2, %3;\n\t@p add.u32 %0, %0, 16;\n\t@p add.s32 %1, %1, %4;\n\t}"
               : "+r"(az), "+r"(cell) : "d"(wz), "d"(ds), "r"(sz));
           if (PERIODIC) {
-            MarchState ms;
-            ms.px = px; ms.py = py; ms.pz = pz;
-            ms.ix = (int32_t)(ax - ux) >> 4; ms.iy = (int32_t)(ay - uy) >> 4; ms.iz = (int32_t)(az - uz) >> 4;
-            const int32_t jx = ms.ix, jy = ms.iy, jz = ms.iz;
-            const bool in = march_inside(g, ms);
-            px = ms.px; py = ms.py; pz = ms.pz;
-            ax += 16u * (uint32_t)(ms.ix - jx); ay += 16u * (uint32_t)(ms.iy - jy); az += 16u * (uint32_t)(ms.iz - jz);
-            cell = ((uint32_t)ms.ix * ncy + (uint32_t)ms.iy) * ncz + (uint32_t)ms.iz;
-            if (!in) state = LANE_ESCAPED;
-          } else if ((ax - ux) >= ncx16 || (ay - uy) >= ncy16 || (az - uz) >= ncz16) {
-            /* the address offsets are 16 * i + 8 * (d >= 0): an index of -1 wraps to a huge unsigned value */
-            state = LANE_ESCAPED;
+            /* is_inside (:187-227): an index that left a periodic axis re-enters on the other side, the position
+             * moves by the box side; rare (once per box crossing), so the indices are recovered from the addresses */
+            if (ax >= ex || ay >= ey || az >= ez) {
+              MarchState ms;
+              ms.px = px; ms.py = py; ms.pz = pz;
+              const int32_t jx = (int32_t)((ax - ux) >> 4), jy = (int32_t)((ay - uy) >> 4), jz = (int32_t)((az - uz) >> 4);
+              ms.ix = (sx > 0) ? jx : (int32_t)ncx - 1 - jx;
+              ms.iy = (sy > 0) ? jy : (int32_t)ncy - 1 - jy;
+              ms.iz = (sz > 0) ? jz : (int32_t)ncz - 1 - jz;
+              const bool in = march_inside(g, ms);
+              px = ms.px; py = ms.py; pz = ms.pz;
+              ax = ux + ((sx > 0) ? 16u * (uint32_t)ms.ix : 16u * (ncx - 1u - (uint32_t)ms.ix) + 8u);
+              ay = uy + ((sy > 0) ? 16u * (uint32_t)ms.iy : 16u * (ncy - 1u - (uint32_t)ms.iy) + 8u);
+              az = uz + ((sz > 0) ? 16u * (uint32_t)ms.iz : 16u * (ncz - 1u - (uint32_t)ms.iz) + 8u);
+              cell = ((uint32_t)ms.ix * ncy + (uint32_t)ms.iy) * ncz + (uint32_t)ms.iz;
+              if (!in) state = LANE_ESCAPED;
+            }
+          } else if (ax >= ex || ay >= ey || az >= ez) {
+            state = LANE_ESCAPED; /* entry n of an axis: the index left the grid */
           }
           if (state == LANE_LIVE) {
             /* tau == 0 exactly: the walk ends inside (loop condition tau > 0, :391), on the wall */
@@ -384,32 +404,46 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
       }
       /* runs of neighbouring lanes with the same record (neighbours inside a group are neighbours
        * in key order): segmented sum towards the first lane of every run */
-      const uint32_t prev = __shfl_up_sync(0xffffffffu, akey, 1);
-      const bool head = group_lane0 || akey != prev;
+      bool head;
+      {
+        /* head = first lane of its group of 2^STEPS lanes, or a record different from the lane below: the shuffle's
+         * own predicate says whether the lane below belongs to the same group (c = segment mask | clamp) */
+        uint32_t prev;
+        int in_group;
+        asm volatile("{\n\t.reg .pred p;\n\tshfl.sync.up.b32 %0|p, %2, 1, %3, 0xffffffff;\n\tselp.s32 %1, 1, 0, p;\n\t}"
+                     : "=r"(prev), "=r"(in_group) : "r"(akey), "n"((32 - (1 << STEPS)) << 8));
+        head = !in_group || akey != prev;
+      }
       const unsigned heads = __ballot_sync(0xffffffffu, head);
       if (heads != 0xffffffffu) {
-        /* bit d-1 of hs: lane + d starts a run (lane 32 counts as one) */
+        /* last lane of my run = lane before the next head above me (lane 32 counts as a head); a shuffle from
+         * beyond it is refused by the clamp operand and its predicate gates the add */
         const unsigned hs = ((heads >> 1) | 0x80000000u) >> lane;
+        const uint32_t run_last = (uint32_t)lane + (uint32_t)(__ffs(hs) - 1);
 #pragma unroll
         for (int d = 1; d < (1 << STEPS); d <<= 1) {
-          /* if no run starts among the next d lanes: v += v of lane + d */
-          const double t0 = __shfl_down_sync(0xffffffffu, v0, d);
-          asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v0) : "d"(t0), "r"(hs & ((1u << d) - 1u)));
+          asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+                       "mov.b64 {lo, hi}, %0;\n\t"
+                       "shfl.sync.down.b32 tl|p, lo, %1, %2, 0xffffffff;\n\t"
+                       "shfl.sync.down.b32 th, hi, %1, %2, 0xffffffff;\n\t"
+                       "mov.b64 t, {tl, th};\n\t"
+                       "@p add.rn.f64 %0, %0, t;\n\t}"
+                       : "+d"(v0) : "r"(d), "r"(run_last));
           if (HEAT) {
-            const double t1 = __shfl_down_sync(0xffffffffu, v1, d);
-            asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(v1) : "d"(t1), "r"(hs & ((1u << d) - 1u)));
+            asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, tl, th;\n\t.reg .f64 t;\n\t"
+                         "mov.b64 {lo, hi}, %0;\n\t"
+                         "shfl.sync.down.b32 tl|p, lo, %1, %2, 0xffffffff;\n\t"
+                         "shfl.sync.down.b32 th, hi, %1, %2, 0xffffffff;\n\t"
+                         "mov.b64 t, {tl, th};\n\t"
+                         "@p add.rn.f64 %0, %0, t;\n\t}"
+                         : "+d"(v1) : "r"(d), "r"(run_last));
           }
         }
       }
       if (head && akey != 0xffffffffu) {
-        /* the record: the cell's, or a hot-cell replica (2^31 | record, HOT_STRIDE doubles each) */
-        const bool is_hot = (akey & 0x80000000u) != 0u;
-        const double *base = is_hot ? P.hot_acc : W.acc_j;
-        const uint32_t idx = is_hot ? (akey << 4) : akey * cell_stride;
-        static_assert(HOT_STRIDE == 16, "hot record index -> doubles is a shift by 4");
-        double *a = const_cast<double *>(base) + idx;
+        double *a = W.acc_j + akey;
         if (v0 != 0.) { atomicAdd(a, v0); ++n_red; }
-        if (HEAT && v1 != 0.) { atomicAdd(a + (is_hot ? (int64_t)1 : P.honly_term_stride), v1); ++n_red; }
+        if (HEAT && v1 != 0.) { atomicAdd(a + ((akey >= W.hot_index0) ? (int64_t)1 : P.honly_term_stride), v1); ++n_red; }
       }
     }
   }

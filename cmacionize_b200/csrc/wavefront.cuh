@@ -51,7 +51,10 @@ enum CtlWord : int {
   CTL_EQCOUNT,      /* entries in the emission queue (re-emissions that survived the decision) */
   CTL_STATUS = 8,   /* ring of CTL_STATUS_SLOTS words: march-queue size after each prepare */
   CTL_STATUS_SLOTS = 64,
-  CTL_WORDS = CTL_STATUS + CTL_STATUS_SLOTS
+  /* walk statistics of this shoot (bit patterns of doubles): the counters of the accumulator buffer when the shoot
+   * began and after the last march, so that the host learns the mean walk length with the read-back it does anyway */
+  CTL_CROSSINGS0 = CTL_STATUS + CTL_STATUS_SLOTS, CTL_EMISSIONS0, CTL_CROSSINGS, CTL_EMISSIONS,
+  CTL_WORDS
 };
 
 /* march-queue fields (8-byte each) */
@@ -70,80 +73,41 @@ struct WavefrontParams {
   double *rq;              /* re-emission queue: [RQ_NFIELDS][capacity] */
   double *eq;              /* emission queue: [EQ_NFIELDS][capacity] */
   uint64_t capacity;
-  /* optional coherence sort of the march queue (grids that do not fit in L2) */
-  int sort;                /* 0: march reads the queue in emission order */
-  uint32_t *key;           /* [capacity] sort key of each queue entry */
+  /* coherent march (sort == 2): the march queue is read in the order of a key (source | direction of a primary,
+   * start position of a re-emitted packet); counting sort: prepare_kernel takes a ticket in its key's bin,
+   * sort_scan_* turn the bin counts into offsets, sort_scatter_kernel writes the order */
+  int sort;                /* 0: march reads the queue in emission order, 2: in key order */
+  uint32_t *key;           /* [capacity] key of each queue entry */
+  uint32_t *rank;          /* [capacity] ticket of each queue entry inside its bin */
   uint32_t *order;         /* [capacity] queue entries in key order */
-  uint32_t *hist;          /* [nbins + 1] */
-  uint32_t nbins;
-  int isrc_bits_shift;     /* key = isrc << shift | direction bin (primaries) */
-  /* sort == 2: coherent march (fine 32-bit keys, radix sort on the host side of the launch,
-   * march_kernel<MODE, true> adds same-cell contributions inside the warp first) */
-  uint64_t sort_n;         /* entries the sort covers (>= items of this round); slots beyond the items get the largest key */
+  uint32_t *hist;          /* [nbins] entries per bin (zero between rounds) */
+  uint32_t *offs;          /* [nbins] first position of each bin in the order */
+  uint32_t *block_sums;    /* [nbins / SORT_SCAN_TILE] */
+  uint32_t nbins;          /* 2^(fine_key_bits + 1), a multiple of SORT_SCAN_TILE */
   int fine_dir_bits;       /* direction bits of a primary's key (even, <= 22) */
-  int fine_key_bits;       /* source + direction bits; bit fine_key_bits flags a re-emitted packet */
+  int fine_key_bits;       /* source + direction + optical-depth bits; bit fine_key_bits flags a re-emitted packet */
+  int tau_bits;            /* low bits of a key: bin of the sampled optical depth (uniform in exp(-tau)) */
   uint32_t chunk_stride;   /* chunk c of the ordered queue is claimed as (c * chunk_stride) % nchunks */
   int agg;                 /* 1: march_kernel<MODE, true> (in-warp sums), 0: the plain kernel on the ordered queue */
   uint32_t lean_n16[3];    /* march_lean_kernel: 16 * ncell per axis */
   int32_t lean_k[2];       /* ... and the cell-index strides ncy * ncz, ncz */
+  double uni_sigH, uni_w;  /* march_lean_kernel<HEAT = false>: sigma_H and weight of every packet of the shoot */
+  uint32_t hot_index0;     /* first hot-cell replica record, in doubles from acc_j (the replicas follow the accumulators
+                            * in the same allocation) */
   double *acc_j;           /* H-only layout: accumulator J_H of cell 0 (sp.acc + ACC_COUNTERS + sp.honly_offset) */
 };
 
 /*
- * Coherence key.  Packets that start at the same source and leave in nearly the same direction
- * walk through the same cells: queue entries are ordered by (source, direction bin on a
- * 64 x 64 octahedral map in Morton order) so that the packets in flight at any time — the
- * warps claim consecutive chunks of the ordered queue — cover a narrow cone of the grid that
- * fits in L2, instead of the whole HBM-resident grid.  Re-emitted packets start anywhere; they are
- * ordered by a 16^3 Morton bin of their start position.  Ordering changes which packets run
- * together, not what any packet does: results are identical up to the order of the atomic adds.
+ * Keys of the coherent march (sort == 2).  Packets that start at the same source and leave in nearly the
+ * same direction walk through the same cells: queue entries are ordered by key so that the packets in flight
+ * at any time — the warps claim consecutive chunks of the ordered queue — cover a narrow cone of the grid that
+ * stays in L2, and the 8 lanes of a refill group cross the same cells in lock-step.  Keys are
+ * fine_key_bits + 1 bits wide (<= 23: the bin tables stay L2 resident): primaries  0 | source | direction on a
+ * 2048 x 2048 octahedral map in Morton order (truncated to fine_dir_bits); re-emitted packets  1 | 1024^3
+ * Morton bin of the start position (truncated).  With 1.6e7 packets of one source in the queue a bin holds ~4
+ * packets that leave within ~0.002 rad of each other.  Ordering changes which packets run together, not what
+ * any packet does: results are identical up to the order of the atomic adds.
  */
-constexpr int SORT_DIR_BITS = 12;  /* 64 x 64 direction bins */
-constexpr int SORT_POS_BINS = 4096; /* 16^3 position bins */
-
-CMIB_D uint32_t morton2_6(uint32_t x, uint32_t y) {
-  uint32_t r = 0;
-#pragma unroll
-  for (int b = 0; b < 6; ++b) r |= ((x >> b) & 1u) << (2 * b) | ((y >> b) & 1u) << (2 * b + 1);
-  return r;
-}
-CMIB_D uint32_t morton3_4(uint32_t x, uint32_t y, uint32_t z) {
-  uint32_t r = 0;
-#pragma unroll
-  for (int b = 0; b < 4; ++b)
-    r |= ((x >> b) & 1u) << (3 * b) | ((y >> b) & 1u) << (3 * b + 1) | ((z >> b) & 1u) << (3 * b + 2);
-  return r;
-}
-CMIB_D uint32_t direction_bin(double dx, double dy, double dz) {
-  const float ax = fabsf((float)dx), ay = fabsf((float)dy), az = fabsf((float)dz);
-  const float inv = 1.f / fmaxf(ax + ay + az, 1e-30f);
-  float u = (float)dx * inv, v = (float)dy * inv;
-  if (dz < 0.) {
-    const float uu = (1.f - fabsf(v)) * (u >= 0.f ? 1.f : -1.f);
-    const float vv = (1.f - fabsf(u)) * (v >= 0.f ? 1.f : -1.f);
-    u = uu; v = vv;
-  }
-  const int iu = min(63, max(0, (int)((u * 0.5f + 0.5f) * 64.f)));
-  const int iv = min(63, max(0, (int)((v * 0.5f + 0.5f) * 64.f)));
-  return morton2_6((uint32_t)iu, (uint32_t)iv);
-}
-CMIB_D uint32_t position_bin(const GridGeom &g, double px, double py, double pz) {
-  const int ix = min(15, max(0, (int)((px - g.anchor[0]) / g.sides[0] * 16.)));
-  const int iy = min(15, max(0, (int)((py - g.anchor[1]) / g.sides[1] * 16.)));
-  const int iz = min(15, max(0, (int)((pz - g.anchor[2]) / g.sides[2] * 16.)));
-  return morton3_4((uint32_t)ix, (uint32_t)iy, (uint32_t)iz);
-}
-
-/*
- * Fine keys of the coherent march (sort == 2), fine_key_bits + 1 bits wide so that the radix sort
- * needs 3 passes for up to 8 sources: primaries  0 | source | direction on a 2048 x 2048 octahedral
- * map in Morton order (truncated to fine_dir_bits); re-emitted packets  1 | 1024^3 Morton bin of
- * the start position (truncated); unused slots all ones (they tie with the last position bin at
- * most, and the stable sort keeps them behind it: they have the largest slot numbers).  With 1.6e7 packets of one
- * source in the queue, 32 neighbours in key order leave within ~0.003 rad of each other: they
- * cross the same cells in lock-step for tens of cells.
- */
-constexpr uint32_t SORT_KEY_UNUSED = 0xffffffffu;
 CMIB_D uint32_t spread2(uint32_t x) { /* 16 bits -> even bit positions */
   x &= 0xffffu;
   x = (x | (x << 8)) & 0x00ff00ffu;
@@ -179,43 +143,94 @@ CMIB_D uint32_t fine_position_key(const GridGeom &g, double px, double py, doubl
   const int iz = min(1023, max(0, (int)((pz - g.anchor[2]) / g.sides[2] * 1024.)));
   return spread3((uint32_t)ix) | (spread3((uint32_t)iy) << 1) | (spread3((uint32_t)iz) << 2);
 }
-__global__ void iota_kernel(uint32_t *v, uint64_t n) {
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    v[i] = (uint32_t)i;
-}
+/* bin counts -> bin offsets: exclusive prefix sum over nbins = ntiles * SORT_SCAN_TILE entries in three small
+ * launches (tile sums, scan of the <= 2048 tile sums, tile-local scan + tile offset).  The last one also clears
+ * the counts for the next round. */
+constexpr int SORT_SCAN_BLOCK = 256;
+constexpr int SORT_SCAN_ITEMS = 16;
+constexpr int SORT_SCAN_TILE = SORT_SCAN_BLOCK * SORT_SCAN_ITEMS; /* 4096 bins per CTA */
+constexpr int SORT_MAX_TILES = SORT_SCAN_BLOCK * 32;              /* what sort_scan_sums_kernel scans in one CTA */
+constexpr int SORT_MAX_KEY_BITS = 23;                             /* + 1 flag bit: 2^24 bins, 64 MB: L2 resident (measured with
+                                                                   * 2^25: the tickets of prepare_kernel thrash, +30 % prepare) */
+static_assert((2ll << SORT_MAX_KEY_BITS) <= (long long)SORT_SCAN_TILE * SORT_MAX_TILES, "bin table larger than the scan");
 
-/* counting sort of the march queue by key: histogram -> exclusive scan -> scatter */
-__global__ void sort_histogram_kernel(const unsigned long long *ctl, const uint32_t *key, uint32_t *hist) {
-  const uint64_t n = ctl[CTL_QCOUNT];
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    atomicAdd(&hist[key[i]], 1u);
-}
-/* one block: hist[b] <- number of entries with a smaller key */
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *hist, uint32_t nbins) {
-  __shared__ uint32_t part[1024];
-  const uint32_t per = (nbins + 1023u) / 1024u;
-  const uint32_t lo = threadIdx.x * per, hi = min(nbins, lo + per);
-  uint32_t sum = 0;
-  for (uint32_t b = lo; b < hi; ++b) sum += hist[b];
-  part[threadIdx.x] = sum;
+CMIB_D uint32_t block_exclusive_scan(uint32_t v, uint32_t *total) {
+  __shared__ uint32_t warp_sums[SORT_SCAN_BLOCK / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    const uint32_t v = (threadIdx.x >= (unsigned)o) ? part[threadIdx.x - o] : 0u;
-    __syncthreads();
-    part[threadIdx.x] += v;
-    __syncthreads();
+  if (warp == 0) {
+    uint32_t s = (lane < SORT_SCAN_BLOCK / 32) ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < SORT_SCAN_BLOCK / 32; o <<= 1) {
+      const uint32_t n = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += n;
+    }
+    if (lane < SORT_SCAN_BLOCK / 32) warp_sums[lane] = s; /* inclusive */
   }
-  uint32_t run = part[threadIdx.x] - sum; /* exclusive */
-  for (uint32_t b = lo; b < hi; ++b) {
-    const uint32_t c = hist[b];
-    hist[b] = run;
-    run += c;
+  __syncthreads();
+  if (total) *total = warp_sums[SORT_SCAN_BLOCK / 32 - 1];
+  return incl - v + (warp > 0 ? warp_sums[warp - 1] : 0u);
+}
+__global__ void __launch_bounds__(SORT_SCAN_BLOCK) sort_scan_tiles_kernel(const uint32_t *hist, uint32_t *block_sums) {
+  const uint4 *h = reinterpret_cast<const uint4 *>(hist + (size_t)blockIdx.x * SORT_SCAN_TILE) + threadIdx.x * (SORT_SCAN_ITEMS / 4);
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SORT_SCAN_ITEMS / 4; ++k) { const uint4 v = h[k]; s += v.x + v.y + v.z + v.w; }
+  uint32_t total;
+  (void)block_exclusive_scan(s, &total);
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+/* one CTA: exclusive scan of the tile sums in place (ntiles <= SORT_MAX_TILES) */
+__global__ void __launch_bounds__(SORT_SCAN_BLOCK) sort_scan_sums_kernel(uint32_t *block_sums, uint32_t ntiles) {
+  constexpr int PER = SORT_MAX_TILES / SORT_SCAN_BLOCK;
+  uint32_t v[PER], s = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const uint32_t i = threadIdx.x * PER + k;
+    v[k] = (i < ntiles) ? block_sums[i] : 0u;
+    s += v[k];
+  }
+  uint32_t run = block_exclusive_scan(s, nullptr);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const uint32_t i = threadIdx.x * PER + k;
+    if (i < ntiles) block_sums[i] = run;
+    run += v[k];
   }
 }
-__global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_t *key, uint32_t *hist, uint32_t *order) {
+__global__ void __launch_bounds__(SORT_SCAN_BLOCK)
+sort_scan_offsets_kernel(uint32_t *hist, const uint32_t *block_sums, uint32_t *offs) {
+  uint4 *h = reinterpret_cast<uint4 *>(hist + (size_t)blockIdx.x * SORT_SCAN_TILE) + threadIdx.x * (SORT_SCAN_ITEMS / 4);
+  uint4 *o = reinterpret_cast<uint4 *>(offs + (size_t)blockIdx.x * SORT_SCAN_TILE) + threadIdx.x * (SORT_SCAN_ITEMS / 4);
+  uint4 v[SORT_SCAN_ITEMS / 4];
+  uint32_t s = 0;
+#pragma unroll
+  for (int k = 0; k < SORT_SCAN_ITEMS / 4; ++k) { v[k] = h[k]; s += v[k].x + v[k].y + v[k].z + v[k].w; }
+  uint32_t run = block_sums[blockIdx.x] + block_exclusive_scan(s, nullptr);
+#pragma unroll
+  for (int k = 0; k < SORT_SCAN_ITEMS / 4; ++k) {
+    uint4 r;
+    r.x = run; run += v[k].x;
+    r.y = run; run += v[k].y;
+    r.z = run; run += v[k].z;
+    r.w = run; run += v[k].w;
+    o[k] = r;
+    h[k] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+/* queue entry i goes to position offs[key] + its ticket */
+__global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_t *key, const uint32_t *rank,
+                                    const uint32_t *offs, uint32_t *order) {
   const uint64_t n = ctl[CTL_QCOUNT];
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    order[atomicAdd(&hist[key[i]], 1u)] = (uint32_t)i;
+    order[offs[key[i]] + rank[i]] = (uint32_t)i;
 }
 
 /* meta word of a queue entry: uniforms consumed (32 bits) | packet type (7 bits) | emitted by the
@@ -400,7 +415,8 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     double sigma[NSIG];
     ++cnt.n_emit;
     packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
-    const double tau = -log(rng_uniform(rng));
+    const double u_tau = rng_uniform(rng);
+    const double tau = -log(u_tau);
     double *q = W.mq + w;
     q[MQ_PX * cap] = px; q[MQ_PY * cap] = py; q[MQ_PZ * cap] = pz;
     q[MQ_DX * cap] = dx; q[MQ_DY * cap] = dy; q[MQ_DZ * cap] = dz;
@@ -411,20 +427,18 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
     if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
     if (W.sort == 2) {
-      W.key[w] = (isrc_key >= 0)
-                     ? (((uint32_t)isrc_key << W.fine_dir_bits) | (fine_direction_key(dx, dy, dz) >> (22 - W.fine_dir_bits)))
-                     : ((1u << W.fine_key_bits) | (fine_position_key(P.geom, px, py, pz) >> (30 - W.fine_key_bits)));
-    } else if (W.sort) {
-      const uint32_t nprim = (uint32_t)m.n_sources << W.isrc_bits_shift;
-      uint32_t k;
-      if (isrc_key >= 0) k = ((uint32_t)isrc_key << W.isrc_bits_shift) | (direction_bin(dx, dy, dz) >> (SORT_DIR_BITS - W.isrc_bits_shift));
-      else k = nprim + position_bin(P.geom, px, py, pz);
+      /* [re-emitted] [source | direction, or position] [optical-depth bin]: neighbours in key order leave in nearly
+       * the same direction AND carry nearly the same optical depth, i.e. they are absorbed near the same place: the
+       * 8 lanes of a refill group finish together instead of waiting for the deepest of 8 random depths */
+      const int kb = W.fine_key_bits - W.tau_bits;
+      uint32_t k = (isrc_key >= 0)
+                       ? (((uint32_t)isrc_key << W.fine_dir_bits) | (fine_direction_key(dx, dy, dz) >> (22 - W.fine_dir_bits)))
+                       : ((1u << kb) | (fine_position_key(P.geom, px, py, pz) >> (30 - kb)));
+      k = (k << W.tau_bits) | (uint32_t)min((int)(u_tau * (double)(1 << W.tau_bits)), (1 << W.tau_bits) - 1);
       W.key[w] = k;
+      W.rank[w] = atomicAdd(&W.hist[k], 1u); /* a ticket inside the bin: counting sort without a second pass */
     }
   }
-  if (W.sort == 2) /* slots of the sorted range that hold no packet this round go last */
-    for (uint64_t w = n_items + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W.sort_n; w += stride)
-      W.key[w] = SORT_KEY_UNUSED;
   reduce_counters(P.acc, cnt);
 }
 
@@ -445,7 +459,15 @@ __global__ void advance_after_prepare_kernel(unsigned long long *ctl, uint64_t c
   ctl[CTL_ROUND] = round + 1;
 }
 
-__global__ void advance_after_march_kernel(unsigned long long *ctl) { ctl[CTL_QCOUNT] = 0; }
+__global__ void advance_after_march_kernel(unsigned long long *ctl, const double *acc) {
+  ctl[CTL_QCOUNT] = 0;
+  ctl[CTL_CROSSINGS] = (unsigned long long)__double_as_longlong(acc[5]);
+  ctl[CTL_EMISSIONS] = (unsigned long long)__double_as_longlong(acc[6]);
+}
+__global__ void shoot_begin_kernel(unsigned long long *ctl, const double *acc) {
+  ctl[CTL_CROSSINGS0] = ctl[CTL_CROSSINGS] = (unsigned long long)__double_as_longlong(acc[5]);
+  ctl[CTL_EMISSIONS0] = ctl[CTL_EMISSIONS] = (unsigned long long)__double_as_longlong(acc[6]);
+}
 
 /* fold the hot-cell replicas into the accumulators and clear them (one thread per
  * (source, neighbour cell, term); the replicas of one record are summed in a fixed order) */

@@ -212,6 +212,7 @@ class IonizationSimulation:
     def fields(self, device_index=0):
         """(number density, temperature, ionic fractions [14][ncell], heating [2][ncell])"""
         ctx = C.c_void_p()
+        _check(lib.cmih_simulation_gather_state(self._h))   # no-op on one device
         _check(lib.cmih_simulation_context_of(self._h, C.c_int(device_index), C.byref(ctx)))
         n = np.empty(self.ncells); T = np.empty(self.ncells)
         x = np.empty((capi.NUM_IONS, self.ncells)); heat = np.empty((capi.NUM_HEAT, self.ncells))

@@ -21,7 +21,8 @@
 #include <vector>
 #include <dlfcn.h>
 #include <sys/utsname.h>
-#include <nccl.h> /* types only: the library is bound at run time, see NcclApi */
+#include <condition_variable>
+#include <mutex>
 #include "../../include/cmib.h"
 #include "Error.hpp"
 #include "HDF5Reader.hpp"

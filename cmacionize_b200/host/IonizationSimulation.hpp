@@ -43,30 +43,34 @@
 
 namespace cmi {
 
-/* ---- NCCL, bound at run time ----
- * Only multi-GPU runs need NCCL, and a process may already carry one (PyTorch bundles its own
- * libnccl.so.2): dlopen picks up whatever is loaded, else the system library; nothing is linked. */
-struct NcclApi {
-  decltype(&ncclCommInitAll) CommInitAll = nullptr;
-  decltype(&ncclAllReduce) AllReduce = nullptr;
-  decltype(&ncclCommDestroy) CommDestroy = nullptr;
-  static NcclApi &get() {
-    static NcclApi api = load();
-    return api;
+/* threads of a multi-GPU iteration meet here before they enter a collective: if any of them failed (a shoot
+ * error, an out-of-memory in a queue resize), ALL skip the collective — a rank that entered an NCCL call alone
+ * would wait for the missing one forever and the run would hang instead of printing the error */
+class Rendezvous {
+public:
+  explicit Rendezvous(int n) : n_(n) {}
+  void reset() { failed_ = false; }
+  /* returns true when every thread arrived with ok == true */
+  bool arrive(bool ok) {
+    std::unique_lock<std::mutex> lock(m_);
+    if (!ok) failed_ = true;
+    const uint64_t generation = generation_;
+    if (++count_ == n_) {
+      count_ = 0;
+      ++generation_;
+      cv_.notify_all();
+    } else {
+      cv_.wait(lock, [&] { return generation_ != generation; });
+    }
+    return !failed_;
   }
 
 private:
-  static NcclApi load() {
-    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) cmi_error("Multi-GPU runs need NCCL: %s", dlerror());
-    NcclApi a;
-    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
-    a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(h, "ncclAllReduce"));
-    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
-    if (!a.CommInitAll || !a.AllReduce || !a.CommDestroy) cmi_error("libnccl lacks the expected entry points!");
-    return a;
-  }
+  std::mutex m_;
+  std::condition_variable cv_;
+  int n_, count_ = 0;
+  uint64_t generation_ = 0;
+  bool failed_ = false;
 };
 
 /* ---- the driver ---- */
@@ -74,11 +78,11 @@ class IonizationSimulation {
 public:
   /* same leading arguments as the reference (IonizationSimulation.hpp:196-202); num_thread is
    * accepted and ignored (the parallelism is the GPU's); the MPICommunicator* is replaced by the
-   * list of devices of this node.  With more than one device the packets of an iteration are
-   * split by global packet id, every device holds the whole grid, and ONE ncclAllReduce over the
-   * accumulator buffers replaces the reference's 16 chunked MPI_Allreduce + counter reductions
-   * (IonizationSimulation.cpp:410-416, 458-529); the state update is then run on every device
-   * (replicated), so no gather is needed (:540-618). */
+   * list of devices of this node.  With more than one device the iteration follows the reference's MPI
+   * decomposition (IonizationSimulation.cpp:392-397, 458-618) with the collectives of include/cmib.h
+   * (cmib_comm_*: NCCL on each context's stream): packets split by global id (MPICommunicator::distribute),
+   * every device holds the whole grid, the accumulators are summed onto the owners of the cell blocks
+   * (distribute_block), every device updates its block, and the opacity records are gathered back. */
   /* task_based = true: the parameter surface of the reference's other driver (`CMacIonize --task-based`,
    * TaskBasedIonizationSimulation.cpp:190-370) on the same GPU path: Monte Carlo parameters come from the
    * `TaskBasedIonizationSimulation:` block (number of iterations 10, number of photons 1e6, random seed,
@@ -252,9 +256,10 @@ public:
       CMIB_CALL(cmib_set_temperature_params(ctx, &tp));
     }
     if (devices_.size() > 1) {
-      comms_.resize(devices_.size());
-      if (NcclApi::get().CommInitAll(comms_.data(), (int)devices_.size(), devices_.data()) != ncclSuccess)
-        cmi_error("ncclCommInitAll failed for %zu devices!", devices_.size());
+      std::vector<cmib_context *> ctxs;
+      for (auto &grid : density_grids_) ctxs.push_back(grid->context());
+      CMIB_CALL(cmib_comm_init_all(ctxs.data(), (int32_t)ctxs.size()));
+      rendezvous_.reset(new Rendezvous((int)ctxs.size()));
     }
 
     output_folder_ = parameter_file_.get_value<std::string>(block_ + "output folder", ".");
@@ -277,7 +282,8 @@ public:
                              std::vector<int>{device}, log, task_based) {}
 
   ~IonizationSimulation() {
-    for (ncclComm_t c : comms_) NcclApi::get().CommDestroy(c);
+    for (auto &grid : density_grids_)
+      if (grid && grid->context()) cmib_comm_finalize(grid->context());
   }
 
   /* IonizationSimulation::initialize (IonizationSimulation.cpp:239-326) */
@@ -313,31 +319,33 @@ public:
     const size_t ndev = density_grids_.size();
     std::vector<IterationResult> part(ndev);
     std::vector<std::string> errors(ndev);
+    if (rendezvous_) rendezvous_->reset();
     auto work = [&](size_t d) {
+      cmib_context *ctx = density_grids_[d]->context();
+      IterationResult &r = part[d];
+      bool ok = true;
+      auto t0 = clock::now(), t1 = t0;
       try {
-        cmib_context *ctx = density_grids_[d]->context();
-        /* MPICommunicator::distribute (MPICommunicator.hpp:207-222): contiguous id blocks */
-        const uint64_t per = numphoton / ndev;
-        const uint64_t lo = d * per;
-        const uint64_t cnt = (d + 1 < ndev) ? per : numphoton - lo;
-        IterationResult &r = part[d];
+        /* MPICommunicator::distribute_block (MPICommunicator.hpp:237-255): contiguous id blocks */
+        uint64_t lo, hi;
+        cmib_distribute_block((int32_t)d, (int32_t)ndev, 0, numphoton, &lo, &hi);
         density_grids_[d]->reset_grid();
         CMIB_CALL(cmib_update_reemission_probabilities(ctx));
         CMIB_CALL(cmib_synchronize(ctx));
-        const auto t0 = clock::now();
-        CMIB_CALL(cmib_shoot(ctx, cnt, lo, (uint64_t)(int64_t)random_seed_, loop, &r.totweight, r.typecount));
-        const auto t1 = clock::now();
-        double totweight = r.totweight;
-        if (ndev > 1) {
-          void *buf = nullptr, *stream = nullptr;
-          uint64_t n = 0;
-          CMIB_CALL(cmib_accumulator_buffer(ctx, &buf, &n));
-          CMIB_CALL(cmib_stream(ctx, &stream));
-          if (NcclApi::get().AllReduce(buf, buf, n, ncclDouble, ncclSum, comms_[d], (cudaStream_t)stream) != ncclSuccess)
-            cmi_error("ncclAllReduce failed on device %d!", devices_[d]);
-          totweight = 0.; /* use the reduced device-side sum */
-        }
-        CMIB_CALL(cmib_update_state(ctx, loop, totweight));
+        t0 = clock::now();
+        CMIB_CALL(cmib_shoot(ctx, hi - lo, lo, (uint64_t)(int64_t)random_seed_, loop, &r.totweight, r.typecount));
+        t1 = clock::now();
+      } catch (const std::exception &e) {
+        errors[d] = e.what();
+        ok = false;
+      }
+      /* nobody enters the collective unless everybody got here without an error */
+      if (rendezvous_ && !rendezvous_->arrive(ok)) return;
+      if (!ok) return;
+      try {
+        /* reduce the accumulators onto the block owners, update the own block, gather the opacity records;
+         * totweight is the reduced device-side sum */
+        CMIB_CALL(cmib_comm_exchange_and_update(ctx, loop, 0));
         CMIB_CALL(cmib_synchronize(ctx));
         const auto t2 = clock::now();
         r.shoot_seconds = std::chrono::duration<double>(t1 - t0).count();
@@ -368,6 +376,26 @@ public:
   /* IonizationSimulation::run */
   /* external_writer: IonizationSimulation::run(DensityGridWriter*) (IonizationSimulation.cpp:334, 655-659):
    * called once with the final grid (host mirror refreshed) */
+  /* the host mirror of device 0 is about to be refreshed: collect the per-cell state that stays with the block
+   * owners between iterations (metal fractions, heating terms); collective over the devices */
+  void gather_state() {
+    if (density_grids_.size() < 2) return;
+    std::vector<std::string> errors(density_grids_.size());
+    std::vector<std::thread> threads;
+    for (size_t d = 0; d < density_grids_.size(); ++d)
+      threads.emplace_back([&, d] {
+        try {
+          CMIB_CALL(cmib_comm_gather_state(density_grids_[d]->context()));
+          CMIB_CALL(cmib_synchronize(density_grids_[d]->context()));
+        } catch (const std::exception &e) {
+          errors[d] = e.what();
+        }
+      });
+    for (auto &t : threads) t.join();
+    for (const std::string &e : errors)
+      if (!e.empty()) throw Error(e);
+  }
+
   void run(const std::function<void(CartesianDensityGrid &)> &external_writer = nullptr) {
     CartesianDensityGrid &grid = *density_grids_[0];
     if (density_grid_writer_) { grid.download(); density_grid_writer_->write(grid, 0, parameter_file_); }
@@ -391,8 +419,9 @@ public:
         log_->write_info("Escape fraction from diffuse helium: ", 100. * r.typecount[2] / W, "%.");
       }
       if (every_iteration_output_ && density_grid_writer_ && loop + 1 < number_of_iterations_)
-      { grid.download(); density_grid_writer_->write(grid, loop + 1, parameter_file_); }
+      { gather_state(); grid.download(); density_grid_writer_->write(grid, loop + 1, parameter_file_); }
     }
+    gather_state();
     if (density_grid_writer_) { grid.download(); density_grid_writer_->write(grid, number_of_iterations_, parameter_file_); }
     if (external_writer) {
       grid.download();
@@ -428,7 +457,7 @@ private:
   std::unique_ptr<RecombinationRates> recombination_rates_;
   std::unique_ptr<DensityFunction> density_function_;
   std::vector<std::unique_ptr<CartesianDensityGrid>> density_grids_;
-  std::vector<ncclComm_t> comms_;
+  std::unique_ptr<Rendezvous> rendezvous_;
   std::unique_ptr<PhotonSourceDistribution> photon_source_distribution_;
   std::unique_ptr<PhotonSourceSpectrum> photon_source_spectrum_;
   std::unique_ptr<PhotonSourceSpectrum> continuous_photon_source_spectrum_;

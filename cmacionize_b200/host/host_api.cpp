@@ -101,6 +101,9 @@ int cmih_simulation_context(void *h, cmib_context **ctx) {
 int cmih_simulation_context_of(void *h, int device_index, cmib_context **ctx) {
   CMIH_TRY(*ctx = static_cast<Sim *>(h)->sim.get_density_grid((size_t)device_index).context());
 }
+/* multi-GPU: bring the per-cell state that stays with the cell-block owners (metal fractions, heating terms) to
+ * every device, before the cells of any device are downloaded */
+int cmih_simulation_gather_state(void *h) { CMIH_TRY(static_cast<Sim *>(h)->sim.gather_state()); }
 
 /* ---- parameter-file probes (parity tests against the reference's ParameterFile) ---- */
 int cmih_paramfile_open(const char *filename, void **out) { CMIH_TRY(*out = new ParameterFile(filename)); }

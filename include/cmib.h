@@ -228,6 +228,60 @@ int cmib_accumulator_buffer(cmib_context *ctx, void **device_ptr, uint64_t *n_do
 /* raw cudaStream_t of the context (for ordering an external collective) */
 int cmib_stream(cmib_context *ctx, void **stream);
 
+/* ---- multi-GPU: the reference's MPICommunicator for this path ----------- */
+/* The reference splits an iteration over MPI ranks (src/IonizationSimulation.cpp:392-397, 458-618): every rank
+ * shoots distribute(numphoton) packets on a replicated grid, 16 chunked MPI_Allreduce calls sum the per-cell
+ * accumulators, every rank updates the cell block distribute_block gives it, and 15 hand-rolled all-gathers
+ * rebuild the replicas.  Here one context = one GPU = one rank; the collectives are NCCL calls on the context's
+ * stream (libnccl.so.2 is bound at run time: single-GPU users need no NCCL).
+ *
+ * cmib_distribute / cmib_distribute_block: MPICommunicator::distribute (MPICommunicator.hpp:207-222) and
+ * ::distribute_block (:237-255), pure functions (no context, no GPU). */
+uint64_t cmib_distribute(uint64_t number, int32_t size, int32_t rank);
+void cmib_distribute_block(int32_t rank, int32_t size, uint64_t begin, uint64_t end, uint64_t *block_begin,
+                           uint64_t *block_end);
+/* One communicator over `size` contexts.  Several processes (one rank each, e.g. under torchrun or mpirun):
+ * rank 0 calls cmib_comm_unique_id and hands the 128 bytes to the others by any means, then every rank calls
+ * cmib_comm_init_rank (collective: it blocks until all ranks have called it).  One process driving several
+ * GPUs from one host thread each: cmib_comm_init_all on the array of contexts. */
+int cmib_comm_unique_id(void *id128);
+int cmib_comm_init_rank(cmib_context *ctx, int32_t size, int32_t rank, const void *id128);
+int cmib_comm_init_all(cmib_context **ctxs, int32_t size);
+int cmib_comm_finalize(cmib_context *ctx);
+/* rank, size and the cell block [begin, end) this context updates (size 1, the whole grid without a communicator) */
+int cmib_comm_info(cmib_context *ctx, int32_t *rank, int32_t *size, uint64_t *cell_begin, uint64_t *cell_end);
+/* The exchange between cmib_shoot and the next iteration, as ONE call per rank (collective):
+ *   1. the accumulators are summed over the ranks — every rank receives the sums of ITS cell block and the 16
+ *      leading counters (a reduce-scatter: what the block update needs; `allreduce` != 0 gives every rank all
+ *      sums, for callers that read the accumulators back);
+ *   2. cmib_update_state on the rank's block (totweight from the reduced counters);
+ *   3. the opacity records (n, x_H, x_He, T) of all blocks are gathered on every rank: all a shoot reads.
+ * The remaining per-cell state (metal fractions, heating terms) stays distributed — block ownership never
+ * changes — until cmib_comm_gather_state is called (before a rank downloads cells it does not own).
+ * Without a communicator the call is cmib_update_state on the whole grid. */
+int cmib_comm_exchange_and_update(cmib_context *ctx, uint32_t loop, int allreduce);
+int cmib_comm_gather_state(cmib_context *ctx);
+/* milliseconds (CUDA events on the context's stream) of the three phases of the last exchange: reduce, update, gather */
+int cmib_comm_exchange_timing(cmib_context *ctx, double ms[3]);
+/* cmib_update_state restricted to the cells [cell_begin, cell_end) */
+int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, uint64_t cell_begin, uint64_t cell_end);
+/* upload / download of a cell block from / to host arrays that hold ONLY that block (same field layout as
+ * cmib_upload_cells / cmib_download_cells with ncell = cell_end - cell_begin): the distributed form of the
+ * end-to-end path — every rank moves 1/size of the bytes, cmib_comm_gather_cells_all replicates what was uploaded */
+int cmib_upload_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cell_end, const double *number_density,
+                            const double *temperature, const double *ionic_fractions);
+int cmib_download_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cell_end, double *number_density,
+                              double *temperature, double *ionic_fractions, double *heating);
+/* all-gather of everything cmib_upload_cells_block wrote (opacity records + metal fractions) */
+int cmib_comm_gather_cells_all(cmib_context *ctx);
+
+/* ---- measured ceilings of the part (roofline denominators) --------------- */
+/* Scattered FP64 RED/s and scattered 16-byte gathers/s of THIS device on tables of `n_cells` records
+ * (tools/microbench/red_bench.cu as a library call): every lane of a warp touches a different 128-byte line.
+ * These are the L1TEX-lane ceilings the walk of an L2-resident grid runs against; bench.py measures them in
+ * the run that reports them. */
+int cmib_measure_scatter_rates(cmib_context *ctx, uint64_t n_cells, double *red_per_s, double *gather_per_s);
+
 /* ---- test hooks (parity against the oracle on identical inputs) -------- */
 /* CartesianDensityGrid::interact on explicit packets (src/CartesianDensityGrid.cpp:375-452).
  * pos/dir [np][3], sigma [np][14], sigma_He_corr/nu/weight/tau [np].  Accumulates

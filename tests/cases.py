@@ -22,10 +22,18 @@ MARCH_GRIDS = {
                         dens=1e13, vac=False, corner=False),
 }
 
+# the full grid size of BASELINE.json configs[4] (tests/test_gpu_parity256.py only: 16.8 M cells); packets start
+# anywhere; mean optical depth per cell ~0.01, so the sampled depths (x 0.01, 1, 100) give early absorptions,
+# walks of a few hundred cells and escapes
+BIG_MARCH_GRIDS = {
+    "clumpy256": dict(anchor=[-5 * PC] * 3, sides=[10 * PC] * 3, ncell=[256, 256, 256], periodic=[0, 0, 0],
+                      dens=1e-2, vac=False, corner=False),
+}
+
 
 def march_case(name: str, npackets: int, seed: int = 7):
     """Random cells + explicit packets for CartesianDensityGrid::interact parity."""
-    g = MARCH_GRIDS[name]
+    g = MARCH_GRIDS.get(name) or BIG_MARCH_GRIDS[name]
     rng = np.random.default_rng(seed)
     anchor = np.array(g["anchor"], float)
     sides = np.array(g["sides"], float)

@@ -16,7 +16,9 @@ def _check(line, n_gpus):
     d = json.loads(line)
     assert KEYS <= set(d) and d["impl"] == "reference" and d["n_gpus"] == n_gpus
     assert d["unit"] == "packets/s" and d["higher_is_better"] is True and d["vs_baseline"] is None and d["dtype"] == "f64"
-    assert d["config"]["workload"] == "lexingtonHII20" and d["config"]["packets_per_iteration"] == n_gpus * 100_000_000
+    # strong scaling, as in the reference: the iteration keeps the parameter file's 1e8 packets for every rank count
+    assert d["config"]["workload"] == "lexingtonHII20" and d["config"]["packets_per_iteration"] == 100_000_000
+    assert d["scaling"] == "strong"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["value"] == d["value"] and cb["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": "packets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

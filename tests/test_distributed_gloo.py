@@ -1,8 +1,10 @@
 """CPU tier: the N>1 path on 2 ranks over gloo.  Each rank shoots its shard of the global packet
 ids (host logic check `hc_shoot` of tests/hostcheck standing in for the kernel: same shoot_packet
-code, same Philox streams), the accumulator buffers are combined with the ONE all-reduce the
-multi-GPU path uses, and the result must equal the single-rank run: identical counters, sums equal
-up to summation order."""
+code, same Philox streams); the exchange then follows the product's protocol (include/cmib.h
+cmib_comm_exchange_and_update, there on NCCL): the 16 counters are all-reduced, every cell block of
+cmib_distribute_block is reduced onto its owner, the owner updates its block, the blocks are
+broadcast back.  The result must equal the single-rank run: identical counters, sums equal up to
+summation order, and every rank ends with the same updated grid."""
 import ctypes as C
 import os
 import socket
@@ -42,20 +44,61 @@ def _shoot(lib_path, lo, cnt):
     return acc
 
 
+def _update(J, heat):
+    """stand-in for the per-cell state update: any deterministic function of the cell's sums"""
+    return 1. / (1. + 1e-10 * J) + 1e-30 * heat
+
+
 def _worker(rank, world, port, lib_path, out):
     import torch
     import torch.distributed as dist
-    from cmacionize_b200.distributed import allreduce_sum, shard_packets
+    from cmacionize_b200.distributed import cell_block, shard_packets
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, cnt = shard_packets(NPK, rank, world)
     acc = torch.from_numpy(_shoot(lib_path, lo, cnt))
-    allreduce_sum(acc)
+    ncells = NC ** 3
+    # 1. counters on every rank, each cell block (interleaved J, heat records) on its owner
+    dist.all_reduce(acc[:16], op=dist.ReduceOp.SUM)
+    cells = acc[16:].view(ncells, 2)
+    for r in range(world):
+        b0, b1 = cell_block(ncells, r, world)
+        dist.reduce(cells[b0:b1], dst=r, op=dist.ReduceOp.SUM)
+    # 2. the owner updates its block; 3. blocks go back to everybody
+    state = torch.full((ncells,), -1., dtype=torch.float64)
+    b0, b1 = cell_block(ncells, rank, world)
+    state[b0:b1] = torch.from_numpy(_update(cells[b0:b1, 0].numpy(), cells[b0:b1, 1].numpy()))
+    for r in range(world):
+        c0, c1 = cell_block(ncells, r, world)
+        dist.broadcast(state[c0:c1], src=r)
+    gathered = [torch.empty_like(cells) for _ in range(world)] if rank == 0 else None
+    mine = torch.zeros_like(cells)
+    mine[b0:b1] = cells[b0:b1]
+    dist.gather(mine, gathered, dst=0)
+    states = [torch.empty_like(state) for _ in range(world)] if rank == 0 else None
+    dist.gather(state, states, dst=0)
     if rank == 0:
-        np.save(out, acc.numpy())
+        np.save(out, np.concatenate([acc[:16].numpy(), sum(g.numpy() for g in gathered).reshape(-1)]))
+        np.save(out + ".state.npy", np.stack([t.numpy() for t in states]))
     dist.barrier()
     dist.destroy_process_group()
+
+
+def test_distribute_matches_the_reference_formulas(cmib):
+    """cmib_distribute / cmib_distribute_block = MPICommunicator::distribute / ::distribute_block
+    (MPICommunicator.hpp:207-255): quotient (+1 for the first `remainder` ranks); blocks tile the range."""
+    from cmacionize_b200 import capi
+    for number in (0, 1, 7, 8, 9, 262144, 10**8, 16777216 + 5):
+        for size in (1, 2, 3, 4, 8, 16):
+            parts = [capi.distribute(number, size, r) for r in range(size)]
+            q, rem = divmod(number, size)
+            assert parts == [q + (1 if r < rem else 0) for r in range(size)] and sum(parts) == number
+            blocks = [capi.distribute_block(r, size, 0, number) for r in range(size)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == number
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(size - 1))
+            assert [b - a for a, b in blocks] == parts
+    assert capi.distribute_block(1, 3, 100, 110) == (104, 107)
 
 
 def test_two_rank_shoot_equals_single_rank(hostcheck, cmib, tmp_path):
@@ -71,6 +114,10 @@ def test_two_rank_shoot_equals_single_rank(hostcheck, cmib, tmp_path):
     out = str(tmp_path / "acc.npy")
     mp.spawn(_worker, args=(2, _free_port(), lib_path, out), nprocs=2, join=True)
     both = np.load(out)
+    states = np.load(out + ".state.npy")
+    assert np.array_equal(states[0], states[1]) and (states[0] > 0.).all()   # every rank holds the whole updated grid
+    cells = both[16:].reshape(-1, 2)
+    assert np.array_equal(states[0], _update(cells[:, 0], cells[:, 1]))
     assert np.array_equal(both[:7], single[:7])          # weights by type, crossings, emissions: exact
     assert both[0] == NPK and both[6] > 1.05 * NPK       # re-emission happened
     scale = np.abs(single[16:]).max()

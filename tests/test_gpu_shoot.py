@@ -169,7 +169,8 @@ def test_shoot_is_deterministic_and_shardable(cmib):
 
 
 @pytest.mark.parametrize("config", ["stromgren", "stromgren_diffuse", "lexington", "fixed_reemission", "periodic",
-                                    "continuous", "continuous_only", "planar", "distant_star", "extended_disc", "spiral_galaxy", "bimodal"])
+                                    "continuous", "continuous_only", "planar", "distant_star", "extended_disc", "spiral_galaxy", "bimodal",
+                                    "periodic_honly", "zero_direction"])
 def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     """The production shoot (prepare/march kernels + device queues, wavefront.cuh) and the
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
@@ -233,6 +234,25 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
         nu_probe = problems.ev_to_hz(np.array([13.7, 19.99, 20.0, 30.]))
         sig = prob.ctx.eval_cross_sections(nu_probe)
         assert np.array_equal(sig[:2], np.tile(low, (2, 1))) and np.array_equal(sig[2:], np.tile(high, (2, 1)))
+    elif config in ("periodic_honly", "zero_direction"):
+        # H-only layout (FixedValue cross sections) in a non-cubic box, two sources, re-emission at a fixed frequency
+        # (so there is a heat term): with two periodic axes ("periodic_honly") and without ("zero_direction" is
+        # that twin; explicit zero direction components are walked in test_gpu_march.py) — the periodic + heat and
+        # the heat variants of the coherent H-only walk (march_lean_kernel<true, *, ..>)
+        per = (True, False, True) if config == "periodic_honly" else (False, False, False)
+        ctx = cmib.Context([-1e17, -2e17, -3e17], [2e17, 5e17, 3e17], [12, 20, 9], periodic=per)
+        ctx.set_abundances()
+        sig = np.zeros(capi.NUM_IONS); sig[0] = 6.3e-22
+        ctx.set_cross_sections(capi.CROSS_SECTIONS_FIXED_VALUE, sig)
+        rr = np.zeros(capi.NUM_IONS); rr[0] = 4.e-19
+        ctx.set_recombination_rates(capi.RECOMBINATION_FIXED_VALUE, rr)
+        ctx.set_sources([[0., 0., 0.], [0.9e17, 2.9e17, -2.9e17]], [0.6, 0.4], 1e49)
+        ctx.set_spectrum(capi.SPECTRUM_MONOCHROMATIC, problems.ev_to_hz(15.))
+        ctx.set_reemission(capi.REEMISSION_FIXED_VALUE, 0.4, problems.ev_to_hz(14.2))
+        ctx.set_temperature_params(do_temperature_calculation=False)
+        nc = ctx.ncells
+        prob = problems.Problem(config, ctx, np.full(nc, 3e8), np.full(nc, 8000.), problems.initial_fractions(nc), npk, 1)
+        prob.upload()
     elif config == "continuous_only":
         prob = problems.lexington(20, ncell=24, n_packets=npk)
         prob.ctx.set_sources(None, None, 0.)
@@ -262,6 +282,7 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), ctx.ncells))
     ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
     results = []
+    # sort 1 = ordered queue read by the plain kernel, 2 = the coherent march (ordered queue + in-warp sums)
     for algorithm, capacity, sort in ((1, None, 0), (0, None, 0), (0, 4096, 0), (0, 1024, 0), (0, None, 1), (0, 2048, 1),
                                       (0, None, 2), (0, 2048, 2), (0, 1024, 2)):
         if capacity is None:
