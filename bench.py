@@ -10,8 +10,9 @@ with line cooling):
     reset accumulators -> re-emission probabilities -> shoot -> exchange (N > 1) -> state update
 
 After the headline the same loop is timed on the two north-star grids (BASELINE.json configs[4] and the 256^3
-Stroemgren grid of the target) and attached under `workloads.{stromgren256, clumpy256}`; each entry carries its own
-`value`, `ms_per_step`, `roofline` (HBM: these grids do not fit in L2), `phases_ms` and `clocks`.
+Stroemgren grid of the target) at the 1e9 packets per iteration configs[4] names, and attached under
+`workloads.{stromgren256, clumpy256}`; each entry carries its own `value`, `ms_per_step`, `roofline` (HBM: these
+grids do not fit in L2), `phases_ms` and `clocks`.
 
 Usage:  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workloads a,b,...]
 N > 1 is launched by torch.distributed.run (one rank per GPU).  Scaling is STRONG, as in the reference
@@ -102,17 +103,17 @@ WORKLOADS = {
     "lexingtonHII20": dict(grid=64, layout="full", label="benchmarks/lexingtonHII20.param",
                            physics="Planck 20000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse "
                                    "re-emission, temperature solve with line cooling",
-                           spinup_packets=1_000_000),
+                           spinup_packets=1_000_000, packets=100_000_000),
     "stromgren256": dict(grid=256, layout="honly", label="stromgren.param physics on a 256^3 grid (north-star target grid)",
                          physics="monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field",
-                         spinup_packets=16_000_000),
+                         spinup_packets=16_000_000, packets=1_000_000_000),
     "clumpy256": dict(grid=256, layout="honly", label="synthetic clumpy 256^3, 16 sources, H-only (BASELINE.json configs[4])",
                       physics="monochromatic 13.6 eV, FixedValue cross sections (H only), no diffuse field",
-                      spinup_packets=16_000_000),
+                      spinup_packets=16_000_000, packets=1_000_000_000),
     "clumpy256L": dict(grid=256, layout="full", label="synthetic clumpy 256^3, 16 sources, Lexington physics",
                        physics="Planck 40000 K, Verner cross sections, 14 ions + 2 heating terms, Physical diffuse "
                                "re-emission, temperature solve with line cooling",
-                       spinup_packets=16_000_000),
+                       spinup_packets=16_000_000, packets=100_000_000),
 }
 
 
@@ -298,7 +299,7 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
             ctx.shoot(my_cnt, packet_offset=my_lo, seed=prob.seed, iteration=loop, want_counters=False)
             if timed:
                 e[2].record(stream)
-                kernel_ms.append(ctx.shoot_timing(want_adds=False)[:3])
+                kernel_ms.append(ctx.shoot_timing(want_adds=False)[:3] + ctx.shoot_overlap())
             ctx.exchange_and_update(loop)        # N == 1: the state update alone
             if timed:
                 e[3].record(stream)
@@ -346,10 +347,11 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
     crossings, emissions = ctx.shoot_statistics()
     _, _, _, red_ops = ctx.shoot_timing()
     mean = lambda xs: float(np.mean(xs))
-    prep_ms, march_ms, rounds = (mean([k[i] for k in kernel_ms]) for i in range(3))
+    prep_ms, march_ms, rounds, lanes, overlap_ms = (mean([k[i] for k in kernel_ms]) for i in range(5))
     phases = {"reset_and_reemission_probabilities": mean([m[0].elapsed_time(m[1]) for m in marks]),
               "shoot": mean([m[1].elapsed_time(m[2]) for m in marks]),
               "shoot_prepare_kernels": prep_ms, "shoot_march_kernels": march_ms,
+              "shoot_prepare_beside_march": overlap_ms,
               "exchange_and_update": mean([m[2].elapsed_time(m[3]) for m in marks])}
     if exch_ms:
         phases["exchange_reduce"], phases["exchange_update_block"], phases["exchange_gather"] = (
@@ -384,6 +386,9 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
                                                    "added (zero terms are skipped, in-warp sums merge same-cell terms); "
                                                    "both counted on the device in this run"},
         "kernel_ms": march_ms, "kernel_launches_per_step": rounds, "kernel_share_of_step": march_ms / ms_per_step,
+        "kernel_ms_note": ("time during which a march kernel was running (CUDA events of the library on its streams; "
+                           f"{int(round(lanes))} lane(s): with two, the union of the launches' intervals, and the emission "
+                           "kernels of the other lane share the SMs during `shoot_prepare_beside_march` ms of it)"),
         "peak_source": peak_src,
         "traffic": None, "traffic_note": None,
     }
@@ -473,6 +478,8 @@ def main():
     ap.add_argument("--workloads", default="stromgren256,clumpy256",
                     help="comma-separated extra workloads attached under `workloads` ('' = none)")
     ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--extra-packets", type=float, default=0., help="packets per iteration of the extra workloads "
+                    "(default: 1e9, BASELINE.json configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -531,7 +538,8 @@ def main():
     if extra:
         line["workloads"] = {}
         for name in extra:
-            rec = run_workload(name, n_packets, args, rank, world, local_rank, args.extra_steps, 2, args.spinup,
+            rec = run_workload(name, int(args.extra_packets or WORKLOADS[name]["packets"]), args, rank, world, local_rank,
+                               args.extra_steps, 2, args.spinup,
                                not args.no_e2e, scatter_l2 if WORKLOADS[name]["grid"] <= 64 else scatter_hbm)
             rec["metric"] = METRIC.replace("lexingtonHII20", name)
             rec["n_gpus"] = world

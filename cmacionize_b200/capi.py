@@ -292,6 +292,12 @@ class Context:
                                      C.byref(d) if want_adds else None))
         return a.value, b.value, int(r.value), d.value
 
+    def shoot_overlap(self):
+        """(lanes of the last shoot, ms during which emission and march kernels ran side by side)"""
+        n, o = C.c_int32(), C.c_double()
+        _check(lib.cmib_shoot_overlap(self._h, C.byref(n), C.byref(o)))
+        return int(n.value), o.value
+
     def update_state(self, loop, totweight=0.):
         _check(lib.cmib_update_state(self._h, C.c_uint32(loop), C.c_double(totweight)))
 

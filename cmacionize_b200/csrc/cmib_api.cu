@@ -6,6 +6,7 @@
  * context's stream.  There is no CPU compute path: every entry point that does
  * work requires a CUDA device and fails loudly otherwise.
  */
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cstdarg>
@@ -13,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <deque>
 #include <vector>
 
 #include <dlfcn.h>
@@ -192,11 +194,26 @@ struct cmib_context {
   bool force_full = false;
   /* wavefront shoot (wavefront.cuh): queues + control block, allocated on first use */
   int shoot_algorithm = 0; /* 0 wavefront (production), 1 one-thread-per-packet kernel (A/B check) */
-  uint64_t queue_capacity = 0;
-  int queue_mode = -1;
-  DevBuf<double> mq, rq, eq;
-  DevBuf<unsigned long long> ctl;
-  DevBuf<uint32_t> sort_key, sort_rank, sort_order, sort_hist, sort_offs, sort_block_sums; /* coherent march: counting sort */
+  /* A shoot runs as one or two LANES: each lane owns a set of queues, a control block and a stream and walks its
+   * share of the packets through rounds of decide -> prepare -> (sort) -> march.  With two lanes the kernels are
+   * launched on half-size grids and the lanes run out of phase, so that the emission of one lane (FP64 / issue
+   * bound) executes on the same SMs as the walk of the other (L1TEX / latency bound) instead of before it. */
+  struct Lane {
+    uint64_t queue_capacity = 0;
+    int queue_mode = -1;
+    DevBuf<double> mq, rq, eq;
+    DevBuf<unsigned long long> ctl;
+    DevBuf<uint32_t> sort_key, sort_rank, sort_order, sort_hist, sort_offs, sort_block_sums; /* coherent march: counting sort */
+    unsigned long long *h_ctl = nullptr; /* pinned mirrors of the control block: one per group of rounds in flight */
+    cudaStream_t stream = nullptr;       /* lane 0: the context's stream */
+    cudaEvent_t group_done[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_pool;    /* optional per-kernel timing */
+    size_t ev_used = 0;
+  };
+  Lane lane[2];
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, origin_ev = nullptr;
+  int shoot_lanes = 1;        /* lanes of the last shoot */
+  double overlap_ms = 0.;     /* time of the last shoot during which an emission kernel ran beside a march kernel */
   DevBuf<uint32_t> d_src_cell;  /* packed cell indices of the sources */
   std::vector<uint32_t> h_src_cell;
   int hot_replicas = 0;
@@ -216,7 +233,6 @@ struct cmib_context {
   double exchange_ms[3] = {0., 0., 0.};
   double walk_cells = 0.; /* mean walk length (cells) of the last large shoot: sizes the direction bins of the sort key */
   size_t l2_bytes = 0;
-  unsigned long long *h_ctl = nullptr; /* pinned mirror of the control block */
   int march_blocks_per_sm[2][2] = {{0, 0}, {0, 0}}; /* [layout][plain, coherent] */
   int lean_grid[2][2][2][2] = {};                   /* resident CTAs per SM of the march_lean_kernel variants */
   int prep_blocks_per_sm[2] = {0, 0};
@@ -224,7 +240,6 @@ struct cmib_context {
   uint64_t shoot_rounds = 0;
   /* optional per-kernel timing of the shoot (CUDA events on the context's stream) */
   bool timing = false;
-  std::vector<cudaEvent_t> ev_pool;
   double prepare_ms = 0., march_ms = 0.;
   double nu_H = 0., nu_He = 0.;
 
@@ -370,20 +385,44 @@ int set_spectrum_model(cmib_context *ctx, SpectrumModel &sp, std::vector<double>
 }
 
 /* packets per round of the wavefront pipeline.  Emission order: 16 Mi (5 GB of queues in the full layout; measured
- * 124 -> 117 ms per lexingtonHII20 step against 4 Mi).  Coherent march: 64 Mi — the sort key has ~log2(packets per
- * round / 4) bits to spend on source, direction and optical depth, so larger rounds order many-source problems
- * finer (clumpy 256^3, 16 sources: 7.7e8 -> 9.1e8 packets/s from 16 Mi to 64 Mi, profiles/r02_lean_march.md) */
-uint64_t default_queue_capacity(bool coherent) {
+ * 124 -> 117 ms per lexingtonHII20 step against 4 Mi).  Coherent march: what the sort key needs (shoot_wavefront) */
+uint64_t default_queue_capacity(bool coherent, uint64_t coherent_round) {
   const char *e = getenv("CMIB_QUEUE_CAPACITY");
   if (e) {
     const long long v = atoll(e);
     if (v >= 1024) return (uint64_t)v;
   }
-  return coherent ? (1ull << 26) : (1ull << 24);
+  return coherent ? coherent_round : (1ull << 24);
 }
 
-/* one cmib_shoot call on the wavefront path: rounds of prepare -> march until the
- * queues run dry.  The host only reads back the march-queue sizes every few rounds. */
+/* measure of a union of intervals (sorted in place), and of the intersection of two such unions */
+void merge_intervals(std::vector<std::pair<double, double>> &v) {
+  std::sort(v.begin(), v.end());
+  size_t n = 0;
+  for (size_t i = 0; i < v.size(); ++i) {
+    if (n > 0 && v[i].first <= v[n - 1].second) v[n - 1].second = std::max(v[n - 1].second, v[i].second);
+    else v[n++] = v[i];
+  }
+  v.resize(n);
+}
+double interval_measure(const std::vector<std::pair<double, double>> &v) {
+  double m = 0.;
+  for (const auto &i : v) m += i.second - i.first;
+  return m;
+}
+double interval_overlap(const std::vector<std::pair<double, double>> &a, const std::vector<std::pair<double, double>> &b) {
+  double m = 0.;
+  size_t i = 0, j = 0;
+  while (i < a.size() && j < b.size()) {
+    const double lo = std::max(a[i].first, b[j].first), hi = std::min(a[i].second, b[j].second);
+    if (hi > lo) m += hi - lo;
+    if (a[i].second < b[j].second) ++i; else ++j;
+  }
+  return m;
+}
+
+/* one cmib_shoot call on the wavefront path: rounds of prepare -> march until the queues run dry, on one or two
+ * lanes (cmib_context::Lane).  The host reads a lane's control block back once per group of rounds. */
 int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   const int mode = ctx->acc_mode;
   /* order of the march queue (cmib_context::sort_mode; CMIB_SORT overrides for A/B runs) */
@@ -393,20 +432,70 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     const size_t working_set = (size_t)ctx->geom.ncells * ((mode == ACC_HONLY ? 16 : sizeof(CellOpacity)) + (mode == ACC_HONLY ? 16 : 128));
     sort = (working_set > ctx->l2_bytes && P.n_packets >= (1ull << 20)) ? 2 : 0;
   }
-  uint64_t cap = default_queue_capacity(sort != 0);
-  if (P.n_packets < cap) cap = (P.n_packets + 1023) / 1024 * 1024;
-  const int nf = (mode == ACC_HONLY) ? MarchQueueLayout<ACC_HONLY>::NFIELDS : MarchQueueLayout<ACC_FULL>::NFIELDS;
-  if (ctx->queue_capacity < cap || ctx->queue_mode != mode) {
-    CUDA_OK(ctx->mq.resize((size_t)nf * cap));
-    CUDA_OK(ctx->rq.resize((size_t)RQ_NFIELDS * cap));
-    CUDA_OK(ctx->eq.resize((size_t)EQ_NFIELDS * cap));
-    ctx->queue_capacity = cap;
-    ctx->queue_mode = mode;
+  /* coherent march: the key wants source + direction bits (below) + a few optical-depth bits, and ~4 packets per
+   * bin: that sets the size of a round, between 16 Mi (one source) and 64 Mi packets (16 sources: clumpy 256^3
+   * 7.7e8 -> 9.1e8 packets/s from 16 Mi to 64 Mi, profiles/r02_lean_march.md) */
+  int src_bits = 0, dir_bits = 0;
+  uint64_t coherent_round = 1ull << 26;
+  if (sort == 2 || sort == 1) {
+    while ((1ll << src_bits) < (long long)P.src.n_sources) ++src_bits;
+    /* how many direction bins?  Packets of one bin should still cross the same cells at the END of their walk:
+     * bin width x walk length ~ one cell, i.e. 4 pi L^2 bins per source for walks of L cells.  L comes from the
+     * previous large shoot of this context (cell crossings per walk / 1.5: an isotropic direction crosses
+     * |dx| + |dy| + |dz| = 1.5 walls per cell of path on average), else half the grid.  Measured (B200, 1.6e7
+     * packets per round): stromgren 256^3, L = 85: 16 direction + 6 depth bits 11.0 ms, 18 + 4 11.5, 22 + 0 13.1;
+     * clumpy 256^3, 16 sources, L = 106: 18 + 0 19.7 ms, 16 + 2 20.2, 14 + 4 22.2 (profiles/r02_lean_march.md). */
+    double walk = 0.5 * (double)std::max(P.geom.ncell[0], std::max(P.geom.ncell[1], P.geom.ncell[2]));
+    if (ctx->walk_cells > 0.) walk = ctx->walk_cells;
+    dir_bits = 2 * (int)std::lround(0.5 * std::log2(4. * 3.14159265358979 * walk * walk)); /* nearest even */
+    if (const char *e = getenv("CMIB_DIR_BITS")) dir_bits = atoi(e) & ~1;
+    if (dir_bits > 22) dir_bits = 22;
+    if (dir_bits < 8) dir_bits = 8;
+    if (src_bits + dir_bits > SORT_MAX_KEY_BITS) dir_bits = (SORT_MAX_KEY_BITS - src_bits) & ~1;
+    const int want_bits = std::min(src_bits + dir_bits + 4, 24) + 2;
+    coherent_round = std::min<uint64_t>(std::max<uint64_t>(1ull << want_bits, 1ull << 24), 1ull << 26);
   }
-  cap = ctx->queue_capacity;
-  if (!ctx->ctl.p) {
-    CUDA_OK(ctx->ctl.resize(CTL_WORDS));
-    CUDA_OK(cudaMallocHost((void **)&ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long)));
+  /* lanes: two for large shoots of the coherent march (four rounds or more), whose walk is bound by instruction
+   * issue with stalls that the emission and sort kernels of the other lane fill (stromgren 256^3, 1e9 packets:
+   * 764 -> 704 ms; clumpy 256^3: 1040 vs 1043 ms); one where walk and emission compete for the same unit
+   * (lexingtonHII20 64^3, both on L1TEX: 98.4 vs 98.9 ms) and for small shoots, where halving the rounds costs
+   * more coherence than the overlap returns (profiles/r02_lanes.md).  CMIB_LANES overrides */
+  int nlanes = (sort == 2 && P.n_packets >= 4 * coherent_round) ? 2 : 1;
+  if (const char *e = getenv("CMIB_LANES")) nlanes = atoi(e) == 2 ? 2 : 1;
+  if (P.n_packets < 2048) nlanes = 1;
+  uint64_t lane_n[2] = {P.n_packets, 0};
+  if (nlanes == 2) {
+    lane_n[1] = P.n_packets / 2;
+    lane_n[0] = P.n_packets - lane_n[1];
+  }
+  const int nf = (mode == ACC_HONLY) ? MarchQueueLayout<ACC_HONLY>::NFIELDS : MarchQueueLayout<ACC_FULL>::NFIELDS;
+  uint64_t lane_cap[2] = {0, 0};
+  for (int l = 0; l < nlanes; ++l) {
+    cmib_context::Lane &L = ctx->lane[l];
+    if (!L.stream) {
+      if (l == 0) L.stream = ctx->stream;
+      else CUDA_OK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    }
+    uint64_t cap = default_queue_capacity(sort != 0, coherent_round);
+    if (lane_n[l] < cap) cap = (lane_n[l] + 1023) / 1024 * 1024;
+    if (L.queue_capacity < cap || L.queue_mode != mode) {
+      CUDA_OK(L.mq.resize((size_t)nf * cap));
+      CUDA_OK(L.rq.resize((size_t)RQ_NFIELDS * cap));
+      CUDA_OK(L.eq.resize((size_t)EQ_NFIELDS * cap));
+      L.queue_capacity = cap;
+      L.queue_mode = mode;
+    }
+    lane_cap[l] = L.queue_capacity;
+    if (!L.ctl.p) {
+      CUDA_OK(L.ctl.resize(CTL_WORDS));
+      CUDA_OK(cudaMallocHost((void **)&L.h_ctl, 2 * CTL_WORDS * sizeof(unsigned long long)));
+      for (cudaEvent_t &e : L.group_done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+  }
+  if (!ctx->fork_ev) {
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreate(&ctx->origin_ev));
     int occ[4] = {0, 0, 0, 0};
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false, true>, MARCH_BLOCK, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], march_kernel<ACC_FULL, true, true>, MARCH_BLOCK, 0));
@@ -417,18 +506,9 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     ctx->march_blocks_per_sm[ACC_HONLY][0] = occ[2];
     ctx->march_blocks_per_sm[ACC_HONLY][1] = occ[3];
   }
-  cudaStream_t s = ctx->stream;
-  memset(ctx->h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
-  ctx->h_ctl[CTL_REMAINING] = P.n_packets;
-  CUDA_OK(cudaMemcpyAsync(ctx->ctl.p, ctx->h_ctl, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyHostToDevice, s));
-  shoot_begin_kernel<<<1, 1, 0, s>>>(ctx->ctl.p, P.acc);
+  cudaStream_t s0 = ctx->stream;
   WavefrontParams W;
   W.sp = P;
-  W.ctl = ctx->ctl.p;
-  W.mq = ctx->mq.p;
-  W.rq = ctx->rq.p;
-  W.eq = ctx->eq.p;
-  W.capacity = cap;
   W.acc_j = P.acc + ACC_COUNTERS + P.honly_offset;
   W.hot_index0 = P.hot_acc ? (uint32_t)(P.hot_acc - W.acc_j) : 0xffffffffu;
   for (int d = 0; d < 3; ++d) W.lean_n16[d] = 16u * (uint32_t)P.geom.ncell[d];
@@ -439,32 +519,37 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   W.sort = sort;
   W.key = W.rank = W.order = W.hist = W.offs = W.block_sums = nullptr;
   W.nbins = 0; W.fine_dir_bits = 22; W.fine_key_bits = 22; W.tau_bits = 0; W.chunk_stride = 1;
+  /* entries a round of lane l may hold: the lane's capacity; CMIB_LANE_ROUNDS = r asks for at least r rounds per
+   * lane (A/B runs); with two lanes the first round of lane 1 is half a round, which puts the lanes out of phase:
+   * the emission of one lane then runs beside the walk of the other */
+  uint64_t lane_fill[2] = {lane_cap[0], lane_cap[1]};
+  {
+    int min_rounds = 1;
+    if (const char *e = getenv("CMIB_LANE_ROUNDS")) min_rounds = atoi(e) > 1 ? atoi(e) : 1;
+    for (int l = 0; l < nlanes; ++l) {
+      const uint64_t per = ((lane_n[l] + min_rounds - 1) / min_rounds + 1023) / 1024 * 1024;
+      if (per < lane_fill[l]) lane_fill[l] = per;
+      if (lane_fill[l] < 1024) lane_fill[l] = 1024;
+    }
+  }
+  auto round_fill = [&](int l, uint64_t round) -> uint64_t {
+    if (nlanes == 2 && l == 1 && round == 0) {
+      const uint64_t first = std::min(lane_fill[1], lane_n[1]);
+      return std::max<uint64_t>(1024, (first / 2 + 1023) / 1024 * 1024);
+    }
+    return lane_fill[l];
+  };
   bool sort_reemitted_rounds = false;
   if (sort == 2) {
-    /* key = source | direction (wavefront.cuh): as many direction bits as the source index leaves of
-     * SORT_MAX_KEY_BITS; 0 | key for primaries, 1 | position key for re-emitted packets */
-    int src_bits = 0;
-    while ((1ll << src_bits) < (long long)P.src.n_sources) ++src_bits;
-    /* how many direction bins?  Packets of one bin should still cross the same cells at the END of their walk:
-     * bin width x walk length ~ one cell, i.e. 4 pi L^2 bins per source for walks of L cells.  L comes from the
-     * previous large shoot of this context (cell crossings per walk / 1.5: an isotropic direction crosses
-     * |dx| + |dy| + |dz| = 1.5 walls per cell of path on average), else half the grid.  Measured (B200, 1.6e7
-     * packets per round): stromgren 256^3, L = 85: 16 direction + 6 depth bits 11.0 ms, 18 + 4 11.5, 22 + 0 13.1;
-     * clumpy 256^3, 16 sources, L = 106: 18 + 0 19.7 ms, 16 + 2 20.2, 14 + 4 22.2 (profiles/r02_lean_march.md).
-     * The bits that are left (of ~log2(packets per round / 4)) order the packets of a direction bin by sampled
-     * optical depth, so that the 8 lanes of a refill group are absorbed close together. */
-    double walk = 0.5 * (double)std::max(P.geom.ncell[0], std::max(P.geom.ncell[1], P.geom.ncell[2]));
-    if (ctx->walk_cells > 0.) walk = ctx->walk_cells;
-    int dir_bits = 2 * (int)std::lround(0.5 * std::log2(4. * 3.14159265358979 * walk * walk)); /* nearest even */
-    if (const char *e = getenv("CMIB_DIR_BITS")) dir_bits = atoi(e) & ~1;
-    if (dir_bits > 22) dir_bits = 22;
-    if (dir_bits < 8) dir_bits = 8;
+    /* key = source | direction | optical depth (wavefront.cuh): 0 | key for primaries, 1 | position key for
+     * re-emitted packets.  The bits that are left (of ~log2(packets per round / 4)) order the packets of a direction
+     * bin by sampled optical depth, so that the 8 lanes of a refill group are absorbed close together. */
     int budget = 2; /* ~4 packets per bin */
-    while ((1ull << budget) < (P.n_packets < cap ? P.n_packets : cap)) ++budget;
+    const uint64_t per_round = std::min(lane_n[0], lane_fill[0]);
+    while ((1ull << budget) < per_round) ++budget;
     budget -= 2;
     if (budget > SORT_MAX_KEY_BITS) budget = SORT_MAX_KEY_BITS;
     if (const char *e = getenv("CMIB_KEY_BITS")) budget = atoi(e) > SORT_MAX_KEY_BITS ? SORT_MAX_KEY_BITS : atoi(e);
-    if (src_bits + dir_bits > SORT_MAX_KEY_BITS) dir_bits = (SORT_MAX_KEY_BITS - src_bits) & ~1;
     int tau_bits = budget - src_bits - dir_bits;
     if (const char *e = getenv("CMIB_TAU_BITS")) tau_bits = atoi(e);
     if (tau_bits < 0) tau_bits = 0;
@@ -478,59 +563,42 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   }
   if (sort == 2) {
     if (const char *e = getenv("CMIB_CHUNK_STRIDE")) W.chunk_stride = (uint32_t)atoll(e); /* e.g. the prime 1000003 */
-    if (W.chunk_stride < 1u || cap / MARCH_CHUNK >= W.chunk_stride) W.chunk_stride = 1u;
+    if (W.chunk_stride < 1u || std::max(lane_cap[0], lane_cap[1]) / MARCH_CHUNK >= W.chunk_stride) W.chunk_stride = 1u;
     if (const char *e = getenv("CMIB_AGG")) W.agg = atoi(e) != 0;
     if (const char *e = getenv("CMIB_SORT_REEMITTED")) sort_reemitted_rounds = atoi(e) != 0;
     W.nbins = 2u << W.fine_key_bits;
-    if (ctx->sort_key.n < cap) {
-      CUDA_OK(ctx->sort_key.resize(cap));
-      CUDA_OK(ctx->sort_rank.resize(cap));
-      CUDA_OK(ctx->sort_order.resize(cap));
+    for (int l = 0; l < nlanes; ++l) {
+      cmib_context::Lane &L = ctx->lane[l];
+      if (L.sort_key.n < lane_cap[l]) {
+        CUDA_OK(L.sort_key.resize(lane_cap[l]));
+        CUDA_OK(L.sort_rank.resize(lane_cap[l]));
+        CUDA_OK(L.sort_order.resize(lane_cap[l]));
+      }
+      if (L.sort_hist.n < W.nbins) {
+        CUDA_OK(L.sort_hist.resize(W.nbins));
+        CUDA_OK(L.sort_offs.resize(W.nbins));
+        CUDA_OK(L.sort_block_sums.resize(SORT_MAX_TILES));
+        CUDA_OK(cudaMemsetAsync(L.sort_hist.p, 0, W.nbins * sizeof(uint32_t), s0));
+      }
     }
-    if (ctx->sort_hist.n < W.nbins) {
-      CUDA_OK(ctx->sort_hist.resize(W.nbins));
-      CUDA_OK(ctx->sort_offs.resize(W.nbins));
-      CUDA_OK(ctx->sort_block_sums.resize(SORT_MAX_TILES));
-      CUDA_OK(cudaMemsetAsync(ctx->sort_hist.p, 0, W.nbins * sizeof(uint32_t), ctx->stream));
-    }
-    W.key = ctx->sort_key.p; W.rank = ctx->sort_rank.p; W.order = ctx->sort_order.p;
-    W.hist = ctx->sort_hist.p; W.offs = ctx->sort_offs.p; W.block_sums = ctx->sort_block_sums.p;
   }
   /* persistent grids: exactly the CTAs that are resident at once (a partial second wave of a
-   * grid-stride kernel runs at a fraction of the machine) */
+   * grid-stride kernel runs at a fraction of the machine); with two lanes each lane launches half of them */
   if (ctx->prep_blocks_per_sm[0] == 0) {
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prep_blocks_per_sm[ACC_FULL], prepare_kernel<ACC_FULL>, 256, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->prep_blocks_per_sm[ACC_HONLY], prepare_kernel<ACC_HONLY>, 256, 0));
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->decide_blocks_per_sm, reemit_decide_kernel, 256, 0));
   }
-  const unsigned prep_grid = (unsigned)(ctx->sm_count * (ctx->prep_blocks_per_sm[mode] > 0 ? ctx->prep_blocks_per_sm[mode] : 1));
-  const unsigned decide_grid = (unsigned)(ctx->sm_count * (ctx->decide_blocks_per_sm > 0 ? ctx->decide_blocks_per_sm : 1));
+  auto lane_grid = [&](unsigned full) -> unsigned { return nlanes == 2 ? (full + 1u) / 2u : full; };
+  const unsigned prep_grid = lane_grid((unsigned)(ctx->sm_count * (ctx->prep_blocks_per_sm[mode] > 0 ? ctx->prep_blocks_per_sm[mode] : 1)));
+  const unsigned decide_grid = lane_grid((unsigned)(ctx->sm_count * (ctx->decide_blocks_per_sm > 0 ? ctx->decide_blocks_per_sm : 1)));
   unsigned march_grids[2];
   for (int a = 0; a < 2; ++a) {
     int bpm = ctx->march_blocks_per_sm[mode][a];
     if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e);
     if (bpm < 1) bpm = 1;
-    march_grids[a] = (unsigned)(ctx->sm_count * bpm);
+    march_grids[a] = lane_grid((unsigned)(ctx->sm_count * bpm));
   }
-  const int group = 4;
-  uint64_t round = 0;
-  size_t ev_used = 0;
-  auto stamp = [&]() {
-    if (!ctx->timing) return;
-    if (ev_used == ctx->ev_pool.size()) {
-      cudaEvent_t e;
-      cudaEventCreate(&e);
-      ctx->ev_pool.push_back(e);
-    }
-    cudaEventRecord(ctx->ev_pool[ev_used++], s);
-  };
-  ctx->prepare_ms = ctx->march_ms = 0.;
-  /* upper bound: every round either emits min(remaining, room) primaries or shrinks the
-   * re-emission population; 1e6 rounds cannot be reached by a sane configuration */
-  /* coherent march: what the host knows about the coming rounds (read back once per group):
-   * while primaries remain a round can fill the queue; afterwards it holds at most the packets
-   * of the round before.  Rounds without primaries (re-emitted packets start anywhere) run
-   * unsorted through the plain kernel. */
   const int sort_cfg = W.sort;
   /* H-only coherent walk: march_lean_kernel (CMIB_LEAN=0: the r01 kernel, for A/B runs) */
   int lean_cfg = 1, lean_steps = 3;
@@ -552,114 +620,243 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
    * the plain kernel is bound by L1TEX lanes, not latency (no gain; -16 % with the full layout's spills) */
   int prefetch_cfg = -1;
   if (const char *e = getenv("CMIB_PREFETCH")) prefetch_cfg = atoi(e) != 0;
-  bool primaries_left = true;
-  /* on any failure below the hot-cell replicas must not leak into the next shoot */
-  auto fail_cleanup = [&]() {
-    if (P.hot_replicas > 0 && P.hot_acc) cudaMemsetAsync(P.hot_acc, 0, ctx->hot_doubles() * sizeof(double), s);
-    if (W.hist) cudaMemsetAsync(W.hist, 0, W.nbins * sizeof(uint32_t), s); /* bin counts are zero between rounds */
+  const bool can_reemit = (P.src.reemission_kind != REEMISSION_NONE);
+
+  /* ---- per-lane state of this shoot ---- */
+  struct Run {
+    WavefrontParams W;
+    uint64_t rounds = 0;      /* rounds enqueued */
+    int enq = 0, fin = 0;     /* groups enqueued / read back */
+    uint64_t group_first[2] = {0, 0};
+    int group_rounds[2] = {0, 0};
+    bool done = false, primaries_left = true;
+  } run[2];
+  if (ctx->timing) CUDA_OK(cudaEventRecord(ctx->origin_ev, s0));
+  shoot_begin_kernel<<<1, 1, 0, s0>>>(ctx->lane[0].ctl.p, P.acc);
+  ++g_launches;
+  if (nlanes == 2) {
+    /* lane 1 starts after everything that is queued on the context's stream */
+    CUDA_OK(cudaEventRecord(ctx->fork_ev, s0));
+    CUDA_OK(cudaStreamWaitEvent(ctx->lane[1].stream, ctx->fork_ev, 0));
+  }
+  for (int l = 0; l < nlanes; ++l) {
+    cmib_context::Lane &L = ctx->lane[l];
+    Run &R = run[l];
+    R.W = W;
+    R.W.sp.packet_offset = P.packet_offset + (l == 0 ? 0 : lane_n[0]);
+    R.W.sp.n_packets = lane_n[l];
+    R.W.ctl = L.ctl.p;
+    R.W.mq = L.mq.p;
+    R.W.rq = L.rq.p;
+    R.W.eq = L.eq.p;
+    R.W.capacity = lane_cap[l];
+    R.W.fill = lane_fill[l];
+    if (sort_cfg == 2) {
+      R.W.key = L.sort_key.p; R.W.rank = L.sort_rank.p; R.W.order = L.sort_order.p;
+      R.W.hist = L.sort_hist.p; R.W.offs = L.sort_offs.p; R.W.block_sums = L.sort_block_sums.p;
+    }
+    L.ev_used = 0;
+    /* control block: everything zero but the primaries to emit (lane 0 keeps what shoot_begin_kernel wrote) */
+    memset(L.h_ctl, 0, CTL_WORDS * sizeof(unsigned long long));
+    L.h_ctl[CTL_REMAINING] = lane_n[l];
+    CUDA_OK(cudaMemcpyAsync(L.ctl.p, L.h_ctl, CTL_CROSSINGS0 * sizeof(unsigned long long), cudaMemcpyHostToDevice, L.stream));
+  }
+  auto stamp = [&](cmib_context::Lane &L) {
+    if (!ctx->timing) return;
+    if (L.ev_used == L.ev_pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      L.ev_pool.push_back(e);
+    }
+    cudaEventRecord(L.ev_pool[L.ev_used++], L.stream);
   };
-  bool done = false;
-  const uint64_t max_rounds = 100000;  /* every round emits min(remaining, room) primaries or shrinks the
-                                        * re-emission population; a sane configuration stays far below */
-  while (!done && round < max_rounds) {
-    for (int k = 0; k < group; ++k, ++round) {
-      /* rounds without primaries (re-emitted packets start anywhere) run unsorted through the plain kernel */
-      if (sort_cfg == 2) W.sort = (primaries_left || sort_reemitted_rounds) ? 2 : 0;
-      const int sort = W.sort;
-      stamp();
-      if (P.src.reemission_kind != REEMISSION_NONE && round > 0) {
-        reemit_decide_kernel<<<decide_grid, 256, 0, s>>>(W);
-        ++g_launches;
-      }
-      if (mode == ACC_HONLY) prepare_kernel<ACC_HONLY><<<prep_grid, 256, 0, s>>>(W);
-      else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(W);
-      stamp();
-      advance_after_prepare_kernel<<<1, 1, 0, s>>>(W.ctl, cap);
-      if (sort == 2) {
-        /* counting sort: prepare_kernel counted the bins and handed out tickets */
-        const unsigned ntiles = W.nbins / SORT_SCAN_TILE;
-        sort_scan_tiles_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(W.hist, W.block_sums);
-        sort_scan_sums_kernel<<<1, SORT_SCAN_BLOCK, 0, s>>>(W.block_sums, ntiles);
-        sort_scan_offsets_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(W.hist, W.block_sums, W.offs);
-        sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(W.ctl, W.key, W.rank, W.offs, W.order);
-        g_launches += 4;
-      }
-      stamp();
-      {
-        const bool agg = (sort == 2 && W.agg);
-        const unsigned march_grid = march_grids[agg ? 1 : 0];
-        const bool prefetch = prefetch_cfg < 0 ? agg : (prefetch_cfg != 0);
-        if (agg && mode == ACC_HONLY && lean_cfg) {
-          /* march_coherent.cuh: the H-only coherent walk, variant by what the packets of this shoot can carry */
-          using K = void (*)(const WavefrontParams);
-          static const K variants[2][2][2][2] = {
-#define CMIB_LEAN_V(H, PER, PR) {march_lean_kernel<H, PER, PR, 2>, march_lean_kernel<H, PER, PR, 3>}
-              {{CMIB_LEAN_V(false, false, false), CMIB_LEAN_V(false, false, true)},
-               {CMIB_LEAN_V(false, true, false), CMIB_LEAN_V(false, true, true)}},
-              {{CMIB_LEAN_V(true, false, false), CMIB_LEAN_V(true, false, true)},
-               {CMIB_LEAN_V(true, true, false), CMIB_LEAN_V(true, true, true)}}};
-#undef CMIB_LEAN_V
-          K k = variants[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
-          if (ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] == 0) {
-            CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem));
-            int occ = 0;
-            CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, MARCH_BLOCK, lean_smem));
-            if (occ < 1) CMIB_FAIL("march_lean_kernel does not fit on an SM with %zu bytes of wall tables", lean_smem);
-            ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] = occ;
-          }
-          int bpm = ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
-          if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e) > 0 ? atoi(e) : bpm;
-          k<<<(unsigned)(ctx->sm_count * bpm), MARCH_BLOCK, lean_smem, s>>>(W);
-        } else
-#define CMIB_LAUNCH_MARCH(M, A, R) march_kernel<M, A, R><<<march_grid, MARCH_BLOCK, 0, s>>>(W)
-        if (mode == ACC_HONLY) {
-          if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, true, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, true, false); }
-          else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, false, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, false, false); }
-        } else {
-          if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, true, true); else CMIB_LAUNCH_MARCH(ACC_FULL, true, false); }
-          else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, false, true); else CMIB_LAUNCH_MARCH(ACC_FULL, false, false); }
-        }
-#undef CMIB_LAUNCH_MARCH
-      }
-      stamp();
-      advance_after_march_kernel<<<1, 1, 0, s>>>(W.ctl, P.acc);
+  /* on any failure below nothing may stay in flight, and the hot-cell replicas and bin counts must not leak
+   * into the next shoot */
+  auto fail_cleanup = [&]() {
+    for (int l = 0; l < nlanes; ++l) cudaStreamSynchronize(ctx->lane[l].stream);
+    if (P.hot_replicas > 0 && P.hot_acc) cudaMemsetAsync(P.hot_acc, 0, ctx->hot_doubles() * sizeof(double), s0);
+    for (int l = 0; l < nlanes; ++l)
+      if (run[l].W.hist) cudaMemsetAsync(run[l].W.hist, 0, W.nbins * sizeof(uint32_t), s0); /* bin counts are zero between rounds */
+    cudaStreamSynchronize(s0);
+  };
+
+  auto enqueue_round = [&](int l) -> int {
+    cmib_context::Lane &L = ctx->lane[l];
+    Run &R = run[l];
+    WavefrontParams &Wl = R.W;
+    cudaStream_t s = L.stream;
+    const uint64_t round = R.rounds;
+    /* rounds without primaries (re-emitted packets start anywhere) run unsorted through the plain kernel */
+    if (sort_cfg == 2) Wl.sort = (R.primaries_left || sort_reemitted_rounds) ? 2 : 0;
+    const int sort = Wl.sort;
+    Wl.fill = round_fill(l, round);
+    stamp(L);
+    if (can_reemit && round > 0) {
+      reemit_decide_kernel<<<decide_grid, 256, 0, s>>>(Wl);
+      ++g_launches;
+    }
+    if (mode == ACC_HONLY) prepare_kernel<ACC_HONLY><<<prep_grid, 256, 0, s>>>(Wl);
+    else prepare_kernel<ACC_FULL><<<prep_grid, 256, 0, s>>>(Wl);
+    stamp(L);
+    advance_after_prepare_kernel<<<1, 1, 0, s>>>(Wl.ctl, Wl.fill);
+    if (sort == 2) {
+      /* counting sort: prepare_kernel counted the bins and handed out tickets */
+      const unsigned ntiles = Wl.nbins / SORT_SCAN_TILE;
+      sort_scan_tiles_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(Wl.hist, Wl.block_sums);
+      sort_scan_sums_kernel<<<1, SORT_SCAN_BLOCK, 0, s>>>(Wl.block_sums, ntiles);
+      sort_scan_offsets_kernel<<<ntiles, SORT_SCAN_BLOCK, 0, s>>>(Wl.hist, Wl.block_sums, Wl.offs);
+      sort_scatter_kernel<<<prep_grid, 256, 0, s>>>(Wl.ctl, Wl.key, Wl.rank, Wl.offs, Wl.order);
       g_launches += 4;
     }
+    stamp(L);
+    {
+      const bool agg = (sort == 2 && Wl.agg);
+      const unsigned march_grid = march_grids[agg ? 1 : 0];
+      const bool prefetch = prefetch_cfg < 0 ? agg : (prefetch_cfg != 0);
+      if (agg && mode == ACC_HONLY && lean_cfg) {
+        /* march_coherent.cuh: the H-only coherent walk, variant by what the packets of this shoot can carry */
+        using K = void (*)(const WavefrontParams);
+        static const K variants[2][2][2][2] = {
+#define CMIB_LEAN_V(H, PER, PR) {march_lean_kernel<H, PER, PR, 2>, march_lean_kernel<H, PER, PR, 3>}
+            {{CMIB_LEAN_V(false, false, false), CMIB_LEAN_V(false, false, true)},
+             {CMIB_LEAN_V(false, true, false), CMIB_LEAN_V(false, true, true)}},
+            {{CMIB_LEAN_V(true, false, false), CMIB_LEAN_V(true, false, true)},
+             {CMIB_LEAN_V(true, true, false), CMIB_LEAN_V(true, true, true)}}};
+#undef CMIB_LEAN_V
+        K k = variants[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
+        if (ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] == 0) {
+          CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lean_smem));
+          int occ = 0;
+          CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, MARCH_BLOCK, lean_smem));
+          if (occ < 1) CMIB_FAIL("march_lean_kernel does not fit on an SM with %zu bytes of wall tables", lean_smem);
+          ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1] = occ;
+        }
+        int bpm = ctx->lean_grid[lean_heat][lean_periodic][prefetch ? 1 : 0][lean_steps == 2 ? 0 : 1];
+        if (const char *e = getenv("CMIB_MARCH_BLOCKS_PER_SM")) bpm = atoi(e) > 0 ? atoi(e) : bpm;
+        k<<<lane_grid((unsigned)(ctx->sm_count * bpm)), MARCH_BLOCK, lean_smem, s>>>(Wl);
+      } else
+#define CMIB_LAUNCH_MARCH(M, A, R) march_kernel<M, A, R><<<march_grid, MARCH_BLOCK, 0, s>>>(Wl)
+      if (mode == ACC_HONLY) {
+        if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, true, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, true, false); }
+        else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_HONLY, false, true); else CMIB_LAUNCH_MARCH(ACC_HONLY, false, false); }
+      } else {
+        if (agg) { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, true, true); else CMIB_LAUNCH_MARCH(ACC_FULL, true, false); }
+        else { if (prefetch) CMIB_LAUNCH_MARCH(ACC_FULL, false, true); else CMIB_LAUNCH_MARCH(ACC_FULL, false, false); }
+      }
+#undef CMIB_LAUNCH_MARCH
+    }
+    stamp(L);
+    advance_after_march_kernel<<<1, 1, 0, s>>>(Wl.ctl, P.acc);
+    g_launches += 4;
+    ++R.rounds;
+    return 0;
+  };
+  /* a group: `n` rounds, then the control block comes back into one of the lane's two pinned mirrors */
+  auto enqueue_group = [&](int l, int n) -> int {
+    cmib_context::Lane &L = ctx->lane[l];
+    Run &R = run[l];
+    const int slot = R.enq & 1;
+    R.group_first[slot] = R.rounds;
+    R.group_rounds[slot] = n;
+    for (int k = 0; k < n; ++k)
+      if (enqueue_round(l)) return 1;
     if (cudaGetLastError() != cudaSuccess) { fail_cleanup(); CMIB_FAIL("a kernel launch of the shoot failed"); }
-    CUDA_OK(cudaMemcpyAsync(ctx->h_ctl, ctx->ctl.p, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-    CUDA_OK(cudaStreamSynchronize(s));
-    if (ctx->h_ctl[CTL_ERROR]) { fail_cleanup(); CMIB_FAIL("march kernel exceeded its pass limit (internal error)"); }
-    for (int k = 0; k < group; ++k)
-      if (ctx->h_ctl[CTL_STATUS + ((round - 1 - k) % CTL_STATUS_SLOTS)] == 0) done = true;
-    if (ctx->h_ctl[CTL_REMAINING] == 0) primaries_left = false;
+    CUDA_OK(cudaMemcpyAsync(L.h_ctl + slot * CTL_WORDS, L.ctl.p, CTL_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost, L.stream));
+    CUDA_OK(cudaEventRecord(L.group_done[slot], L.stream));
+    ++R.enq;
+    return 0;
+  };
+  /* rounds a lane needs to emit its primaries when nothing is re-emitted (re-emitted packets take room: then
+   * this is a lower bound); one more round finds the queues empty and reports the end */
+  auto rounds_for_primaries = [&](int l) -> int {
+    uint64_t rem = lane_n[l], r = 0;
+    while (rem > 0 && r < 60) {
+      const uint64_t f = round_fill(l, r);
+      rem -= std::min(rem, f);
+      ++r;
+    }
+    return (int)r;
+  };
+  const int group = 4;
+  const uint64_t max_rounds = 100000; /* every round emits min(remaining, room) primaries or shrinks the
+                                       * re-emission population; a sane configuration stays far below */
+  std::deque<int> inflight; /* lanes in the order their groups were enqueued */
+  for (int l = 0; l < nlanes; ++l) {
+    if (enqueue_group(l, std::min(rounds_for_primaries(l) + 1, (int)CTL_STATUS_SLOTS - 1))) return 1;
+    inflight.push_back(l);
   }
-  if (!done) {
-    fail_cleanup();
-    CMIB_FAIL("the shoot did not finish in %llu rounds: packets are still queued (a re-emission probability of 1 "
-              "in a box that cannot be left?)", (unsigned long long)max_rounds);
+  if (can_reemit) /* the number of rounds is not known: keep one group ahead of the read-back */
+    for (int l = 0; l < nlanes; ++l) {
+      if (enqueue_group(l, group)) return 1;
+      inflight.push_back(l);
+    }
+  while (!inflight.empty()) {
+    const int l = inflight.front();
+    inflight.pop_front();
+    cmib_context::Lane &L = ctx->lane[l];
+    Run &R = run[l];
+    const int slot = R.fin & 1;
+    CUDA_OK(cudaEventSynchronize(L.group_done[slot]));
+    ++R.fin;
+    const unsigned long long *h = L.h_ctl + slot * CTL_WORDS;
+    if (h[CTL_ERROR]) { fail_cleanup(); CMIB_FAIL("march kernel exceeded its pass limit (internal error)"); }
+    for (int k = 0; k < R.group_rounds[slot]; ++k)
+      if (h[CTL_STATUS + ((R.group_first[slot] + k) % CTL_STATUS_SLOTS)] == 0) R.done = true;
+    if (h[CTL_REMAINING] == 0) R.primaries_left = false;
+    if (!R.done) {
+      if (R.rounds >= max_rounds) {
+        fail_cleanup();
+        CMIB_FAIL("the shoot did not finish in %llu rounds: packets are still queued (a re-emission probability of 1 "
+                  "in a box that cannot be left?)", (unsigned long long)max_rounds);
+      }
+      if (enqueue_group(l, group)) return 1;
+      inflight.push_back(l);
+    }
   }
-  ctx->shoot_rounds = round;
+  /* every group of every lane has been read back: nothing of this shoot is in flight */
+  ctx->shoot_rounds = run[0].rounds + (nlanes == 2 ? run[1].rounds : 0);
+  ctx->shoot_lanes = nlanes;
   {
-    /* mean walk length of this shoot, for the key layout of the next one */
-    double c0, c1, e0, e1;
-    memcpy(&c0, &ctx->h_ctl[CTL_CROSSINGS0], 8); memcpy(&c1, &ctx->h_ctl[CTL_CROSSINGS], 8);
-    memcpy(&e0, &ctx->h_ctl[CTL_EMISSIONS0], 8); memcpy(&e1, &ctx->h_ctl[CTL_EMISSIONS], 8);
+    /* mean walk length of this shoot, for the key layout of the next one: the counters of the accumulator buffer
+     * as the lane that finished last saw them */
+    double c0, c1 = 0., e0, e1 = 0.;
+    memcpy(&c0, &ctx->lane[0].h_ctl[((run[0].fin - 1) & 1) * CTL_WORDS + CTL_CROSSINGS0], 8);
+    memcpy(&e0, &ctx->lane[0].h_ctl[((run[0].fin - 1) & 1) * CTL_WORDS + CTL_EMISSIONS0], 8);
+    for (int l = 0; l < nlanes; ++l) {
+      const unsigned long long *h = ctx->lane[l].h_ctl + ((run[l].fin - 1) & 1) * CTL_WORDS;
+      double c, e;
+      memcpy(&c, &h[CTL_CROSSINGS], 8); memcpy(&e, &h[CTL_EMISSIONS], 8);
+      if (e > e1) { e1 = e; c1 = c; }
+    }
     if (P.n_packets >= (1ull << 20) && e1 > e0) ctx->walk_cells = (c1 - c0) / (e1 - e0) / 1.5;
   }
   if (P.hot_replicas > 0) {
     const int n = P.src.n_sources * HOT_CELLS * HOT_STRIDE;
-    if (mode == ACC_HONLY) fold_hot_cells_kernel<ACC_HONLY><<<blocks_for(n, 128), 128, 0, s>>>(P);
-    else fold_hot_cells_kernel<ACC_FULL><<<blocks_for(n, 128), 128, 0, s>>>(P);
+    if (mode == ACC_HONLY) fold_hot_cells_kernel<ACC_HONLY><<<blocks_for(n, 128), 128, 0, s0>>>(P);
+    else fold_hot_cells_kernel<ACC_FULL><<<blocks_for(n, 128), 128, 0, s0>>>(P);
     ++g_launches;
     CUDA_OK(cudaGetLastError());
-    CUDA_OK(cudaStreamSynchronize(s));
+    CUDA_OK(cudaStreamSynchronize(s0));
   }
-  for (size_t k = 0; k + 3 < ev_used; k += 4) {
-    float a = 0.f, b = 0.f;
-    cudaEventElapsedTime(&a, ctx->ev_pool[k], ctx->ev_pool[k + 1]);
-    cudaEventElapsedTime(&b, ctx->ev_pool[k + 2], ctx->ev_pool[k + 3]);
-    ctx->prepare_ms += a;
-    ctx->march_ms += b;
+  ctx->prepare_ms = ctx->march_ms = ctx->overlap_ms = 0.;
+  if (ctx->timing) {
+    /* time with an emission kernel (decide, prepare) running, with a march kernel running, and with both
+     * (two lanes): measures of unions of the kernels' intervals on a common clock (the origin event) */
+    std::vector<std::pair<double, double>> prep, march;
+    for (int l = 0; l < nlanes; ++l) {
+      cmib_context::Lane &L = ctx->lane[l];
+      for (size_t k = 0; k + 3 < L.ev_used; k += 4) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 4; ++j) cudaEventElapsedTime(&t[j], ctx->origin_ev, L.ev_pool[k + j]);
+        prep.emplace_back(t[0], t[1]);
+        march.emplace_back(t[2], t[3]);
+      }
+    }
+    merge_intervals(prep);
+    merge_intervals(march);
+    ctx->prepare_ms = interval_measure(prep);
+    ctx->march_ms = interval_measure(march);
+    ctx->overlap_ms = interval_overlap(prep, march);
   }
   return 0;
 }
@@ -750,8 +947,15 @@ int cmib_destroy(cmib_context *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaStreamDestroy(ctx->stream);
-  if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
-  for (cudaEvent_t e : ctx->ev_pool) cudaEventDestroy(e);
+  for (cmib_context::Lane &L : ctx->lane) {
+    if (L.h_ctl) cudaFreeHost(L.h_ctl);
+    for (cudaEvent_t e : L.ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : L.group_done)
+      if (e) cudaEventDestroy(e);
+    if (L.stream && L.stream != ctx->stream) cudaStreamDestroy(L.stream);
+  }
+  for (cudaEvent_t e : {ctx->fork_ev, ctx->join_ev, ctx->origin_ev})
+    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->xev)
     if (e) cudaEventDestroy(e);
   if (ctx->comm) NcclApi::get().CommDestroy(ctx->comm);
@@ -1290,6 +1494,13 @@ int cmib_shoot_timing(cmib_context *ctx, double *prepare_ms, double *march_ms, u
     CUDA_OK(cudaStreamSynchronize(ctx->stream));
     *accumulator_adds = v;
   }
+  return 0;
+}
+
+int cmib_shoot_overlap(cmib_context *ctx, int32_t *lanes, double *overlap_ms) {
+  CHECK_CTX(ctx);
+  if (lanes) *lanes = ctx->shoot_lanes;
+  if (overlap_ms) *overlap_ms = ctx->overlap_ms;
   return 0;
 }
 

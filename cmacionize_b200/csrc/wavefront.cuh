@@ -72,7 +72,8 @@ struct WavefrontParams {
   double *mq;              /* march queue: [NFIELDS][capacity] */
   double *rq;              /* re-emission queue: [RQ_NFIELDS][capacity] */
   double *eq;              /* emission queue: [EQ_NFIELDS][capacity] */
-  uint64_t capacity;
+  uint64_t capacity;       /* stride of the queue arrays */
+  uint64_t fill;           /* entries one round may hold (<= capacity; set per round by the host) */
   /* coherent march (sort == 2): the march queue is read in the order of a key (source | direction of a primary,
    * start position of a re-emitted packet); counting sort: prepare_kernel takes a ticket in its key's bin,
    * sort_scan_* turn the bin counts into offsets, sort_scatter_kernel writes the order */
@@ -384,7 +385,7 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
   const uint64_t n_eq = W.ctl[CTL_EQCOUNT];
   const uint64_t remaining = W.ctl[CTL_REMAINING];
   const uint64_t next_fresh = W.ctl[CTL_NEXT_FRESH];
-  const uint64_t room = cap - n_eq;
+  const uint64_t room = W.fill > n_eq ? W.fill - n_eq : 0;
   const uint64_t n_fresh = remaining < room ? remaining : room;
   const uint64_t n_items = n_eq + n_fresh;
   ShootCounters cnt;
@@ -443,10 +444,10 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
 }
 
 /* bookkeeping after prepare: consume the primaries, empty the re-emission queue */
-__global__ void advance_after_prepare_kernel(unsigned long long *ctl, uint64_t capacity) {
+__global__ void advance_after_prepare_kernel(unsigned long long *ctl, uint64_t fill) {
   const uint64_t n_eq = ctl[CTL_EQCOUNT];
   const uint64_t remaining = ctl[CTL_REMAINING];
-  const uint64_t room = capacity - n_eq;
+  const uint64_t room = fill > n_eq ? fill - n_eq : 0;
   const uint64_t n_fresh = remaining < room ? remaining : room;
   ctl[CTL_REMAINING] = remaining - n_fresh;
   ctl[CTL_NEXT_FRESH] += n_fresh;

@@ -211,6 +211,12 @@ int cmib_shoot_optical_depth(cmib_context *ctx, double *tau_traversed);
 int cmib_set_shoot_timing(cmib_context *ctx, int on);
 int cmib_shoot_timing(cmib_context *ctx, double *prepare_ms, double *march_ms, uint64_t *rounds,
                       double *accumulator_adds);
+/* A large shoot runs as two lanes (two sets of queues on two streams, out of phase) so that the emission kernels
+ * of one lane execute beside the march kernel of the other.  With lanes the times of cmib_shoot_timing are the
+ * durations during which AT LEAST ONE emission kernel (prepare_ms) / march kernel (march_ms) was running (unions of
+ * the kernels' intervals on a common clock); this call adds the number of lanes of the last shoot and the time
+ * during which both kinds ran at once (prepare_ms + march_ms - overlap_ms = time with any of them running). */
+int cmib_shoot_overlap(cmib_context *ctx, int32_t *lanes, double *overlap_ms);
 
 /* test hook: 0 = wavefront pipeline (default, production: prepare/march kernels connected by
  * device queues), 1 = one-thread-per-packet kernel.  Both draw the same packets from the same

@@ -66,5 +66,6 @@ for rep in range(args.repeat):
     ms = e0.elapsed_time(e1)
     print(f"{args.problem}: shoot of {n} packets: {ms:.3f} ms (host {1e3*(t1-t0):.3f} ms) -> {n/ms*1e3:.3e} packets/s, "
           f"{cross/n:.2f} crossings/packet ({cross/ms*1e3:.3e} crossings/s), {emis/n:.3f} emissions/packet; "
-          f"prepare {ctx.shoot_timing()[0]:.3f} ms, march {ctx.shoot_timing()[1]:.3f} ms, rounds {ctx.shoot_timing()[2]}")
+          f"prepare {ctx.shoot_timing()[0]:.3f} ms, march {ctx.shoot_timing()[1]:.3f} ms, rounds {ctx.shoot_timing()[2]}, "
+          f"lanes {ctx.shoot_overlap()[0]}, overlap {ctx.shoot_overlap()[1]:.3f} ms")
 ctx.close()
