@@ -19,7 +19,7 @@ N > 1 is launched by torch.distributed.run (one rank per GPU).  Scaling is STRON
 (IonizationSimulation.cpp:392-397 -> MPICommunicator::distribute): the iteration keeps the configuration's packet
 count and the ranks split it by global packet id; the grid is replicated; the exchange between shoot and update is
 the product's own NCCL code behind the C ABI (include/cmib.h cmib_comm_exchange_and_update: the accumulators are
-summed onto the owners of the cell blocks, every rank updates its block, the opacity records are gathered) — the
+all-reduced, every rank updates the cell chunks it owns, the opacity records are all-gathered) — the
 same calls the C++ driver `CMacIonizeB200 --gpus` makes.  `weak` (N > 1) adds the figure with N x the packets.
 
 One JSON line is printed by rank 0 (schema: task contract + `roofline`, `cpu_baseline`, `e2e`, `clocks`,
@@ -254,8 +254,8 @@ def config_of(name, n_packets, world, scaling="strong"):
     return {"workload": name, "description": w["label"], "grid": f"{nc}^3", "packets_per_iteration": n_packets,
             "physics": w["physics"],
             "parallelism": (f"{world} GPU(s): {scaling} scaling, packets split by global id "
-                            "(MPICommunicator::distribute), replicated grid, accumulators reduced onto cell-block "
-                            "owners, block-wise state update, opacity records gathered (NCCL behind the C ABI)"),
+                            "(MPICommunicator::distribute), replicated grid, accumulators all-reduced, "
+                            "state update of the owned cell chunks, opacity records all-gathered (NCCL behind the C ABI)"),
             "l2_policy": ("cells + accumulators (41 MB) are L2 resident and re-zeroed / rewritten every iteration; each "
                           "step streams 1e8 independent random rays (1.5 - 5 GB of packet queues per round: larger than L2)"
                           if nc == 64 else
@@ -423,14 +423,16 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
 
     # ---- e2e: the same iteration through the C ABI with HOST buffers ----
     # every rank uploads ITS cell block from pinned host memory, the blocks are gathered over NVLink, the rank
-    # shoots its packets, joins the exchange and reads its block of the result back; wall clock between
+    # shoots its packets, joins the exchange and reads the cells it updated back; wall clock between
     # barriers, max over ranks
     if want_e2e:
         nc = ctx.ncells
         b0, b1 = cell_block(nc, rank, world)
         nb = b1 - b0
         pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
-        n_h, T_h, x_h, heat_h = pin(nb), pin(nb), pin(14, nb), pin(2, nb)
+        n_h, T_h, x_h = pin(nb), pin(nb), pin(14, nb)
+        no = ctx.owned_cells()       # the cells this rank updates: chunks dealt round-robin (cmib_owned_cell)
+        n_o, T_o, x_o, heat_o = pin(no), pin(no), pin(14, no), pin(2, no)
         if world > 1:
             ctx.comm_gather_state()
         n0, T0, x0, _ = ctx.download_cells()
@@ -444,7 +446,7 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
                 ctx.upload_cells_block(b0, b1, n_h, T_h, x_h)             # H2D: 16 doubles per cell of the block
                 ctx.comm_gather_cells_all()                               # N > 1: replicate what was uploaded
                 step(loop)
-                ctx.download_cells_block_into(b0, b1, n_h, T_h, x_h, heat_h)  # D2H: 18 doubles per cell of the block
+                ctx.download_cells_owned_into(n_o, T_o, x_o, heat_o)      # D2H: 18 doubles per cell the rank updated
             loop += 1
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0)

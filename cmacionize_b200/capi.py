@@ -63,6 +63,10 @@ def _load() -> C.CDLL:
     lib.cmib_kernel_launch_count.restype = C.c_uint64
     lib.cmib_distribute.restype = C.c_uint64
     lib.cmib_distribute.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    lib.cmib_owned_cell.restype = C.c_uint64
+    lib.cmib_owned_cell.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
+    lib.cmib_owned_cell_count.restype = C.c_uint64
+    lib.cmib_owned_cell_count.argtypes = [C.c_uint64, C.c_int32, C.c_int32]
     lib.cmib_distribute_block.restype = None
     lib.cmib_distribute_block.argtypes = [C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64),
                                           C.POINTER(C.c_uint64)]
@@ -113,6 +117,15 @@ def distribute_block(rank: int, size: int, begin: int, end: int):
     lo, hi = C.c_uint64(), C.c_uint64()
     lib.cmib_distribute_block(rank, size, begin, end, C.byref(lo), C.byref(hi))
     return int(lo.value), int(hi.value)
+
+
+def owned_cell(j: int, size: int, rank: int) -> int:
+    """cell index of work item j of rank `rank`: the multi-GPU state update deals chunks of 1024 cells round-robin"""
+    return int(lib.cmib_owned_cell(j, size, rank))
+
+
+def owned_cell_count(ncells: int, size: int, rank: int) -> int:
+    return int(lib.cmib_owned_cell_count(ncells, size, rank))
 
 
 def comm_unique_id() -> bytes:
@@ -353,6 +366,16 @@ class Context:
     def download_cells_block_into(self, cell_begin, cell_end, n, T, x, heat):
         _check(lib.cmib_download_cells_block(self._h, C.c_uint64(cell_begin), C.c_uint64(cell_end), _p(n), _p(T), _p(x),
                                              _p(heat)))
+
+    def owned_cells(self):
+        """number of cells this rank updates (all of them without a communicator)"""
+        n = C.c_uint64()
+        _check(lib.cmib_comm_owned_cells(self._h, C.byref(n)))
+        return int(n.value)
+
+    def download_cells_owned_into(self, n, T, x, heat):
+        """the cells this rank owns, in work-item order (capi.owned_cell): n, T [n_owned], x [14][n_owned], heat [2][n_owned]"""
+        _check(lib.cmib_download_cells_owned(self._h, _p(n), _p(T), _p(x), _p(heat)))
 
     def measure_scatter_rates(self, n_cells=None):
         """(scattered FP64 RED/s, scattered 16-byte gathers/s) of this device, measured now"""

@@ -102,6 +102,7 @@ struct NcclApi {
   decltype(&ncclCommInitAll) CommInitAll = nullptr;
   decltype(&ncclCommDestroy) CommDestroy = nullptr;
   decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
   decltype(&ncclReduce) Reduce = nullptr;
   decltype(&ncclBroadcast) Broadcast = nullptr;
   decltype(&ncclGroupStart) GroupStart = nullptr;
@@ -124,10 +125,10 @@ private:
     }
 #define CMIB_NCCL_SYM(name) a.name = reinterpret_cast<decltype(a.name)>(dlsym(h, "nccl" #name))
     CMIB_NCCL_SYM(GetUniqueId); CMIB_NCCL_SYM(CommInitRank); CMIB_NCCL_SYM(CommInitAll); CMIB_NCCL_SYM(CommDestroy);
-    CMIB_NCCL_SYM(AllReduce); CMIB_NCCL_SYM(Reduce); CMIB_NCCL_SYM(Broadcast); CMIB_NCCL_SYM(GroupStart);
+    CMIB_NCCL_SYM(AllReduce); CMIB_NCCL_SYM(AllGather); CMIB_NCCL_SYM(Reduce); CMIB_NCCL_SYM(Broadcast); CMIB_NCCL_SYM(GroupStart);
     CMIB_NCCL_SYM(GroupEnd); CMIB_NCCL_SYM(GetErrorString);
 #undef CMIB_NCCL_SYM
-    if (!a.GetUniqueId || !a.CommInitRank || !a.CommInitAll || !a.CommDestroy || !a.AllReduce || !a.Reduce ||
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommInitAll || !a.CommDestroy || !a.AllReduce || !a.AllGather || !a.Reduce ||
         !a.Broadcast || !a.GroupStart || !a.GroupEnd || !a.GetErrorString)
       a.error = "libnccl lacks the expected entry points";
     return a;
@@ -230,6 +231,7 @@ struct cmib_context {
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_size = 1;
   cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr};
+  DevBuf<double> xchg_pack, xchg_all; /* packs of the owned chunks: own, and of all ranks (gathers) */
   double exchange_ms[3] = {0., 0., 0.};
   double walk_cells = 0.; /* mean walk length (cells) of the last large shoot: sizes the direction bins of the sort key */
   size_t l2_bytes = 0;
@@ -1411,11 +1413,25 @@ int cmib_update_state(cmib_context *ctx, uint32_t loop, double totweight) {
   return cmib_update_state_block(ctx, loop, totweight, 0, (uint64_t)ctx->geom.ncells);
 }
 
-int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, uint64_t cell_begin, uint64_t cell_end) {
-  CHECK_CTX(ctx);
-  if (ensure_acc(ctx)) return 1;
-  if (cell_end > (uint64_t)ctx->geom.ncells || cell_begin > cell_end) CMIB_FAIL("cell block outside the grid");
-  if (cell_begin == cell_end) return 0;
+} /* extern "C" */
+
+namespace {
+/* number of work items of rank `rank` of `size` (kernels.cuh owned_cell): its chunks, the last one of the grid
+ * counted in full; and the cells among them that exist */
+int64_t owned_work_items(int64_t ncells, int32_t size, int32_t rank) {
+  const int64_t nchunks = (ncells + OWN_CHUNK - 1) / OWN_CHUNK;
+  return (nchunks > rank ? (nchunks - rank + size - 1) / size : 0) * OWN_CHUNK;
+}
+int64_t owned_cell_count(int64_t ncells, int32_t size, int32_t rank) {
+  const int64_t nw = owned_work_items(ncells, size, rank);
+  if (nw == 0) return 0;
+  const int64_t last = owned_cell(nw - 1, rank, size); /* last cell of the rank's last chunk */
+  return last < ncells ? nw : nw - (last + 1 - ncells);
+}
+
+/* the state update of the cells [cell_begin, cell_end) (own_size <= 1) or of the chunks rank own_rank of own_size owns */
+int update_state_cells(cmib_context *ctx, uint32_t loop, double totweight, uint64_t cell_begin, uint64_t cell_end,
+                       int32_t own_rank, int32_t own_size) {
   UpdateParams P;
   P.geom = ctx->geom;
   P.cells = ctx->cells.p;
@@ -1436,7 +1452,11 @@ int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, 
   P.solve_temperature = (ctx->tp.do_temperature && loop > ctx->tp.min_iterations) ? 1 : 0;
   P.cell_begin = (int64_t)cell_begin;
   P.cell_end = (int64_t)cell_end;
-  const int64_t nc = (int64_t)(cell_end - cell_begin);
+  P.own_rank = own_rank;
+  P.own_size = own_size;
+  P.n_work = (own_size > 1) ? owned_work_items(ctx->geom.ncells, own_size, own_rank) : (int64_t)(cell_end - cell_begin);
+  const int64_t nc = P.n_work;
+  if (nc == 0) return 0;
   const char *simple = getenv("CMIB_UPDATE_SIMPLE");
   if (P.solve_temperature && !(simple && simple[0] == '1')) {
     /* temperature solve: persistent warps with dynamic cell hand-out (kernels.cuh) */
@@ -1447,8 +1467,7 @@ int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, 
       CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->update_blocks_per_sm[ACC_HONLY],
                                                             update_temperature_kernel<ACC_HONLY>, 128, 0));
     }
-    const unsigned long long first = cell_begin;
-    CUDA_OK(cudaMemcpyAsync(ctx->upd_counter.p, &first, sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_OK(cudaMemsetAsync(ctx->upd_counter.p, 0, sizeof(unsigned long long), ctx->stream)); /* next work item */
     int bpm = ctx->update_blocks_per_sm[ctx->acc_mode];
     if (bpm < 1) bpm = 1;
     unsigned grid = (unsigned)(ctx->sm_count * bpm);
@@ -1467,6 +1486,17 @@ int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, 
   CUDA_OK(cudaGetLastError());
   ctx->reemit_prob_valid = false;
   return 0;
+}
+} // namespace
+
+extern "C" {
+
+int cmib_update_state_block(cmib_context *ctx, uint32_t loop, double totweight, uint64_t cell_begin, uint64_t cell_end) {
+  CHECK_CTX(ctx);
+  if (ensure_acc(ctx)) return 1;
+  if (cell_end > (uint64_t)ctx->geom.ncells || cell_begin > cell_end) CMIB_FAIL("cell block outside the grid");
+  if (cell_begin == cell_end) return 0;
+  return update_state_cells(ctx, loop, totweight, cell_begin, cell_end, 0, 1);
 }
 
 int cmib_set_shoot_algorithm(cmib_context *ctx, int algorithm) {
@@ -1637,33 +1667,30 @@ int gather_blocks(cmib_context *ctx, T *array, size_t per_cell) {
   return 0;
 }
 
-/* sum over the ranks: every rank gets the sums of its own cell block (+ the 16 counters on all ranks) */
-int reduce_scatter_accumulators(cmib_context *ctx) {
+/* all-gather of a per-cell array with `per_cell` doubles per cell whose chunks were updated by their owners
+ * (kernels.cuh owned_cell): pack the own chunks, ncclAllGather of the equal-sized packs, scatter the others' */
+int gather_owned(cmib_context *ctx, double *array, int per_cell, bool opacity_records) {
   NcclApi &nccl = NcclApi::get();
-  const uint64_t nc = (uint64_t)ctx->geom.ncells;
-  double *acc = ctx->acc.p;
-  NCCL_OK(nccl.GroupStart());
-  NCCL_OK(nccl.AllReduce(acc, acc, ACC_COUNTERS, ncclDouble, ncclSum, ctx->comm, ctx->stream));
-  for (int r = 0; r < ctx->comm_size; ++r) {
-    uint64_t lo, hi;
-    cmib_distribute_block(r, ctx->comm_size, 0, nc, &lo, &hi);
-    if (hi == lo) continue;
-    if (ctx->acc_mode == ACC_FULL) {
-      double *blk = acc + ACC_COUNTERS + lo * 16;
-      NCCL_OK(nccl.Reduce(blk, blk, (hi - lo) * 16, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
-    } else if (ctx->honly_planar()) {
-      for (int term = 0; term < 2; ++term) {
-        double *blk = acc + ACC_COUNTERS + ctx->honly_offset() + lo + (uint64_t)term * (uint64_t)ctx->honly_term_stride();
-        NCCL_OK(nccl.Reduce(blk, blk, hi - lo, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
-      }
-    } else { /* interleaved / padded records of honly_cell_stride doubles */
-      double *blk = acc + ACC_COUNTERS + lo * (uint64_t)ctx->honly_cell_stride();
-      uint64_t n = (hi - lo) * (uint64_t)ctx->honly_cell_stride();
-      if (r == ctx->comm_size - 1) n = ctx->acc_main_doubles(ACC_HONLY) - (ACC_COUNTERS + lo * (uint64_t)ctx->honly_cell_stride()); /* + the offset tail */
-      NCCL_OK(nccl.Reduce(blk, blk, n, ncclDouble, ncclSum, r, ctx->comm, ctx->stream));
-    }
-  }
-  NCCL_OK(nccl.GroupEnd());
+  const int64_t nc = ctx->geom.ncells;
+  const int32_t size = ctx->comm_size, rank = ctx->comm_rank;
+  const int64_t nw = owned_work_items(nc, size, 0); /* rank 0 owns the most chunks: the common pack size */
+  const size_t pack = (size_t)nw * per_cell;
+  if (ctx->xchg_pack.n < pack) CUDA_OK(ctx->xchg_pack.resize(pack));
+  if (ctx->xchg_all.n < pack * size) CUDA_OK(ctx->xchg_all.resize(pack * size));
+  cudaStream_t s = ctx->stream;
+  if (opacity_records)
+    pack_owned_records_kernel<<<blocks_for(nw, 256), 256, 0, s>>>(nw, nc, rank, size, reinterpret_cast<const CellOpacity *>(array),
+                                                                reinterpret_cast<CellOpacity *>(ctx->xchg_pack.p));
+  else
+    pack_owned_doubles_kernel<<<blocks_for(nw * per_cell, 256), 256, 0, s>>>(nw, nc, rank, size, per_cell, array, ctx->xchg_pack.p);
+  NCCL_OK(nccl.AllGather(ctx->xchg_pack.p, ctx->xchg_all.p, pack, ncclDouble, ctx->comm, s));
+  if (opacity_records)
+    unpack_owned_records_kernel<<<blocks_for(nw * size, 256), 256, 0, s>>>(nw, nc, rank, size, reinterpret_cast<const CellOpacity *>(ctx->xchg_all.p),
+                                                                         ctx->cells.p, ctx->cells_h.p);
+  else
+    unpack_owned_doubles_kernel<<<blocks_for(nw * per_cell * size, 256), 256, 0, s>>>(nw, nc, rank, size, per_cell, ctx->xchg_all.p, array);
+  g_launches += 2;
+  CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -1673,29 +1700,20 @@ extern "C" {
 
 int cmib_comm_exchange_and_update(cmib_context *ctx, uint32_t loop, int allreduce) {
   CHECK_CTX(ctx);
+  (void)allreduce; /* every rank receives all sums (see include/cmib.h) */
   if (ensure_acc(ctx)) return 1;
   if (!ctx->comm || ctx->comm_size == 1) return cmib_update_state(ctx, loop, 0.);
   cudaStream_t s = ctx->stream;
   if (!ctx->xev[0])
     for (int k = 0; k < 4; ++k) CUDA_OK(cudaEventCreate(&ctx->xev[k]));
   CUDA_OK(cudaEventRecord(ctx->xev[0], s));
-  if (allreduce) {
-    NCCL_OK(NcclApi::get().AllReduce(ctx->acc.p, ctx->acc.p, ctx->acc_main_doubles(ctx->acc_mode), ncclDouble, ncclSum, ctx->comm, s));
-  } else if (reduce_scatter_accumulators(ctx)) {
-    return 1;
-  }
+  NCCL_OK(NcclApi::get().AllReduce(ctx->acc.p, ctx->acc.p, ctx->acc_main_doubles(ctx->acc_mode), ncclDouble, ncclSum, ctx->comm, s));
   CUDA_OK(cudaEventRecord(ctx->xev[1], s));
-  uint64_t lo, hi;
-  cmib_distribute_block(ctx->comm_rank, ctx->comm_size, 0, (uint64_t)ctx->geom.ncells, &lo, &hi);
-  if (cmib_update_state_block(ctx, loop, 0., lo, hi)) return 1; /* totweight: the reduced counter on the device */
+  /* totweight: the reduced counter on the device */
+  if (update_state_cells(ctx, loop, 0., 0, (uint64_t)ctx->geom.ncells, ctx->comm_rank, ctx->comm_size)) return 1;
   CUDA_OK(cudaEventRecord(ctx->xev[2], s));
-  if (gather_blocks(ctx, ctx->cells.p, 1)) return 1;
-  /* the compact (n, x_H) copy of the other ranks' blocks: rebuilt from the gathered records (HBM is ~10x NVLink) */
-  const int64_t nc = ctx->geom.ncells;
-  if (lo > 0) rebuild_cells_h_kernel<<<blocks_for((int64_t)lo, 256), 256, 0, s>>>(0, (int64_t)lo, ctx->cells.p, ctx->cells_h.p);
-  if ((int64_t)hi < nc) rebuild_cells_h_kernel<<<blocks_for(nc - (int64_t)hi, 256), 256, 0, s>>>((int64_t)hi, nc, ctx->cells.p, ctx->cells_h.p);
-  g_launches += 2;
-  CUDA_OK(cudaGetLastError());
+  static_assert(sizeof(CellOpacity) == 4 * sizeof(double), "opacity records travel as 4 doubles");
+  if (gather_owned(ctx, reinterpret_cast<double *>(ctx->cells.p), 4, true)) return 1;
   CUDA_OK(cudaEventRecord(ctx->xev[3], s));
   ctx->reemit_prob_valid = false;
   return 0;
@@ -1718,8 +1736,42 @@ int cmib_comm_exchange_timing(cmib_context *ctx, double ms[3]) {
 int cmib_comm_gather_state(cmib_context *ctx) {
   CHECK_CTX(ctx);
   if (!ctx->comm || ctx->comm_size == 1) return 0;
-  if (gather_blocks(ctx, ctx->xmetal.p, 12)) return 1;
-  if (gather_blocks(ctx, ctx->heat_norm.p, 2)) return 1;
+  if (gather_owned(ctx, ctx->xmetal.p, 12, false)) return 1;
+  if (gather_owned(ctx, ctx->heat_norm.p, 2, false)) return 1;
+  return 0;
+}
+
+int cmib_comm_owned_cells(cmib_context *ctx, uint64_t *n_owned) {
+  CHECK_CTX(ctx);
+  if (!n_owned) CMIB_FAIL("null argument");
+  *n_owned = (ctx->comm_size > 1) ? (uint64_t)owned_cell_count(ctx->geom.ncells, ctx->comm_size, ctx->comm_rank) : (uint64_t)ctx->geom.ncells;
+  return 0;
+}
+
+uint64_t cmib_owned_cell(uint64_t j, int32_t size, int32_t rank) {
+  return size > 1 ? (uint64_t)owned_cell((int64_t)j, rank, size) : j;
+}
+
+uint64_t cmib_owned_cell_count(uint64_t ncells, int32_t size, int32_t rank) {
+  return size > 1 ? (uint64_t)owned_cell_count((int64_t)ncells, size, rank) : ncells;
+}
+
+int cmib_download_cells_owned(cmib_context *ctx, double *n, double *T, double *x, double *heat) {
+  CHECK_CTX(ctx);
+  if (ctx->comm_size <= 1) return cmib_download_cells(ctx, n, T, x, heat);
+  const size_t no = (size_t)owned_cell_count(ctx->geom.ncells, ctx->comm_size, ctx->comm_rank);
+  if (no == 0) return 0;
+  if (ctx->stage.n < no * 18) CUDA_OK(ctx->stage.resize(no * 18));
+  double *s = ctx->stage.p;
+  unpack_cells_owned_kernel<<<blocks_for(no, 256), 256, 0, ctx->stream>>>((int64_t)no, ctx->comm_rank, ctx->comm_size, ctx->cells.p,
+                                                                          ctx->xmetal.p, ctx->heat_norm.p, s, s + no, s + 2 * no, s + 16 * no);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  if (n) CUDA_OK(cudaMemcpyAsync(n, s, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (T) CUDA_OK(cudaMemcpyAsync(T, s + no, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (x) CUDA_OK(cudaMemcpyAsync(x, s + 2 * no, no * 14 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (heat) CUDA_OK(cudaMemcpyAsync(heat, s + 16 * no, no * 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

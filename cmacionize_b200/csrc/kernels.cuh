@@ -165,12 +165,29 @@ struct UpdateParams {
   TemperatureParams tp;
   int solve_temperature;
   int64_t cell_begin, cell_end; /* the cell block this launch updates (MPICommunicator::distribute_block) */
+  /* work items j = 0 .. n_work - 1 of this launch.  own_size <= 1: cell = cell_begin + j (a contiguous block).
+   * own_size > 1: the rank's share of a multi-GPU update — the grid is cut into chunks of OWN_CHUNK cells and
+   * chunk c belongs to rank c % own_size, so that the expensive cells (the temperature solve inside the ionised
+   * region) are spread over all ranks; cell = ((j / OWN_CHUNK) * own_size + own_rank) * OWN_CHUNK + j % OWN_CHUNK,
+   * items whose cell lies behind cell_end (the tail of the last chunk) are skipped */
+  int64_t n_work;
+  int32_t own_rank, own_size;
 };
+
+constexpr int64_t OWN_CHUNK = 1024;
+CMIB_HD int64_t owned_cell(int64_t j, int32_t rank, int32_t size) {
+  return ((j / OWN_CHUNK) * size + rank) * OWN_CHUNK + (j % OWN_CHUNK);
+}
+CMIB_D int64_t work_cell(const UpdateParams &P, int64_t j) {
+  return (P.own_size <= 1) ? P.cell_begin + j : owned_cell(j, P.own_rank, P.own_size);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(128)
 update_state_kernel(const __grid_constant__ UpdateParams P) {
-  const int64_t i = P.cell_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t jw = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (jw >= P.n_work) return;
+  const int64_t i = work_cell(P, jw);
   if (i >= P.cell_end) return;
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   /* jfac = L / W, hfac = jfac * h, both divided by the cell volume per cell
@@ -247,7 +264,7 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
   const int role = lane % 3;            /* 0: 1.1 T0, 1: 0.9 T0, 2: T0 */
   const int slot_base = lane - role;    /* first lane of this cell's three */
   const unsigned role0_mask = 0x09249249u; /* lanes 0, 3, ..., 27 */
-  const int64_t ncells = P.cell_end; /* next_cell starts at P.cell_begin */
+  const int64_t nwork = P.n_work; /* next_cell counts work items from 0 */
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   const double jfac = (P.luminosity / totweight) / P.geom.cell_volume;
   const double hfac = ((P.luminosity / totweight) * PLANCK) / P.geom.cell_volume;
@@ -282,9 +299,10 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
       const int leader = __ffs(idle) - 1;
       if (lane == leader) base = atomicAdd(next_cell, (unsigned long long)__popc(idle));
       base = __shfl_sync(0xffffffffu, base, leader);
-      if (base + __popc(idle) >= (unsigned long long)ncells) exhausted = true;
-      const int64_t i = (int64_t)base + __popc(idle & ((1u << slot_base) - 1u));
-      if (in_slot && !has && i < ncells) {
+      if (base + __popc(idle) >= (unsigned long long)nwork) exhausted = true;
+      const int64_t jw = (int64_t)base + __popc(idle & ((1u << slot_base) - 1u));
+      const int64_t i = (jw < nwork) ? work_cell(P, jw) : P.cell_end;
+      if (in_slot && !has && i < P.cell_end) {
         /* the three lanes of the slot load the same cell and begin the same solve */
         double J[NUM_IONS], heat[NUM_HEAT], xprev[NUM_IONS];
         if (MODE == ACC_HONLY) {
@@ -389,6 +407,64 @@ __global__ void unpack_cells_kernel(int64_t ncell, const CellOpacity *cells, con
   for (int k = 0; k < 12; ++k) x[(2 + k) * ncell + i] = xmetal[i * 12 + k];
   heat[i] = heat_norm[2 * i];
   heat[ncell + i] = heat_norm[2 * i + 1];
+}
+
+/* gathers of the owned chunks (UpdateParams): the owner packs its cells' records in work-item order, ncclAllGather
+ * moves the equal-sized packs, every rank scatters the packs of the others back into cell order */
+__global__ void pack_owned_records_kernel(int64_t n_work, int64_t ncells, int32_t rank, int32_t size, const CellOpacity *cells,
+                                          CellOpacity *pack) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_work) return;
+  const int64_t i = owned_cell(j, rank, size);
+  CellOpacity c;
+  c.n = c.xH = c.xHe = c.T = 0.;
+  if (i < ncells) c = cells[i];
+  pack[j] = c;
+}
+__global__ void unpack_owned_records_kernel(int64_t n_work, int64_t ncells, int32_t my_rank, int32_t size, const CellOpacity *packs,
+                                            CellOpacity *cells, double2 *cells_h) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_work * size) return;
+  const int32_t r = (int32_t)(t / n_work);
+  if (r == my_rank) return;
+  const int64_t i = owned_cell(t % n_work, r, size);
+  if (i >= ncells) return;
+  const CellOpacity c = packs[t];
+  cells[i] = c;
+  cells_h[i] = make_double2(c.n, c.xH);
+}
+/* the same for a plain array of `per_cell` doubles per cell (metal fractions, heating terms) */
+__global__ void pack_owned_doubles_kernel(int64_t n_work, int64_t ncells, int32_t rank, int32_t size, int per_cell,
+                                          const double *array, double *pack) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_work * per_cell) return;
+  const int64_t i = owned_cell(t / per_cell, rank, size);
+  pack[t] = (i < ncells) ? array[i * per_cell + t % per_cell] : 0.;
+}
+__global__ void unpack_owned_doubles_kernel(int64_t n_work, int64_t ncells, int32_t my_rank, int32_t size, int per_cell,
+                                            const double *packs, double *array) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_work * per_cell * size) return;
+  const int32_t r = (int32_t)(t / (n_work * per_cell));
+  if (r == my_rank) return;
+  const int64_t u = t % (n_work * per_cell);
+  const int64_t i = owned_cell(u / per_cell, r, size);
+  if (i < ncells) array[i * per_cell + u % per_cell] = packs[t];
+}
+/* host layout of the cells a rank owns, in work-item order (the distributed read-back of an iteration) */
+__global__ void unpack_cells_owned_kernel(int64_t n_owned, int32_t rank, int32_t size, const CellOpacity *cells, const double *xmetal,
+                                          const double *heat_norm, double *n, double *T, double *x, double *heat) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_owned) return;
+  const int64_t i = owned_cell(j, rank, size);
+  const CellOpacity c = cells[i];
+  n[j] = c.n;
+  T[j] = c.T;
+  x[j] = c.xH;
+  x[n_owned + j] = c.xHe;
+  for (int k = 0; k < 12; ++k) x[(2 + k) * n_owned + j] = xmetal[i * 12 + k];
+  heat[j] = heat_norm[2 * i];
+  heat[n_owned + j] = heat_norm[2 * i + 1];
 }
 
 /* compact (n, x_H) copy of the opacity records of cells [lo, hi): rebuilt locally after a gather of the records */

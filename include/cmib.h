@@ -238,7 +238,7 @@ int cmib_stream(cmib_context *ctx, void **stream);
 /* The reference splits an iteration over MPI ranks (src/IonizationSimulation.cpp:392-397, 458-618): every rank
  * shoots distribute(numphoton) packets on a replicated grid, 16 chunked MPI_Allreduce calls sum the per-cell
  * accumulators, every rank updates the cell block distribute_block gives it, and 15 hand-rolled all-gathers
- * rebuild the replicas.  Here one context = one GPU = one rank; the collectives are NCCL calls on the context's
+ * rebuild the replicas.  Same three steps here, with a load-balanced deal of the cells (below).  Here one context = one GPU = one rank; the collectives are NCCL calls on the context's
  * stream (libnccl.so.2 is bound at run time: single-GPU users need no NCCL).
  *
  * cmib_distribute / cmib_distribute_block: MPICommunicator::distribute (MPICommunicator.hpp:207-222) and
@@ -254,16 +254,21 @@ int cmib_comm_unique_id(void *id128);
 int cmib_comm_init_rank(cmib_context *ctx, int32_t size, int32_t rank, const void *id128);
 int cmib_comm_init_all(cmib_context **ctxs, int32_t size);
 int cmib_comm_finalize(cmib_context *ctx);
-/* rank, size and the cell block [begin, end) this context updates (size 1, the whole grid without a communicator) */
+/* rank, size and the cell block [begin, end) of cmib_distribute_block for this rank: the block a distributed caller
+ * uploads (cmib_upload_cells_block) — size 1 and the whole grid without a communicator */
 int cmib_comm_info(cmib_context *ctx, int32_t *rank, int32_t *size, uint64_t *cell_begin, uint64_t *cell_end);
 /* The exchange between cmib_shoot and the next iteration, as ONE call per rank (collective):
- *   1. the accumulators are summed over the ranks — every rank receives the sums of ITS cell block and the 16
- *      leading counters (a reduce-scatter: what the block update needs; `allreduce` != 0 gives every rank all
- *      sums, for callers that read the accumulators back);
- *   2. cmib_update_state on the rank's block (totweight from the reduced counters);
- *   3. the opacity records (n, x_H, x_He, T) of all blocks are gathered on every rank: all a shoot reads.
- * The remaining per-cell state (metal fractions, heating terms) stays distributed — block ownership never
- * changes — until cmib_comm_gather_state is called (before a rank downloads cells it does not own).
+ *   1. the accumulators (and the 16 leading counters) are summed over the ranks: one ncclAllReduce, every rank
+ *      receives all sums (`allreduce` is kept for source compatibility and ignored);
+ *   2. cmib_update_state on the cells the rank OWNS (totweight from the reduced counters).  Ownership is dealt in
+ *      chunks of 1024 cells, chunk c to rank c % size (cmib_owned_cell): the reference's contiguous blocks
+ *      (distribute_block) put the whole ionised region — where the temperature solve iterates — on the middle
+ *      ranks (measured on lexingtonHII20, 8 GPUs: 2.1 ms for the slowest block against 0.6 ms for an eighth of
+ *      the work); the result per cell does not depend on who computes it;
+ *   3. the opacity records (n, x_H, x_He, T) of all chunks are gathered on every rank (equal-sized packs of the
+ *      owned chunks, one ncclAllGather): all a shoot reads.
+ * The remaining per-cell state (metal fractions, heating terms) stays distributed — ownership never changes —
+ * until cmib_comm_gather_state is called (before a rank downloads cells it does not own).
  * Without a communicator the call is cmib_update_state on the whole grid. */
 int cmib_comm_exchange_and_update(cmib_context *ctx, uint32_t loop, int allreduce);
 int cmib_comm_gather_state(cmib_context *ctx);
@@ -278,8 +283,18 @@ int cmib_upload_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cel
                             const double *temperature, const double *ionic_fractions);
 int cmib_download_cells_block(cmib_context *ctx, uint64_t cell_begin, uint64_t cell_end, double *number_density,
                               double *temperature, double *ionic_fractions, double *heating);
-/* all-gather of everything cmib_upload_cells_block wrote (opacity records + metal fractions) */
+/* all-gather of everything cmib_upload_cells_block wrote (opacity records + metal fractions); the blocks are those
+ * of cmib_distribute_block over the communicator */
 int cmib_comm_gather_cells_all(cmib_context *ctx);
+/* the cells a rank owns in the state update: work item j of rank `rank` of `size` is cell cmib_owned_cell(j, size, rank)
+ * (pure functions); cmib_comm_owned_cells = cmib_owned_cell_count of the context's grid and rank;
+ * cmib_download_cells_owned reads the owned cells back in work-item order (field layout of cmib_download_cells with
+ * ncell = the number of owned cells): the distributed read-back of an iteration, no gather needed */
+uint64_t cmib_owned_cell(uint64_t j, int32_t size, int32_t rank);
+uint64_t cmib_owned_cell_count(uint64_t ncells, int32_t size, int32_t rank);
+int cmib_comm_owned_cells(cmib_context *ctx, uint64_t *n_owned);
+int cmib_download_cells_owned(cmib_context *ctx, double *number_density, double *temperature, double *ionic_fractions,
+                              double *heating);
 
 /* ---- measured ceilings of the part (roofline denominators) --------------- */
 /* Scattered FP64 RED/s and scattered 16-byte gathers/s of THIS device on tables of `n_cells` records

@@ -1,9 +1,8 @@
 """CPU tier: the N>1 path on 2 ranks over gloo.  Each rank shoots its shard of the global packet
 ids (host logic check `hc_shoot` of tests/hostcheck standing in for the kernel: same shoot_packet
 code, same Philox streams); the exchange then follows the product's protocol (include/cmib.h
-cmib_comm_exchange_and_update, there on NCCL): the 16 counters are all-reduced, every cell block of
-cmib_distribute_block is reduced onto its owner, the owner updates its block, the blocks are
-broadcast back.  The result must equal the single-rank run: identical counters, sums equal up to
+cmib_comm_exchange_and_update, there on NCCL): the accumulators are all-reduced, every rank updates
+the chunks of cells it owns (cmib_owned_cell), equal-sized packs of the owned chunks are all-gathered.  The result must equal the single-rank run: identical counters, sums equal up to
 summation order, and every rank ends with the same updated grid."""
 import ctypes as C
 import os
@@ -52,29 +51,34 @@ def _update(J, heat):
 def _worker(rank, world, port, lib_path, out):
     import torch
     import torch.distributed as dist
-    from cmacionize_b200.distributed import cell_block, shard_packets
+    from cmacionize_b200 import capi
+    from cmacionize_b200.distributed import shard_packets
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, cnt = shard_packets(NPK, rank, world)
     acc = torch.from_numpy(_shoot(lib_path, lo, cnt))
     ncells = NC ** 3
-    # 1. counters on every rank, each cell block (interleaved J, heat records) on its owner
-    dist.all_reduce(acc[:16], op=dist.ReduceOp.SUM)
+    # 1. the accumulators (counters + interleaved J, heat records) are summed on every rank
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM)
     cells = acc[16:].view(ncells, 2)
-    for r in range(world):
-        b0, b1 = cell_block(ncells, r, world)
-        dist.reduce(cells[b0:b1], dst=r, op=dist.ReduceOp.SUM)
-    # 2. the owner updates its block; 3. blocks go back to everybody
+    # 2. every rank updates the chunks it owns (chunk c of 1024 cells belongs to rank c % world)
     state = torch.full((ncells,), -1., dtype=torch.float64)
-    b0, b1 = cell_block(ncells, rank, world)
-    state[b0:b1] = torch.from_numpy(_update(cells[b0:b1, 0].numpy(), cells[b0:b1, 1].numpy()))
+    n_owned = capi.owned_cell_count(ncells, world, rank)
+    own = np.array([capi.owned_cell(j, world, rank) for j in range(n_owned)])
+    state[own] = torch.from_numpy(_update(cells[own, 0].numpy(), cells[own, 1].numpy()))
+    # 3. equal-sized packs of the owned chunks are all-gathered and scattered back into cell order
+    n_pack = max(capi.owned_cell_count(ncells, world, r) for r in range(world))
+    pack = torch.zeros(n_pack, dtype=torch.float64)
+    pack[:n_owned] = state[own]
+    packs = [torch.empty_like(pack) for _ in range(world)]
+    dist.all_gather(packs, pack)
     for r in range(world):
-        c0, c1 = cell_block(ncells, r, world)
-        dist.broadcast(state[c0:c1], src=r)
+        if r != rank:
+            n_r = capi.owned_cell_count(ncells, world, r)
+            state[np.array([capi.owned_cell(j, world, r) for j in range(n_r)])] = packs[r][:n_r]
     gathered = [torch.empty_like(cells) for _ in range(world)] if rank == 0 else None
-    mine = torch.zeros_like(cells)
-    mine[b0:b1] = cells[b0:b1]
+    mine = cells.clone() if rank == 0 else torch.zeros_like(cells)   # the sums are the same on every rank
     dist.gather(mine, gathered, dst=0)
     states = [torch.empty_like(state) for _ in range(world)] if rank == 0 else None
     dist.gather(state, states, dst=0)
@@ -99,6 +103,22 @@ def test_distribute_matches_the_reference_formulas(cmib):
             assert all(blocks[r][1] == blocks[r + 1][0] for r in range(size - 1))
             assert [b - a for a, b in blocks] == parts
     assert capi.distribute_block(1, 3, 100, 110) == (104, 107)
+
+
+def test_owned_chunks_tile_the_grid(cmib):
+    """cmib_owned_cell / cmib_owned_cell_count: chunks of 1024 cells dealt round-robin; every cell has one owner"""
+    from cmacionize_b200 import capi
+    for ncells in (1, 1023, 1024, 1025, 4096, 16 ** 3, 5000, 64 ** 3 + 7):
+        for size in (1, 2, 3, 8):
+            seen = np.zeros(ncells, int)
+            for r in range(size):
+                n = capi.owned_cell_count(ncells, size, r)
+                cells = np.array([capi.owned_cell(j, size, r) for j in range(n)], dtype=np.int64)
+                assert (cells < ncells).all() and (np.diff(cells) > 0).all()
+                if size > 1:
+                    assert ((cells // 1024) % size == r).all()
+                seen[cells] += 1
+            assert (seen == 1).all()
 
 
 def test_two_rank_shoot_equals_single_rank(hostcheck, cmib, tmp_path):

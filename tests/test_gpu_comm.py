@@ -1,5 +1,5 @@
 """GPU tier, 2 GPUs: the multi-GPU exchange of the C ABI (include/cmib.h cmib_comm_*: NCCL reduce of the
-accumulators onto the owners of the cell blocks, block-wise state update, gather of the opacity records)
+accumulators, state update of the owned cell chunks, all-gather of the opacity records)
 under one process per GPU (torchrun, the launch bench.py uses) against the same iterations on one GPU."""
 import subprocess
 import sys
@@ -79,6 +79,15 @@ nb = b1 - b0
 bn, bT, bx, bh = np.empty(nb), np.empty(nb), np.empty((14, nb)), np.empty((2, nb))
 team.ctx.download_cells_block_into(b0, b1, bn, bT, bx, bh)
 assert np.array_equal(bT, T0[b0:b1] + 1.) and np.array_equal(bn, n0[b0:b1]), 'block download'
+# the distributed read-back: the cells the rank updated, in work-item order, against the full download
+no = team.ctx.owned_cells()
+assert no == capi.owned_cell_count(nc, world, rank)
+own = np.array([capi.owned_cell(j, world, rank) for j in range(no)])
+on, oT, ox, oh = np.empty(no), np.empty(no), np.empty((14, no)), np.empty((2, no))
+_, _, _, h2 = team.ctx.download_cells()
+team.ctx.download_cells_owned_into(on, oT, ox, oh)
+assert np.array_equal(oT, T2[own]) and np.array_equal(on, n2[own]) and np.array_equal(np.nan_to_num(ox), np.nan_to_num(x2[:, own]))
+assert np.array_equal(oh, h2[:, own]), 'owned download'
 team.ctx.comm_finalize()
 dist.barrier()
 if rank == 0:
