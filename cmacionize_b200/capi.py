@@ -305,6 +305,10 @@ class Context:
                                      C.byref(d) if want_adds else None))
         return a.value, b.value, int(r.value), d.value
 
+    def set_packet_conventions(self, conventions):
+        """0: IonizationSimulation (default), 1: TaskBasedIonizationSimulation (include/cmib.h)"""
+        _check(lib.cmib_set_packet_conventions(self._h, C.c_int(conventions)))
+
     def shoot_overlap(self):
         """(lanes of the last shoot, ms during which emission and march kernels ran side by side)"""
         n, o = C.c_int32(), C.c_double()

@@ -244,6 +244,15 @@ struct cmib_context {
   bool timing = false;
   double prepare_ms = 0., march_ms = 0.;
   double nu_H = 0., nu_He = 0.;
+  int conventions = 0; /* CMIB_CONVENTIONS_* */
+  /* the abundance factors the packets carry (SourceModel::fold) follow the abundances and the conventions */
+  void apply_conventions() {
+    static const int element_of_ion[NUM_IONS] = {-1, EL_He, EL_C, EL_C, EL_N, EL_N, EL_N, EL_O, EL_O, EL_Ne, EL_Ne, EL_S, EL_S, EL_S};
+    for (int ion = 0; ion < NUM_IONS; ++ion)
+      src.fold[ion] = (conventions == 1 && ion > 0) ? abund[element_of_ion[ion]] : 1.;
+    src.A_He = abund[EL_He];
+    src.A_He_reemit = (conventions == 1) ? 1. : abund[EL_He];
+  }
 
   int pick_acc_mode() const {
     if (force_full) return ACC_FULL;
@@ -936,6 +945,7 @@ int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
   /* DensityGrid.hpp:219-222 */
   ctx->nu_H = ev_to_hz(13.6);
   ctx->nu_He = ev_to_hz(24.6);
+  ctx->apply_conventions();
   ctx->acc_mode = -1;
   if (ensure_acc(ctx)) {
     delete ctx;
@@ -1052,7 +1062,25 @@ int cmib_set_abundances(cmib_context *ctx, const double *abundances) {
   CHECK_CTX(ctx);
   if (!abundances) CMIB_FAIL("null abundances");
   for (int k = 0; k < NUM_ELEMENTS; ++k) ctx->abund[k] = abundances[k];
-  ctx->src.A_He = abundances[EL_He];
+  ctx->apply_conventions();
+  return 0;
+}
+
+int cmib_set_packet_conventions(cmib_context *ctx, int conventions) {
+  CHECK_CTX(ctx);
+  if (conventions == CMIB_CONVENTIONS_IONIZATION_SIMULATION) {
+    /* DensityGrid.hpp:219-222 */
+    ctx->nu_H = ev_to_hz(13.6);
+    ctx->nu_He = ev_to_hz(24.6);
+  } else if (conventions == CMIB_CONVENTIONS_TASK_BASED) {
+    /* DensitySubGrid.hpp:608-612 */
+    ctx->nu_H = 3.288e15;
+    ctx->nu_He = 5.948e15;
+  } else {
+    CMIB_FAIL("unknown packet conventions %d", conventions);
+  }
+  ctx->conventions = conventions;
+  ctx->apply_conventions();
   return 0;
 }
 
@@ -1455,6 +1483,7 @@ int update_state_cells(cmib_context *ctx, uint32_t loop, double totweight, uint6
   P.cell_end = (int64_t)cell_end;
   P.own_rank = own_rank;
   P.own_size = own_size;
+  P.fold_abundances = (ctx->conventions == 1) ? 1 : 0;
   P.n_work = (own_size > 1) ? owned_work_items(ctx->geom.ncells, own_size, own_rank) : (int64_t)(cell_end - cell_begin);
   const int64_t nc = P.n_work;
   if (nc == 0) return 0;

@@ -172,7 +172,25 @@ struct UpdateParams {
    * items whose cell lies behind cell_end (the tail of the last chunk) are skipped */
   int64_t n_work;
   int32_t own_rank, own_size;
+  /* TaskBasedIonizationSimulation.cpp:932-951: the packets carried abundance-weighted cross sections; the mean
+   * intensities of every ion but H0 are divided by the abundance of the ion's element (where it is positive), the
+   * helium heating term by the helium abundance, before the state is computed */
+  int fold_abundances;
 };
+
+/* element of ion k >= 1 in the order of `Element` (ElementNames.hpp get_element) */
+CMIB_HD int ion_element(int ion) {
+  return (ion == ION_He_n) ? EL_He : (ion <= ION_C_p2) ? EL_C : (ion <= ION_N_p2) ? EL_N : (ion <= ION_O_p1) ? EL_O
+         : (ion <= ION_Ne_p1) ? EL_Ne : EL_S;
+}
+CMIB_HD void unfold_abundances(const double *abund, double *J, double *heat) {
+#pragma unroll
+  for (int ion = 1; ion < NUM_IONS; ++ion) {
+    const double a = abund[ion_element(ion)];
+    if (a > 0.) J[ion] = J[ion] / a;
+  }
+  if (abund[EL_He] > 0.) heat[1] = heat[1] / abund[EL_He];
+}
 
 constexpr int64_t OWN_CHUNK = 1024;
 CMIB_HD int64_t owned_cell(int64_t j, int32_t rank, int32_t size) {
@@ -210,6 +228,7 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
     heat[0] = a[acc_slot(NUM_IONS)];
     heat[1] = a[acc_slot(NUM_IONS + 1)];
   }
+  if (P.fold_abundances) unfold_abundances(P.abund, J, heat);
   CellOpacity c = P.cells[i];
   CellState out;
   if (P.solve_temperature) {
@@ -318,6 +337,7 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
           heat[0] = a[acc_slot(NUM_IONS)];
           heat[1] = a[acc_slot(NUM_IONS + 1)];
         }
+        if (P.fold_abundances) unfold_abundances(P.abund, J, heat);
         const CellOpacity c = P.cells[i];
         xprev[0] = c.xH;
         xprev[1] = c.xHe;

@@ -116,6 +116,13 @@ struct SourceModel {
   double xs_high[NUM_IONS];      /* Bimodal (BimodalCrossSections.hpp:247-254): at and above xs_limit */
   double xs_limit;
   double A_He;
+  /* what the packet carries as sigma[ion]: the cross section times fold[ion].  IonizationSimulation: 1 for every
+   * ion.  TaskBasedIonizationSimulation folds the abundance of the ion's element into the cross section of every ion
+   * but H0 (SourceDiscretePhotonTaskContext.hpp:172-180, PhotonReemitTaskContext.hpp:150-156) and divides the mean
+   * intensities by it before the state update (TaskBasedIonizationSimulation.cpp:932-951); its re-emission decision
+   * then uses a helium abundance of 1 (PhotonReemitTaskContext.hpp:121-127): A_He_reemit */
+  double fold[NUM_IONS];
+  double A_He_reemit;
   /* diffuse re-emission */
   int reemission_kind;
   double fixed_reemission_probability;
@@ -562,18 +569,18 @@ CMIB_HD void packet_cross_sections(const SourceModel &m, double nu, double *sigm
 #pragma unroll 1
     for (int ion = 0; ion < NUM_IONS; ++ion) {
       const double s = verner_cross_section(ion, nu);
-      if (ion < NSIG) sigma[ion] = s;
+      if (ion < NSIG) sigma[ion] = s * m.fold[ion]; /* x * 1 == x: the legacy convention is untouched */
       if (ion == ION_He_n) sHe = s;
     }
     sigma_He_corr = m.A_He * sHe;
   } else if (m.xs_kind == XS_BIMODAL) {
     const bool low = nu < m.xs_limit;
 #pragma unroll
-    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = low ? m.xs_fixed[ion] : m.xs_high[ion];
+    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = (low ? m.xs_fixed[ion] : m.xs_high[ion]) * m.fold[ion];
     sigma_He_corr = m.A_He * (low ? m.xs_fixed[ION_He_n] : m.xs_high[ION_He_n]);
   } else {
 #pragma unroll
-    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = m.xs_fixed[ion];
+    for (int ion = 0; ion < NSIG; ++ion) sigma[ion] = m.xs_fixed[ion] * m.fold[ion];
     sigma_He_corr = m.A_He * m.xs_fixed[ION_He_n];
   }
 }
@@ -588,7 +595,7 @@ CMIB_HD double physical_reemit(const SourceModel &m, double sigma_H, double sigm
                                double xHe, double T, const double *p, Rng &rng, int &type) {
   double nu = 0.;
   const double nH0anuH0 = xH * sigma_H;
-  const double nHe0anuHe0 = xHe * m.A_He * sigma_He;
+  const double nHe0anuHe0 = xHe * m.A_He_reemit * sigma_He;
   const double pHabs = nH0anuH0 / (nH0anuH0 + nHe0anuHe0);
   double x = rng_uniform(rng);
   type = PACKET_ABSORBED;

@@ -89,10 +89,14 @@ public:
    * output folder, diffuse field), the periodicity from `DensitySubGridCreator:periodicity`, and the
    * diffuse re-emission handler exists only when `diffuse field` is true (:338-346).  The task queues,
    * buffers, subgrids and source copies of that driver are CPU scheduling and have no counterpart here
-   * (their keys are read so that they show up in the used-values file).  The packet conventions that
-   * differ inside the reference's task-based code (abundance-weighted cross sections carried by the
-   * packet, DensitySubGrid.hpp:593-612) describe the same physics; results agree with either reference
-   * driver within Monte Carlo noise (tests/test_gpu_benchmarks.py). */
+   * (their keys are read so that they show up in the used-values file).  The packet conventions of that
+   * driver are switched on on the device (cmib_set_packet_conventions: abundance-weighted cross sections
+   * carried by the packet and divided out again before the state update, TaskBasedIonizationSimulation.cpp
+   * :932-951; heating relative to the hard-coded 3.288e15 / 5.948e15 Hz, DensitySubGrid.hpp:593-612; A_He = 1
+   * in the re-emission decision).  What stays as in IonizationSimulation: the arithmetic of the walk
+   * (whole-box coordinates instead of subgrid-relative ones: the same cells, positions equal to rounding) and
+   * the order of a packet's random draws (its own counter-based stream either way).  Pinned on the reference's
+   * own task-based run of lexingtonHII20.param (tests/test_gpu_benchmarks.py). */
   IonizationSimulation(bool write_output, bool every_iteration_output, bool output_statistics, int num_thread,
                        const std::string &parameterfile, const std::vector<int> &devices, Log *log = nullptr,
                        bool task_based = false)
@@ -229,6 +233,7 @@ public:
     for (auto &grid : density_grids_) {
       cmib_context *ctx = grid->context();
       CMIB_CALL(cmib_set_abundances(ctx, abundances_.abundance));
+      CMIB_CALL(cmib_set_packet_conventions(ctx, task_based ? CMIB_CONVENTIONS_TASK_BASED : CMIB_CONVENTIONS_IONIZATION_SIMULATION));
       CMIB_CALL(cross_sections_->set_on(ctx));
       CMIB_CALL(cmib_set_recombination_rates(ctx, recombination_rates_->kind, recombination_rates_->fixed));
       CMIB_CALL(cmib_set_sources(ctx, (int32_t)ns, pos.data(), w.data(), discrete_luminosity));

@@ -107,6 +107,19 @@ int cmib_reset_accumulators(cmib_context *ctx);
 /* ---- plugins ----------------------------------------------------------- */
 /* Abundances (src/Abundances.hpp:53-76): He C N O Ne S relative to H */
 int cmib_set_abundances(cmib_context *ctx, const double abundances[CMIB_NUM_ELEMENTS]);
+/* The reference has two drivers with different conventions for what a packet carries (same physics):
+ *   CMIB_CONVENTIONS_IONIZATION_SIMULATION (default): plain cross sections; heating terms relative to 13.6 eV and
+ *     24.6 eV converted to Hz (src/DensityGrid.hpp:219-222);
+ *   CMIB_CONVENTIONS_TASK_BASED (`CMacIonize --task-based`): the abundance of an ion's element is folded into the cross
+ *     section of every ion but H0 (src/SourceDiscretePhotonTaskContext.hpp:172-180), the mean intensities are divided by
+ *     it again before the state update, the helium heating term by the helium abundance
+ *     (src/TaskBasedIonizationSimulation.cpp:932-951), the re-emission decision uses A_He = 1
+ *     (src/PhotonReemitTaskContext.hpp:121-127), and the heating terms use the hard-coded thresholds 3.288e15 Hz and
+ *     5.948e15 Hz (src/DensitySubGrid.hpp:608-612).
+ * cmib_download_accumulators returns what the shoot accumulated (abundance-weighted under the second convention). */
+#define CMIB_CONVENTIONS_IONIZATION_SIMULATION 0
+#define CMIB_CONVENTIONS_TASK_BASED 1
+int cmib_set_packet_conventions(cmib_context *ctx, int conventions);
 /* CrossSectionsFactory (src/CrossSectionsFactory.hpp:60-80); fixed[14] in m^2 is read
  * for FIXED_VALUE (src/FixedValueCrossSections.hpp), ignored for VERNER */
 int cmib_set_cross_sections(cmib_context *ctx, int kind, const double fixed[CMIB_NUM_IONS]);

@@ -15,7 +15,8 @@ What this does (it does NOT run the reference's CMake build system):
   2. copies the five atomic-data files the path reads into ``oracle/_ref/data``
      (the data-location macros are pointed at a run-time resolver in the
      harness so the .so stays relocatable);
-  3. compiles the 38 sources of SURVEY.md Appendix E *where they lie* under
+  3. compiles the 38 sources of SURVEY.md Appendix E (+ TaskBasedIonizationSimulation.cpp, the reference's other
+     driver, for the f2 parity test) *where they lie* under
      /root/reference/src with the reference's default FP semantics
      (``-std=c++11 -O3 -fopenmp``, no ``-march``, no ``-ffast-math``) plus
      ``oracle/ref_harness.cpp`` and links one shared object.
@@ -49,7 +50,7 @@ PhantomSnapshotDensityFunction PhotonSource PhysicalDiffuseReemissionHandler Pla
 PopStarPhotonSourceSpectrum Signals SPHNGSnapshotDensityFunction SPHNGVoronoiGeneratorDistribution
 TemperatureCalculator VernerCrossSections VernerRecombinationRates WMBasicPhotonSourceSpectrum
 CartesianDensityGrid DensityGrid IonizationSimulation NewVoronoiCellConstructor NewVoronoiGrid
-OldVoronoiCell OldVoronoiGrid VoronoiDensityGrid SPHArrayInterface CMILibrary
+OldVoronoiCell OldVoronoiGrid VoronoiDensityGrid SPHArrayInterface CMILibrary TaskBasedIonizationSimulation
 """.split()
 
 DATA_FILES = ["verner_A.dat", "verner_B.dat", "verner_C.dat",

@@ -403,6 +403,19 @@ def run_paramfile(path, ncells, num_threads=-1, verbose=False):
     return fields, times
 
 
+def run_paramfile_taskbased(path, ncells, num_threads=-1, verbose=False):
+    """Run the reference TaskBasedIonizationSimulation (`CMacIonize --task-based`); fields[32][ncell] in the
+    Cartesian cell order of the whole box: n, T, x[14], J[14] / abundance, heat[2] as the last temperature step left them."""
+    fields = np.zeros((32, ncells))
+    L = lib()
+    L.cmi_ref_run_paramfile_taskbased.restype = C.c_int64
+    n = L.cmi_ref_run_paramfile_taskbased(str(path).encode(), C.c_int(num_threads), C.c_int(1 if verbose else 0),
+                                          _p(fields), C.c_int64(ncells))
+    if n != ncells:
+        raise RuntimeError(f"reference task-based run returned {n} cells, expected {ncells}")
+    return fields
+
+
 class Simulation:
     """The reference IonizationSimulation driven one iteration at a time (probe
     cmi_ref_sim_*: the loop body of IonizationSimulation::run on the reference's objects)."""

@@ -69,6 +69,7 @@
 #include "PhysicalDiffuseReemissionHandler.hpp"
 #include "PlanckPhotonSourceSpectrum.hpp"
 #include "RandomGenerator.hpp"
+#include "TaskBasedIonizationSimulation.hpp"
 #include "SPHArrayInterface.hpp"
 #include "SpiralGalaxyContinuousPhotonSource.hpp"
 #include "TemperatureCalculator.hpp"
@@ -321,8 +322,35 @@ public:
       _out[31 * _n + i] = iv.get_heating(HEATINGTERM_He);
     }
   }
-  virtual void write(DensitySubGridCreator<DensitySubGrid> &, const uint_fast32_t,
-                     ParameterFile &, double) {}
+  /* task-based grid (TaskBasedIonizationSimulation.cpp:1091): the cells of all original subgrids, placed by the
+   * cell midpoint into the Cartesian cell order of the whole box */
+  virtual void write(DensitySubGridCreator<DensitySubGrid> &creator, const uint_fast32_t,
+                     ParameterFile &params, double) {
+    const CoordinateVector<> anchor = params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:anchor");
+    const CoordinateVector<> sides = params.get_physical_vector<QUANTITY_LENGTH>("SimulationBox:sides");
+    const CoordinateVector<int_fast32_t> nc =
+        params.get_value<CoordinateVector<int_fast32_t>>("DensityGrid:number of cells");
+    _n = (int64_t)nc.x() * nc.y() * nc.z();
+    if (_n > _cap) return;
+    for (auto gridit = creator.begin(); gridit != creator.original_end(); ++gridit) {
+      for (auto cellit = (*gridit).begin(); cellit != (*gridit).end(); ++cellit) {
+        const CoordinateVector<> mid = cellit.get_cell_midpoint();
+        const int64_t ix = (int64_t)((mid.x() - anchor.x()) / sides.x() * nc.x());
+        const int64_t iy = (int64_t)((mid.y() - anchor.y()) / sides.y() * nc.y());
+        const int64_t iz = (int64_t)((mid.z() - anchor.z()) / sides.z() * nc.z());
+        const int64_t i = (ix * nc.y() + iy) * nc.z() + iz;
+        const IonizationVariables &iv = cellit.get_ionization_variables();
+        _out[0 * _n + i] = iv.get_number_density();
+        _out[1 * _n + i] = iv.get_temperature();
+        for (int ion = 0; ion < NUMBER_OF_IONNAMES; ++ion) {
+          _out[(2 + ion) * _n + i] = iv.get_ionic_fraction(ion);
+          _out[(16 + ion) * _n + i] = iv.get_mean_intensity(ion);
+        }
+        _out[30 * _n + i] = iv.get_heating(HEATINGTERM_H);
+        _out[31 * _n + i] = iv.get_heating(HEATINGTERM_He);
+      }
+    }
+  }
   virtual void write(DensitySubGridCreator<HydroDensitySubGrid> &, const uint_fast32_t,
                      ParameterFile &, double) {}
 };
@@ -347,6 +375,27 @@ int64_t cmi_ref_run_paramfile(const char *paramfile, int num_threads, int verbos
   return n;
 }
 
+/* f2: the reference's task-based driver (TaskBasedIonizationSimulation.cpp:190-1097: `CMacIonize --task-based`)
+ * on a parameter file; fields as cmi_ref_run_paramfile (J and heat: what the last temperature step left, i.e.
+ * already divided by the abundances, :932-951).  The driver's own writer (built from the parameter file) is
+ * replaced by the capturing one before the run; run() writes through the member, not through its argument (:1091). */
+int64_t cmi_ref_run_paramfile_taskbased(const char *paramfile, int num_threads, int verbose, double *fields,
+                                        int64_t ncell_capacity) {
+  TerminalLog *log = verbose ? new TerminalLog(LOGLEVEL_STATUS) : nullptr;
+  int64_t n = -1;
+  {
+    if (num_threads <= 0) num_threads = omp_get_max_threads();
+    TaskBasedIonizationSimulation simulation(num_threads, paramfile, false, false, log);
+    simulation.initialize();
+    CaptureWriter *writer = new CaptureWriter(fields, ncell_capacity);
+    delete simulation._density_grid_writer;
+    simulation._density_grid_writer = writer; /* deleted by the simulation's destructor */
+    simulation.run(nullptr);
+    n = writer->_n;
+  }
+  delete log;
+  return n;
+}
 
 /* ---------------------------------------------------------------------------
  * Charge transfer (ChargeTransferRates.cpp:44-395).  out is [n][3][14]:

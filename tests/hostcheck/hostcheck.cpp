@@ -269,6 +269,8 @@ void hc_random_photons(const double *anchor, const double *sides, int n_sources,
   }
   m.xs_kind = XS_VERNER;
   m.A_He = A_He;
+  m.A_He_reemit = A_He;
+  for (int k = 0; k < NUM_IONS; ++k) m.fold[k] = 1.; /* IonizationSimulation conventions */
   RanluxRng rng(seed);
   for (int64_t i = 0; i < n; ++i) {
     int isrc;
@@ -287,6 +289,8 @@ void hc_reemit_sequence(double A_He, int seed, int64_t n, const double *xH, cons
   memset(&m, 0, sizeof(m));
   m.xs_kind = XS_VERNER;
   m.A_He = A_He;
+  m.A_He_reemit = A_He;
+  for (int k = 0; k < NUM_IONS; ++k) m.fold[k] = 1.; /* IonizationSimulation conventions */
   m.reemission_kind = REEMISSION_PHYSICAL;
   std::vector<double> hf, ht, hc, hef, het, hec, tf, tc;
   host::build_lyc_table(0, [](double nu) { return verner_cross_section(ION_H_n, nu); }, hf, ht, hc);
@@ -454,6 +458,8 @@ void hc_shoot(const double *anchor, const double *sides, const int32_t *ncell,
   m.xs_kind = iparams[2];
   for (int k = 0; k < NUM_IONS; ++k) m.xs_fixed[k] = xs_fixed ? xs_fixed[k] : 0.;
   m.A_He = dparams[1];
+  m.A_He_reemit = dparams[1];
+  for (int k = 0; k < NUM_IONS; ++k) m.fold[k] = 1.; /* IonizationSimulation conventions */
   m.reemission_kind = iparams[3];
   m.fixed_reemission_probability = dparams[2];
   m.fixed_reemission_frequency = dparams[3];
@@ -547,6 +553,8 @@ void hc_simulation(const double *anchor, const double *sides, const int32_t *nce
   m.spectrum.planck = planck.data();
   m.xs_kind = XS_VERNER;
   m.A_He = abund[EL_He];
+  m.A_He_reemit = abund[EL_He];
+  for (int k = 0; k < NUM_IONS; ++k) m.fold[k] = 1.; /* IonizationSimulation conventions */
   m.reemission_kind = REEMISSION_PHYSICAL;
   host::build_lyc_table(0, [](double nu) { return verner_cross_section(ION_H_n, nu); }, hf, ht, hc);
   host::build_lyc_table(1, [](double nu) { return verner_cross_section(ION_He_n, nu); }, hef, het, hec);

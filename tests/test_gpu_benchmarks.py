@@ -39,20 +39,32 @@ def make_paramfile(tmp_path, name, seed):
     if ov:
         extra += f"  number of photons: {ov[0]}\n  number of iterations: {ov[1]}\n"
     extra += f"\nTaskBasedIonizationSimulation:\n  random seed: {seed}\n  output folder: {tmp_path}\n"
+    if ov:
+        extra += f"  number of photons: {ov[0]}\n  number of iterations: {ov[1]}\n"
+    if CASES[name]["full_physics"]:
+        # the Lexington files switch the diffuse field on through `DiffuseReemissionHandler:`; the task-based driver
+        # has its own switch.  The oracle is built without HDF5: both drivers get the ASCII writer (never used here)
+        extra += "  diffuse field: true\nDensityGridWriter:\n  type: AsciiFile\n"
     pf = tmp_path / f"{name}_{seed}.param"
     pf.write_text(text + extra)
     return pf
 
 
-@pytest.mark.parametrize("name,task_based", [(n, False) for n in CASES] + [("stromgren_diffuse", True)])
+@pytest.mark.parametrize("name,task_based", [(n, False) for n in CASES] + [("stromgren_diffuse", True), ("lexingtonHII20", True)])
 def test_benchmark_parameter_file(host, ref, tmp_path, name, task_based):  # noqa: F811
     """task_based: the same file through the `CMacIonize --task-based` parameter surface
-    (TaskBasedIonizationSimulation: block, diffuse field switch) — same problem, same reference runs."""
+    (TaskBasedIonizationSimulation: block, diffuse field switch) with that driver's packet conventions on the
+    device (cmib_set_packet_conventions).  stromgren_diffuse (A_He = 0: the conventions cannot show) against the
+    IonizationSimulation runs; lexingtonHII20 (He + metals, temperature solve) against two runs of the reference's
+    own TaskBasedIonizationSimulation (oracle probe cmi_ref_run_paramfile_taskbased)."""
     case = CASES[name]
     nc = 64
     runs = []
     for seed in (42, 4242):
-        fields, _ = ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)
+        if task_based and case["full_physics"]:
+            fields = ref.run_paramfile_taskbased(make_paramfile(tmp_path, name, seed), nc ** 3)
+        else:
+            fields, _ = ref.run_paramfile(make_paramfile(tmp_path, name, seed), nc ** 3)
         runs.append(fields)
     sim = host.IonizationSimulation(make_paramfile(tmp_path, name, 42), task_based=task_based)
     assert sim.number_of_photons == (1_000_000 if case["override"] is None else case["override"][0])

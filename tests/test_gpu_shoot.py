@@ -534,3 +534,49 @@ def test_source_configuration_errors(cmib):
             ctx.set_spectrum_table([3.3e15], [1.])
         with pytest.raises(cmib.CmibError, match="do not sum to 1"):
             ctx.set_sources([[0., 0., 0.], [0.1, 0., 0.]], [0.5, 0.4], 1e49)
+
+
+def test_task_based_packet_conventions(cmib):
+    """cmib_set_packet_conventions(TASK_BASED): the packets carry abundance-weighted cross sections and the heating
+    terms use the hard-coded thresholds of DensitySubGrid.hpp:608-612.  Same packets as under the default convention
+    (same Philox streams), so per cell  J_ion(task) = A_element(ion) * J_ion(default),  heat_H(task) = heat_H(default) +
+    (nu_H(13.6 eV) - 3.288e15) * J_H,  heat_He(task) = A_He * (heat_He(default) + (nu_He(24.6 eV) - 5.948e15) * J_He);
+    and the state update divides the abundances out again (TaskBasedIonizationSimulation.cpp:932-951): the
+    ionization-only update gives the same fractions."""
+    from cmacionize_b200 import problems
+    npk = 400_000
+    out = []
+    for conv in (0, 1):
+        prob = problems.lexington(20, ncell=16, n_packets=npk)
+        ctx = prob.ctx
+        ctx.set_packet_conventions(conv)
+        rng = np.random.default_rng(5)
+        x = prob.ionic_fractions.copy()
+        x[0] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-2), ctx.ncells))
+        x[1] = np.exp(rng.uniform(np.log(1e-4), np.log(1e-1), ctx.ncells))
+        ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
+        ctx.reset_accumulators()
+        ctx.update_reemission_probabilities()
+        tw, tc = ctx.shoot(npk, seed=77, iteration=1)
+        J, heat = ctx.download_accumulators()
+        ctx.update_state(1, 0.)
+        n1, T1, x1, h1 = ctx.download_cells()
+        out.append((tw, tc.copy(), J, heat, x1, h1))
+        ctx.close()
+    (tw0, tc0, J0, H0, x0, h0), (tw1, tc1, J1, H1, x1, h1) = out
+    assert tw0 == tw1 and np.array_equal(tc0, tc1)            # every packet met the same fate
+    A = dict(He=0.1, C=2.2e-4, N=4.e-5, O=3.3e-4, Ne=5.e-5, S=9.e-6)
+    el = ["H", "He", "C", "C", "N", "N", "N", "O", "O", "Ne", "Ne", "S", "S", "S"]
+    assert np.abs(J1[0] - J0[0]).max() <= 1e-12 * J0[0].max()
+    for ion in range(1, 14):
+        a = A[el[ion]]
+        assert np.abs(J1[ion] - a * J0[ion]).max() <= 1e-12 * a * J0[ion].max(), ion
+    assert sum(J0[ion].max() > 0. for ion in range(14)) >= 8     # the hard ions see no photon of a 20 000 K star
+    nuH, nuHe = problems.ev_to_hz(13.6), problems.ev_to_hz(24.6)
+    eH = H0[0] + (nuH - 3.288e15) * J0[0]
+    eHe = A["He"] * (H0[1] + (nuHe - 5.948e15) * J0[1])
+    assert np.abs(H1[0] - eH).max() <= 1e-10 * np.abs(eH).max()
+    assert np.abs(H1[1] - eHe).max() <= 1e-10 * np.abs(eHe).max()
+    ok = np.isfinite(x0)
+    assert np.array_equal(ok, np.isfinite(x1))
+    assert np.abs(x1[ok] - x0[ok]).max() <= 1e-10               # ionization-only update: J / A * A to rounding
