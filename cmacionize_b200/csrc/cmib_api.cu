@@ -500,6 +500,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     lane_cap[l] = L.queue_capacity;
     if (!L.ctl.p) {
       CUDA_OK(L.ctl.resize(CTL_WORDS));
+      CUDA_OK(cudaMemsetAsync(L.ctl.p, 0, CTL_WORDS * sizeof(unsigned long long), L.stream));
       CUDA_OK(cudaMallocHost((void **)&L.h_ctl, 2 * CTL_WORDS * sizeof(unsigned long long)));
       for (cudaEvent_t &e : L.group_done) CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
@@ -633,6 +634,8 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   int prefetch_cfg = -1;
   if (const char *e = getenv("CMIB_PREFETCH")) prefetch_cfg = atoi(e) != 0;
   const bool can_reemit = (P.src.reemission_kind != REEMISSION_NONE);
+  int tail_cfg = 1;
+  if (const char *e = getenv("CMIB_TAIL")) tail_cfg = atoi(e) != 0;
 
   /* ---- per-lane state of this shoot ---- */
   struct Run {
@@ -704,6 +707,13 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     Wl.fill = round_fill(l, round);
     stamp(L);
     if (can_reemit && round > 0) {
+      if (tail_cfg) {
+        /* the last generations of re-emitted packets in one launch (a no-op until few enough are left) */
+        const unsigned tail_grid = (unsigned)((TAIL_MAX + TAIL_BLOCK - 1) / TAIL_BLOCK);
+        if (mode == ACC_HONLY) tail_kernel<ACC_HONLY><<<tail_grid, TAIL_BLOCK, 0, s>>>(Wl);
+        else tail_kernel<ACC_FULL><<<tail_grid, TAIL_BLOCK, 0, s>>>(Wl);
+        ++g_launches;
+      }
       reemit_decide_kernel<<<decide_grid, 256, 0, s>>>(Wl);
       ++g_launches;
     }

@@ -141,48 +141,47 @@ CMIB_HD CellOpacity load_cell(const CellOpacity *cells, int64_t cell) {
 #endif
 }
 
-/* the life of one packet drawing from `rng`: the kernels pass the packet's own Philox stream, the CPU-tier
- * test passes the reference's RANLUX stream shared by all packets of a thread, as IonizationPhotonShootJob does */
+/* The walks of one packet until it leaves the box or is absorbed for good (IonizationPhotonShootJob.hpp:135-146:
+ * interact, reemit, repeat).  `s` holds position and direction, sigma / sigma_He_corr / nu / type / weight the packet.
+ * reemit_first = false: the packet has just been emitted and walks first; true: it was absorbed in cell s.last_cell
+ * whose record is `c` (the tail of the wavefront pipeline resumes packets there) and the re-emission decision comes
+ * first. */
 template <int MODE, class Adder, class Rng>
-CMIB_HD void shoot_packet_from(const ShootParams &P, Rng &rng, const Adder &add, ShootCounters &cnt) {
+CMIB_HD void packet_walks(const ShootParams &P, Rng &rng, const Adder &add, ShootCounters &cnt, MarchState &s,
+                          double *sigma, double &sigma_He_corr, double &nu, int &type, double weight, bool reemit_first,
+                          const CellOpacity &c_absorbed) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   const GridGeom &g = P.geom;
   const SourceModel &m = P.src;
-  MarchState s;
-  double sigma[NSIG];
-  double sigma_He_corr;
-  double nu;
-  int type = PACKET_PRIMARY;
-  /* --- PhotonSource::get_random_photon --- */
-  int isrc;
-  emit_primary(m, g, rng, s.px, s.py, s.pz, s.dx, s.dy, s.dz, nu, isrc);
-  const double weight = (isrc >= 0) ? m.discrete_weight : m.continuous_weight;
-  packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
-
+  CellOpacity c = c_absorbed;
   bool alive = true;
+  bool walk = !reemit_first;
   while (alive) {
-    ++cnt.n_emit;
-    s.ix_ = 1. / s.dx;
-    s.iy_ = 1. / s.dy;
-    s.iz_ = 1. / s.dz;
-    s.tau = -log(rng_uniform(rng));
-    const double tau0 = s.tau;
-    march_locate(g, s);
-    const double dnu_H = nu - P.nu_H;
-    const double dnu_He = nu - P.nu_He;
-    CellOpacity c = {0., 0., 0., 0.};
-    bool inside;
-    while ((inside = march_inside(g, s)) && s.tau > 0.) {
-      const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
-      s.last_cell = cell;
-      c = load_cell(P.cells, cell);
-      const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
-      if (c.n > 0.) accumulate<MODE>(add, P, cell, ds, weight, sigma, dnu_H, dnu_He);
-      ++cnt.n_steps;
+    if (walk) {
+      ++cnt.n_emit;
+      s.ix_ = 1. / s.dx;
+      s.iy_ = 1. / s.dy;
+      s.iz_ = 1. / s.dz;
+      s.tau = -log(rng_uniform(rng));
+      const double tau0 = s.tau;
+      march_locate(g, s);
+      const double dnu_H = nu - P.nu_H;
+      const double dnu_He = nu - P.nu_He;
+      c.n = c.xH = c.xHe = c.T = 0.;
+      bool inside;
+      while ((inside = march_inside(g, s)) && s.tau > 0.) {
+        const int64_t cell = long_index(g, s.ix, s.iy, s.iz);
+        s.last_cell = cell;
+        c = load_cell(P.cells, cell);
+        const double ds = march_step(g, s, c.n, c.xH, c.xHe, sigma[0], sigma_He_corr);
+        if (c.n > 0.) accumulate<MODE>(add, P, cell, ds, weight, sigma, dnu_H, dnu_He);
+        ++cnt.n_steps;
+      }
+      /* optical depth traversed by this walk: all of it when absorbed, the used part when it left */
+      cnt.tau_sum += tau0 - ((s.tau > 0.) ? s.tau : 0.);
+      if (!inside) break; /* left the box: keeps its last type */
     }
-    /* optical depth traversed by this walk: all of it when absorbed, the used part when it left */
-    cnt.tau_sum += tau0 - ((s.tau > 0.) ? s.tau : 0.);
-    if (!inside) break; /* left the box: keeps its last type */
+    walk = true;
     /* --- PhotonSource::reemit --- */
     double new_nu = 0.;
     if (m.reemission_kind == REEMISSION_PHYSICAL) {
@@ -214,6 +213,26 @@ CMIB_HD void shoot_packet_from(const ShootParams &P, Rng &rng, const Adder &add,
   cnt.w_tot += weight;
 #pragma unroll
   for (int t = 0; t < NUM_PACKET_TYPES; ++t) cnt.w_type[t] += (t == type) ? weight : 0.;
+}
+
+/* the life of one packet drawing from `rng`: the kernels pass the packet's own Philox stream, the CPU-tier
+ * test passes the reference's RANLUX stream shared by all packets of a thread, as IonizationPhotonShootJob does */
+template <int MODE, class Adder, class Rng>
+CMIB_HD void shoot_packet_from(const ShootParams &P, Rng &rng, const Adder &add, ShootCounters &cnt) {
+  constexpr int NSIG = AccLayout<MODE>::NSIG;
+  const SourceModel &m = P.src;
+  MarchState s;
+  double sigma[NSIG];
+  double sigma_He_corr;
+  double nu;
+  int type = PACKET_PRIMARY;
+  /* --- PhotonSource::get_random_photon --- */
+  int isrc;
+  emit_primary(m, P.geom, rng, s.px, s.py, s.pz, s.dx, s.dy, s.dz, nu, isrc);
+  const double weight = (isrc >= 0) ? m.discrete_weight : m.continuous_weight;
+  packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
+  const CellOpacity none = {0., 0., 0., 0.};
+  packet_walks<MODE>(P, rng, add, cnt, s, sigma, sigma_He_corr, nu, type, weight, false, none);
 }
 
 /* packet `i` of this call (global id P.packet_offset + i) */

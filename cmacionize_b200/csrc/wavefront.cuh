@@ -54,6 +54,7 @@ enum CtlWord : int {
   /* walk statistics of this shoot (bit patterns of doubles): the counters of the accumulator buffer when the shoot
    * began and after the last march, so that the host learns the mean walk length with the read-back it does anyway */
   CTL_CROSSINGS0 = CTL_STATUS + CTL_STATUS_SLOTS, CTL_EMISSIONS0, CTL_CROSSINGS, CTL_EMISSIONS,
+  CTL_TAIL_BLOCKS,  /* CTAs of tail_kernel that have finished (returns to 0 by itself) */
   CTL_WORDS
 };
 
@@ -363,6 +364,72 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
     }
   }
   reduce_counters(P.acc, cnt);
+}
+
+/* ------------------------------------------------------------------------- */
+/* tail: the last generations of re-emitted packets, one thread per packet     */
+/* ------------------------------------------------------------------------- */
+/* Once the primaries are out, every round holds ~0.36 x the packets of the round before (lexingtonHII20): from a few
+ * 1e4 packets on a round costs its fixed price (five launches, one walk latency), ~25 of them per shoot — 1.5 ms of a
+ * 15 ms shoot at 8 GPUs (profiles/r02_exchange.md).  When no primaries remain and the re-emission queue holds at most
+ * TAIL_MAX packets, this kernel follows each of them to its end (packet_walks of shoot.cuh: the very code the
+ * per-packet kernel runs, entered at the re-emission decision) and empties the queue; the round then finds nothing to
+ * emit and the shoot ends.  Launched at the head of every round; a no-op until its condition holds. */
+constexpr unsigned long long TAIL_MAX = 65536;
+constexpr int TAIL_BLOCK = 128;
+struct CountingAdder {
+  uint32_t *n;
+  __device__ __forceinline__ void operator()(double *addr, double v) const {
+    atomicAdd(addr, v);
+    ++*n;
+  }
+};
+template <int MODE>
+__global__ void __launch_bounds__(TAIL_BLOCK)
+tail_kernel(const __grid_constant__ WavefrontParams W) {
+  constexpr int NSIG = AccLayout<MODE>::NSIG;
+  const ShootParams &P = W.sp;
+  const SourceModel &m = P.src;
+  const uint64_t cap = W.capacity;
+  const uint64_t n_re = W.ctl[CTL_RQCOUNT];
+  if (n_re == 0 || n_re > TAIL_MAX || W.ctl[CTL_REMAINING] != 0) return; /* uniform over the grid */
+  ShootCounters cnt;
+  const CountingAdder add = {&cnt.n_red};
+  const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n_re) {
+    MarchState s;
+    s.px = W.rq[RQ_PX * cap + w];
+    s.py = W.rq[RQ_PY * cap + w];
+    s.pz = W.rq[RQ_PZ * cap + w];
+    s.dx = s.dy = s.dz = 0.;
+    double sigma[NSIG];
+#pragma unroll
+    for (int k = 0; k < NSIG; ++k) sigma[k] = 0.;
+    sigma[0] = W.rq[RQ_SIGH * cap + w];
+    if (NSIG > 1) sigma[(NSIG > 1) ? ION_He_n : 0] = W.rq[RQ_SIGHE * cap + w];
+    double sigma_He_corr = 0.; /* set by the cross sections of the re-emitted packet before it is used */
+    s.last_cell = __double_as_longlong(W.rq[RQ_CELL * cap + w]);
+    const uint64_t id = (uint64_t)__double_as_longlong(W.rq[RQ_ID * cap + w]);
+    const uint64_t meta = (uint64_t)__double_as_longlong(W.rq[RQ_META * cap + w]);
+    PacketRng rng;
+    rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
+    int type = meta_type(meta);
+    const double weight = meta_continuous(meta) ? m.continuous_weight : m.discrete_weight;
+    double nu = 0.;
+    const CellOpacity c = load_cell(P.cells, s.last_cell);
+    packet_walks<MODE>(P, rng, add, cnt, s, sigma, sigma_He_corr, nu, type, weight, true, c);
+  }
+  reduce_counters(P.acc, cnt);
+  /* the CTA that finishes last empties the queue (every CTA has read its size by then) */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long done = atomicAdd(&W.ctl[CTL_TAIL_BLOCKS], 1ull);
+    if (done == (unsigned long long)gridDim.x - 1ull) {
+      W.ctl[CTL_TAIL_BLOCKS] = 0ull;
+      W.ctl[CTL_RQCOUNT] = 0ull;
+    }
+  }
 }
 
 /* ------------------------------------------------------------------------- */
