@@ -54,6 +54,21 @@ template <int OFF> CMIB_D unsigned long long lds_u64(uint32_t a) {
 template <int OFF> CMIB_D void sts_u64(uint32_t a, unsigned long long v) {
   asm volatile("st.shared.u64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "l"(v));
 }
+/* queue entries are read once, 8 bytes out of every 32-byte sector (the ordered queue is read through an index):
+ * do not keep them in L1, and let L2 drop them first, so that the cell records and accumulators of the cone the
+ * packets in flight walk through stay resident */
+CMIB_D double ld_queue_f64(const double *p) {
+  double v;
+  asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+               "ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], pol;\n\t}" : "=d"(v) : "l"(p));
+  return v;
+}
+CMIB_D uint32_t ld_queue_u32(const uint32_t *p) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+               "ld.global.L1::no_allocate.L2::cache_hint.u32 %0, [%1], pol;\n\t}" : "=r"(v) : "l"(p));
+  return v;
+}
 CMIB_D uint32_t opaque_u32(uint32_t v) {
   uint32_t r;
   asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
@@ -219,12 +234,12 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
           base = __shfl_sync(0xffffffffu, base, leader);
           if (state == LANE_ABSORBED) {
             double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
-            q[RQ_PX * cap] = fpx; q[RQ_PY * cap] = fpy; q[RQ_PZ * cap] = fpz;
-            q[RQ_SIGH * cap] = HEAT ? lds_f64<PT_SIGH * PT_STRIDE>(pt) : W.uni_sigH;
-            q[RQ_SIGHE * cap] = 0.;
-            q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
-            q[RQ_ID * cap] = __longlong_as_double((long long)lds_u64<PT_ID * PT_STRIDE>(pt));
-            q[RQ_META * cap] = __longlong_as_double((long long)(meta_old & 0xffffffffffull));
+            __stcs(q + RQ_PX * cap, fpx); __stcs(q + RQ_PY * cap, fpy); __stcs(q + RQ_PZ * cap, fpz);
+            __stcs(q + RQ_SIGH * cap, HEAT ? lds_f64<PT_SIGH * PT_STRIDE>(pt) : W.uni_sigH);
+            __stcs(q + RQ_SIGHE * cap, 0.);
+            __stcs(q + RQ_CELL * cap, __longlong_as_double((long long)cell));
+            __stcs(q + RQ_ID * cap, __longlong_as_double((long long)lds_u64<PT_ID * PT_STRIDE>(pt)));
+            __stcs(q + RQ_META * cap, __longlong_as_double((long long)(meta_old & 0xffffffffffull)));
           }
         }
       }
@@ -248,15 +263,15 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
           const uint64_t avail = end - cur;
           const int nfill = __popc(fill_m);
           if (state == LANE_EMPTY && ((fill_m >> lane) & 1u) && (uint64_t)rank < avail) {
-            const uint64_t slot = (uint64_t)W.order[cur + rank];
+            const uint64_t slot = (uint64_t)ld_queue_u32(W.order + cur + rank);
             const double *q = W.mq + slot;
-            px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
-            dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
-            const double nu = q[MQ_NU * cap];
-            tau = q[MQ_TAU * cap];
+            px = ld_queue_f64(q + MQ_PX * cap); py = ld_queue_f64(q + MQ_PY * cap); pz = ld_queue_f64(q + MQ_PZ * cap);
+            dx = ld_queue_f64(q + MQ_DX * cap); dy = ld_queue_f64(q + MQ_DY * cap); dz = ld_queue_f64(q + MQ_DZ * cap);
+            const double nu = ld_queue_f64(q + MQ_NU * cap);
+            tau = ld_queue_f64(q + MQ_TAU * cap);
             sts_f64<PT_TAU0 * PT_STRIDE>(pt, tau);
-            sts_u64<PT_ID * PT_STRIDE>(pt, (unsigned long long)__double_as_longlong(q[MQ_ID * cap]));
-            const unsigned long long meta = (unsigned long long)__double_as_longlong(q[MQ_META * cap]);
+            sts_u64<PT_ID * PT_STRIDE>(pt, (unsigned long long)__double_as_longlong(ld_queue_f64(q + MQ_ID * cap)));
+            const unsigned long long meta = (unsigned long long)__double_as_longlong(ld_queue_f64(q + MQ_META * cap));
             sts_u64<PT_META * PT_STRIDE>(pt, meta);
             hot = 0;
             if (P.hot_replicas > 0) {
@@ -264,7 +279,7 @@ march_lean_kernel(const __grid_constant__ WavefrontParams W) {
               if (isrc >= 0) hot = (uint32_t)(isrc + 1) << 2;
             }
             if (HEAT) {
-              sts_f64<PT_SIGH * PT_STRIDE>(pt, q[MQ_SIGMA * cap]);
+              sts_f64<PT_SIGH * PT_STRIDE>(pt, ld_queue_f64(q + MQ_SIGMA * cap));
               sts_f64<PT_W * PT_STRIDE>(pt, meta_continuous(meta) ? P.src.continuous_weight : P.src.discrete_weight);
               sts_f64<PT_DNU * PT_STRIDE>(pt, nu - P.nu_H);
             }

@@ -232,7 +232,7 @@ __global__ void sort_scatter_kernel(const unsigned long long *ctl, const uint32_
                                     const uint32_t *offs, uint32_t *order) {
   const uint64_t n = ctl[CTL_QCOUNT];
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    order[offs[key[i]] + rank[i]] = (uint32_t)i;
+    order[offs[__ldcs(key + i)] + __ldcs(rank + i)] = (uint32_t)i;
 }
 
 /* meta word of a queue entry: uniforms consumed (32 bits) | packet type (7 bits) | emitted by the
@@ -313,14 +313,14 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
     int type = PACKET_ABSORBED;
     int cont = 0;
     if (w < n_re) {
-      px = W.rq[RQ_PX * cap + w];
-      py = W.rq[RQ_PY * cap + w];
-      pz = W.rq[RQ_PZ * cap + w];
-      const double sigH = W.rq[RQ_SIGH * cap + w];
-      const double sigHe = W.rq[RQ_SIGHE * cap + w];
-      const int64_t cell = __double_as_longlong(W.rq[RQ_CELL * cap + w]);
-      id = (uint64_t)__double_as_longlong(W.rq[RQ_ID * cap + w]);
-      const uint64_t meta = (uint64_t)__double_as_longlong(W.rq[RQ_META * cap + w]);
+      px = __ldcs(W.rq + RQ_PX * cap + w);
+      py = __ldcs(W.rq + RQ_PY * cap + w);
+      pz = __ldcs(W.rq + RQ_PZ * cap + w);
+      const double sigH = __ldcs(W.rq + RQ_SIGH * cap + w);
+      const double sigHe = __ldcs(W.rq + RQ_SIGHE * cap + w);
+      const int64_t cell = __double_as_longlong(__ldcs(W.rq + RQ_CELL * cap + w));
+      id = (uint64_t)__double_as_longlong(__ldcs(W.rq + RQ_ID * cap + w));
+      const uint64_t meta = (uint64_t)__double_as_longlong(__ldcs(W.rq + RQ_META * cap + w));
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
       type = meta_type(meta);
       cont = meta_continuous(meta);
@@ -356,10 +356,10 @@ reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
       base = __shfl_sync(0xffffffffu, base, leader);
       if (emit) {
         double *q = W.eq + (base + __popc(ballot & ((1u << lane) - 1u)));
-        q[EQ_PX * cap] = px; q[EQ_PY * cap] = py; q[EQ_PZ * cap] = pz;
-        q[EQ_NU * cap] = nu;
-        q[EQ_ID * cap] = __longlong_as_double((long long)id);
-        q[EQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type | cont));
+        __stcs(q + EQ_PX * cap, px); __stcs(q + EQ_PY * cap, py); __stcs(q + EQ_PZ * cap, pz);
+        __stcs(q + EQ_NU * cap, nu);
+        __stcs(q + EQ_ID * cap, __longlong_as_double((long long)id));
+        __stcs(q + EQ_META * cap, __longlong_as_double((long long)pack_meta(rng_save(rng), type | cont)));
       }
     }
   }
@@ -398,19 +398,19 @@ tail_kernel(const __grid_constant__ WavefrontParams W) {
   const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < n_re) {
     MarchState s;
-    s.px = W.rq[RQ_PX * cap + w];
-    s.py = W.rq[RQ_PY * cap + w];
-    s.pz = W.rq[RQ_PZ * cap + w];
+    s.px = __ldcs(W.rq + RQ_PX * cap + w);
+    s.py = __ldcs(W.rq + RQ_PY * cap + w);
+    s.pz = __ldcs(W.rq + RQ_PZ * cap + w);
     s.dx = s.dy = s.dz = 0.;
     double sigma[NSIG];
 #pragma unroll
     for (int k = 0; k < NSIG; ++k) sigma[k] = 0.;
-    sigma[0] = W.rq[RQ_SIGH * cap + w];
-    if (NSIG > 1) sigma[(NSIG > 1) ? ION_He_n : 0] = W.rq[RQ_SIGHE * cap + w];
+    sigma[0] = __ldcs(W.rq + RQ_SIGH * cap + w);
+    if (NSIG > 1) sigma[(NSIG > 1) ? ION_He_n : 0] = __ldcs(W.rq + RQ_SIGHE * cap + w);
     double sigma_He_corr = 0.; /* set by the cross sections of the re-emitted packet before it is used */
-    s.last_cell = __double_as_longlong(W.rq[RQ_CELL * cap + w]);
-    const uint64_t id = (uint64_t)__double_as_longlong(W.rq[RQ_ID * cap + w]);
-    const uint64_t meta = (uint64_t)__double_as_longlong(W.rq[RQ_META * cap + w]);
+    s.last_cell = __double_as_longlong(__ldcs(W.rq + RQ_CELL * cap + w));
+    const uint64_t id = (uint64_t)__double_as_longlong(__ldcs(W.rq + RQ_ID * cap + w));
+    const uint64_t meta = (uint64_t)__double_as_longlong(__ldcs(W.rq + RQ_META * cap + w));
     PacketRng rng;
     rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
     int type = meta_type(meta);
@@ -464,12 +464,12 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     int type = PACKET_PRIMARY; /* | META_CONTINUOUS */
     int isrc_key = -1; /* source index of a primary of a discrete source, -1 otherwise */
     if (w < n_eq) {
-      px = W.eq[EQ_PX * cap + w];
-      py = W.eq[EQ_PY * cap + w];
-      pz = W.eq[EQ_PZ * cap + w];
-      nu = W.eq[EQ_NU * cap + w];
-      id = (uint64_t)__double_as_longlong(W.eq[EQ_ID * cap + w]);
-      const uint64_t meta = (uint64_t)__double_as_longlong(W.eq[EQ_META * cap + w]);
+      px = __ldcs(W.eq + EQ_PX * cap + w);
+      py = __ldcs(W.eq + EQ_PY * cap + w);
+      pz = __ldcs(W.eq + EQ_PZ * cap + w);
+      nu = __ldcs(W.eq + EQ_NU * cap + w);
+      id = (uint64_t)__double_as_longlong(__ldcs(W.eq + EQ_ID * cap + w));
+      const uint64_t meta = (uint64_t)__double_as_longlong(__ldcs(W.eq + EQ_META * cap + w));
       rng_restore(rng, P.seed, P.iteration, id, (uint32_t)meta);
       type = meta_type(meta) | meta_continuous(meta);
       random_direction(rng, dx, dy, dz);
@@ -485,15 +485,16 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
     packet_cross_sections<NSIG>(m, nu, sigma, sigma_He_corr);
     const double u_tau = rng_uniform(rng);
     const double tau = -log(u_tau);
+    /* streaming stores: a queue entry is read once, by the march, after the rest of the round has been written */
     double *q = W.mq + w;
-    q[MQ_PX * cap] = px; q[MQ_PY * cap] = py; q[MQ_PZ * cap] = pz;
-    q[MQ_DX * cap] = dx; q[MQ_DY * cap] = dy; q[MQ_DZ * cap] = dz;
-    q[MQ_NU * cap] = nu; q[MQ_TAU * cap] = tau;
-    q[MQ_ID * cap] = __longlong_as_double((long long)id);
-    q[MQ_META * cap] = __longlong_as_double((long long)pack_meta(rng_save(rng), type, isrc_key));
+    __stcs(q + MQ_PX * cap, px); __stcs(q + MQ_PY * cap, py); __stcs(q + MQ_PZ * cap, pz);
+    __stcs(q + MQ_DX * cap, dx); __stcs(q + MQ_DY * cap, dy); __stcs(q + MQ_DZ * cap, dz);
+    __stcs(q + MQ_NU * cap, nu); __stcs(q + MQ_TAU * cap, tau);
+    __stcs(q + MQ_ID * cap, __longlong_as_double((long long)id));
+    __stcs(q + MQ_META * cap, __longlong_as_double((long long)pack_meta(rng_save(rng), type, isrc_key)));
 #pragma unroll
-    for (int k = 0; k < NSIG; ++k) q[(MQ_SIGMA + k) * cap] = sigma[k];
-    if (MODE == ACC_FULL) q[(MQ_SIGMA + NSIG) * cap] = sigma_He_corr;
+    for (int k = 0; k < NSIG; ++k) __stcs(q + (MQ_SIGMA + k) * cap, sigma[k]);
+    if (MODE == ACC_FULL) __stcs(q + (MQ_SIGMA + NSIG) * cap, sigma_He_corr);
     if (W.sort == 2) {
       /* [re-emitted] [source | direction, or position] [optical-depth bin]: neighbours in key order leave in nearly
        * the same direction AND carry nearly the same optical depth, i.e. they are absorbed near the same place: the
@@ -503,8 +504,8 @@ prepare_kernel(const __grid_constant__ WavefrontParams W) {
                        ? (((uint32_t)isrc_key << W.fine_dir_bits) | (fine_direction_key(dx, dy, dz) >> (22 - W.fine_dir_bits)))
                        : ((1u << kb) | (fine_position_key(P.geom, px, py, pz) >> (30 - kb)));
       k = (k << W.tau_bits) | (uint32_t)min((int)(u_tau * (double)(1 << W.tau_bits)), (1 << W.tau_bits) - 1);
-      W.key[w] = k;
-      W.rank[w] = atomicAdd(&W.hist[k], 1u); /* a ticket inside the bin: counting sort without a second pass */
+      __stcs(W.key + w, k);
+      __stcs(W.rank + w, atomicAdd(&W.hist[k], 1u)); /* a ticket inside the bin: counting sort without a second pass */
     }
   }
   reduce_counters(P.acc, cnt);
@@ -765,12 +766,12 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           base = __shfl_sync(0xffffffffu, base, leader);
           if (state == LANE_ABSORBED) {
             double *q = W.rq + (base + __popc(ab & ((1u << lane) - 1u)));
-            q[RQ_PX * cap] = fpx; q[RQ_PY * cap] = fpy; q[RQ_PZ * cap] = fpz;
-            q[RQ_SIGH * cap] = sigH;
-            q[RQ_SIGHE * cap] = (MODE == ACC_FULL) ? s_sig[NMETAL][tid] : 0.;
-            q[RQ_CELL * cap] = __longlong_as_double((long long)cell);
-            q[RQ_ID * cap] = __longlong_as_double((long long)s_id[tid]);
-            q[RQ_META * cap] = __longlong_as_double((long long)(s_meta[tid] & 0xffffffffffull));
+            __stcs(q + RQ_PX * cap, fpx); __stcs(q + RQ_PY * cap, fpy); __stcs(q + RQ_PZ * cap, fpz);
+            __stcs(q + RQ_SIGH * cap, sigH);
+            __stcs(q + RQ_SIGHE * cap, (MODE == ACC_FULL) ? s_sig[NMETAL][tid] : 0.);
+            __stcs(q + RQ_CELL * cap, __longlong_as_double((long long)cell));
+            __stcs(q + RQ_ID * cap, __longlong_as_double((long long)s_id[tid]));
+            __stcs(q + RQ_META * cap, __longlong_as_double((long long)(s_meta[tid] & 0xffffffffffull)));
           }
         }
       }
@@ -800,13 +801,14 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
           if (state == LANE_EMPTY && ((fill_m >> lane) & 1u) && (uint64_t)rank < avail) {
             const uint64_t slot = W.sort ? (uint64_t)W.order[cur + rank] : (cur + rank);
             const double *q = W.mq + slot;
-            px = q[MQ_PX * cap]; py = q[MQ_PY * cap]; pz = q[MQ_PZ * cap];
-            dx = q[MQ_DX * cap]; dy = q[MQ_DY * cap]; dz = q[MQ_DZ * cap];
-            const double nu = q[MQ_NU * cap];
-            tau = q[MQ_TAU * cap];
+            /* streaming loads: a queue entry is read once */
+            px = __ldcs(q + MQ_PX * cap); py = __ldcs(q + MQ_PY * cap); pz = __ldcs(q + MQ_PZ * cap);
+            dx = __ldcs(q + MQ_DX * cap); dy = __ldcs(q + MQ_DY * cap); dz = __ldcs(q + MQ_DZ * cap);
+            const double nu = __ldcs(q + MQ_NU * cap);
+            tau = __ldcs(q + MQ_TAU * cap);
             s_tau0[tid] = tau;
-            s_id[tid] = (unsigned long long)__double_as_longlong(q[MQ_ID * cap]);
-            s_meta[tid] = (unsigned long long)__double_as_longlong(q[MQ_META * cap]);
+            s_id[tid] = (unsigned long long)__double_as_longlong(__ldcs(q + MQ_ID * cap));
+            s_meta[tid] = (unsigned long long)__double_as_longlong(__ldcs(q + MQ_META * cap));
             hot = 0;
             if (P.hot_replicas > 0) {
               const int isrc = meta_source(s_meta[tid]);
@@ -815,14 +817,14 @@ march_kernel(const __grid_constant__ WavefrontParams W) {
                 hot_cell = P.src_cell[isrc];
               }
             }
-            sigH = q[MQ_SIGMA * cap];
+            sigH = __ldcs(q + MQ_SIGMA * cap);
             mask = meta_continuous(s_meta[tid]) ? MASK_CONTINUOUS : 0u;
             if (MODE == ACC_FULL) {
-              s_sig[NMETAL][tid] = q[(MQ_SIGMA + 1) * cap];
-              sigHe_corr = q[(MQ_SIGMA + NSIG) * cap];
+              s_sig[NMETAL][tid] = __ldcs(q + (MQ_SIGMA + 1) * cap);
+              sigHe_corr = __ldcs(q + (MQ_SIGMA + NSIG) * cap);
 #pragma unroll
               for (int k = 0; k < NMETAL; ++k) {
-                const double v = q[(MQ_SIGMA + 2 + k) * cap];
+                const double v = __ldcs(q + (MQ_SIGMA + 2 + k) * cap);
                 s_sig[k][tid] = v;
                 mask |= (v != 0.) ? (1u << (2 + k)) : 0u;
               }
