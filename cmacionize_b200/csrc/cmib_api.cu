@@ -1494,6 +1494,8 @@ int update_state_cells(cmib_context *ctx, uint32_t loop, double totweight, uint6
   P.own_rank = own_rank;
   P.own_size = own_size;
   P.fold_abundances = (ctx->conventions == 1) ? 1 : 0;
+  P.lc_wide_max_pairs = LC_WIDE_MAX_PAIRS;
+  if (const char *e = getenv("CMIB_LC_WIDE")) P.lc_wide_max_pairs = atoi(e);
   P.n_work = (own_size > 1) ? owned_work_items(ctx->geom.ncells, own_size, own_rank) : (int64_t)(cell_end - cell_begin);
   const int64_t nc = P.n_work;
   if (nc == 0) return 0;

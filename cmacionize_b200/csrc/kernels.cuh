@@ -176,6 +176,8 @@ struct UpdateParams {
    * intensities of every ion but H0 are divided by the abundance of the ion's element (where it is positive), the
    * helium heating term by the helium abundance, before the state is computed */
   int fold_abundances;
+  int lc_wide_max_pairs; /* update_temperature_kernel: line cooling warp-wide when a warp holds at most this many
+                          * (cell, temperature) pairs (LC_WIDE_MAX_PAIRS; 0 = never, CMIB_LC_WIDE for A/B runs) */
 };
 
 /* element of ion k >= 1 in the order of `Element` (ElementNames.hpp get_element) */
@@ -275,15 +277,79 @@ update_state_kernel(const __grid_constant__ UpdateParams P) {
  * path is three times shorter here.  The arithmetic per cell is unchanged (bitwise equal to the
  * per-cell kernel, tests/test_gpu_simulation.py).
  */
+/*
+ * Line cooling of the LAST cell of a warp, warp-wide.  A cell that runs many secant iterations is a chain of balance
+ * evaluations, and two thirds of the instructions (one third of the latency) of an evaluation is the line cooling: ten five-level systems (10 collision strengths,
+ * 10 Boltzmann factors, a 5 x 5 solve each) and three two-level ones, one after the other on the cell's lane.  While a
+ * warp is full that is the right shape (every lane is busy); when only a few (cell, temperature) pairs are left the other
+ * lanes idle and the chain is what the whole state update waits for (profiles/r02_exchange.md: 2.0 ms for an eighth of
+ * the cells at 8 GPUs).  Here up to three pairs per round are served by ten lanes each: lane k of a group evaluates
+ * five-level element k (lanes 0-2 also two-level element k) for its pair from the pair's T, n_e and abundances
+ * (shuffles), the owner collects the 13 terms and adds them in the order of line_cooling().  Every term is computed by
+ * the code line_cooling() runs (line_cooling_term5 / term2), only on another lane and with the table read from shared
+ * memory (the lanes of a warp read different elements): the result is bit-identical.
+ *   pairs: lanes that hold a pair; has: this lane does; T, ne, ab: the pair's inputs (BalanceMid). */
+constexpr int LC_WIDE_MAX_PAIRS = 3; /* the three temperatures of ONE cell: a single round.  Measured (lexingtonHII20 64^3,
+                                      * mean state update over 24 iterations): never 4.13 ms, 3 pairs 3.47 ms, 9 pairs 3.61 ms;
+                                      * an iteration with a 100-iteration cell 9.3 -> 6.8 ms (profiles/r02_update.md) */
+__device__ __noinline__ double line_cooling_wide(const double *s_tab, unsigned pairs, bool has, double T, double ne, const double *ab) {
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / 10, k = lane - 10 * g; /* group 3 = lanes 30, 31: no work */
+  const LcTablePtr tab = {s_tab};
+  double result = 0.;
+  unsigned todo = pairs;
+  while (todo != 0u) {
+    const int o0 = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const int o1 = todo ? __ffs(todo) - 1 : -1;
+    if (todo) todo &= todo - 1u;
+    const int o2 = todo ? __ffs(todo) - 1 : -1;
+    if (todo) todo &= todo - 1u;
+    const int src = (g == 0) ? o0 : ((g == 1) ? o1 : ((g == 2) ? o2 : -1));
+    const int from = (src < 0) ? lane : src;
+    const double Ts = __shfl_sync(full, T, from), nes = __shfl_sync(full, ne, from);
+    double ab5 = 0., ab2 = 0.;
+#pragma unroll
+    for (int i = 0; i < LC_NUM; ++i) {
+      const double v = __shfl_sync(full, ab[i], from);
+      if (i == k) ab5 = v;
+      if (i == LC_NUM5 + k) ab2 = v;
+    }
+    double t5 = 0., t2 = 0.;
+    if (src >= 0 && nes != 0.) {
+      const double prefactor = tab[LC_OFF_PREFACTOR] * nes / sqrt(Ts);
+      const double Tinv = 1. / Ts;
+      const double logT = log(Ts);
+      t5 = line_cooling_term5(tab, k, prefactor, Ts, Tinv, logT, ab5);
+      if (k < 3) t2 = line_cooling_term2(tab, k, prefactor, Ts, Tinv, logT, ab2);
+    }
+    /* owners collect: group of the owner = its rank in this round */
+    const int mine = (lane == o0) ? 0 : ((lane == o1) ? 10 : ((lane == o2) ? 20 : -1));
+    const int base = (mine < 0) ? 0 : mine;
+    double cooling = 0.;
+#pragma unroll
+    for (int e = 0; e < LC_NUM5; ++e) cooling += __shfl_sync(full, t5, base + e);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) cooling += __shfl_sync(full, t2, base + i);
+    if (mine >= 0 && has) result = (ne == 0.) ? 1.e-99 : cooling;
+  }
+  return result;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128)
 update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long long *next_cell) {
+  __shared__ double s_lc_tab[LC_TABLE_SIZE];
+  for (int i = threadIdx.x; i < LC_TABLE_SIZE; i += blockDim.x) s_lc_tab[i] = CMIB_TBL(LINECOOLING)[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const bool in_slot = lane < 30;
   const int role = lane % 3;            /* 0: 1.1 T0, 1: 0.9 T0, 2: T0 */
   const int slot_base = lane - role;    /* first lane of this cell's three */
   const unsigned role0_mask = 0x09249249u; /* lanes 0, 3, ..., 27 */
   const int64_t nwork = P.n_work; /* next_cell counts work items from 0 */
+  const int wide_max = P.lc_wide_max_pairs;
   const double totweight = (P.totweight > 0.) ? P.totweight : P.acc[0];
   const double jfac = (P.luminosity / totweight) / P.geom.cell_volume;
   const double hfac = ((P.luminosity / totweight) * PLANCK) / P.geom.cell_volume;
@@ -369,10 +435,25 @@ update_temperature_kernel(const __grid_constant__ UpdateParams P, unsigned long 
     }
     /* ---- one balance evaluation per lane: the slot's three temperatures side by side ---- */
     double h0e = 0., he0e = 0., gain = 0., loss = 0.;
+    BalanceMid mid;
+    mid.T = 1.; mid.ne = 0.;
+#pragma unroll
+    for (int i = 0; i < LC_NUM; ++i) mid.ab[i] = 0.;
     if (has) {
       const double Te = (role == 0) ? 1.1 * S.T0 : ((role == 1) ? 0.9 * S.T0 : S.T0);
-      cooling_heating_balance(h0e, he0e, gain, loss, Te, ntot, midz, j, P.abund, h, P.tp.pahfac, S.crfac,
-                              P.tp.crscale, P.rr, out.x);
+      balance_before_line_cooling(h0e, he0e, gain, mid, Te, ntot, midz, j, P.abund, h, P.tp.pahfac, S.crfac, P.tp.crscale,
+                                  P.rr, out.x);
+    }
+    {
+      /* line cooling: per lane while the warp is busy, warp-wide for its last pairs */
+      const unsigned pairs = __ballot_sync(0xffffffffu, has);
+      double cooling = 0.;
+      if (__popc(pairs) > wide_max) {
+        if (has) cooling = line_cooling(mid.T, mid.ne, mid.ab);
+      } else {
+        cooling = line_cooling_wide(s_lc_tab, pairs, has, mid.T, mid.ne, mid.ab);
+      }
+      if (has) balance_after_line_cooling(gain, loss, cooling, mid);
     }
     /* exchange within the slot (all lanes take part in the shuffles) */
     const double gain1 = __shfl_sync(0xffffffffu, gain, slot_base), loss1 = __shfl_sync(0xffffffffu, loss, slot_base);

@@ -93,25 +93,40 @@ CMIB_HD int solve5(double A[5][5], double B[5]) {
   return 0;
 }
 
-CMIB_HD double collision_strength(const double *c, double prefactor, double T, double Tinv,
-                                  double logT) {
-  return prefactor * powl(T, logT, 1. + c[0]) *
-         (c[1] + c[2] * Tinv + c[3] * logT + c[4] * T * (1. + (c[5] - 1.) * powl(T, logT, c[6])));
+/* where the table is read from: __constant__ memory when all lanes of a warp evaluate the same ion at the same time (the
+ * constant-cache broadcast), a plain pointer (shared memory copy) when the lanes of a warp evaluate DIFFERENT ions
+ * (line_cooling_wide of kernels.cuh) */
+struct LcTableConst {
+  CMIB_HD double operator[](int i) const { return CMIB_TBL(LINECOOLING)[i]; }
+};
+struct LcTablePtr {
+  const double *p;
+  CMIB_HD double operator[](int i) const { return p[i]; }
+};
+
+/* c = offset of the 7 fit coefficients of the transition */
+template <class Tab>
+CMIB_HD double collision_strength(const Tab &tab, int c, double prefactor, double T, double Tinv, double logT) {
+  return prefactor * powl(T, logT, 1. + tab[c]) *
+         (tab[c + 1] + tab[c + 2] * Tinv + tab[c + 3] * logT + tab[c + 4] * T * (1. + (tab[c + 5] - 1.) * powl(T, logT, tab[c + 6])));
 }
 
 /* level populations of five-level element e; returns solver status */
-CMIB_HD int five_level_populations(int e, double prefactor, double T, double Tinv, double logT,
+template <class Tab>
+CMIB_HD int five_level_populations(const Tab &tab, int e, double prefactor, double T, double Tinv, double logT,
                                    double pop[5]) {
-  const double *tab = CMIB_TBL(LINECOOLING);
-  const double *A = tab + LC_OFF_A5 + 10 * e;
-  const double *E = tab + LC_OFF_E5 + 10 * e;
-  const double *w = tab + LC_OFF_W5 + 5 * e;
+  const int oA = LC_OFF_A5 + 10 * e, oE = LC_OFF_E5 + 10 * e, ow = LC_OFF_W5 + 5 * e;
+  double A[10], w[5];
+#pragma unroll
+  for (int t = 0; t < 10; ++t) A[t] = tab[oA + t];
+#pragma unroll
+  for (int t = 0; t < 5; ++t) w[t] = tab[ow + t];
   double dn[10], up[10];
 #pragma unroll
   for (int t = 0; t < 10; ++t) {
-    const double cs = collision_strength(tab + LC_OFF_CS5 + (e * 10 + t) * 7, prefactor, T, Tinv, logT);
+    const double cs = collision_strength(tab, LC_OFF_CS5 + (e * 10 + t) * 7, prefactor, T, Tinv, logT);
     dn[t] = cs;
-    up[t] = cs * exp(-E[t] * Tinv);
+    up[t] = cs * exp(-tab[oE + t] * Tinv);
   }
   double M[5][5];
 #pragma unroll
@@ -142,42 +157,56 @@ CMIB_HD int five_level_populations(int e, double prefactor, double T, double Tin
   M[4][4] = -(A[3] + A[6] + A[8] + A[9] + w[4] * (dn[3] + dn[6] + dn[8] + dn[9]));
   return solve5(M, pop);
 }
+CMIB_HD int five_level_populations(int e, double prefactor, double T, double Tinv, double logT, double pop[5]) {
+  return five_level_populations(LcTableConst(), e, prefactor, T, Tinv, logT, pop);
+}
 
-CMIB_HD double two_level_population(int i, double prefactor, double T, double Tinv, double logT) {
-  const double *tab = CMIB_TBL(LINECOOLING);
+template <class Tab>
+CMIB_HD double two_level_population(const Tab &tab, int i, double prefactor, double T, double Tinv, double logT) {
   const double ksi = tab[LC_OFF_E2 + i];
   const double A = tab[LC_OFF_A2 + i];
-  const double cs = collision_strength(tab + LC_OFF_CS2 + 7 * i, prefactor, T, Tinv, logT);
+  const double cs = collision_strength(tab, LC_OFF_CS2 + 7 * i, prefactor, T, Tinv, logT);
   const double inv_omega_1 = tab[LC_OFF_W2 + 2 * i];
   const double inv_omega_2 = tab[LC_OFF_W2 + 2 * i + 1];
   const double Texp = exp(-ksi * Tinv);
   return cs * Texp * inv_omega_1 / (A + cs * (inv_omega_2 + Texp * inv_omega_1));
 }
+CMIB_HD double two_level_population(int i, double prefactor, double T, double Tinv, double logT) {
+  return two_level_population(LcTableConst(), i, prefactor, T, Tinv, logT);
+}
+
+/* the terms of the cooling sum (LineCoolingData::get_cooling, LineCoolingData.cpp): five-level element e, two-level
+ * element i; abund = the abundance of that element's ion */
+template <class Tab>
+CMIB_HD double line_cooling_term5(const Tab &tab, int e, double prefactor, double T, double Tinv, double logT, double abund) {
+  double pop[5];
+  five_level_populations(tab, e, prefactor, T, Tinv, logT, pop);
+  const int oA = LC_OFF_A5 + 10 * e, oE = LC_OFF_E5 + 10 * e;
+  const double cl2 = pop[1] * tab[oA] * tab[oE];
+  const double cl3 = pop[2] * (tab[oA + 1] * tab[oE + 1] + tab[oA + 4] * tab[oE + 4]);
+  const double cl4 = pop[3] * (tab[oA + 2] * tab[oE + 2] + tab[oA + 5] * tab[oE + 5] + tab[oA + 7] * tab[oE + 7]);
+  const double cl5 = pop[4] * (tab[oA + 3] * tab[oE + 3] + tab[oA + 6] * tab[oE + 6] + tab[oA + 8] * tab[oE + 8] + tab[oA + 9] * tab[oE + 9]);
+  return abund * BOLTZMANN * (cl2 + cl3 + cl4 + cl5);
+}
+template <class Tab>
+CMIB_HD double line_cooling_term2(const Tab &tab, int i, double prefactor, double T, double Tinv, double logT, double abund) {
+  const double lp = two_level_population(tab, i, prefactor, T, Tinv, logT);
+  return abund * BOLTZMANN * tab[LC_OFF_E2 + i] * tab[LC_OFF_A2 + i] * lp;
+}
 
 /* cooling rate per hydrogen atom (J s^-1); abund in LineCoolElement order */
 CMIB_HD double line_cooling(double T, double ne, const double abund[LC_NUM]) {
   if (ne == 0.) return 1.e-99;
-  const double *tab = CMIB_TBL(LINECOOLING);
+  const LcTableConst tab;
   const double prefactor = tab[LC_OFF_PREFACTOR] * ne / sqrt(T);
   const double Tinv = 1. / T;
   const double logT = log(T);
   double cooling = 0.;
-  for (int e = 0; e < LC_NUM5; ++e) {
-    double pop[5];
-    five_level_populations(e, prefactor, T, Tinv, logT, pop);
-    const double *A = tab + LC_OFF_A5 + 10 * e;
-    const double *E = tab + LC_OFF_E5 + 10 * e;
-    const double cl2 = pop[1] * A[0] * E[0];
-    const double cl3 = pop[2] * (A[1] * E[1] + A[4] * E[4]);
-    const double cl4 = pop[3] * (A[2] * E[2] + A[5] * E[5] + A[7] * E[7]);
-    const double cl5 = pop[4] * (A[3] * E[3] + A[6] * E[6] + A[8] * E[8] + A[9] * E[9]);
-    cooling += abund[e] * BOLTZMANN * (cl2 + cl3 + cl4 + cl5);
-  }
-  for (int i = 0; i < 3; ++i) {
-    const double lp = two_level_population(i, prefactor, T, Tinv, logT);
-    cooling += abund[LC_NUM5 + i] * BOLTZMANN * tab[LC_OFF_E2 + i] * tab[LC_OFF_A2 + i] * lp;
-  }
+  for (int e = 0; e < LC_NUM5; ++e) cooling += line_cooling_term5(tab, e, prefactor, T, Tinv, logT, abund[e]);
+  for (int i = 0; i < 3; ++i) cooling += line_cooling_term2(tab, i, prefactor, T, Tinv, logT, abund[LC_NUM5 + i]);
   return cooling;
 }
+
+constexpr int LC_TABLE_SIZE = LC_OFF_PREFACTOR + 1;
 
 } // namespace cmib

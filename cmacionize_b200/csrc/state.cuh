@@ -242,10 +242,17 @@ CMIB_HD void cell_ionization_state(double jfac, double hfac, const double *J, co
 
 /* heating/cooling balance at temperature T.  j[14], h[2] normalised.  Writes the
  * 12 metal fractions into xm (index by Ion). */
-CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, double &loss, double T,
-                                     double n, double midz, const double *j, const double *abund,
-                                     const double *h, double pahfac, double crfac, double crscale,
-                                     const RecombinationModel &rr, double *xm) {
+/* what the balance hands from its first half (ionization states, heating) over the line cooling to its second half
+ * (the remaining cooling terms): the kernel evaluates the line cooling of its last cells warp-wide in between */
+struct BalanceMid {
+  double T, n, ne, nenhp, nenhep, sqrtT, logT;
+  double ab[LC_NUM];
+};
+
+CMIB_HD void balance_before_line_cooling(double &h0, double &he0, double &gain, BalanceMid &mid, double T, double n,
+                                         double midz, const double *j, const double *abund, const double *h,
+                                         double pahfac, double crfac, double crscale, const RecombinationModel &rr,
+                                         double *xm) {
   const double alphaH = recombination_rate(rr, ION_H_n, T);
   const double alphaHe = recombination_rate(rr, ION_He_n, T);
   const double jH = j[ION_H_n];
@@ -281,7 +288,7 @@ CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, doub
   const double nhe0 = n * he0 * AHe;
   ionization_states_metals(j + 2, ne, T, T4, nh0, nhe0, nhp, rr, xm);
 
-  double ab[LC_NUM];
+  double *ab = mid.ab;
   ab[LC_CII] = abund[EL_C] * (1. - xm[ION_C_p1] - xm[ION_C_p2]);
   ab[LC_CIII] = abund[EL_C] * xm[ION_C_p1];
   ab[LC_NI] = abund[EL_N] * (1. - xm[ION_N_n] - xm[ION_N_p1] - xm[ION_N_p2]);
@@ -295,8 +302,13 @@ CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, doub
   ab[LC_SII] = abund[EL_S] * (1. - xm[ION_S_p1] - xm[ION_S_p2] - xm[ION_S_p3]);
   ab[LC_SIII] = abund[EL_S] * xm[ION_S_p1];
   ab[LC_SIV] = abund[EL_S] * xm[ION_S_p2];
+  mid.T = T; mid.n = n; mid.ne = ne; mid.nenhp = nenhp; mid.nenhep = nenhep; mid.sqrtT = sqrtT; mid.logT = logT;
+}
 
-  loss = line_cooling(T, ne, ab) * n;
+/* cooling = the line cooling per hydrogen atom (line_cooling(mid.T, mid.ne, mid.ab)) */
+CMIB_HD void balance_after_line_cooling(double &gain, double &loss, double cooling, const BalanceMid &mid) {
+  const double T = mid.T, sqrtT = mid.sqrtT, logT = mid.logT, nenhp = mid.nenhp, nenhep = mid.nenhep;
+  loss = cooling * mid.n;
 
   const double c = 5.5 - logT;
   const double gff = 1.1 + 0.34 * exp(-c * c / 3.);
@@ -306,6 +318,15 @@ CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, doub
   loss += Lhp + Lhep;
   loss = (loss < 0.) ? 0. : loss; /* std::max(loss, 0.) */
   gain = (gain < 0.) ? 0. : gain;
+}
+
+CMIB_HD void cooling_heating_balance(double &h0, double &he0, double &gain, double &loss, double T,
+                                     double n, double midz, const double *j, const double *abund,
+                                     const double *h, double pahfac, double crfac, double crscale,
+                                     const RecombinationModel &rr, double *xm) {
+  BalanceMid mid;
+  balance_before_line_cooling(h0, he0, gain, mid, T, n, midz, j, abund, h, pahfac, crfac, crscale, rr, xm);
+  balance_after_line_cooling(gain, loss, line_cooling(mid.T, mid.ne, mid.ab), mid);
 }
 
 CMIB_HD void set_neutral_T(CellState &out) {
