@@ -466,13 +466,14 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
     const int want_bits = std::min(src_bits + dir_bits + 4, 24) + 2;
     coherent_round = std::min<uint64_t>(std::max<uint64_t>(1ull << want_bits, 1ull << 24), 1ull << 26);
   }
-  /* lanes: two for large shoots (four rounds or more) of the coherent march when its key is content with 16 Mi
-   * rounds (few sources): that walk is bound by instruction issue with stalls that the emission and sort kernels of
-   * the other lane fill (stromgren 256^3, 1e9 packets: 764 -> 704 ms).  One lane where the walk is latency bound and
-   * needs the largest rounds (clumpy 256^3, 16 sources: 1040 vs 1043 ms), where walk and emission compete for the
-   * same unit (lexingtonHII20 64^3, both on L1TEX: 98.4 vs 98.9 ms) and for small shoots, where halving the rounds
-   * costs more coherence than the overlap returns (profiles/r02_lanes.md).  CMIB_LANES overrides */
-  int nlanes = (sort == 2 && coherent_round <= (1ull << 24) && P.n_packets >= 4 * coherent_round) ? 2 : 1;
+  /* lanes: one.  Two lanes (CMIB_LANES=2: half grids, out of phase, so that emission and sort of one lane run beside
+   * the walk of the other) were worth +8 % on the one-source 256^3 grid while the queue writes of prepare_kernel still
+   * pushed the cone's cells out of L2 (stromgren 256^3, 1e9 packets: 764 -> 704 ms); with streaming queue stores the
+   * serial emission costs 5 % of the shoot and two lanes return 1 % (696 vs 689 ms), nothing on clumpy 256^3 (latency
+   * bound, needs the largest rounds) and nothing on lexingtonHII20 64^3 (walk and emission both live on L1TEX:
+   * 98.4 vs 98.9 ms) — profiles/r02_lanes.md.  One lane keeps the march kernel alone on the machine, which is also
+   * what its roofline figure assumes. */
+  int nlanes = 1;
   if (const char *e = getenv("CMIB_LANES")) nlanes = atoi(e) == 2 ? 2 : 1;
   if (P.n_packets < 2048) nlanes = 1;
   uint64_t lane_n[2] = {P.n_packets, 0};
