@@ -282,22 +282,27 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     x[1] = np.exp(rng.uniform(np.log(1e-5), np.log(1e-1), ctx.ncells))
     ctx.upload_cells(prob.number_density, np.where(prob.number_density > 0, 7500., 0.), x)
     results = []
-    # sort 1 = ordered queue read by the plain kernel, 2 = the coherent march (ordered queue + in-warp sums)
-    for algorithm, capacity, sort in ((1, None, 0), (0, None, 0), (0, 4096, 0), (0, 1024, 0), (0, None, 1), (0, 2048, 1),
-                                      (0, None, 2), (0, 2048, 2), (0, 1024, 2)):
+    # sort 1 = ordered queue read by the plain kernel, 2 = the coherent march (ordered queue + in-warp sums);
+    # lanes 2 = two sets of queues on two streams, out of phase; tail 0 = the last generations of re-emitted packets
+    # round by round instead of in the tail kernel
+    for algorithm, capacity, sort, lanes, tail in ((1, None, 0, 1, 1), (0, None, 0, 1, 1), (0, 4096, 0, 1, 1), (0, 1024, 0, 1, 0),
+                                                   (0, None, 1, 1, 1), (0, 2048, 1, 1, 1), (0, None, 2, 1, 1), (0, 2048, 2, 1, 1),
+                                                   (0, 1024, 2, 1, 0), (0, 2048, 0, 2, 1), (0, 2048, 2, 2, 1), (0, None, 2, 2, 0)):
         if capacity is None:
             os.environ.pop("CMIB_QUEUE_CAPACITY", None)
         else:
             os.environ["CMIB_QUEUE_CAPACITY"] = str(capacity)
         os.environ["CMIB_SORT"] = str(sort)   # coherence sort of the march queue (wavefront.cuh)
+        os.environ["CMIB_LANES"] = str(lanes)
+        os.environ["CMIB_TAIL"] = str(tail)
         ctx.set_shoot_algorithm(algorithm)
         ctx.reset_accumulators()
         ctx.update_reemission_probabilities()
         tw, tc = ctx.shoot(npk, packet_offset=1000, seed=99, iteration=4)
         J, heat = ctx.download_accumulators()
         results.append((tw, tc, ctx.shoot_statistics(), J, heat))
-    os.environ.pop("CMIB_QUEUE_CAPACITY", None)
-    os.environ.pop("CMIB_SORT", None)
+    for k in ("CMIB_QUEUE_CAPACITY", "CMIB_SORT", "CMIB_LANES", "CMIB_TAIL"):
+        os.environ.pop(k, None)
     ctx.close()
     tw0, tc0, st0, J0, h0 = results[0]
     if config in ("continuous", "distant_star"):
