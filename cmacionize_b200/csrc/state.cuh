@@ -1,7 +1,13 @@
 /*
  * state.cuh — per-cell ionization-state and temperature solve.
  *
- * Behavioural contract:
+ * The closed forms below (H/He balance, the metal ladders, the heating/cooling balance) are a TRANSLITERATION of the
+ * reference's arithmetic, operation for operation and in its order: the results have to be bit-equal on the
+ * reference's random stream (tests/test_host_physics.py: a whole simulation, all cells, all 14 fractions), which
+ * leaves no freedom in the expressions.  What is this repository's own is around them: the resumable per-cell state
+ * machine (TemperatureSolve), three lanes per cell, the warp-wide line cooling of a warp's last cell (kernels.cuh).
+ *
+ * Reference code restated here:
  *   IonizationStateCalculator::calculate_ionization_state(jfac,hfac,cell)
  *                                   /root/reference/src/IonizationStateCalculator.cpp:70-272
  *   ::compute_ionization_states_hydrogen_helium                     ...:649-753
@@ -12,7 +18,7 @@
  *   TemperatureCalculator::calculate_temperature(cell,...)          ...:567-931
  *   grid-level dispatch (do_T && loop > min_iter)                   ...:944-970
  *
- * One thread owns one cell; everything stays in registers.  All quirks of the
+ * All quirks of the
  * reference that affect the result are kept: the
  * neutral branch of the ionization-only path sets N0/O0/Ne0 fractions to 1 while
  * the temperature path sets them to 0, the metals written by the LAST balance
