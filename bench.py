@@ -422,29 +422,24 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
            "roofline": roofline, "phases_ms": phases, "gpu_launches": int(launches), "clocks": clocks.summary()}
 
     # ---- e2e: the same iteration through the C ABI with HOST buffers ----
-    # every rank uploads ITS cell block from pinned host memory, the blocks are gathered over NVLink, the rank
-    # shoots its packets, joins the exchange and reads the cells it updated back; wall clock between
+    # every rank uploads the cells it owns from pinned host memory, their opacity records are gathered over NVLink,
+    # the rank shoots its packets, joins the exchange and reads the cells it updated back; wall clock between
     # barriers, max over ranks
     if want_e2e:
         nc = ctx.ncells
-        b0, b1 = cell_block(nc, rank, world)
-        nb = b1 - b0
         pin = lambda *shape: torch.empty(*shape, dtype=torch.float64).pin_memory().numpy()
-        n_h, T_h, x_h = pin(nb), pin(nb), pin(14, nb)
         no = ctx.owned_cells()       # the cells this rank updates: chunks dealt round-robin (cmib_owned_cell)
         n_o, T_o, x_o, heat_o = pin(no), pin(no), pin(14, no), pin(2, no)
         if world > 1:
             ctx.comm_gather_state()
-        n0, T0, x0, _ = ctx.download_cells()
-        n_h[:] = n0[b0:b1]; T_h[:] = T0[b0:b1]; x_h[:] = x0[:, b0:b1]
-        del n0, T0, x0
+        ctx.download_cells_owned_into(n_o, T_o, x_o, heat_o)
         e2e_steps = max(2, min(steps, 3))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             with torch.cuda.stream(stream):
-                ctx.upload_cells_block(b0, b1, n_h, T_h, x_h)             # H2D: 16 doubles per cell of the block
-                ctx.comm_gather_cells_all()                               # N > 1: replicate what was uploaded
+                ctx.upload_cells_owned(n_o, T_o, x_o)                     # H2D: 16 doubles per owned cell
+                ctx.comm_gather_owned_cells()                             # N > 1: replicate the opacity records
                 step(loop)
                 ctx.download_cells_owned_into(n_o, T_o, x_o, heat_o)      # D2H: 18 doubles per cell the rank updated
             loop += 1
@@ -452,7 +447,7 @@ def run_workload(name, n_packets, args, rank, world, local_rank, steps, warmup, 
         dt = max_over_ranks(time.perf_counter() - t0)
         rec["e2e"] = {"value": n_packets * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * 8 * nc,
                       "d2h_bytes_per_step": 18 * 8 * nc, "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
-                      "note": "bytes are totals over the ranks: every rank moves its own cell block"}
+                      "note": "bytes are totals over the ranks: every rank moves the cells it owns"}
     else:
         rec["e2e"] = None
     if world > 1:

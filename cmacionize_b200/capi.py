@@ -377,6 +377,13 @@ class Context:
         _check(lib.cmib_comm_owned_cells(self._h, C.byref(n)))
         return int(n.value)
 
+    def upload_cells_owned(self, n, T, x):
+        """host arrays hold ONLY the owned cells in work-item order: n, T [n_owned], x [14][n_owned]"""
+        _check(lib.cmib_upload_cells_owned(self._h, _p(n), _p(T), _p(x)))
+
+    def comm_gather_owned_cells(self):
+        _check(lib.cmib_comm_gather_owned_cells(self._h))
+
     def download_cells_owned_into(self, n, T, x, heat):
         """the cells this rank owns, in work-item order (capi.owned_cell): n, T [n_owned], x [14][n_owned], heat [2][n_owned]"""
         _check(lib.cmib_download_cells_owned(self._h, _p(n), _p(T), _p(x), _p(heat)))

@@ -1799,6 +1799,34 @@ uint64_t cmib_owned_cell_count(uint64_t ncells, int32_t size, int32_t rank) {
   return size > 1 ? (uint64_t)owned_cell_count((int64_t)ncells, size, rank) : ncells;
 }
 
+int cmib_upload_cells_owned(cmib_context *ctx, const double *n, const double *T, const double *x) {
+  CHECK_CTX(ctx);
+  if (ctx->comm_size <= 1) return cmib_upload_cells(ctx, n, T, x, nullptr);
+  if (!n || !T || !x) CMIB_FAIL("null cell array");
+  const size_t no = (size_t)owned_cell_count(ctx->geom.ncells, ctx->comm_size, ctx->comm_rank);
+  if (no == 0) return 0;
+  if (ctx->stage.n < no * 18) CUDA_OK(ctx->stage.resize(no * 18));
+  double *s = ctx->stage.p;
+  CUDA_OK(cudaMemcpyAsync(s, n, no * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + no, T, no * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(cudaMemcpyAsync(s + 2 * no, x, no * 14 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  pack_cells_owned_kernel<<<blocks_for(no, 256), 256, 0, ctx->stream>>>((int64_t)no, ctx->comm_rank, ctx->comm_size, s, s + no, s + 2 * no,
+                                                                        ctx->cells.p, ctx->cells_h.p, ctx->xmetal.p);
+  ++g_launches;
+  CUDA_OK(cudaGetLastError());
+  ctx->reemit_prob_valid = false;
+  CUDA_OK(cudaStreamSynchronize(ctx->stream)); /* host arrays may be reused on return */
+  return 0;
+}
+
+int cmib_comm_gather_owned_cells(cmib_context *ctx) {
+  CHECK_CTX(ctx);
+  if (!ctx->comm || ctx->comm_size == 1) return 0;
+  if (gather_owned(ctx, reinterpret_cast<double *>(ctx->cells.p), 4, true)) return 1;
+  ctx->reemit_prob_valid = false;
+  return 0;
+}
+
 int cmib_download_cells_owned(cmib_context *ctx, double *n, double *T, double *x, double *heat) {
   CHECK_CTX(ctx);
   if (ctx->comm_size <= 1) return cmib_download_cells(ctx, n, T, x, heat);

@@ -552,6 +552,22 @@ __global__ void unpack_owned_doubles_kernel(int64_t n_work, int64_t ncells, int3
   const int64_t i = owned_cell(u / per_cell, r, size);
   if (i < ncells) array[i * per_cell + u % per_cell] = packs[t];
 }
+/* host arrays that hold the cells a rank owns, in work-item order -> device layout (the distributed upload) */
+__global__ void pack_cells_owned_kernel(int64_t n_owned, int32_t rank, int32_t size, const double *n, const double *T, const double *x,
+                                        CellOpacity *cells, double2 *cells_h, double *xmetal) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_owned) return;
+  const int64_t i = owned_cell(j, rank, size);
+  CellOpacity c;
+  c.n = n[j];
+  c.T = T[j];
+  c.xH = x[j];
+  c.xHe = x[n_owned + j];
+  cells[i] = c;
+  cells_h[i] = make_double2(c.n, c.xH);
+  for (int k = 0; k < 12; ++k) xmetal[i * 12 + k] = x[(2 + k) * n_owned + j];
+}
+
 /* host layout of the cells a rank owns, in work-item order (the distributed read-back of an iteration) */
 __global__ void unpack_cells_owned_kernel(int64_t n_owned, int32_t rank, int32_t size, const CellOpacity *cells, const double *xmetal,
                                           const double *heat_norm, double *n, double *T, double *x, double *heat) {

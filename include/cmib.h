@@ -308,6 +308,12 @@ uint64_t cmib_owned_cell_count(uint64_t ncells, int32_t size, int32_t rank);
 int cmib_comm_owned_cells(cmib_context *ctx, uint64_t *n_owned);
 int cmib_download_cells_owned(cmib_context *ctx, double *number_density, double *temperature, double *ionic_fractions,
                               double *heating);
+/* ... and the distributed upload: host arrays of the owned cells in the same order; cmib_comm_gather_owned_cells then
+ * replicates the opacity records (all a shoot reads) — the metal fractions stay with the owner, who is the one that
+ * updates them: every rank moves 1/size of the bytes and the gather carries 32 of the 128 bytes per cell */
+int cmib_upload_cells_owned(cmib_context *ctx, const double *number_density, const double *temperature,
+                            const double *ionic_fractions);
+int cmib_comm_gather_owned_cells(cmib_context *ctx);
 
 /* ---- measured ceilings of the part (roofline denominators) --------------- */
 /* Scattered FP64 RED/s and scattered 16-byte gathers/s of THIS device on tables of `n_cells` records

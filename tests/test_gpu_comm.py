@@ -88,6 +88,12 @@ _, _, _, h2 = team.ctx.download_cells()
 team.ctx.download_cells_owned_into(on, oT, ox, oh)
 assert np.array_equal(oT, T2[own]) and np.array_equal(on, n2[own]) and np.array_equal(np.nan_to_num(ox), np.nan_to_num(x2[:, own]))
 assert np.array_equal(oh, h2[:, own]), 'owned download'
+# ... and the distributed upload: every rank uploads the cells it owns, the opacity records are gathered
+team.ctx.upload_cells_owned(on, oT + 2., ox)
+team.ctx.comm_gather_owned_cells()
+n3, T3, x3, _ = team.ctx.download_cells()
+assert np.array_equal(T3, T2 + 2.) and np.array_equal(n3, n2) and np.array_equal(np.nan_to_num(x3[:2]), np.nan_to_num(x2[:2])), 'owned upload + gather'
+assert np.array_equal(np.nan_to_num(x3[2:, own]), np.nan_to_num(x2[2:, own]))
 team.ctx.comm_finalize()
 dist.barrier()
 if rank == 0:
