@@ -292,9 +292,15 @@ CMIB_D void reduce_counters(double *acc, const ShootCounters &cnt) {
  * into the emission queue so that the expensive, uniform part of an emission (direction, 14 cross
  * sections, optical depth) runs on full warps in prepare_kernel.  (With both in one kernel the
  * mixed rounds ran at 10 active threads per instruction, profiles/r01_prepare.md.) */
+#ifndef CMIB_PREP_BLOCKS
+#define CMIB_PREP_BLOCKS 4
+#endif
+#ifndef CMIB_DECIDE_BLOCKS
+#define CMIB_DECIDE_BLOCKS 4 /* 64 registers, no spills: emission kernels of a lexingtonHII20 step 21.45 -> 20.77 ms against 3 CTAs (80 registers); 5 CTAs (48 registers, spills): 22.2 ms */
+#endif
 enum EmitField : int { EQ_PX = 0, EQ_PY, EQ_PZ, EQ_NU, EQ_ID, EQ_META, EQ_NFIELDS };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CMIB_DECIDE_BLOCKS)
 reemit_decide_kernel(const __grid_constant__ WavefrontParams W) {
   const ShootParams &P = W.sp;
   const SourceModel &m = P.src;
@@ -441,9 +447,10 @@ tail_kernel(const __grid_constant__ WavefrontParams W) {
  * (PhotonSource.hpp:141-148), evaluate the 14 cross sections (set_cross_sections, :189-199) and the
  * optical depth tau = -ln u (IonizationPhotonShootJob.hpp:135). */
 template <int MODE>
-__global__ void __launch_bounds__(256, 3) /* 3 CTAs per SM: without the bound the rarely taken continuous-source
-                                           * branches of emit_primary push it to 104 registers (2 CTAs, +2 ms per
-                                           * lexingtonHII20 step) */
+__global__ void __launch_bounds__(256, CMIB_PREP_BLOCKS) /* 4 CTAs per SM (64 registers, 36 bytes of spills).  Without a bound
+                                                          * the rarely taken continuous-source branches of emit_primary push
+                                                          * it to 104 registers (2 CTAs, +2 ms per lexingtonHII20 step); 3
+                                                          * CTAs (80 registers): emission kernels 20.77 ms per step, 4: 20.3 */
 prepare_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   const ShootParams &P = W.sp;
