@@ -45,6 +45,14 @@ def random_stream(seed, n):
     return out
 
 
+def test_rendezvous(nthreads, rounds, failing_thread=-1, failing_round=-1):
+    """per iteration: 1 = every device thread saw success, 0 = every thread saw the failure, -1 = they disagree"""
+    out = np.zeros(rounds, dtype=np.int32)
+    _check(lib.cmih_test_rendezvous(C.c_int(nthreads), C.c_int(rounds), C.c_int(failing_thread), C.c_int(failing_round),
+                                    out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def sph_mapping(paramfile, mapping_type, x, y, z, h, m, ncell, xH_cells, box=None):
     """(number density per cell, neutral fraction per particle) of the host layer's SPHArrayInterface: the
     device-free half of the cmi_* C ABI (host/SPHArrayInterface.hpp)"""

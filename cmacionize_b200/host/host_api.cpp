@@ -374,6 +374,28 @@ int cmih_random_stream(int32_t seed, int64_t n, double *out) {
     for (int64_t i = 0; i < n; ++i) out[i] = rg.get_uniform_random_double();
   });
 }
+/* test hook for the multi-GPU driver's failure handling (IonizationSimulation.hpp Rendezvous): `nthreads` threads go
+ * through `rounds` iterations; thread `failing_thread` reports a failure in iteration `failing_round` (-1: nobody fails).
+ * out[round] = 1 if every thread saw the round succeed, 0 if every thread saw it fail, -1 if they disagree.  Returns
+ * (does not hang) in every case. */
+int cmih_test_rendezvous(int nthreads, int rounds, int failing_thread, int failing_round, int *out) {
+  CMIH_TRY({
+    Rendezvous rv(nthreads);
+    std::vector<std::vector<int>> seen(nthreads, std::vector<int>(rounds, -1));
+    for (int r = 0; r < rounds; ++r) { /* as the driver does it: reset, one thread per device, join */
+      rv.reset();
+      std::vector<std::thread> threads;
+      for (int t = 0; t < nthreads; ++t)
+        threads.emplace_back([&, t, r]() { seen[t][r] = rv.arrive(!(t == failing_thread && r == failing_round)) ? 1 : 0; });
+      for (auto &th : threads) th.join();
+    }
+    for (int r = 0; r < rounds; ++r) {
+      out[r] = seen[0][r];
+      for (int t = 1; t < nthreads; ++t)
+        if (seen[t][r] != seen[0][r]) out[r] = -1;
+    }
+  });
+}
 /* the parameter file's PhotonSourceDistribution: info = {number of sources, total luminosity};
  * positions[capacity][3], weights[capacity] */
 int cmih_photon_source_distribution(void *h, double *info, double *positions, double *weights, int capacity) {

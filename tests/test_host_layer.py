@@ -457,6 +457,17 @@ def test_planck_sampler_and_masked_spectrum_bitexact(host, ref, tmp_path):
     assert s["cdf"][-1] == 1. and (np.diff(s["cdf"]) >= 0).all()
 
 
+def test_multi_gpu_driver_threads_agree_on_a_failure(host):
+    """The device threads of a multi-GPU iteration meet in a rendezvous before they enter the collective
+    (IonizationSimulation.hpp): when one of them failed, ALL of them must learn it and skip the NCCL call (a rank that
+    entered it alone would wait forever), and the next iteration starts clean."""
+    for nthreads in (2, 3, 8):
+        assert (host.test_rendezvous(nthreads, 4) == 1).all()
+        for bad in (0, nthreads - 1):
+            out = host.test_rendezvous(nthreads, 5, failing_thread=bad, failing_round=2)
+            assert out.tolist() == [1, 1, 0, 1, 1], (nthreads, bad, out)
+
+
 def test_malformed_parameter_files_end_in_errors_not_crashes(host, tmp_path):
     """A parameter file with broken indentation or stray characters is reported (the reference aborts with
     "Line has a different indentation than expected" / "no ':' found"); it must never take the process down:
