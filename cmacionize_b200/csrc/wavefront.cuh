@@ -17,7 +17,8 @@
  *                    packets); packets absorbed inside the box are appended to the
  *                    re-emission queue with one warp-aggregated atomic.
  *   fold_hot_cells_kernel  adds the replicated accumulators of the cells around the sources.
- *   sort_*_kernel    optional coherence sort of the march queue (off: measured slower).
+ *   sort_*_kernel    counting sort of the march queue for the coherent march (grids that do not fit in L2).
+ *   tail_kernel      the last generations of re-emitted packets in one launch (packet_walks of shoot.cuh).
  *
  * Why: in a one-thread-per-packet kernel (shoot_kernel, kept as the A/B check)
  * ncu showed 3.9 active threads per warp instruction: lanes sit in different

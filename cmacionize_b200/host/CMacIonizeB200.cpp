@@ -7,7 +7,7 @@
  *                    [--output-statistics] [--dry-run] [--verbose] [--task-based]
  *
  * --threads is accepted for command-line compatibility and ignored.  --gpus G uses devices
- * D .. D+G-1 of this node (packets split by global id; accumulators reduced onto cell-block owners, block update, gather: include/cmib.h cmib_comm_*).  --task-based
+ * D .. D+G-1 of this node (packets split by global id; accumulators all-reduced, update of the owned cell chunks, gather of the opacity records: include/cmib.h cmib_comm_*).  --task-based
  * (:304-338) reads the `TaskBasedIonizationSimulation:` parameter block instead of `IonizationSimulation:`
  * (host/IonizationSimulation.hpp) and runs the same GPU path.  Other modes of the reference (--rhd,
  * --dusty-radiative-transfer, --emission, --task-based-rhd) are outside the accelerated path and are rejected

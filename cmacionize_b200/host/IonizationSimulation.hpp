@@ -81,8 +81,8 @@ public:
    * list of devices of this node.  With more than one device the iteration follows the reference's MPI
    * decomposition (IonizationSimulation.cpp:392-397, 458-618) with the collectives of include/cmib.h
    * (cmib_comm_*: NCCL on each context's stream): packets split by global id (MPICommunicator::distribute),
-   * every device holds the whole grid, the accumulators are summed onto the owners of the cell blocks
-   * (distribute_block), every device updates its block, and the opacity records are gathered back. */
+   * every device holds the whole grid, the accumulators are all-reduced, every device updates the cell chunks it owns
+   * (cmib_owned_cell), and the opacity records are gathered back. */
   /* task_based = true: the parameter surface of the reference's other driver (`CMacIonize --task-based`,
    * TaskBasedIonizationSimulation.cpp:190-370) on the same GPU path: Monte Carlo parameters come from the
    * `TaskBasedIonizationSimulation:` block (number of iterations 10, number of photons 1e6, random seed,
@@ -348,7 +348,7 @@ public:
       if (rendezvous_ && !rendezvous_->arrive(ok)) return;
       if (!ok) return;
       try {
-        /* reduce the accumulators onto the block owners, update the own block, gather the opacity records;
+        /* all-reduce the accumulators, update the owned cell chunks, all-gather the opacity records;
          * totweight is the reduced device-side sum */
         CMIB_CALL(cmib_comm_exchange_and_update(ctx, loop, 0));
         CMIB_CALL(cmib_synchronize(ctx));

@@ -101,7 +101,7 @@ int cmih_simulation_context(void *h, cmib_context **ctx) {
 int cmih_simulation_context_of(void *h, int device_index, cmib_context **ctx) {
   CMIH_TRY(*ctx = static_cast<Sim *>(h)->sim.get_density_grid((size_t)device_index).context());
 }
-/* multi-GPU: bring the per-cell state that stays with the cell-block owners (metal fractions, heating terms) to
+/* multi-GPU: bring the per-cell state that stays with the owners of the cell chunks (metal fractions, heating terms) to
  * every device, before the cells of any device are downloaded */
 int cmih_simulation_gather_state(void *h) { CMIH_TRY(static_cast<Sim *>(h)->sim.gather_state()); }
 

@@ -201,8 +201,8 @@ IonizationSimulation:
 
 
 def test_two_gpu_driver_equals_one_gpu(host, tmp_path):
-    """C++ driver on 2 GPUs (packets split by global id, accumulators reduced onto the owners of the cell
-    blocks, block-wise state update, opacity records gathered: include/cmib.h cmib_comm_*) == the same
+    """C++ driver on 2 GPUs (packets split by global id, accumulators all-reduced, state update of the owned
+    cell chunks, opacity records gathered: include/cmib.h cmib_comm_*) == the same
     parameter file on 1 GPU: same packets, sums equal up to order."""
     ngpu = len([l for l in subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout.splitlines()
                 if l.startswith("GPU ")])

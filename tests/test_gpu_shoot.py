@@ -176,9 +176,9 @@ def test_wavefront_pipeline_equals_the_per_packet_kernel(cmib, config):
     one-thread-per-packet kernel run the same shoot_packet logic on the same per-packet random
     streams: identical counters (packets by type, cell crossings, (re-)emissions) and
     accumulators equal up to the order of the atomic adds.  Small queue capacities force many
-    rounds, chunk boundaries and partially filled warps; the coherence sorts (1: coarse counting
-    sort, 2: the coherent march = fine radix sort + in-warp sums of same-cell terms, the default)
-    only change which packets run together and in which order their terms are added."""
+    rounds, chunk boundaries and partially filled warps; the queue orders (1: ordered queue read by the
+    plain kernel, 2: the coherent march = counting sort by (source | direction | depth) + in-warp sums of
+    same-cell terms), two lanes and the round-by-round tail only change which packets run together and in which order their terms are added."""
     import os
     from cmacionize_b200 import problems, capi
     npk = 60000
