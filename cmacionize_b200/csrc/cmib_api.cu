@@ -620,6 +620,8 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   if (const char *e = getenv("CMIB_LEAN_STEPS")) lean_steps = atoi(e) == 2 ? 2 : 3;
   const size_t lean_smem = lean_smem_bytes(P.geom);
   if (lean_smem > 200 * 1024) lean_cfg = 0; /* wall tables of > ~11000 cells per axis sum: the r01 kernel */
+  /* march_lean_kernel addresses accumulators (and the hot-cell replicas behind them) by a 32-bit index in doubles */
+  if (ctx->acc_doubles(mode) >= (size_t)0xffffffffu) lean_cfg = 0;
   /* a heat term exists unless every packet of the shoot sits exactly at the threshold: a monochromatic
    * source at nu_H without re-emission (then nu - nu_H == 0 and the r01 kernel skipped the add at run time) */
   const int lean_heat = !(P.src.spectrum.kind == SPECTRUM_MONOCHROMATIC && P.src.spectrum.mono_frequency == P.nu_H &&
@@ -905,6 +907,8 @@ int cmib_create(const cmib_grid_desc *grid, int device, cmib_context **out) {
     if (grid->ncell[d] <= 0) CMIB_FAIL("number of cells must be positive");
     if (!(grid->sides[d] > 0.)) CMIB_FAIL("box sides must be positive");
   }
+  if ((double)grid->ncell[0] * grid->ncell[1] * grid->ncell[2] >= 4294967296.)
+    CMIB_FAIL("grids of 2^32 cells or more are not supported (the walk carries 32-bit cell indices)");
   CUDA_OK(cudaSetDevice(device));
   cudaDeviceProp prop;
   CUDA_OK(cudaGetDeviceProperties(&prop, device));
