@@ -795,7 +795,7 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
    * this is a lower bound); one more round finds the queues empty and reports the end */
   auto rounds_for_primaries = [&](int l) -> int {
     uint64_t rem = lane_n[l], r = 0;
-    while (rem > 0 && r < 60) {
+    while (rem > 0 && r < 100000) {
       const uint64_t f = round_fill(l, r);
       rem -= std::min(rem, f);
       ++r;
@@ -834,7 +834,10 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
         CMIB_FAIL("the shoot did not finish in %llu rounds: packets are still queued (a re-emission probability of 1 "
                   "in a box that cannot be left?)", (unsigned long long)max_rounds);
       }
-      if (enqueue_group(l, group)) return 1;
+      /* without re-emission the rounds still needed are known (a shoot of more primaries than one group holds) */
+      const int left = rounds_for_primaries(l) - (int)std::min<uint64_t>(R.rounds, 1u << 20);
+      const int next = (!can_reemit && left > 0) ? std::min(left + 1, (int)CTL_STATUS_SLOTS - 1) : group;
+      if (enqueue_group(l, next)) return 1;
       inflight.push_back(l);
     }
   }

@@ -585,3 +585,32 @@ def test_task_based_packet_conventions(cmib):
     ok = np.isfinite(x0)
     assert np.array_equal(ok, np.isfinite(x1))
     assert np.abs(x1[ok] - x0[ok]).max() <= 1e-10               # ionization-only update: J / A * A to rounding
+
+
+def test_shoot_of_more_rounds_than_one_group_of_rounds(cmib):
+    """A shoot whose primaries need more rounds than the host enqueues in one group (63): 300 rounds of 1024 packets
+    without re-emission, and the same with re-emission (groups of 4 kept ahead of the read-back), against one round."""
+    import os
+    from cmacionize_b200 import problems
+    npk = 300_000
+    for diffuse in (False, True):
+        prob = problems.stromgren(ncell=16, n_packets=npk, diffuse=diffuse)
+        ctx = prob.ctx
+        out = []
+        for cap in (None, 1024):
+            if cap is None:
+                os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+            else:
+                os.environ["CMIB_QUEUE_CAPACITY"] = str(cap)
+            try:
+                ctx.reset_accumulators()
+                ctx.update_reemission_probabilities()
+                tw, tc = ctx.shoot(npk, seed=3, iteration=1)
+            finally:
+                os.environ.pop("CMIB_QUEUE_CAPACITY", None)
+            J, heat = ctx.download_accumulators()
+            out.append((tw, tc.copy(), ctx.shoot_statistics(), J))
+        ctx.close()
+        (tw0, tc0, st0, J0), (tw1, tc1, st1, J1) = out
+        assert tw0 == tw1 == npk and np.array_equal(tc0, tc1) and st0 == st1
+        assert np.abs(J1[0] - J0[0]).max() <= 1e-12 * J0[0].max()
