@@ -50,12 +50,12 @@ def make_paramfile(tmp_path, name, seed):
     return pf
 
 
-@pytest.mark.parametrize("name,task_based", [(n, False) for n in CASES] + [("stromgren_diffuse", True), ("lexingtonHII20", True)])
+@pytest.mark.parametrize("name,task_based", [(n, False) for n in CASES] + [("stromgren_diffuse", True), ("lexingtonHII20", True), ("lexingtonHII40", True)])
 def test_benchmark_parameter_file(host, ref, tmp_path, name, task_based):  # noqa: F811
     """task_based: the same file through the `CMacIonize --task-based` parameter surface
     (TaskBasedIonizationSimulation: block, diffuse field switch) with that driver's packet conventions on the
     device (cmib_set_packet_conventions).  stromgren_diffuse (A_He = 0: the conventions cannot show) against the
-    IonizationSimulation runs; lexingtonHII20 (He + metals, temperature solve) against two runs of the reference's
+    IonizationSimulation runs; lexingtonHII20 / HII40 (He + metals, temperature solve) against two runs of the reference's
     own TaskBasedIonizationSimulation (oracle probe cmi_ref_run_paramfile_taskbased)."""
     case = CASES[name]
     nc = 64
