@@ -257,7 +257,7 @@ def config_of(name, n_packets, world, scaling="strong"):
                             "(MPICommunicator::distribute), replicated grid, accumulators all-reduced, "
                             "state update of the owned cell chunks, opacity records all-gathered (NCCL behind the C ABI)"),
             "l2_policy": ("cells + accumulators (41 MB) are L2 resident and re-zeroed / rewritten every iteration; each "
-                          "step streams 1e8 independent random rays (1.5 - 5 GB of packet queues per round: larger than L2)"
+                          "step streams 1e8 independent random rays (up to 21 GB of packet queues per round: larger than L2)"
                           if nc == 64 else
                           "cells + accumulators (0.5 - 2.7 GB) do not fit in L2; every step streams independent random rays")}
 

@@ -395,15 +395,17 @@ int set_spectrum_model(cmib_context *ctx, SpectrumModel &sp, std::vector<double>
   return 0;
 }
 
-/* packets per round of the wavefront pipeline.  Emission order: 16 Mi (5 GB of queues in the full layout; measured
- * 124 -> 117 ms per lexingtonHII20 step against 4 Mi).  Coherent march: what the sort key needs (shoot_wavefront) */
+/* packets per round of the wavefront pipeline.  Emission order: 64 Mi (21 GB of queues in the full layout, of 180 GB):
+ * every round ends in a tail in which the last long walks keep the whole machine waiting, so fewer, larger rounds win
+ * — lexingtonHII20, 1e8 packets: 4 Mi 124 ms (r01), 16 Mi 96.9 ms, 32 Mi 95.7, 64 Mi 95.2, 128 Mi 95.1.  Coherent
+ * march: what the sort key needs (shoot_wavefront). */
 uint64_t default_queue_capacity(bool coherent, uint64_t coherent_round) {
   const char *e = getenv("CMIB_QUEUE_CAPACITY");
   if (e) {
     const long long v = atoll(e);
     if (v >= 1024) return (uint64_t)v;
   }
-  return coherent ? coherent_round : (1ull << 24);
+  return coherent ? coherent_round : (1ull << 26);
 }
 
 /* measure of a union of intervals (sorted in place), and of the intersection of two such unions */
