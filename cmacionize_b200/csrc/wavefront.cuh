@@ -612,13 +612,18 @@ constexpr int AGG_GROUP = 8; /* lanes that are refilled together */
  * L2/DRAM latency overlaps the in-warp sums, the loop control and the wall distances of the next
  * pass instead of stalling the optical-depth arithmetic right behind the load.
  */
+#ifndef CMIB_PLAIN_BLOCKS
+#define CMIB_PLAIN_BLOCKS 3 /* resident CTAs per SM of the plain kernel (80 registers).  The walk is sensitive to both ends:
+                             * 2 CTAs (grid halved): lexingtonHII20 march 74.9 -> 95.9 ms; 4 CTAs (64 registers, 130 bytes of
+                             * spills in the full layout): 94.4 ms */
+#endif
 #ifndef CMIB_AGG_BLOCKS
 #define CMIB_AGG_BLOCKS 3 /* resident CTAs per SM the coherent variants are compiled for.  Measured with 2 (118
                            * registers, no spills): H-only 26.9 -> 32.2 ms on clumpy 256^3, full layout 117 -> 114 ms:
                            * the 24 warps per SM matter more than the spills */
 #endif
 template <int MODE, bool AGG, bool PRE>
-__global__ void __launch_bounds__(MARCH_BLOCK, (AGG ? CMIB_AGG_BLOCKS : 3))
+__global__ void __launch_bounds__(MARCH_BLOCK, (AGG ? CMIB_AGG_BLOCKS : CMIB_PLAIN_BLOCKS))
 march_kernel(const __grid_constant__ WavefrontParams W) {
   constexpr int NSIG = AccLayout<MODE>::NSIG;
   constexpr int NMETAL = (MODE == ACC_FULL) ? 12 : 0;
