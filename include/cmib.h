@@ -272,7 +272,8 @@ int cmib_comm_finalize(cmib_context *ctx);
 int cmib_comm_info(cmib_context *ctx, int32_t *rank, int32_t *size, uint64_t *cell_begin, uint64_t *cell_end);
 /* The exchange between cmib_shoot and the next iteration, as ONE call per rank (collective):
  *   1. the accumulators (and the 16 leading counters) are summed over the ranks: one ncclAllReduce, every rank
- *      receives all sums (`allreduce` is kept for source compatibility and ignored);
+ *      receives all sums (`allreduce` is kept for source compatibility and ignored); the heating plane of the H-only
+ *      layout is left out when nothing shot since cmib_reset_accumulators could add to it;
  *   2. cmib_update_state on the cells the rank OWNS (totweight from the reduced counters).  Ownership is dealt in
  *      chunks of 1024 cells, chunk c to rank c % size (cmib_owned_cell): the reference's contiguous blocks
  *      (distribute_block) put the whole ionised region — where the temperature solve iterates — on the middle
