@@ -212,7 +212,7 @@ struct cmib_context {
     size_t ev_used = 0;
   };
   Lane lane[2];
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, origin_ev = nullptr;
+  cudaEvent_t fork_ev = nullptr, origin_ev = nullptr;
   int shoot_lanes = 1;        /* lanes of the last shoot */
   double overlap_ms = 0.;     /* time of the last shoot during which an emission kernel ran beside a march kernel */
   DevBuf<uint32_t> d_src_cell;  /* packed cell indices of the sources */
@@ -232,7 +232,6 @@ struct cmib_context {
   int comm_rank = 0, comm_size = 1;
   cudaEvent_t xev[4] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf<double> xchg_pack, xchg_all; /* packs of the owned chunks: own, and of all ranks (gathers) */
-  double exchange_ms[3] = {0., 0., 0.};
   double walk_cells = 0.; /* mean walk length (cells) of the last large shoot: sizes the direction bins of the sort key */
   size_t l2_bytes = 0;
   int march_blocks_per_sm[2][2] = {{0, 0}, {0, 0}}; /* [layout][plain, coherent] */
@@ -515,7 +514,6 @@ int shoot_wavefront(cmib_context *ctx, const ShootParams &P) {
   }
   if (!ctx->fork_ev) {
     CUDA_OK(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    CUDA_OK(cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreate(&ctx->origin_ev));
     int occ[4] = {0, 0, 0, 0};
     CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], march_kernel<ACC_FULL, false, true>, MARCH_BLOCK, 0));
@@ -992,7 +990,7 @@ int cmib_destroy(cmib_context *ctx) {
       if (e) cudaEventDestroy(e);
     if (L.stream && L.stream != ctx->stream) cudaStreamDestroy(L.stream);
   }
-  for (cudaEvent_t e : {ctx->fork_ev, ctx->join_ev, ctx->origin_ev})
+  for (cudaEvent_t e : {ctx->fork_ev, ctx->origin_ev})
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->xev)
     if (e) cudaEventDestroy(e);
